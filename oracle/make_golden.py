@@ -1,0 +1,103 @@
+"""oracle/make_golden.py -- TEST INFRASTRUCTURE ONLY: (re)generate tests/golden/*.npz.
+
+Runs the UNMODIFIED reference (/root/reference/sphy.py, via oracle/run_reference.py + oracle/pcr_shim.py)
+on small seeded synthetic catchments and stores its per-step state maps, daily reported flux maps and
+the exact inputs it saw.  Must be run in the build container (needs /root/reference); the resulting
+fixtures travel to the GPU box.
+
+    python -m oracle.make_golden            # all cases
+    python -m oracle.make_golden c2_glac    # one case
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+
+from sphy_b200 import synth
+
+from .run_reference import run_reference
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+REPORT = ("TotRF", "TotETactF", "TotETref", "Infil", "wbal", "TotRootRF", "TotRootDF", "TotRootPF", "TotSubPF",
+          "TotCapRF", "TotBaseRF", "TotSnowRF", "TotGlacRF", "TotGlacMelt", "TotSnowMelt", "StorSnow", "QallRAtot")
+
+# wetter / shallower than the cfg defaults so that saturation, runoff, drainage, percolation, baseflow and the
+# ET cliff (ET.py:31) all occur inside a short run
+WET = dict(SubWater=470.0, RootDepthFlat=150.0, Pscale=2.5)
+WETK = dict(WET, RootKsat=12.0)          # rain often exceeds Ksat: the min(rain, Ksat, deficit) branches
+COLD = dict(WETK, Toffset=9.0)
+GLAC = dict(WETK, Toffset=15.0)
+
+# name -> (make_catchment kwargs, nsteps)
+CASES = {
+    # BASELINE config 1: rootzone+subzone+groundwater+routing, snow/glacier off
+    "c1_base": (dict(nrows=12, ncols=10, seed=11, params=WET), 60),
+    # same with infiltration excess (the shipped cfg default) and all 7 routed components
+    "c1_infil_comp": (dict(nrows=12, ncols=10, seed=12, infil_excess=1, rout_components=True, params=WET), 60),
+    # groundwater module off: seepage + sub-drainage branch
+    "c1_noground": (dict(nrows=12, ncols=10, seed=13, ground=False, params=WET), 40),
+    # three soil classes: distributed soil parameters
+    "c1_soilcls": (dict(nrows=12, ncols=10, seed=14, soil_classes=3, params=WETK), 40),
+    # BASELINE config 2: snow on (spring melt season, snow line inside the catchment)
+    "c2_snow": (dict(nrows=12, ncols=10, seed=21, snow=True, params=COLD, start=(2001, 3, 15), zrange=(1500.0, 5200.0)), 90),
+    # BASELINE config 2: snow + glacier, all components routed
+    "c2_glac": (dict(nrows=12, ncols=10, seed=22, snow=True, glacier=True, rout_components=True, params=GLAC,
+                     start=(2001, 4, 15), zrange=(1500.0, 5200.0)), 90),
+    # BASELINE config 3: reservoirs (simple + advanced) and lakes
+    "c3_res_lake": (dict(nrows=16, ncols=14, seed=31, cellsize=1000.0, reservoirs=True, lakes=True, n_res_simple=2,
+                         n_res_adv=2, n_lakes=4, params=WET, start=(2001, 5, 1)), 70),
+    "c3_res_only": (dict(nrows=14, ncols=12, seed=32, cellsize=1000.0, reservoirs=True, n_res_simple=2, n_res_adv=1,
+                         params=WETK), 40),
+    "c3_lake_only": (dict(nrows=14, ncols=12, seed=33, cellsize=1000.0, lakes=True, n_lakes=4, params=WET), 40),
+}
+
+
+def build_case(name):
+    import datetime
+    kw, nsteps = CASES[name]
+    kw = dict(kw)
+    if "start" in kw:
+        kw["start"] = datetime.date(*kw["start"])
+    return synth.make_catchment(nsteps=nsteps, report_daily=REPORT, **kw), nsteps
+
+
+def make(name):
+    cat, nsteps = build_case(name)
+    ref = run_reference(cat, nsteps)
+    forcing = {k: np.stack([cat.forcing(t)[k] for t in range(1, nsteps + 1)]) for k in ("prec", "tavg", "tmin", "tmax")}
+    payload = {"meta": np.array(json.dumps(dict(case=name, nsteps=nsteps, kwargs=CASES[name][0])))}
+    for k, v in cat.static_maps().items():
+        payload["map/" + k] = v
+    for k, v in forcing.items():
+        payload["forcing/" + k] = v
+    for k, v in ref["states"].items():
+        payload["state/" + k] = v
+    for k, v in ref["reports"].items():
+        payload["report/" + k] = v
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    path = os.path.join(GOLDEN_DIR, name + ".npz")
+    np.savez_compressed(path, **payload)
+    # coverage summary: make sure the case exercises the branches it is meant to pin
+    st, rp = ref["states"], ref["reports"]
+    cov = {
+        "RootDrain>0": float((st["RootDrain"][1:] > 0).mean()),
+        "runoff>0": float((rp["RootR"] > 0).mean()) if "RootR" in rp else None,
+        "perc>0": float((rp["RootP"] > 0).mean()) if "RootP" in rp else None,
+        "subperc>0": float((rp["SubP"] > 0).mean()) if "SubP" in rp else None,
+        "BaseR>0": float((st["BaseR"][1:] > 0).mean()) if "BaseR" in st else None,
+        "ETa==0": float((rp["ETaF"] == 0).mean()) if "ETaF" in rp else None,
+        "Snow>0": float((st["SnowStore"][1:] > 0).mean()) if "SnowStore" in st else None,
+        "GlacMelt>0": float((rp["GMel"] > 0).mean()) if "GMel" in rp else None,
+        "StorRES range": [float(st["StorRES"][1:].max()), float(st["StorRES"][-1].max())] if "StorRES" in st else None,
+    }
+    print(name, os.path.getsize(path) // 1024, "KiB", {k: (round(v, 3) if isinstance(v, float) else v)
+                                                       for k, v in cov.items() if v is not None})
+
+
+if __name__ == "__main__":
+    for nm in (sys.argv[1:] or list(CASES)):
+        make(nm)

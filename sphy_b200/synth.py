@@ -1,0 +1,561 @@
+"""Synthetic catchments for tests and bench: DEM -> priority-flood LDD, soils, forcing,
+glacier table, reservoirs/lakes, plus a complete `sphy_config.cfg` + lookup tables + `reporting.csv`
+written in the reference's own formats (/root/reference/sphy_config.cfg), so the same case can be fed to
+the reference (through the oracle harness), to the oracle port and to the B200 SphyModel.
+
+Map names are the cfg values relative to `inputdir`, exactly as the reference concatenates them
+(`self.inpath + config.get(...)`, /root/reference/sphy.py:141-198).
+"""
+from __future__ import annotations
+
+import ctypes
+import datetime
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _build
+
+_HG = None
+
+
+def _hostgen():
+    global _HG
+    if _HG is None:
+        lib = ctypes.CDLL(_build.build_hostgen())
+        P = ctypes.c_void_p
+        lib.hostgen_flood_ldd.restype = ctypes.c_int
+        lib.hostgen_flood_ldd.argtypes = [P, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_int, P, P]
+        lib.hostgen_dem.restype = None
+        lib.hostgen_dem.argtypes = [P, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_float, ctypes.c_float]
+        lib.hostgen_nup.restype = ctypes.c_int
+        lib.hostgen_nup.argtypes = [P, ctypes.c_int, ctypes.c_int, P]
+        _HG = lib
+    return _HG
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def make_dem_ldd(nrows, ncols, cellsize, seed=1, outlets="single", zrange=None):
+    """Returns (dem_raw, dem_filled, ldd uint8, slope float32)."""
+    hg = _hostgen()
+    dem = np.empty((nrows, ncols), np.float32)
+    zmin, zmax = (zrange if zrange else (0.0, 0.0))
+    hg.hostgen_dem(_ptr(dem), nrows, ncols, seed, zmin, zmax)
+    raw = dem.copy()
+    ldd = np.empty((nrows, ncols), np.uint8)
+    slope = np.empty((nrows, ncols), np.float32)
+    mode = 1 if outlets == "single" else 0
+    rc = hg.hostgen_flood_ldd(_ptr(dem), nrows, ncols, float(cellsize), mode, nrows - 1, (ncols - 1) // 2,
+                              _ptr(ldd), _ptr(slope))
+    if rc != 0:
+        raise MemoryError("hostgen_flood_ldd failed")
+    return raw, dem, ldd, slope
+
+
+def upstream_counts(ldd):
+    hg = _hostgen()
+    ldd = np.ascontiguousarray(ldd, np.uint8)
+    nup = np.empty(ldd.shape, np.int32)
+    rc = hg.hostgen_nup(_ptr(ldd), ldd.shape[0], ldd.shape[1], _ptr(nup))
+    if rc != 0:
+        raise ValueError("LDD has a cycle")
+    return nup
+
+
+def _smooth_noise(rng, nrows, ncols, k=8):
+    """Bilinear up-sampling of a (k+1)x(k+1) N(0,1) lattice -> smooth field, float32."""
+    lat = rng.standard_normal((k + 1, k + 1))
+    r = np.linspace(0, k, nrows)
+    c = np.linspace(0, k, ncols)
+    r0 = np.minimum(r.astype(int), k - 1)
+    c0 = np.minimum(c.astype(int), k - 1)
+    tr = (r - r0)[:, None]
+    tc = (c - c0)[None, :]
+    a = lat[r0][:, c0]
+    b = lat[r0][:, c0 + 1]
+    d = lat[r0 + 1][:, c0]
+    e = lat[r0 + 1][:, c0 + 1]
+    return ((a * (1 - tc) + b * tc) * (1 - tr) + (d * (1 - tc) + e * tc) * tr).astype(np.float32)
+
+
+# cfg defaults of the reference (/root/reference/sphy_config.cfg:161-176,197-202,241-267,391-407,491)
+DEFAULT_PARAMS = dict(
+    RootFieldMap=0.30, RootSatMap=0.45, RootDryMap=0.08, RootWiltMap=0.15, RootKsat=50.0,
+    SubFieldMap=0.30, SubSatMap=0.45, SubKsat=20.0,
+    RootDepthFlat=400.0, SubDepthFlat=1600.0, CapRiseMax=0.571,
+    GwDepth=2000.0, GwSat=200.0, deltaGw=300.0, BaseThresh=0.0, alphaGw=0.508, YieldGw=0.05,
+    GwRecharge=0.0, BaseR=0.0, Gw=100.0, H_gw=3.0,
+    SubWater=10.0, CapRise=0.0, RootDrain=0.0, SubDrain=0.0,
+    kx=0.971, Gsc=0.0820, Kc=1.0,
+    Tcrit=-0.52, SnowSC=0.196, DDFS=1.401, SnowF=0.274, SnowCth=5.0, SnowIni=0.0, SnowWatStore=0.0,
+    DDFG=4.0, DDFDG=4.0, GlacF=0.555,
+    Alpha=0.32, Labda_infil=1.65, K_eff=0.5,
+    Pcorr_fact=1.0, Tcorr_fact=0.0,
+    SeePage=0.5, GWL_base=2.0,
+    kcOpenWater=1.2,
+)
+
+
+@dataclass
+class Catchment:
+    nrows: int
+    ncols: int
+    cellsize: float
+    seed: int
+    dem: np.ndarray
+    ldd: np.ndarray
+    slope: np.ndarray
+    lat: np.ndarray
+    flags: dict
+    params: dict
+    start: datetime.date
+    nsteps: int
+    locations: np.ndarray
+    soil_maps: dict
+    rout_components: bool = False
+    infil_excess: int = 0
+    glac_table: dict | None = None       # column name -> ndarray (U_ID, MOD_ID, GLAC_ID, MOD_H, GLAC_H, DEBRIS, FRAC_GLAC, ICE_DEPTH)
+    model_id: np.ndarray | None = None
+    glac_id: np.ndarray | None = None
+    tlapse: np.ndarray | None = None     # 12 monthly lapse rates
+    res_id: np.ndarray | None = None
+    lake_id: np.ndarray | None = None
+    res_tables: dict = field(default_factory=dict)   # file name -> 2-D list (matrix table incl. header row)
+    lake_tables: dict = field(default_factory=dict)
+    open_water_frac: np.ndarray | None = None
+    report_daily: tuple = ()
+
+    # ------------------------------------------------------------------------------------------
+    @property
+    def ncell(self):
+        return self.nrows * self.ncols
+
+    def forcing(self, day):
+        """Day `day` (1-based model time step) -> dict of float32 rasters prec, tavg, tmin, tmax."""
+        rng = np.random.default_rng([self.seed + 2, int(day)])
+        doy = (self.start + datetime.timedelta(days=int(day) - 1)).timetuple().tm_yday
+        z = self.dem
+        season = 10.0 * np.sin(2.0 * np.pi * (doy - 105) / 365.0)
+        tavg = (12.0 + self.params.get("Toffset", 0.0) - 6.5e-3 * (z - 1000.0) + season + 2.0 * rng.standard_normal()
+                + 1.0 * _smooth_noise(rng, self.nrows, self.ncols)).astype(np.float32)
+        tmax = (tavg + np.float32(5.0) + (2.0 * rng.random((self.nrows, self.ncols))).astype(np.float32)).astype(np.float32)
+        tmin = (tavg - np.float32(5.0) - (2.0 * rng.random((self.nrows, self.ncols))).astype(np.float32)).astype(np.float32)
+        wet = rng.random() < 0.35
+        if wet:
+            base = rng.gamma(0.8, 12.0)
+            mult = np.maximum(0.0, 1.0 + 0.3 * rng.standard_normal((self.nrows, self.ncols)))
+            prec = (self.params.get("Pscale", 1.0) * base * mult).astype(np.float32)
+        else:
+            rng.gamma(0.8, 12.0)
+            prec = np.zeros((self.nrows, self.ncols), np.float32)
+        return dict(prec=prec, tavg=tavg, tmin=tmin, tmax=tmax)
+
+    # ------------------------------------------------------------------------------------------
+    def static_maps(self):
+        """name (relative to inputdir) -> ndarray; dtype decides the PCRaster value scale
+        (bool -> boolean, uint8 -> ldd, int32 -> nominal, float32 -> scalar)."""
+        m = {
+            "clone.map": np.ones((self.nrows, self.ncols), np.bool_),
+            "dem.map": self.dem.astype(np.float32),
+            "slope.map": self.slope.astype(np.float32),
+            "stations.map": self.locations.astype(np.int32),
+            "ldd.map": self.ldd.astype(np.uint8),
+            "latitude.map": self.lat.astype(np.float32),
+            "landuse.map": np.ones((self.nrows, self.ncols), np.int32),
+        }
+        for k, v in self.soil_maps.items():
+            m[_SOIL_FILES[k]] = v.astype(np.float32)
+        if self.model_id is not None:
+            m["MOD_ID.map"] = self.model_id.astype(np.int32)
+            m["GLAC_ID.map"] = self.glac_id.astype(np.int32)
+        if self.res_id is not None:
+            m["res_id.map"] = self.res_id.astype(np.int32)
+        if self.lake_id is not None:
+            m["lake_id.map"] = self.lake_id.astype(np.int32)
+        if self.open_water_frac is not None:
+            m["openwater_frac.map"] = self.open_water_frac.astype(np.float32)
+        return m
+
+    def forcing_map_names(self, day):
+        tag = _name_t(day)
+        return {"prec": "forcings/prec" + tag, "tavg": "forcings/tavg" + tag, "tmin": "forcings/tmin" + tag,
+                "tmax": "forcings/tmax" + tag}
+
+    # ------------------------------------------------------------------------------------------
+    def write_inputs(self, inputdir, outputdir=None):
+        """Write sphy_config.cfg, reporting.csv and lookup tables under `inputdir`; return cfg path."""
+        os.makedirs(inputdir, exist_ok=True)
+        outputdir = outputdir or os.path.join(inputdir, "out")
+        os.makedirs(outputdir, exist_ok=True)
+        p, f = self.params, self.flags
+        end = self.start + datetime.timedelta(days=self.nsteps - 1)
+        with open(os.path.join(inputdir, "kc.tbl"), "w") as fh:
+            fh.write(f"1 {p['Kc']}\n")
+        with open(os.path.join(inputdir, "paved.tbl"), "w") as fh:
+            fh.write("1 0.0\n")
+        with open(os.path.join(inputdir, "reporting.csv"), "w") as fh:
+            fh.write("name,map,avg,timeseries,filename,comment\n")
+            for name, fname in _REPORT_VARS:
+                mode = "D" if name in self.report_daily else "NONE"
+                fh.write(f"{name},{mode},NONE,NONE,{fname},synthetic\n")
+        if self.glac_table is not None:
+            cols = ["U_ID", "MOD_ID", "GLAC_ID", "MOD_H", "GLAC_H", "DEBRIS", "FRAC_GLAC", "ICE_DEPTH"]
+            with open(os.path.join(inputdir, "glaciers.csv"), "w") as fh:
+                fh.write(",".join(cols) + "\n")
+                n = len(self.glac_table["U_ID"])
+                for i in range(n):
+                    fh.write(",".join(repr(float(self.glac_table[c][i])) if c in ("MOD_H", "GLAC_H", "FRAC_GLAC", "ICE_DEPTH")
+                                      else str(int(self.glac_table[c][i])) for c in cols) + "\n")
+            with open(os.path.join(inputdir, "tlapse.tbl"), "w") as fh:
+                for mth in range(12):
+                    fh.write(f"{mth + 1} {float(self.tlapse[mth])!r}\n")
+        for name, rows in list(self.res_tables.items()) + list(self.lake_tables.items()):
+            with open(os.path.join(inputdir, name), "w") as fh:
+                for row in rows:
+                    fh.write(" ".join(repr(float(v)) for v in row) + "\n")
+
+        rout_init = "QRA_init = 0\n"
+        if self.rout_components:
+            rout_init += "".join(f"{c}RA_init = 0\n" for c in ("RootR", "RootD", "Rain", "Snow", "Glac", "Base"))
+        ground = f["GroundFLAG"] == 1 or f["GlacFLAG"] == 1
+        cfg = f"""[MODULES]
+GlacFLAG = {f['GlacFLAG']}
+SnowFLAG = {f['SnowFLAG']}
+RoutFLAG = {f['RoutFLAG']}
+LakeFLAG = {f['LakeFLAG']}
+ResFLAG = {f['ResFLAG']}
+DynVegFLAG = 0
+GroundFLAG = {f['GroundFLAG']}
+SedFLAG = 0
+SedTransFLAG = 0
+[DIRS]
+inputdir = {inputdir.rstrip('/')}/
+outputdir = {outputdir.rstrip('/')}/
+[TIMING]
+startyear_timestep1 = {self.start.year}
+startmonth_timestep1 = {self.start.month}
+startday_timestep1 = {self.start.day}
+startyear = {self.start.year}
+startmonth = {self.start.month}
+startday = {self.start.day}
+endyear = {end.year}
+endmonth = {end.month}
+endday = {end.day}
+spinupyears = 0
+[GENERAL]
+mask = clone.map
+dem = dem.map
+Slope = slope.map
+locations = stations.map
+[SOIL]
+RootFieldMap = root_field.map
+RootSatMap = root_sat.map
+RootDryMap = root_dry.map
+RootWiltMap = root_wilt.map
+RootKsat = root_ksat.map
+SubFieldMap = sub_field.map
+SubSatMap = sub_sat.map
+SubKsat = sub_ksat.map
+[PEDOTRANSFER]
+PedotransferFLAG = 0
+[SOIL_INIT]
+RootWater =
+SubWater = {p['SubWater']}
+CapRise = {p['CapRise']}
+RootDrain = {p['RootDrain']}
+SubDrain = {p['SubDrain']}
+[SOIL_CAL]
+RootFieldFrac = 1
+RootSatFrac = 1
+RootDryFrac = 1
+RootWiltFrac = 1
+RootKsatFrac = 1
+[SOILPARS]
+RootDepthFlat = {p['RootDepthFlat']}
+SubDepthFlat = {p['SubDepthFlat']}
+CapRiseMax = {p['CapRiseMax']}
+SeepStatic = 1
+SeePage = {p['SeePage']}
+GWL_base = {p['GWL_base']}
+[INFILTRATION]
+Infil_excess = {self.infil_excess}
+Alpha = {p['Alpha']}
+Labda_infil = {p['Labda_infil']}
+K_eff = {p['K_eff']}
+PavedFrac = paved.tbl
+[GROUNDW_PARS]
+GwDepth = {p['GwDepth']}
+GwSat = {p['GwSat']}
+deltaGw = {p['deltaGw']}
+BaseThresh = {p['BaseThresh']}
+alphaGw = {p['alphaGw']}
+YieldGw = {p['YieldGw']}
+[GROUNDW_INIT]
+GwRecharge = {p['GwRecharge']}
+BaseR = {p['BaseR']}
+Gw = {p['Gw']}
+H_gw = {p['H_gw']}
+[LANDUSE]
+LandUse = landuse.map
+KCstatic = 1
+CropFac = kc.tbl
+KC =
+[PWS]
+PWS_FLAG = 0
+PFactor = depletion.tbl
+[OPENWATER]
+ETOpenWaterFLAG = {1 if self.open_water_frac is not None else 0}
+kcOpenWater = {p['kcOpenWater']}
+openWaterFrac = openwater_frac.map
+[GLACIER]
+GlacTable = glaciers.csv
+ModelID = MOD_ID.map
+GlacID = GLAC_ID.map
+DDFG = {p['DDFG']}
+DDFDG = {p['DDFDG']}
+GlacF = {p['GlacF']}
+GlacID_flag = 0
+GlacVars = FRAC_GLAC,GlacMelt
+GlacRetreat = 0
+GlacID_memerror = 1
+GlacUpdate = 30,9
+TLapse = tlapse.tbl
+[SNOW]
+TCrit = {p['Tcrit']}
+SnowSC = {p['SnowSC']}
+DDFS = {p['DDFS']}
+SnowF = {p['SnowF']}
+SnowCth = {p['SnowCth']}
+[SNOW_INIT]
+SnowIni = {p['SnowIni']}
+SnowWatStore = {p['SnowWatStore']}
+[CLIMATE]
+Prec = forcings/prec
+Pcorr_fact = {p['Pcorr_fact']}
+precNetcdfFLAG = 0
+Tair = forcings/tavg
+Tcorr_fact = {p['Tcorr_fact']}
+tempNetcdfFLAG = 0
+[ETREF]
+ETREF_FLAG = 0
+ETref = forcings/etref
+Lat = latitude.map
+Gsc = {p['Gsc']}
+Tmin = forcings/tmin
+TminNetcdfFLAG = 0
+Tmax = forcings/tmax
+TmaxNetcdfFLAG = 0
+[ROUTING]
+flowdir = ldd.map
+kx = {p['kx']}
+Rout_components = 1
+[ROUT_INIT]
+{rout_init}[LAKE]
+LakeId = lake_id.map
+LakeStor = lake_stor.tbl
+LakeFunc = lake_function.tbl
+LakeQH = lake_qh.tbl
+LakeSH = lake_sh.tbl
+LakeHS = lake_hs.tbl
+[RESERVOIR]
+ResId = res_id.map
+ResFuncStor = res_funcstor.tbl
+{'ResSimple = res_simple.tbl' if 'res_simple.tbl' in self.res_tables else ''}
+{'ResAdv = res_adv.tbl' if 'res_adv.tbl' in self.res_tables else ''}
+[REPORTING]
+RepTab = reporting.csv
+mm_rep_FLAG = 0
+QTOT_mm_FLAG = 0
+QSNOW_mm_FLAG = 0
+QROOTR_mm_FLAG = 0
+QROOTD_mm_FLAG = 0
+QRAIN_mm_FLAG = 0
+GMelt_mm_FLAG = 0
+QGLAC_mm_FLAG = 0
+QBASE_mm_FLAG = 0
+Prec_mm_FLAG = 0
+ETa_mm_FLAG = 0
+Seep_mm_FLAG = 0
+wbal_TSS_FLAG = 0
+Lake_wbal = 0
+Res_wbal = 0
+RepSnow_FLAG = 0
+RepRootR_FLAG = 0
+RepRootD_FLAG = 0
+RepRain_FLAG = 0
+RepGlac_FLAG = 0
+RepBase_FLAG = 0
+"""
+        del ground
+        path = os.path.join(inputdir, "sphy_config.cfg")
+        with open(path, "w") as fh:
+            fh.write(cfg)
+        return path
+
+
+_SOIL_FILES = dict(RootFieldMap="root_field.map", RootSatMap="root_sat.map", RootDryMap="root_dry.map",
+                   RootWiltMap="root_wilt.map", RootKsat="root_ksat.map", SubFieldMap="sub_field.map",
+                   SubSatMap="sub_sat.map", SubKsat="sub_ksat.map")
+
+# (reporting name, file prefix) pairs -- the names `reporting.reporting()` is called with on the hot path
+_REPORT_VARS = [
+    ("wbal", "wbal"), ("TotPrec", "Prec"), ("TotPrecF", "PrecF"), ("TotRain", "Rain"), ("TotRainF", "RainF"),
+    ("TotETref", "ETr"), ("TotETrefF", "ETrF"), ("TotETpot", "ETp"), ("TotETpotF", "ETpF"), ("TotETact", "ETa"),
+    ("TotETactF", "ETaF"), ("PlantStress", "PStr"), ("TotSnow", "Snow"), ("TotSnowF", "SnowF"),
+    ("TotSnowMelt", "SMel"), ("TotSnowMeltF", "SMelF"), ("TotGlacMelt", "GMel"), ("TotGlacR", "GlacR"),
+    ("TotGlacPerc", "GlacP"), ("TotGlacRF", "GlacRF"), ("TotRootRF", "RootR"), ("TotRootDF", "RootD"),
+    ("TotRootPF", "RootP"), ("TotSubDF", "SubD"), ("TotSubPF", "SubP"), ("TotCapRF", "CapR"),
+    ("TotSeepF", "SeepF"), ("TotGwRechargeF", "Rchg"), ("TotRainRF", "RainR"), ("TotSnowRF", "SnowR"),
+    ("TotBaseRF", "BaseR"), ("TotRF", "TotR"), ("Infil", "Infil"), ("StorRootW", "RootW"), ("StorSubW", "SubW"),
+    ("StorGroundW", "GrndW"), ("StorSnow", "SnowS"), ("StorSnowW", "SnowW"), ("SCover", "SCov"), ("GWL", "GWL"),
+    ("QallRAtot", "QAll"), ("RootRRAtot", "QRoR"), ("RootDRAtot", "QRoD"), ("RainRAtot", "QRain"),
+    ("SnowRAtot", "QSnow"), ("GlacRAtot", "QGlac"), ("BaseRAtot", "QBase"),
+]
+
+
+def _name_t(t):
+    """Suffix of PCRaster's stack naming for an <=4-letter prefix such as 'prec': prec0000.001."""
+    s = "prec" + "0" * (11 - 4 - len(str(t))) + str(t)
+    return (s[:8] + "." + s[8:])[4:]
+
+
+# ----------------------------------------------------------------------------------------------
+def make_catchment(nrows, ncols, cellsize=250.0, seed=1, nsteps=365, snow=False, glacier=False,
+                   reservoirs=False, lakes=False, ground=True, routing=True, infil_excess=0,
+                   rout_components=False, outlets="single", start=datetime.date(2001, 1, 1),
+                   n_res_simple=0, n_res_adv=0, n_lakes=0, open_water=False, params=None,
+                   report_daily=(), soil_classes=1, zrange=None):
+    """Build one of the BASELINE.json synthetic configurations."""
+    p = dict(DEFAULT_PARAMS)
+    if params:
+        p.update(params)
+    if zrange is None:
+        zrange = (1500.0, 6500.0) if (snow or glacier) else None
+    raw, filled, ldd, slope = make_dem_ldd(nrows, ncols, cellsize, seed=seed, outlets=outlets, zrange=zrange)
+    lat = np.repeat(np.linspace(27.0, 31.0, nrows, dtype=np.float32)[::-1, None], ncols, axis=1)
+    flags = dict(GlacFLAG=int(glacier), SnowFLAG=int(snow or glacier), RoutFLAG=int(routing),
+                 LakeFLAG=int(lakes), ResFLAG=int(reservoirs), GroundFLAG=int(ground or glacier))
+    rng = np.random.default_rng([seed, 77])
+    soil_maps = {}
+    cls = (rng.integers(0, soil_classes, size=(nrows, ncols)) if soil_classes > 1 else np.zeros((nrows, ncols), int))
+    scale = 1.0 + 0.05 * np.arange(soil_classes)
+    for k in _SOIL_FILES:
+        soil_maps[k] = (np.float32(p[k]) * scale[cls].astype(np.float32)).astype(np.float32)
+    nup = upstream_counts(ldd)
+    # stations: the outlet(s) with the largest upstream area + a few interior cells
+    locations = np.zeros((nrows, ncols), np.int32)
+    flat = np.argsort(nup.ravel())[::-1]
+    picks = [flat[0]]
+    for q in (0.999, 0.99, 0.9):
+        picks.append(flat[int((1 - q) * flat.size)])
+    for k, g in enumerate(dict.fromkeys(int(x) for x in picks)):
+        locations.ravel()[g] = k + 1
+    cat = Catchment(nrows=nrows, ncols=ncols, cellsize=float(cellsize), seed=seed, dem=raw, ldd=ldd, slope=slope,
+                    lat=lat, flags=flags, params=p, start=start, nsteps=nsteps, locations=locations,
+                    soil_maps=soil_maps, rout_components=rout_components, infil_excess=infil_excess,
+                    report_daily=tuple(report_daily))
+    if glacier:
+        _add_glaciers(cat, rng)
+    if reservoirs or lakes:
+        _add_reservoirs_lakes(cat, rng, nup, n_res_simple if reservoirs else 0, n_res_adv if reservoirs else 0,
+                              n_lakes if lakes else 0)
+        if open_water:
+            ow = np.zeros((nrows, ncols), np.float32)
+            sel = (cat.res_id > 0) if cat.res_id is not None else np.zeros((nrows, ncols), bool)
+            ow[sel] = 0.5
+            cat.open_water_frac = ow
+    return cat
+
+
+def _add_glaciers(cat, rng):
+    """Glacier fragments on cells above 5000 m: 1-3 fragments per cell."""
+    z = cat.dem
+    thresh = 5000.0 if z.max() > 5200.0 else np.quantile(z, 0.85)
+    cells = np.flatnonzero(z.ravel() > thresh)
+    cat.model_id = (np.arange(cat.ncell, dtype=np.int32) + 1).reshape(cat.nrows, cat.ncols)
+    glac_id = np.zeros(cat.ncell, np.int32)
+    cols = {k: [] for k in ("U_ID", "MOD_ID", "GLAC_ID", "MOD_H", "GLAC_H", "DEBRIS", "FRAC_GLAC", "ICE_DEPTH")}
+    uid = 1
+    for g in cells:
+        nfrag = int(rng.integers(1, 4))
+        gid = int(g // max(1, cat.ncols // 4) % 7 + 1)
+        glac_id[g] = gid
+        for _ in range(nfrag):
+            cols["U_ID"].append(uid)
+            uid += 1
+            cols["MOD_ID"].append(int(g) + 1)
+            cols["GLAC_ID"].append(gid)
+            cols["MOD_H"].append(float(z.ravel()[g]))
+            cols["GLAC_H"].append(float(z.ravel()[g] + rng.uniform(-200.0, 200.0)))
+            cols["DEBRIS"].append(int(rng.random() < 0.3))
+            cols["FRAC_GLAC"].append(float(rng.uniform(0.1, 0.5) / nfrag * 1.5))
+            cols["ICE_DEPTH"].append(float(rng.uniform(20.0, 150.0)))
+    # shuffle rows so the reference's sort_values("MOD_ID") (glacier.py:82) has work to do
+    perm = rng.permutation(len(cols["U_ID"]))
+    cat.glac_table = {k: np.asarray(v)[perm] for k, v in cols.items()}
+    cat.glac_id = glac_id.reshape(cat.nrows, cat.ncols)
+    cat.tlapse = np.full(12, -0.0065)
+
+
+def _add_reservoirs_lakes(cat, rng, nup, n_simple, n_adv, n_lakes):
+    ncell = cat.ncell
+    lo, hi = max(20, ncell // 4000), max(200, ncell // 40)
+    cand = np.flatnonzero((nup.ravel() >= lo) & (nup.ravel() <= hi) & (cat.ldd.ravel() != 5))
+    total = n_simple + n_adv + n_lakes
+    if cand.size < total:
+        raise ValueError("not enough candidate cells for reservoirs/lakes")
+    chosen = rng.choice(cand, size=total, replace=False)
+    area = cat.cellsize * cat.cellsize
+    res_id = np.zeros(ncell, np.int32)
+    lake_id = np.zeros(ncell, np.int32)
+    funcstor = [[0, 1, 2]]
+    simple = [[0, 1, 2, 3]]
+    adv = [[0, 1, 2, 3, 4, 5, 6]]
+    for k in range(n_simple + n_adv):
+        g = chosen[k]
+        rid = k + 1
+        res_id[g] = rid
+        inflow_mcm = nup.ravel()[g] * area * 0.002 / 1e6            # ~2 mm/day over the upstream area
+        smax = 40.0 * inflow_mcm
+        if k < n_simple:
+            funcstor.append([rid, 1, 0.5 * smax])
+            simple.append([rid, float(rng.uniform(0.02, 0.08)), 1.5, smax])
+        else:
+            funcstor.append([rid, 2, 0.6 * smax])
+            adv.append([rid, smax, 0.1 * smax, 3.0 * inflow_mcm, 0.8 * inflow_mcm, int(rng.integers(100, 200)),
+                        int(rng.integers(220, 300))])
+    if n_simple + n_adv:
+        cat.res_id = res_id.reshape(cat.nrows, cat.ncols)
+        cat.res_tables["res_funcstor.tbl"] = funcstor
+        if n_simple:
+            cat.res_tables["res_simple.tbl"] = simple
+        if n_adv:
+            cat.res_tables["res_adv.tbl"] = adv
+    if n_lakes:
+        stor = [[0, 1]]
+        func = [[0, 1, 2, 3]]
+        qh = [[0, 1, 2, 3, 4, 5, 6]]
+        sh = [[0, 1, 2, 3, 4, 5, 6]]
+        hs = [[0, 1, 2, 3, 4, 5, 6]]
+        for k in range(n_lakes):
+            g = chosen[n_simple + n_adv + k]
+            lid = k + 1
+            lake_id[g] = lid
+            inflow = nup.ravel()[g] * area * 0.002                   # m3/day
+            s0 = 60.0 * inflow                                       # m3, reference storage
+            ftype = k % 4 + 1
+            stor.append([lid, s0 / 1e6])
+            func.append([lid, ftype, ftype, ftype])
+            # h(S): level ~ 2 m at S0; Q(h) in m3/s ~ inflow at h = 2
+            qref = inflow / 86400.0
+            qh.append([lid, qref / np.exp(1.6), 0.8, 0.0, qref / 2.0, qref / 8.0, qref / 32.0])
+            sh.append([lid, s0 / np.exp(1.0), 0.5, 0.0, s0 / 2.0, s0 / 8.0, s0 / 32.0])
+            hs.append([lid, 2.0 / np.exp(0.5), 0.5 / s0, 1.0, 1.0 / s0, 0.2 / s0 ** 2, 0.05 / s0 ** 3])
+        cat.lake_id = lake_id.reshape(cat.nrows, cat.ncols)
+        cat.lake_tables = {"lake_stor.tbl": stor, "lake_function.tbl": func, "lake_qh.tbl": qh, "lake_sh.tbl": sh,
+                           "lake_hs.tbl": hs}
