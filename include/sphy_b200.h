@@ -1,0 +1,210 @@
+/*
+ * sphy_b200.h -- C ABI of the B200-native SPHY hot path (libsphy_b200.so, sm_100a only).
+ *
+ * The reference (FutureWater/SPHY v3.1) has no FFI: its operator boundary is the `pcr` namespace that
+ * every process module receives as an argument plus the initial()/dynamic() contract.  Each entry point
+ * below names the reference interface it replaces (file:line relative to /root/reference).
+ *
+ * Conventions
+ *   - returns 0 on success, a negative SPHY_E_* code otherwise; never throws, never exits;
+ *     sphy_last_error() gives the message of the last failure on that context.
+ *   - every data buffer is DEVICE memory owned by the caller (torch tensors on the Python side);
+ *     the context owns only its LDD structures and workspaces.
+ *   - calls are asynchronous on the passed cudaStream_t (void*); no hidden synchronisation and no
+ *     allocation after sphy_ldd_build() except where stated.
+ *   - one context per GPU, not thread-safe per context (the reference is single-threaded).
+ *   - all maps are float32 arrays over the N active cells in compact row-major order
+ *     (SURVEY.md Appendix C); "scalar-or-map" parameters mirror the reference's
+ *     `try readmap / except getfloat` idiom (e.g. modules/groundwater.py:51-57).
+ */
+#ifndef SPHY_B200_H
+#define SPHY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPHY_OK 0
+#define SPHY_E_INVALID (-1)   /* bad argument */
+#define SPHY_E_CUDA (-2)      /* CUDA runtime error */
+#define SPHY_E_CYCLE (-3)     /* unsound LDD (cycle) */
+#define SPHY_E_STATE (-4)     /* call order (e.g. routing before sphy_ldd_build) */
+#define SPHY_E_NOMEM (-5)
+
+typedef struct sphy_ctx sphy_ctx;
+
+/* scalar-or-map parameter: map != NULL -> per-cell values, else the broadcast scalar */
+typedef struct { const float *map; float value; } sphy_param;
+
+/* ---- context ------------------------------------------------------------------------------ */
+/* replaces pcr.setclone / the clone map (sphy.py:141-145); cellsize feeds pcr.cellarea() */
+int sphy_ctx_create(sphy_ctx **out, int device, int nrows, int ncols, float cellsize);
+void sphy_ctx_destroy(sphy_ctx *ctx);
+const char *sphy_last_error(const sphy_ctx *ctx);
+int sphy_sm_count(const sphy_ctx *ctx);
+/* sizeof() of the ABI structs, so foreign-language bindings can verify their layout without a GPU:
+ * 0 sphy_param, 1 sphy_wb_params, 2 sphy_wb_state, 3 sphy_wb_forcing, 4 sphy_wb_out, 5 sphy_glac_table,
+ * 6 sphy_glac_out, 7 sphy_reslake */
+size_t sphy_abi_sizeof(int which);
+
+/* ---- K3: LDD -> integer structures (once per run) ------------------------------------------
+ * replaces what pcr.accuflux/accufractionflux/upstream derive implicitly from the UINT1 LDD map read at
+ * modules/routing.py:34.  ldd_dev: nrows*ncols keypad codes (1-9, 5 = pit, anything else = MV);
+ * active_dev: optional nrows*ncols mask (clone, sphy.py:143).  Synchronises the stream (one-time build). */
+int sphy_ldd_build(sphy_ctx *ctx, const uint8_t *ldd_dev, const uint8_t *active_dev, void *stream);
+int64_t sphy_ncells(const sphy_ctx *ctx);
+int32_t sphy_nlevels(const sphy_ctx *ctx);
+/* copy one structure to a caller device buffer for bit-exact checks.  name / element type / count:
+ *   "cidx" i32 nrows*ncols | "down" i32 N | "indeg" u8 N | "level" i32 N | "order" i32 N |
+ *   "level_ptr" i32 L+1 | "don_ptr" i32 N+1 | "don_idx" i32 don_ptr[N] | "nup" i64 N */
+int sphy_ldd_export(sphy_ctx *ctx, const char *name, void *dst_dev, size_t dst_bytes, void *stream);
+
+/* raster <-> compact (readmap / report side of the boundary): out[k] = raster[cell k] and back */
+int sphy_gather_f32(sphy_ctx *ctx, const float *raster_dev, float *compact_dev, void *stream);
+int sphy_scatter_f32(sphy_ctx *ctx, const float *compact_dev, float *raster_dev, float fill, void *stream);
+/* TimeoutputTimeseries.sample (sphy.py:683-691): out[j] = map[cells[j]] */
+int sphy_sample(sphy_ctx *ctx, const float *map_dev, const int32_t *cells_dev, int n, float *out_dev, void *stream);
+
+/* ---- K1: fused vertical water balance of one daily step -------------------------------------
+ * replaces sphy.dynamic() sphy.py:732-1097 + 1114-1212, i.e. hargreaves.extrarad/Hargreaves
+ * (hargreaves.py:24-47), ET.ETpot/ETact/ks (ET.py:24-47), snow.dynamic (modules/snow.py:110-187),
+ * rootzone.RootRunoff/RootDrainage/RootPercolation/CalcFrac (rootzone.py:24-94), subzone.CapilRise/
+ * SubPercolation/SubDrainage (subzone.py:24-51) and groundwater.dynamic (modules/groundwater.py:90-125). */
+#define SPHY_WB_SNOW 1u          /* SnowFLAG (sphy.py:869) */
+#define SPHY_WB_GROUND 2u        /* GroundFLAG (sphy.py:1033,1080) */
+#define SPHY_WB_INFIL_EXCESS 4u  /* InfilFLAG == 1 (rootzone.py:26) */
+#define SPHY_WB_PWS 8u           /* PlantWaterStressFLAG (sphy.py:919) */
+#define SPHY_WB_ETREF_INPUT 16u  /* ETREF_FLAG == 1: forcing.etref is read instead of Hargreaves (sphy.py:814) */
+
+#define SPHY_RA_TABLE 0          /* Ra looked up by latitude class (lat_class u16 + per-day table) */
+#define SPHY_RA_CELL 1           /* Ra from per-cell sin/cos/tan(latitude) maps */
+
+typedef struct {
+    uint32_t flags;
+    int32_t ra_mode;
+    /* latitude: TABLE mode: class map + unique latitudes in degrees (the kernel forms Lat*REAL4(pi/180)) */
+    const uint16_t *lat_class;      /* N */
+    const float *lat_unique_deg;    /* n_lat_unique */
+    int32_t n_lat_unique;
+    /* CELL mode: REAL4(sin), REAL4(cos), REAL4(tan) of LatRad, each evaluated in double (sphy_map_unary) */
+    const float *sin_lat, *cos_lat, *tan_lat;
+    float k0;                       /* REAL4(((24*60)/pi)*Gsc), the Python-double prefix of hargreaves.py:32-33 */
+    float pcorr, tcorr;             /* Pcorr_fact (divides, sphy.py:757), Tcorr_fact */
+    /* soil (sphy.py:173-247); e_root = REAL4(exp(-1/RootTT)), e_sub = REAL4(exp(-1/SubTT)) */
+    sphy_param root_field, root_sat, root_dry, root_wilt, root_ksat, root_drainvel, e_root;
+    sphy_param sub_field, sub_sat, sub_drainvel, e_sub;
+    sphy_param caprise_max, kc, pmap /* PWS p-factor */, glac_frac /* NULL+0 when no glaciers */;
+    sphy_param open_water_frac;
+    float kc_open_water;            /* [OPENWATER] kcOpenWater (sphy.py:898) */
+    /* infiltration excess (sphy.py:439-458) */
+    float k_eff, alpha, alpha_sq /* REAL4(Alpha**2) */, labda_infil;
+    sphy_param paved_frac;
+    /* groundwater (modules/groundwater.py:51-57); e_delta = REAL4(exp(-1/deltaGw)), e_alpha = REAL4(exp(-alphaGw)),
+     * h_den = REAL4(800*YieldGw*alphaGw) */
+    sphy_param gw_sat, base_thresh, e_delta, e_alpha, h_den;
+    sphy_param seepage;             /* GroundFLAG == 0 (sphy.py:1004) */
+    /* snow (modules/snow.py:84-90) */
+    float tcrit, snow_sc, ddfs, snow_f, one_minus_snow_f;
+    float melt_cos[24];             /* REAL4(cos(3.1415*h/12)), h = 1..24 (snow.py:30) */
+} sphy_wb_params;
+
+typedef struct {                     /* in/out, updated in place (attribute names of the reference) */
+    float *RootWater, *SubWater, *CapRise, *RootDrain;
+    float *GwRecharge, *Gw, *BaseR, *H_gw;            /* GROUND */
+    float *SubDrain;                                  /* !GROUND */
+    float *SnowStore, *SnowWatStore, *TotalSnowStore; /* SNOW */
+    float *waterbalanceTot;                           /* optional accumulator (sphy.py:1192) */
+} sphy_wb_state;
+
+typedef struct {                     /* forcing maps of the day (sphy.py:755-809) */
+    const float *prec, *tavg, *tmin, *tmax, *etref;
+    /* glacier aggregates of the day from sphy_glac_step (NULL when GlacFLAG = 0) */
+    const float *TotalSnowStore_GLAC, *SnowR_GLAC, *GlacPerc, *GlacR;
+} sphy_wb_forcing;
+
+typedef struct {                     /* outputs; every pointer except TotR may be NULL */
+    float *TotR;                     /* sphy.py:1096 */
+    float *RootRR, *RootDR, *RainR, *SnowR;           /* component runoff (sphy.py:1067-1075, snow.py:183) */
+    float *ETref, *ETact, *ActETact, *Infil, *Rain, *RootPerc, *SubPerc, *wbal, *ETOpenWater;
+} sphy_wb_out;
+
+/* init-time derived maps, evaluated like the oracle (double on the REAL4 operand, REAL4 result):
+ *   EXP_NEG_INV: exp(-1/x) with -1/x a REAL4 division (rootzone.py:70, subzone.py:38, groundwater.py:27)
+ *   SIN/COS/TAN_DEG2RAD: f(x*REAL4(pi/180)) for the latitude map (hargreaves.py:26-37); EXP_NEG: exp(-x) */
+#define SPHY_UNARY_EXP_NEG_INV 0
+#define SPHY_UNARY_SIN_DEG 1
+#define SPHY_UNARY_COS_DEG 2
+#define SPHY_UNARY_TAN_DEG 3
+#define SPHY_UNARY_EXP_NEG 4
+int sphy_map_unary(sphy_ctx *ctx, int op, const float *in, float *out, int64_t count, void *stream);
+
+/* K1 alone does not need the LDD: declare the number of active cells directly */
+int sphy_set_ncells(sphy_ctx *ctx, int64_t n);
+
+int sphy_wb_step(sphy_ctx *ctx, const sphy_wb_params *p, const sphy_wb_state *s, const sphy_wb_forcing *f,
+                 const sphy_wb_out *o, int day_of_year, void *stream);
+
+/* ---- K2: glacier fragment table ------------------------------------------------------------
+ * replaces glacier.dynamic (modules/glacier.py:256-498): float64 per-fragment physics + groupby(MOD_ID).sum().
+ * Table columns are device float64 arrays of n_rows (rows sorted by MOD_ID); `cell` = compact cell of each row;
+ * `seg_ptr` (n_seg+1) delimits the rows of one model cell, `seg_cell` (n_seg) is that cell. */
+typedef struct {
+    int32_t n_rows, n_seg;
+    const int32_t *cell, *seg_ptr, *seg_cell;
+    const double *MOD_H, *GLAC_H, *FRAC_GLAC;
+    const uint8_t *DEBRIS;
+    double *Rain_GLAC, *Snow_GLAC;                     /* stale-value semantics (quirk Q7) */
+    double *SnowStore_GLAC, *SnowWatStore_GLAC, *TotalSnowStore_GLAC, *AccuGlacMelt;
+    double *GlacMelt, *GlacR, *GlacPerc, *SnowR_GLAC, *ActSnowMelt_GLAC, *GLAC_T;   /* per-row diagnostics */
+    double tcrit, ddfs, snow_sc, ddfg, ddfdg, glac_f, lapse;
+} sphy_glac_table;
+
+typedef struct {                     /* per-cell aggregates (REAL4, written only at glacier cells) */
+    float *Rain_GLAC, *Snow_GLAC, *ActSnowMelt_GLAC, *TotalSnowStore_GLAC, *SnowR_GLAC, *GlacMelt, *GlacR, *GlacPerc;
+} sphy_glac_out;
+
+int sphy_glac_step(sphy_ctx *ctx, const sphy_glac_table *t, const float *tavg, const float *prec, float tcorr,
+                   float pcorr, const sphy_glac_out *o, void *stream);
+
+/* ---- K4: flow routing ------------------------------------------------------------------------
+ * replaces routing.ROUT / routing.dynamic (modules/routing.py:25-29,70-116):
+ *   Q = (1-kx) * accuflux(ldd, q*0.001*cellarea/86400) + kx*Qold   for ncomp runoff maps sharing one sweep.
+ * runoff_mm[c]: N-cell map [mm/day]; q_state[c]: Qold in, Q out (N cells, compact order).
+ * method: SPHY_ROUTE_LEVELS = level-by-level sweep, per-cell REAL8 sum stored REAL4 (bit-exact with the
+ * oracle); SPHY_ROUTE_SCAN = subtree ranges over a DFS pre-order + float64 prefix sums. */
+#define SPHY_ROUTE_LEVELS 0
+#define SPHY_ROUTE_SCAN 1
+int sphy_route_step(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm, float *const *q_state, sphy_param kx,
+                    float one_minus_kx /* REAL4(1-kx) when kx is a scalar: Python-double subtraction, routing.py:28 */,
+                    int method, void *stream);
+/* plain pcr.accuflux(ldd, m) / pcr.catchmenttotal(m, ldd) (sphy.py:838, routing.py:27) and pcr.upstream */
+int sphy_accuflux(sphy_ctx *ctx, const float *material, const float *fraction /*nullable*/, float *flux, int method,
+                  void *stream);
+int sphy_upstream(sphy_ctx *ctx, const float *x, float *out, void *stream);
+
+/* ---- K5 + routing with lakes/reservoirs ------------------------------------------------------
+ * replaces advanced_routing.dynamic / ROUT (modules/advanced_routing.py:27-38,134-217), lakes.UpdateLakeHStore /
+ * QLake (modules/lakes.py:28-158, no measured levels) and reservoirs.QRes/QSimple/QAdv (modules/reservoirs.py:26-86).
+ * Structures are listed once (n_struct cells with QFRAC == 0); kind 1 = simple reservoir, 2 = advanced reservoir,
+ * 3 = lake.  par[k][j]: parameter k of structure j (see reslake.cu for the column layout). */
+#define SPHY_RL_NPAR 23
+typedef struct {
+    int32_t n_struct;
+    const int32_t *cell;             /* compact cell of each structure */
+    const int32_t *kind;
+    const float *par;                /* [SPHY_RL_NPAR][n_struct] */
+    const float *qfrac;              /* dense N-cell QFRAC map (0 at structures, 1 elsewhere; lakes.py:224) */
+    float *StorRES;                  /* [n_struct] in/out, m3 */
+    float *Qout, *Qin;               /* [n_struct] outputs of the step, m3/day */
+} sphy_reslake;
+
+int sphy_route_reslake_step(sphy_ctx *ctx, const sphy_reslake *rl, const float *totr_mm, float *q_state,
+                            sphy_param kx, float one_minus_kx, int day_of_year, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPHY_B200_H */

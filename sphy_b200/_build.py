@@ -39,16 +39,37 @@ def cuda_sources():
 
 
 def build_cuda(force=False, verbose=False):
+    """Compile every csrc/*.cu to an object (in parallel) and link libsphy_b200.so."""
+    from concurrent.futures import ThreadPoolExecutor
+
     srcs, deps = cuda_sources()
     if not force and _newer(CUDA_LIB, srcs + deps):
         return CUDA_LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libsphy_b200.so (no CPU fallback exists)")
-    cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC, "-o", CUDA_LIB] + srcs
+    objdir = os.path.join(PKG, "build")
+    os.makedirs(objdir, exist_ok=True)
+    cflags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        if not force and _newer(obj, [src] + deps):
+            return obj, ""
+        cmd = [nvcc] + cflags + (["-Xptxas=-v"] if verbose else []) + ["-I", INCLUDE, "-I", CSRC, "-c", "-o", obj, src]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed for %s:\n%s" % (src, r.stderr))
+        return obj, r.stderr
+
+    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        results = list(ex.map(compile_one, srcs))
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    subprocess.check_call(cmd)
+        for _, log in results:
+            if log:
+                print(log)
+    objs = [o for o, _ in results]
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", CUDA_LIB] + objs)
     return CUDA_LIB
 
 

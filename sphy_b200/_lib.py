@@ -1,0 +1,140 @@
+"""ctypes binding of libsphy_b200.so (the C ABI in include/sphy_b200.h).
+
+There is no fallback: if the CUDA library cannot be loaded, or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import _build
+
+P = C.c_void_p
+
+
+class SphyParam(C.Structure):
+    _fields_ = [("map", P), ("value", C.c_float)]
+
+
+class WbParams(C.Structure):
+    _fields_ = [
+        ("flags", C.c_uint32), ("ra_mode", C.c_int32),
+        ("lat_class", P), ("lat_unique_deg", P), ("n_lat_unique", C.c_int32),
+        ("sin_lat", P), ("cos_lat", P), ("tan_lat", P),
+        ("k0", C.c_float), ("pcorr", C.c_float), ("tcorr", C.c_float),
+        ("root_field", SphyParam), ("root_sat", SphyParam), ("root_dry", SphyParam), ("root_wilt", SphyParam),
+        ("root_ksat", SphyParam), ("root_drainvel", SphyParam), ("e_root", SphyParam),
+        ("sub_field", SphyParam), ("sub_sat", SphyParam), ("sub_drainvel", SphyParam), ("e_sub", SphyParam),
+        ("caprise_max", SphyParam), ("kc", SphyParam), ("pmap", SphyParam), ("glac_frac", SphyParam),
+        ("open_water_frac", SphyParam), ("kc_open_water", C.c_float),
+        ("k_eff", C.c_float), ("alpha", C.c_float), ("alpha_sq", C.c_float), ("labda_infil", C.c_float),
+        ("paved_frac", SphyParam),
+        ("gw_sat", SphyParam), ("base_thresh", SphyParam), ("e_delta", SphyParam), ("e_alpha", SphyParam),
+        ("h_den", SphyParam), ("seepage", SphyParam),
+        ("tcrit", C.c_float), ("snow_sc", C.c_float), ("ddfs", C.c_float), ("snow_f", C.c_float),
+        ("one_minus_snow_f", C.c_float), ("melt_cos", C.c_float * 24),
+    ]
+
+
+class WbState(C.Structure):
+    _fields_ = [(k, P) for k in ("RootWater", "SubWater", "CapRise", "RootDrain", "GwRecharge", "Gw", "BaseR", "H_gw",
+                                 "SubDrain", "SnowStore", "SnowWatStore", "TotalSnowStore", "waterbalanceTot")]
+
+
+class WbForcing(C.Structure):
+    _fields_ = [(k, P) for k in ("prec", "tavg", "tmin", "tmax", "etref", "TotalSnowStore_GLAC", "SnowR_GLAC",
+                                 "GlacPerc", "GlacR")]
+
+
+class WbOut(C.Structure):
+    _fields_ = [(k, P) for k in ("TotR", "RootRR", "RootDR", "RainR", "SnowR", "ETref", "ETact", "ActETact", "Infil",
+                                 "Rain", "RootPerc", "SubPerc", "wbal", "ETOpenWater")]
+
+
+class GlacTable(C.Structure):
+    _fields_ = ([("n_rows", C.c_int32), ("n_seg", C.c_int32), ("cell", P), ("seg_ptr", P), ("seg_cell", P),
+                 ("MOD_H", P), ("GLAC_H", P), ("FRAC_GLAC", P), ("DEBRIS", P), ("Rain_GLAC", P), ("Snow_GLAC", P),
+                 ("SnowStore_GLAC", P), ("SnowWatStore_GLAC", P), ("TotalSnowStore_GLAC", P), ("AccuGlacMelt", P),
+                 ("GlacMelt", P), ("GlacR", P), ("GlacPerc", P), ("SnowR_GLAC", P), ("ActSnowMelt_GLAC", P),
+                 ("GLAC_T", P)]
+                + [(k, C.c_double) for k in ("tcrit", "ddfs", "snow_sc", "ddfg", "ddfdg", "glac_f", "lapse")])
+
+
+class GlacOut(C.Structure):
+    _fields_ = [(k, P) for k in ("Rain_GLAC", "Snow_GLAC", "ActSnowMelt_GLAC", "TotalSnowStore_GLAC", "SnowR_GLAC",
+                                 "GlacMelt", "GlacR", "GlacPerc")]
+
+
+class ResLake(C.Structure):
+    _fields_ = [("n_struct", C.c_int32), ("cell", P), ("kind", P), ("par", P), ("qfrac", P), ("StorRES", P),
+                ("Qout", P), ("Qin", P)]
+
+
+RL_NPAR = 23
+WB_SNOW, WB_GROUND, WB_INFIL_EXCESS, WB_PWS, WB_ETREF_INPUT = 1, 2, 4, 8, 16
+RA_TABLE, RA_CELL = 0, 1
+ROUTE_LEVELS, ROUTE_SCAN = 0, 1
+UNARY_EXP_NEG_INV, UNARY_SIN_DEG, UNARY_COS_DEG, UNARY_TAN_DEG, UNARY_EXP_NEG = 0, 1, 2, 3, 4
+
+# every symbol include/sphy_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "sphy_ctx_create": (C.c_int, [C.POINTER(P), C.c_int, C.c_int, C.c_int, C.c_float]),
+    "sphy_ctx_destroy": (None, [P]),
+    "sphy_last_error": (C.c_char_p, [P]),
+    "sphy_sm_count": (C.c_int, [P]),
+    "sphy_abi_sizeof": (C.c_size_t, [C.c_int]),
+    "sphy_ldd_build": (C.c_int, [P, P, P, P]),
+    "sphy_ncells": (C.c_int64, [P]),
+    "sphy_nlevels": (C.c_int32, [P]),
+    "sphy_ldd_export": (C.c_int, [P, C.c_char_p, P, C.c_size_t, P]),
+    "sphy_gather_f32": (C.c_int, [P, P, P, P]),
+    "sphy_scatter_f32": (C.c_int, [P, P, P, C.c_float, P]),
+    "sphy_sample": (C.c_int, [P, P, P, C.c_int, P, P]),
+    "sphy_map_unary": (C.c_int, [P, C.c_int, P, P, C.c_int64, P]),
+    "sphy_set_ncells": (C.c_int, [P, C.c_int64]),
+    "sphy_wb_step": (C.c_int, [P, C.POINTER(WbParams), C.POINTER(WbState), C.POINTER(WbForcing), C.POINTER(WbOut),
+                               C.c_int, P]),
+    "sphy_glac_step": (C.c_int, [P, C.POINTER(GlacTable), P, P, C.c_float, C.c_float, C.POINTER(GlacOut), P]),
+    "sphy_route_step": (C.c_int, [P, C.c_int, C.POINTER(P), C.POINTER(P), SphyParam, C.c_float, C.c_int, P]),
+    "sphy_accuflux": (C.c_int, [P, P, P, P, C.c_int, P]),
+    "sphy_upstream": (C.c_int, [P, P, P, P]),
+    "sphy_route_reslake_step": (C.c_int, [P, C.POINTER(ResLake), P, P, SphyParam, C.c_float, C.c_int, P]),
+}
+
+ABI_STRUCTS = (SphyParam, WbParams, WbState, WbForcing, WbOut, GlacTable, GlacOut, ResLake)
+
+_LIB = None
+
+
+def library_path():
+    return _build.CUDA_LIB
+
+
+def load(build=True):
+    """Load libsphy_b200.so, building it in-tree first if needed.  Raises if that is impossible."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if build:
+        path = _build.build_cuda()
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(sphy_b200 has no CPU fallback)")
+    lib = C.CDLL(path)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)          # AttributeError here = header and library disagree
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+class SphyError(RuntimeError):
+    pass
+
+
+def check(lib, ctx, rc, what):
+    if rc != 0:
+        msg = lib.sphy_last_error(ctx).decode() if ctx else ""
+        raise SphyError(f"{what} failed with code {rc}: {msg}")

@@ -1,0 +1,85 @@
+// common.cuh -- context object and small helpers shared by the sm_100a translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "sphy_b200.h"
+
+struct RoutePlanSeg {
+    int32_t first_level;   // first level of the segment
+    int32_t n_levels;      // 1 for a wide level (grid launch), >1 for a run of narrow levels (one CTA)
+};
+
+struct sphy_ctx {
+    int device = 0;
+    int nrows = 0, ncols = 0;
+    float cellsize = 1.f, cellarea = 1.f;
+    int sm_count = 148;
+    int64_t nraster = 0;
+    int64_t n = 0;             // active cells
+    int32_t nlevels = 0;
+    bool ldd_ready = false;
+    // Appendix-C structures (device), compact row-major numbering
+    int32_t *cidx = nullptr, *flat_active = nullptr, *down = nullptr, *level = nullptr, *order = nullptr;
+    int32_t *level_ptr = nullptr, *don_ptr = nullptr, *don_idx = nullptr;
+    uint8_t *indeg = nullptr;
+    int64_t *nup = nullptr;
+    int64_t n_don = 0;
+    // level-sweep layout (routing order = position in `order`): pos[i] = position of cell i,
+    // dpos_ptr/dpos = donor CSR expressed in positions, indexed by position
+    int32_t *pos = nullptr, *dpos_ptr = nullptr, *dpos = nullptr;
+    std::vector<int32_t> h_level_ptr;
+    std::vector<RoutePlanSeg> plan;
+    // scan layout (DFS pre-order): built lazily by route_scan.cu
+    bool scan_ready = false;
+    int32_t *pre = nullptr;        // cell -> pre-order rank
+    int32_t *pre_cell = nullptr;   // rank -> cell
+    int32_t *sub_size = nullptr;   // by rank: subtree size (== nup)
+    double *scan_local = nullptr;  // [ncomp_max][n] tile-local inclusive prefix sums (by rank)
+    double *scan_tile = nullptr;   // [ncomp_max][ntiles+1] exclusive prefix of tile totals
+    int32_t n_tiles = 0;
+    unsigned int *scan_flags = nullptr;
+    // workspaces
+    float *acc = nullptr;          // [ROUTE_MAX_COMP][n] accumulated flux in routing order
+    float *qsorted = nullptr;      // scratch [ROUTE_MAX_COMP][n]
+    float *ra_table = nullptr;     // per-day Ra by latitude class
+    int32_t ra_table_cap = 0;
+    float *tmp_n[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool qout_zeroed = false;
+    std::string err;
+};
+
+constexpr int ROUTE_MAX_COMP = 8;
+constexpr int ROUTE_WIDE_LEVEL = 2048;   // levels with at least this many cells get their own grid launch
+
+#define SPHY_FAIL(ctx, code, ...)                                 \
+    do {                                                          \
+        char _b[512];                                             \
+        snprintf(_b, sizeof(_b), __VA_ARGS__);                    \
+        if (ctx) (ctx)->err = _b;                                 \
+        return (code);                                            \
+    } while (0)
+
+#define SPHY_CUDA(ctx, call)                                                                       \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            SPHY_FAIL(ctx, SPHY_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+#define SPHY_LAUNCH_CHECK(ctx) SPHY_CUDA(ctx, cudaGetLastError())
+
+static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+template <typename T>
+static inline int dev_alloc(sphy_ctx *ctx, T **p, size_t count)
+{
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (count == 0) count = 1;
+    SPHY_CUDA(ctx, cudaMalloc((void **)p, count * sizeof(T)));
+    return SPHY_OK;
+}

@@ -1,0 +1,106 @@
+// ctx.cu -- context life cycle and the raster <-> compact boundary kernels.
+#include "common.cuh"
+
+extern "C" int sphy_ctx_create(sphy_ctx **out, int device, int nrows, int ncols, float cellsize)
+{
+    if (!out || nrows <= 0 || ncols <= 0 || !(cellsize > 0.f)) return SPHY_E_INVALID;
+    if ((int64_t)nrows * ncols >= (1ll << 31)) return SPHY_E_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return SPHY_E_CUDA;
+    sphy_ctx *ctx = new (std::nothrow) sphy_ctx();
+    if (!ctx) return SPHY_E_NOMEM;
+    ctx->device = device;
+    ctx->nrows = nrows;
+    ctx->ncols = ncols;
+    ctx->cellsize = cellsize;
+    ctx->cellarea = cellsize * cellsize;          // REAL4 cellarea() (routing.py:26)
+    ctx->nraster = (int64_t)nrows * ncols;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        delete ctx;
+        return SPHY_E_CUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    *out = ctx;
+    return SPHY_OK;
+}
+
+extern "C" void sphy_ctx_destroy(sphy_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    void *ptrs[] = {ctx->cidx, ctx->flat_active, ctx->down, ctx->level, ctx->order, ctx->level_ptr, ctx->don_ptr,
+                    ctx->don_idx, ctx->indeg, ctx->nup, ctx->pos, ctx->dpos_ptr, ctx->dpos, ctx->pre, ctx->pre_cell,
+                    ctx->sub_size, ctx->scan_local, ctx->scan_tile, ctx->scan_flags, ctx->acc, ctx->qsorted,
+                    ctx->ra_table, ctx->tmp_n[0], ctx->tmp_n[1], ctx->tmp_n[2], ctx->tmp_n[3]};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    delete ctx;
+}
+
+extern "C" const char *sphy_last_error(const sphy_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" int sphy_sm_count(const sphy_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
+
+namespace {
+__global__ void k_gather(const float *__restrict__ raster, const int32_t *__restrict__ flat, int64_t n, float *__restrict__ out)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = raster[flat[i]];
+}
+__global__ void k_scatter(const float *__restrict__ comp, const int32_t *__restrict__ cidx, int64_t nraster, float fill,
+                          float *__restrict__ raster)
+{
+    int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g < nraster) {
+        int32_t i = cidx[g];
+        raster[g] = i >= 0 ? comp[i] : fill;
+    }
+}
+__global__ void k_sample(const float *__restrict__ map, const int32_t *__restrict__ cells, int n, float *__restrict__ out)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) out[j] = map[cells[j]];
+}
+}  // namespace
+
+extern "C" int sphy_gather_f32(sphy_ctx *ctx, const float *raster, float *compact, void *stream)
+{
+    if (!ctx || !raster || !compact) return SPHY_E_INVALID;
+    if (!ctx->ldd_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_gather_f32 before sphy_ldd_build");
+    k_gather<<<div_up(ctx->n, 256), 256, 0, (cudaStream_t)stream>>>(raster, ctx->flat_active, ctx->n, compact);
+    SPHY_LAUNCH_CHECK(ctx);
+    return SPHY_OK;
+}
+
+extern "C" int sphy_scatter_f32(sphy_ctx *ctx, const float *compact, float *raster, float fill, void *stream)
+{
+    if (!ctx || !raster || !compact) return SPHY_E_INVALID;
+    if (!ctx->ldd_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_scatter_f32 before sphy_ldd_build");
+    k_scatter<<<div_up(ctx->nraster, 256), 256, 0, (cudaStream_t)stream>>>(compact, ctx->cidx, ctx->nraster, fill, raster);
+    SPHY_LAUNCH_CHECK(ctx);
+    return SPHY_OK;
+}
+
+extern "C" int sphy_sample(sphy_ctx *ctx, const float *map, const int32_t *cells, int n, float *out, void *stream)
+{
+    if (!ctx || !map || !cells || !out || n < 0) return SPHY_E_INVALID;
+    if (n == 0) return SPHY_OK;
+    k_sample<<<div_up(n, 128), 128, 0, (cudaStream_t)stream>>>(map, cells, n, out);
+    SPHY_LAUNCH_CHECK(ctx);
+    return SPHY_OK;
+}
+
+extern "C" size_t sphy_abi_sizeof(int which)
+{
+    switch (which) {
+        case 0: return sizeof(sphy_param);
+        case 1: return sizeof(sphy_wb_params);
+        case 2: return sizeof(sphy_wb_state);
+        case 3: return sizeof(sphy_wb_forcing);
+        case 4: return sizeof(sphy_wb_out);
+        case 5: return sizeof(sphy_glac_table);
+        case 6: return sizeof(sphy_glac_out);
+        case 7: return sizeof(sphy_reslake);
+        default: return 0;
+    }
+}

@@ -1,0 +1,365 @@
+// route.cu -- K4: flow accumulation over the LDD as a topological level sweep, fused with the kx recession.
+//
+// Replaces pcr.accuflux / pcr.accufractionflux / pcr.upstream as called by routing.ROUT
+// (/root/reference/modules/routing.py:25-29) and advanced_routing.ROUT (modules/advanced_routing.py:27-38).
+// Cells are visited in routing order (position k in `order`, i.e. sorted by (level, cell)); a cell's flux is
+// its own material plus the fluxes of its <=8 donors, summed in REAL8 and stored REAL4 (assumption A1), which
+// makes the result independent of the donor order and bit-identical with oracle/ldd_oracle.c.
+//   * wide levels (>= 2048 cells): one grid launch per level, one thread per cell;
+//   * runs of narrow levels: ONE CTA walks the run level by level; 8 lanes per cell fetch the donors in
+//     parallel and reduce with warp shuffles, the previous level's fluxes (the frontier) are staged in
+//     shared memory so the dependent read does not go back to L2.
+// All routed components (total + up to 6 fractions, routing.py:81-101) share one sweep: the index
+// structures are read once.
+#include "common.cuh"
+
+namespace {
+
+enum { MODE_PLAIN = 0, MODE_ROUT = 1, MODE_ADV = 2 };
+
+struct SweepArgs {
+    int ncomp;
+    int mode;
+    const float *m[ROUTE_MAX_COMP];      // material per component, cell order
+    float *qstate[ROUTE_MAX_COMP];       // MODE_ROUT/ADV: Qold in, Q out (cell order)
+    float *flux_out[ROUTE_MAX_COMP];     // MODE_PLAIN: flux in cell order
+    const float *frac;                   // accufractionflux fraction (cell order) or NULL
+    const float *qout_dense;             // MODE_ADV: structure outflow, m3/day, cell order
+    float *acc;                          // [ncomp][n] flux in routing order
+    float *qday;                         // MODE_ADV: [n] blended Q in m3/day, routing order
+    const int32_t *order, *dpos_ptr, *dpos, *level_ptr;
+    sphy_param kx;
+    float one_m_kx;
+    float cellarea;
+    int64_t n;
+};
+
+__device__ __forceinline__ float material(const SweepArgs &a, int c, int32_t i)
+{
+    float q = __ldg(a.m[c] + i);
+    if (a.mode == MODE_ROUT) return ((q * 0.001f) * a.cellarea) / 86400.0f;   // routing.py:26
+    return q;
+}
+
+// finish a cell: fraction cut, store flux, recession blend
+__device__ __forceinline__ float finish(const SweepArgs &a, int c, int64_t k, int32_t i, double tot)
+{
+    float f;
+    float fr = 1.0f;
+    if (a.frac) {
+        fr = __ldg(a.frac + i);
+        f = (float)((double)fr * tot);
+    } else {
+        f = (float)tot;
+    }
+    a.acc[(int64_t)c * a.n + k] = f;
+    if (a.mode == MODE_PLAIN) {
+        if (a.flux_out[c]) a.flux_out[c][i] = f;
+    } else {
+        const float kx = a.kx.map ? __ldg(a.kx.map + i) : a.kx.value;
+        const float omk = a.kx.map ? 1.0f - kx : a.one_m_kx;
+        float *qs = a.qstate[c];
+        if (a.mode == MODE_ROUT) {
+            qs[i] = omk * f + kx * qs[i];                                      // routing.py:28
+        } else {
+            // advanced_routing.py:31-37: Q = QFRAC==0 ? Qout : (1-kx)*Q + (Qold*24*3600)*kx ; Q/86400 is the state
+            float qd = fr == 0.0f ? __ldg(a.qout_dense + i) : omk * f + ((qs[i] * 24.0f) * 3600.0f) * kx;
+            a.qday[k] = qd;
+            qs[i] = qd / 86400.0f;
+        }
+    }
+    return f;
+}
+
+// one wide level: positions [k0, k1)
+__global__ void __launch_bounds__(256) k_sweep_wide(const __grid_constant__ SweepArgs a, int32_t k0, int32_t k1)
+{
+    int64_t k = k0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= k1) return;
+    const int32_t i = __ldg(a.order + k);
+    const int32_t b = __ldg(a.dpos_ptr + k), e = __ldg(a.dpos_ptr + k + 1);
+    for (int c = 0; c < a.ncomp; ++c) {
+        double s = (double)material(a, c, i);
+        const float *acc = a.acc + (int64_t)c * a.n;
+        for (int32_t q = b; q < e; ++q) s += (double)acc[__ldg(a.dpos + q)];
+        finish(a, c, k, i, s);
+    }
+}
+
+constexpr int NARROW_THREADS = 1024;
+constexpr int FRONT_CAP = ROUTE_WIDE_LEVEL;   // max cells of a narrow level
+
+// a run of narrow levels [l0, l0+nl) walked by one CTA
+__global__ void __launch_bounds__(NARROW_THREADS) k_sweep_narrow(const __grid_constant__ SweepArgs a, int32_t l0, int32_t nl)
+{
+    extern __shared__ float front[];     // [2][ncomp][FRONT_CAP] fluxes of the previous / current level
+    const int tid = threadIdx.x;
+    const int sub = tid & 7;             // donor lane
+    const int slot = tid >> 3;           // cell slot (128 cells per pass)
+    const int ncomp = a.ncomp;
+    int cur = 0;
+    int32_t prev_begin = -1, prev_end = -1;
+    for (int32_t l = l0; l < l0 + nl; ++l) {
+        const int32_t kb = __ldg(a.level_ptr + l), ke = __ldg(a.level_ptr + l + 1);
+        float *fcur = front + (size_t)cur * ncomp * FRONT_CAP;
+        const float *fprev = front + (size_t)(cur ^ 1) * ncomp * FRONT_CAP;
+        for (int32_t base = kb; base < ke; base += NARROW_THREADS / 8) {
+            const int32_t k = base + slot;
+            const bool live = k < ke;
+            int32_t i = 0, dp = -1;
+            if (live) {
+                i = __ldg(a.order + k);
+                const int32_t b = __ldg(a.dpos_ptr + k), e = __ldg(a.dpos_ptr + k + 1);
+                if (b + sub < e) dp = __ldg(a.dpos + b + sub);
+            }
+            for (int c = 0; c < ncomp; ++c) {
+                double s = 0.0;
+                if (dp >= 0) {
+                    if (dp >= prev_begin && dp < prev_end) s = (double)fprev[c * FRONT_CAP + (dp - prev_begin)];
+                    else s = (double)a.acc[(int64_t)c * a.n + dp];
+                }
+                // warp-shuffle reduction over the 8 donor lanes of the cell
+                s += __shfl_xor_sync(0xffffffffu, s, 4, 8);
+                s += __shfl_xor_sync(0xffffffffu, s, 2, 8);
+                s += __shfl_xor_sync(0xffffffffu, s, 1, 8);
+                if (live && sub == 0) {
+                    s += (double)material(a, c, i);
+                    float f = finish(a, c, k, i, s);
+                    fcur[c * FRONT_CAP + (k - kb)] = f;
+                }
+            }
+        }
+        prev_begin = kb;
+        prev_end = ke;
+        cur ^= 1;
+        __syncthreads();
+    }
+}
+
+__global__ void k_upstream(const float *__restrict__ x, const int32_t *__restrict__ don_ptr, const int32_t *__restrict__ don_idx,
+                           int64_t n, float *__restrict__ out)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0.0;
+    for (int32_t q = don_ptr[i]; q < don_ptr[i + 1]; ++q) s += (double)x[don_idx[q]];
+    out[i] = (float)s;
+}
+
+}  // namespace
+
+// run the level sweep described by `a` following the launch plan built in ldd_build.cu
+int route_levels_run(sphy_ctx *ctx, SweepArgs &a, cudaStream_t st)
+{
+    a.order = ctx->order;
+    a.dpos_ptr = ctx->dpos_ptr;
+    a.dpos = ctx->dpos;
+    a.level_ptr = ctx->level_ptr;
+    a.acc = ctx->acc;
+    a.n = ctx->n;
+    a.cellarea = ctx->cellarea;
+    const size_t smem = (size_t)2 * a.ncomp * FRONT_CAP * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        SPHY_CUDA(ctx, cudaFuncSetAttribute(k_sweep_narrow, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            2 * ROUTE_MAX_COMP * FRONT_CAP * (int)sizeof(float)));
+        attr_set = true;
+    }
+    for (const RoutePlanSeg &seg : ctx->plan) {
+        if (seg.n_levels == 1 && ctx->h_level_ptr[seg.first_level + 1] - ctx->h_level_ptr[seg.first_level] >= FRONT_CAP) {
+            const int32_t k0 = ctx->h_level_ptr[seg.first_level], k1 = ctx->h_level_ptr[seg.first_level + 1];
+            k_sweep_wide<<<div_up(k1 - k0, 256), 256, 0, st>>>(a, k0, k1);
+        } else {
+            k_sweep_narrow<<<1, NARROW_THREADS, smem, st>>>(a, seg.first_level, seg.n_levels);
+        }
+    }
+    SPHY_LAUNCH_CHECK(ctx);
+    return SPHY_OK;
+}
+
+int route_scan_run(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm, float *const *q_state, sphy_param kx,
+                   float one_m_kx, cudaStream_t st);   // route_scan.cu
+
+extern "C" int sphy_route_step(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm, float *const *q_state,
+                               sphy_param kx, float one_minus_kx, int method, void *stream)
+{
+    if (!ctx || !runoff_mm || !q_state || ncomp < 1 || ncomp > ROUTE_MAX_COMP) return SPHY_E_INVALID;
+    if (!ctx->ldd_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_route_step before sphy_ldd_build");
+    for (int c = 0; c < ncomp; ++c)
+        if (!runoff_mm[c] || !q_state[c]) SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_route_step: component %d has a NULL map", c);
+    if (method == SPHY_ROUTE_SCAN) return route_scan_run(ctx, ncomp, runoff_mm, q_state, kx, one_minus_kx, (cudaStream_t)stream);
+    if (method != SPHY_ROUTE_LEVELS) SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_route_step: unknown method %d", method);
+    SweepArgs a = {};
+    a.ncomp = ncomp;
+    a.mode = MODE_ROUT;
+    for (int c = 0; c < ncomp; ++c) {
+        a.m[c] = runoff_mm[c];
+        a.qstate[c] = q_state[c];
+    }
+    a.kx = kx;
+    a.one_m_kx = one_minus_kx;
+    return route_levels_run(ctx, a, (cudaStream_t)stream);
+}
+
+extern "C" int sphy_accuflux(sphy_ctx *ctx, const float *mat, const float *fraction, float *flux, int method, void *stream)
+{
+    if (!ctx || !mat || !flux) return SPHY_E_INVALID;
+    if (!ctx->ldd_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_accuflux before sphy_ldd_build");
+    if (method != SPHY_ROUTE_LEVELS) SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_accuflux: only SPHY_ROUTE_LEVELS is available");
+    SweepArgs a = {};
+    a.ncomp = 1;
+    a.mode = MODE_PLAIN;
+    a.m[0] = mat;
+    a.flux_out[0] = flux;
+    a.frac = fraction;
+    return route_levels_run(ctx, a, (cudaStream_t)stream);
+}
+
+extern "C" int sphy_upstream(sphy_ctx *ctx, const float *x, float *out, void *stream)
+{
+    if (!ctx || !x || !out) return SPHY_E_INVALID;
+    if (!ctx->ldd_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_upstream before sphy_ldd_build");
+    k_upstream<<<div_up(ctx->n, 256), 256, 0, (cudaStream_t)stream>>>(x, ctx->don_ptr, ctx->don_idx, ctx->n, out);
+    SPHY_LAUNCH_CHECK(ctx);
+    return SPHY_OK;
+}
+
+// ---- lakes / reservoirs ---------------------------------------------------------------------------------
+namespace {
+
+// parameter rows of sphy_reslake.par (SPHY_RL_NPAR x n_struct)
+enum {
+    RL_KR = 0, RL_B, RL_SMAX,                                   // simple reservoir (reservoirs.py:62-70)
+    RL_EVOL, RL_PVOL, RL_MAXFL, RL_DEMFL, RL_FLSTART, RL_FLEND,  // advanced reservoir (reservoirs.py:26-58)
+    RL_HS_FUNC, RL_HS_EXPA, RL_HS_EXPB, RL_HS_B, RL_HS_A1, RL_HS_A2, RL_HS_A3,   // lake h(S) (lakes.py:98-131)
+    RL_QH_FUNC, RL_QH_EXPA, RL_QH_EXPB, RL_QH_B,                // lake Q(h); a1..a3 follow in rows 20..22
+};
+
+__device__ __forceinline__ float dpowf(float x, float y) { return (float)pow((double)x, (double)y); }
+__device__ __forceinline__ float dexpf(float x) { return (float)exp((double)x); }
+
+__device__ float lake_fun(float fn, float ea, float eb, float pb, float a1, float a2, float a3, float x)
+{
+    if (fn == 1.0f) return ea * dexpf(eb * x);
+    if (fn == 2.0f) return a1 * x + pb;
+    if (fn == 3.0f) return ((a2 * dpowf(x, 2.0f)) + a1 * x) + pb;
+    return (((a3 * dpowf(x, 3.0f)) + (a2 * dpowf(x, 2.0f))) + a1 * x) + pb;
+}
+
+__global__ void k_rl_pre(sphy_reslake rl, const float *__restrict__ totr, float vol_factor, int doy, float *__restrict__ qout_dense)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= rl.n_struct) return;
+    const int ns = rl.n_struct;
+    const int32_t c = rl.cell[j];
+    auto P = [&](int row) { return rl.par[(size_t)row * ns + j]; };
+    float S = rl.StorRES[j] + vol_factor * totr[c];             // advanced_routing.py:136-138
+    float q = 0.0f;
+    const int kind = rl.kind[j];
+    if (kind == 1) {                                            // QSimple
+        q = fmaxf(fminf((P(RL_KR) * S) * dpowf(S / P(RL_SMAX), P(RL_B)), S), S - P(RL_SMAX));
+    } else if (kind == 2) {                                     // QAdv
+        const float D = (float)doy, fs = P(RL_FLSTART), fe = P(RL_FLEND);
+        bool flood;
+        if (fs < fe) flood = D >= fs && D <= fe;
+        else if (D >= fe) flood = D >= fs;
+        else flood = D <= fe ? D <= fs : false;
+        const float avail = fmaxf(S - P(RL_PVOL), 0.0f);
+        const float den = P(RL_EVOL) - P(RL_PVOL);
+        q = fmaxf(flood ? (P(RL_MAXFL) * avail) / den : (P(RL_DEMFL) * avail) / den, S - P(RL_EVOL));
+    } else if (kind == 3) {                                     // lake: level from storage, Q from level
+        const float h = lake_fun(P(RL_HS_FUNC), P(RL_HS_EXPA), P(RL_HS_EXPB), P(RL_HS_B), P(RL_HS_A1), P(RL_HS_A2), P(RL_HS_A3), S);
+        const float qh = lake_fun(P(RL_QH_FUNC), P(RL_QH_EXPA), P(RL_QH_EXPB), P(RL_QH_B), P(20), P(21), P(22), h);
+        q = (fmaxf(0.0f, qh) * 3600.0f) * 24.0f;                // lakes.py:155-157
+    }
+    rl.StorRES[j] = S;
+    rl.Qout[j] = q;
+    qout_dense[c] = q;
+}
+
+__global__ void k_rl_material(const float *__restrict__ totr, const float *__restrict__ qfrac, float vol_factor, int64_t n,
+                              float *__restrict__ m)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    m[i] = qfrac[i] == 0.0f ? 0.0f : vol_factor * totr[i];     // advanced_routing.py:159-161 (second term)
+}
+
+// add upstream(ldd, Qout) to the material of each receiver of a structure (once per receiver)
+__global__ void k_rl_upstream_add(sphy_reslake rl, const int32_t *__restrict__ down, const int32_t *__restrict__ don_ptr,
+                                  const int32_t *__restrict__ don_idx, const float *__restrict__ qfrac,
+                                  const float *__restrict__ qout_dense, float *__restrict__ m)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= rl.n_struct) return;
+    const int32_t c = rl.cell[j];
+    const int32_t r = down[c];
+    if (r < 0) return;
+    double s = 0.0;
+    bool first = true;
+    for (int32_t q = don_ptr[r]; q < don_ptr[r + 1]; ++q) {
+        const int32_t d = don_idx[q];
+        if (qfrac[d] == 0.0f) {
+            if (d < c) first = false;                           // a lower-indexed structure donor owns the update
+            s += (double)qout_dense[d];
+        }
+    }
+    if (first) m[r] = (float)s + m[r];
+}
+
+__global__ void k_rl_post(sphy_reslake rl, const int32_t *__restrict__ don_ptr, const int32_t *__restrict__ don_idx,
+                          const int32_t *__restrict__ pos, const float *__restrict__ qday)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= rl.n_struct) return;
+    const int32_t c = rl.cell[j];
+    double s = 0.0;
+    for (int32_t q = don_ptr[c]; q < don_ptr[c + 1]; ++q) s += (double)qday[pos[don_idx[q]]];
+    const float qin = (float)s;                                 // upstream(ldd, Q) at the structure cell
+    rl.Qin[j] = qin;
+    rl.StorRES[j] = (rl.StorRES[j] - rl.Qout[j]) + qin;         // advanced_routing.py:36
+}
+
+}  // namespace
+
+extern "C" int sphy_route_reslake_step(sphy_ctx *ctx, const sphy_reslake *rl, const float *totr, float *q_state, sphy_param kx,
+                                       float one_minus_kx, int doy, void *stream)
+{
+    if (!ctx || !rl || !totr || !q_state) return SPHY_E_INVALID;
+    if (!ctx->ldd_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_route_reslake_step before sphy_ldd_build");
+    if (rl->n_struct < 0 || !rl->qfrac || (rl->n_struct > 0 && (!rl->cell || !rl->kind || !rl->par || !rl->StorRES || !rl->Qout || !rl->Qin)))
+        SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_route_reslake_step: incomplete structure table");
+    cudaStream_t st = (cudaStream_t)stream;
+    const float vol_factor = 0.001f * ctx->cellarea;            // 0.001 * cellarea() as REAL4 (advanced_routing.py:137)
+    float *qout_dense = ctx->tmp_n[1], *m = ctx->tmp_n[0];
+    if (!ctx->qout_zeroed) {                                    // qout_dense is only ever written at structure cells
+        SPHY_CUDA(ctx, cudaMemsetAsync(qout_dense, 0, sizeof(float) * ctx->n, st));
+        ctx->qout_zeroed = true;
+    }
+    const int ns = rl->n_struct;
+    if (ns > 0) {
+        k_rl_pre<<<div_up(ns, 128), 128, 0, st>>>(*rl, totr, vol_factor, doy, qout_dense);
+    }
+    k_rl_material<<<div_up(ctx->n, 256), 256, 0, st>>>(totr, rl->qfrac, vol_factor, ctx->n, m);
+    if (ns > 0) {
+        k_rl_upstream_add<<<div_up(ns, 128), 128, 0, st>>>(*rl, ctx->down, ctx->don_ptr, ctx->don_idx, rl->qfrac, qout_dense, m);
+    }
+    SPHY_LAUNCH_CHECK(ctx);
+    SweepArgs a = {};
+    a.ncomp = 1;
+    a.mode = MODE_ADV;
+    a.m[0] = m;
+    a.qstate[0] = q_state;
+    a.frac = rl->qfrac;
+    a.qout_dense = qout_dense;
+    a.qday = ctx->qsorted;
+    a.kx = kx;
+    a.one_m_kx = one_minus_kx;
+    int rc = route_levels_run(ctx, a, st);
+    if (rc != SPHY_OK) return rc;
+    if (ns > 0) {
+        k_rl_post<<<div_up(ns, 128), 128, 0, st>>>(*rl, ctx->don_ptr, ctx->don_idx, ctx->pos, ctx->qsorted);
+        SPHY_LAUNCH_CHECK(ctx);
+    }
+    return SPHY_OK;
+}

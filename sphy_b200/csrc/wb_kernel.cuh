@@ -1,0 +1,437 @@
+// wb_kernel.cuh -- K1 device code: the fused vertical water balance, templated on the module switches.
+// Included by the wb_inst_*.cu translation units (one per SnowFLAG x GroundFLAG combination, so that the
+// 48 instantiations compile in parallel) and by wb_step.cu (host launcher, Ra table, init-time maps).
+#pragma once
+#include <math.h>
+
+#include "common.cuh"
+
+namespace wb {
+
+struct DayScalars {
+    float k0dr;        // REAL4(k0) * dr                                   hargreaves.py:31-34
+    float sin_delta, cos_delta, tan_delta;
+    float hg_c;        // REAL4(0.0023 * 0.408)                            hargreaves.py:45
+};
+
+struct WbArgs {
+    sphy_wb_params p;
+    sphy_wb_state s;
+    sphy_wb_forcing f;
+    sphy_wb_out o;
+    DayScalars d;
+    const float *ra_table;
+    int64_t n;
+};
+
+// ---- 128-bit streaming accessors ------------------------------------------------------------------
+struct V4 { float v[4]; };
+
+__device__ __forceinline__ V4 ld4(const float *p, int64_t i)
+{
+    float4 t = __ldg(reinterpret_cast<const float4 *>(p + i));
+    return V4{{t.x, t.y, t.z, t.w}};
+}
+__device__ __forceinline__ V4 ld4_rw(const float *p, int64_t i)
+{
+    float4 t = *reinterpret_cast<const float4 *>(p + i);
+    return V4{{t.x, t.y, t.z, t.w}};
+}
+__device__ __forceinline__ void st4(float *p, int64_t i, const V4 &a)
+{
+    *reinterpret_cast<float4 *>(p + i) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
+}
+__device__ __forceinline__ V4 splat(float x) { return V4{{x, x, x, x}}; }
+
+template <int W>
+struct Lanes;   // W cells per thread: 4 (vector path) or 1 (tail)
+
+template <>
+struct Lanes<4> {
+    static __device__ __forceinline__ V4 in(const float *p, int64_t i) { return ld4(p, i); }
+    static __device__ __forceinline__ V4 inrw(const float *p, int64_t i) { return ld4_rw(p, i); }
+    static __device__ __forceinline__ void out(float *p, int64_t i, const V4 &a) { st4(p, i, a); }
+    static __device__ __forceinline__ V4 par(const sphy_param &q, int64_t i) { return q.map ? ld4(q.map, i) : splat(q.value); }
+};
+template <>
+struct Lanes<1> {
+    static __device__ __forceinline__ V4 in(const float *p, int64_t i) { return splat(__ldg(p + i)); }
+    static __device__ __forceinline__ V4 inrw(const float *p, int64_t i) { return splat(p[i]); }
+    static __device__ __forceinline__ void out(float *p, int64_t i, const V4 &a) { p[i] = a.v[0]; }
+    static __device__ __forceinline__ V4 par(const sphy_param &q, int64_t i) { return splat(q.map ? __ldg(q.map + i) : q.value); }
+};
+
+// double-evaluated transcendentals stored as REAL4 (assumption A2, see oracle/pcr_shim.py)
+__device__ __forceinline__ float d_acos(float x) { return (float)acos((double)x); }
+__device__ __forceinline__ float d_sin(float x) { return (float)sin((double)x); }
+__device__ __forceinline__ float d_pow(float x, float y) { return (float)pow((double)x, (double)y); }
+
+// Ra for one latitude (hargreaves.py:24-39)
+__device__ __forceinline__ float extrarad(float sinl, float cosl, float tanl, const DayScalars &d)
+{
+    float x = (-1.0f * tanl) * d.tan_delta;
+    float omegas = d_acos(x);
+    return d.k0dr * ((omegas * sinl) * d.sin_delta + (cosl * d.cos_delta) * d_sin(omegas));
+}
+
+// ---- the per-cell physics, W cells per call --------------------------------------------------------
+template <bool SNOW, bool GROUND, bool INFIL, int RA /*0 table, 1 cell, 2 etref input*/, bool DIAG, bool USOIL, int W>
+__device__ __forceinline__ void wb_cells(const WbArgs &a, int64_t i)
+{
+    using L = Lanes<W>;
+    const sphy_wb_params &p = a.p;
+    // ---- loads (all issued up front: ~14 independent 128-bit requests per thread) -------------------
+    V4 prec = L::in(a.f.prec, i), tavg = L::in(a.f.tavg, i);
+    V4 tmin, tmax, etref_in, ra;
+    if (RA == 2) {
+        etref_in = L::in(a.f.etref, i);
+    } else {
+        tmin = L::in(a.f.tmin, i);
+        tmax = L::in(a.f.tmax, i);
+    }
+    if (SNOW && RA == 2) tmax = L::in(a.f.tmax, i);
+    V4 sinl, cosl, tanl;
+    if (RA == 0) {
+        if (W == 4) {
+            uint2 c = __ldg(reinterpret_cast<const uint2 *>(p.lat_class + i));
+            ra.v[0] = __ldg(a.ra_table + (c.x & 0xffffu));
+            ra.v[1] = __ldg(a.ra_table + (c.x >> 16));
+            ra.v[2] = __ldg(a.ra_table + (c.y & 0xffffu));
+            ra.v[3] = __ldg(a.ra_table + (c.y >> 16));
+        } else {
+            ra = splat(__ldg(a.ra_table + __ldg(p.lat_class + i)));
+        }
+    } else if (RA == 1) {
+        sinl = L::in(p.sin_lat, i);
+        cosl = L::in(p.cos_lat, i);
+        tanl = L::in(p.tan_lat, i);
+    }
+    V4 RW = L::inrw(a.s.RootWater, i), SW = L::inrw(a.s.SubWater, i), CapRise = L::inrw(a.s.CapRise, i),
+       RootDrain = L::inrw(a.s.RootDrain, i);
+    V4 GwRecharge, Gw, BaseR, H_gw, SubDrain, SnowStore, SnowWatStore, TotalSnowStore;
+    if (GROUND) {
+        GwRecharge = L::inrw(a.s.GwRecharge, i);
+        Gw = L::inrw(a.s.Gw, i);
+        BaseR = L::inrw(a.s.BaseR, i);
+        H_gw = L::inrw(a.s.H_gw, i);
+    } else {
+        SubDrain = L::inrw(a.s.SubDrain, i);
+    }
+    if (SNOW) {
+        SnowStore = L::inrw(a.s.SnowStore, i);
+        SnowWatStore = L::inrw(a.s.SnowWatStore, i);
+        TotalSnowStore = L::inrw(a.s.TotalSnowStore, i);
+    }
+    // soil / groundwater parameters: USOIL = every one of them is a scalar (uniform soils, the cfg defaults):
+    // they are then read straight from the kernel-parameter constant bank and cost no registers and no bytes
+    V4 root_field, root_sat, root_dry, root_wilt, root_ksat, e_root, sub_field, sub_sat, e_sub, capmax, kc;
+    if (!USOIL) {
+        root_field = L::par(p.root_field, i); root_sat = L::par(p.root_sat, i); root_dry = L::par(p.root_dry, i);
+        root_wilt = L::par(p.root_wilt, i); root_ksat = L::par(p.root_ksat, i); e_root = L::par(p.e_root, i);
+        sub_field = L::par(p.sub_field, i); sub_sat = L::par(p.sub_sat, i); e_sub = L::par(p.e_sub, i);
+        capmax = L::par(p.caprise_max, i); kc = L::par(p.kc, i);
+    }
+    V4 drainvel = L::par(p.root_drainvel, i);
+#define PV(vec, par) (USOIL ? p.par.value : vec.v[j])
+    const bool has_glac = p.glac_frac.map != nullptr;
+    const bool has_ow = p.open_water_frac.map != nullptr;
+    V4 glac_frac = L::par(p.glac_frac, i), ow = L::par(p.open_water_frac, i);
+    V4 g_tss, g_snowr, g_perc, g_r;
+    const bool glac_in = a.f.GlacR != nullptr;
+    if (glac_in) {
+        g_tss = L::in(a.f.TotalSnowStore_GLAC, i);
+        g_snowr = L::in(a.f.SnowR_GLAC, i);
+        g_perc = L::in(a.f.GlacPerc, i);
+        g_r = L::in(a.f.GlacR, i);
+    }
+    V4 gw_sat, base_thresh, e_delta, e_alpha, h_den, seep, sub_drainvel, pmap, paved;
+    if (GROUND) {
+        if (!USOIL) {
+            gw_sat = L::par(p.gw_sat, i); base_thresh = L::par(p.base_thresh, i); e_delta = L::par(p.e_delta, i);
+            e_alpha = L::par(p.e_alpha, i); h_den = L::par(p.h_den, i);
+        }
+    } else {
+        if (!USOIL) seep = L::par(p.seepage, i);
+        sub_drainvel = L::par(p.sub_drainvel, i);
+    }
+    const bool pws = (p.flags & SPHY_WB_PWS) != 0;
+    if (pws) pmap = L::par(p.pmap, i);
+    if (INFIL) paved = L::par(p.paved_frac, i);
+    V4 wtot;
+    if (DIAG && a.s.waterbalanceTot) wtot = L::inrw(a.s.waterbalanceTot, i);
+
+    V4 o_totr, o_rootrr, o_rootdr, o_rainr, o_snowr, o_etref, o_etact, o_actet, o_infil, o_rain, o_rperc, o_sperc, o_wbal, o_etow;
+
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        const float one = 1.0f;
+        const float gf = glac_frac.v[j];
+        const float omg = has_glac ? one - gf : one;                      // 1 - GlacFrac
+        const float omow = has_ow ? one - ow.v[j] : one;                   // 1 - openWaterFrac
+        const float ss0 = SNOW ? SnowStore.v[j] : 0.0f;
+        const float SnowFrac = ss0 > 0.0f ? omg : 0.0f;                    // sphy.py:732
+        const float RainFrac = ss0 == 0.0f ? omg : 0.0f;                   // sphy.py:733
+        const float Precip = prec.v[j] / p.pcorr;                          // sphy.py:757 (divides)
+        const float Temp = tavg.v[j] + p.tcorr;
+        float TempMax = 0.0f, ETref;
+        if (RA == 2) {
+            ETref = etref_in.v[j];
+            if (SNOW) TempMax = tmax.v[j] + p.tcorr;
+        } else {
+            const float TempMin = tmin.v[j] + p.tcorr;
+            TempMax = tmax.v[j] + p.tcorr;
+            const float Ra = (RA == 0) ? ra.v[j] : extrarad(sinl.v[j], cosl.v[j], tanl.v[j], a.d);
+            // hargreaves.py:44-46; x**0.5 == sqrtf(x) exactly (double sqrt then REAL4 is double-rounding safe)
+            ETref = fmaxf(((a.d.hg_c * Ra) * (Temp + 17.8f)) * sqrtf(fmaxf(TempMax - TempMin, 0.0f)), 0.0f);
+        }
+        // ---- snow, modules/snow.py:110-187 ----------------------------------------------------------
+        float Rain = Precip, SnowR = 0.0f, SnowSoil = 0.0f, OldTotalSnowStore = 0.0f, tss = 0.0f;
+        float ss = ss0, sws = 0.0f;
+        if (SNOW) {
+            sws = SnowWatStore.v[j];
+            const float Snow = Temp >= p.tcrit ? 0.0f : Precip;
+            Rain = Temp < p.tcrit ? 0.0f : Precip;
+            float thour = 0.0f;
+            const float dT = TempMax - Temp;
+#pragma unroll
+            for (int h = 0; h < 24; ++h) thour = thour + fmaxf(0.0f, Temp + dT * p.melt_cos[h]);
+            const float melt = (thour * p.ddfs) / 24.0f;
+            const float PotSnowMelt = TempMax < 0.0f ? 0.0f : melt;
+            const float ActSnowMelt = fminf(ss, PotSnowMelt);
+            ss = ((ss + Snow) - ActSnowMelt) + (Temp < 0.0f ? sws : 0.0f);
+            const float MaxSWS = p.snow_sc * ss;
+            const float OldSWS = sws;
+            sws = TempMax < 0.0f ? 0.0f : fminf(MaxSWS, (sws + ActSnowMelt) + Rain);
+            OldTotalSnowStore = TotalSnowStore.v[j];
+            tss = (ss + sws) * (SnowFrac + RainFrac);
+            if (glac_in) tss = tss + g_tss.v[j];
+            SnowR = sws == MaxSWS ? ((ActSnowMelt + Rain) - (sws - OldSWS)) * SnowFrac : 0.0f;
+            if (glac_in) SnowR = SnowR + g_snowr.v[j];
+            SnowSoil = SnowR * p.snow_f;
+            SnowR = SnowR * p.one_minus_snow_f;
+            if (has_ow) SnowR = SnowR * omow;
+        }
+        const float ETpot = ETref * PV(kc, kc);                               // ET.py:24-26
+        // ---- rootzone, sphy.py:904-981 + rootzone.py ---------------------------------------------------
+        float rw = RW.v[j] + CapRise.v[j];
+        if (SNOW) rw = rw + SnowSoil;
+        const float rsat = PV(root_sat, root_sat), rfield = PV(root_field, root_field);
+        float Infil, RootRunoff;
+        if (INFIL) {
+            const float cap = ((p.k_eff * PV(root_ksat, root_ksat)) / 24.0f) * d_pow(one + ((rsat - rw) / rsat), p.labda_infil);
+            const float ar = p.alpha * Rain;
+            const float dd = ar - cap;
+            const float iex = ar > cap ? Rain - (dd * dd) / (p.alpha_sq * Rain) : Rain;
+            Infil = fmaxf(0.0f, fminf(iex, rsat - rw)) * (one - paved.v[j]);
+            RootRunoff = Rain - Infil;
+        } else {
+            Infil = fmaxf(0.0f, fminf(fminf(Rain, PV(root_ksat, root_ksat)), rsat - rw));
+            RootRunoff = RainFrac > 0.0f ? Rain - Infil : 0.0f;
+        }
+        rw = RainFrac > 0.0f ? rw + Infil : rw;
+        float etreddry;
+        if (pws) {                                                         // ET.py:39-47
+            const float TAW = rfield - PV(root_dry, root_dry);
+            const float pf = fmaxf(fminf(pmap.v[j] + 0.04f * (5.0f - ETpot), 0.8f), 0.1f);
+            const float RootPWS = rfield - TAW * pf;
+            etreddry = fmaxf(fminf((rw - PV(root_dry, root_dry)) / (RootPWS - PV(root_dry, root_dry)), one), 0.0f);
+        } else {
+            etreddry = fmaxf(fminf((rw - PV(root_dry, root_dry)) / (PV(root_wilt, root_wilt) - PV(root_dry, root_dry)), one), 0.0f);
+        }
+        const float etredwet = rw >= rsat ? 0.0f : one;                    // ET.py:31
+        const float ETact = RainFrac > 0.0f ? fminf((ETpot * etreddry) * etredwet, rw) : 0.0f;
+        const float ActETact = ETact * RainFrac;
+        rw = fmaxf(rw - ETact, 0.0f);
+        const float er = PV(e_root, e_root);
+        const float ex = fmaxf(rw - rfield, 0.0f);
+        const float rootlat = (ex / (rsat - rfield)) * drainvel.v[j];
+        const float tD = fmaxf(fminf(ex, rootlat * (one - er) + RootDrain.v[j] * er), 0.0f);    // rootzone.py:63-74
+        float sw = SW.v[j];
+        const float ssat = PV(sub_sat, sub_sat);
+        float perc = ex * (one - er);                                      // rootzone.py:78-85
+        perc = sw >= ssat ? 0.0f : fminf(ssat - sw, perc);
+        const float tP = fmaxf(fminf(perc, ex), 0.0f);
+        const float RootOut = tD + tP;
+        const float frac = (RootOut - ex) / RootOut;                       // rootzone.py:89-94
+        const bool over = RootOut > ex;
+        const float rdrain = over ? tD - tD * frac : tD;
+        const float rootperc = over ? tP - tP * frac : tP;
+        rw = rw - (rdrain + rootperc);
+        // ---- subzone, sphy.py:991-1056 + subzone.py ----------------------------------------------------
+        sw = sw + rootperc;
+        if (!GROUND) sw = fminf(fmaxf(sw - PV(seep, seepage), 0.0f), ssat);
+        const float sfield = PV(sub_field, sub_field);
+        const float subrel = fmaxf(fminf(sw / sfield, one), 0.0f);
+        const float rootrel = fmaxf(fminf(rw / rfield, one), 0.0f);
+        float cr = fminf(sw, (PV(capmax, caprise_max) * (one - rootrel)) * subrel);
+        cr = fminf(cr, rsat - rw);
+        sw = sw - cr;
+        float subperc = 0.0f, ActSubPerc = 0.0f, sdrain = 0.0f;
+        const float es = PV(e_sub, e_sub);
+        if (GROUND) {
+            const float dsw = sw - sfield;
+            subperc = (Gw.v[j] < PV(gw_sat, gw_sat) && dsw > 0.0f) ? dsw * (one - es) : 0.0f;          // subzone.py:35-41
+            ActSubPerc = has_glac ? subperc * omg : subperc;
+            sw = sw - subperc;
+        } else {
+            const float subex = fmaxf(sw - sfield, 0.0f);                                      // subzone.py:45-51
+            const float sublat = (subex / (ssat - sfield)) * sub_drainvel.v[j];
+            sdrain = (sublat + SubDrain.v[j]) * (one - es);
+            sdrain = fmaxf(fminf(sdrain, sw), 0.0f);
+            sw = sw - sdrain;
+        }
+        // ---- runoff assembly, sphy.py:1063-1077 --------------------------------------------------------
+        float RootRR = RootRunoff * RainFrac;
+        if (has_ow) RootRR = RootRR * omow;
+        float RootDR = has_glac ? rdrain * omg : rdrain;
+        if (has_ow) RootDR = RootDR * omow;
+        const float RainR = RootRR + RootDR;
+        // ---- groundwater, modules/groundwater.py:90-125 -------------------------------------------------
+        float baser, gw = 0.0f, gwr = 0.0f, hgw = 0.0f;
+        if (GROUND) {
+            const float ed = PV(e_delta, e_delta), ea = PV(e_alpha, e_alpha);
+            float inflow = ActSubPerc;
+            if (glac_in) inflow = inflow + g_perc.v[j];
+            const float gwseep = (one - ed) * inflow;
+            gwr = (ed * GwRecharge.v[j]) + gwseep;
+            gw = Gw.v[j] + gwr;
+            baser = gw <= PV(base_thresh, base_thresh) ? 0.0f : (BaseR.v[j] * ea + gwr * (one - ea));
+            gw = gw - baser;
+            if (has_ow) baser = baser * omow;
+            hgw = (H_gw.v[j] * ea) + ((gwr * (one - ea)) / PV(h_den, h_den));
+        } else {
+            baser = sdrain;                                                // sphy.py:1085
+        }
+        float TotR = (baser + RainR) + SnowR;                              // sphy.py:1096
+        if (glac_in) TotR = TotR + g_r.v[j];
+        // ---- water balance, sphy.py:1114-1212 (GlacRetreat = 0 branches) ----------------------------------
+        if (DIAG && (a.o.wbal || a.s.waterbalanceTot)) {
+            float dS = (rw - RW.v[j]) + (sw - SW.v[j]);
+            if (has_glac) dS = dS * omg;
+            float wb;
+            if (GROUND) {
+                dS = dS + (gw - Gw.v[j]);
+                if (SNOW) dS = dS + (tss - OldTotalSnowStore);
+                wb = (((Precip - ActETact) - baser) - RainR) - SnowR;
+                if (glac_in) wb = wb - g_r.v[j];
+                wb = wb - dS;
+            } else {
+                if (SNOW) dS = dS + (tss - OldTotalSnowStore);
+                wb = (((((Precip - ActETact) - baser) - RainR) - SnowR) - dS) - PV(seep, seepage);
+            }
+            o_wbal.v[j] = wb;
+            if (a.s.waterbalanceTot) wtot.v[j] = wtot.v[j] + wb;
+        }
+        // ---- write back to the register tile ------------------------------------------------------------
+        RW.v[j] = rw;
+        SW.v[j] = sw;
+        CapRise.v[j] = cr;
+        RootDrain.v[j] = rdrain;
+        if (GROUND) {
+            GwRecharge.v[j] = gwr;
+            Gw.v[j] = gw;
+            BaseR.v[j] = baser;
+            H_gw.v[j] = hgw;
+        } else {
+            SubDrain.v[j] = sdrain;
+        }
+        if (SNOW) {
+            SnowStore.v[j] = ss;
+            SnowWatStore.v[j] = sws;
+            TotalSnowStore.v[j] = tss;
+        }
+        o_totr.v[j] = TotR;
+        o_rootrr.v[j] = RootRR;
+        o_rootdr.v[j] = RootDR;
+        o_rainr.v[j] = RainR;
+        o_snowr.v[j] = SnowR;
+        if (DIAG) {
+            o_etref.v[j] = ETref;
+            o_etact.v[j] = ETact;
+            o_actet.v[j] = ActETact;
+            o_infil.v[j] = Infil;
+            o_rain.v[j] = Rain;
+            o_rperc.v[j] = rootperc;
+            o_sperc.v[j] = ActSubPerc;
+            o_etow.v[j] = ETref * p.kc_open_water;
+        }
+    }
+#undef PV
+    // ---- stores ----------------------------------------------------------------------------------------
+    L::out(a.s.RootWater, i, RW);
+    L::out(a.s.SubWater, i, SW);
+    L::out(a.s.CapRise, i, CapRise);
+    L::out(a.s.RootDrain, i, RootDrain);
+    if (GROUND) {
+        L::out(a.s.GwRecharge, i, GwRecharge);
+        L::out(a.s.Gw, i, Gw);
+        L::out(a.s.BaseR, i, BaseR);
+        L::out(a.s.H_gw, i, H_gw);
+    } else {
+        L::out(a.s.SubDrain, i, SubDrain);
+    }
+    if (SNOW) {
+        L::out(a.s.SnowStore, i, SnowStore);
+        L::out(a.s.SnowWatStore, i, SnowWatStore);
+        L::out(a.s.TotalSnowStore, i, TotalSnowStore);
+    }
+    if (DIAG && a.s.waterbalanceTot) L::out(a.s.waterbalanceTot, i, wtot);
+    L::out(a.o.TotR, i, o_totr);
+    if (a.o.RootRR) L::out(a.o.RootRR, i, o_rootrr);
+    if (a.o.RootDR) L::out(a.o.RootDR, i, o_rootdr);
+    if (a.o.RainR) L::out(a.o.RainR, i, o_rainr);
+    if (a.o.SnowR) L::out(a.o.SnowR, i, o_snowr);
+    if (DIAG) {
+        if (a.o.ETref) L::out(a.o.ETref, i, o_etref);
+        if (a.o.ETact) L::out(a.o.ETact, i, o_etact);
+        if (a.o.ActETact) L::out(a.o.ActETact, i, o_actet);
+        if (a.o.Infil) L::out(a.o.Infil, i, o_infil);
+        if (a.o.Rain) L::out(a.o.Rain, i, o_rain);
+        if (a.o.RootPerc) L::out(a.o.RootPerc, i, o_rperc);
+        if (a.o.SubPerc) L::out(a.o.SubPerc, i, o_sperc);
+        if (a.o.wbal) L::out(a.o.wbal, i, o_wbal);
+        if (a.o.ETOpenWater) L::out(a.o.ETOpenWater, i, o_etow);
+    }
+}
+
+constexpr int WB_THREADS = 128;
+
+template <bool SNOW, bool GROUND, bool INFIL, int RA, bool DIAG, bool USOIL>
+__global__ void __launch_bounds__(WB_THREADS) k_wb_step(const __grid_constant__ WbArgs a)
+{
+    const int64_t n4 = a.n >> 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n4; q += stride)
+        wb_cells<SNOW, GROUND, INFIL, RA, DIAG, USOIL, 4>(a, q << 2);
+    // ragged tail (< 4 cells)
+    const int64_t tail0 = n4 << 2;
+    if (blockIdx.x == 0 && threadIdx.x < (a.n - tail0)) wb_cells<SNOW, GROUND, INFIL, RA, DIAG, USOIL, 1>(a, tail0 + threadIdx.x);
+}
+
+typedef void (*wb_kernel_t)(const WbArgs);
+
+template <bool S, bool G, bool U>
+wb_kernel_t pick_sgu(bool infil, int ra, bool diag)
+{
+#define SPHY_WB_CASE(I, R, D) if (infil == I && ra == R && diag == D) return k_wb_step<S, G, I, R, D, U>;
+    SPHY_WB_CASE(false, 0, false) SPHY_WB_CASE(false, 1, false) SPHY_WB_CASE(false, 2, false)
+    SPHY_WB_CASE(true, 0, false) SPHY_WB_CASE(true, 1, false) SPHY_WB_CASE(true, 2, false)
+    SPHY_WB_CASE(false, 0, true) SPHY_WB_CASE(false, 1, true) SPHY_WB_CASE(false, 2, true)
+    SPHY_WB_CASE(true, 0, true) SPHY_WB_CASE(true, 1, true) SPHY_WB_CASE(true, 2, true)
+#undef SPHY_WB_CASE
+    return nullptr;
+}
+
+template <bool S, bool G>
+wb_kernel_t pick_sg(bool infil, int ra, bool diag, bool usoil)
+{
+    return usoil ? pick_sgu<S, G, true>(infil, ra, diag) : pick_sgu<S, G, false>(infil, ra, diag);
+}
+
+}  // namespace wb
+
+// one per translation unit wb_inst_{s}{g}.cu
+wb::wb_kernel_t wb_pick_00(bool infil, int ra, bool diag, bool usoil);
+wb::wb_kernel_t wb_pick_01(bool infil, int ra, bool diag, bool usoil);
+wb::wb_kernel_t wb_pick_10(bool infil, int ra, bool diag, bool usoil);
+wb::wb_kernel_t wb_pick_11(bool infil, int ra, bool diag, bool usoil);

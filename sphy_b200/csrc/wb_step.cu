@@ -1,0 +1,151 @@
+// wb_step.cu -- K1 host side: day scalars, the per-day Ra table, init-time derived maps, launch.
+// Device code lives in wb_kernel.cuh (instantiated in wb_inst_*.cu).
+#include "wb_kernel.cuh"
+
+using namespace wb;
+
+namespace {
+
+__global__ void k_ra_table(const float *__restrict__ lat_deg, int n, DayScalars d, float *__restrict__ ra)
+{
+    int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n) return;
+    float latrad = lat_deg[u] * 0.017453292519943295f;     // Lat * REAL4(pi/180)
+    float sinl = (float)sin((double)latrad), cosl = (float)cos((double)latrad), tanl = (float)tan((double)latrad);
+    ra[u] = extrarad(sinl, cosl, tanl, d);
+}
+
+__global__ void k_map_unary(int op, const float *__restrict__ in, float *__restrict__ out, int64_t n)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float x = in[i];
+    float r;
+    switch (op) {
+        case SPHY_UNARY_EXP_NEG_INV: r = (float)exp((double)(-1.0f / x)); break;
+        case SPHY_UNARY_SIN_DEG: r = (float)sin((double)(x * 0.017453292519943295f)); break;
+        case SPHY_UNARY_COS_DEG: r = (float)cos((double)(x * 0.017453292519943295f)); break;
+        case SPHY_UNARY_TAN_DEG: r = (float)tan((double)(x * 0.017453292519943295f)); break;
+        default: r = (float)exp((double)(-x)); break;
+    }
+    out[i] = r;
+}
+
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+// Day-of-year scalars, evaluated on the host exactly as the reference does (hargreaves.py:25-29):
+// Python double angle -> REAL4 non-spatial -> libm double -> REAL4.
+static DayScalars day_scalars(int doy, float k0)
+{
+    const double pi = 3.141592653589793;
+    const double ang = (2.0 * pi * (double)doy) / 365.0;
+    DayScalars d;
+    const float dr = 1.0f + 0.033f * (float)cos((double)(float)ang);
+    const float delta = 0.409f * (float)sin((double)(float)(ang - 1.39));
+    d.k0dr = k0 * dr;
+    d.sin_delta = (float)sin((double)delta);
+    d.cos_delta = (float)cos((double)delta);
+    d.tan_delta = (float)tan((double)delta);
+    d.hg_c = (float)(0.0023 * 0.408);
+    return d;
+}
+
+extern "C" int sphy_map_unary(sphy_ctx *ctx, int op, const float *in, float *out, int64_t count, void *stream)
+{
+    if (!ctx || !in || !out || count < 0 || op < 0 || op > 4) return SPHY_E_INVALID;
+    if (count == 0) return SPHY_OK;
+    k_map_unary<<<div_up(count, 256), 256, 0, (cudaStream_t)stream>>>(op, in, out, count);
+    SPHY_LAUNCH_CHECK(ctx);
+    return SPHY_OK;
+}
+
+extern "C" int sphy_wb_step(sphy_ctx *ctx, const sphy_wb_params *p, const sphy_wb_state *s, const sphy_wb_forcing *f,
+                            const sphy_wb_out *o, int doy, void *stream_)
+{
+    if (!ctx || !p || !s || !f || !o) return SPHY_E_INVALID;
+    if (!ctx->ldd_ready && ctx->n <= 0) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_wb_step: no active cells (call sphy_ldd_build or sphy_set_ncells)");
+    cudaStream_t st = (cudaStream_t)stream_;
+    const bool snow = p->flags & SPHY_WB_SNOW, ground = p->flags & SPHY_WB_GROUND, infil = p->flags & SPHY_WB_INFIL_EXCESS;
+    const bool etin = p->flags & SPHY_WB_ETREF_INPUT;
+    const int ra = etin ? 2 : p->ra_mode;
+    // argument validation: the reference would raise a Python exception on a missing map
+    if (!f->prec || !f->tavg || !o->TotR || !s->RootWater || !s->SubWater || !s->CapRise || !s->RootDrain)
+        SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_wb_step: missing mandatory forcing/state/output map");
+    if (etin ? !f->etref : (!f->tmin || !f->tmax)) SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_wb_step: missing ETref / Tmin / Tmax forcing");
+    if (snow && (!f->tmax || !s->SnowStore || !s->SnowWatStore || !s->TotalSnowStore))
+        SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_wb_step: SnowFLAG needs tmax and the three snow state maps (quirk Q3)");
+    if (ground ? (!s->GwRecharge || !s->Gw || !s->BaseR || !s->H_gw) : !s->SubDrain)
+        SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_wb_step: missing groundwater / SubDrain state map");
+    if (!etin && ra == SPHY_RA_TABLE && (!p->lat_class || !p->lat_unique_deg || p->n_lat_unique <= 0 || p->n_lat_unique > 65536))
+        SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_wb_step: RA_TABLE needs lat_class and 1..65536 unique latitudes");
+    if (!etin && ra == SPHY_RA_CELL && (!p->sin_lat || !p->cos_lat || !p->tan_lat))
+        SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_wb_step: RA_CELL needs sin/cos/tan latitude maps");
+    const bool g_any = f->GlacR || f->GlacPerc || f->SnowR_GLAC || f->TotalSnowStore_GLAC;
+    if (g_any && !(f->GlacR && f->GlacPerc && f->SnowR_GLAC && f->TotalSnowStore_GLAC))
+        SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_wb_step: glacier aggregates must be given together");
+    const void *ptrs[] = {f->prec, f->tavg, f->tmin, f->tmax, f->etref, f->TotalSnowStore_GLAC, f->SnowR_GLAC, f->GlacPerc,
+                          f->GlacR, s->RootWater, s->SubWater, s->CapRise, s->RootDrain, s->GwRecharge, s->Gw, s->BaseR,
+                          s->H_gw, s->SubDrain, s->SnowStore, s->SnowWatStore, s->TotalSnowStore, s->waterbalanceTot,
+                          o->TotR, o->RootRR, o->RootDR, o->RainR, o->SnowR, o->ETref, o->ETact, o->ActETact, o->Infil,
+                          o->Rain, o->RootPerc, o->SubPerc, o->wbal, o->ETOpenWater, p->sin_lat, p->cos_lat, p->tan_lat,
+                          p->root_field.map, p->root_sat.map, p->root_dry.map, p->root_wilt.map, p->root_ksat.map,
+                          p->root_drainvel.map, p->e_root.map, p->sub_field.map, p->sub_sat.map, p->sub_drainvel.map,
+                          p->e_sub.map, p->caprise_max.map, p->kc.map, p->pmap.map, p->glac_frac.map,
+                          p->open_water_frac.map, p->paved_frac.map, p->gw_sat.map, p->base_thresh.map, p->e_delta.map,
+                          p->e_alpha.map, p->h_den.map, p->seepage.map};
+    for (const void *q : ptrs)
+        if (q && !aligned16(q)) SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_wb_step: every map must be 16-byte aligned");
+    if (p->lat_class && (reinterpret_cast<uintptr_t>(p->lat_class) & 7u))
+        SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_wb_step: lat_class must be 8-byte aligned");
+
+    WbArgs a;
+    a.p = *p;
+    a.s = *s;
+    a.f = *f;
+    a.o = *o;
+    a.n = ctx->n;
+    a.d = day_scalars(doy, p->k0);
+    a.ra_table = nullptr;
+    if (ra == SPHY_RA_TABLE) {
+        if (ctx->ra_table_cap < p->n_lat_unique) {
+            // grows only when a larger latitude table is first seen (normally once, at the first step)
+            int rc = dev_alloc(ctx, &ctx->ra_table, (size_t)p->n_lat_unique);
+            if (rc != SPHY_OK) return rc;
+            ctx->ra_table_cap = p->n_lat_unique;
+        }
+        k_ra_table<<<div_up(p->n_lat_unique, 128), 128, 0, st>>>(p->lat_unique_deg, p->n_lat_unique, a.d, ctx->ra_table);
+        SPHY_LAUNCH_CHECK(ctx);
+        a.ra_table = ctx->ra_table;
+    }
+    const bool diag = s->waterbalanceTot || o->ETref || o->ETact || o->ActETact || o->Infil || o->Rain || o->RootPerc ||
+                      o->SubPerc || o->wbal || o->ETOpenWater;
+    const bool usoil = !(p->root_field.map || p->root_sat.map || p->root_dry.map || p->root_wilt.map || p->root_ksat.map ||
+                         p->e_root.map || p->sub_field.map || p->sub_sat.map || p->e_sub.map || p->caprise_max.map ||
+                         p->kc.map || p->gw_sat.map || p->base_thresh.map || p->e_delta.map || p->e_alpha.map ||
+                         p->h_den.map || p->seepage.map);
+    wb_kernel_t kern = snow ? (ground ? wb_pick_11(infil, ra, diag, usoil) : wb_pick_10(infil, ra, diag, usoil))
+                            : (ground ? wb_pick_01(infil, ra, diag, usoil) : wb_pick_00(infil, ra, diag, usoil));
+    if (!kern) SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_wb_step: no kernel for this switch combination");
+    const int64_t n4 = (a.n + 3) >> 2;
+    int occ = 0;
+    SPHY_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WB_THREADS, 0));
+    if (occ < 1) occ = 1;
+    int64_t want = (n4 + WB_THREADS - 1) / WB_THREADS;
+    int64_t cap = (int64_t)ctx->sm_count * occ;
+    int grid = (int)(want < cap ? (want > 0 ? want : 1) : cap);
+    kern<<<grid, WB_THREADS, 0, st>>>(a);
+    SPHY_LAUNCH_CHECK(ctx);
+    return SPHY_OK;
+}
+
+// K1 does not need the LDD: let callers that only run the water balance declare N directly
+extern "C" int sphy_set_ncells(sphy_ctx *ctx, int64_t n)
+{
+    if (!ctx || n <= 0) return SPHY_E_INVALID;
+    if (ctx->ldd_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_set_ncells after sphy_ldd_build");
+    ctx->n = n;
+    return SPHY_OK;
+}

@@ -1,0 +1,803 @@
+"""SphyModel -- host side of the B200 hot path, mirroring the reference's model object.
+
+The reference is one class `sphy(pcrm.DynamicModel)` with `__init__` (cfg + map loading,
+/root/reference/sphy.py:38-562), `initial()` (sphy.py:565-717) and `dynamic()` (sphy.py:719-1263), driven by
+`DynamicFramework.run()`.  This class keeps that contract -- same `sphy_config.cfg` switches, same state
+attribute names (`RootWater`, `SubWater`, `CapRise`, `RootDrain`, `GwRecharge`, `Gw`, `BaseR`, `H_gw`,
+`SnowStore`, `SnowWatStore`, `TotalSnowStore`, `QRAold`, `*RAold`, `StorRES`, `QFRAC`, `GlacFrac`) -- but the
+~250 PCRaster raster passes of one `dynamic()` collapse into 2-4 CUDA kernel launches through the C ABI.
+State lives in torch CUDA tensors over the N active cells (compact row-major order); torch is used for
+buffers, streams and copies only.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import configparser
+import ctypes as C
+import datetime
+import math
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import SphyParam
+
+f32 = np.float32
+COMPONENTS = ("RootR", "RootD", "Rain", "Snow", "Glac", "Base")       # modules/routing.py:53
+
+
+# ----------------------------------------------------------------------------------------------
+# map sources (the `pcr.readmap` side of the boundary)
+# ----------------------------------------------------------------------------------------------
+class MapSource:
+    """Where `readmap(inputdir + name)` gets its rasters from.  read() returns a 2-D ndarray or raises
+    FileNotFoundError (the reference's scalar-or-map idiom relies on readmap failing)."""
+
+    def read(self, name):
+        raise FileNotFoundError(name)
+
+
+class DictMapSource(MapSource):
+    def __init__(self, static_maps, forcing_fn=None, forcing_names=None):
+        self.maps = dict(static_maps)
+        self.forcing_fn = forcing_fn
+        self.forcing_names = forcing_names
+        self._cache = (None, None)
+
+    def read(self, name):
+        if name in self.maps:
+            return self.maps[name]
+        raise FileNotFoundError(name)
+
+    def read_forcing(self, prefix_key, counter):
+        """prefix_key in prec/tavg/tmin/tmax; one generator call per day is cached."""
+        if self._cache[0] != counter:
+            self._cache = (counter, self.forcing_fn(counter))
+        return self._cache[1][prefix_key]
+
+
+class CatchmentSource(DictMapSource):
+    """Feeds a synthetic `synth.Catchment` (its static maps and seeded daily forcing)."""
+
+    def __init__(self, cat):
+        super().__init__(cat.static_maps(), forcing_fn=cat.forcing)
+        self.cellsize = cat.cellsize          # the reference takes it from the clone map's CSF header
+
+
+class DirMapSource(MapSource):
+    """A directory of `<name>.npy` rasters laid out like the reference's input directory."""
+
+    def __init__(self, root):
+        self.root = root
+
+    def read(self, name):
+        path = os.path.join(self.root, name + ".npy")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        return np.load(path)
+
+    def read_forcing(self, prefix_key, counter):
+        stem = {"prec": "prec", "tavg": "tavg", "tmin": "tmin", "tmax": "tmax"}[prefix_key]
+        return self.read(os.path.join("forcings", stem + name_t(counter)))
+
+
+def name_t(t):
+    """PCRaster stack-name suffix for a 4-letter prefix: 1 -> '0000.001', 1000 -> '0001.000' (generateNameT)."""
+    s = "xxxx" + "0" * (11 - 4 - len(str(t))) + str(t)
+    return (s[:8] + "." + s[8:])[4:]
+
+
+def julian(date):
+    """utilities/timecalc.py:24-29"""
+    return date.toordinal() - datetime.date(date.year, 1, 1).toordinal() + 1
+
+
+def _read_matrix_table(path):
+    rows = []
+    with open(path) as fh:
+        for line in fh:
+            line = line.strip()
+            if line and not line.startswith("#"):
+                rows.append([float(t) for t in line.replace(",", " ").split()])
+    return rows
+
+
+def _table_col(rows, col):
+    j = [float(x) for x in rows[0][1:]].index(float(col)) + 1
+    return {int(r[0]): float(r[j]) for r in rows[1:]}
+
+
+# ----------------------------------------------------------------------------------------------
+class SphyModel:
+    def __init__(self, cfg, maps: MapSource, device="cuda:0", route_method="levels", diagnostics=False,
+                 collect_tss=True):
+        if not torch.cuda.is_available():
+            raise RuntimeError("SphyModel needs a CUDA device (B200); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        self.maps = maps
+        self.diagnostics = diagnostics
+        self.collect_tss = collect_tss
+        self.route_method = {"levels": _lib.ROUTE_LEVELS, "scan": _lib.ROUTE_SCAN}[route_method]
+        if isinstance(cfg, configparser.RawConfigParser):
+            self.config = cfg
+        else:
+            self.config = configparser.RawConfigParser()
+            if not self.config.read(cfg):
+                raise FileNotFoundError(cfg)
+        config = self.config
+        self.MV = -9999
+        # -- module switches, sphy.py:49-57,81-83
+        g = lambda k: config.getint("MODULES", k)  # noqa: E731
+        self.GlacFLAG, self.SnowFLAG, self.RoutFLAG = g("GlacFLAG"), g("SnowFLAG"), g("RoutFLAG")
+        self.ResFLAG, self.LakeFLAG, self.DynVegFLAG = g("ResFLAG"), g("LakeFLAG"), g("DynVegFLAG")
+        self.GroundFLAG, self.SedFLAG = g("GroundFLAG"), g("SedFLAG")
+        if self.GlacFLAG == 1:
+            self.SnowFLAG = 1
+            self.GroundFLAG = 1
+        for flag, what in ((self.DynVegFLAG, "dynamic vegetation"), (self.SedFLAG, "sediment")):
+            if flag:
+                raise NotImplementedError(f"{what} is outside the B200 hot path (SURVEY.md section 2)")
+        self.inpath = config.get("DIRS", "inputdir")
+        self.outpath = config.get("DIRS", "outputdir")
+        # -- timing, sphy.py:90-110
+        ti = lambda k: config.getint("TIMING", k)  # noqa: E731
+        self.startdate = datetime.datetime(ti("startyear"), ti("startmonth"), ti("startday"))
+        self.enddate = datetime.datetime(ti("endyear"), ti("endmonth"), ti("endday"))
+        self.ts1date = datetime.datetime(ti("startyear_timestep1"), ti("startmonth_timestep1"), ti("startday_timestep1"))
+        # -- clone, sphy.py:141-145
+        clone = np.asarray(self._readmap(config.get("GENERAL", "mask")))
+        self.nrows, self.ncols = clone.shape
+        self.clone_mask = clone.astype(bool)
+        self.cellsize = float(config.get("GENERAL", "cellsize")) if config.has_option("GENERAL", "cellsize") else None
+        if self.cellsize is None:
+            self.cellsize = float(getattr(maps, "cellsize", 0) or 0) or None
+        if self.cellsize is None:
+            raise ValueError("cell size unknown: give [GENERAL] cellsize in the cfg or a `cellsize` attribute on the map source")
+        self.cellArea = f32(f32(self.cellsize) * f32(self.cellsize))
+        self._ctx = C.c_void_p()
+        _lib.check(self.lib, None, self.lib.sphy_ctx_create(C.byref(self._ctx), self.device.index or 0, self.nrows,
+                                                            self.ncols, C.c_float(self.cellsize)), "sphy_ctx_create")
+        self._keep = []               # tensors referenced by raw pointers
+        self._stream = lambda: C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)  # noqa: E731
+        # -- routing structures first: they define the active cells / compact order (routing.py:33-38)
+        self._build_cells()
+        self._read_parameters()
+
+    # ------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None):
+            torch.cuda.synchronize(self.device)
+            self.lib.sphy_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        _lib.check(self.lib, self._ctx, rc, what)
+
+    def _readmap(self, name):
+        return self.maps.read(name)
+
+    def _scalar_or_map(self, section, key):
+        """`try getfloat / except readmap` (e.g. groundwater.py:51-57): float or compact device-ready ndarray."""
+        raw = self.config.get(section, key)
+        try:
+            return float(raw)
+        except ValueError:
+            return self._compact_np(self._readmap(raw))
+
+    # -- compact layout ------------------------------------------------------------------------
+    def _build_cells(self):
+        cfg = self.config
+        need_ldd = self.RoutFLAG == 1 or self.ResFLAG == 1 or self.LakeFLAG == 1
+        if need_ldd:
+            ldd = np.ascontiguousarray(self._readmap(cfg.get("ROUTING", "flowdir")), dtype=np.uint8)
+            self._ldd_host = ldd
+            ldd_d = torch.from_numpy(ldd).to(self.device)
+            act_d = torch.from_numpy(self.clone_mask.astype(np.uint8)).to(self.device)
+            self._ck(self.lib.sphy_ldd_build(self._ctx, ldd_d.data_ptr(), act_d.data_ptr(), self._stream()), "sphy_ldd_build")
+            self.n = int(self.lib.sphy_ncells(self._ctx))
+            self.nlevels = int(self.lib.sphy_nlevels(self._ctx))
+            flat = torch.empty(self.n, dtype=torch.int32, device=self.device)
+            self._ck(self.lib.sphy_ldd_export(self._ctx, b"flat_active", flat.data_ptr(), flat.numel() * 4, self._stream()),
+                     "sphy_ldd_export")
+            self.flat_active = flat.cpu().numpy().astype(np.int64)
+        else:
+            self.flat_active = np.flatnonzero(self.clone_mask.ravel())
+            self.n = int(self.flat_active.size)
+            self.nlevels = 0
+            self._ck(self.lib.sphy_set_ncells(self._ctx, self.n), "sphy_set_ncells")
+        self.full_raster = self.n == self.nrows * self.ncols
+        self._cidx_host = np.full(self.nrows * self.ncols, -1, np.int64)
+        self._cidx_host[self.flat_active] = np.arange(self.n)
+
+    def ldd_structure(self, name):
+        """Device copy of one Appendix-C structure (bit-exact parity checks)."""
+        n, L = self.n, self.nlevels
+        spec = {"cidx": (torch.int32, self.nrows * self.ncols), "down": (torch.int32, n), "indeg": (torch.uint8, n),
+                "level": (torch.int32, n), "order": (torch.int32, n), "level_ptr": (torch.int32, L + 1),
+                "don_ptr": (torch.int32, n + 1), "nup": (torch.int64, n)}
+        if name == "don_idx":
+            ptr = self.ldd_structure("don_ptr")
+            spec["don_idx"] = (torch.int32, int(ptr[-1].item()))
+        dt, cnt = spec[name]
+        out = torch.empty(max(cnt, 1), dtype=dt, device=self.device)
+        self._ck(self.lib.sphy_ldd_export(self._ctx, name.encode(), out.data_ptr(), out.numel() * out.element_size(),
+                                          self._stream()), "sphy_ldd_export")
+        return out[:cnt]
+
+    def _compact_np(self, raster, dtype=np.float32):
+        flat = np.asarray(raster).ravel()
+        if not self.full_raster:
+            flat = flat[self.flat_active]
+        return np.ascontiguousarray(flat, dtype=dtype)
+
+    def _dev(self, arr, dtype=None):
+        t = torch.from_numpy(np.ascontiguousarray(arr if dtype is None else np.asarray(arr, dtype=dtype))).to(self.device)
+        return t
+
+    def _full(self, value, dtype=torch.float32):
+        return torch.full((self.n,), float(value), dtype=dtype, device=self.device)
+
+    def to_raster(self, compact, fill=np.nan):
+        """compact device map -> (nrows, ncols) ndarray (the `report` side)."""
+        out = np.full(self.nrows * self.ncols, fill, np.float32)
+        out[self.flat_active] = compact.detach().cpu().numpy()
+        return out.reshape(self.nrows, self.ncols)
+
+    def _param(self, x):
+        """scalar-or-map -> (SphyParam, keepalive)"""
+        if isinstance(x, torch.Tensor):
+            self._keep.append(x)
+            return SphyParam(x.data_ptr(), 0.0)
+        if isinstance(x, np.ndarray):
+            if x.size and np.all(x == x.flat[0]):           # spatially uniform map: behaves as the scalar
+                return SphyParam(None, float(x.flat[0]))
+            t = self._dev(x, np.float32)
+            self._keep.append(t)
+            return SphyParam(t.data_ptr(), 0.0)
+        return SphyParam(None, float(f32(x)))
+
+    # -- parameters, sphy.py:147-458 -------------------------------------------------------------
+    def _read_parameters(self):
+        cfg = self.config
+        cn = self._compact_np
+        rd = lambda sec, key: cn(self._readmap(cfg.get(sec, key)))  # noqa: E731
+        if cfg.getint("PEDOTRANSFER", "PedotransferFLAG") == 1:
+            raise NotImplementedError("pedotransfer functions are init-time only and outside the hot path (SURVEY.md section 2)")
+        sc = lambda k: f32(cfg.getfloat("SOIL_CAL", k))  # noqa: E731
+        self.Slope = rd("GENERAL", "Slope")
+        self.Locations = cn(self._readmap(cfg.get("GENERAL", "locations")), np.int32)
+        RootFieldMap = rd("SOIL", "RootFieldMap") * sc("RootFieldFrac")                     # sphy.py:173-192
+        RootSatMap = rd("SOIL", "RootSatMap") * sc("RootSatFrac")
+        RootDryMap = rd("SOIL", "RootDryMap") * sc("RootDryFrac")
+        RootWiltMap = rd("SOIL", "RootWiltMap") * sc("RootWiltFrac")
+        self.RootKsat = rd("SOIL", "RootKsat") * sc("RootKsatFrac")
+        SubSatMap, SubFieldMap, self.SubKsat = rd("SOIL", "SubSatMap"), rd("SOIL", "SubFieldMap"), rd("SOIL", "SubKsat")
+        self.RootDrainVel = self.RootKsat * self.Slope                                        # sphy.py:198
+        for k in ("CapRiseMax", "RootDepthFlat", "SubDepthFlat"):                              # sphy.py:201-206
+            setattr(self, k, self._scalar_or_map("SOILPARS", k))
+        fl = lambda x: x if isinstance(x, np.ndarray) else f32(x)  # noqa: E731
+        self.RootField = RootFieldMap * fl(self.RootDepthFlat)                                # sphy.py:240-247
+        self.RootSat = RootSatMap * fl(self.RootDepthFlat)
+        self.RootDry = RootDryMap * fl(self.RootDepthFlat)
+        self.RootWilt = RootWiltMap * fl(self.RootDepthFlat)
+        self.SubSat = SubSatMap * fl(self.SubDepthFlat)
+        self.SubField = SubFieldMap * fl(self.SubDepthFlat)
+        with np.errstate(all="ignore"):
+            self.RootTT = np.maximum((self.RootSat - self.RootField) / self.RootKsat, f32(0.0001))
+            self.SubTT = np.maximum((self.SubSat - self.SubField) / self.SubKsat, f32(0.0001))
+            # static transcendentals, evaluated like the reference (double on the REAL4 operand, REAL4 result)
+            self._e_root = np.exp((f32(-1) / self.RootTT).astype(np.float64)).astype(np.float32)
+            self._e_sub = np.exp((f32(-1) / self.SubTT).astype(np.float64)).astype(np.float32)
+        if self.GroundFLAG == 1:                                                               # groundwater.py:51-57
+            for k in ("GwDepth", "GwSat", "deltaGw", "BaseThresh", "alphaGw", "YieldGw"):
+                setattr(self, k, self._scalar_or_map("GROUNDW_PARS", k))
+        else:
+            if cfg.get("SOILPARS", "SeepStatic").strip() in ("", "0"):
+                raise NotImplementedError("seepage map series (SeepStatic = 0) is not supported yet")
+            self.SeePage = self._scalar_or_map("SOILPARS", "SeePage")
+            self.GWL_base = self._scalar_or_map("SOILPARS", "GWL_base")
+            self.SubDrainVel = self.SubKsat * self.Slope                                      # sphy.py:237
+        # land use / crop coefficient, sphy.py:254-281
+        self.LandUse = cn(self._readmap(cfg.get("LANDUSE", "LandUse")), np.int32)
+        if cfg.getint("LANDUSE", "KCstatic") != 1:
+            raise NotImplementedError("Kc map series (KCstatic = 0) is not supported yet")
+        self.Kc = self._lookup_column_table(os.path.join(self.inpath, cfg.get("LANDUSE", "CropFac")), self.LandUse)
+        self.PlantWaterStressFLAG = cfg.getint("PWS", "PWS_FLAG")
+        self.PMap = (self._lookup_column_table(os.path.join(self.inpath, cfg.get("PWS", "PFactor")), self.LandUse)
+                     if self.PlantWaterStressFLAG == 1 else None)
+        # climate, sphy.py:305-370
+        for k in ("precNetcdfFLAG", "tempNetcdfFLAG"):
+            if cfg.has_option("CLIMATE", k) and cfg.getint("CLIMATE", k) == 1:
+                raise NotImplementedError("NetCDF forcing is outside the hot path (SURVEY.md section 2)")
+        self.Pcorr = cfg.getfloat("CLIMATE", "Pcorr_fact")
+        self.Tcorr = cfg.getfloat("CLIMATE", "Tcorr_fact")
+        self.ETREF_FLAG = cfg.getint("ETREF", "ETREF_FLAG")
+        if self.ETREF_FLAG == 0:
+            self.Lat = rd("ETREF", "Lat")
+            self.Gsc = cfg.getfloat("ETREF", "Gsc")
+        if self.SnowFLAG == 1:                                                                 # snow.py:84-90
+            for k in ("Tcrit", "SnowSC", "DDFS", "SnowF", "SnowCth"):
+                v = self._scalar_or_map("SNOW", k)
+                if isinstance(v, np.ndarray):
+                    raise NotImplementedError(f"[SNOW] {k} as a map is not supported yet")
+                setattr(self, k, v)
+            if self.ETREF_FLAG == 1:
+                raise ValueError("SnowFLAG = 1 needs ETREF_FLAG = 0: TempMax is only defined on that branch "
+                                 "(reference quirk Q3, sphy.py:788-813,875)")
+        if self.RoutFLAG == 1 or self.ResFLAG == 1 or self.LakeFLAG == 1:                      # routing.py:33-38
+            self.kx = self._scalar_or_map("ROUTING", "kx")
+        # open water, sphy.py:416-436
+        self.ETOpenWaterFLAG = cfg.getint("OPENWATER", "ETOpenWaterFLAG")
+        if self.ETOpenWaterFLAG == 1:
+            raise NotImplementedError("open-water evaporation (areatotal over clumps) is not supported yet")
+        self.openWaterFrac = None
+        # infiltration excess, sphy.py:439-458
+        self.InfilFLAG = cfg.getfloat("INFILTRATION", "Infil_excess")
+        if self.InfilFLAG == 1:
+            self.K_eff = cfg.getfloat("INFILTRATION", "K_eff")
+            self.Alpha = cfg.getfloat("INFILTRATION", "Alpha")
+            self.Labda_Infil = cfg.getfloat("INFILTRATION", "Labda_infil")
+            try:
+                self.pavedFrac = self._lookup_column_table(os.path.join(self.inpath, cfg.get("INFILTRATION", "PavedFrac")),
+                                                           self.LandUse)
+            except (OSError, configparser.Error):
+                self.pavedFrac = 0.0
+
+    def _lookup_column_table(self, path, keys):
+        """pcr.lookupscalar(table, nominal map) in column-table mode: rows `key value`."""
+        table = {}
+        with open(path) as fh:
+            for line in fh:
+                t = line.replace(",", " ").split()
+                if t and not t[0].startswith("#"):
+                    table[int(float(t[0]))] = float(t[-1])
+        out = np.full(keys.shape, np.nan, np.float32)
+        for k, v in table.items():
+            out[keys == k] = f32(v)
+        return out
+
+    # -- initial(), sphy.py:565-717 -----------------------------------------------------------------
+    def _init_value(self, section, key, default=None):
+        raw = self.config.get(section, key) if self.config.has_option(section, key) else ""
+        if not raw.strip():
+            return default
+        try:
+            return float(raw)
+        except ValueError:
+            return self._compact_np(self._readmap(raw))
+
+    def _state(self, value):
+        if isinstance(value, np.ndarray):
+            return self._dev(value, np.float32).clone()
+        return self._full(f32(value))
+
+    def initial(self):
+        cfg = self.config
+        self.counter = (self.startdate - self.ts1date).days
+        self.curdate = self.startdate
+        self.RootWater = self._state(self._init_value("SOIL_INIT", "RootWater", self.RootField))
+        self.SubWater = self._state(self._init_value("SOIL_INIT", "SubWater", self.SubField))
+        self.CapRise = self._state(self._init_value("SOIL_INIT", "CapRise"))
+        self.RootDrain = self._state(self._init_value("SOIL_INIT", "RootDrain"))
+        if self.GroundFLAG == 1:                                                               # groundwater.py:61-86
+            self.GwRecharge = self._state(self._init_value("GROUNDW_INIT", "GwRecharge"))
+            self.BaseR = self._state(self._init_value("GROUNDW_INIT", "BaseR"))
+            self.Gw = self._state(self._init_value("GROUNDW_INIT", "Gw"))
+            h0 = self._init_value("GROUNDW_INIT", "H_gw")
+            parts = (self.RootDepthFlat, self.SubDepthFlat, self.GwDepth, h0)
+            if any(isinstance(x, np.ndarray) for x in parts):
+                a = [x if isinstance(x, np.ndarray) else f32(x) for x in parts]
+                hg = np.maximum((a[0] + a[1] + a[2]) / f32(1000) - a[3], f32(0)).astype(np.float32)
+            else:
+                hg = f32(max((parts[0] + parts[1] + parts[2]) / 1000 - parts[3], 0))
+            self.H_gw = self._state(hg)
+            self.SubDrain = None
+        else:
+            self.SubDrain = self._state(self._init_value("SOIL_INIT", "SubDrain"))
+            self.BaseR = self._full(0.0)
+            self.GwRecharge = self.Gw = self.H_gw = None
+        if self.SnowFLAG == 1:                                                                 # snow.py:94-106
+            self.SnowStore = self._state(self._init_value("SNOW_INIT", "SnowIni"))
+            self.SnowWatStore = self._state(self._init_value("SNOW_INIT", "SnowWatStore"))
+            self.TotalSnowStore = self.SnowStore + self.SnowWatStore
+        else:
+            self.SnowStore = self.SnowWatStore = self.TotalSnowStore = None
+        self.GlacFrac = None
+        if self.GlacFLAG == 1:
+            self._glacier_initial()
+        self._zeros = self._full(0.0)
+        if self.RoutFLAG == 1 or self.ResFLAG == 1 or self.LakeFLAG == 1:                      # routing.py:42-66
+            self.QRAold = self._state(self._init_value("ROUT_INIT", "QRA_init", 0.0))
+            self.RA_FLAG = {}
+            for c in COMPONENTS:
+                v = self._init_value("ROUT_INIT", c + "RA_init")
+                self.RA_FLAG[c] = v is not None
+                if v is not None:
+                    setattr(self, c + "RAold", self._state(v))
+        if self.LakeFLAG == 1 or self.ResFLAG == 1:
+            self._reslake_initial()
+            for c in COMPONENTS:          # advanced_routing.initial: every component flag ends up False (quirk Q9)
+                self.RA_FLAG[c] = False
+        self.waterbalanceTot = self._full(0.0) if self.diagnostics else None
+        # per-step outputs (device maps)
+        self.TotR = self._full(0.0)
+        comp_needed = self.diagnostics or (self.RoutFLAG == 1 and any(self.RA_FLAG.values()))
+        self.RootRR = self._full(0.0) if comp_needed else None
+        self.RootDR = self._full(0.0) if comp_needed else None
+        self.RainR = self._full(0.0) if comp_needed else None
+        self.SnowR = self._full(0.0) if (comp_needed and self.SnowFLAG == 1) else None
+        self.out = {}
+        if self.diagnostics:
+            for k in ("ETref", "ETact", "ActETact", "Infil", "Rain", "RootPerc", "SubPerc", "wbal"):
+                self.out[k] = self._full(0.0)
+        self._prepare_wb_structs()
+        # time series at `Locations` (TimeoutputTimeseries, sphy.py:683-691): cells with id > 0, ordered by id
+        loc_cells = np.flatnonzero(self.Locations > 0)
+        loc_cells = loc_cells[np.argsort(self.Locations[loc_cells], kind="stable")]
+        self.station_ids = self.Locations[loc_cells]
+        self._station_cells = self._dev(loc_cells.astype(np.int32))
+        self._station_buf = torch.empty(max(len(loc_cells), 1), dtype=torch.float32, device=self.device)
+        self.tss = {"QallRAtot": []}
+        self._forcing_dev = None
+        self._forcing_host = None
+        self._fdev = None
+        self._staging = None
+        self._prof = None
+
+    # -- glacier.init + glacier.initial, modules/glacier.py:52-252 ------------------------------------
+    def _glacier_initial(self):
+        import pandas as pd
+        cfg = self.config
+        tab = pd.read_csv(os.path.join(self.inpath, cfg.get("GLACIER", "GlacTable")))
+        tab = tab.sort_values(by="MOD_ID", kind="stable").reset_index(drop=True)
+        model_id = np.asarray(self._readmap(cfg.get("GLACIER", "ModelID"))).ravel()
+        lookup = {int(v): i for i, v in enumerate(model_id)}                                   # ModelID_1d == ID
+        mod = tab["MOD_ID"].to_numpy().astype(np.int64)
+        try:
+            flat = np.array([lookup[int(m)] for m in mod], np.int64)
+        except KeyError as e:
+            raise ValueError(f"glacier table MOD_ID {e} is not present in the ModelID map") from None
+        cell = self._cidx_host[flat]
+        if (cell < 0).any():
+            raise ValueError("glacier fragment on an inactive cell")
+        uniq, first = np.unique(mod, return_index=True)
+        seg_ptr = np.concatenate([first, [len(mod)]]).astype(np.int32)
+        seg_cell = cell[first].astype(np.int32)
+        for k in ("DDFG", "DDFDG", "GlacF"):
+            v = self._scalar_or_map("GLACIER", k)
+            if isinstance(v, np.ndarray):
+                raise NotImplementedError(f"[GLACIER] {k} as a map is not supported yet")
+            setattr(self, k, v)
+        lapse = pd.read_csv(os.path.join(self.inpath, cfg.get("GLACIER", "TLapse")), header=None, index_col=0, sep=" ",
+                            skipinitialspace=True)
+        self.TLapse = lapse.iloc[:, 0].astype(float)
+        if cfg.getint("GLACIER", "GlacRetreat") == 1:
+            raise NotImplementedError("glacier retreat is a yearly table update outside the daily hot path (SURVEY.md 8f)")
+        d64 = lambda a: self._dev(np.asarray(a, np.float64))  # noqa: E731
+        n_rows = len(mod)
+        z64 = lambda: torch.zeros(n_rows, dtype=torch.float64, device=self.device)  # noqa: E731
+        G = {"cell": self._dev(cell.astype(np.int32)), "seg_ptr": self._dev(seg_ptr), "seg_cell": self._dev(seg_cell),
+             "MOD_H": d64(tab["MOD_H"]), "GLAC_H": d64(tab["GLAC_H"]), "FRAC_GLAC": d64(tab["FRAC_GLAC"]),
+             "DEBRIS": self._dev((tab["DEBRIS"].to_numpy() != 0).astype(np.uint8))}
+        for k in ("Rain_GLAC", "Snow_GLAC", "AccuGlacMelt", "GlacMelt", "GlacR", "GlacPerc", "SnowR_GLAC",
+                  "ActSnowMelt_GLAC", "GLAC_T"):
+            G[k] = z64()
+        snow0 = self.SnowStore.cpu().numpy()[cell].astype(np.float64)                          # glacier.py:161-184
+        wat0 = self.SnowWatStore.cpu().numpy()[cell].astype(np.float64)
+        G["SnowStore_GLAC"], G["SnowWatStore_GLAC"] = d64(snow0), d64(wat0)
+        G["TotalSnowStore_GLAC"] = d64(snow0 + wat0)
+        self.GlacTable = G
+        self._glac_n = (n_rows, len(uniq))
+        gf = np.zeros(self.n, np.float64)                                                      # glacier.py:188-196
+        np.add.at(gf, cell, tab["FRAC_GLAC"].to_numpy().astype(np.float64))
+        self.GlacFrac = self._dev(gf.astype(np.float32))
+        self._glac_agg = {k: self._full(0.0) for k in ("Rain_GLAC", "Snow_GLAC", "ActSnowMelt_GLAC",
+                                                       "TotalSnowStore_GLAC", "SnowR_GLAC", "GlacMelt", "GlacR", "GlacPerc")}
+        self.GlacR = self._glac_agg["GlacR"]
+        self.TotalSnowStore_GLAC = self._glac_agg["TotalSnowStore_GLAC"]
+
+    # -- lakes.init/initial, reservoirs.init/initial, modules/lakes.py:162-224, reservoirs.py:90-162 ---
+    def _reslake_initial(self):
+        cfg = self.config
+        n = self.n
+        res_id = np.zeros(n, np.int32)
+        lake_id = np.zeros(n, np.int32)
+        stor = np.zeros(n, np.float32)
+        million = f32(10 ** 6)
+        rows = {}                                   # cell -> parameter column
+        if self.LakeFLAG == 1:
+            lake_id = np.maximum(self._compact_np(self._readmap(cfg.get("LAKE", "LakeId")), np.int32), 0)
+            T = {k: _read_matrix_table(os.path.join(self.inpath, cfg.get("LAKE", k)))
+                 for k in ("LakeStor", "LakeFunc", "LakeQH", "LakeSH", "LakeHS")}
+            st = _table_col(T["LakeStor"], 1)
+            for c in np.flatnonzero(lake_id > 0):
+                lid = int(lake_id[c])
+                stor[c] = f32(st.get(lid, 0.0)) * million                                     # lakes.py:220-222
+                col = np.full(_lib.RL_NPAR, np.nan, np.float32)
+                col[9] = _table_col(T["LakeFunc"], 3).get(lid, np.nan)                         # HS func
+                for j in range(6):
+                    col[10 + j] = _table_col(T["LakeHS"], j + 1).get(lid, np.nan)              # exp_a exp_b pol_b a1 a2 a3
+                col[16] = _table_col(T["LakeFunc"], 1).get(lid, np.nan)                        # QH func
+                qh = [_table_col(T["LakeQH"], j + 1).get(lid, np.nan) for j in range(6)]
+                col[17], col[18], col[19], col[20], col[21], col[22] = qh
+                rows[int(c)] = (3, col)
+            if cfg.has_option("LAKE", "updatelakelevel") and cfg.get("LAKE", "updatelakelevel").strip():
+                try:
+                    self._readmap(cfg.get("LAKE", "updatelakelevel"))
+                    raise NotImplementedError("assimilation of measured lake levels is not supported yet")
+                except FileNotFoundError:
+                    pass
+        if self.ResFLAG == 1:
+            res_id = np.maximum(self._compact_np(self._readmap(cfg.get("RESERVOIR", "ResId")), np.int32), 0)
+            fs = _read_matrix_table(os.path.join(self.inpath, cfg.get("RESERVOIR", "ResFuncStor")))
+            func, st = _table_col(fs, 1), _table_col(fs, 2)
+            simple = adv = None
+            if cfg.has_option("RESERVOIR", "ResSimple") and cfg.get("RESERVOIR", "ResSimple").strip():
+                simple = _read_matrix_table(os.path.join(self.inpath, cfg.get("RESERVOIR", "ResSimple")))
+            if cfg.has_option("RESERVOIR", "ResAdv") and cfg.get("RESERVOIR", "ResAdv").strip():
+                adv = _read_matrix_table(os.path.join(self.inpath, cfg.get("RESERVOIR", "ResAdv")))
+            for c in np.flatnonzero(res_id > 0):
+                rid = int(res_id[c])
+                stor[c] = stor[c] + f32(st.get(rid, 0.0)) * million                           # reservoirs.py:152-156
+                col = np.full(_lib.RL_NPAR, np.nan, np.float32)
+                fn = int(func.get(rid, 0))
+                kind = 0
+                if fn == 1 and simple is not None:
+                    kind = 1
+                    col[0] = _table_col(simple, 1).get(rid, np.nan)
+                    col[1] = _table_col(simple, 2).get(rid, np.nan)
+                    col[2] = f32(_table_col(simple, 3).get(rid, np.nan)) * million
+                elif fn == 2 and adv is not None:
+                    kind = 2
+                    for j in range(4):
+                        col[3 + j] = f32(_table_col(adv, j + 1).get(rid, np.nan)) * million
+                    col[7] = _table_col(adv, 5).get(rid, np.nan)
+                    col[8] = _table_col(adv, 6).get(rid, np.nan)
+                rows[int(c)] = (kind, col)                                                    # ResID != 0 wins over LakeID
+        cells = np.array(sorted(rows), np.int32)
+        ns = len(cells)
+        par = np.full((_lib.RL_NPAR, max(ns, 1)), np.nan, np.float32)
+        kind = np.zeros(max(ns, 1), np.int32)
+        for j, c in enumerate(cells):
+            kind[j], par[:, j] = rows[int(c)]
+        qfrac = np.ones(n, np.float32)
+        qfrac[cells] = 0.0
+        self.QFRAC = self._dev(qfrac)
+        self._rl_cells_host = cells
+        self._rl = {"cell": self._dev(cells if ns else np.zeros(1, np.int32)), "kind": self._dev(kind), "par": self._dev(par),
+                    "StorRES": self._dev(stor[cells] if ns else np.zeros(1, np.float32)),
+                    "Qout": torch.zeros(max(ns, 1), dtype=torch.float32, device=self.device),
+                    "Qin": torch.zeros(max(ns, 1), dtype=torch.float32, device=self.device)}
+        r = self._rl
+        self._rl_struct = _lib.ResLake(ns, r["cell"].data_ptr(), r["kind"].data_ptr(), r["par"].data_ptr(),
+                                       self.QFRAC.data_ptr(), r["StorRES"].data_ptr(), r["Qout"].data_ptr(), r["Qin"].data_ptr())
+
+    @property
+    def StorRES(self):
+        """Dense view of the lake/reservoir storage map (reference attribute name), m3."""
+        out = torch.zeros(self.n, dtype=torch.float32, device=self.device)
+        if len(self._rl_cells_host):
+            out[torch.from_numpy(self._rl_cells_host.astype(np.int64)).to(self.device)] = self._rl["StorRES"]
+        return out
+
+    # -- kernel argument structs ---------------------------------------------------------------------
+    def _prepare_wb_structs(self):
+        P = _lib.WbParams()
+        flags = 0
+        if self.SnowFLAG == 1:
+            flags |= _lib.WB_SNOW
+        if self.GroundFLAG == 1:
+            flags |= _lib.WB_GROUND
+        if self.InfilFLAG == 1:
+            flags |= _lib.WB_INFIL_EXCESS
+        if self.PlantWaterStressFLAG == 1:
+            flags |= _lib.WB_PWS
+        if self.ETREF_FLAG == 1:
+            flags |= _lib.WB_ETREF_INPUT
+        P.flags = flags
+        if self.ETREF_FLAG == 0:
+            uniq, inv = np.unique(self.Lat, return_inverse=True)
+            if len(uniq) <= 65536:
+                P.ra_mode = _lib.RA_TABLE
+                self._lat_class = self._dev(inv.astype(np.uint16))
+                self._lat_unique = self._dev(uniq.astype(np.float32))
+                P.lat_class, P.lat_unique_deg, P.n_lat_unique = self._lat_class.data_ptr(), self._lat_unique.data_ptr(), len(uniq)
+            else:
+                P.ra_mode = _lib.RA_CELL
+                lat_d = self._dev(self.Lat)
+                self._lat_trig = [torch.empty_like(lat_d) for _ in range(3)]
+                for op, t in zip((_lib.UNARY_SIN_DEG, _lib.UNARY_COS_DEG, _lib.UNARY_TAN_DEG), self._lat_trig):
+                    self._ck(self.lib.sphy_map_unary(self._ctx, op, lat_d.data_ptr(), t.data_ptr(), self.n, self._stream()),
+                             "sphy_map_unary")
+                P.sin_lat, P.cos_lat, P.tan_lat = (t.data_ptr() for t in self._lat_trig)
+            P.k0 = float(f32(((24 * 60) / math.pi) * self.Gsc))                              # hargreaves.py:32-33
+        P.pcorr, P.tcorr = float(f32(self.Pcorr)), float(f32(self.Tcorr))
+        pr = self._param
+        P.root_field, P.root_sat, P.root_dry, P.root_wilt = pr(self.RootField), pr(self.RootSat), pr(self.RootDry), pr(self.RootWilt)
+        P.root_ksat, P.root_drainvel, P.e_root = pr(self.RootKsat), pr(self.RootDrainVel), pr(self._e_root)
+        P.sub_field, P.sub_sat, P.e_sub = pr(self.SubField), pr(self.SubSat), pr(self._e_sub)
+        P.caprise_max, P.kc = pr(self.CapRiseMax), pr(self.Kc)
+        if self.PMap is not None:
+            P.pmap = pr(self.PMap)
+        if self.GlacFrac is not None:
+            P.glac_frac = SphyParam(self.GlacFrac.data_ptr(), 0.0)
+        if self.InfilFLAG == 1:
+            P.k_eff, P.alpha = float(f32(self.K_eff)), float(f32(self.Alpha))
+            P.alpha_sq, P.labda_infil = float(f32(self.Alpha ** 2)), float(f32(self.Labda_Infil))
+            P.paved_frac = pr(self.pavedFrac)
+        dbl_exp = lambda x: np.exp(np.asarray(x, np.float32).astype(np.float64)).astype(np.float32)  # noqa: E731
+        if self.GroundFLAG == 1:
+            P.gw_sat, P.base_thresh = pr(self.GwSat), pr(self.BaseThresh)
+            dg, ag, yg = self.deltaGw, self.alphaGw, self.YieldGw
+            # exp(-1/deltaGw): `-1/deltaGw` is a Python double when deltaGw is a cfg float (groundwater.py:27)
+            e_delta = dbl_exp(f32(-1) / dg) if isinstance(dg, np.ndarray) else dbl_exp(-1 / dg)
+            e_alpha = dbl_exp(-ag)
+            if isinstance(yg, np.ndarray) or isinstance(ag, np.ndarray):
+                fl = lambda x: x if isinstance(x, np.ndarray) else f32(x)  # noqa: E731
+                h_den = f32(800) * fl(yg) * fl(ag)
+            else:
+                h_den = f32(800 * yg * ag)                                                     # groundwater.py:45
+            P.e_delta, P.e_alpha, P.h_den = pr(e_delta), pr(e_alpha), pr(h_den)
+        else:
+            P.seepage, P.sub_drainvel = pr(self.SeePage), pr(self.SubDrainVel)
+        if self.SnowFLAG == 1:
+            P.tcrit, P.snow_sc, P.ddfs = float(f32(self.Tcrit)), float(f32(self.SnowSC)), float(f32(self.DDFS))
+            P.snow_f, P.one_minus_snow_f = float(f32(self.SnowF)), float(f32(1 - self.SnowF))
+            for h in range(1, 25):                                                             # snow.py:30 (3.1415)
+                P.melt_cos[h - 1] = float(f32(math.cos(float(f32(3.1415 * h / 12)))))
+        self._wbP = P
+        ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+        S = _lib.WbState()
+        for k in ("RootWater", "SubWater", "CapRise", "RootDrain", "GwRecharge", "Gw", "BaseR", "H_gw", "SubDrain",
+                  "SnowStore", "SnowWatStore", "TotalSnowStore", "waterbalanceTot"):
+            setattr(S, k, ptr(getattr(self, k)))
+        if self.GroundFLAG != 1:
+            S.BaseR = None
+        self._wbS = S
+        O = _lib.WbOut()
+        O.TotR = self.TotR.data_ptr()
+        for k in ("RootRR", "RootDR", "RainR", "SnowR"):
+            setattr(O, k, ptr(getattr(self, k)))
+        for k, t in self.out.items():
+            setattr(O, k, t.data_ptr())
+        self._wbO = O
+        if self.GlacFLAG == 1:
+            G = self.GlacTable
+            t = _lib.GlacTable()
+            t.n_rows, t.n_seg = self._glac_n
+            for k in ("cell", "seg_ptr", "seg_cell", "MOD_H", "GLAC_H", "FRAC_GLAC", "DEBRIS", "Rain_GLAC", "Snow_GLAC",
+                      "SnowStore_GLAC", "SnowWatStore_GLAC", "TotalSnowStore_GLAC", "AccuGlacMelt", "GlacMelt", "GlacR",
+                      "GlacPerc", "SnowR_GLAC", "ActSnowMelt_GLAC", "GLAC_T"):
+                setattr(t, k, G[k].data_ptr())
+            t.tcrit, t.ddfs, t.snow_sc = self.Tcrit, self.DDFS, self.SnowSC
+            t.ddfg, t.ddfdg, t.glac_f = self.DDFG, self.DDFDG, self.GlacF
+            self._glT = t
+            o = _lib.GlacOut()
+            for k, v in self._glac_agg.items():
+                setattr(o, k, v.data_ptr())
+            self._glO = o
+        if self.RoutFLAG == 1 or self.ResFLAG == 1 or self.LakeFLAG == 1:
+            self._kx = pr(self.kx)
+            if self._kx.map:
+                self._one_m_kx = 0.0                       # per-cell 1 - kx is formed in the kernel (REAL4)
+            elif isinstance(self.kx, np.ndarray):          # spatially uniform map: `1 - kx` was a REAL4 map operation
+                self._one_m_kx = float(f32(1) - f32(self._kx.value))
+            else:                                          # cfg float: Python-double subtraction, then REAL4 (routing.py:28)
+                self._one_m_kx = float(f32(1 - self.kx))
+
+    # -- forcing ---------------------------------------------------------------------------------------
+    def set_device_forcing(self, fn):
+        """fn(counter) -> dict of compact float32 CUDA tensors (prec, tavg, tmin, tmax[, etref]) already resident in HBM."""
+        self._forcing_dev = fn
+
+    def set_host_forcing(self, fn):
+        """fn(counter) -> dict of compact float32 PINNED host tensors; each step copies them host->device."""
+        self._forcing_host = fn
+
+    def enable_profiling(self, on=True):
+        """Record CUDA events around the water-balance and routing launches of every dynamic() call."""
+        self._prof = {"wb": [], "route": []} if on else None
+
+    def _ingest(self, counter):
+        if self._forcing_dev is not None:
+            return self._forcing_dev(counter)
+        keys = ("prec", "tavg", "etref") if self.ETREF_FLAG == 1 else ("prec", "tavg", "tmin", "tmax")
+        if getattr(self, "_forcing_host", None) is not None:
+            if getattr(self, "_fdev", None) is None:
+                self._fdev = {k: torch.empty(self.n, dtype=torch.float32, device=self.device) for k in keys}
+            host = self._forcing_host(counter)
+            for k in keys:
+                self._fdev[k].copy_(host[k], non_blocking=True)
+            return self._fdev
+        if self._staging is None:
+            self._staging = {k: torch.empty(self.n, dtype=torch.float32).pin_memory() for k in keys}
+        if self._fdev is None:
+            self._fdev = {k: torch.empty(self.n, dtype=torch.float32, device=self.device) for k in keys}
+        for k in keys:
+            raster = self.maps.read_forcing(k, counter)
+            src = np.asarray(raster, np.float32).ravel()
+            self._staging[k].numpy()[:] = src if self.full_raster else src[self.flat_active]
+            self._fdev[k].copy_(self._staging[k], non_blocking=True)
+        return self._fdev
+
+    # -- dynamic(), sphy.py:719-1263 ------------------------------------------------------------------------
+    def dynamic(self):
+        self.counter += 1
+        lib, ctx, st = self.lib, self._ctx, self._stream()
+        f = self._ingest(self.counter)
+        F = _lib.WbForcing()
+        F.prec, F.tavg = f["prec"].data_ptr(), f["tavg"].data_ptr()
+        if self.ETREF_FLAG == 1:
+            F.etref = f["etref"].data_ptr()
+        else:
+            F.tmin, F.tmax = f["tmin"].data_ptr(), f["tmax"].data_ptr()
+        doy = julian(self.curdate)
+        if self.GlacFLAG == 1:                                                                 # sphy.py:843-853
+            self._glT.lapse = float(self.TLapse.at[self.curdate.month])
+            self._ck(lib.sphy_glac_step(ctx, C.byref(self._glT), f["tavg"].data_ptr(), f["prec"].data_ptr(),
+                                        C.c_float(self._wbP.tcorr), C.c_float(self._wbP.pcorr), C.byref(self._glO), st),
+                     "sphy_glac_step")
+            a = self._glac_agg
+            F.TotalSnowStore_GLAC, F.SnowR_GLAC = a["TotalSnowStore_GLAC"].data_ptr(), a["SnowR_GLAC"].data_ptr()
+            F.GlacPerc, F.GlacR = a["GlacPerc"].data_ptr(), a["GlacR"].data_ptr()
+        prof = self._prof
+        if prof is not None:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
+        self._ck(lib.sphy_wb_step(ctx, C.byref(self._wbP), C.byref(self._wbS), C.byref(F), C.byref(self._wbO), doy, st),
+                 "sphy_wb_step")
+        if prof is not None:
+            ev[1].record()
+        self.Q = None
+        if self.LakeFLAG == 1 or self.ResFLAG == 1:                                            # sphy.py:1100-1104
+            self._ck(lib.sphy_route_reslake_step(ctx, C.byref(self._rl_struct), self.TotR.data_ptr(), self.QRAold.data_ptr(),
+                                                 self._kx, C.c_float(self._one_m_kx), doy, st), "sphy_route_reslake_step")
+            self.Q = self.QRAold
+        elif self.RoutFLAG == 1:                                                               # sphy.py:1107-1108
+            src = [self.TotR]
+            dst = [self.QRAold]
+            comp_src = {"RootR": self.RootRR, "RootD": self.RootDR, "Rain": self.RainR,
+                        "Snow": self.SnowR if self.SnowR is not None else self._zeros,
+                        "Glac": self.GlacR if self.GlacFLAG == 1 else self._zeros,
+                        "Base": self.BaseR if self.GroundFLAG == 1 else self.SubDrain}          # sphy.py:1085
+            for c in COMPONENTS:
+                if self.RA_FLAG[c]:
+                    src.append(comp_src[c])
+                    dst.append(getattr(self, c + "RAold"))
+            nc = len(src)
+            srcp = (C.c_void_p * nc)(*[t.data_ptr() for t in src])
+            dstp = (C.c_void_p * nc)(*[t.data_ptr() for t in dst])
+            self._ck(lib.sphy_route_step(ctx, nc, srcp, dstp, self._kx, C.c_float(self._one_m_kx), self.route_method, st),
+                     "sphy_route_step")
+            self.Q = self.QRAold
+        if prof is not None:
+            ev[2].record()
+            prof["wb"].append((ev[0], ev[1]))
+            prof["route"].append((ev[1], ev[2]))
+        if self.collect_tss and self.Q is not None and len(self.station_ids):
+            self._ck(lib.sphy_sample(ctx, self.Q.data_ptr(), self._station_cells.data_ptr(), len(self.station_ids),
+                                     self._station_buf.data_ptr(), st), "sphy_sample")
+            self.tss["QallRAtot"].append(self._station_buf[: len(self.station_ids)].clone())
+        self.curdate = self.curdate + datetime.timedelta(days=1)
+        return self.Q if self.Q is not None else self.TotR
+
+    def timesteps(self):
+        """utilities/timecalc.py:32-36"""
+        return (self.enddate - self.startdate).days + 1
+
+    def run(self, nsteps=None):
+        """DynamicFramework(model, lastTimeStep, firstTimestep=1).run(): initial() once, then dynamic() per step."""
+        self.initial()
+        for _ in range(nsteps or self.timesteps()):
+            self.dynamic()
+        torch.cuda.synchronize(self.device)
+        return self

@@ -449,11 +449,13 @@ def make_catchment(nrows, ncols, cellsize=250.0, seed=1, nsteps=365, snow=False,
     nup = upstream_counts(ldd)
     # stations: the outlet(s) with the largest upstream area + a few interior cells
     locations = np.zeros((nrows, ncols), np.int32)
-    flat = np.argsort(nup.ravel())[::-1]
-    picks = [flat[0]]
-    for q in (0.999, 0.99, 0.9):
-        picks.append(flat[int((1 - q) * flat.size)])
-    for k, g in enumerate(dict.fromkeys(int(x) for x in picks)):
+    nflat = nup.ravel()
+    picks = [int(np.argmax(nflat))]
+    for frac in (0.1, 0.01, 0.001):               # first cell (row-major) draining at least that share of the raster
+        hit = np.flatnonzero(nflat >= max(2, int(frac * nflat.size)))
+        if hit.size:
+            picks.append(int(hit[0]))
+    for k, g in enumerate(dict.fromkeys(picks)):
         locations.ravel()[g] = k + 1
     cat = Catchment(nrows=nrows, ncols=ncols, cellsize=float(cellsize), seed=seed, dem=raw, ldd=ldd, slope=slope,
                     lat=lat, flags=flags, params=p, start=start, nsteps=nsteps, locations=locations,
