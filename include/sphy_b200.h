@@ -180,6 +180,9 @@ int sphy_glac_step(sphy_ctx *ctx, const sphy_glac_table *t, const float *tavg, c
 int sphy_route_step(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm, float *const *q_state, sphy_param kx,
                     float one_minus_kx /* REAL4(1-kx) when kx is a scalar: Python-double subtraction, routing.py:28 */,
                     int method, void *stream);
+/* DFS pre-order structures of the SPHY_ROUTE_SCAN path, for tests: "pre" (cell -> rank), "pre_cell" (rank -> cell),
+ * "sub_size" (by rank); each int32 x N.  Builds the layout on first use. */
+int sphy_scan_export(sphy_ctx *ctx, const char *name, void *dst_dev, size_t dst_bytes, void *stream);
 /* plain pcr.accuflux(ldd, m) / pcr.catchmenttotal(m, ldd) (sphy.py:838, routing.py:27) and pcr.upstream */
 int sphy_accuflux(sphy_ctx *ctx, const float *material, const float *fraction /*nullable*/, float *flux, int method,
                   void *stream);

@@ -96,6 +96,7 @@ SYMBOLS = {
                                C.c_int, P]),
     "sphy_glac_step": (C.c_int, [P, C.POINTER(GlacTable), P, P, C.c_float, C.c_float, C.POINTER(GlacOut), P]),
     "sphy_route_step": (C.c_int, [P, C.c_int, C.POINTER(P), C.POINTER(P), SphyParam, C.c_float, C.c_int, P]),
+    "sphy_scan_export": (C.c_int, [P, C.c_char_p, P, C.c_size_t, P]),
     "sphy_accuflux": (C.c_int, [P, P, P, P, C.c_int, P]),
     "sphy_upstream": (C.c_int, [P, P, P, P]),
     "sphy_route_reslake_step": (C.c_int, [P, C.POINTER(ResLake), P, P, SphyParam, C.c_float, C.c_int, P]),

@@ -42,6 +42,7 @@ struct sphy_ctx {
     double *scan_local = nullptr;  // [ncomp_max][n] tile-local inclusive prefix sums (by rank)
     double *scan_tile = nullptr;   // [ncomp_max][ntiles+1] exclusive prefix of tile totals
     int32_t n_tiles = 0;
+    int scan_comp_cap = 0;
     unsigned int *scan_flags = nullptr;
     // workspaces
     float *acc = nullptr;          // [ROUTE_MAX_COMP][n] accumulated flux in routing order

@@ -1,0 +1,95 @@
+"""GPU: the SPHY_ROUTE_SCAN path (DFS pre-order + float64 prefix sums) vs the oracle and vs the level sweep.
+Tolerance 1e-5 relative (north_star): float64 range sums have no per-cell REAL4 rounding along the flow path,
+so this path is close to, not bit-identical with, the REAL4-per-cell oracle; the float64 oracle brackets it."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _ctx(lib, torch, ldd, cellsize):
+    from sphy_b200 import _lib
+    ctx = C.c_void_p()
+    _lib.check(lib, None, lib.sphy_ctx_create(C.byref(ctx), 0, ldd.shape[0], ldd.shape[1], C.c_float(cellsize)), "create")
+    ldd_d = torch.from_numpy(np.ascontiguousarray(ldd, np.uint8)).cuda()
+    _lib.check(lib, ctx, lib.sphy_ldd_build(ctx, ldd_d.data_ptr(), None, None), "ldd_build")
+    return ctx
+
+
+@pytest.mark.parametrize("shape,outlets,seed", [((9, 7), "single", 1), ((120, 90), "border", 2), ((700, 900), "single", 3)])
+def test_preorder_is_a_valid_dfs_numbering(shape, outlets, seed):
+    import torch
+    from oracle.ldd_oracle import LddStruct
+    from sphy_b200 import _lib, synth
+    lib = _lib.load()
+    _, _, ldd, _ = synth.make_dem_ldd(shape[0], shape[1], 100.0, seed=seed, outlets=outlets)
+    st = LddStruct(ldd)
+    ctx = _ctx(lib, torch, ldd, 100.0)
+    n = st.n
+    got = {}
+    for name in ("pre", "pre_cell", "sub_size"):
+        t = torch.empty(n, dtype=torch.int32, device="cuda")
+        _lib.check(lib, ctx, lib.sphy_scan_export(ctx, name.encode(), t.data_ptr(), n * 4, None), name)
+        torch.cuda.synchronize()
+        got[name] = t.cpu().numpy().astype(np.int64)
+    pre, pre_cell, size = got["pre"], got["pre_cell"], got["sub_size"]
+    assert np.array_equal(np.sort(pre), np.arange(n))                       # a permutation
+    assert np.array_equal(pre_cell[pre], np.arange(n))                      # inverse
+    assert np.array_equal(size[pre], st.nup)                                # subtree sizes = upstream counts
+    has_down = st.down >= 0
+    d = st.down[has_down]
+    i = np.flatnonzero(has_down)
+    assert (pre[i] > pre[d]).all()                                          # parent first
+    assert (pre[i] + st.nup[i] <= pre[d] + st.nup[d]).all()                 # child range nested in the parent's
+    lib.sphy_ctx_destroy(ctx)
+
+
+@pytest.mark.parametrize("shape,ncomp,kxmap,seed", [((60, 50), 1, False, 1), ((400, 300), 3, False, 2), ((900, 1100), 2, True, 3)])
+def test_scan_routing_matches_oracle(shape, ncomp, kxmap, seed):
+    import torch
+    from oracle.ldd_oracle import LddStruct
+    from sphy_b200 import _lib, synth
+    lib = _lib.load()
+    cellsize = 250.0
+    _, _, ldd, _ = synth.make_dem_ldd(shape[0], shape[1], cellsize, seed=seed, outlets="single")
+    st = LddStruct(ldd)
+    n = st.n
+    ctx = _ctx(lib, torch, ldd, cellsize)
+    rng = np.random.default_rng(seed)
+    kx_np = (0.9 + 0.09 * rng.random(n)).astype(np.float32) if kxmap else None
+    kx_d = torch.from_numpy(kx_np).cuda() if kxmap else None
+    kx = _lib.SphyParam(kx_d.data_ptr() if kxmap else None, 0.971)
+    one_m = float(np.float32(1 - 0.971))
+    area = np.float32(cellsize) * np.float32(cellsize)
+    q_lv = [torch.zeros(n, device="cuda") for _ in range(ncomp)]
+    q_sc = [torch.zeros(n, device="cuda") for _ in range(ncomp)]
+    q_or = [np.zeros(n, np.float32) for _ in range(ncomp)]
+    q_64 = [np.zeros(n, np.float64) for _ in range(ncomp)]
+    for step in range(4):
+        mm = [(rng.gamma(0.8, 4.0, n) * (rng.random(n) < 0.7)).astype(np.float32) for _ in range(ncomp)]
+        mm_d = [torch.from_numpy(m).cuda() for m in mm]
+        src = (C.c_void_p * ncomp)(*[t.data_ptr() for t in mm_d])
+        for q, method in ((q_lv, _lib.ROUTE_LEVELS), (q_sc, _lib.ROUTE_SCAN)):
+            dst = (C.c_void_p * ncomp)(*[t.data_ptr() for t in q])
+            _lib.check(lib, ctx, lib.sphy_route_step(ctx, ncomp, src, dst, kx, C.c_float(one_m), method, None), "route")
+        torch.cuda.synchronize()
+        for c in range(ncomp):
+            rr = (mm[c] * np.float32(0.001) * area) / np.float32(86400)
+            ra = st.accuflux(rr)
+            ra64 = st.accuflux_f64(rr)
+            if kxmap:
+                q_or[c] = (np.float32(1) - kx_np) * ra + kx_np * q_or[c]
+                q_64[c] = (1.0 - kx_np.astype(np.float64)) * ra64 + kx_np.astype(np.float64) * q_64[c]
+            else:
+                q_or[c] = np.float32(one_m) * ra + np.float32(0.971) * q_or[c]
+                q_64[c] = float(np.float32(one_m)) * ra64 + float(np.float32(0.971)) * q_64[c]
+            lv = q_lv[c].cpu().numpy()
+            sc = q_sc[c].cpu().numpy().astype(np.float64)
+            assert np.array_equal(lv.view(np.int32), q_or[c].view(np.int32)), "level sweep must stay bit-exact"
+            tol = 1e-5 * np.abs(q_or[c]) + 1e-12
+            assert (np.abs(sc - q_or[c]) <= tol).all(), f"step {step} comp {c}: scan vs REAL4 oracle {np.max(np.abs(sc - q_or[c]) / (np.abs(q_or[c]) + 1e-30)):.2e}"
+            # the scan path must be at least as close to the float64 oracle as 1e-6 relative
+            assert (np.abs(sc - q_64[c]) <= 2e-6 * np.abs(q_64[c]) + 1e-12).all()
+    lib.sphy_ctx_destroy(ctx)
