@@ -55,11 +55,22 @@ size_t sphy_abi_sizeof(int which);
  * modules/routing.py:34.  ldd_dev: nrows*ncols keypad codes (1-9, 5 = pit, anything else = MV);
  * active_dev: optional nrows*ncols mask (clone, sphy.py:143).  Synchronises the stream (one-time build). */
 int sphy_ldd_build(sphy_ctx *ctx, const uint8_t *ldd_dev, const uint8_t *active_dev, void *stream);
+/* Order of the N cells in every compact map (call before sphy_ldd_build).  ROWMAJOR = the canonical compact
+ * numbering; DFS (default) = depth-first pre-order of the drainage forest, so that a cell's upstream area is the
+ * contiguous index range [j, j + sub_size[j]) -- what SPHY_ROUTE_SCAN streams over.  The water balance is per-cell
+ * and indifferent to the order; raster <-> compact conversion goes through sphy_gather_f32 / sphy_scatter_f32 or
+ * the "flat_active" export (device index -> raster index). */
+#define SPHY_ORDER_ROWMAJOR 0
+#define SPHY_ORDER_DFS 1
+int sphy_set_cell_order(sphy_ctx *ctx, int mode);
 int64_t sphy_ncells(const sphy_ctx *ctx);
 int32_t sphy_nlevels(const sphy_ctx *ctx);
-/* copy one structure to a caller device buffer for bit-exact checks.  name / element type / count:
+/* copy one structure to a caller device buffer for bit-exact checks.  name / element type / count
+ * (canonical compact row-major numbering, SURVEY.md Appendix C, whatever the device cell order is):
  *   "cidx" i32 nrows*ncols | "down" i32 N | "indeg" u8 N | "level" i32 N | "order" i32 N |
- *   "level_ptr" i32 L+1 | "don_ptr" i32 N+1 | "don_idx" i32 don_ptr[N] | "nup" i64 N */
+ *   "level_ptr" i32 L+1 | "don_ptr" i32 N+1 | "don_idx" i32 don_ptr[N] | "nup" i64 N
+ * and the device-order maps: "flat_active" i32 N (device index -> raster index), "cell_order" i32 N (device
+ * index -> canonical index), "sub_size" i32 N (upstream cell count by device index) */
 int sphy_ldd_export(sphy_ctx *ctx, const char *name, void *dst_dev, size_t dst_bytes, void *stream);
 
 /* raster <-> compact (readmap / report side of the boundary): out[k] = raster[cell k] and back */
@@ -174,15 +185,12 @@ int sphy_glac_step(sphy_ctx *ctx, const sphy_glac_table *t, const float *tavg, c
  *   Q = (1-kx) * accuflux(ldd, q*0.001*cellarea/86400) + kx*Qold   for ncomp runoff maps sharing one sweep.
  * runoff_mm[c]: N-cell map [mm/day]; q_state[c]: Qold in, Q out (N cells, compact order).
  * method: SPHY_ROUTE_LEVELS = level-by-level sweep, per-cell REAL8 sum stored REAL4 (bit-exact with the
- * oracle); SPHY_ROUTE_SCAN = subtree ranges over a DFS pre-order + float64 prefix sums. */
+ * oracle); SPHY_ROUTE_SCAN = subtree index ranges + float64 prefix sums (needs SPHY_ORDER_DFS). */
 #define SPHY_ROUTE_LEVELS 0
 #define SPHY_ROUTE_SCAN 1
 int sphy_route_step(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm, float *const *q_state, sphy_param kx,
                     float one_minus_kx /* REAL4(1-kx) when kx is a scalar: Python-double subtraction, routing.py:28 */,
                     int method, void *stream);
-/* DFS pre-order structures of the SPHY_ROUTE_SCAN path, for tests: "pre" (cell -> rank), "pre_cell" (rank -> cell),
- * "sub_size" (by rank); each int32 x N.  Builds the layout on first use. */
-int sphy_scan_export(sphy_ctx *ctx, const char *name, void *dst_dev, size_t dst_bytes, void *stream);
 /* plain pcr.accuflux(ldd, m) / pcr.catchmenttotal(m, ldd) (sphy.py:838, routing.py:27) and pcr.upstream */
 int sphy_accuflux(sphy_ctx *ctx, const float *material, const float *fraction /*nullable*/, float *flux, int method,
                   void *stream);

@@ -74,6 +74,7 @@ RL_NPAR = 23
 WB_SNOW, WB_GROUND, WB_INFIL_EXCESS, WB_PWS, WB_ETREF_INPUT = 1, 2, 4, 8, 16
 RA_TABLE, RA_CELL = 0, 1
 ROUTE_LEVELS, ROUTE_SCAN = 0, 1
+ORDER_ROWMAJOR, ORDER_DFS = 0, 1
 UNARY_EXP_NEG_INV, UNARY_SIN_DEG, UNARY_COS_DEG, UNARY_TAN_DEG, UNARY_EXP_NEG = 0, 1, 2, 3, 4
 
 # every symbol include/sphy_b200.h declares: name -> (restype, argtypes)
@@ -83,6 +84,7 @@ SYMBOLS = {
     "sphy_last_error": (C.c_char_p, [P]),
     "sphy_sm_count": (C.c_int, [P]),
     "sphy_abi_sizeof": (C.c_size_t, [C.c_int]),
+    "sphy_set_cell_order": (C.c_int, [P, C.c_int]),
     "sphy_ldd_build": (C.c_int, [P, P, P, P]),
     "sphy_ncells": (C.c_int64, [P]),
     "sphy_nlevels": (C.c_int32, [P]),
@@ -96,7 +98,6 @@ SYMBOLS = {
                                C.c_int, P]),
     "sphy_glac_step": (C.c_int, [P, C.POINTER(GlacTable), P, P, C.c_float, C.c_float, C.POINTER(GlacOut), P]),
     "sphy_route_step": (C.c_int, [P, C.c_int, C.POINTER(P), C.POINTER(P), SphyParam, C.c_float, C.c_int, P]),
-    "sphy_scan_export": (C.c_int, [P, C.c_char_p, P, C.c_size_t, P]),
     "sphy_accuflux": (C.c_int, [P, P, P, P, C.c_int, P]),
     "sphy_upstream": (C.c_int, [P, P, P, P]),
     "sphy_route_reslake_step": (C.c_int, [P, C.POINTER(ResLake), P, P, SphyParam, C.c_float, C.c_int, P]),

@@ -23,9 +23,17 @@ struct sphy_ctx {
     int64_t n = 0;             // active cells
     int32_t nlevels = 0;
     bool ldd_ready = false;
-    // Appendix-C structures (device), compact row-major numbering
-    int32_t *cidx = nullptr, *flat_active = nullptr, *down = nullptr, *level = nullptr, *order = nullptr;
-    int32_t *level_ptr = nullptr, *don_ptr = nullptr, *don_idx = nullptr;
+    // Appendix-C structures (device), canonical compact row-major numbering (what sphy_ldd_export returns)
+    int32_t *c_cidx = nullptr, *c_flat_active = nullptr, *c_down = nullptr, *c_order = nullptr, *c_pos = nullptr;
+    int32_t *c_don_ptr = nullptr, *c_don_idx = nullptr;
+    int32_t *level = nullptr, *level_ptr = nullptr;
+    // the same structures in device cell order (what the kernels use); see finalize_cell_order()
+    int order_mode = SPHY_ORDER_DFS;
+    int32_t *cidx = nullptr, *flat_active = nullptr, *down = nullptr, *order = nullptr;
+    int32_t *don_ptr = nullptr, *don_idx = nullptr;
+    int32_t *pre = nullptr;        // canonical cell -> device index
+    int32_t *cell_canon = nullptr; // device index -> canonical cell
+    int32_t *sub_size = nullptr;   // by device index: upstream cell count incl. self (subtree size)
     uint8_t *indeg = nullptr;
     int64_t *nup = nullptr;
     int64_t n_don = 0;
@@ -34,11 +42,8 @@ struct sphy_ctx {
     int32_t *pos = nullptr, *dpos_ptr = nullptr, *dpos = nullptr;
     std::vector<int32_t> h_level_ptr;
     std::vector<RoutePlanSeg> plan;
-    // scan layout (DFS pre-order): built lazily by route_scan.cu
+    // scan routing workspaces (route_scan.cu)
     bool scan_ready = false;
-    int32_t *pre = nullptr;        // cell -> pre-order rank
-    int32_t *pre_cell = nullptr;   // rank -> cell
-    int32_t *sub_size = nullptr;   // by rank: subtree size (== nup)
     double *scan_local = nullptr;  // [ncomp_max][n] tile-local inclusive prefix sums (by rank)
     double *scan_tile = nullptr;   // [ncomp_max][ntiles+1] exclusive prefix of tile totals
     int32_t n_tiles = 0;

@@ -29,13 +29,22 @@ extern "C" void sphy_ctx_destroy(sphy_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    void *ptrs[] = {ctx->cidx, ctx->flat_active, ctx->down, ctx->level, ctx->order, ctx->level_ptr, ctx->don_ptr,
-                    ctx->don_idx, ctx->indeg, ctx->nup, ctx->pos, ctx->dpos_ptr, ctx->dpos, ctx->pre, ctx->pre_cell,
+    void *ptrs[] = {ctx->c_cidx, ctx->c_flat_active, ctx->c_down, ctx->c_order, ctx->c_pos, ctx->c_don_ptr, ctx->c_don_idx,
+                    ctx->cidx, ctx->flat_active, ctx->down, ctx->level, ctx->order, ctx->level_ptr, ctx->don_ptr,
+                    ctx->don_idx, ctx->indeg, ctx->nup, ctx->pos, ctx->dpos_ptr, ctx->dpos, ctx->pre, ctx->cell_canon,
                     ctx->sub_size, ctx->scan_local, ctx->scan_tile, ctx->scan_flags, ctx->acc, ctx->qsorted,
                     ctx->ra_table, ctx->tmp_n[0], ctx->tmp_n[1], ctx->tmp_n[2], ctx->tmp_n[3]};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     delete ctx;
+}
+
+extern "C" int sphy_set_cell_order(sphy_ctx *ctx, int mode)
+{
+    if (!ctx || (mode != SPHY_ORDER_ROWMAJOR && mode != SPHY_ORDER_DFS)) return SPHY_E_INVALID;
+    if (ctx->ldd_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_set_cell_order after sphy_ldd_build");
+    ctx->order_mode = mode;
+    return SPHY_OK;
 }
 
 extern "C" const char *sphy_last_error(const sphy_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }

@@ -201,15 +201,6 @@ extern "C" int sphy_route_step(sphy_ctx *ctx, int ncomp, const float *const *run
     return route_levels_run(ctx, a, (cudaStream_t)stream);
 }
 
-int route_scan_export(sphy_ctx *ctx, const char *name, void *dst, size_t bytes, cudaStream_t st);   // route_scan.cu
-
-extern "C" int sphy_scan_export(sphy_ctx *ctx, const char *name, void *dst, size_t bytes, void *stream)
-{
-    if (!ctx || !name || !dst) return SPHY_E_INVALID;
-    if (!ctx->ldd_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_scan_export before sphy_ldd_build");
-    return route_scan_export(ctx, name, dst, bytes, (cudaStream_t)stream);
-}
-
 extern "C" int sphy_accuflux(sphy_ctx *ctx, const float *mat, const float *fraction, float *flux, int method, void *stream)
 {
     if (!ctx || !mat || !flux) return SPHY_E_INVALID;

@@ -110,8 +110,8 @@ def _table_col(rows, col):
 
 # ----------------------------------------------------------------------------------------------
 class SphyModel:
-    def __init__(self, cfg, maps: MapSource, device="cuda:0", route_method="levels", diagnostics=False,
-                 collect_tss=True):
+    def __init__(self, cfg, maps: MapSource, device="cuda:0", route_method="scan", diagnostics=False,
+                 collect_tss=True, cell_order="dfs"):
         if not torch.cuda.is_available():
             raise RuntimeError("SphyModel needs a CUDA device (B200); there is no CPU fallback")
         self.lib = _lib.load()
@@ -121,6 +121,9 @@ class SphyModel:
         self.diagnostics = diagnostics
         self.collect_tss = collect_tss
         self.route_method = {"levels": _lib.ROUTE_LEVELS, "scan": _lib.ROUTE_SCAN}[route_method]
+        self.cell_order_mode = {"rowmajor": _lib.ORDER_ROWMAJOR, "dfs": _lib.ORDER_DFS}[cell_order]
+        if self.route_method == _lib.ROUTE_SCAN and self.cell_order_mode != _lib.ORDER_DFS:
+            raise ValueError("route_method='scan' needs cell_order='dfs'")
         if isinstance(cfg, configparser.RawConfigParser):
             self.config = cfg
         else:
@@ -202,19 +205,25 @@ class SphyModel:
             self._ldd_host = ldd
             ldd_d = torch.from_numpy(ldd).to(self.device)
             act_d = torch.from_numpy(self.clone_mask.astype(np.uint8)).to(self.device)
+            self._ck(self.lib.sphy_set_cell_order(self._ctx, self.cell_order_mode), "sphy_set_cell_order")
             self._ck(self.lib.sphy_ldd_build(self._ctx, ldd_d.data_ptr(), act_d.data_ptr(), self._stream()), "sphy_ldd_build")
             self.n = int(self.lib.sphy_ncells(self._ctx))
             self.nlevels = int(self.lib.sphy_nlevels(self._ctx))
             flat = torch.empty(self.n, dtype=torch.int32, device=self.device)
             self._ck(self.lib.sphy_ldd_export(self._ctx, b"flat_active", flat.data_ptr(), flat.numel() * 4, self._stream()),
                      "sphy_ldd_export")
-            self.flat_active = flat.cpu().numpy().astype(np.int64)
+            self.flat_active = flat.cpu().numpy().astype(np.int64)      # device cell index -> raster index
+            self._ck(self.lib.sphy_ldd_export(self._ctx, b"cell_order", flat.data_ptr(), flat.numel() * 4, self._stream()),
+                     "sphy_ldd_export")
+            self.cell_order = flat.cpu().numpy().astype(np.int64)       # device cell index -> canonical compact index
         else:
             self.flat_active = np.flatnonzero(self.clone_mask.ravel())
+            self.cell_order = np.arange(self.flat_active.size)
             self.n = int(self.flat_active.size)
             self.nlevels = 0
             self._ck(self.lib.sphy_set_ncells(self._ctx, self.n), "sphy_set_ncells")
-        self.full_raster = self.n == self.nrows * self.ncols
+        self.full_raster = (self.n == self.nrows * self.ncols and
+                            bool(np.array_equal(self.flat_active, np.arange(self.n))))   # compact order == raster order
         self._cidx_host = np.full(self.nrows * self.ncols, -1, np.int64)
         self._cidx_host[self.flat_active] = np.arange(self.n)
 
@@ -223,7 +232,8 @@ class SphyModel:
         n, L = self.n, self.nlevels
         spec = {"cidx": (torch.int32, self.nrows * self.ncols), "down": (torch.int32, n), "indeg": (torch.uint8, n),
                 "level": (torch.int32, n), "order": (torch.int32, n), "level_ptr": (torch.int32, L + 1),
-                "don_ptr": (torch.int32, n + 1), "nup": (torch.int64, n)}
+                "don_ptr": (torch.int32, n + 1), "nup": (torch.int64, n), "sub_size": (torch.int32, n),
+                "cell_order": (torch.int32, n), "flat_active": (torch.int32, n)}
         if name == "don_idx":
             ptr = self.ldd_structure("don_ptr")
             spec["don_idx"] = (torch.int32, int(ptr[-1].item()))
@@ -450,6 +460,7 @@ class SphyModel:
         self._forcing_dev = None
         self._forcing_host = None
         self._fdev = None
+        self._fraster = None
         self._staging = None
         self._prof = None
 
@@ -700,7 +711,8 @@ class SphyModel:
         self._forcing_dev = fn
 
     def set_host_forcing(self, fn):
-        """fn(counter) -> dict of compact float32 PINNED host tensors; each step copies them host->device."""
+        """fn(counter) -> dict of float32 PINNED host tensors holding the day's forcing RASTERS (nrows*ncols, the
+        layout readmap delivers); each step copies them host->device and compacts them into device cell order."""
         self._forcing_host = fn
 
     def enable_profiling(self, on=True):
@@ -715,8 +727,16 @@ class SphyModel:
             if getattr(self, "_fdev", None) is None:
                 self._fdev = {k: torch.empty(self.n, dtype=torch.float32, device=self.device) for k in keys}
             host = self._forcing_host(counter)
+            if self.full_raster:
+                for k in keys:
+                    self._fdev[k].copy_(host[k], non_blocking=True)
+                return self._fdev
+            if getattr(self, "_fraster", None) is None:
+                self._fraster = {k: torch.empty(self.nrows * self.ncols, dtype=torch.float32, device=self.device) for k in keys}
             for k in keys:
-                self._fdev[k].copy_(host[k], non_blocking=True)
+                self._fraster[k].copy_(host[k], non_blocking=True)
+                self._ck(self.lib.sphy_gather_f32(self._ctx, self._fraster[k].data_ptr(), self._fdev[k].data_ptr(), self._stream()),
+                         "sphy_gather_f32")
             return self._fdev
         if self._staging is None:
             self._staging = {k: torch.empty(self.n, dtype=torch.float32).pin_memory() for k in keys}

@@ -24,6 +24,7 @@ def close(a, b):
 
 def make_model(cat, **kw):
     from sphy_b200.model import CatchmentSource, SphyModel
+    kw.setdefault("route_method", "levels")        # the bit-exact routing path; the scan path has its own tests
     tmp = tempfile.mkdtemp(prefix="sphy_gpu_")
     cfg = cat.write_inputs(os.path.join(tmp, "in"), os.path.join(tmp, "out"))
     m = SphyModel(cfg, CatchmentSource(cat), **kw)
@@ -38,11 +39,12 @@ def model_attr(model, key):
     return v
 
 
+@pytest.mark.parametrize("order", ["dfs", "rowmajor"])
 @pytest.mark.parametrize("name", golden_cases())
-def test_model_matches_reference_golden(name):
+def test_model_matches_reference_golden(name, order):
     import torch
     cat, z, meta = catchment_from_golden(name)
-    model = make_model(cat, diagnostics=True)
+    model = make_model(cat, diagnostics=True, cell_order=order)
     src = model.maps
     src.forcing_fn = lambda t: golden_forcing(z, t)              # feed exactly the forcing the reference saw
     not_bit_equal = 0
@@ -114,7 +116,7 @@ def test_model_matches_oracle_port(kw, nsteps, route_method="levels"):
         torch.cuda.synchronize()
         for k in keys:
             got = model_attr(model, k).cpu().numpy()
-            want = getattr(port, k)
+            want = getattr(port, k)[model.cell_order]           # oracle is in canonical order, the model in device order
             ok = close(got, want)
             assert ok.all(), f"t={t} {k}: {int((~ok).sum())} cells beyond {RTOL}"
             nb += int((~bit_equal(got, want)).sum())
@@ -122,7 +124,7 @@ def test_model_matches_oracle_port(kw, nsteps, route_method="levels"):
         if cat.rout_components:
             for c in ("RootR", "RootD", "Rain", "Snow", "Glac", "Base"):
                 got = getattr(model, c + "RAold").cpu().numpy()
-                ok = close(got, port.compRAold[c])
+                ok = close(got, port.compRAold[c][model.cell_order])
                 assert ok.all(), f"t={t} {c}RAold"
     if route_method == "levels":
         assert nb <= 1e-4 * tot, f"{nb} of {tot} values are not bit-identical"

@@ -109,35 +109,36 @@ def test_accuflux_upstream_bit_exact(env, shape, seed):
     ctx, st = _check_structures(lib, torch, ldd)
     rng = np.random.default_rng(seed)
     m = (rng.gamma(0.7, 3.0, st.n) * (rng.random(st.n) < 0.6)).astype(np.float32)
-    m_d = torch.from_numpy(m).cuda()
+    canon = _export(lib, torch, ctx, "cell_order", torch.int32, st.n).astype(np.int64)   # device index -> canonical
+    m_d = torch.from_numpy(m[canon]).cuda()
     out = torch.empty_like(m_d)
     _lib.check(lib, ctx, lib.sphy_accuflux(ctx, m_d.data_ptr(), None, out.data_ptr(), 0, None), "accuflux")
     torch.cuda.synchronize()
     got = out.cpu().numpy()
-    want = st.accuflux(m)
+    want = st.accuflux(m)[canon]
     assert np.array_equal(got.view(np.int32), want.view(np.int32))
     # accuflux(ldd, 1) == upstream cell count (exact below 2**24), a pit holds its catchment total
     ones = torch.ones(st.n, device="cuda")
     _lib.check(lib, ctx, lib.sphy_accuflux(ctx, ones.data_ptr(), None, out.data_ptr(), 0, None), "accuflux")
     torch.cuda.synchronize()
     if st.n < 2 ** 24:
-        assert np.array_equal(out.cpu().numpy().astype(np.int64), st.nup)
+        assert np.array_equal(out.cpu().numpy().astype(np.int64), st.nup[canon])
     # fraction cut (QFRAC in {0,1}): nothing crosses a cut cell
     frac = np.ones(st.n, np.float32)
     frac[rng.choice(st.n, size=max(1, st.n // 200), replace=False)] = 0.0
-    f_d = torch.from_numpy(frac).cuda()
+    f_d = torch.from_numpy(frac[canon]).cuda()
     _lib.check(lib, ctx, lib.sphy_accuflux(ctx, m_d.data_ptr(), f_d.data_ptr(), out.data_ptr(), 0, None), "accufractionflux")
     torch.cuda.synchronize()
-    want = st.accuflux(m, frac)
+    want = st.accuflux(m, frac)[canon]
     got = out.cpu().numpy()
     assert np.array_equal(got.view(np.int32), want.view(np.int32))
-    assert (got[frac == 0] == 0).all()
+    assert (got[frac[canon] == 0] == 0).all()
     # upstream
     _lib.check(lib, ctx, lib.sphy_upstream(ctx, m_d.data_ptr(), out.data_ptr(), None), "upstream")
     torch.cuda.synchronize()
-    assert np.array_equal(out.cpu().numpy().view(np.int32), st.upstream(m).view(np.int32))
+    assert np.array_equal(out.cpu().numpy().view(np.int32), st.upstream(m)[canon].view(np.int32))
     # linearity (size-independent property): accuflux(a*m) == a*accuflux(m) for a power of two
-    m2 = torch.from_numpy(m * np.float32(4.0)).cuda()
+    m2 = torch.from_numpy((m * np.float32(4.0))[canon]).cuda()
     out2 = torch.empty_like(m_d)
     _lib.check(lib, ctx, lib.sphy_accuflux(ctx, m2.data_ptr(), None, out2.data_ptr(), 0, None), "accuflux")
     _lib.check(lib, ctx, lib.sphy_accuflux(ctx, m_d.data_ptr(), None, out.data_ptr(), 0, None), "accuflux")

@@ -19,7 +19,7 @@ def _ctx(lib, torch, ldd, cellsize):
 
 
 @pytest.mark.parametrize("shape,outlets,seed", [((9, 7), "single", 1), ((120, 90), "border", 2), ((700, 900), "single", 3)])
-def test_preorder_is_a_valid_dfs_numbering(shape, outlets, seed):
+def test_device_order_is_a_valid_dfs_numbering(shape, outlets, seed):
     import torch
     from oracle.ldd_oracle import LddStruct
     from sphy_b200 import _lib, synth
@@ -29,20 +29,22 @@ def test_preorder_is_a_valid_dfs_numbering(shape, outlets, seed):
     ctx = _ctx(lib, torch, ldd, 100.0)
     n = st.n
     got = {}
-    for name in ("pre", "pre_cell", "sub_size"):
+    for name in ("cell_order", "sub_size", "flat_active"):
         t = torch.empty(n, dtype=torch.int32, device="cuda")
-        _lib.check(lib, ctx, lib.sphy_scan_export(ctx, name.encode(), t.data_ptr(), n * 4, None), name)
+        _lib.check(lib, ctx, lib.sphy_ldd_export(ctx, name.encode(), t.data_ptr(), n * 4, None), name)
         torch.cuda.synchronize()
         got[name] = t.cpu().numpy().astype(np.int64)
-    pre, pre_cell, size = got["pre"], got["pre_cell"], got["sub_size"]
-    assert np.array_equal(np.sort(pre), np.arange(n))                       # a permutation
-    assert np.array_equal(pre_cell[pre], np.arange(n))                      # inverse
-    assert np.array_equal(size[pre], st.nup)                                # subtree sizes = upstream counts
+    canon, size = got["cell_order"], got["sub_size"]          # device index -> canonical cell; subtree size by device index
+    assert np.array_equal(np.sort(canon), np.arange(n))                     # a permutation
+    pre = np.empty(n, np.int64)
+    pre[canon] = np.arange(n)                                               # canonical cell -> device index
+    assert np.array_equal(size, st.nup[canon])                              # subtree sizes = upstream counts
+    assert np.array_equal(got["flat_active"], st.flat_active[canon])        # raster index of every device cell
     has_down = st.down >= 0
     d = st.down[has_down]
     i = np.flatnonzero(has_down)
-    assert (pre[i] > pre[d]).all()                                          # parent first
-    assert (pre[i] + st.nup[i] <= pre[d] + st.nup[d]).all()                 # child range nested in the parent's
+    assert (pre[i] > pre[d]).all()                                          # receiver first
+    assert (pre[i] + st.nup[i] <= pre[d] + st.nup[d]).all()                 # donor range nested in the receiver's
     lib.sphy_ctx_destroy(ctx)
 
 
@@ -58,8 +60,12 @@ def test_scan_routing_matches_oracle(shape, ncomp, kxmap, seed):
     n = st.n
     ctx = _ctx(lib, torch, ldd, cellsize)
     rng = np.random.default_rng(seed)
-    kx_np = (0.9 + 0.09 * rng.random(n)).astype(np.float32) if kxmap else None
-    kx_d = torch.from_numpy(kx_np).cuda() if kxmap else None
+    t = torch.empty(n, dtype=torch.int32, device="cuda")
+    _lib.check(lib, ctx, lib.sphy_ldd_export(ctx, b"cell_order", t.data_ptr(), n * 4, None), "cell_order")
+    torch.cuda.synchronize()
+    canon = t.cpu().numpy().astype(np.int64)                  # device index -> canonical cell
+    kx_np = (0.9 + 0.09 * rng.random(n)).astype(np.float32) if kxmap else None      # canonical order
+    kx_d = torch.from_numpy(kx_np[canon]).cuda() if kxmap else None
     kx = _lib.SphyParam(kx_d.data_ptr() if kxmap else None, 0.971)
     one_m = float(np.float32(1 - 0.971))
     area = np.float32(cellsize) * np.float32(cellsize)
@@ -69,7 +75,7 @@ def test_scan_routing_matches_oracle(shape, ncomp, kxmap, seed):
     q_64 = [np.zeros(n, np.float64) for _ in range(ncomp)]
     for step in range(4):
         mm = [(rng.gamma(0.8, 4.0, n) * (rng.random(n) < 0.7)).astype(np.float32) for _ in range(ncomp)]
-        mm_d = [torch.from_numpy(m).cuda() for m in mm]
+        mm_d = [torch.from_numpy(m[canon]).cuda() for m in mm]
         src = (C.c_void_p * ncomp)(*[t.data_ptr() for t in mm_d])
         for q, method in ((q_lv, _lib.ROUTE_LEVELS), (q_sc, _lib.ROUTE_SCAN)):
             dst = (C.c_void_p * ncomp)(*[t.data_ptr() for t in q])
@@ -85,8 +91,10 @@ def test_scan_routing_matches_oracle(shape, ncomp, kxmap, seed):
             else:
                 q_or[c] = np.float32(one_m) * ra + np.float32(0.971) * q_or[c]
                 q_64[c] = float(np.float32(one_m)) * ra64 + float(np.float32(0.971)) * q_64[c]
-            lv = q_lv[c].cpu().numpy()
-            sc = q_sc[c].cpu().numpy().astype(np.float64)
+            lv = np.empty(n, np.float32)
+            lv[canon] = q_lv[c].cpu().numpy()                 # back to canonical order
+            sc = np.empty(n, np.float64)
+            sc[canon] = q_sc[c].cpu().numpy().astype(np.float64)
             assert np.array_equal(lv.view(np.int32), q_or[c].view(np.int32)), "level sweep must stay bit-exact"
             tol = 1e-5 * np.abs(q_or[c]) + 1e-12
             assert (np.abs(sc - q_or[c]) <= tol).all(), f"step {step} comp {c}: scan vs REAL4 oracle {np.max(np.abs(sc - q_or[c]) / (np.abs(q_or[c]) + 1e-30)):.2e}"
