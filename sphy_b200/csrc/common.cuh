@@ -42,13 +42,15 @@ struct sphy_ctx {
     int32_t *pos = nullptr, *dpos_ptr = nullptr, *dpos = nullptr;
     std::vector<int32_t> h_level_ptr;
     std::vector<RoutePlanSeg> plan;
-    // scan routing workspaces (route_scan.cu)
+    // scan routing (route_scan.cu): static lists of the cells whose index range crosses a tile boundary + workspaces
     bool scan_ready = false;
-    double *scan_local = nullptr;  // [ncomp_max][n] tile-local inclusive prefix sums (by rank)
-    double *scan_tile = nullptr;   // [ncomp_max][ntiles+1] exclusive prefix of tile totals
+    int32_t *cross_r = nullptr, *cross_ptr = nullptr, *end_e = nullptr, *end_k = nullptr, *end_ptr = nullptr;
+    int32_t n_cross = 0;
+    double *park_before = nullptr, *park_end = nullptr;
+    double *scan_tile = nullptr;   // [ncomp][ntiles] tile totals
+    double *scan_excl = nullptr;   // [ncomp][ntiles+1] exclusive prefix of the tile totals
     int32_t n_tiles = 0;
     int scan_comp_cap = 0;
-    unsigned int *scan_flags = nullptr;
     // workspaces
     float *acc = nullptr;          // [ROUTE_MAX_COMP][n] accumulated flux in routing order
     float *qsorted = nullptr;      // scratch [ROUTE_MAX_COMP][n]

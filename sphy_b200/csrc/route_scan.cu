@@ -1,16 +1,19 @@
-// route_scan.cu -- K4b: flow accumulation as subtree range sums over a DFS pre-order (no level latency chain).
+// route_scan.cu -- K4b: flow accumulation as subtree range sums over the DFS cell order (no level latency chain).
 //
 // accuflux is linear and the drainage network is a forest, so with the cells stored in a depth-first pre-order
-// (SPHY_ORDER_DFS, built in ldd_build.cu) the subtree of cell j is the contiguous index range [j, j + sub_size[j]): its accumulated flux is a difference of prefix
-// sums of the per-cell material taken in rank order.  One step is therefore two streaming passes instead of a
-// walk over ~10^4 dependent levels:
-//   pass A  per tile of 2048 cells: stream runoff, convert to m3/s (routing.py:26), float64 inclusive scan inside
-//           the tile (cub::BlockScan), tile total;   + a tiny exclusive scan of the tile totals;
-//   pass B  per cell: range sum from the tile-local prefixes (+ tile prefix only when the subtree spans tiles, so
-//           small subtrees never see the global magnitude), REAL4 flux, kx recession blend (routing.py:28).
-// The float64 range sums have no per-cell REAL4 rounding along the flow path, so this path agrees with the
-// level sweep / the oracle to ~1e-6 relative (tested at 1e-5), not bit-for-bit; the level sweep stays the
-// bit-exact reference path.  Pre-order ranks are built once from the Appendix-C structures.
+// (SPHY_ORDER_DFS, built in ldd_build.cu) the upstream area of cell j is the contiguous index range
+// [j, j + sub_size[j]) and its accumulated flux is a difference of prefix sums of the per-cell material.
+// One step is a single streaming pass plus two tiny fix-up kernels instead of a walk over ~10^4 dependent levels:
+//   main   per tile of 2048 cells (one CTA): stream runoff, convert to m3/s (routing.py:26), float64 inclusive
+//          scan inside the tile (cub::BlockScan) kept in shared memory; every cell whose range ends inside the
+//          tile (~96 % of them) gets its flux from two shared-memory reads and is blended with Qold and written
+//          (routing.py:28) right away -- 16 B of HBM traffic per cell and component;
+//   totals exclusive scan of the per-tile totals (one CTA per component);
+//   cross  the few cells whose range crosses a tile boundary (a static list built once): tile suffix + whole
+//          tiles in between + prefix inside the end tile, from values the main pass parked for them.
+// Small subtrees never see the global magnitude, so relative accuracy holds for tiny fluxes too.  The float64
+// range sums have no per-cell REAL4 rounding along the flow path, hence this path agrees with the level sweep /
+// the oracle to ~1e-6 relative (tested at 1e-5), not bit-for-bit; the level sweep stays the bit-exact path.
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -19,55 +22,112 @@ namespace {
 
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
-constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;   // 2048 ranks
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;   // 2048 cells
 
 struct ScanArgs {
     int ncomp;
-    const float *m[ROUTE_MAX_COMP];       // runoff mm/day, cell order
-    float *qstate[ROUTE_MAX_COMP];        // Qold in / Q out, cell order
+    const float *m[ROUTE_MAX_COMP];       // runoff mm/day
+    float *qstate[ROUTE_MAX_COMP];        // Qold in / Q out
     const int32_t *sub_size;
-    double *local;                        // [ncomp][n] tile-local inclusive prefix, by rank
-    double *tile_tot;                     // [ncomp][ntiles+1] tile totals, then exclusive prefix in place
+    // static crossing lists (see build_cross_lists)
+    const int32_t *cross_r, *cross_ptr;   // crossing cells sorted by index; per-tile ranges
+    const int32_t *end_e, *end_k, *end_ptr;   // their range ends sorted by index, the owning list slot, per-tile ranges
+    int32_t n_cross;
+    double *park_before;                  // [ncomp][n_cross] tile-local exclusive prefix at the crossing cell
+    double *park_end;                     // [ncomp][n_cross] tile-local inclusive prefix at its range end
+    double *tile_tot;                     // [ncomp][ntiles]   tile totals
+    double *tile_excl;                    // [ncomp][ntiles+1] exclusive prefix of the totals
     sphy_param kx;
     float one_m_kx, cellarea;
     int64_t n;
-    int64_t stride;                       // per-component stride of `local` (n rounded up to even: 16-byte aligned rows)
     int32_t ntiles;
 };
 
-// pass A
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const __grid_constant__ ScanArgs a)
+__device__ __forceinline__ float to_m3s(float mm, float cellarea) { return ((mm * 0.001f) * cellarea) / 86400.0f; }
+
+// main pass: one CTA per tile
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_main(const __grid_constant__ ScanArgs a)
 {
     typedef cub::BlockScan<double, SCAN_THREADS> BlockScan;
     __shared__ typename BlockScan::TempStorage tmp;
-    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    __shared__ double Ls[SCAN_TILE];
+    const int32_t t = blockIdx.x;
+    const int64_t tbase = (int64_t)t * SCAN_TILE;
+    const int lo = threadIdx.x * SCAN_ITEMS;
+    const int64_t base = tbase + lo;
+    const int64_t tend = min(tbase + (int64_t)SCAN_TILE, a.n);   // one past the last cell of the tile
     const bool full = base + SCAN_ITEMS <= a.n;
+    int32_t sz[SCAN_ITEMS];
+    if (full) {
+        const int4 s0 = __ldg(reinterpret_cast<const int4 *>(a.sub_size + base));
+        const int4 s1 = __ldg(reinterpret_cast<const int4 *>(a.sub_size + base + 4));
+        sz[0] = s0.x; sz[1] = s0.y; sz[2] = s0.z; sz[3] = s0.w; sz[4] = s1.x; sz[5] = s1.y; sz[6] = s1.z; sz[7] = s1.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < SCAN_ITEMS; ++j) sz[j] = base + j < a.n ? __ldg(a.sub_size + base + j) : 1;
+    }
+    float kxv[SCAN_ITEMS];
+    if (a.kx.map) {
+#pragma unroll
+        for (int j = 0; j < SCAN_ITEMS; ++j) kxv[j] = base + j < a.n ? __ldg(a.kx.map + base + j) : 0.0f;
+    }
+    const int32_t cb = __ldg(a.cross_ptr + t), ce = __ldg(a.cross_ptr + t + 1);
+    const int32_t eb = __ldg(a.end_ptr + t), ee = __ldg(a.end_ptr + t + 1);
     for (int c = 0; c < a.ncomp; ++c) {
-        double v[SCAN_ITEMS];
         const float *m = a.m[c];
-        if (full) {                                        // 2 x 128-bit loads per thread
+        float *qs = a.qstate[c];
+        float q[SCAN_ITEMS], mm[SCAN_ITEMS];
+        if (full) {                                            // 128-bit loads
             const float4 x = __ldg(reinterpret_cast<const float4 *>(m + base));
             const float4 y = __ldg(reinterpret_cast<const float4 *>(m + base + 4));
-            const float q[SCAN_ITEMS] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
-#pragma unroll
-            for (int j = 0; j < SCAN_ITEMS; ++j) v[j] = (double)(((q[j] * 0.001f) * a.cellarea) / 86400.0f);   // routing.py:26
+            mm[0] = x.x; mm[1] = x.y; mm[2] = x.z; mm[3] = x.w; mm[4] = y.x; mm[5] = y.y; mm[6] = y.z; mm[7] = y.w;
+            const float4 u = *reinterpret_cast<const float4 *>(qs + base);
+            const float4 w = *reinterpret_cast<const float4 *>(qs + base + 4);
+            q[0] = u.x; q[1] = u.y; q[2] = u.z; q[3] = u.w; q[4] = w.x; q[5] = w.y; q[6] = w.z; q[7] = w.w;
         } else {
 #pragma unroll
-            for (int j = 0; j < SCAN_ITEMS; ++j)
-                v[j] = base + j < a.n ? (double)(((__ldg(m + base + j) * 0.001f) * a.cellarea) / 86400.0f) : 0.0;
+            for (int j = 0; j < SCAN_ITEMS; ++j) {
+                mm[j] = base + j < a.n ? __ldg(m + base + j) : 0.0f;
+                q[j] = base + j < a.n ? qs[base + j] : 0.0f;
+            }
         }
+        double v[SCAN_ITEMS];
+#pragma unroll
+        for (int j = 0; j < SCAN_ITEMS; ++j) v[j] = base + j < a.n ? (double)to_m3s(mm[j], a.cellarea) : 0.0;
         double total;
         BlockScan(tmp).InclusiveSum(v, v, total);
-        double *out = a.local + (int64_t)c * a.stride;
-        if (full) {
 #pragma unroll
-            for (int j = 0; j < SCAN_ITEMS; j += 2) *reinterpret_cast<double2 *>(out + base + j) = make_double2(v[j], v[j + 1]);
+        for (int j = 0; j < SCAN_ITEMS; ++j) Ls[lo + j] = v[j];
+        __syncthreads();
+        double before = lo == 0 ? 0.0 : Ls[lo - 1];            // tile-local exclusive prefix at the thread's first cell
+#pragma unroll
+        for (int j = 0; j < SCAN_ITEMS; ++j) {
+            const int64_t e = base + j + sz[j] - 1;            // last cell of the upstream range
+            if (e < tend) {
+                const float f = (float)(Ls[(int)(e - tbase)] - before);
+                const float kx = a.kx.map ? kxv[j] : a.kx.value;
+                const float omk = a.kx.map ? 1.0f - kx : a.one_m_kx;
+                q[j] = omk * f + kx * q[j];                    // routing.py:28
+            }                                                  // else: crossing cell, left to k_scan_cross
+            before = v[j];
+        }
+        if (full) {
+            *reinterpret_cast<float4 *>(qs + base) = make_float4(q[0], q[1], q[2], q[3]);
+            *reinterpret_cast<float4 *>(qs + base + 4) = make_float4(q[4], q[5], q[6], q[7]);
         } else {
 #pragma unroll
             for (int j = 0; j < SCAN_ITEMS; ++j)
-                if (base + j < a.n) out[base + j] = v[j];
+                if (base + j < a.n) qs[base + j] = q[j];
         }
-        if (threadIdx.x == 0) a.tile_tot[(int64_t)c * (a.ntiles + 1) + blockIdx.x] = total;
+        // park what the crossing cells of / ending in this tile will need
+        double *pb = a.park_before + (int64_t)c * a.n_cross, *pe = a.park_end + (int64_t)c * a.n_cross;
+        for (int32_t k = cb + threadIdx.x; k < ce; k += SCAN_THREADS) {
+            const int off = (int)(__ldg(a.cross_r + k) - tbase);
+            pb[k] = off == 0 ? 0.0 : Ls[off - 1];
+        }
+        for (int32_t j = eb + threadIdx.x; j < ee; j += SCAN_THREADS)
+            pe[__ldg(a.end_k + j)] = Ls[(int)(__ldg(a.end_e + j) - tbase)];
+        if (threadIdx.x == 0) a.tile_tot[(int64_t)c * a.ntiles + t] = total;
         __syncthreads();
     }
 }
@@ -78,7 +138,8 @@ __global__ void __launch_bounds__(1024) k_scan_tile_totals(const __grid_constant
     typedef cub::BlockScan<double, 1024> BlockScan;
     __shared__ typename BlockScan::TempStorage tmp;
     __shared__ double carry_s;
-    double *t = a.tile_tot + (int64_t)blockIdx.x * (a.ntiles + 1);
+    const double *t = a.tile_tot + (int64_t)blockIdx.x * a.ntiles;
+    double *x = a.tile_excl + (int64_t)blockIdx.x * (a.ntiles + 1);
     if (threadIdx.x == 0) carry_s = 0.0;
     __syncthreads();
     for (int32_t b = 0; b < a.ntiles + 1; b += 1024) {
@@ -86,56 +147,146 @@ __global__ void __launch_bounds__(1024) k_scan_tile_totals(const __grid_constant
         double v = k < a.ntiles ? t[k] : 0.0, ex, tot;
         BlockScan(tmp).ExclusiveSum(v, ex, tot);
         const double carry = carry_s;
-        if (k < a.ntiles + 1) t[k] = carry + ex;
+        if (k < a.ntiles + 1) x[k] = carry + ex;
         __syncthreads();
         if (threadIdx.x == 0) carry_s = carry + tot;
         __syncthreads();
     }
 }
 
-// pass B
-__global__ void __launch_bounds__(256) k_scan_apply(const __grid_constant__ ScanArgs a)
+// cells whose upstream range crosses a tile boundary
+__global__ void __launch_bounds__(256) k_scan_cross(const __grid_constant__ ScanArgs a)
 {
-    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (r >= a.n) return;
-    const int64_t cell = r;                                   // device order IS the pre-order
-    const int64_t e = r + __ldg(a.sub_size + r) - 1;          // last index of the subtree
+    const int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.n_cross) return;
+    const int64_t r = __ldg(a.cross_r + k);
+    const int64_t e = r + __ldg(a.sub_size + r) - 1;
     const int32_t ta = (int32_t)(r / SCAN_TILE), te = (int32_t)(e / SCAN_TILE);
-    const bool a_first = (r % SCAN_TILE) == 0;
-    const float kx = a.kx.map ? __ldg(a.kx.map + cell) : a.kx.value;
+    const float kx = a.kx.map ? __ldg(a.kx.map + r) : a.kx.value;
     const float omk = a.kx.map ? 1.0f - kx : a.one_m_kx;
     for (int c = 0; c < a.ncomp; ++c) {
-        const double *L = a.local + (int64_t)c * a.stride;
-        const double *T = a.tile_tot + (int64_t)c * (a.ntiles + 1);
-        const double before = a_first ? 0.0 : L[r - 1];       // tile-local exclusive prefix at r
-        double s;
-        if (ta == te) {
-            s = L[e] - before;
-        } else {
-            const int64_t ta_last = (int64_t)(ta + 1) * SCAN_TILE - 1;
-            s = (L[ta_last] - before) + (T[te] - T[ta + 1]) + L[e];
-        }
+        const double *T = a.tile_tot + (int64_t)c * a.ntiles;
+        const double *X = a.tile_excl + (int64_t)c * (a.ntiles + 1);
+        const double s = (T[ta] - a.park_before[(int64_t)c * a.n_cross + k]) + (X[te] - X[ta + 1]) +
+                         a.park_end[(int64_t)c * a.n_cross + k];
         const float f = (float)s;
         float *qs = a.qstate[c];
-        qs[cell] = omk * f + kx * qs[cell];                    // routing.py:28
+        qs[r] = omk * f + kx * qs[r];                          // routing.py:28
     }
 }
 
+// ---- one-time construction of the crossing lists ---------------------------------------------------------
+__global__ void k_cross_flag(const int32_t *sub_size, int64_t n, uint8_t *flag)
+{
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r < n) flag[r] = (r / SCAN_TILE) != ((r + sub_size[r] - 1) / SCAN_TILE);
+}
+
+__global__ void k_cross_ends(const int32_t *cross_r, const int32_t *sub_size, int32_t nc, int32_t *e, int32_t *k)
+{
+    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nc) {
+        e[i] = cross_r[i] + sub_size[cross_r[i]] - 1;
+        k[i] = i;
+    }
+}
+
+// ptr[t] = first position in the sorted key list with key >= t * SCAN_TILE (t = 0..ntiles)
+__global__ void k_tile_lower_bound(const int32_t *keys, int32_t nk, int32_t ntiles, int32_t *ptr)
+{
+    int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > ntiles) return;
+    const int64_t want = (int64_t)t * SCAN_TILE;
+    int32_t lo = 0, hi = nk;
+    while (lo < hi) {
+        const int32_t mid = (lo + hi) >> 1;
+        if (keys[mid] < want) lo = mid + 1; else hi = mid;
+    }
+    ptr[t] = lo;
+}
+
 }  // namespace
+
+static int build_cross_lists(sphy_ctx *ctx, cudaStream_t st)
+{
+    const int64_t n = ctx->n;
+    const int32_t ntiles = (int32_t)((n + SCAN_TILE - 1) / SCAN_TILE);
+    ctx->n_tiles = ntiles;
+    uint8_t *flag = nullptr;
+    int32_t *sel = nullptr, *nsel = nullptr, *e_in = nullptr, *k_in = nullptr;
+    void *tmp = nullptr;
+    size_t tb = 0;
+    cudaError_t e = cudaSuccess;
+#define FK(call) do { if (e == cudaSuccess) e = (call); } while (0)
+    FK(cudaMalloc(&flag, (size_t)n));
+    FK(cudaMalloc(&sel, sizeof(int32_t) * n));
+    FK(cudaMalloc(&nsel, sizeof(int32_t)));
+    int32_t nc = 0;
+    if (e == cudaSuccess) {
+        k_cross_flag<<<div_up(n, 256), 256, 0, st>>>(ctx->sub_size, n, flag);
+        cub::CountingInputIterator<int32_t> counting(0);
+        FK(cub::DeviceSelect::Flagged(nullptr, tb, counting, flag, sel, nsel, (int)n, st));
+        FK(cudaMalloc(&tmp, tb));
+        FK(cub::DeviceSelect::Flagged(tmp, tb, counting, flag, sel, nsel, (int)n, st));
+        FK(cudaMemcpyAsync(&nc, nsel, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        FK(cudaStreamSynchronize(st));
+    }
+    ctx->n_cross = nc;
+    const size_t ncs = nc > 0 ? (size_t)nc : 1;
+    int rc = SPHY_OK;
+    if (e == cudaSuccess &&
+        ((rc = dev_alloc(ctx, &ctx->cross_r, ncs)) || (rc = dev_alloc(ctx, &ctx->cross_ptr, (size_t)ntiles + 1)) ||
+         (rc = dev_alloc(ctx, &ctx->end_e, ncs)) || (rc = dev_alloc(ctx, &ctx->end_k, ncs)) ||
+         (rc = dev_alloc(ctx, &ctx->end_ptr, (size_t)ntiles + 1)))) {
+        cudaFree(flag); cudaFree(sel); cudaFree(nsel); cudaFree(tmp);
+        return rc;
+    }
+    if (e == cudaSuccess && nc > 0) {
+        FK(cudaMemcpyAsync(ctx->cross_r, sel, sizeof(int32_t) * nc, cudaMemcpyDeviceToDevice, st));
+        FK(cudaMalloc(&e_in, sizeof(int32_t) * nc));
+        FK(cudaMalloc(&k_in, sizeof(int32_t) * nc));
+        if (e == cudaSuccess) {
+            k_cross_ends<<<div_up(nc, 256), 256, 0, st>>>(ctx->cross_r, ctx->sub_size, nc, e_in, k_in);
+            size_t need = 0;
+            FK(cub::DeviceRadixSort::SortPairs(nullptr, need, e_in, ctx->end_e, k_in, ctx->end_k, nc, 0, 32, st));
+            if (need > tb) { cudaFree(tmp); tmp = nullptr; FK(cudaMalloc(&tmp, need)); tb = need; }
+            FK(cub::DeviceRadixSort::SortPairs(tmp, need, e_in, ctx->end_e, k_in, ctx->end_k, nc, 0, 32, st));
+        }
+    }
+    if (e == cudaSuccess) {
+        k_tile_lower_bound<<<div_up(ntiles + 1, 256), 256, 0, st>>>(ctx->cross_r, nc, ntiles, ctx->cross_ptr);
+        k_tile_lower_bound<<<div_up(ntiles + 1, 256), 256, 0, st>>>(ctx->end_e, nc, ntiles, ctx->end_ptr);
+        FK(cudaGetLastError());
+        FK(cudaStreamSynchronize(st));
+    }
+#undef FK
+    cudaFree(flag); cudaFree(sel); cudaFree(nsel); cudaFree(e_in); cudaFree(k_in); cudaFree(tmp);
+    if (e != cudaSuccess) SPHY_FAIL(ctx, SPHY_E_CUDA, "build_cross_lists: %s", cudaGetErrorString(e));
+    ctx->scan_ready = true;
+    return SPHY_OK;
+}
 
 int route_scan_run(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm, float *const *q_state, sphy_param kx,
                    float one_m_kx, cudaStream_t st)
 {
     if (ctx->order_mode != SPHY_ORDER_DFS)
         SPHY_FAIL(ctx, SPHY_E_STATE, "SPHY_ROUTE_SCAN needs the cells in SPHY_ORDER_DFS (sphy_set_cell_order)");
-    ctx->n_tiles = (int32_t)((ctx->n + SCAN_TILE - 1) / SCAN_TILE);
+    if (!ctx->scan_ready) {                       // one-time list build (synchronises, allocates)
+        int rc = build_cross_lists(ctx, st);
+        if (rc != SPHY_OK) return rc;
+    }
     if (ctx->scan_comp_cap < ncomp) {             // grows only when more components are first routed
         int rc;
-        if ((rc = dev_alloc(ctx, &ctx->scan_local, (size_t)ncomp * (ctx->n + 1))) ||
-            (rc = dev_alloc(ctx, &ctx->scan_tile, (size_t)ncomp * (ctx->n_tiles + 1))))
+        const size_t ncs = ctx->n_cross > 0 ? (size_t)ctx->n_cross : 1;
+        if ((rc = dev_alloc(ctx, &ctx->park_before, (size_t)ncomp * ncs)) || (rc = dev_alloc(ctx, &ctx->park_end, (size_t)ncomp * ncs)) ||
+            (rc = dev_alloc(ctx, &ctx->scan_tile, (size_t)ncomp * ctx->n_tiles)) ||
+            (rc = dev_alloc(ctx, &ctx->scan_excl, (size_t)ncomp * (ctx->n_tiles + 1))))
             return rc;
         ctx->scan_comp_cap = ncomp;
     }
+    for (int c = 0; c < ncomp; ++c)
+        if ((reinterpret_cast<uintptr_t>(runoff_mm[c]) | reinterpret_cast<uintptr_t>(q_state[c])) & 15u)
+            SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_route_step: maps must be 16-byte aligned");
     ScanArgs a = {};
     a.ncomp = ncomp;
     for (int c = 0; c < ncomp; ++c) {
@@ -143,18 +294,24 @@ int route_scan_run(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm, floa
         a.qstate[c] = q_state[c];
     }
     a.sub_size = ctx->sub_size;
-    a.local = ctx->scan_local;
+    a.cross_r = ctx->cross_r;
+    a.cross_ptr = ctx->cross_ptr;
+    a.end_e = ctx->end_e;
+    a.end_k = ctx->end_k;
+    a.end_ptr = ctx->end_ptr;
+    a.n_cross = ctx->n_cross;
+    a.park_before = ctx->park_before;
+    a.park_end = ctx->park_end;
     a.tile_tot = ctx->scan_tile;
+    a.tile_excl = ctx->scan_excl;
     a.kx = kx;
     a.one_m_kx = one_m_kx;
     a.cellarea = ctx->cellarea;
     a.n = ctx->n;
-    a.stride = (ctx->n + 1) & ~(int64_t)1;
     a.ntiles = ctx->n_tiles;
-    k_scan_tiles<<<ctx->n_tiles, SCAN_THREADS, 0, st>>>(a);
+    k_scan_main<<<ctx->n_tiles, SCAN_THREADS, 0, st>>>(a);
     k_scan_tile_totals<<<ncomp, 1024, 0, st>>>(a);
-    k_scan_apply<<<div_up(ctx->n, 256), 256, 0, st>>>(a);
+    if (ctx->n_cross > 0) k_scan_cross<<<div_up(ctx->n_cross, 256), 256, 0, st>>>(a);
     SPHY_LAUNCH_CHECK(ctx);
     return SPHY_OK;
 }
-
