@@ -4,9 +4,9 @@
 // (SPHY_ORDER_DFS, built in ldd_build.cu) the upstream area of cell j is the contiguous index range
 // [j, j + sub_size[j]) and its accumulated flux is a difference of prefix sums of the per-cell material.
 // One step is a single streaming pass plus two tiny fix-up kernels instead of a walk over ~10^4 dependent levels:
-//   main   per tile of 2048 cells (one CTA): stream runoff, convert to m3/s (routing.py:26), float64 inclusive
+//   main   per tile of 1024 cells (one CTA): stream runoff, convert to m3/s (routing.py:26), float64 inclusive
 //          scan inside the tile (cub::BlockScan) kept in shared memory; every cell whose range ends inside the
-//          tile (~96 % of them) gets its flux from two shared-memory reads and is blended with Qold and written
+//          tile (~94 % of them) gets its flux from two shared-memory reads and is blended with Qold and written
 //          (routing.py:28) right away -- 16 B of HBM traffic per cell and component;
 //   totals exclusive scan of the per-tile totals (one CTA per component);
 //   cross  the few cells whose range crosses a tile boundary (a static list built once): tile suffix + whole
@@ -21,8 +21,8 @@
 namespace {
 
 constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_ITEMS = 8;
-constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;   // 2048 cells
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;   // 1024 cells
 
 struct ScanArgs {
     int ncomp;
@@ -46,7 +46,7 @@ struct ScanArgs {
 __device__ __forceinline__ float to_m3s(float mm, float cellarea) { return ((mm * 0.001f) * cellarea) / 86400.0f; }
 
 // main pass: one CTA per tile
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_main(const __grid_constant__ ScanArgs a)
+__global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_main(const __grid_constant__ ScanArgs a)
 {
     typedef cub::BlockScan<double, SCAN_THREADS> BlockScan;
     __shared__ typename BlockScan::TempStorage tmp;
@@ -60,8 +60,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_main(const __grid_constan
     int32_t sz[SCAN_ITEMS];
     if (full) {
         const int4 s0 = __ldg(reinterpret_cast<const int4 *>(a.sub_size + base));
-        const int4 s1 = __ldg(reinterpret_cast<const int4 *>(a.sub_size + base + 4));
-        sz[0] = s0.x; sz[1] = s0.y; sz[2] = s0.z; sz[3] = s0.w; sz[4] = s1.x; sz[5] = s1.y; sz[6] = s1.z; sz[7] = s1.w;
+        sz[0] = s0.x; sz[1] = s0.y; sz[2] = s0.z; sz[3] = s0.w;
     } else {
 #pragma unroll
         for (int j = 0; j < SCAN_ITEMS; ++j) sz[j] = base + j < a.n ? __ldg(a.sub_size + base + j) : 1;
@@ -79,11 +78,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_main(const __grid_constan
         float q[SCAN_ITEMS], mm[SCAN_ITEMS];
         if (full) {                                            // 128-bit loads
             const float4 x = __ldg(reinterpret_cast<const float4 *>(m + base));
-            const float4 y = __ldg(reinterpret_cast<const float4 *>(m + base + 4));
-            mm[0] = x.x; mm[1] = x.y; mm[2] = x.z; mm[3] = x.w; mm[4] = y.x; mm[5] = y.y; mm[6] = y.z; mm[7] = y.w;
+            mm[0] = x.x; mm[1] = x.y; mm[2] = x.z; mm[3] = x.w;
             const float4 u = *reinterpret_cast<const float4 *>(qs + base);
-            const float4 w = *reinterpret_cast<const float4 *>(qs + base + 4);
-            q[0] = u.x; q[1] = u.y; q[2] = u.z; q[3] = u.w; q[4] = w.x; q[5] = w.y; q[6] = w.z; q[7] = w.w;
+            q[0] = u.x; q[1] = u.y; q[2] = u.z; q[3] = u.w;
         } else {
 #pragma unroll
             for (int j = 0; j < SCAN_ITEMS; ++j) {
@@ -113,7 +110,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_main(const __grid_constan
         }
         if (full) {
             *reinterpret_cast<float4 *>(qs + base) = make_float4(q[0], q[1], q[2], q[3]);
-            *reinterpret_cast<float4 *>(qs + base + 4) = make_float4(q[4], q[5], q[6], q[7]);
         } else {
 #pragma unroll
             for (int j = 0; j < SCAN_ITEMS; ++j)
@@ -132,9 +128,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_main(const __grid_constan
     }
 }
 
-// exclusive scan of the tile totals, one CTA per component (ntiles ~ 5e4 at 10^8 cells)
+// exclusive scan of the tile totals, one CTA per component (ntiles ~ 1e5 at 10^8 cells), 8 tiles per thread
 __global__ void __launch_bounds__(1024) k_scan_tile_totals(const __grid_constant__ ScanArgs a)
 {
+    constexpr int PER = 8;
     typedef cub::BlockScan<double, 1024> BlockScan;
     __shared__ typename BlockScan::TempStorage tmp;
     __shared__ double carry_s;
@@ -142,12 +139,17 @@ __global__ void __launch_bounds__(1024) k_scan_tile_totals(const __grid_constant
     double *x = a.tile_excl + (int64_t)blockIdx.x * (a.ntiles + 1);
     if (threadIdx.x == 0) carry_s = 0.0;
     __syncthreads();
-    for (int32_t b = 0; b < a.ntiles + 1; b += 1024) {
-        const int32_t k = b + threadIdx.x;
-        double v = k < a.ntiles ? t[k] : 0.0, ex, tot;
-        BlockScan(tmp).ExclusiveSum(v, ex, tot);
+    for (int32_t b = 0; b < a.ntiles + 1; b += 1024 * PER) {
+        const int32_t k0 = b + threadIdx.x * PER;
+        double v[PER];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) v[j] = k0 + j < a.ntiles ? t[k0 + j] : 0.0;
+        double tot;
+        BlockScan(tmp).ExclusiveSum(v, v, tot);
         const double carry = carry_s;
-        if (k < a.ntiles + 1) x[k] = carry + ex;
+#pragma unroll
+        for (int j = 0; j < PER; ++j)
+            if (k0 + j < a.ntiles + 1) x[k0 + j] = carry + v[j];
         __syncthreads();
         if (threadIdx.x == 0) carry_s = carry + tot;
         __syncthreads();

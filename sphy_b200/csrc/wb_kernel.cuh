@@ -54,6 +54,24 @@ struct Lanes<4> {
     static __device__ __forceinline__ V4 par(const sphy_param &q, int64_t i) { return q.map ? ld4(q.map, i) : splat(q.value); }
 };
 template <>
+struct Lanes<2> {
+    static __device__ __forceinline__ V4 in(const float *p, int64_t i)
+    {
+        float2 t = __ldg(reinterpret_cast<const float2 *>(p + i));
+        return V4{{t.x, t.y, 0.f, 0.f}};
+    }
+    static __device__ __forceinline__ V4 inrw(const float *p, int64_t i)
+    {
+        float2 t = *reinterpret_cast<const float2 *>(p + i);
+        return V4{{t.x, t.y, 0.f, 0.f}};
+    }
+    static __device__ __forceinline__ void out(float *p, int64_t i, const V4 &a)
+    {
+        *reinterpret_cast<float2 *>(p + i) = make_float2(a.v[0], a.v[1]);
+    }
+    static __device__ __forceinline__ V4 par(const sphy_param &q, int64_t i) { return q.map ? in(q.map, i) : splat(q.value); }
+};
+template <>
 struct Lanes<1> {
     static __device__ __forceinline__ V4 in(const float *p, int64_t i) { return splat(__ldg(p + i)); }
     static __device__ __forceinline__ V4 inrw(const float *p, int64_t i) { return splat(p[i]); }
@@ -98,6 +116,10 @@ __device__ __forceinline__ void wb_cells(const WbArgs &a, int64_t i)
             ra.v[1] = __ldg(a.ra_table + (c.x >> 16));
             ra.v[2] = __ldg(a.ra_table + (c.y & 0xffffu));
             ra.v[3] = __ldg(a.ra_table + (c.y >> 16));
+        } else if (W == 2) {
+            unsigned c = __ldg(reinterpret_cast<const unsigned *>(p.lat_class + i));
+            ra.v[0] = __ldg(a.ra_table + (c & 0xffffu));
+            ra.v[1] = __ldg(a.ra_table + (c >> 16));
         } else {
             ra = splat(__ldg(a.ra_table + __ldg(p.lat_class + i)));
         }
@@ -396,24 +418,24 @@ __device__ __forceinline__ void wb_cells(const WbArgs &a, int64_t i)
 
 constexpr int WB_THREADS = 128;
 
-template <bool SNOW, bool GROUND, bool INFIL, int RA, bool DIAG, bool USOIL>
+template <bool SNOW, bool GROUND, bool INFIL, int RA, bool DIAG, bool USOIL, int CPT>
 __global__ void __launch_bounds__(WB_THREADS) k_wb_step(const __grid_constant__ WbArgs a)
 {
-    const int64_t n4 = a.n >> 2;
+    const int64_t ng = a.n / CPT;                       // groups of CPT consecutive cells
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n4; q += stride)
-        wb_cells<SNOW, GROUND, INFIL, RA, DIAG, USOIL, 4>(a, q << 2);
-    // ragged tail (< 4 cells)
-    const int64_t tail0 = n4 << 2;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < ng; q += stride)
+        wb_cells<SNOW, GROUND, INFIL, RA, DIAG, USOIL, CPT>(a, q * CPT);
+    // ragged tail (< CPT cells)
+    const int64_t tail0 = ng * CPT;
     if (blockIdx.x == 0 && threadIdx.x < (a.n - tail0)) wb_cells<SNOW, GROUND, INFIL, RA, DIAG, USOIL, 1>(a, tail0 + threadIdx.x);
 }
 
 typedef void (*wb_kernel_t)(const WbArgs);
 
-template <bool S, bool G, bool U>
+template <bool S, bool G, bool U, int CPT>
 wb_kernel_t pick_sgu(bool infil, int ra, bool diag)
 {
-#define SPHY_WB_CASE(I, R, D) if (infil == I && ra == R && diag == D) return k_wb_step<S, G, I, R, D, U>;
+#define SPHY_WB_CASE(I, R, D) if (infil == I && ra == R && diag == D) return k_wb_step<S, G, I, R, D, U, CPT>;
     SPHY_WB_CASE(false, 0, false) SPHY_WB_CASE(false, 1, false) SPHY_WB_CASE(false, 2, false)
     SPHY_WB_CASE(true, 0, false) SPHY_WB_CASE(true, 1, false) SPHY_WB_CASE(true, 2, false)
     SPHY_WB_CASE(false, 0, true) SPHY_WB_CASE(false, 1, true) SPHY_WB_CASE(false, 2, true)
@@ -423,15 +445,16 @@ wb_kernel_t pick_sgu(bool infil, int ra, bool diag)
 }
 
 template <bool S, bool G>
-wb_kernel_t pick_sg(bool infil, int ra, bool diag, bool usoil)
+wb_kernel_t pick_sg(bool infil, int ra, bool diag, bool usoil, int cpt)
 {
-    return usoil ? pick_sgu<S, G, true>(infil, ra, diag) : pick_sgu<S, G, false>(infil, ra, diag);
+    if (cpt == 2) return usoil ? pick_sgu<S, G, true, 2>(infil, ra, diag) : pick_sgu<S, G, false, 2>(infil, ra, diag);
+    return usoil ? pick_sgu<S, G, true, 4>(infil, ra, diag) : pick_sgu<S, G, false, 4>(infil, ra, diag);
 }
 
 }  // namespace wb
 
 // one per translation unit wb_inst_{s}{g}.cu
-wb::wb_kernel_t wb_pick_00(bool infil, int ra, bool diag, bool usoil);
-wb::wb_kernel_t wb_pick_01(bool infil, int ra, bool diag, bool usoil);
-wb::wb_kernel_t wb_pick_10(bool infil, int ra, bool diag, bool usoil);
-wb::wb_kernel_t wb_pick_11(bool infil, int ra, bool diag, bool usoil);
+wb::wb_kernel_t wb_pick_00(bool infil, int ra, bool diag, bool usoil, int cpt);
+wb::wb_kernel_t wb_pick_01(bool infil, int ra, bool diag, bool usoil, int cpt);
+wb::wb_kernel_t wb_pick_10(bool infil, int ra, bool diag, bool usoil, int cpt);
+wb::wb_kernel_t wb_pick_11(bool infil, int ra, bool diag, bool usoil, int cpt);
