@@ -447,7 +447,9 @@ wb_kernel_t pick_sgu(bool infil, int ra, bool diag)
 template <bool S, bool G>
 wb_kernel_t pick_sg(bool infil, int ra, bool diag, bool usoil, int cpt)
 {
-    if (cpt == 2) return usoil ? pick_sgu<S, G, true, 2>(infil, ra, diag) : pick_sgu<S, G, false, 2>(infil, ra, diag);
+    // measured on B200 (profiles/r1_k1_variants.md): 4 cells/thread at 96 registers (5 CTAs/SM) beats both
+    // 2 cells/thread (80 registers) and a 6-CTA register cap (spills), so only CPT = 4 is instantiated
+    (void)cpt;
     return usoil ? pick_sgu<S, G, true, 4>(infil, ra, diag) : pick_sgu<S, G, false, 4>(infil, ra, diag);
 }
 
