@@ -191,6 +191,21 @@ int sphy_glac_step(sphy_ctx *ctx, const sphy_glac_table *t, const float *tavg, c
 int sphy_route_step(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm, float *const *q_state, sphy_param kx,
                     float one_minus_kx /* REAL4(1-kx) when kx is a scalar: Python-double subtraction, routing.py:28 */,
                     int method, void *stream);
+/* Multi-GPU (one context per GPU, each built on the whole LDD): restrict this context to the contiguous device-index
+ * range [cell_begin, cell_end) of the DFS order (cell_begin on a 1024-cell tile).  After the call every compact map
+ * and sphy_ncells() refer to the local cells only.  pub_e: local indices at which other ranks' upstream ranges end
+ * (ascending); remote_*: for each local cell whose range ends on another rank (ascending), its slot in this
+ * context's tile-crossing list, the rank that owns the range end, and the slot in that rank's pub_e.  The lists are
+ * planned on the host (sphy_b200/multigpu.py) from the "sub_size" export.  The per-step confluence exchange is
+ *   sphy_route_scan_begin -> all-gather of `send` (stride doubles per component and rank) -> sphy_route_scan_finish
+ * and replaces the single-GPU sphy_route_step (modules/routing.py:25-29) on a partitioned context. */
+int sphy_set_partition(sphy_ctx *ctx, int64_t cell_begin, int64_t cell_end, int32_t n_pub, const int32_t *pub_e_dev,
+                       int32_t n_remote, const int32_t *remote_k_dev, const int32_t *remote_rank_dev,
+                       const int32_t *remote_slot_dev, void *stream);
+int sphy_route_scan_begin(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm, float *const *q_state, sphy_param kx,
+                          float one_minus_kx, double *send_dev, int32_t stride, void *stream);
+int sphy_route_scan_finish(sphy_ctx *ctx, int ncomp, float *const *q_state, sphy_param kx, float one_minus_kx,
+                           const double *gathered_dev, int32_t stride, int rank, int world, void *stream);
 /* plain pcr.accuflux(ldd, m) / pcr.catchmenttotal(m, ldd) (sphy.py:838, routing.py:27) and pcr.upstream */
 int sphy_accuflux(sphy_ctx *ctx, const float *material, const float *fraction /*nullable*/, float *flux, int method,
                   void *stream);

@@ -75,6 +75,7 @@ WB_SNOW, WB_GROUND, WB_INFIL_EXCESS, WB_PWS, WB_ETREF_INPUT = 1, 2, 4, 8, 16
 RA_TABLE, RA_CELL = 0, 1
 ROUTE_LEVELS, ROUTE_SCAN = 0, 1
 ORDER_ROWMAJOR, ORDER_DFS = 0, 1
+SCAN_TILE = 1024                      # cells per scan-routing tile (csrc/route_scan.cu)
 UNARY_EXP_NEG_INV, UNARY_SIN_DEG, UNARY_COS_DEG, UNARY_TAN_DEG, UNARY_EXP_NEG = 0, 1, 2, 3, 4
 
 # every symbol include/sphy_b200.h declares: name -> (restype, argtypes)
@@ -98,6 +99,9 @@ SYMBOLS = {
                                C.c_int, P]),
     "sphy_glac_step": (C.c_int, [P, C.POINTER(GlacTable), P, P, C.c_float, C.c_float, C.POINTER(GlacOut), P]),
     "sphy_route_step": (C.c_int, [P, C.c_int, C.POINTER(P), C.POINTER(P), SphyParam, C.c_float, C.c_int, P]),
+    "sphy_set_partition": (C.c_int, [P, C.c_int64, C.c_int64, C.c_int32, P, C.c_int32, P, P, P, P]),
+    "sphy_route_scan_begin": (C.c_int, [P, C.c_int, C.POINTER(P), C.POINTER(P), SphyParam, C.c_float, P, C.c_int32, P]),
+    "sphy_route_scan_finish": (C.c_int, [P, C.c_int, C.POINTER(P), SphyParam, C.c_float, P, C.c_int32, C.c_int, C.c_int, P]),
     "sphy_accuflux": (C.c_int, [P, P, P, P, C.c_int, P]),
     "sphy_upstream": (C.c_int, [P, P, P, P]),
     "sphy_route_reslake_step": (C.c_int, [P, C.POINTER(ResLake), P, P, SphyParam, C.c_float, C.c_int, P]),

@@ -51,6 +51,13 @@ struct sphy_ctx {
     double *scan_excl = nullptr;   // [ncomp][ntiles+1] exclusive prefix of the tile totals
     int32_t n_tiles = 0;
     int scan_comp_cap = 0;
+    // multi-GPU partition: this context owns the device-index range [part_begin, part_begin + n) of the DFS order
+    bool partitioned = false;
+    int64_t part_begin = 0, n_global = 0;
+    int32_t *sub_size_loc = nullptr, *flat_loc = nullptr;   // views into sub_size / flat_active at part_begin
+    int32_t n_pub = 0, n_remote = 0;
+    int32_t *pub_e = nullptr;                                // local indices other ranks' ranges end at (ascending)
+    int32_t *remote_k = nullptr, *remote_rank = nullptr, *remote_slot = nullptr;   // per remote-ending crossing cell
     // workspaces
     float *acc = nullptr;          // [ROUTE_MAX_COMP][n] accumulated flux in routing order
     float *qsorted = nullptr;      // scratch [ROUTE_MAX_COMP][n]

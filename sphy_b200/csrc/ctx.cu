@@ -33,7 +33,8 @@ extern "C" void sphy_ctx_destroy(sphy_ctx *ctx)
                     ctx->cidx, ctx->flat_active, ctx->down, ctx->level, ctx->order, ctx->level_ptr, ctx->don_ptr,
                     ctx->don_idx, ctx->indeg, ctx->nup, ctx->pos, ctx->dpos_ptr, ctx->dpos, ctx->pre, ctx->cell_canon,
                     ctx->sub_size, ctx->cross_r, ctx->cross_ptr, ctx->end_e, ctx->end_k, ctx->end_ptr, ctx->park_before,
-                    ctx->park_end, ctx->scan_tile, ctx->scan_excl, ctx->acc, ctx->qsorted,
+                    ctx->park_end, ctx->scan_tile, ctx->scan_excl, ctx->acc, ctx->qsorted, ctx->pub_e, ctx->remote_k,
+                    ctx->remote_rank, ctx->remote_slot,
                     ctx->ra_table, ctx->tmp_n[0], ctx->tmp_n[1], ctx->tmp_n[2], ctx->tmp_n[3]};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -77,7 +78,7 @@ extern "C" int sphy_gather_f32(sphy_ctx *ctx, const float *raster, float *compac
 {
     if (!ctx || !raster || !compact) return SPHY_E_INVALID;
     if (!ctx->ldd_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_gather_f32 before sphy_ldd_build");
-    k_gather<<<div_up(ctx->n, 256), 256, 0, (cudaStream_t)stream>>>(raster, ctx->flat_active, ctx->n, compact);
+    k_gather<<<div_up(ctx->n, 256), 256, 0, (cudaStream_t)stream>>>(raster, ctx->flat_loc, ctx->n, compact);
     SPHY_LAUNCH_CHECK(ctx);
     return SPHY_OK;
 }
@@ -86,6 +87,7 @@ extern "C" int sphy_scatter_f32(sphy_ctx *ctx, const float *compact, float *rast
 {
     if (!ctx || !raster || !compact) return SPHY_E_INVALID;
     if (!ctx->ldd_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_scatter_f32 before sphy_ldd_build");
+    if (ctx->partitioned) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_scatter_f32 is not available on a partitioned context");
     k_scatter<<<div_up(ctx->nraster, 256), 256, 0, (cudaStream_t)stream>>>(compact, ctx->cidx, ctx->nraster, fill, raster);
     SPHY_LAUNCH_CHECK(ctx);
     return SPHY_OK;

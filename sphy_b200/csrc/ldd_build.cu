@@ -314,6 +314,11 @@ static int finalize_cell_order(sphy_ctx *ctx, cudaStream_t st)
 #undef FK
     cudaFree(val); cudaFree(off); cudaFree(deg); cudaFree(tmp);
     if (e != cudaSuccess) SPHY_FAIL(ctx, SPHY_E_CUDA, "finalize_cell_order: %s", cudaGetErrorString(e));
+    ctx->sub_size_loc = ctx->sub_size;
+    ctx->flat_loc = ctx->flat_active;
+    ctx->partitioned = false;
+    ctx->part_begin = 0;
+    ctx->n_global = n;
     return SPHY_OK;
 }
 

@@ -187,6 +187,7 @@ extern "C" int sphy_route_step(sphy_ctx *ctx, int ncomp, const float *const *run
     if (!ctx->ldd_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_route_step before sphy_ldd_build");
     for (int c = 0; c < ncomp; ++c)
         if (!runoff_mm[c] || !q_state[c]) SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_route_step: component %d has a NULL map", c);
+    if (ctx->partitioned) SPHY_FAIL(ctx, SPHY_E_STATE, "partitioned context: use sphy_route_scan_begin / sphy_route_scan_finish");
     if (method == SPHY_ROUTE_SCAN) return route_scan_run(ctx, ncomp, runoff_mm, q_state, kx, one_minus_kx, (cudaStream_t)stream);
     if (method != SPHY_ROUTE_LEVELS) SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_route_step: unknown method %d", method);
     SweepArgs a = {};
@@ -205,6 +206,7 @@ extern "C" int sphy_accuflux(sphy_ctx *ctx, const float *mat, const float *fract
 {
     if (!ctx || !mat || !flux) return SPHY_E_INVALID;
     if (!ctx->ldd_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_accuflux before sphy_ldd_build");
+    if (ctx->partitioned) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_accuflux is not available on a partitioned context");
     if (method != SPHY_ROUTE_LEVELS) SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_accuflux: only SPHY_ROUTE_LEVELS is available");
     SweepArgs a = {};
     a.ncomp = 1;
@@ -219,6 +221,7 @@ extern "C" int sphy_upstream(sphy_ctx *ctx, const float *x, float *out, void *st
 {
     if (!ctx || !x || !out) return SPHY_E_INVALID;
     if (!ctx->ldd_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_upstream before sphy_ldd_build");
+    if (ctx->partitioned) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_upstream is not available on a partitioned context");
     k_upstream<<<div_up(ctx->n, 256), 256, 0, (cudaStream_t)stream>>>(x, ctx->don_ptr, ctx->don_idx, ctx->n, out);
     SPHY_LAUNCH_CHECK(ctx);
     return SPHY_OK;
@@ -327,6 +330,7 @@ extern "C" int sphy_route_reslake_step(sphy_ctx *ctx, const sphy_reslake *rl, co
 {
     if (!ctx || !rl || !totr || !q_state) return SPHY_E_INVALID;
     if (!ctx->ldd_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_route_reslake_step before sphy_ldd_build");
+    if (ctx->partitioned) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_route_reslake_step is not available on a partitioned context");
     if (rl->n_struct < 0 || !rl->qfrac || (rl->n_struct > 0 && (!rl->cell || !rl->kind || !rl->par || !rl->StorRES || !rl->Qout || !rl->Qin)))
         SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_route_reslake_step: incomplete structure table");
     cudaStream_t st = (cudaStream_t)stream;

@@ -37,6 +37,12 @@ struct ScanArgs {
     double *park_end;                     // [ncomp][n_cross] tile-local inclusive prefix at its range end
     double *tile_tot;                     // [ncomp][ntiles]   tile totals
     double *tile_excl;                    // [ncomp][ntiles+1] exclusive prefix of the totals
+    // multi-GPU (partitioned context)
+    int32_t n_pub, n_remote;
+    const int32_t *pub_e, *remote_k, *remote_rank, *remote_slot;
+    double *send;                         // [ncomp][stride]: range total, then range-local inclusive prefix at pub_e[j]
+    const double *gathered;               // [world][ncomp][stride]
+    int32_t stride, rank, world;
     sphy_param kx;
     float one_m_kx, cellarea;
     int64_t n;
@@ -116,7 +122,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_main(const __grid_cons
                 if (base + j < a.n) qs[base + j] = q[j];
         }
         // park what the crossing cells of / ending in this tile will need
-        double *pb = a.park_before + (int64_t)c * a.n_cross, *pe = a.park_end + (int64_t)c * a.n_cross;
+        double *pb = a.park_before + (int64_t)c * a.n_cross, *pe = a.park_end + (int64_t)c * (a.n_cross + a.n_pub);
         for (int32_t k = cb + threadIdx.x; k < ce; k += SCAN_THREADS) {
             const int off = (int)(__ldg(a.cross_r + k) - tbase);
             pb[k] = off == 0 ? 0.0 : Ls[off - 1];
@@ -169,11 +175,47 @@ __global__ void __launch_bounds__(256) k_scan_cross(const __grid_constant__ Scan
     for (int c = 0; c < a.ncomp; ++c) {
         const double *T = a.tile_tot + (int64_t)c * a.ntiles;
         const double *X = a.tile_excl + (int64_t)c * (a.ntiles + 1);
+        if (e >= a.n) {                                        // range ends on another rank: keep the part up to the
+            double *pb = a.park_before + (int64_t)c * a.n_cross + k;   // end of this rank's range for k_scan_remote
+            *pb = (T[ta] - *pb) + (X[a.ntiles] - X[ta + 1]);
+            continue;
+        }
         const double s = (T[ta] - a.park_before[(int64_t)c * a.n_cross + k]) + (X[te] - X[ta + 1]) +
-                         a.park_end[(int64_t)c * a.n_cross + k];
+                         a.park_end[(int64_t)c * (a.n_cross + a.n_pub) + k];
         const float f = (float)s;
         float *qs = a.qstate[c];
         qs[r] = omk * f + kx * qs[r];                          // routing.py:28
+    }
+}
+
+// multi-GPU: what the other ranks need from this one -- the range total and the range-local inclusive prefix at
+// every position one of their trunk cells' upstream range ends at
+__global__ void k_scan_publish(const __grid_constant__ ScanArgs a)
+{
+    const int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int c = 0; c < a.ncomp; ++c) {
+        const double *X = a.tile_excl + (int64_t)c * (a.ntiles + 1);
+        double *out = a.send + (int64_t)c * a.stride;
+        if (j == 0) out[0] = X[a.ntiles];
+        if (j < a.n_pub) out[1 + j] = X[a.pub_e[j] / SCAN_TILE] + a.park_end[(int64_t)c * (a.n_cross + a.n_pub) + a.n_cross + j];
+    }
+}
+
+// multi-GPU: finish the cells whose upstream range ends on another rank, after the all-gather
+__global__ void k_scan_remote(const __grid_constant__ ScanArgs a)
+{
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_remote) return;
+    const int32_t k = a.remote_k[i], q = a.remote_rank[i], slot = a.remote_slot[i];
+    const int64_t r = a.cross_r[k];
+    const float kx = a.kx.map ? __ldg(a.kx.map + r) : a.kx.value;
+    const float omk = a.kx.map ? 1.0f - kx : a.one_m_kx;
+    for (int c = 0; c < a.ncomp; ++c) {
+        double s = a.park_before[(int64_t)c * a.n_cross + k];                     // r .. end of this rank's range
+        for (int u = a.rank + 1; u < q; ++u) s += a.gathered[((int64_t)u * a.ncomp + c) * a.stride];   // whole ranks in between
+        s += a.gathered[((int64_t)q * a.ncomp + c) * a.stride + 1 + slot];        // start of rank q's range .. range end
+        float *qs = a.qstate[c];
+        qs[r] = omk * (float)s + kx * qs[r];                                      // routing.py:28
     }
 }
 
@@ -184,11 +226,18 @@ __global__ void k_cross_flag(const int32_t *sub_size, int64_t n, uint8_t *flag)
     if (r < n) flag[r] = (r / SCAN_TILE) != ((r + sub_size[r] - 1) / SCAN_TILE);
 }
 
-__global__ void k_cross_ends(const int32_t *cross_r, const int32_t *sub_size, int32_t nc, int32_t *e, int32_t *k)
+// sort keys of the "end" list: range ends of the crossing cells (INT32_MAX = ends on another rank: sorted last and
+// cut off), followed by the positions published for other ranks (slots n_cross + j)
+__global__ void k_cross_ends(const int32_t *cross_r, const int32_t *sub_size, int32_t nc, int64_t n, const int32_t *pub_e,
+                             int32_t n_pub, int32_t *e, int32_t *k)
 {
     int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nc) {
-        e[i] = cross_r[i] + sub_size[cross_r[i]] - 1;
+        const int64_t end = (int64_t)cross_r[i] + sub_size[cross_r[i]] - 1;
+        e[i] = end < n ? (int32_t)end : INT32_MAX;
+        k[i] = i;
+    } else if (i < nc + n_pub) {
+        e[i] = pub_e[i - nc];
         k[i] = i;
     }
 }
@@ -225,7 +274,7 @@ static int build_cross_lists(sphy_ctx *ctx, cudaStream_t st)
     FK(cudaMalloc(&nsel, sizeof(int32_t)));
     int32_t nc = 0;
     if (e == cudaSuccess) {
-        k_cross_flag<<<div_up(n, 256), 256, 0, st>>>(ctx->sub_size, n, flag);
+        k_cross_flag<<<div_up(n, 256), 256, 0, st>>>(ctx->sub_size_loc, n, flag);
         cub::CountingInputIterator<int32_t> counting(0);
         FK(cub::DeviceSelect::Flagged(nullptr, tb, counting, flag, sel, nsel, (int)n, st));
         FK(cudaMalloc(&tmp, tb));
@@ -234,30 +283,32 @@ static int build_cross_lists(sphy_ctx *ctx, cudaStream_t st)
         FK(cudaStreamSynchronize(st));
     }
     ctx->n_cross = nc;
-    const size_t ncs = nc > 0 ? (size_t)nc : 1;
+    const int32_t nend_all = nc + ctx->n_pub;
+    const size_t ncs = nc > 0 ? (size_t)nc : 1, nes = nend_all > 0 ? (size_t)nend_all : 1;
     int rc = SPHY_OK;
     if (e == cudaSuccess &&
         ((rc = dev_alloc(ctx, &ctx->cross_r, ncs)) || (rc = dev_alloc(ctx, &ctx->cross_ptr, (size_t)ntiles + 1)) ||
-         (rc = dev_alloc(ctx, &ctx->end_e, ncs)) || (rc = dev_alloc(ctx, &ctx->end_k, ncs)) ||
+         (rc = dev_alloc(ctx, &ctx->end_e, nes)) || (rc = dev_alloc(ctx, &ctx->end_k, nes)) ||
          (rc = dev_alloc(ctx, &ctx->end_ptr, (size_t)ntiles + 1)))) {
         cudaFree(flag); cudaFree(sel); cudaFree(nsel); cudaFree(tmp);
         return rc;
     }
-    if (e == cudaSuccess && nc > 0) {
-        FK(cudaMemcpyAsync(ctx->cross_r, sel, sizeof(int32_t) * nc, cudaMemcpyDeviceToDevice, st));
-        FK(cudaMalloc(&e_in, sizeof(int32_t) * nc));
-        FK(cudaMalloc(&k_in, sizeof(int32_t) * nc));
+    if (e == cudaSuccess && nc > 0) FK(cudaMemcpyAsync(ctx->cross_r, sel, sizeof(int32_t) * nc, cudaMemcpyDeviceToDevice, st));
+    if (e == cudaSuccess && nend_all > 0) {
+        FK(cudaMalloc(&e_in, sizeof(int32_t) * nend_all));
+        FK(cudaMalloc(&k_in, sizeof(int32_t) * nend_all));
         if (e == cudaSuccess) {
-            k_cross_ends<<<div_up(nc, 256), 256, 0, st>>>(ctx->cross_r, ctx->sub_size, nc, e_in, k_in);
+            k_cross_ends<<<div_up(nend_all, 256), 256, 0, st>>>(ctx->cross_r, ctx->sub_size_loc, nc, n, ctx->pub_e, ctx->n_pub, e_in, k_in);
             size_t need = 0;
-            FK(cub::DeviceRadixSort::SortPairs(nullptr, need, e_in, ctx->end_e, k_in, ctx->end_k, nc, 0, 32, st));
+            FK(cub::DeviceRadixSort::SortPairs(nullptr, need, e_in, ctx->end_e, k_in, ctx->end_k, nend_all, 0, 32, st));
             if (need > tb) { cudaFree(tmp); tmp = nullptr; FK(cudaMalloc(&tmp, need)); tb = need; }
-            FK(cub::DeviceRadixSort::SortPairs(tmp, need, e_in, ctx->end_e, k_in, ctx->end_k, nc, 0, 32, st));
+            FK(cub::DeviceRadixSort::SortPairs(tmp, need, e_in, ctx->end_e, k_in, ctx->end_k, nend_all, 0, 32, st));
         }
     }
     if (e == cudaSuccess) {
+        // keys >= ntiles*TILE (the INT32_MAX remote ends) fall behind end_ptr[ntiles] and are never visited
         k_tile_lower_bound<<<div_up(ntiles + 1, 256), 256, 0, st>>>(ctx->cross_r, nc, ntiles, ctx->cross_ptr);
-        k_tile_lower_bound<<<div_up(ntiles + 1, 256), 256, 0, st>>>(ctx->end_e, nc, ntiles, ctx->end_ptr);
+        k_tile_lower_bound<<<div_up(ntiles + 1, 256), 256, 0, st>>>(ctx->end_e, nend_all, ntiles, ctx->end_ptr);
         FK(cudaGetLastError());
         FK(cudaStreamSynchronize(st));
     }
@@ -268,8 +319,8 @@ static int build_cross_lists(sphy_ctx *ctx, cudaStream_t st)
     return SPHY_OK;
 }
 
-int route_scan_run(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm, float *const *q_state, sphy_param kx,
-                   float one_m_kx, cudaStream_t st)
+static int scan_prepare(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm, float *const *q_state, sphy_param kx,
+                        float one_m_kx, cudaStream_t st, ScanArgs &a)
 {
     if (ctx->order_mode != SPHY_ORDER_DFS)
         SPHY_FAIL(ctx, SPHY_E_STATE, "SPHY_ROUTE_SCAN needs the cells in SPHY_ORDER_DFS (sphy_set_cell_order)");
@@ -280,22 +331,23 @@ int route_scan_run(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm, floa
     if (ctx->scan_comp_cap < ncomp) {             // grows only when more components are first routed
         int rc;
         const size_t ncs = ctx->n_cross > 0 ? (size_t)ctx->n_cross : 1;
-        if ((rc = dev_alloc(ctx, &ctx->park_before, (size_t)ncomp * ncs)) || (rc = dev_alloc(ctx, &ctx->park_end, (size_t)ncomp * ncs)) ||
+        if ((rc = dev_alloc(ctx, &ctx->park_before, (size_t)ncomp * ncs)) ||
+            (rc = dev_alloc(ctx, &ctx->park_end, (size_t)ncomp * (ncs + ctx->n_pub))) ||
             (rc = dev_alloc(ctx, &ctx->scan_tile, (size_t)ncomp * ctx->n_tiles)) ||
             (rc = dev_alloc(ctx, &ctx->scan_excl, (size_t)ncomp * (ctx->n_tiles + 1))))
             return rc;
         ctx->scan_comp_cap = ncomp;
     }
     for (int c = 0; c < ncomp; ++c)
-        if ((reinterpret_cast<uintptr_t>(runoff_mm[c]) | reinterpret_cast<uintptr_t>(q_state[c])) & 15u)
-            SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_route_step: maps must be 16-byte aligned");
-    ScanArgs a = {};
+        if ((reinterpret_cast<uintptr_t>(runoff_mm ? runoff_mm[c] : nullptr) | reinterpret_cast<uintptr_t>(q_state[c])) & 15u)
+            SPHY_FAIL(ctx, SPHY_E_INVALID, "scan routing: maps must be 16-byte aligned");
+    a = ScanArgs{};
     a.ncomp = ncomp;
     for (int c = 0; c < ncomp; ++c) {
-        a.m[c] = runoff_mm[c];
+        a.m[c] = runoff_mm ? runoff_mm[c] : nullptr;
         a.qstate[c] = q_state[c];
     }
-    a.sub_size = ctx->sub_size;
+    a.sub_size = ctx->sub_size_loc;
     a.cross_r = ctx->cross_r;
     a.cross_ptr = ctx->cross_ptr;
     a.end_e = ctx->end_e;
@@ -306,14 +358,104 @@ int route_scan_run(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm, floa
     a.park_end = ctx->park_end;
     a.tile_tot = ctx->scan_tile;
     a.tile_excl = ctx->scan_excl;
+    a.n_pub = ctx->n_pub;
+    a.n_remote = ctx->n_remote;
+    a.pub_e = ctx->pub_e;
+    a.remote_k = ctx->remote_k;
+    a.remote_rank = ctx->remote_rank;
+    a.remote_slot = ctx->remote_slot;
     a.kx = kx;
     a.one_m_kx = one_m_kx;
     a.cellarea = ctx->cellarea;
     a.n = ctx->n;
     a.ntiles = ctx->n_tiles;
+    return SPHY_OK;
+}
+
+int route_scan_run(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm, float *const *q_state, sphy_param kx,
+                   float one_m_kx, cudaStream_t st)
+{
+    ScanArgs a;
+    int rc = scan_prepare(ctx, ncomp, runoff_mm, q_state, kx, one_m_kx, st, a);
+    if (rc != SPHY_OK) return rc;
     k_scan_main<<<ctx->n_tiles, SCAN_THREADS, 0, st>>>(a);
     k_scan_tile_totals<<<ncomp, 1024, 0, st>>>(a);
     if (ctx->n_cross > 0) k_scan_cross<<<div_up(ctx->n_cross, 256), 256, 0, st>>>(a);
+    SPHY_LAUNCH_CHECK(ctx);
+    return SPHY_OK;
+}
+
+// ---- multi-GPU -------------------------------------------------------------------------------------------------
+extern "C" int sphy_set_partition(sphy_ctx *ctx, int64_t cell_begin, int64_t cell_end, int32_t n_pub, const int32_t *pub_e_dev,
+                                  int32_t n_remote, const int32_t *remote_k_dev, const int32_t *remote_rank_dev,
+                                  const int32_t *remote_slot_dev, void *stream)
+{
+    if (!ctx) return SPHY_E_INVALID;
+    if (!ctx->ldd_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_set_partition before sphy_ldd_build");
+    if (ctx->order_mode != SPHY_ORDER_DFS) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_set_partition needs SPHY_ORDER_DFS");
+    if (ctx->partitioned) SPHY_FAIL(ctx, SPHY_E_STATE, "context is already partitioned");
+    if (cell_begin < 0 || cell_end > ctx->n_global || cell_begin >= cell_end || (cell_begin % SCAN_TILE) != 0 || n_pub < 0 ||
+        n_remote < 0 || (n_pub > 0 && !pub_e_dev) || (n_remote > 0 && (!remote_k_dev || !remote_rank_dev || !remote_slot_dev)))
+        SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_set_partition: bad range or lists (the range must start on a %d-cell tile)", SCAN_TILE);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if ((rc = dev_alloc(ctx, &ctx->pub_e, (size_t)n_pub)) || (rc = dev_alloc(ctx, &ctx->remote_k, (size_t)n_remote)) ||
+        (rc = dev_alloc(ctx, &ctx->remote_rank, (size_t)n_remote)) || (rc = dev_alloc(ctx, &ctx->remote_slot, (size_t)n_remote)))
+        return rc;
+    if (n_pub) SPHY_CUDA(ctx, cudaMemcpyAsync(ctx->pub_e, pub_e_dev, sizeof(int32_t) * n_pub, cudaMemcpyDeviceToDevice, st));
+    if (n_remote) {
+        SPHY_CUDA(ctx, cudaMemcpyAsync(ctx->remote_k, remote_k_dev, sizeof(int32_t) * n_remote, cudaMemcpyDeviceToDevice, st));
+        SPHY_CUDA(ctx, cudaMemcpyAsync(ctx->remote_rank, remote_rank_dev, sizeof(int32_t) * n_remote, cudaMemcpyDeviceToDevice, st));
+        SPHY_CUDA(ctx, cudaMemcpyAsync(ctx->remote_slot, remote_slot_dev, sizeof(int32_t) * n_remote, cudaMemcpyDeviceToDevice, st));
+    }
+    SPHY_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->n_pub = n_pub;
+    ctx->n_remote = n_remote;
+    ctx->part_begin = cell_begin;
+    ctx->n = cell_end - cell_begin;
+    ctx->sub_size_loc = ctx->sub_size + cell_begin;
+    ctx->flat_loc = ctx->flat_active + cell_begin;
+    ctx->partitioned = true;
+    ctx->scan_ready = false;
+    ctx->scan_comp_cap = 0;
+    return SPHY_OK;
+}
+
+extern "C" int sphy_route_scan_begin(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm, float *const *q_state, sphy_param kx,
+                                     float one_minus_kx, double *send_dev, int32_t stride, void *stream)
+{
+    if (!ctx || !runoff_mm || !q_state || !send_dev || ncomp < 1 || ncomp > ROUTE_MAX_COMP) return SPHY_E_INVALID;
+    if (!ctx->ldd_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_route_scan_begin before sphy_ldd_build");
+    if (stride < 1 + ctx->n_pub) SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_route_scan_begin: stride %d < 1 + n_pub %d", stride, ctx->n_pub);
+    cudaStream_t st = (cudaStream_t)stream;
+    ScanArgs a;
+    int rc = scan_prepare(ctx, ncomp, runoff_mm, q_state, kx, one_minus_kx, st, a);
+    if (rc != SPHY_OK) return rc;
+    a.send = send_dev;
+    a.stride = stride;
+    k_scan_main<<<ctx->n_tiles, SCAN_THREADS, 0, st>>>(a);
+    k_scan_tile_totals<<<ncomp, 1024, 0, st>>>(a);
+    if (ctx->n_cross > 0) k_scan_cross<<<div_up(ctx->n_cross, 256), 256, 0, st>>>(a);
+    k_scan_publish<<<div_up(ctx->n_pub > 0 ? ctx->n_pub : 1, 256), 256, 0, st>>>(a);
+    SPHY_LAUNCH_CHECK(ctx);
+    return SPHY_OK;
+}
+
+extern "C" int sphy_route_scan_finish(sphy_ctx *ctx, int ncomp, float *const *q_state, sphy_param kx, float one_minus_kx,
+                                      const double *gathered_dev, int32_t stride, int rank, int world, void *stream)
+{
+    if (!ctx || !q_state || !gathered_dev || ncomp < 1 || ncomp > ROUTE_MAX_COMP || rank < 0 || rank >= world) return SPHY_E_INVALID;
+    if (!ctx->scan_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_route_scan_finish before sphy_route_scan_begin");
+    if (ctx->n_remote == 0) return SPHY_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    ScanArgs a;
+    int rc = scan_prepare(ctx, ncomp, nullptr, q_state, kx, one_minus_kx, st, a);
+    if (rc != SPHY_OK) return rc;
+    a.gathered = gathered_dev;
+    a.stride = stride;
+    a.rank = rank;
+    a.world = world;
+    k_scan_remote<<<div_up(ctx->n_remote, 256), 256, 0, st>>>(a);
     SPHY_LAUNCH_CHECK(ctx);
     return SPHY_OK;
 }

@@ -111,7 +111,7 @@ def _table_col(rows, col):
 # ----------------------------------------------------------------------------------------------
 class SphyModel:
     def __init__(self, cfg, maps: MapSource, device="cuda:0", route_method="scan", diagnostics=False,
-                 collect_tss=True, cell_order="dfs"):
+                 collect_tss=True, cell_order="dfs", rank=0, world=1):
         if not torch.cuda.is_available():
             raise RuntimeError("SphyModel needs a CUDA device (B200); there is no CPU fallback")
         self.lib = _lib.load()
@@ -124,6 +124,9 @@ class SphyModel:
         self.cell_order_mode = {"rowmajor": _lib.ORDER_ROWMAJOR, "dfs": _lib.ORDER_DFS}[cell_order]
         if self.route_method == _lib.ROUTE_SCAN and self.cell_order_mode != _lib.ORDER_DFS:
             raise ValueError("route_method='scan' needs cell_order='dfs'")
+        self.rank, self.world = int(rank), int(world)
+        if self.world > 1 and (self.route_method != _lib.ROUTE_SCAN):
+            raise ValueError("multi-GPU partitioning needs route_method='scan'")
         if isinstance(cfg, configparser.RawConfigParser):
             self.config = cfg
         else:
@@ -216,16 +219,45 @@ class SphyModel:
             self._ck(self.lib.sphy_ldd_export(self._ctx, b"cell_order", flat.data_ptr(), flat.numel() * 4, self._stream()),
                      "sphy_ldd_export")
             self.cell_order = flat.cpu().numpy().astype(np.int64)       # device cell index -> canonical compact index
+            self.n_global = self.n
+            if self.world > 1:
+                self._partition(flat)
         else:
             self.flat_active = np.flatnonzero(self.clone_mask.ravel())
             self.cell_order = np.arange(self.flat_active.size)
             self.n = int(self.flat_active.size)
+            self.n_global = self.n
+            if self.world > 1:
+                raise ValueError("multi-GPU partitioning needs the routing structures (RoutFLAG = 1)")
             self.nlevels = 0
             self._ck(self.lib.sphy_set_ncells(self._ctx, self.n), "sphy_set_ncells")
         self.full_raster = (self.n == self.nrows * self.ncols and
                             bool(np.array_equal(self.flat_active, np.arange(self.n))))   # compact order == raster order
         self._cidx_host = np.full(self.nrows * self.ncols, -1, np.int64)
         self._cidx_host[self.flat_active] = np.arange(self.n)
+
+    def _partition(self, scratch):
+        """Restrict this rank to its contiguous DFS-order range (sphy_b200/multigpu.py plans the exchange lists)."""
+        from . import multigpu
+        if self.ResFLAG == 1 or self.LakeFLAG == 1:
+            raise NotImplementedError("lakes/reservoirs are not supported on a partitioned basin yet")
+        self._ck(self.lib.sphy_ldd_export(self._ctx, b"sub_size", scratch.data_ptr(), scratch.numel() * 4, self._stream()),
+                 "sphy_ldd_export")
+        sub_size = scratch.cpu().numpy()
+        bounds, ranks, stride = multigpu.plan(sub_size, self.world)
+        me = ranks[self.rank]
+        lo, hi = int(bounds[self.rank]), int(bounds[self.rank + 1])
+        d = {k: self._dev(np.ascontiguousarray(me[k], np.int32)) for k in ("pub_e", "remote_k", "remote_rank", "remote_slot")}
+        ptr = lambda t: t.data_ptr() if t.numel() else None  # noqa: E731
+        self._ck(self.lib.sphy_set_partition(self._ctx, lo, hi, len(me["pub_e"]), ptr(d["pub_e"]), len(me["remote_k"]),
+                                             ptr(d["remote_k"]), ptr(d["remote_rank"]), ptr(d["remote_slot"]), self._stream()),
+                 "sphy_set_partition")
+        self.part_range = (lo, hi)
+        self.flat_active = self.flat_active[lo:hi]
+        self.cell_order = self.cell_order[lo:hi]
+        self.n = hi - lo
+        self._mg_stride = int(stride)
+        self._mg_plan = me
 
     def ldd_structure(self, name):
         """Device copy of one Appendix-C structure (bit-exact parity checks)."""
@@ -710,10 +742,11 @@ class SphyModel:
         """fn(counter) -> dict of compact float32 CUDA tensors (prec, tavg, tmin, tmax[, etref]) already resident in HBM."""
         self._forcing_dev = fn
 
-    def set_host_forcing(self, fn):
+    def set_host_forcing(self, fn, compact=False):
         """fn(counter) -> dict of float32 PINNED host tensors holding the day's forcing RASTERS (nrows*ncols, the
         layout readmap delivers); each step copies them host->device and compacts them into device cell order."""
         self._forcing_host = fn
+        self._forcing_host_compact = compact      # True: fn already returns this rank's cells in device order
 
     def enable_profiling(self, on=True):
         """Record CUDA events around the water-balance and routing launches of every dynamic() call."""
@@ -727,7 +760,7 @@ class SphyModel:
             if getattr(self, "_fdev", None) is None:
                 self._fdev = {k: torch.empty(self.n, dtype=torch.float32, device=self.device) for k in keys}
             host = self._forcing_host(counter)
-            if self.full_raster:
+            if self.full_raster or getattr(self, "_forcing_host_compact", False):
                 for k in keys:
                     self._fdev[k].copy_(host[k], non_blocking=True)
                 return self._fdev
@@ -796,8 +829,11 @@ class SphyModel:
             nc = len(src)
             srcp = (C.c_void_p * nc)(*[t.data_ptr() for t in src])
             dstp = (C.c_void_p * nc)(*[t.data_ptr() for t in dst])
-            self._ck(lib.sphy_route_step(ctx, nc, srcp, dstp, self._kx, C.c_float(self._one_m_kx), self.route_method, st),
-                     "sphy_route_step")
+            if self.world > 1:
+                self._route_partitioned(nc, srcp, dstp, st)
+            else:
+                self._ck(lib.sphy_route_step(ctx, nc, srcp, dstp, self._kx, C.c_float(self._one_m_kx), self.route_method, st),
+                         "sphy_route_step")
             self.Q = self.QRAold
         if prof is not None:
             ev[2].record()
@@ -809,6 +845,19 @@ class SphyModel:
             self.tss["QallRAtot"].append(self._station_buf[: len(self.station_ids)].clone())
         self.curdate = self.curdate + datetime.timedelta(days=1)
         return self.Q if self.Q is not None else self.TotR
+
+    def _route_partitioned(self, nc, srcp, dstp, st):
+        """Per-step confluence exchange: local scan -> all-gather of range totals / prefixes over NCCL -> trunk fix-up."""
+        import torch.distributed as dist
+        if getattr(self, "_mg_send", None) is None or self._mg_send.shape[0] != nc:
+            self._mg_send = torch.zeros((nc, self._mg_stride), dtype=torch.float64, device=self.device)
+            self._mg_recv = torch.zeros((self.world, nc, self._mg_stride), dtype=torch.float64, device=self.device)
+        self._ck(self.lib.sphy_route_scan_begin(self._ctx, nc, srcp, dstp, self._kx, C.c_float(self._one_m_kx),
+                                                self._mg_send.data_ptr(), self._mg_stride, st), "sphy_route_scan_begin")
+        dist.all_gather_into_tensor(self._mg_recv.view(-1), self._mg_send.view(-1))
+        self._ck(self.lib.sphy_route_scan_finish(self._ctx, nc, dstp, self._kx, C.c_float(self._one_m_kx),
+                                                 self._mg_recv.data_ptr(), self._mg_stride, self.rank, self.world, st),
+                 "sphy_route_scan_finish")
 
     def timesteps(self):
         """utilities/timecalc.py:32-36"""

@@ -1,0 +1,185 @@
+"""Multi-GPU: one large basin split along its drainage tree across the GPUs of one box.
+
+In the DFS device order the upstream area of every cell is a contiguous index range, so the basin is cut into P
+contiguous, tile-aligned index ranges (whole sub-basins plus pieces of the trunk), one per rank.  The vertical water
+balance is per-cell: no communication.  Routing: every rank scans its own range; the only cells that need remote
+data are the trunk cells whose upstream range ends on another rank (a few thousand out of 1e8).  Per step each rank
+publishes (i) the total of its range and (ii) the range-local prefix at the few positions other ranks' ranges end
+at; one small all-gather over NCCL/NVLink delivers these "confluence inflows" to everybody, and a sparse kernel
+finishes the trunk cells.  The reference has no counterpart (it is a single process).
+
+`plan()` is pure host logic (NumPy) and is what the CPU/gloo tests exercise.
+"""
+from __future__ import annotations
+
+import json
+import os
+import tempfile
+import time
+
+import numpy as np
+
+from . import _lib
+
+TILE = _lib.SCAN_TILE
+
+
+def partition_bounds(n, world, tile=TILE):
+    """P+1 cell boundaries: contiguous ranges of whole tiles, balanced by cell count."""
+    ntiles = -(-n // tile)
+    tb = np.round(np.arange(world + 1) * ntiles / world).astype(np.int64)
+    b = np.minimum(tb * tile, n)
+    b[-1] = n
+    if np.any(np.diff(b) <= 0):
+        raise ValueError(f"{n} cells are too few for {world} ranks of {tile}-cell tiles")
+    return b
+
+
+def plan(sub_size, world, tile=TILE):
+    """Exchange plan for every rank from the global `sub_size` (upstream cell count by device index, DFS order).
+
+    Returns (bounds, ranks) where ranks[p] is a dict with
+      pub_e        int32  local indices (ascending) whose range-local inclusive prefix rank p publishes
+      remote_k     int32  for each local cell whose range ends on another rank (ascending index): its slot in rank p's
+                          tile-crossing list (all local cells whose range leaves their tile, ascending)
+      remote_rank  int32  rank owning the end of that range
+      remote_slot  int32  slot of that end in the owner's pub_e
+      remote_r     int64  local index of those cells (for tests)
+    """
+    sub_size = np.asarray(sub_size)
+    n = sub_size.size
+    b = partition_bounds(n, world, tile)
+    ranks = [dict() for _ in range(world)]
+    wanted = [[] for _ in range(world)]                 # global end indices requested from each owner
+    per_rank_remote = []
+    for p in range(world):
+        lo, hi = int(b[p]), int(b[p + 1])
+        size = sub_size[lo:hi].astype(np.int64)
+        r_loc = np.arange(hi - lo, dtype=np.int64)
+        e_glob = lo + r_loc + size - 1
+        leaves_tile = (r_loc // tile) != ((r_loc + size - 1) // tile)
+        cross_list = np.flatnonzero(leaves_tile)        # == the C side's list (ascending)
+        remote = np.flatnonzero(e_glob >= hi)
+        owner = np.searchsorted(b, e_glob[remote], side="right") - 1
+        per_rank_remote.append((remote, e_glob[remote], owner, cross_list))
+        for q in np.unique(owner):
+            wanted[int(q)].append(e_glob[remote][owner == q])
+    pub_global = []
+    for q in range(world):
+        ends = np.unique(np.concatenate(wanted[q])) if wanted[q] else np.zeros(0, np.int64)
+        pub_global.append(ends)
+        ranks[q]["pub_e"] = (ends - b[q]).astype(np.int32)
+    for p in range(world):
+        remote, e_glob, owner, cross_list = per_rank_remote[p]
+        slot = np.zeros(remote.size, np.int64)
+        for q in np.unique(owner):
+            sel = owner == q
+            slot[sel] = np.searchsorted(pub_global[int(q)], e_glob[sel])
+        ranks[p]["remote_r"] = remote
+        ranks[p]["remote_k"] = np.searchsorted(cross_list, remote).astype(np.int32)
+        ranks[p]["remote_rank"] = owner.astype(np.int32)
+        ranks[p]["remote_slot"] = slot.astype(np.int32)
+    stride = 1 + max(len(r["pub_e"]) for r in ranks)
+    return b, ranks, stride
+
+
+# ----------------------------------------------------------------------------------------------
+def bench_main(args, rank, world):
+    """bench.py for N > 1: the BASELINE config-4 basin split across `world` GPUs (strong scaling)."""
+    import torch
+    import torch.distributed as dist
+
+    import bench
+    from .model import CatchmentSource, SphyModel
+
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    dist.init_process_group("nccl", device_id=dev)
+    t_setup = time.time()
+    cat = bench.make_case(args.size)
+    tmp = tempfile.mkdtemp(prefix=f"sphy_bench_r{rank}_")
+    cfg = cat.write_inputs(os.path.join(tmp, "in"), os.path.join(tmp, "out"))
+    model = SphyModel(cfg, CatchmentSource(cat), device=str(dev), route_method="scan", diagnostics=False, rank=rank, world=world)
+    model.initial()
+    n_local, n_global = model.n, model.n_global
+    dem_dev = torch.from_numpy(model._compact_np(cat.dem)).to(dev)
+    ring = bench.device_forcing_ring(torch, dem_dev, args.ring, seed=1234 + rank)
+    del dem_dev
+    torch.cuda.synchronize()
+    dist.barrier()
+    setup_s = time.time() - t_setup
+
+    def timed(nsteps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(nsteps):
+            model.dynamic()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)          # max over ranks
+        dist.barrier()
+        return float(ms.item())
+
+    model.set_device_forcing(lambda t: ring[t % len(ring)])
+    for _ in range(max(args.warmup, 3)):
+        model.dynamic()
+    model.enable_profiling(True)
+    sampler = bench.ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_total = timed(args.steps)
+    clocks = sampler.stop() if sampler else None
+    wb_ms = float(np.mean([a.elapsed_time(b) for a, b in model._prof["wb"]]))
+    rt_ms = float(np.mean([a.elapsed_time(b) for a, b in model._prof["route"]]))
+    model.enable_profiling(False)
+    value = n_global * args.steps / (ms_total * 1e-3) / 1e6
+
+    # e2e: every rank copies its own cells' forcing from pinned host memory each step, reads its stations back
+    host_ring = [{k: v.cpu().pin_memory() for k, v in day.items()} for day in ring[:2]]
+    model.set_device_forcing(None)
+    model.set_host_forcing(lambda t: host_ring[t % len(host_ring)], compact=True)
+    for _ in range(2):
+        model.dynamic()
+    e2e_steps = max(3, min(args.steps, 10))
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(e2e_steps):
+        model.dynamic()
+        if model.tss["QallRAtot"]:
+            q = model.tss["QallRAtot"][-1].cpu()
+            d2h += q.numel() * 4
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_val = n_global * e2e_steps / float(dt.item()) / 1e6
+    peak, peak_kind = bench.measured_peak()
+    ach = bench.ALG_BYTES_WB * n_local / (wb_ms * 1e-3) / 1e9
+    if rank == 0:
+        line = {
+            "metric": "Mcell-timesteps/s", "value": value, "unit": "Mcell-timesteps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": bench.workload_name(args.size), "cells": n_global, "cells_per_gpu": n_local,
+                       "partition": f"{world} contiguous DFS-order ranges (sub-basins + trunk pieces), per-step all-gather of "
+                                    f"{model._mg_stride} float64 per rank (confluence exchange over NCCL)",
+                       "routing": "scan", "forcing_ring_days": args.ring, "setup_s": round(setup_s, 1),
+                       "l2": "per-GPU per-step working set %.2f GB (larger than the 126 MB L2)" % (bench.ALG_BYTES_WB * n_local / 1e9)},
+            "roofline": {"kernel": "k_wb_step (fused vertical water balance), rank 0", "bound": "hbm", "achieved": ach, "peak": peak,
+                         "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                         "alg_bytes_per_cell": bench.ALG_BYTES_WB, "kernel_ms": wb_ms, "route_ms": rt_ms},
+            "cpu_baseline": None,
+            "e2e": {"value": e2e_val, "unit": "Mcell-timesteps/s", "h2d_bytes_per_step": 16 * n_global,
+                    "d2h_bytes_per_step": d2h // e2e_steps, "steps": e2e_steps},
+            "gpu_launches": 9 * args.steps * world,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    model.close()
+    dist.barrier()
+    dist.destroy_process_group()

@@ -1,0 +1,98 @@
+"""GPU: the partitioned scan-routing kernels (sphy_set_partition / sphy_route_scan_begin / _finish) with the ranks
+emulated one after the other on a single GPU (no kernel ever waits on another: the all-gather is a torch.cat),
+against the single-context scan path and the oracle.  The real NCCL exchange is exercised by bench.py --gpus N."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _ctx(lib, torch, ldd, cellsize):
+    from sphy_b200 import _lib
+    ctx = C.c_void_p()
+    _lib.check(lib, None, lib.sphy_ctx_create(C.byref(ctx), 0, ldd.shape[0], ldd.shape[1], C.c_float(cellsize)), "create")
+    ldd_d = torch.from_numpy(np.ascontiguousarray(ldd, np.uint8)).cuda()
+    _lib.check(lib, ctx, lib.sphy_ldd_build(ctx, ldd_d.data_ptr(), None, None), "ldd_build")
+    return ctx
+
+
+def _export(lib, torch, ctx, name, n):
+    from sphy_b200 import _lib
+    t = torch.empty(n, dtype=torch.int32, device="cuda")
+    _lib.check(lib, ctx, lib.sphy_ldd_export(ctx, name.encode(), t.data_ptr(), n * 4, None), name)
+    torch.cuda.synchronize()
+    return t.cpu().numpy().astype(np.int64)
+
+
+@pytest.mark.parametrize("world,shape,outlets,ncomp", [(2, (300, 260), "single", 1), (3, (420, 380), "single", 2),
+                                                       (4, (500, 610), "border", 2), (8, (640, 700), "single", 1)])
+def test_partitioned_scan_matches_single_context(world, shape, outlets, ncomp):
+    import torch
+    from oracle.ldd_oracle import LddStruct
+    from sphy_b200 import _lib, multigpu, synth
+    lib = _lib.load()
+    cellsize = 250.0
+    _, _, ldd, _ = synth.make_dem_ldd(shape[0], shape[1], cellsize, seed=world, outlets=outlets)
+    st = LddStruct(ldd)
+    n = st.n
+    ref = _ctx(lib, torch, ldd, cellsize)
+    canon = _export(lib, torch, ref, "cell_order", n)
+    sub_size = _export(lib, torch, ref, "sub_size", n)
+    bounds, ranks, stride = multigpu.plan(sub_size, world)
+    parts = []
+    for p in range(world):
+        ctx = _ctx(lib, torch, ldd, cellsize)
+        me = ranks[p]
+        d = {k: torch.from_numpy(np.ascontiguousarray(me[k], np.int32)).cuda() for k in ("pub_e", "remote_k", "remote_rank", "remote_slot")}
+        ptr = lambda t: t.data_ptr() if t.numel() else None  # noqa: E731
+        _lib.check(lib, ctx, lib.sphy_set_partition(ctx, int(bounds[p]), int(bounds[p + 1]), len(me["pub_e"]), ptr(d["pub_e"]),
+                                                    len(me["remote_k"]), ptr(d["remote_k"]), ptr(d["remote_rank"]),
+                                                    ptr(d["remote_slot"]), None), "set_partition")
+        assert lib.sphy_ncells(ctx) == bounds[p + 1] - bounds[p]
+        parts.append((ctx, d))
+    kx = _lib.SphyParam(None, 0.971)
+    one_m = float(np.float32(1 - 0.971))
+    rng = np.random.default_rng(world)
+    q_ref = [torch.zeros(n, device="cuda") for _ in range(ncomp)]
+    q_par = [[torch.zeros(int(bounds[p + 1] - bounds[p]), device="cuda") for _ in range(ncomp)] for p in range(world)]
+    q64 = [np.zeros(n) for _ in range(ncomp)]
+    area = np.float32(cellsize) * np.float32(cellsize)
+    for step in range(3):
+        mm = [(rng.gamma(0.8, 4.0, n) * (rng.random(n) < 0.7)).astype(np.float32) for _ in range(ncomp)]     # canonical order
+        mm_dev = [torch.from_numpy(m[canon]).cuda() for m in mm]                                            # device order
+        src = (C.c_void_p * ncomp)(*[t.data_ptr() for t in mm_dev])
+        dst = (C.c_void_p * ncomp)(*[t.data_ptr() for t in q_ref])
+        _lib.check(lib, ref, lib.sphy_route_step(ref, ncomp, src, dst, kx, C.c_float(one_m), _lib.ROUTE_SCAN, None), "route")
+        sends = []
+        locals_ = []
+        for p, (ctx, _) in enumerate(parts):
+            lo, hi = int(bounds[p]), int(bounds[p + 1])
+            loc = [t[lo:hi].clone() for t in mm_dev]                     # this rank's cells (16-byte aligned copies)
+            locals_.append(loc)
+            send = torch.zeros((ncomp, stride), dtype=torch.float64, device="cuda")
+            srcp = (C.c_void_p * ncomp)(*[t.data_ptr() for t in loc])
+            dstp = (C.c_void_p * ncomp)(*[t.data_ptr() for t in q_par[p]])
+            _lib.check(lib, ctx, lib.sphy_route_scan_begin(ctx, ncomp, srcp, dstp, kx, C.c_float(one_m), send.data_ptr(), stride, None),
+                       "scan_begin")
+            sends.append(send)
+        gathered = torch.stack(sends).contiguous()                       # == all_gather_into_tensor
+        for p, (ctx, _) in enumerate(parts):
+            dstp = (C.c_void_p * ncomp)(*[t.data_ptr() for t in q_par[p]])
+            _lib.check(lib, ctx, lib.sphy_route_scan_finish(ctx, ncomp, dstp, kx, C.c_float(one_m), gathered.data_ptr(), stride, p, world,
+                                                            None), "scan_finish")
+        torch.cuda.synchronize()
+        for c in range(ncomp):
+            got = torch.cat([q_par[p][c] for p in range(world)]).cpu().numpy().astype(np.float64)
+            single = q_ref[c].cpu().numpy().astype(np.float64)
+            rr = (mm[c] * np.float32(0.001) * area) / np.float32(86400)
+            q64[c] = float(np.float32(one_m)) * st.accuflux_f64(rr) + float(np.float32(0.971)) * q64[c]
+            want = q64[c][canon]
+            assert np.all(np.abs(got - want) <= 2e-6 * np.abs(want) + 1e-12), f"step {step} comp {c}: partitioned vs float64 oracle"
+            assert np.all(np.abs(got - single) <= 1e-6 * np.abs(single) + 1e-12), f"step {step} comp {c}: partitioned vs single context"
+    # a partitioned context refuses the whole-basin entry points
+    assert lib.sphy_upstream(parts[0][0], mm_dev[0].data_ptr(), q_ref[0].data_ptr(), None) == -4
+    for ctx, _ in parts:
+        lib.sphy_ctx_destroy(ctx)
+    lib.sphy_ctx_destroy(ref)
