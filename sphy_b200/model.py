@@ -276,7 +276,10 @@ class SphyModel:
         return out[:cnt]
 
     def _compact_np(self, raster, dtype=np.float32):
-        flat = np.asarray(raster).ravel()
+        raster = np.asarray(raster)
+        if raster.ndim == 2 and raster.strides == (0, 0):      # spatially uniform map delivered as a zero-stride view
+            return np.asarray(raster.flat[0], dtype=dtype)     # 0-d array: keeps "map" (REAL4) arithmetic semantics
+        flat = raster.ravel()
         if not self.full_raster:
             flat = flat[self.flat_active]
         return np.ascontiguousarray(flat, dtype=dtype)
@@ -300,7 +303,7 @@ class SphyModel:
             self._keep.append(x)
             return SphyParam(x.data_ptr(), 0.0)
         if isinstance(x, np.ndarray):
-            if x.size and np.all(x == x.flat[0]):           # spatially uniform map: behaves as the scalar
+            if x.ndim == 0 or (x.size and np.all(x == x.flat[0])):     # spatially uniform map: behaves as the scalar
                 return SphyParam(None, float(x.flat[0]))
             t = self._dev(x, np.float32)
             self._keep.append(t)
@@ -402,6 +405,8 @@ class SphyModel:
                 t = line.replace(",", " ").split()
                 if t and not t[0].startswith("#"):
                     table[int(float(t[0]))] = float(t[-1])
+        if keys.ndim == 0:
+            return np.asarray(table.get(int(keys), np.nan), np.float32)
         out = np.full(keys.shape, np.nan, np.float32)
         for k, v in table.items():
             out[keys == k] = f32(v)
@@ -418,7 +423,7 @@ class SphyModel:
             return self._compact_np(self._readmap(raw))
 
     def _state(self, value):
-        if isinstance(value, np.ndarray):
+        if isinstance(value, np.ndarray) and value.ndim > 0:
             return self._dev(value, np.float32).clone()
         return self._full(f32(value))
 
@@ -648,7 +653,11 @@ class SphyModel:
             flags |= _lib.WB_ETREF_INPUT
         P.flags = flags
         if self.ETREF_FLAG == 0:
-            uniq, inv = np.unique(self.Lat, return_inverse=True)
+            try:                                   # hash-based, O(N): np.unique sorts 1e8 values for ~10 s
+                import pandas as pd
+                inv, uniq = pd.factorize(np.ascontiguousarray(self.Lat), sort=False)
+            except ImportError:
+                uniq, inv = np.unique(self.Lat, return_inverse=True)
             if len(uniq) <= 65536:
                 P.ra_mode = _lib.RA_TABLE
                 self._lat_class = self._dev(inv.astype(np.uint16))

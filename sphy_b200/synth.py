@@ -160,16 +160,16 @@ class Catchment:
         """name (relative to inputdir) -> ndarray; dtype decides the PCRaster value scale
         (bool -> boolean, uint8 -> ldd, int32 -> nominal, float32 -> scalar)."""
         m = {
-            "clone.map": np.ones((self.nrows, self.ncols), np.bool_),
-            "dem.map": self.dem.astype(np.float32),
-            "slope.map": self.slope.astype(np.float32),
-            "stations.map": self.locations.astype(np.int32),
-            "ldd.map": self.ldd.astype(np.uint8),
-            "latitude.map": self.lat.astype(np.float32),
-            "landuse.map": np.ones((self.nrows, self.ncols), np.int32),
+            "clone.map": np.broadcast_to(np.bool_(True), (self.nrows, self.ncols)),
+            "dem.map": np.asarray(self.dem, np.float32),
+            "slope.map": np.asarray(self.slope, np.float32),
+            "stations.map": np.asarray(self.locations, np.int32),
+            "ldd.map": np.asarray(self.ldd, np.uint8),
+            "latitude.map": np.asarray(self.lat, np.float32),
+            "landuse.map": np.broadcast_to(np.int32(1), (self.nrows, self.ncols)),
         }
         for k, v in self.soil_maps.items():
-            m[_SOIL_FILES[k]] = v.astype(np.float32)
+            m[_SOIL_FILES[k]] = np.asarray(v, np.float32)
         if self.model_id is not None:
             m["MOD_ID.map"] = self.model_id.astype(np.int32)
             m["GLAC_ID.map"] = self.glac_id.astype(np.int32)
@@ -437,7 +437,7 @@ def make_catchment(nrows, ncols, cellsize=250.0, seed=1, nsteps=365, snow=False,
     if zrange is None:
         zrange = (1500.0, 6500.0) if (snow or glacier) else None
     raw, filled, ldd, slope = make_dem_ldd(nrows, ncols, cellsize, seed=seed, outlets=outlets, zrange=zrange)
-    lat = np.repeat(np.linspace(27.0, 31.0, nrows, dtype=np.float32)[::-1, None], ncols, axis=1)
+    lat = np.broadcast_to(np.linspace(27.0, 31.0, nrows, dtype=np.float32)[::-1, None], (nrows, ncols))
     flags = dict(GlacFLAG=int(glacier), SnowFLAG=int(snow or glacier), RoutFLAG=int(routing),
                  LakeFLAG=int(lakes), ResFLAG=int(reservoirs), GroundFLAG=int(ground or glacier))
     rng = np.random.default_rng([seed, 77])
@@ -445,7 +445,10 @@ def make_catchment(nrows, ncols, cellsize=250.0, seed=1, nsteps=365, snow=False,
     cls = (rng.integers(0, soil_classes, size=(nrows, ncols)) if soil_classes > 1 else np.zeros((nrows, ncols), int))
     scale = 1.0 + 0.05 * np.arange(soil_classes)
     for k in _SOIL_FILES:
-        soil_maps[k] = (np.float32(p[k]) * scale[cls].astype(np.float32)).astype(np.float32)
+        if soil_classes > 1:
+            soil_maps[k] = (np.float32(p[k]) * scale[cls].astype(np.float32)).astype(np.float32)
+        else:       # uniform soils: a zero-stride view, no memory (a 10000 x 10000 map would be 400 MB each)
+            soil_maps[k] = np.broadcast_to(np.float32(np.float32(p[k]) * np.float32(scale[0])), (nrows, ncols))
     nup = upstream_counts(ldd)
     # stations: the outlet(s) with the largest upstream area + a few interior cells
     locations = np.zeros((nrows, ncols), np.int32)
