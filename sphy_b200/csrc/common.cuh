@@ -47,7 +47,9 @@ struct sphy_ctx {
     int32_t *cross_r = nullptr, *cross_ptr = nullptr, *end_e = nullptr, *end_k = nullptr, *end_ptr = nullptr;
     int32_t n_cross = 0;
     double *park_before = nullptr, *park_end = nullptr;
-    double *scan_tile = nullptr;   // [ncomp][ntiles] tile totals
+    double *scan_tile = nullptr;   // [ncomp][ntiles+1] tile totals (trailing 0)
+    void *scan_tmp = nullptr;      // cub temp storage for the tile-total scans
+    size_t scan_tmp_bytes = 0;
     double *scan_excl = nullptr;   // [ncomp][ntiles+1] exclusive prefix of the tile totals
     int32_t n_tiles = 0;
     int scan_comp_cap = 0;

@@ -35,7 +35,7 @@ struct ScanArgs {
     int32_t n_cross;
     double *park_before;                  // [ncomp][n_cross] tile-local exclusive prefix at the crossing cell
     double *park_end;                     // [ncomp][n_cross] tile-local inclusive prefix at its range end
-    double *tile_tot;                     // [ncomp][ntiles]   tile totals
+    double *tile_tot;                     // [ncomp][ntiles+1] tile totals (+ a trailing 0 so the scan yields the grand total)
     double *tile_excl;                    // [ncomp][ntiles+1] exclusive prefix of the totals
     // multi-GPU (partitioned context)
     int32_t n_pub, n_remote;
@@ -51,114 +51,111 @@ struct ScanArgs {
 
 __device__ __forceinline__ float to_m3s(float mm, float cellarea) { return ((mm * 0.001f) * cellarea) / 86400.0f; }
 
-// main pass: one CTA per tile
-__global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_main(const __grid_constant__ ScanArgs a)
+// guarded 128-bit tile loads (4 consecutive cells per thread)
+__device__ __forceinline__ void load_sizes(const ScanArgs &a, int64_t base, int32_t sz[SCAN_ITEMS])
 {
-    typedef cub::BlockScan<double, SCAN_THREADS> BlockScan;
-    __shared__ typename BlockScan::TempStorage tmp;
-    __shared__ double Ls[SCAN_TILE];
-    const int32_t t = blockIdx.x;
-    const int64_t tbase = (int64_t)t * SCAN_TILE;
-    const int lo = threadIdx.x * SCAN_ITEMS;
-    const int64_t base = tbase + lo;
-    const int64_t tend = min(tbase + (int64_t)SCAN_TILE, a.n);   // one past the last cell of the tile
-    const bool full = base + SCAN_ITEMS <= a.n;
-    int32_t sz[SCAN_ITEMS];
-    if (full) {
+    if (base + SCAN_ITEMS <= a.n) {
         const int4 s0 = __ldg(reinterpret_cast<const int4 *>(a.sub_size + base));
         sz[0] = s0.x; sz[1] = s0.y; sz[2] = s0.z; sz[3] = s0.w;
     } else {
 #pragma unroll
         for (int j = 0; j < SCAN_ITEMS; ++j) sz[j] = base + j < a.n ? __ldg(a.sub_size + base + j) : 1;
     }
-    float kxv[SCAN_ITEMS];
-    if (a.kx.map) {
-#pragma unroll
-        for (int j = 0; j < SCAN_ITEMS; ++j) kxv[j] = base + j < a.n ? __ldg(a.kx.map + base + j) : 0.0f;
-    }
-    const int32_t cb = __ldg(a.cross_ptr + t), ce = __ldg(a.cross_ptr + t + 1);
-    const int32_t eb = __ldg(a.end_ptr + t), ee = __ldg(a.end_ptr + t + 1);
-    for (int c = 0; c < a.ncomp; ++c) {
-        const float *m = a.m[c];
-        float *qs = a.qstate[c];
-        float q[SCAN_ITEMS], mm[SCAN_ITEMS];
-        if (full) {                                            // 128-bit loads
-            const float4 x = __ldg(reinterpret_cast<const float4 *>(m + base));
-            mm[0] = x.x; mm[1] = x.y; mm[2] = x.z; mm[3] = x.w;
-            const float4 u = *reinterpret_cast<const float4 *>(qs + base);
-            q[0] = u.x; q[1] = u.y; q[2] = u.z; q[3] = u.w;
-        } else {
-#pragma unroll
-            for (int j = 0; j < SCAN_ITEMS; ++j) {
-                mm[j] = base + j < a.n ? __ldg(m + base + j) : 0.0f;
-                q[j] = base + j < a.n ? qs[base + j] : 0.0f;
-            }
-        }
-        double v[SCAN_ITEMS];
-#pragma unroll
-        for (int j = 0; j < SCAN_ITEMS; ++j) v[j] = base + j < a.n ? (double)to_m3s(mm[j], a.cellarea) : 0.0;
-        double total;
-        BlockScan(tmp).InclusiveSum(v, v, total);
-#pragma unroll
-        for (int j = 0; j < SCAN_ITEMS; ++j) Ls[lo + j] = v[j];
-        __syncthreads();
-        double before = lo == 0 ? 0.0 : Ls[lo - 1];            // tile-local exclusive prefix at the thread's first cell
+}
+__device__ __forceinline__ void load_comp(const ScanArgs &a, int c, int64_t base, float mm[SCAN_ITEMS], float q[SCAN_ITEMS])
+{
+    const float *m = a.m[c];
+    const float *qs = a.qstate[c];
+    if (base + SCAN_ITEMS <= a.n) {
+        const float4 x = __ldg(reinterpret_cast<const float4 *>(m + base));
+        mm[0] = x.x; mm[1] = x.y; mm[2] = x.z; mm[3] = x.w;
+        const float4 u = *reinterpret_cast<const float4 *>(qs + base);
+        q[0] = u.x; q[1] = u.y; q[2] = u.z; q[3] = u.w;
+    } else {
 #pragma unroll
         for (int j = 0; j < SCAN_ITEMS; ++j) {
-            const int64_t e = base + j + sz[j] - 1;            // last cell of the upstream range
-            if (e < tend) {
-                const float f = (float)(Ls[(int)(e - tbase)] - before);
-                const float kx = a.kx.map ? kxv[j] : a.kx.value;
-                const float omk = a.kx.map ? 1.0f - kx : a.one_m_kx;
-                q[j] = omk * f + kx * q[j];                    // routing.py:28
-            }                                                  // else: crossing cell, left to k_scan_cross
-            before = v[j];
+            mm[j] = base + j < a.n ? __ldg(m + base + j) : 0.0f;
+            q[j] = base + j < a.n ? qs[base + j] : 0.0f;
         }
-        if (full) {
-            *reinterpret_cast<float4 *>(qs + base) = make_float4(q[0], q[1], q[2], q[3]);
-        } else {
-#pragma unroll
-            for (int j = 0; j < SCAN_ITEMS; ++j)
-                if (base + j < a.n) qs[base + j] = q[j];
-        }
-        // park what the crossing cells of / ending in this tile will need
-        double *pb = a.park_before + (int64_t)c * a.n_cross, *pe = a.park_end + (int64_t)c * (a.n_cross + a.n_pub);
-        for (int32_t k = cb + threadIdx.x; k < ce; k += SCAN_THREADS) {
-            const int off = (int)(__ldg(a.cross_r + k) - tbase);
-            pb[k] = off == 0 ? 0.0 : Ls[off - 1];
-        }
-        for (int32_t j = eb + threadIdx.x; j < ee; j += SCAN_THREADS)
-            pe[__ldg(a.end_k + j)] = Ls[(int)(__ldg(a.end_e + j) - tbase)];
-        if (threadIdx.x == 0) a.tile_tot[(int64_t)c * a.ntiles + t] = total;
-        __syncthreads();
     }
 }
 
-// exclusive scan of the tile totals, one CTA per component (ntiles ~ 1e5 at 10^8 cells), 8 tiles per thread
-__global__ void __launch_bounds__(1024) k_scan_tile_totals(const __grid_constant__ ScanArgs a)
+// main pass: persistent CTAs walk the tiles; the loads of the next tile are issued before the current one is
+// scanned, so the HBM latency hides behind the block scan and the shared-memory phase
+__global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_main(const __grid_constant__ ScanArgs a)
 {
-    constexpr int PER = 8;
-    typedef cub::BlockScan<double, 1024> BlockScan;
+    typedef cub::BlockScan<double, SCAN_THREADS, cub::BLOCK_SCAN_WARP_SCANS> BlockScan;
     __shared__ typename BlockScan::TempStorage tmp;
-    __shared__ double carry_s;
-    const double *t = a.tile_tot + (int64_t)blockIdx.x * a.ntiles;
-    double *x = a.tile_excl + (int64_t)blockIdx.x * (a.ntiles + 1);
-    if (threadIdx.x == 0) carry_s = 0.0;
-    __syncthreads();
-    for (int32_t b = 0; b < a.ntiles + 1; b += 1024 * PER) {
-        const int32_t k0 = b + threadIdx.x * PER;
-        double v[PER];
+    __shared__ double Ls[SCAN_TILE];
+    const int lo = threadIdx.x * SCAN_ITEMS;
+    int32_t t = blockIdx.x;
+    if (t >= a.ntiles) return;
+    int32_t sz_n[SCAN_ITEMS];
+    float mm_n[SCAN_ITEMS], q_n[SCAN_ITEMS];
+    load_sizes(a, (int64_t)t * SCAN_TILE + lo, sz_n);
+    load_comp(a, 0, (int64_t)t * SCAN_TILE + lo, mm_n, q_n);
+    for (; t < a.ntiles; t += gridDim.x) {
+        const int64_t tbase = (int64_t)t * SCAN_TILE;
+        const int64_t base = tbase + lo;
+        const int64_t tend = min(tbase + (int64_t)SCAN_TILE, a.n);   // one past the last cell of the tile
+        const bool full = base + SCAN_ITEMS <= a.n;
+        int32_t sz[SCAN_ITEMS];
+        float q[SCAN_ITEMS], mm[SCAN_ITEMS];
 #pragma unroll
-        for (int j = 0; j < PER; ++j) v[j] = k0 + j < a.ntiles ? t[k0 + j] : 0.0;
-        double tot;
-        BlockScan(tmp).ExclusiveSum(v, v, tot);
-        const double carry = carry_s;
+        for (int j = 0; j < SCAN_ITEMS; ++j) { sz[j] = sz_n[j]; mm[j] = mm_n[j]; q[j] = q_n[j]; }
+        const int32_t tn = t + gridDim.x;
+        if (tn < a.ntiles) {                                   // prefetch the next tile of this CTA
+            load_sizes(a, (int64_t)tn * SCAN_TILE + lo, sz_n);
+            load_comp(a, 0, (int64_t)tn * SCAN_TILE + lo, mm_n, q_n);
+        }
+        float kxv[SCAN_ITEMS];
+        if (a.kx.map) {
 #pragma unroll
-        for (int j = 0; j < PER; ++j)
-            if (k0 + j < a.ntiles + 1) x[k0 + j] = carry + v[j];
-        __syncthreads();
-        if (threadIdx.x == 0) carry_s = carry + tot;
-        __syncthreads();
+            for (int j = 0; j < SCAN_ITEMS; ++j) kxv[j] = base + j < a.n ? __ldg(a.kx.map + base + j) : 0.0f;
+        }
+        const int32_t cb = __ldg(a.cross_ptr + t), ce = __ldg(a.cross_ptr + t + 1);
+        const int32_t eb = __ldg(a.end_ptr + t), ee = __ldg(a.end_ptr + t + 1);
+        for (int c = 0; c < a.ncomp; ++c) {
+            float *qs = a.qstate[c];
+            if (c > 0) load_comp(a, c, base, mm, q);
+            double v[SCAN_ITEMS];
+#pragma unroll
+            for (int j = 0; j < SCAN_ITEMS; ++j) v[j] = base + j < a.n ? (double)to_m3s(mm[j], a.cellarea) : 0.0;
+            double total;
+            BlockScan(tmp).InclusiveSum(v, v, total);
+#pragma unroll
+            for (int j = 0; j < SCAN_ITEMS; ++j) Ls[lo + j] = v[j];
+            __syncthreads();
+            double before = lo == 0 ? 0.0 : Ls[lo - 1];        // tile-local exclusive prefix at the thread's first cell
+#pragma unroll
+            for (int j = 0; j < SCAN_ITEMS; ++j) {
+                const int64_t e = base + j + sz[j] - 1;        // last cell of the upstream range
+                if (e < tend) {
+                    const float f = (float)(Ls[(int)(e - tbase)] - before);
+                    const float kx = a.kx.map ? kxv[j] : a.kx.value;
+                    const float omk = a.kx.map ? 1.0f - kx : a.one_m_kx;
+                    q[j] = omk * f + kx * q[j];                // routing.py:28
+                }                                              // else: crossing cell, left to k_scan_cross
+                before = v[j];
+            }
+            if (full) {
+                *reinterpret_cast<float4 *>(qs + base) = make_float4(q[0], q[1], q[2], q[3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < SCAN_ITEMS; ++j)
+                    if (base + j < a.n) qs[base + j] = q[j];
+            }
+            // park what the crossing cells of / ending in this tile will need
+            double *pb = a.park_before + (int64_t)c * a.n_cross, *pe = a.park_end + (int64_t)c * (a.n_cross + a.n_pub);
+            for (int32_t k = cb + threadIdx.x; k < ce; k += SCAN_THREADS) {
+                const int off = (int)(__ldg(a.cross_r + k) - tbase);
+                pb[k] = off == 0 ? 0.0 : Ls[off - 1];
+            }
+            for (int32_t j = eb + threadIdx.x; j < ee; j += SCAN_THREADS)
+                pe[__ldg(a.end_k + j)] = Ls[(int)(__ldg(a.end_e + j) - tbase)];
+            if (threadIdx.x == 0) a.tile_tot[(int64_t)c * (a.ntiles + 1) + t] = total;
+            __syncthreads();
+        }
     }
 }
 
@@ -173,7 +170,7 @@ __global__ void __launch_bounds__(256) k_scan_cross(const __grid_constant__ Scan
     const float kx = a.kx.map ? __ldg(a.kx.map + r) : a.kx.value;
     const float omk = a.kx.map ? 1.0f - kx : a.one_m_kx;
     for (int c = 0; c < a.ncomp; ++c) {
-        const double *T = a.tile_tot + (int64_t)c * a.ntiles;
+        const double *T = a.tile_tot + (int64_t)c * (a.ntiles + 1);
         const double *X = a.tile_excl + (int64_t)c * (a.ntiles + 1);
         if (e >= a.n) {                                        // range ends on another rank: keep the part up to the
             double *pb = a.park_before + (int64_t)c * a.n_cross + k;   // end of this rank's range for k_scan_remote
@@ -333,9 +330,18 @@ static int scan_prepare(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm,
         const size_t ncs = ctx->n_cross > 0 ? (size_t)ctx->n_cross : 1;
         if ((rc = dev_alloc(ctx, &ctx->park_before, (size_t)ncomp * ncs)) ||
             (rc = dev_alloc(ctx, &ctx->park_end, (size_t)ncomp * (ncs + ctx->n_pub))) ||
-            (rc = dev_alloc(ctx, &ctx->scan_tile, (size_t)ncomp * ctx->n_tiles)) ||
+            (rc = dev_alloc(ctx, &ctx->scan_tile, (size_t)ncomp * (ctx->n_tiles + 1))) ||
             (rc = dev_alloc(ctx, &ctx->scan_excl, (size_t)ncomp * (ctx->n_tiles + 1))))
             return rc;
+        SPHY_CUDA(ctx, cudaMemsetAsync(ctx->scan_tile, 0, sizeof(double) * (size_t)ncomp * (ctx->n_tiles + 1), st));
+        size_t need = 0;
+        SPHY_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, need, ctx->scan_tile, ctx->scan_excl, ctx->n_tiles + 1, st));
+        if (need > ctx->scan_tmp_bytes) {
+            if (ctx->scan_tmp) cudaFree(ctx->scan_tmp);
+            ctx->scan_tmp = nullptr;
+            SPHY_CUDA(ctx, cudaMalloc(&ctx->scan_tmp, need));
+            ctx->scan_tmp_bytes = need;
+        }
         ctx->scan_comp_cap = ncomp;
     }
     for (int c = 0; c < ncomp; ++c)
@@ -372,15 +378,28 @@ static int scan_prepare(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm,
     return SPHY_OK;
 }
 
+// main pass -> exclusive scan of the tile totals (cub, one call per component) -> crossing cells
+static int scan_launch_local(sphy_ctx *ctx, ScanArgs &a, cudaStream_t st)
+{
+    const int grid = ctx->n_tiles < ctx->sm_count * 4 ? ctx->n_tiles : ctx->sm_count * 4;
+    k_scan_main<<<grid, SCAN_THREADS, 0, st>>>(a);
+    for (int c = 0; c < a.ncomp; ++c) {
+        size_t need = ctx->scan_tmp_bytes;
+        SPHY_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->scan_tmp, need, ctx->scan_tile + (size_t)c * (ctx->n_tiles + 1),
+                                                     ctx->scan_excl + (size_t)c * (ctx->n_tiles + 1), ctx->n_tiles + 1, st));
+    }
+    if (ctx->n_cross > 0) k_scan_cross<<<div_up(ctx->n_cross, 256), 256, 0, st>>>(a);
+    return SPHY_OK;
+}
+
 int route_scan_run(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm, float *const *q_state, sphy_param kx,
                    float one_m_kx, cudaStream_t st)
 {
     ScanArgs a;
     int rc = scan_prepare(ctx, ncomp, runoff_mm, q_state, kx, one_m_kx, st, a);
     if (rc != SPHY_OK) return rc;
-    k_scan_main<<<ctx->n_tiles, SCAN_THREADS, 0, st>>>(a);
-    k_scan_tile_totals<<<ncomp, 1024, 0, st>>>(a);
-    if (ctx->n_cross > 0) k_scan_cross<<<div_up(ctx->n_cross, 256), 256, 0, st>>>(a);
+    int rc2 = scan_launch_local(ctx, a, st);
+    if (rc2 != SPHY_OK) return rc2;
     SPHY_LAUNCH_CHECK(ctx);
     return SPHY_OK;
 }
@@ -433,9 +452,8 @@ extern "C" int sphy_route_scan_begin(sphy_ctx *ctx, int ncomp, const float *cons
     if (rc != SPHY_OK) return rc;
     a.send = send_dev;
     a.stride = stride;
-    k_scan_main<<<ctx->n_tiles, SCAN_THREADS, 0, st>>>(a);
-    k_scan_tile_totals<<<ncomp, 1024, 0, st>>>(a);
-    if (ctx->n_cross > 0) k_scan_cross<<<div_up(ctx->n_cross, 256), 256, 0, st>>>(a);
+    rc = scan_launch_local(ctx, a, st);
+    if (rc != SPHY_OK) return rc;
     k_scan_publish<<<div_up(ctx->n_pub > 0 ? ctx->n_pub : 1, 256), 256, 0, st>>>(a);
     SPHY_LAUNCH_CHECK(ctx);
     return SPHY_OK;
