@@ -79,6 +79,7 @@ class ClockSampler:
 
 
 def make_case(size, seed=1, cellsize=250.0, nsteps=365):
+    """The synthetic basin of BASELINE config 4 (and, at 2000 x 2000 / 1 km, the grid of configs 3 and 5)."""
     from sphy_b200 import synth
     return synth.make_catchment(size, size, cellsize=cellsize, seed=seed, nsteps=nsteps, outlets="single", params=PARAMS,
                                 start=datetime.date(2001, 6, 1))
@@ -156,6 +157,10 @@ def main():
     ap.add_argument("--route", default=os.environ.get("SPHY_BENCH_ROUTE", "scan"), choices=["levels", "scan"])
     ap.add_argument("--ring", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="basin", choices=["basin", "ensemble"],
+                    help="basin: BASELINE config 4 (default, the headline); ensemble: BASELINE config 5")
+    ap.add_argument("--members", type=int, default=64)
+    ap.add_argument("--ens-size", type=int, default=2000)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -163,6 +168,9 @@ def main():
         if rank == 0:
             run_reference(args)
         return
+    if args.workload == "ensemble":
+        from sphy_b200 import multigpu
+        return multigpu.ensemble_main(args, rank, world)
     if world > 1:
         from sphy_b200 import multigpu
         return multigpu.bench_main(args, rank, world)

@@ -42,6 +42,8 @@ CASES = {
     "c1_noground": (dict(nrows=12, ncols=10, seed=13, ground=False, params=WET), 40),
     # three soil classes: distributed soil parameters
     "c1_soilcls": (dict(nrows=12, ncols=10, seed=14, soil_classes=3, params=WETK), 40),
+    # plant water stress (ET.ks) instead of the wilting-point reduction
+    "c1_pws": (dict(nrows=12, ncols=10, seed=15, pws=True, params=WET), 40),
     # BASELINE config 2: snow on (spring melt season, snow line inside the catchment)
     "c2_snow": (dict(nrows=12, ncols=10, seed=21, snow=True, params=COLD, start=(2001, 3, 15), zrange=(1500.0, 5200.0)), 90),
     # BASELINE config 2: snow + glacier, all components routed

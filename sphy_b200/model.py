@@ -111,7 +111,7 @@ def _table_col(rows, col):
 # ----------------------------------------------------------------------------------------------
 class SphyModel:
     def __init__(self, cfg, maps: MapSource, device="cuda:0", route_method="scan", diagnostics=False,
-                 collect_tss=True, cell_order="dfs", rank=0, world=1):
+                 collect_tss=True, cell_order="dfs", rank=0, world=1, share_from=None):
         if not torch.cuda.is_available():
             raise RuntimeError("SphyModel needs a CUDA device (B200); there is no CPU fallback")
         self.lib = _lib.load()
@@ -163,9 +163,17 @@ class SphyModel:
         if self.cellsize is None:
             raise ValueError("cell size unknown: give [GENERAL] cellsize in the cfg or a `cellsize` attribute on the map source")
         self.cellArea = f32(f32(self.cellsize) * f32(self.cellsize))
-        self._ctx = C.c_void_p()
-        _lib.check(self.lib, None, self.lib.sphy_ctx_create(C.byref(self._ctx), self.device.index or 0, self.nrows,
-                                                            self.ncols, C.c_float(self.cellsize)), "sphy_ctx_create")
+        # ensemble members (BASELINE config 5) share one context: the LDD structures are built and held once per GPU
+        self._owns_ctx = share_from is None
+        if share_from is not None:
+            if (share_from.nrows, share_from.ncols, share_from.device) != (self.nrows, self.ncols, self.device):
+                raise ValueError("share_from: the members of an ensemble must live on the same grid and GPU")
+            self._ctx = share_from._ctx
+        else:
+            self._ctx = C.c_void_p()
+            _lib.check(self.lib, None, self.lib.sphy_ctx_create(C.byref(self._ctx), self.device.index or 0, self.nrows,
+                                                                self.ncols, C.c_float(self.cellsize)), "sphy_ctx_create")
+        self._share_from = share_from
         self._keep = []               # tensors referenced by raw pointers
         self._stream = lambda: C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)  # noqa: E731
         # -- routing structures first: they define the active cells / compact order (routing.py:33-38)
@@ -176,7 +184,8 @@ class SphyModel:
     def close(self):
         if getattr(self, "_ctx", None):
             torch.cuda.synchronize(self.device)
-            self.lib.sphy_ctx_destroy(self._ctx)
+            if self._owns_ctx:
+                self.lib.sphy_ctx_destroy(self._ctx)
             self._ctx = None
 
     def __del__(self):
@@ -202,6 +211,14 @@ class SphyModel:
     # -- compact layout ------------------------------------------------------------------------
     def _build_cells(self):
         cfg = self.config
+        if self._share_from is not None:
+            o = self._share_from
+            for k in ("n", "n_global", "nlevels", "flat_active", "cell_order", "full_raster", "_cidx_host"):
+                setattr(self, k, getattr(o, k))
+            for k in ("part_range", "_mg_stride", "_mg_plan"):
+                if hasattr(o, k):
+                    setattr(self, k, getattr(o, k))
+            return
         need_ldd = self.RoutFLAG == 1 or self.ResFLAG == 1 or self.LakeFLAG == 1
         if need_ldd:
             ldd = np.ascontiguousarray(self._readmap(cfg.get("ROUTING", "flowdir")), dtype=np.uint8)

@@ -183,3 +183,85 @@ def bench_main(args, rank, world):
     model.close()
     dist.barrier()
     dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------
+def ensemble_main(args, rank, world):
+    """BASELINE config 5: a forcing/parameter ensemble on the 2000 x 2000 basin, members sharded across the GPUs.
+    Members are independent: no data-path collective (only the timing barrier / max-over-ranks)."""
+    import copy
+
+    import torch
+
+    import bench
+    from .model import CatchmentSource, SphyModel
+
+    dist = None
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    total = args.members
+    mine = [m for m in range(total) if m % world == rank]
+    size = args.ens_size
+    cat = bench.make_case(size, cellsize=1000.0)
+    members, rings = [], []
+    t_setup = time.time()
+    for m in mine:
+        c = copy.copy(cat)
+        rng = np.random.default_rng(1000 + m)
+        c.params = dict(cat.params)
+        for k in ("kx", "alphaGw", "deltaGw"):                # +-10 % parameter perturbation (SURVEY 8d, C5)
+            c.params[k] = cat.params[k] * (1.0 + 0.1 * (2.0 * rng.random() - 1.0))
+        c.params["kx"] = min(c.params["kx"], 0.999)
+        tmp = tempfile.mkdtemp(prefix=f"sphy_ens_r{rank}_m{m}_")
+        cfg = c.write_inputs(os.path.join(tmp, "in"), os.path.join(tmp, "out"))
+        model = SphyModel(cfg, CatchmentSource(c), device=str(dev), route_method="scan", diagnostics=False, collect_tss=False,
+                          share_from=members[0] if members else None)
+        model.initial()
+        members.append(model)
+        dem_dev = torch.from_numpy(np.ascontiguousarray(model._compact_np(cat.dem))).to(dev)
+        ring = bench.device_forcing_ring(torch, dem_dev, 2, seed=5000 + m)
+        rings.append(ring)
+        model.set_device_forcing(lambda t, ring=ring: ring[t % len(ring)])
+    n = members[0].n
+    torch.cuda.synchronize()
+    setup_s = time.time() - t_setup
+
+    def step_all():
+        for model in members:
+            model.dynamic()
+
+    for _ in range(max(args.warmup, 3)):
+        step_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        step_all()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if dist:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.barrier()
+    ms_total = float(ms.item())
+    if rank == 0:
+        value = total * n * args.steps / (ms_total * 1e-3) / 1e6
+        line = {"metric": "Mcell-timesteps/s", "value": value, "unit": "Mcell-timesteps/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"{total}-member forcing/parameter ensemble on the {size}x{size} 1 km basin (BASELINE config 5), "
+                                       f"members sharded across {world} GPU(s), LDD structures shared per GPU, no collective",
+                           "cells_per_member": n, "members_per_gpu": len(mine), "setup_s": round(setup_s, 1)},
+                "gpu_launches": 6 * args.steps * total}
+        print(json.dumps(line), flush=True)
+    for model in reversed(members):
+        model.close()
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()

@@ -129,6 +129,7 @@ class Catchment:
     lake_tables: dict = field(default_factory=dict)
     open_water_frac: np.ndarray | None = None
     report_daily: tuple = ()
+    pws: bool = False                    # plant water stress (ET.ks, PWS_FLAG)
 
     # ------------------------------------------------------------------------------------------
     @property
@@ -198,6 +199,8 @@ class Catchment:
             fh.write(f"1 {p['Kc']}\n")
         with open(os.path.join(inputdir, "paved.tbl"), "w") as fh:
             fh.write("1 0.0\n")
+        with open(os.path.join(inputdir, "depletion.tbl"), "w") as fh:
+            fh.write(f"1 {p.get('PFactor', 0.5)}\n")
         with open(os.path.join(inputdir, "reporting.csv"), "w") as fh:
             fh.write("name,map,avg,timeseries,filename,comment\n")
             for name, fname in _REPORT_VARS:
@@ -306,7 +309,7 @@ KCstatic = 1
 CropFac = kc.tbl
 KC =
 [PWS]
-PWS_FLAG = 0
+PWS_FLAG = {1 if self.pws else 0}
 PFactor = depletion.tbl
 [OPENWATER]
 ETOpenWaterFLAG = {1 if self.open_water_frac is not None else 0}
@@ -429,7 +432,7 @@ def make_catchment(nrows, ncols, cellsize=250.0, seed=1, nsteps=365, snow=False,
                    reservoirs=False, lakes=False, ground=True, routing=True, infil_excess=0,
                    rout_components=False, outlets="single", start=datetime.date(2001, 1, 1),
                    n_res_simple=0, n_res_adv=0, n_lakes=0, open_water=False, params=None,
-                   report_daily=(), soil_classes=1, zrange=None):
+                   report_daily=(), soil_classes=1, zrange=None, pws=False):
     """Build one of the BASELINE.json synthetic configurations."""
     p = dict(DEFAULT_PARAMS)
     if params:
@@ -463,7 +466,7 @@ def make_catchment(nrows, ncols, cellsize=250.0, seed=1, nsteps=365, snow=False,
     cat = Catchment(nrows=nrows, ncols=ncols, cellsize=float(cellsize), seed=seed, dem=raw, ldd=ldd, slope=slope,
                     lat=lat, flags=flags, params=p, start=start, nsteps=nsteps, locations=locations,
                     soil_maps=soil_maps, rout_components=rout_components, infil_excess=infil_excess,
-                    report_daily=tuple(report_daily))
+                    report_daily=tuple(report_daily), pws=bool(pws))
     if glacier:
         _add_glaciers(cat, rng)
     if reservoirs or lakes:

@@ -135,3 +135,38 @@ def test_model_with_scan_routing_matches_oracle_port():
     """Whole model with SPHY_ROUTE_SCAN: water balance stays bit-identical, discharge within 1e-5 relative."""
     test_model_matches_oracle_port(dict(nrows=310, ncols=270, seed=8, rout_components=True,
                                         params=dict(SubWater=470.0, RootDepthFlat=150.0, Pscale=2.5)), 15, route_method="scan")
+
+
+def test_ensemble_members_share_one_context():
+    """BASELINE config 5 in miniature: members with perturbed kx / alphaGw / deltaGw and their own forcing share the
+    LDD structures of one context and still match the oracle member by member."""
+    import datetime
+    import torch
+    from oracle.sphy_port import PortInputs, PortModel
+    from sphy_b200 import synth
+    base = dict(nrows=120, ncols=100, seed=9, nsteps=8, start=datetime.date(2001, 5, 1))
+    members, ports, cats = [], [], []
+    for m in range(3):
+        p = dict(SubWater=470.0, RootDepthFlat=150.0, Pscale=2.5, kx=0.971 * (1 - 0.03 * m), alphaGw=0.508 * (1 + 0.05 * m),
+                 deltaGw=300.0 * (1 - 0.04 * m))
+        cat = synth.make_catchment(params=p, **base)
+        cat.seed = 100 + m                                     # member-specific forcing, same terrain
+        cats.append(cat)
+        model = make_model(cat, route_method="scan", share_from=members[0] if members else None)
+        members.append(model)
+        ports.append(PortModel(PortInputs(cat)))
+    assert all(m._ctx is members[0]._ctx for m in members)
+    g = PortInputs(cats[0]).lddst.gather
+    for t in range(1, 9):
+        for model, port, cat in zip(members, ports, cats):
+            model.dynamic()
+            port.dynamic({k: g(v) for k, v in cat.forcing(t).items()})
+    torch.cuda.synchronize()
+    for model, port in zip(members, ports):
+        for k in ("RootWater", "SubWater", "Gw", "BaseR"):
+            got = getattr(model, k).cpu().numpy()
+            assert bit_equal(got, getattr(port, k)[model.cell_order]).all(), k
+        got = model.QRAold.cpu().numpy()
+        assert close(got, port.QRAold[model.cell_order]).all()
+    for model in reversed(members):
+        model.close()
