@@ -152,6 +152,41 @@ typedef struct {                     /* outputs; every pointer except TotR may b
 #define SPHY_UNARY_EXP_NEG 4
 int sphy_map_unary(sphy_ctx *ctx, int op, const float *in, float *out, int64_t count, void *stream);
 
+/* The reference's per-cell process functions one at a time (whole-map pass per call, like PCRaster), so that the
+ * module call signatures stay usable: the same device functions the fused kernel composes (csrc/sphy_functions.cuh).
+ * Inputs are scalar-or-map in the order of the reference's argument list (see csrc/wb_step.cu: k_module_op);
+ * time-constant transcendentals are passed evaluated (e_root = REAL4(exp(-1/rootTT)) ...). */
+enum {
+    SPHY_OP_EXTRARAD = 0,        /* hargreaves.extrarad        hargreaves.py:24-39   in: Lat[deg] (+ k0, day_of_year) */
+    SPHY_OP_HARGREAVES,          /* hargreaves.Hargreaves      hargreaves.py:43-47 */
+    SPHY_OP_ETPOT,               /* ET.ETpot                   ET.py:24-26 */
+    SPHY_OP_ETACT,               /* ET.ETact                   ET.py:30-35 */
+    SPHY_OP_KS,                  /* ET.ks                      ET.py:39-47 */
+    SPHY_OP_POTSNOWMELT,         /* snow.PotSnowMelt           modules/snow.py:27-33 */
+    SPHY_OP_ACTSNOWMELT,         /* snow.ActSnowMelt           :37-39 */
+    SPHY_OP_SNOWSTOREUPDATE,     /* snow.SnowStoreUpdate       :43-50 */
+    SPHY_OP_MAXSNOWWATSTORAGE,   /* snow.MaxSnowWatStorage     :54-56 */
+    SPHY_OP_SNOWWATSTORAGE,      /* snow.SnowWatStorage        :60-64 */
+    SPHY_OP_TOTSNOWSTORAGE,      /* snow.TotSnowStorage        :68-70 */
+    SPHY_OP_SNOWR,               /* snow.SnowR                 :74-80 */
+    SPHY_OP_ROOTRUNOFF_SAT,      /* rootzone.RootRunoff, InfilFLAG = 0   rootzone.py:50-57  (2 outputs) */
+    SPHY_OP_ROOTRUNOFF_INFIL,    /* rootzone.RootRunoff, InfilFLAG = 1   rootzone.py:26-47  (2 outputs) */
+    SPHY_OP_ROOTDRAINAGE,        /* rootzone.RootDrainage      rootzone.py:63-74 */
+    SPHY_OP_ROOTPERCOLATION,     /* rootzone.RootPercolation   :78-85 */
+    SPHY_OP_CALCFRAC,            /* rootzone.CalcFrac          :89-94  (2 outputs) */
+    SPHY_OP_CAPILRISE,           /* subzone.CapilRise          subzone.py:24-31 */
+    SPHY_OP_SUBPERCOLATION,      /* subzone.SubPercolation     :35-41 */
+    SPHY_OP_SUBDRAINAGE,         /* subzone.SubDrainage        :45-51 */
+    SPHY_OP_GWRECHARGE,          /* groundwater.GroundWaterRecharge  modules/groundwater.py:26-29 */
+    SPHY_OP_BASEFLOW,            /* groundwater.BaseFlow       :33-39 */
+    SPHY_OP_HLEVEL,              /* groundwater.HLevel         :43-47 */
+    SPHY_OP_SNOW_DYNAMIC,        /* snow.dynamic               modules/snow.py:110-187   (6 outputs) */
+    SPHY_OP_GROUNDWATER_DYNAMIC, /* groundwater.dynamic        modules/groundwater.py:90-125 (4 outputs) */
+    SPHY_OP_COUNT
+};
+int sphy_module_op(sphy_ctx *ctx, int op, const sphy_param *in, int n_in, float *const *out, int n_out, int64_t count,
+                   float k0, int day_of_year, void *stream);
+
 /* K1 alone does not need the LDD: declare the number of active cells directly */
 int sphy_set_ncells(sphy_ctx *ctx, int64_t n);
 

@@ -76,6 +76,11 @@ RA_TABLE, RA_CELL = 0, 1
 ROUTE_LEVELS, ROUTE_SCAN = 0, 1
 ORDER_ROWMAJOR, ORDER_DFS = 0, 1
 SCAN_TILE = 1024                      # cells per scan-routing tile (csrc/route_scan.cu)
+OPS = ("EXTRARAD", "HARGREAVES", "ETPOT", "ETACT", "KS", "POTSNOWMELT", "ACTSNOWMELT", "SNOWSTOREUPDATE", "MAXSNOWWATSTORAGE",
+       "SNOWWATSTORAGE", "TOTSNOWSTORAGE", "SNOWR", "ROOTRUNOFF_SAT", "ROOTRUNOFF_INFIL", "ROOTDRAINAGE", "ROOTPERCOLATION",
+       "CALCFRAC", "CAPILRISE", "SUBPERCOLATION", "SUBDRAINAGE", "GWRECHARGE", "BASEFLOW", "HLEVEL", "SNOW_DYNAMIC",
+       "GROUNDWATER_DYNAMIC")
+OP = {name: i for i, name in enumerate(OPS)}
 UNARY_EXP_NEG_INV, UNARY_SIN_DEG, UNARY_COS_DEG, UNARY_TAN_DEG, UNARY_EXP_NEG = 0, 1, 2, 3, 4
 
 # every symbol include/sphy_b200.h declares: name -> (restype, argtypes)
@@ -95,6 +100,7 @@ SYMBOLS = {
     "sphy_sample": (C.c_int, [P, P, P, C.c_int, P, P]),
     "sphy_map_unary": (C.c_int, [P, C.c_int, P, P, C.c_int64, P]),
     "sphy_set_ncells": (C.c_int, [P, C.c_int64]),
+    "sphy_module_op": (C.c_int, [P, C.c_int, C.POINTER(SphyParam), C.c_int, C.POINTER(P), C.c_int, C.c_int64, C.c_float, C.c_int, P]),
     "sphy_wb_step": (C.c_int, [P, C.POINTER(WbParams), C.POINTER(WbState), C.POINTER(WbForcing), C.POINTER(WbOut),
                                C.c_int, P]),
     "sphy_glac_step": (C.c_int, [P, C.POINTER(GlacTable), P, P, C.c_float, C.c_float, C.POINTER(GlacOut), P]),

@@ -5,6 +5,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "sphy_functions.cuh"
 
 namespace wb {
 
@@ -79,17 +80,10 @@ struct Lanes<1> {
     static __device__ __forceinline__ V4 par(const sphy_param &q, int64_t i) { return splat(q.map ? __ldg(q.map + i) : q.value); }
 };
 
-// double-evaluated transcendentals stored as REAL4 (assumption A2, see oracle/pcr_shim.py)
-__device__ __forceinline__ float d_acos(float x) { return (float)acos((double)x); }
-__device__ __forceinline__ float d_sin(float x) { return (float)sin((double)x); }
-__device__ __forceinline__ float d_pow(float x, float y) { return (float)pow((double)x, (double)y); }
-
 // Ra for one latitude (hargreaves.py:24-39)
 __device__ __forceinline__ float extrarad(float sinl, float cosl, float tanl, const DayScalars &d)
 {
-    float x = (-1.0f * tanl) * d.tan_delta;
-    float omegas = d_acos(x);
-    return d.k0dr * ((omegas * sinl) * d.sin_delta + (cosl * d.cos_delta) * d_sin(omegas));
+    return sf::extrarad(sinl, cosl, tanl, d.k0dr, d.sin_delta, d.cos_delta, d.tan_delta);
 }
 
 // ---- the per-cell physics, W cells per call --------------------------------------------------------
@@ -203,8 +197,7 @@ __device__ __forceinline__ void wb_cells(const WbArgs &a, int64_t i)
             const float TempMin = tmin.v[j] + p.tcorr;
             TempMax = tmax.v[j] + p.tcorr;
             const float Ra = (RA == 0) ? ra.v[j] : extrarad(sinl.v[j], cosl.v[j], tanl.v[j], a.d);
-            // hargreaves.py:44-46; x**0.5 == sqrtf(x) exactly (double sqrt then REAL4 is double-rounding safe)
-            ETref = fmaxf(((a.d.hg_c * Ra) * (Temp + 17.8f)) * sqrtf(fmaxf(TempMax - TempMin, 0.0f)), 0.0f);
+            ETref = sf::Hargreaves(a.d.hg_c, Ra, Temp, TempMax, TempMin);                   // hargreaves.py:43-47
         }
         // ---- snow, modules/snow.py:110-187 ----------------------------------------------------------
         float Rain = Precip, SnowR = 0.0f, SnowSoil = 0.0f, OldTotalSnowStore = 0.0f, tss = 0.0f;
@@ -213,93 +206,65 @@ __device__ __forceinline__ void wb_cells(const WbArgs &a, int64_t i)
             sws = SnowWatStore.v[j];
             const float Snow = Temp >= p.tcrit ? 0.0f : Precip;
             Rain = Temp < p.tcrit ? 0.0f : Precip;
-            float thour = 0.0f;
-            const float dT = TempMax - Temp;
-#pragma unroll
-            for (int h = 0; h < 24; ++h) thour = thour + fmaxf(0.0f, Temp + dT * p.melt_cos[h]);
-            const float melt = (thour * p.ddfs) / 24.0f;
-            const float PotSnowMelt = TempMax < 0.0f ? 0.0f : melt;
-            const float ActSnowMelt = fminf(ss, PotSnowMelt);
-            ss = ((ss + Snow) - ActSnowMelt) + (Temp < 0.0f ? sws : 0.0f);
-            const float MaxSWS = p.snow_sc * ss;
+            const float PotSnowMelt = TempMax < 0.0f ? 0.0f : sf::PotSnowMelt(Temp, TempMax, p.ddfs, p.melt_cos);
+            const float ActSnowMelt = sf::ActSnowMelt(ss, PotSnowMelt);
+            ss = sf::SnowStoreUpdate(ss, Snow, ActSnowMelt, Temp, sws);
+            const float MaxSWS = sf::MaxSnowWatStorage(p.snow_sc, ss);
             const float OldSWS = sws;
-            sws = TempMax < 0.0f ? 0.0f : fminf(MaxSWS, (sws + ActSnowMelt) + Rain);
+            sws = sf::SnowWatStorage(TempMax, MaxSWS, sws, ActSnowMelt, Rain);          // tested on Tmax (quirk Q5)
             OldTotalSnowStore = TotalSnowStore.v[j];
-            tss = (ss + sws) * (SnowFrac + RainFrac);
+            tss = sf::TotSnowStorage(ss, sws, SnowFrac, RainFrac);
             if (glac_in) tss = tss + g_tss.v[j];
-            SnowR = sws == MaxSWS ? ((ActSnowMelt + Rain) - (sws - OldSWS)) * SnowFrac : 0.0f;
+            SnowR = sf::SnowR(sws, MaxSWS, ActSnowMelt, Rain, OldSWS, SnowFrac);
             if (glac_in) SnowR = SnowR + g_snowr.v[j];
             SnowSoil = SnowR * p.snow_f;
             SnowR = SnowR * p.one_minus_snow_f;
             if (has_ow) SnowR = SnowR * omow;
         }
-        const float ETpot = ETref * PV(kc, kc);                               // ET.py:24-26
+        const float ETpot = sf::ETpot(ETref, PV(kc, kc));                  // ET.py:24-26
         // ---- rootzone, sphy.py:904-981 + rootzone.py ---------------------------------------------------
         float rw = RW.v[j] + CapRise.v[j];
         if (SNOW) rw = rw + SnowSoil;
         const float rsat = PV(root_sat, root_sat), rfield = PV(root_field, root_field);
         float Infil, RootRunoff;
-        if (INFIL) {
-            const float cap = ((p.k_eff * PV(root_ksat, root_ksat)) / 24.0f) * d_pow(one + ((rsat - rw) / rsat), p.labda_infil);
-            const float ar = p.alpha * Rain;
-            const float dd = ar - cap;
-            const float iex = ar > cap ? Rain - (dd * dd) / (p.alpha_sq * Rain) : Rain;
-            Infil = fmaxf(0.0f, fminf(iex, rsat - rw)) * (one - paved.v[j]);
-            RootRunoff = Rain - Infil;
-        } else {
-            Infil = fmaxf(0.0f, fminf(fminf(Rain, PV(root_ksat, root_ksat)), rsat - rw));
-            RootRunoff = RainFrac > 0.0f ? Rain - Infil : 0.0f;
-        }
+        if (INFIL)
+            sf::RootRunoff_infil(p.k_eff, PV(root_ksat, root_ksat), rsat, rw, p.labda_infil, p.alpha, p.alpha_sq, Rain, paved.v[j],
+                                 RootRunoff, Infil);
+        else
+            sf::RootRunoff_sat(RainFrac, Rain, rw, rsat, PV(root_ksat, root_ksat), RootRunoff, Infil);
         rw = RainFrac > 0.0f ? rw + Infil : rw;
-        float etreddry;
-        if (pws) {                                                         // ET.py:39-47
-            const float TAW = rfield - PV(root_dry, root_dry);
-            const float pf = fmaxf(fminf(pmap.v[j] + 0.04f * (5.0f - ETpot), 0.8f), 0.1f);
-            const float RootPWS = rfield - TAW * pf;
-            etreddry = fmaxf(fminf((rw - PV(root_dry, root_dry)) / (RootPWS - PV(root_dry, root_dry)), one), 0.0f);
-        } else {
-            etreddry = fmaxf(fminf((rw - PV(root_dry, root_dry)) / (PV(root_wilt, root_wilt) - PV(root_dry, root_dry)), one), 0.0f);
-        }
-        const float etredwet = rw >= rsat ? 0.0f : one;                    // ET.py:31
-        const float ETact = RainFrac > 0.0f ? fminf((ETpot * etreddry) * etredwet, rw) : 0.0f;
+        const float etreddry = pws ? sf::ks(rfield, PV(root_dry, root_dry), pmap.v[j], rw, ETpot)
+                                   : sf::etreddry(rw, PV(root_dry, root_dry), PV(root_wilt, root_wilt));
+        const float ETact = sf::ETact(ETpot, rw, rsat, etreddry, RainFrac);
         const float ActETact = ETact * RainFrac;
         rw = fmaxf(rw - ETact, 0.0f);
         const float er = PV(e_root, e_root);
         const float ex = fmaxf(rw - rfield, 0.0f);
-        const float rootlat = (ex / (rsat - rfield)) * drainvel.v[j];
-        const float tD = fmaxf(fminf(ex, rootlat * (one - er) + RootDrain.v[j] * er), 0.0f);    // rootzone.py:63-74
+        const float tD = sf::RootDrainage(rw, RootDrain.v[j], rfield, rsat, drainvel.v[j], er);
         float sw = SW.v[j];
         const float ssat = PV(sub_sat, sub_sat);
-        float perc = ex * (one - er);                                      // rootzone.py:78-85
-        perc = sw >= ssat ? 0.0f : fminf(ssat - sw, perc);
-        const float tP = fmaxf(fminf(perc, ex), 0.0f);
+        const float tP = sf::RootPercolation(rw, sw, rfield, er, ssat);
         const float RootOut = tD + tP;
-        const float frac = (RootOut - ex) / RootOut;                       // rootzone.py:89-94
-        const bool over = RootOut > ex;
-        const float rdrain = over ? tD - tD * frac : tD;
-        const float rootperc = over ? tP - tP * frac : tP;
+        float newD, newP;
+        sf::CalcFrac(rw, rfield, tD, tP, newD, newP);
+        const bool over = RootOut > ex;                                    // sphy.py:976-978
+        const float rdrain = over ? newD : tD;
+        const float rootperc = over ? newP : tP;
         rw = rw - (rdrain + rootperc);
         // ---- subzone, sphy.py:991-1056 + subzone.py ----------------------------------------------------
         sw = sw + rootperc;
         if (!GROUND) sw = fminf(fmaxf(sw - PV(seep, seepage), 0.0f), ssat);
         const float sfield = PV(sub_field, sub_field);
-        const float subrel = fmaxf(fminf(sw / sfield, one), 0.0f);
-        const float rootrel = fmaxf(fminf(rw / rfield, one), 0.0f);
-        float cr = fminf(sw, (PV(capmax, caprise_max) * (one - rootrel)) * subrel);
-        cr = fminf(cr, rsat - rw);
+        const float cr = sf::CapilRise(sfield, sw, PV(capmax, caprise_max), rw, rsat, rfield);
         sw = sw - cr;
         float subperc = 0.0f, ActSubPerc = 0.0f, sdrain = 0.0f;
         const float es = PV(e_sub, e_sub);
         if (GROUND) {
-            const float dsw = sw - sfield;
-            subperc = (Gw.v[j] < PV(gw_sat, gw_sat) && dsw > 0.0f) ? dsw * (one - es) : 0.0f;          // subzone.py:35-41
+            subperc = sf::SubPercolation(sw, sfield, es, Gw.v[j], PV(gw_sat, gw_sat));
             ActSubPerc = has_glac ? subperc * omg : subperc;
             sw = sw - subperc;
         } else {
-            const float subex = fmaxf(sw - sfield, 0.0f);                                      // subzone.py:45-51
-            const float sublat = (subex / (ssat - sfield)) * sub_drainvel.v[j];
-            sdrain = (sublat + SubDrain.v[j]) * (one - es);
-            sdrain = fmaxf(fminf(sdrain, sw), 0.0f);
+            sdrain = sf::SubDrainage(sw, sfield, ssat, sub_drainvel.v[j], SubDrain.v[j], es);
             sw = sw - sdrain;
         }
         // ---- runoff assembly, sphy.py:1063-1077 --------------------------------------------------------
@@ -314,13 +279,12 @@ __device__ __forceinline__ void wb_cells(const WbArgs &a, int64_t i)
             const float ed = PV(e_delta, e_delta), ea = PV(e_alpha, e_alpha);
             float inflow = ActSubPerc;
             if (glac_in) inflow = inflow + g_perc.v[j];
-            const float gwseep = (one - ed) * inflow;
-            gwr = (ed * GwRecharge.v[j]) + gwseep;
+            gwr = sf::GroundWaterRecharge(ed, GwRecharge.v[j], inflow);
             gw = Gw.v[j] + gwr;
-            baser = gw <= PV(base_thresh, base_thresh) ? 0.0f : (BaseR.v[j] * ea + gwr * (one - ea));
+            baser = sf::BaseFlow(gw, BaseR.v[j], gwr, PV(base_thresh, base_thresh), ea);
             gw = gw - baser;
             if (has_ow) baser = baser * omow;
-            hgw = (H_gw.v[j] * ea) + ((gwr * (one - ea)) / PV(h_den, h_den));
+            hgw = sf::HLevel(H_gw.v[j], ea, gwr, PV(h_den, h_den));
         } else {
             baser = sdrain;                                                // sphy.py:1085
         }

@@ -153,3 +153,109 @@ extern "C" int sphy_set_ncells(sphy_ctx *ctx, int64_t n)
     ctx->n = n;
     return SPHY_OK;
 }
+
+
+// ---- the reference's per-cell process functions, one at a time -----------------------------------------------------
+// sphy_module_op keeps the module call signatures of the reference usable on device maps (sphy_b200/modules/*.py):
+// the same __device__ functions the fused kernel composes, evaluated one whole-map pass per call like PCRaster does.
+namespace {
+
+struct OpArgs {
+    int op;
+    sphy_param in[16];
+    float *out[6];
+    DayScalars d;
+    float melt_cos[24];
+    int64_t n;
+};
+
+__global__ void k_module_op(const __grid_constant__ OpArgs a)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    auto I = [&](int k) { return a.in[k].map ? __ldg(a.in[k].map + i) : a.in[k].value; };
+    float r0 = 0.0f, r1 = 0.0f, r2 = 0.0f, r3 = 0.0f, r4 = 0.0f, r5 = 0.0f;
+    switch (a.op) {
+        case SPHY_OP_SNOW_DYNAMIC: {                   // snow.dynamic, modules/snow.py:110-187
+            // in: Temp TempMax Precip Tcrit DDFS SnowSC SnowStore SnowWatStore SnowFrac RainFrac TotalSnowStore_GLAC
+            //     SnowR_GLAC SnowF (1-SnowF) (1-openWaterFrac)     out: Rain SnowR SnowSoil SnowStore SnowWatStore TotalSnowStore
+            const float Temp = I(0), TempMax = I(1), Precip = I(2);
+            const float Snow = Temp >= I(3) ? 0.0f : Precip;
+            const float Rain = Temp < I(3) ? 0.0f : Precip;
+            const float Pot = TempMax < 0.0f ? 0.0f : sf::PotSnowMelt(Temp, TempMax, I(4), a.melt_cos);
+            const float Act = sf::ActSnowMelt(I(6), Pot);
+            const float ss = sf::SnowStoreUpdate(I(6), Snow, Act, Temp, I(7));
+            const float MaxSWS = sf::MaxSnowWatStorage(I(5), ss);
+            const float sws = sf::SnowWatStorage(TempMax, MaxSWS, I(7), Act, Rain);
+            const float tss = sf::TotSnowStorage(ss, sws, I(8), I(9)) + I(10);
+            float SnowR = sf::SnowR(sws, MaxSWS, Act, Rain, I(7), I(8)) + I(11);
+            const float SnowSoil = SnowR * I(12);
+            SnowR = (SnowR * I(13)) * I(14);
+            r0 = Rain; r1 = SnowR; r2 = SnowSoil; r3 = ss; r4 = sws; r5 = tss;
+        } break;
+        case SPHY_OP_GROUNDWATER_DYNAMIC: {            // groundwater.dynamic, modules/groundwater.py:90-125
+            // in: e_delta GwRecharge ActSubPerc GlacPerc Gw BaseR BaseThresh e_alpha H_gw h_den (1-openWaterFrac)
+            // out: GwRecharge Gw BaseR H_gw
+            const float gwr = sf::GroundWaterRecharge(I(0), I(1), I(2) + I(3));
+            float gw = I(4) + gwr;
+            float baser = sf::BaseFlow(gw, I(5), gwr, I(6), I(7));
+            gw = gw - baser;
+            baser = baser * I(10);
+            r0 = gwr; r1 = gw; r2 = baser; r3 = sf::HLevel(I(8), I(7), gwr, I(9));
+        } break;
+        case SPHY_OP_EXTRARAD: {                       // in: Lat [deg]
+            const float latrad = I(0) * 0.017453292519943295f;
+            r0 = extrarad(sf::d_sin(latrad), sf::d_cos(latrad), sf::d_tan(latrad), a.d);
+        } break;
+        case SPHY_OP_HARGREAVES: r0 = sf::Hargreaves(a.d.hg_c, I(0), I(1), I(2), I(3)); break;        // ra temp tempmax tempmin
+        case SPHY_OP_ETPOT: r0 = sf::ETpot(I(0), I(1)); break;                                         // etr kc
+        case SPHY_OP_ETACT: r0 = sf::ETact(I(0), I(1), I(2), I(3), I(4)); break;                       // etpot rootwater rootsat etreddry rainfrac
+        case SPHY_OP_KS: r0 = sf::ks(I(0), I(1), I(2), I(3), I(4)); break;                             // rootfield rootdry pmap rootwater etpot
+        case SPHY_OP_POTSNOWMELT: r0 = sf::PotSnowMelt(I(0), I(1), I(2), a.melt_cos); break;           // temp tempmax ddfs
+        case SPHY_OP_ACTSNOWMELT: r0 = sf::ActSnowMelt(I(0), I(1)); break;
+        case SPHY_OP_SNOWSTOREUPDATE: r0 = sf::SnowStoreUpdate(I(0), I(1), I(2), I(3), I(4)); break;
+        case SPHY_OP_MAXSNOWWATSTORAGE: r0 = sf::MaxSnowWatStorage(I(0), I(1)); break;
+        case SPHY_OP_SNOWWATSTORAGE: r0 = sf::SnowWatStorage(I(0), I(1), I(2), I(3), I(4)); break;
+        case SPHY_OP_TOTSNOWSTORAGE: r0 = sf::TotSnowStorage(I(0), I(1), I(2), I(3)); break;
+        case SPHY_OP_SNOWR: r0 = sf::SnowR(I(0), I(1), I(2), I(3), I(4), I(5)); break;
+        case SPHY_OP_ROOTRUNOFF_SAT: sf::RootRunoff_sat(I(0), I(1), I(2), I(3), I(4), r0, r1); break;  // rainfrac rain rootwater rootsat rootksat
+        case SPHY_OP_ROOTRUNOFF_INFIL:                 // k_eff rootksat rootsat rootwater labda alpha alpha_sq rain paved
+            sf::RootRunoff_infil(I(0), I(1), I(2), I(3), I(4), I(5), I(6), I(7), I(8), r0, r1);
+            break;
+        case SPHY_OP_ROOTDRAINAGE: r0 = sf::RootDrainage(I(0), I(1), I(2), I(3), I(4), I(5)); break;   // rootwater rootdrain rootfield rootsat drainvel e_root
+        case SPHY_OP_ROOTPERCOLATION: r0 = sf::RootPercolation(I(0), I(1), I(2), I(3), I(4)); break;   // rootwater subwater rootfield e_root subsat
+        case SPHY_OP_CALCFRAC: sf::CalcFrac(I(0), I(1), I(2), I(3), r0, r1); break;                    // rootwater rootfield rootdrain rootperc
+        case SPHY_OP_CAPILRISE: r0 = sf::CapilRise(I(0), I(1), I(2), I(3), I(4), I(5)); break;         // subfield subwater capmax rootwater rootsat rootfield
+        case SPHY_OP_SUBPERCOLATION: r0 = sf::SubPercolation(I(0), I(1), I(2), I(3), I(4)); break;     // subwater subfield e_sub gw gwsat
+        case SPHY_OP_SUBDRAINAGE: r0 = sf::SubDrainage(I(0), I(1), I(2), I(3), I(4), I(5)); break;     // subwater subfield subsat drainvel subdrainage e_sub
+        case SPHY_OP_GWRECHARGE: r0 = sf::GroundWaterRecharge(I(0), I(1), I(2) + I(3)); break;         // e_delta gwrecharge subperc glacperc
+        case SPHY_OP_BASEFLOW: r0 = sf::BaseFlow(I(0), I(1), I(2), I(3), I(4)); break;                 // gw baser gwrecharge basethresh e_alpha
+        case SPHY_OP_HLEVEL: r0 = sf::HLevel(I(0), I(1), I(2), I(3)); break;                           // Hgw e_alpha gwrecharge h_den
+        default: break;
+    }
+    const float r[6] = {r0, r1, r2, r3, r4, r5};
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+        if (a.out[k]) a.out[k][i] = r[k];
+}
+
+}  // namespace
+
+extern "C" int sphy_module_op(sphy_ctx *ctx, int op, const sphy_param *in, int n_in, float *const *out, int n_out, int64_t count,
+                              float k0, int day_of_year, void *stream)
+{
+    if (!ctx || !in || !out || n_in < 1 || n_in > 16 || n_out < 1 || n_out > 6 || count < 0 || op < 0 || op >= SPHY_OP_COUNT)
+        return SPHY_E_INVALID;
+    if (count == 0) return SPHY_OK;
+    OpArgs a = {};
+    a.op = op;
+    for (int k = 0; k < n_in; ++k) a.in[k] = in[k];
+    for (int k = 0; k < n_out; ++k) a.out[k] = out[k];
+    if (!a.out[0]) SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_module_op: first output is NULL");
+    a.d = day_scalars(day_of_year, k0);
+    for (int h = 1; h <= 24; ++h) a.melt_cos[h - 1] = (float)cos((double)(float)(3.1415 * h / 12));     // snow.py:30
+    a.n = count;
+    k_module_op<<<div_up(count, 256), 256, 0, (cudaStream_t)stream>>>(a);
+    SPHY_LAUNCH_CHECK(ctx);
+    return SPHY_OK;
+}

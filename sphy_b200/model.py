@@ -179,6 +179,13 @@ class SphyModel:
         # -- routing structures first: they define the active cells / compact order (routing.py:33-38)
         self._build_cells()
         self._read_parameters()
+        # the process modules under the reference's attribute names (sphy.py:60-78, 210-213, 297-300, 374-377 ...)
+        from . import modules
+        modules.bind(self)
+        self.ET, self.rootzone, self.subzone, self.Hargreaves = modules.ET, modules.rootzone, modules.subzone, modules.hargreaves
+        self.groundwater, self.snow, self.glacier = modules.groundwater, modules.snow, modules.glacier
+        self.routing, self.advanced_routing = modules.routing, modules.advanced_routing
+        self.lakes, self.reservoirs = modules.lakes, modules.reservoirs
 
     # ------------------------------------------------------------------------------------------
     def close(self):
@@ -820,12 +827,9 @@ class SphyModel:
         else:
             F.tmin, F.tmax = f["tmin"].data_ptr(), f["tmax"].data_ptr()
         doy = julian(self.curdate)
+        self._doy = doy
         if self.GlacFLAG == 1:                                                                 # sphy.py:843-853
-            self._glT.lapse = float(self.TLapse.at[self.curdate.month])
-            self._ck(lib.sphy_glac_step(ctx, C.byref(self._glT), f["tavg"].data_ptr(), f["prec"].data_ptr(),
-                                        C.c_float(self._wbP.tcorr), C.c_float(self._wbP.pcorr), C.byref(self._glO), st),
-                     "sphy_glac_step")
-            a = self._glac_agg
+            a = self._glacier_step(f["tavg"], f["prec"])
             F.TotalSnowStore_GLAC, F.SnowR_GLAC = a["TotalSnowStore_GLAC"].data_ptr(), a["SnowR_GLAC"].data_ptr()
             F.GlacPerc, F.GlacR = a["GlacPerc"].data_ptr(), a["GlacR"].data_ptr()
         prof = self._prof
@@ -838,29 +842,9 @@ class SphyModel:
             ev[1].record()
         self.Q = None
         if self.LakeFLAG == 1 or self.ResFLAG == 1:                                            # sphy.py:1100-1104
-            self._ck(lib.sphy_route_reslake_step(ctx, C.byref(self._rl_struct), self.TotR.data_ptr(), self.QRAold.data_ptr(),
-                                                 self._kx, C.c_float(self._one_m_kx), doy, st), "sphy_route_reslake_step")
-            self.Q = self.QRAold
+            self.Q = self.advanced_routing.dynamic(self, None, None, self.config, self.TotR, None, None)
         elif self.RoutFLAG == 1:                                                               # sphy.py:1107-1108
-            src = [self.TotR]
-            dst = [self.QRAold]
-            comp_src = {"RootR": self.RootRR, "RootD": self.RootDR, "Rain": self.RainR,
-                        "Snow": self.SnowR if self.SnowR is not None else self._zeros,
-                        "Glac": self.GlacR if self.GlacFLAG == 1 else self._zeros,
-                        "Base": self.BaseR if self.GroundFLAG == 1 else self.SubDrain}          # sphy.py:1085
-            for c in COMPONENTS:
-                if self.RA_FLAG[c]:
-                    src.append(comp_src[c])
-                    dst.append(getattr(self, c + "RAold"))
-            nc = len(src)
-            srcp = (C.c_void_p * nc)(*[t.data_ptr() for t in src])
-            dstp = (C.c_void_p * nc)(*[t.data_ptr() for t in dst])
-            if self.world > 1:
-                self._route_partitioned(nc, srcp, dstp, st)
-            else:
-                self._ck(lib.sphy_route_step(ctx, nc, srcp, dstp, self._kx, C.c_float(self._one_m_kx), self.route_method, st),
-                         "sphy_route_step")
-            self.Q = self.QRAold
+            self.Q = self.routing.dynamic(self, None, self.TotR)
         if prof is not None:
             ev[2].record()
             prof["wb"].append((ev[0], ev[1]))
@@ -871,6 +855,59 @@ class SphyModel:
             self.tss["QallRAtot"].append(self._station_buf[: len(self.station_ids)].clone())
         self.curdate = self.curdate + datetime.timedelta(days=1)
         return self.Q if self.Q is not None else self.TotR
+
+    def _glacier_step(self, tavg, prec):
+        """glacier.dynamic (modules/glacier.py:256-498) on the raw forcing maps of the day -> per-cell aggregates."""
+        self._glT.lapse = float(self.TLapse.at[self.curdate.month])
+        self._ck(self.lib.sphy_glac_step(self._ctx, C.byref(self._glT), tavg.data_ptr(), prec.data_ptr(), C.c_float(self._wbP.tcorr),
+                                         C.c_float(self._wbP.pcorr), C.byref(self._glO), self._stream()), "sphy_glac_step")
+        return self._glac_agg
+
+    def _route_simple(self, TotR):
+        """routing.dynamic (modules/routing.py:70-116): total flow + every flagged component share one pass."""
+        src = [TotR]
+        dst = [self.QRAold]
+        comp_src = {"RootR": self.RootRR, "RootD": self.RootDR, "Rain": self.RainR,
+                    "Snow": self.SnowR if self.SnowR is not None else self._zeros,
+                    "Glac": self.GlacR if self.GlacFLAG == 1 else self._zeros,
+                    "Base": self.BaseR if self.GroundFLAG == 1 else self.SubDrain}              # sphy.py:1085
+        for c in COMPONENTS:
+            if self.RA_FLAG[c]:
+                src.append(comp_src[c])
+                dst.append(getattr(self, c + "RAold"))
+        nc = len(src)
+        srcp = (C.c_void_p * nc)(*[t.data_ptr() for t in src])
+        dstp = (C.c_void_p * nc)(*[t.data_ptr() for t in dst])
+        st = self._stream()
+        if self.world > 1:
+            self._route_partitioned(nc, srcp, dstp, st)
+        else:
+            self._ck(self.lib.sphy_route_step(self._ctx, nc, srcp, dstp, self._kx, C.c_float(self._one_m_kx), self.route_method, st),
+                     "sphy_route_step")
+        return self.QRAold
+
+    def _route_reslake(self, TotR):
+        """advanced_routing.dynamic (modules/advanced_routing.py:134-217) incl. lakes.QLake / reservoirs.QRes."""
+        self._ck(self.lib.sphy_route_reslake_step(self._ctx, C.byref(self._rl_struct), TotR.data_ptr(), self.QRAold.data_ptr(),
+                                                  self._kx, C.c_float(self._one_m_kx), self._doy, self._stream()),
+                 "sphy_route_reslake_step")
+        return self.QRAold
+
+    def structure_outflow(self, kind=None):
+        """Dense map of the last step's lake/reservoir outflow Qout [m3/day] (0 elsewhere); kind 1 simple reservoir,
+        2 advanced reservoir, 3 lake, or a tuple of kinds."""
+        out = torch.zeros(self.n, dtype=torch.float32, device=self.device)
+        if len(self._rl_cells_host):
+            kinds = self._rl["kind"]
+            q = self._rl["Qout"]
+            if kind is not None:
+                ks = kind if isinstance(kind, (tuple, list)) else (kind,)
+                sel = torch.zeros_like(kinds, dtype=torch.bool)
+                for k in ks:
+                    sel |= kinds == k
+                q = torch.where(sel, q, torch.zeros_like(q))
+            out[torch.from_numpy(self._rl_cells_host.astype(np.int64)).to(self.device)] = q
+        return out
 
     def _route_partitioned(self, nc, srcp, dstp, st):
         """Per-step confluence exchange: local scan -> all-gather of range totals / prefixes over NCCL -> trunk fix-up."""
