@@ -47,7 +47,7 @@ const char *sphy_last_error(const sphy_ctx *ctx);
 int sphy_sm_count(const sphy_ctx *ctx);
 /* sizeof() of the ABI structs, so foreign-language bindings can verify their layout without a GPU:
  * 0 sphy_param, 1 sphy_wb_params, 2 sphy_wb_state, 3 sphy_wb_forcing, 4 sphy_wb_out, 5 sphy_glac_table,
- * 6 sphy_glac_out, 7 sphy_reslake */
+ * 6 sphy_glac_out, 7 sphy_reslake, 8 sphy_openwater */
 size_t sphy_abi_sizeof(int which);
 
 /* ---- K3: LDD -> integer structures (once per run) ------------------------------------------
@@ -264,6 +264,21 @@ typedef struct {
 
 int sphy_route_reslake_step(sphy_ctx *ctx, const sphy_reslake *rl, const float *totr_mm, float *q_state,
                             sphy_param kx, float one_minus_kx, int day_of_year, void *stream);
+
+/* Open-water evaporation and precipitation on lakes/reservoirs (modules/advanced_routing.py:167-196, ETOpenWaterFLAG):
+ * StorRES -= min(areatotal(ETOpenWater*cellarea*openWaterFrac, class)*0.001, StorRES); += areatotal(Precip*...)*0.001.
+ * ow_ptr/ow_cell: for each structure, the cells of its open-water class (sphy.py:425-431: 8-connected clumps of
+ * openWaterFrac > 0 labelled with the largest reservoir id inside) that have openWaterFrac > 0.  Call after
+ * sphy_route_reslake_step. */
+typedef struct {
+    const int32_t *ow_ptr;           /* [n_struct + 1] */
+    const int32_t *ow_cell;          /* [ow_ptr[n_struct]] */
+    const float *open_water_frac;    /* dense N-cell map */
+    const float *et_open_water;      /* dense N-cell map: sphy_wb_out.ETOpenWater of the step */
+    const float *prec;               /* dense N-cell map: the day's raw precipitation forcing */
+    float pcorr;
+} sphy_openwater;
+int sphy_reslake_openwater(sphy_ctx *ctx, const sphy_reslake *rl, const sphy_openwater *ow, void *stream);
 
 #ifdef __cplusplus
 }

@@ -52,6 +52,9 @@ CASES = {
     # BASELINE config 3: reservoirs (simple + advanced) and lakes
     "c3_res_lake": (dict(nrows=16, ncols=14, seed=31, cellsize=1000.0, reservoirs=True, lakes=True, n_res_simple=2,
                          n_res_adv=2, n_lakes=4, params=WET, start=(2001, 5, 1)), 70),
+    # open-water evaporation / precipitation on the water bodies (advanced_routing.py:167-196)
+    "c3_openwater": (dict(nrows=16, ncols=14, seed=34, cellsize=1000.0, reservoirs=True, lakes=True, n_res_simple=2, n_res_adv=1,
+                          n_lakes=2, open_water=True, params=WET, start=(2001, 6, 1)), 50),
     "c3_res_only": (dict(nrows=14, ncols=12, seed=32, cellsize=1000.0, reservoirs=True, n_res_simple=2, n_res_adv=1,
                          params=WETK), 40),
     "c3_lake_only": (dict(nrows=14, ncols=12, seed=33, cellsize=1000.0, lakes=True, n_lakes=4, params=WET), 40),

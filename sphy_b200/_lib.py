@@ -70,6 +70,10 @@ class ResLake(C.Structure):
                 ("Qout", P), ("Qin", P)]
 
 
+class OpenWater(C.Structure):
+    _fields_ = [("ow_ptr", P), ("ow_cell", P), ("open_water_frac", P), ("et_open_water", P), ("prec", P), ("pcorr", C.c_float)]
+
+
 RL_NPAR = 23
 WB_SNOW, WB_GROUND, WB_INFIL_EXCESS, WB_PWS, WB_ETREF_INPUT = 1, 2, 4, 8, 16
 RA_TABLE, RA_CELL = 0, 1
@@ -110,10 +114,11 @@ SYMBOLS = {
     "sphy_route_scan_finish": (C.c_int, [P, C.c_int, C.POINTER(P), SphyParam, C.c_float, P, C.c_int32, C.c_int, C.c_int, P]),
     "sphy_accuflux": (C.c_int, [P, P, P, P, C.c_int, P]),
     "sphy_upstream": (C.c_int, [P, P, P, P]),
+    "sphy_reslake_openwater": (C.c_int, [P, C.POINTER(ResLake), C.POINTER(OpenWater), P]),
     "sphy_route_reslake_step": (C.c_int, [P, C.POINTER(ResLake), P, P, SphyParam, C.c_float, C.c_int, P]),
 }
 
-ABI_STRUCTS = (SphyParam, WbParams, WbState, WbForcing, WbOut, GlacTable, GlacOut, ResLake)
+ABI_STRUCTS = (SphyParam, WbParams, WbState, WbForcing, WbOut, GlacTable, GlacOut, ResLake, OpenWater)
 
 _LIB = None
 

@@ -113,6 +113,7 @@ extern "C" size_t sphy_abi_sizeof(int which)
         case 5: return sizeof(sphy_glac_table);
         case 6: return sizeof(sphy_glac_out);
         case 7: return sizeof(sphy_reslake);
+        case 8: return sizeof(sphy_openwater);
         default: return 0;
     }
 }

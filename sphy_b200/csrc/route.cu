@@ -367,3 +367,43 @@ extern "C" int sphy_route_reslake_step(sphy_ctx *ctx, const sphy_reslake *rl, co
     }
     return SPHY_OK;
 }
+
+
+// ---- open-water evaporation / precipitation on the structures (advanced_routing.py:167-196) -----------------------
+namespace {
+__global__ void k_rl_openwater(sphy_reslake rl, sphy_openwater ow, float cellarea)
+{
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;          // one warp per structure
+    const int lane = threadIdx.x & 31;
+    if (j >= rl.n_struct) return;
+    double se = 0.0, sp = 0.0;
+    for (int32_t q = ow.ow_ptr[j] + lane; q < ow.ow_ptr[j + 1]; q += 32) {
+        const int32_t c = ow.ow_cell[q];
+        const float fr = ow.open_water_frac[c];
+        se += (double)((ow.et_open_water[c] * cellarea) * fr);             // areatotal: REAL8 sum of REAL4 terms
+        sp += (double)(((ow.prec[c] / ow.pcorr) * cellarea) * fr);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        se += __shfl_xor_sync(0xffffffffu, se, o);
+        sp += __shfl_xor_sync(0xffffffffu, sp, o);
+    }
+    if (lane == 0) {
+        const float S = rl.StorRES[j];
+        const float eta = S > 0.0f ? fminf((float)se * 0.001f, S) : 0.0f;
+        const float pr = S > 0.0f ? (float)sp * 0.001f : 0.0f;
+        rl.StorRES[j] = (S - eta) + pr;
+    }
+}
+}  // namespace
+
+extern "C" int sphy_reslake_openwater(sphy_ctx *ctx, const sphy_reslake *rl, const sphy_openwater *ow, void *stream)
+{
+    if (!ctx || !rl || !ow) return SPHY_E_INVALID;
+    if (rl->n_struct <= 0) return SPHY_OK;
+    if (!ow->ow_ptr || !ow->ow_cell || !ow->open_water_frac || !ow->et_open_water || !ow->prec || !rl->StorRES)
+        SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_reslake_openwater: incomplete arguments");
+    k_rl_openwater<<<div_up((int64_t)rl->n_struct * 32, 128), 128, 0, (cudaStream_t)stream>>>(*rl, *ow, ctx->cellarea);
+    SPHY_LAUNCH_CHECK(ctx);
+    return SPHY_OK;
+}

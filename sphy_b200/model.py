@@ -406,9 +406,14 @@ class SphyModel:
             self.kx = self._scalar_or_map("ROUTING", "kx")
         # open water, sphy.py:416-436
         self.ETOpenWaterFLAG = cfg.getint("OPENWATER", "ETOpenWaterFLAG")
-        if self.ETOpenWaterFLAG == 1:
-            raise NotImplementedError("open-water evaporation (areatotal over clumps) is not supported yet")
         self.openWaterFrac = None
+        if self.ETOpenWaterFLAG == 1:
+            if self.ResFLAG != 1:
+                raise ValueError("ETOpenWaterFLAG = 1 needs ResFLAG = 1: the open-water classes are labelled with ResID "
+                                 "(reference quirk Q21, sphy.py:430)")
+            self.kcOpenWater = cfg.getfloat("OPENWATER", "kcOpenWater")
+            self._ow_raster = np.asarray(self._readmap(cfg.get("OPENWATER", "openWaterFrac")), np.float32)
+            self.openWaterFrac = cn(self._ow_raster)
         # infiltration excess, sphy.py:439-458
         self.InfilFLAG = cfg.getfloat("INFILTRATION", "Infil_excess")
         if self.InfilFLAG == 1:
@@ -510,6 +515,8 @@ class SphyModel:
         if self.diagnostics:
             for k in ("ETref", "ETact", "ActETact", "Infil", "Rain", "RootPerc", "SubPerc", "wbal"):
                 self.out[k] = self._full(0.0)
+        if self.ETOpenWaterFLAG == 1:
+            self.out["ETOpenWater"] = self._full(0.0)                   # ET.ETpot(ETref, kcOpenWater), sphy.py:898
         self._prepare_wb_structs()
         # time series at `Locations` (TimeoutputTimeseries, sphy.py:683-691): cells with id > 0, ordered by id
         loc_cells = np.flatnonzero(self.Locations > 0)
@@ -649,9 +656,38 @@ class SphyModel:
                     "StorRES": self._dev(stor[cells] if ns else np.zeros(1, np.float32)),
                     "Qout": torch.zeros(max(ns, 1), dtype=torch.float32, device=self.device),
                     "Qin": torch.zeros(max(ns, 1), dtype=torch.float32, device=self.device)}
+        if self.ETOpenWaterFLAG == 1:
+            self._openwater_initial(cells)
         r = self._rl
         self._rl_struct = _lib.ResLake(ns, r["cell"].data_ptr(), r["kind"].data_ptr(), r["par"].data_ptr(),
                                        self.QFRAC.data_ptr(), r["StorRES"].data_ptr(), r["Qout"].data_ptr(), r["Qin"].data_ptr())
+
+    def _openwater_initial(self, struct_cells):
+        """sphy.py:425-431: 8-connected clumps of the open-water mask, each labelled with the largest ResID inside;
+        per structure the list of cells of its class with openWaterFrac > 0 (what areatotal sums over)."""
+        from scipy import ndimage
+        mask = self._ow_raster > 0
+        clumps = np.zeros(mask.shape, np.int64)
+        nxt = 0
+        for val in (False, True):
+            lab, cnt = ndimage.label(mask == val, structure=np.ones((3, 3), dtype=int))
+            clumps[lab > 0] = lab[lab > 0] + nxt
+            nxt += cnt
+        res_raster = np.maximum(np.asarray(self._readmap(self.config.get("RESERVOIR", "ResId"))), 0).astype(np.int64)
+        best = np.zeros(nxt + 1, np.int64)
+        np.maximum.at(best, clumps.ravel(), res_raster.ravel())
+        cls = self._compact_np(best[clumps], np.int64)                 # class of every active cell (device order)
+        wet = np.flatnonzero(self.openWaterFrac > 0)
+        by_class = {}
+        for c in wet:
+            by_class.setdefault(int(cls[c]), []).append(int(c))
+        ptr, lst = [0], []
+        for c in struct_cells:
+            lst.extend(by_class.get(int(cls[int(c)]), []))
+            ptr.append(len(lst))
+        self._ow_ptr = self._dev(np.asarray(ptr, np.int32))
+        self._ow_cell = self._dev(np.asarray(lst if lst else [0], np.int32))
+        self._ow_frac_dev = self._dev(self.openWaterFrac)
 
     @property
     def StorRES(self):
@@ -706,6 +742,9 @@ class SphyModel:
             P.pmap = pr(self.PMap)
         if self.GlacFrac is not None:
             P.glac_frac = SphyParam(self.GlacFrac.data_ptr(), 0.0)
+        if self.openWaterFrac is not None:
+            P.open_water_frac = SphyParam(self._ow_frac_dev.data_ptr(), 0.0)
+            P.kc_open_water = float(f32(self.kcOpenWater))
         if self.InfilFLAG == 1:
             P.k_eff, P.alpha = float(f32(self.K_eff)), float(f32(self.Alpha))
             P.alpha_sq, P.labda_infil = float(f32(self.Alpha ** 2)), float(f32(self.Labda_Infil))
@@ -822,6 +861,7 @@ class SphyModel:
         f = self._ingest(self.counter)
         F = _lib.WbForcing()
         F.prec, F.tavg = f["prec"].data_ptr(), f["tavg"].data_ptr()
+        self._prec_ptr = F.prec
         if self.ETREF_FLAG == 1:
             F.etref = f["etref"].data_ptr()
         else:
@@ -891,6 +931,11 @@ class SphyModel:
         self._ck(self.lib.sphy_route_reslake_step(self._ctx, C.byref(self._rl_struct), TotR.data_ptr(), self.QRAold.data_ptr(),
                                                   self._kx, C.c_float(self._one_m_kx), self._doy, self._stream()),
                  "sphy_route_reslake_step")
+        if self.ETOpenWaterFLAG == 1:                                                          # advanced_routing.py:167-196
+            ow = _lib.OpenWater(self._ow_ptr.data_ptr(), self._ow_cell.data_ptr(), self._ow_frac_dev.data_ptr(),
+                                self.out["ETOpenWater"].data_ptr(), self._prec_ptr, self._wbP.pcorr)
+            self._ck(self.lib.sphy_reslake_openwater(self._ctx, C.byref(self._rl_struct), C.byref(ow), self._stream()),
+                     "sphy_reslake_openwater")
         return self.QRAold
 
     def structure_outflow(self, kind=None):

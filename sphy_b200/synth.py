@@ -473,9 +473,15 @@ def make_catchment(nrows, ncols, cellsize=250.0, seed=1, nsteps=365, snow=False,
         _add_reservoirs_lakes(cat, rng, nup, n_res_simple if reservoirs else 0, n_res_adv if reservoirs else 0,
                               n_lakes if lakes else 0)
         if open_water:
+            # water bodies of a few cells around every reservoir (fractions 0.3-0.9): clumps, some merging
             ow = np.zeros((nrows, ncols), np.float32)
-            sel = (cat.res_id > 0) if cat.res_id is not None else np.zeros((nrows, ncols), bool)
-            ow[sel] = 0.5
+            if cat.res_id is not None:
+                for r, c in zip(*np.nonzero(cat.res_id > 0)):
+                    r0, r1, c0, c1 = max(r - 1, 0), min(r + 2, nrows), max(c - 1, 0), min(c + 2, ncols)
+                    blk = rng.uniform(0.3, 0.9, size=(r1 - r0, c1 - c0)).astype(np.float32)
+                    blk[rng.random(blk.shape) < 0.4] = 0.0
+                    ow[r0:r1, c0:c1] = np.maximum(ow[r0:r1, c0:c1], blk)
+                    ow[r, c] = np.float32(rng.uniform(0.5, 0.9))
             cat.open_water_frac = ow
     return cat
 
