@@ -76,6 +76,10 @@ int sphy_ldd_export(sphy_ctx *ctx, const char *name, void *dst_dev, size_t dst_b
 /* raster <-> compact (readmap / report side of the boundary): out[k] = raster[cell k] and back */
 int sphy_gather_f32(sphy_ctx *ctx, const float *raster_dev, float *compact_dev, void *stream);
 int sphy_scatter_f32(sphy_ctx *ctx, const float *compact_dev, float *raster_dev, float fill, void *stream);
+/* reporting accumulators (utilities/reporting.py:24-95): acc = acc + x (divisor == 0) or acc + x/divisor, and
+ * out = in/divisor, each one REAL4 operation per cell like the reference's `tot + var`, `var / dim`, `tot / ydays` */
+int sphy_map_accumulate(sphy_ctx *ctx, float *acc, const float *x, float divisor, int64_t count, void *stream);
+int sphy_map_divide(sphy_ctx *ctx, const float *in, float divisor, float *out, int64_t count, void *stream);
 /* TimeoutputTimeseries.sample (sphy.py:683-691): out[j] = map[cells[j]] */
 int sphy_sample(sphy_ctx *ctx, const float *map_dev, const int32_t *cells_dev, int n, float *out_dev, void *stream);
 
@@ -139,7 +143,7 @@ typedef struct {                     /* forcing maps of the day (sphy.py:755-809
 typedef struct {                     /* outputs; every pointer except TotR may be NULL */
     float *TotR;                     /* sphy.py:1096 */
     float *RootRR, *RootDR, *RainR, *SnowR;           /* component runoff (sphy.py:1067-1075, snow.py:183) */
-    float *ETref, *ETact, *ActETact, *Infil, *Rain, *RootPerc, *SubPerc, *wbal, *ETOpenWater;
+    float *ETref, *ETact, *ActETact, *Infil, *Rain, *RootPerc, *SubPerc, *wbal, *ETOpenWater, *Precip;
 } sphy_wb_out;
 
 /* init-time derived maps, evaluated like the oracle (double on the REAL4 operand, REAL4 result):

@@ -44,6 +44,11 @@ CASES = {
     "c1_soilcls": (dict(nrows=12, ncols=10, seed=14, soil_classes=3, params=WETK), 40),
     # plant water stress (ET.ks) instead of the wilting-point reduction
     "c1_pws": (dict(nrows=12, ncols=10, seed=15, pws=True, params=WET), 40),
+    # reporting.csv driven outputs (utilities/reporting.py): month / year / final maps, averages, long-term sums, TSS
+    "c1_reporting": (dict(nrows=10, ncols=9, seed=16, rout_components=True, params=WET, start=(2001, 11, 20),
+                          report_opts={"TotRF": ("M+F", "Y", "D"), "TotETactF": ("Y", "M", "M"), "QallRAtot": ("D", "NONE", "D+Y"),
+                                       "StorRootW": ("YS", "YA", "NONE"), "TotPrec": ("MS", "MA", "NONE"),
+                                       "BaseRAtot": ("M", "NONE", "M")}), 75),
     # BASELINE config 2: snow on (spring melt season, snow line inside the catchment)
     "c2_snow": (dict(nrows=12, ncols=10, seed=21, snow=True, params=COLD, start=(2001, 3, 15), zrange=(1500.0, 5200.0)), 90),
     # BASELINE config 2: snow + glacier, all components routed
@@ -67,7 +72,8 @@ def build_case(name):
     kw = dict(kw)
     if "start" in kw:
         kw["start"] = datetime.date(*kw["start"])
-    return synth.make_catchment(nsteps=nsteps, report_daily=REPORT, **kw), nsteps
+    daily = () if "report_opts" in kw else REPORT
+    return synth.make_catchment(nsteps=nsteps, report_daily=daily, **kw), nsteps
 
 
 def make(name):
@@ -83,6 +89,11 @@ def make(name):
         payload["state/" + k] = v
     for k, v in ref["reports"].items():
         payload["report/" + k] = v
+    if CASES[name][0].get("report_opts"):
+        for k, v in ref["report_files"].items():
+            payload["repfile/" + k] = v
+        for k, v in ref["tss_tables"].items():
+            payload["tss/" + k] = v
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     path = os.path.join(GOLDEN_DIR, name + ".npz")
     np.savez_compressed(path, **payload)
@@ -90,6 +101,8 @@ def make(name):
     st, rp = ref["states"], ref["reports"]
     cov = {
         "RootDrain>0": float((st["RootDrain"][1:] > 0).mean()),
+        "report files": len(ref["report_files"]) if CASES[name][0].get("report_opts") else None,
+        "tss": sorted(ref["tss_tables"]) if CASES[name][0].get("report_opts") else None,
         "runoff>0": float((rp["RootR"] > 0).mean()) if "RootR" in rp else None,
         "perc>0": float((rp["RootP"] > 0).mean()) if "RootP" in rp else None,
         "subperc>0": float((rp["SubP"] > 0).mean()) if "SubP" in rp else None,

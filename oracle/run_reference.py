@@ -155,6 +155,14 @@ def run_reference(cat, nsteps=None, dtype=np.float32, keep_table=False, quiet=Tr
         steps = sorted(t for t in per_t if t is not None)
         if len(steps) == nsteps:
             result["reports"][os.path.basename(name)] = np.stack([per_t[t] for t in steps]).astype(np.float32)
+    # everything self.report / pcr.report wrote, keyed like the files PCRaster would create
+    from sphy_b200.csf import stack_name
+    result["report_files"] = {}
+    for name, per_t in shim.G.reports.items():
+        base = os.path.basename(name)
+        for t, arr in per_t.items():
+            result["report_files"][base if t is None else stack_name(base, t)] = np.asarray(arr, np.float32)
+    result["tss_tables"] = {k: np.array([[t] + list(v) for t, v in rows], np.float64) for k, rows in result["tss"].items()}
     if keep_table:
         result["glac_table"] = tables
     return result

@@ -48,7 +48,7 @@ class WbForcing(C.Structure):
 
 class WbOut(C.Structure):
     _fields_ = [(k, P) for k in ("TotR", "RootRR", "RootDR", "RainR", "SnowR", "ETref", "ETact", "ActETact", "Infil",
-                                 "Rain", "RootPerc", "SubPerc", "wbal", "ETOpenWater")]
+                                 "Rain", "RootPerc", "SubPerc", "wbal", "ETOpenWater", "Precip")]
 
 
 class GlacTable(C.Structure):
@@ -102,6 +102,8 @@ SYMBOLS = {
     "sphy_gather_f32": (C.c_int, [P, P, P, P]),
     "sphy_scatter_f32": (C.c_int, [P, P, P, C.c_float, P]),
     "sphy_sample": (C.c_int, [P, P, P, C.c_int, P, P]),
+    "sphy_map_accumulate": (C.c_int, [P, P, P, C.c_float, C.c_int64, P]),
+    "sphy_map_divide": (C.c_int, [P, P, C.c_float, P, C.c_int64, P]),
     "sphy_map_unary": (C.c_int, [P, C.c_int, P, P, C.c_int64, P]),
     "sphy_set_ncells": (C.c_int, [P, C.c_int64]),
     "sphy_module_op": (C.c_int, [P, C.c_int, C.POINTER(SphyParam), C.c_int, C.POINTER(P), C.c_int, C.c_int64, C.c_float, C.c_int, P]),

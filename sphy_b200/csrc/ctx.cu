@@ -102,6 +102,37 @@ extern "C" int sphy_sample(sphy_ctx *ctx, const float *map, const int32_t *cells
     return SPHY_OK;
 }
 
+namespace {
+__global__ void k_accumulate(float *__restrict__ acc, const float *__restrict__ x, float divisor, int64_t n)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) acc[i] = acc[i] + (divisor != 0.0f ? x[i] / divisor : x[i]);
+}
+__global__ void k_divide(const float *__restrict__ in, float divisor, float *__restrict__ out, int64_t n)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] / divisor;
+}
+}  // namespace
+
+extern "C" int sphy_map_accumulate(sphy_ctx *ctx, float *acc, const float *x, float divisor, int64_t count, void *stream)
+{
+    if (!ctx || !acc || !x || count < 0) return SPHY_E_INVALID;
+    if (count == 0) return SPHY_OK;
+    k_accumulate<<<div_up(count, 256), 256, 0, (cudaStream_t)stream>>>(acc, x, divisor, count);
+    SPHY_LAUNCH_CHECK(ctx);
+    return SPHY_OK;
+}
+
+extern "C" int sphy_map_divide(sphy_ctx *ctx, const float *in, float divisor, float *out, int64_t count, void *stream)
+{
+    if (!ctx || !in || !out || count < 0 || divisor == 0.0f) return SPHY_E_INVALID;
+    if (count == 0) return SPHY_OK;
+    k_divide<<<div_up(count, 256), 256, 0, (cudaStream_t)stream>>>(in, divisor, out, count);
+    SPHY_LAUNCH_CHECK(ctx);
+    return SPHY_OK;
+}
+
 extern "C" size_t sphy_abi_sizeof(int which)
 {
     switch (which) {

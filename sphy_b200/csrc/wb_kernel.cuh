@@ -176,7 +176,7 @@ __device__ __forceinline__ void wb_cells(const WbArgs &a, int64_t i)
     V4 wtot;
     if (DIAG && a.s.waterbalanceTot) wtot = L::inrw(a.s.waterbalanceTot, i);
 
-    V4 o_totr, o_rootrr, o_rootdr, o_rainr, o_snowr, o_etref, o_etact, o_actet, o_infil, o_rain, o_rperc, o_sperc, o_wbal, o_etow;
+    V4 o_totr, o_rootrr, o_rootdr, o_rainr, o_snowr, o_etref, o_etact, o_actet, o_infil, o_rain, o_rperc, o_sperc, o_wbal, o_etow, o_prec;
 
 #pragma unroll
     for (int j = 0; j < W; ++j) {
@@ -340,6 +340,7 @@ __device__ __forceinline__ void wb_cells(const WbArgs &a, int64_t i)
             o_rperc.v[j] = rootperc;
             o_sperc.v[j] = ActSubPerc;
             o_etow.v[j] = ETref * p.kc_open_water;
+            o_prec.v[j] = Precip;
         }
     }
 #undef PV
@@ -377,6 +378,7 @@ __device__ __forceinline__ void wb_cells(const WbArgs &a, int64_t i)
         if (a.o.SubPerc) L::out(a.o.SubPerc, i, o_sperc);
         if (a.o.wbal) L::out(a.o.wbal, i, o_wbal);
         if (a.o.ETOpenWater) L::out(a.o.ETOpenWater, i, o_etow);
+        if (a.o.Precip) L::out(a.o.Precip, i, o_prec);
     }
 }
 

@@ -92,7 +92,7 @@ extern "C" int sphy_wb_step(sphy_ctx *ctx, const sphy_wb_params *p, const sphy_w
                           f->GlacR, s->RootWater, s->SubWater, s->CapRise, s->RootDrain, s->GwRecharge, s->Gw, s->BaseR,
                           s->H_gw, s->SubDrain, s->SnowStore, s->SnowWatStore, s->TotalSnowStore, s->waterbalanceTot,
                           o->TotR, o->RootRR, o->RootDR, o->RainR, o->SnowR, o->ETref, o->ETact, o->ActETact, o->Infil,
-                          o->Rain, o->RootPerc, o->SubPerc, o->wbal, o->ETOpenWater, p->sin_lat, p->cos_lat, p->tan_lat,
+                          o->Rain, o->RootPerc, o->SubPerc, o->wbal, o->ETOpenWater, o->Precip, p->sin_lat, p->cos_lat, p->tan_lat,
                           p->root_field.map, p->root_sat.map, p->root_dry.map, p->root_wilt.map, p->root_ksat.map,
                           p->root_drainvel.map, p->e_root.map, p->sub_field.map, p->sub_sat.map, p->sub_drainvel.map,
                           p->e_sub.map, p->caprise_max.map, p->kc.map, p->pmap.map, p->glac_frac.map,
@@ -123,7 +123,7 @@ extern "C" int sphy_wb_step(sphy_ctx *ctx, const sphy_wb_params *p, const sphy_w
         a.ra_table = ctx->ra_table;
     }
     const bool diag = s->waterbalanceTot || o->ETref || o->ETact || o->ActETact || o->Infil || o->Rain || o->RootPerc ||
-                      o->SubPerc || o->wbal || o->ETOpenWater;
+                      o->SubPerc || o->wbal || o->ETOpenWater || o->Precip;
     const bool usoil = !(p->root_field.map || p->root_sat.map || p->root_dry.map || p->root_wilt.map || p->root_ksat.map ||
                          p->e_root.map || p->sub_field.map || p->sub_sat.map || p->e_sub.map || p->caprise_max.map ||
                          p->kc.map || p->gw_sat.map || p->base_thresh.map || p->e_delta.map || p->e_alpha.map ||

@@ -111,14 +111,16 @@ def _table_col(rows, col):
 # ----------------------------------------------------------------------------------------------
 class SphyModel:
     def __init__(self, cfg, maps: MapSource, device="cuda:0", route_method="scan", diagnostics=False,
-                 collect_tss=True, cell_order="dfs", rank=0, world=1, share_from=None):
+                 collect_tss=True, cell_order="dfs", rank=0, world=1, share_from=None, reporting=False, write_outputs=False):
         if not torch.cuda.is_available():
             raise RuntimeError("SphyModel needs a CUDA device (B200); there is no CPU fallback")
         self.lib = _lib.load()
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
         self.maps = maps
-        self.diagnostics = diagnostics
+        self.diagnostics = diagnostics or reporting          # reported fluxes come from the diagnostic outputs of K1
+        self.enable_reporting = reporting
+        self.write_outputs = write_outputs
         self.collect_tss = collect_tss
         self.route_method = {"levels": _lib.ROUTE_LEVELS, "scan": _lib.ROUTE_SCAN}[route_method]
         self.cell_order_mode = {"rowmajor": _lib.ORDER_ROWMAJOR, "dfs": _lib.ORDER_DFS}[cell_order]
@@ -153,6 +155,9 @@ class SphyModel:
         self.startdate = datetime.datetime(ti("startyear"), ti("startmonth"), ti("startday"))
         self.enddate = datetime.datetime(ti("endyear"), ti("endmonth"), ti("endday"))
         self.ts1date = datetime.datetime(ti("startyear_timestep1"), ti("startmonth_timestep1"), ti("startday_timestep1"))
+        self.startYear, self.endYear = ti("startyear"), ti("endyear")                          # sphy.py:107-110
+        self.spinUpYears = ti("spinupyears")
+        self.simYears = self.endYear - self.startYear - self.spinUpYears + 1
         # -- clone, sphy.py:141-145
         clone = np.asarray(self._readmap(config.get("GENERAL", "mask")))
         self.nrows, self.ncols = clone.shape
@@ -513,7 +518,7 @@ class SphyModel:
         self.SnowR = self._full(0.0) if (comp_needed and self.SnowFLAG == 1) else None
         self.out = {}
         if self.diagnostics:
-            for k in ("ETref", "ETact", "ActETact", "Infil", "Rain", "RootPerc", "SubPerc", "wbal"):
+            for k in ("ETref", "ETact", "ActETact", "Infil", "Rain", "RootPerc", "SubPerc", "wbal", "Precip"):
                 self.out[k] = self._full(0.0)
         if self.ETOpenWaterFLAG == 1:
             self.out["ETOpenWater"] = self._full(0.0)                   # ET.ETpot(ETref, kcOpenWater), sphy.py:898
@@ -525,6 +530,12 @@ class SphyModel:
         self._station_cells = self._dev(loc_cells.astype(np.int32))
         self._station_buf = torch.empty(max(len(loc_cells), 1), dtype=torch.float32, device=self.device)
         self.tss = {"QallRAtot": []}
+        self.timestep = 0
+        self.report = None
+        rep_csv = os.path.join(self.inpath, self.config.get("REPORTING", "RepTab"))
+        if self.enable_reporting and os.path.exists(rep_csv):                                  # reporting.initial, sphy.py:708
+            from .reporting import Reporting
+            self.report = Reporting(self, rep_csv, write_files=self.write_outputs)
         self._forcing_dev = None
         self._forcing_host = None
         self._fdev = None
@@ -893,6 +904,9 @@ class SphyModel:
             self._ck(lib.sphy_sample(ctx, self.Q.data_ptr(), self._station_cells.data_ptr(), len(self.station_ids),
                                      self._station_buf.data_ptr(), st), "sphy_sample")
             self.tss["QallRAtot"].append(self._station_buf[: len(self.station_ids)].clone())
+        self.timestep += 1
+        if self.report is not None:
+            self.report.step()
         self.curdate = self.curdate + datetime.timedelta(days=1)
         return self.Q if self.Q is not None else self.TotR
 
@@ -966,6 +980,44 @@ class SphyModel:
         self._ck(self.lib.sphy_route_scan_finish(self._ctx, nc, dstp, self._kx, C.c_float(self._one_m_kx),
                                                  self._mg_recv.data_ptr(), self._mg_stride, self.rank, self.world, st),
                  "sphy_route_scan_finish")
+
+    def reportable(self):
+        """reporting.csv variable name -> callable giving the device map of the day (utilities/reporting.py call sites in
+        sphy.py:762-1097, groundwater.py:96-125, routing.py:73-101).  Names whose expression carries a (1-GlacFrac) or
+        (1-openWaterFrac) factor are only offered while that factor is exactly 1."""
+        o, plain = self.out, (self.GlacFLAG != 1 and self.openWaterFrac is None)
+        d = {}
+        if o:
+            d.update(TotPrec=lambda: o["Precip"], TotETref=lambda: o["ETref"], TotRain=lambda: o["Rain"],
+                     TotETactF=lambda: o["ActETact"], Infil=lambda: o["Infil"], wbal=lambda: o["wbal"], TotSubPF=lambda: o["SubPerc"])
+            if plain:
+                d.update(TotPrecF=lambda: o["Precip"], TotETrefF=lambda: o["ETref"], TotRainF=lambda: o["Rain"],
+                         TotETact=lambda: o["ETact"], TotRootPF=lambda: o["RootPerc"])
+        d["TotRF"] = lambda: self.TotR
+        if self.RootRR is not None:
+            d.update(TotRootRF=lambda: self.RootRR, TotRootDF=lambda: self.RootDR, TotRainRF=lambda: self.RainR)
+        if self.SnowR is not None:
+            d["TotSnowRF"] = lambda: self.SnowR
+        if self.GlacFLAG == 1:
+            d["TotGlacRF"] = lambda: self.GlacR
+        if self.GroundFLAG == 1:
+            d.update(TotBaseRF=lambda: self.BaseR, TotGwRechargeF=lambda: self.GwRecharge)
+            if self.openWaterFrac is None:
+                d["StorGroundW"] = lambda: self.Gw
+        else:
+            d["TotSubDF"] = lambda: self.SubDrain
+        if plain:
+            d["TotCapRF"] = lambda: self.CapRise
+        if self.openWaterFrac is None:
+            d.update(StorRootW=lambda: self.RootWater, StorSubW=lambda: self.SubWater)
+        if self.SnowFLAG == 1:
+            d.update(StorSnow=lambda: self.TotalSnowStore, StorSnowW=lambda: self.SnowWatStore)
+        if getattr(self, "QRAold", None) is not None:
+            d["QallRAtot"] = lambda: self.QRAold
+            for c in COMPONENTS:
+                if self.RA_FLAG.get(c):
+                    d[c + "RAtot"] = (lambda c=c: getattr(self, c + "RAold"))
+        return d
 
     def timesteps(self):
         """utilities/timecalc.py:32-36"""

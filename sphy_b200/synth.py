@@ -130,6 +130,7 @@ class Catchment:
     open_water_frac: np.ndarray | None = None
     report_daily: tuple = ()
     pws: bool = False                    # plant water stress (ET.ks, PWS_FLAG)
+    report_opts: dict = field(default_factory=dict)   # reporting.csv: name -> (map, avg, timeseries) option strings
 
     # ------------------------------------------------------------------------------------------
     @property
@@ -205,7 +206,8 @@ class Catchment:
             fh.write("name,map,avg,timeseries,filename,comment\n")
             for name, fname in _REPORT_VARS:
                 mode = "D" if name in self.report_daily else "NONE"
-                fh.write(f"{name},{mode},NONE,NONE,{fname},synthetic\n")
+                mp, av, ts = self.report_opts.get(name, (mode, "NONE", "NONE"))
+                fh.write(f"{name},{mp},{av},{ts},{fname},synthetic\n")
         if self.glac_table is not None:
             cols = ["U_ID", "MOD_ID", "GLAC_ID", "MOD_H", "GLAC_H", "DEBRIS", "FRAC_GLAC", "ICE_DEPTH"]
             with open(os.path.join(inputdir, "glaciers.csv"), "w") as fh:
@@ -432,7 +434,7 @@ def make_catchment(nrows, ncols, cellsize=250.0, seed=1, nsteps=365, snow=False,
                    reservoirs=False, lakes=False, ground=True, routing=True, infil_excess=0,
                    rout_components=False, outlets="single", start=datetime.date(2001, 1, 1),
                    n_res_simple=0, n_res_adv=0, n_lakes=0, open_water=False, params=None,
-                   report_daily=(), soil_classes=1, zrange=None, pws=False):
+                   report_daily=(), soil_classes=1, zrange=None, pws=False, report_opts=None):
     """Build one of the BASELINE.json synthetic configurations."""
     p = dict(DEFAULT_PARAMS)
     if params:
@@ -466,7 +468,7 @@ def make_catchment(nrows, ncols, cellsize=250.0, seed=1, nsteps=365, snow=False,
     cat = Catchment(nrows=nrows, ncols=ncols, cellsize=float(cellsize), seed=seed, dem=raw, ldd=ldd, slope=slope,
                     lat=lat, flags=flags, params=p, start=start, nsteps=nsteps, locations=locations,
                     soil_maps=soil_maps, rout_components=rout_components, infil_excess=infil_excess,
-                    report_daily=tuple(report_daily), pws=bool(pws))
+                    report_daily=tuple(report_daily), pws=bool(pws), report_opts=dict(report_opts or {}))
     if glacier:
         _add_glaciers(cat, rng)
     if reservoirs or lakes:

@@ -33,6 +33,8 @@ def catchment_from_golden(name):
     """Re-create the Catchment the golden run used and check the generator still produces the stored inputs."""
     z, meta = load_golden(name)
     kw = dict(meta["kwargs"])
+    if "report_opts" in kw:
+        kw["report_opts"] = {k: tuple(v) for k, v in kw["report_opts"].items()}
     if "start" in kw:
         kw["start"] = datetime.date(*kw["start"])
     cat = synth.make_catchment(nsteps=meta["nsteps"], **kw)

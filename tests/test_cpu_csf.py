@@ -1,0 +1,36 @@
+"""CPU: CSF map / TSS writers and PCRaster stack names (sphy_b200/csf.py) round-trip and follow the documented layout."""
+import os
+import struct
+
+import numpy as np
+
+from sphy_b200 import csf
+
+
+def test_stack_names_like_generateNameT():
+    assert csf.stack_name("forcings/prec", 1) == "forcings/prec0000.001"
+    assert csf.stack_name("prec", 365) == "prec0000.365"
+    assert csf.stack_name("prec", 1000) == "prec0001.000"
+    assert csf.stack_name("out/TotRM", 42) == "out/TotRM000.042"
+
+
+def test_map_round_trip(tmp_path):
+    rng = np.random.default_rng(0)
+    a = rng.normal(size=(7, 5)).astype(np.float32)
+    a[2, 3] = np.nan
+    for arr in (a, rng.integers(1, 10, (7, 5)).astype(np.uint8), rng.integers(-5, 500, (7, 5)).astype(np.int32), a > 0):
+        p = str(tmp_path / "m.map")
+        csf.write_map(p, arr, cellsize=250.0, x_ul=10.0, y_ul=99.0)
+        back, info = csf.read_map(p)
+        assert np.array_equal(back, arr, equal_nan=arr.dtype.kind == "f")
+        assert (info["nrows"], info["ncols"], info["cellsize"]) == (7, 5, 250.0)
+        assert os.path.getsize(p) == 256 + arr.size * (1 if arr.dtype in (np.uint8, np.bool_) else 4)
+        raw = open(p, "rb").read(256)
+        assert raw.startswith(b"RUU CROSS SYSTEM MAP FORMAT") and struct.unpack_from("<H", raw, 32)[0] == 2
+
+
+def test_tss_file(tmp_path):
+    p = str(tmp_path / "q.tss")
+    csf.write_tss(p, [1, 2], [(1, [0.5, 1.5]), (2, [0.25, 2.0])])
+    lines = open(p).read().splitlines()
+    assert lines[:5] == ["timeseries scalar", "3", "timestep", "1", "2"] and len(lines) == 7

@@ -170,3 +170,37 @@ def test_ensemble_members_share_one_context():
         assert close(got, port.QRAold[model.cell_order]).all()
     for model in reversed(members):
         model.close()
+
+
+def test_reporting_outputs_match_reference():
+    """utilities/reporting.py semantics (month / year / final maps, averages, long-term sums and averages, TSS at the
+    stations, PCRaster stack names) against what the reference's own reporting module wrote for the same run."""
+    import torch
+    cat, z, meta = catchment_from_golden("c1_reporting")
+    model = make_model(cat, reporting=True)
+    model.maps.forcing_fn = lambda t: golden_forcing(z, t)
+    for _ in range(meta["nsteps"]):
+        model.dynamic()
+    torch.cuda.synchronize()
+    want_files = {k[len("repfile/"):]: z[k] for k in z.files if k.startswith("repfile/")}
+    assert len(want_files) > 80
+    got = model.report.maps
+    assert set(want_files) == set(got), (sorted(set(want_files) - set(got))[:5], sorted(set(got) - set(want_files))[:5])
+    for k, want in want_files.items():
+        assert close(got[k], want).all(), f"reported map {k} differs"
+    for k in (f for f in z.files if f.startswith("tss/")):
+        want = z[k]
+        rows = model.report.tss[k[len("tss/"):]]
+        assert [r[0] for r in rows] == [int(t) for t in want[:, 0]], f"{k}: sampled time steps differ"
+        assert close(np.array([r[1] for r in rows]), want[:, 1:]).all(), k
+    # files on disk: CSF maps and .tss that read back
+    import tempfile
+    from sphy_b200 import csf
+    model.outpath = tempfile.mkdtemp(prefix="sphy_out_") + "/"
+    model.report.write_tss()
+    assert os.path.exists(os.path.join(model.outpath, "TotRDTS.tss"))
+    path = os.path.join(model.outpath, "x.map")
+    csf.write_map(path, got["TotR.map"], cellsize=model.cellsize)
+    back, info = csf.read_map(path)
+    assert np.array_equal(back, got["TotR.map"], equal_nan=True) and info["cellsize"] == model.cellsize
+    model.close()
