@@ -48,13 +48,19 @@ class DictMapSource(MapSource):
     def read(self, name):
         if name in self.maps:
             return self.maps[name]
+        # map stacks `forcings/<key>0000.001` (pcrm.generateNameT, sphy.py:756) are served by the forcing generator
+        base = os.path.basename(name)
+        if self.forcing_fn is not None and len(base) == 12 and base[8] == ".":
+            key = base[:8].rstrip("0123456789")
+            try:
+                t = int(base[len(key):8] + base[9:])
+            except ValueError:
+                raise FileNotFoundError(name) from None
+            if self._cache[0] != t:
+                self._cache = (t, self.forcing_fn(t))
+            if key in self._cache[1]:
+                return self._cache[1][key]
         raise FileNotFoundError(name)
-
-    def read_forcing(self, prefix_key, counter):
-        """prefix_key in prec/tavg/tmin/tmax; one generator call per day is cached."""
-        if self._cache[0] != counter:
-            self._cache = (counter, self.forcing_fn(counter))
-        return self._cache[1][prefix_key]
 
 
 class CatchmentSource(DictMapSource):
@@ -66,20 +72,24 @@ class CatchmentSource(DictMapSource):
 
 
 class DirMapSource(MapSource):
-    """A directory of `<name>.npy` rasters laid out like the reference's input directory."""
+    """The reference's input directory: PCRaster CSF maps (`dem.map`, `forcings/prec0000.001`, ...) read with
+    sphy_b200.csf, or `<name>.npy` rasters.  The cell size comes from the clone map's CSF header like in PCRaster."""
 
-    def __init__(self, root):
+    def __init__(self, root, cellsize=None):
         self.root = root
+        self.cellsize = cellsize
 
     def read(self, name):
-        path = os.path.join(self.root, name + ".npy")
-        if not os.path.exists(path):
-            raise FileNotFoundError(path)
-        return np.load(path)
-
-    def read_forcing(self, prefix_key, counter):
-        stem = {"prec": "prec", "tavg": "tavg", "tmin": "tmin", "tmax": "tmax"}[prefix_key]
-        return self.read(os.path.join("forcings", stem + name_t(counter)))
+        from . import csf
+        path = os.path.join(self.root, name)
+        if os.path.exists(path):
+            arr, info = csf.read_map(path)
+            if self.cellsize is None:
+                self.cellsize = info["cellsize"]
+            return arr
+        if os.path.exists(path + ".npy"):
+            return np.load(path + ".npy")
+        raise FileNotFoundError(path)
 
 
 def name_t(t):
@@ -392,12 +402,17 @@ class SphyModel:
         for k in ("precNetcdfFLAG", "tempNetcdfFLAG"):
             if cfg.has_option("CLIMATE", k) and cfg.getint("CLIMATE", k) == 1:
                 raise NotImplementedError("NetCDF forcing is outside the hot path (SURVEY.md section 2)")
+        self.Prec = cfg.get("CLIMATE", "Prec")                                                # map-stack prefixes, sphy.py:318,334
+        self.Tair = cfg.get("CLIMATE", "Tair")
         self.Pcorr = cfg.getfloat("CLIMATE", "Pcorr_fact")
         self.Tcorr = cfg.getfloat("CLIMATE", "Tcorr_fact")
         self.ETREF_FLAG = cfg.getint("ETREF", "ETREF_FLAG")
         if self.ETREF_FLAG == 0:
             self.Lat = rd("ETREF", "Lat")
             self.Gsc = cfg.getfloat("ETREF", "Gsc")
+            self.Tmin, self.Tmax = cfg.get("ETREF", "Tmin"), cfg.get("ETREF", "Tmax")
+        else:
+            self.ETref = cfg.get("ETREF", "ETref")
         if self.SnowFLAG == 1:                                                                 # snow.py:84-90
             for k in ("Tcrit", "SnowSC", "DDFS", "SnowF", "SnowCth"):
                 v = self._scalar_or_map("SNOW", k)
@@ -538,8 +553,9 @@ class SphyModel:
             self.report = Reporting(self, rep_csv, write_files=self.write_outputs)
         self._forcing_dev = None
         self._forcing_host = None
+        self._forcing_host_compact = False
         self._fdev = None
-        self._fraster = None
+        self._copy_stream = None
         self._staging = None
         self._prof = None
 
@@ -830,40 +846,78 @@ class SphyModel:
         layout readmap delivers); each step copies them host->device and compacts them into device cell order."""
         self._forcing_host = fn
         self._forcing_host_compact = compact      # True: fn already returns this rank's cells in device order
+        self._copy_stream = None
 
     def enable_profiling(self, on=True):
         """Record CUDA events around the water-balance and routing launches of every dynamic() call."""
         self._prof = {"wb": [], "route": []} if on else None
 
+    def _forcing_names(self, counter):
+        from . import csf
+        if self.ETREF_FLAG == 1:
+            pre = {"prec": self.Prec, "tavg": self.Tair, "etref": self.ETref}
+        else:
+            pre = {"prec": self.Prec, "tavg": self.Tair, "tmin": self.Tmin, "tmax": self.Tmax}
+        return {k: csf.stack_name(v, counter) for k, v in pre.items()}
+
     def _ingest(self, counter):
+        """The day's forcing as compact device maps.  Three sources: maps already resident in HBM
+        (set_device_forcing), pinned host rasters (set_host_forcing: asynchronous H2D on a copy stream, double
+        buffered so that day t+1 uploads while day t computes, then compaction into device cell order), or the
+        map source (readmap of `generateNameT(prefix, counter)` like sphy.py:755-809)."""
         if self._forcing_dev is not None:
             return self._forcing_dev(counter)
         keys = ("prec", "tavg", "etref") if self.ETREF_FLAG == 1 else ("prec", "tavg", "tmin", "tmax")
-        if getattr(self, "_forcing_host", None) is not None:
-            if getattr(self, "_fdev", None) is None:
-                self._fdev = {k: torch.empty(self.n, dtype=torch.float32, device=self.device) for k in keys}
-            host = self._forcing_host(counter)
-            if self.full_raster or getattr(self, "_forcing_host_compact", False):
-                for k in keys:
-                    self._fdev[k].copy_(host[k], non_blocking=True)
-                return self._fdev
-            if getattr(self, "_fraster", None) is None:
-                self._fraster = {k: torch.empty(self.nrows * self.ncols, dtype=torch.float32, device=self.device) for k in keys}
-            for k in keys:
-                self._fraster[k].copy_(host[k], non_blocking=True)
-                self._ck(self.lib.sphy_gather_f32(self._ctx, self._fraster[k].data_ptr(), self._fdev[k].data_ptr(), self._stream()),
-                         "sphy_gather_f32")
-            return self._fdev
-        if self._staging is None:
-            self._staging = {k: torch.empty(self.n, dtype=torch.float32).pin_memory() for k in keys}
         if self._fdev is None:
             self._fdev = {k: torch.empty(self.n, dtype=torch.float32, device=self.device) for k in keys}
+        if self._forcing_host is not None:
+            return self._ingest_host(counter, keys)
+        if self._staging is None:
+            self._staging = {k: torch.empty(self.n, dtype=torch.float32).pin_memory() for k in keys}
+        names = self._forcing_names(counter)
         for k in keys:
-            raster = self.maps.read_forcing(k, counter)
-            src = np.asarray(raster, np.float32).ravel()
+            src = np.asarray(self.maps.read(names[k]), np.float32).ravel()
             self._staging[k].numpy()[:] = src if self.full_raster else src[self.flat_active]
             self._fdev[k].copy_(self._staging[k], non_blocking=True)
         return self._fdev
+
+    def _ingest_host(self, counter, keys):
+        compact = self.full_raster or self._forcing_host_compact
+        size = self.n if compact else self.nrows * self.ncols
+        main = torch.cuda.current_stream(self.device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._hbuf = [{k: torch.empty(size, dtype=torch.float32, device=self.device) for k in keys} for _ in range(2)]
+            self._hready = [None, None]          # (counter, event) of the upload sitting in each buffer
+        cs = self._copy_stream
+
+        def upload(t, slot):
+            try:
+                host = self._forcing_host(t)
+            except (IndexError, KeyError, FileNotFoundError):
+                return
+            cs.wait_stream(main)                 # the buffer's previous contents have been consumed
+            with torch.cuda.stream(cs):
+                for k in keys:
+                    self._hbuf[slot][k].copy_(host[k], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+            self._hready[slot] = (t, ev)
+
+        slot = counter % 2
+        if self._hready[slot] is None or self._hready[slot][0] != counter:
+            upload(counter, slot)
+        main.wait_event(self._hready[slot][1])
+        buf = self._hbuf[slot]
+        if compact:
+            out = buf
+        else:
+            for k in keys:
+                self._ck(self.lib.sphy_gather_f32(self._ctx, buf[k].data_ptr(), self._fdev[k].data_ptr(), self._stream()),
+                         "sphy_gather_f32")
+            out = self._fdev
+        upload(counter + 1, 1 - slot)            # prefetch tomorrow while today computes
+        return out
 
     # -- dynamic(), sphy.py:719-1263 ------------------------------------------------------------------------
     def dynamic(self):

@@ -188,6 +188,18 @@ class Catchment:
         return {"prec": "forcings/prec" + tag, "tavg": "forcings/tavg" + tag, "tmin": "forcings/tmin" + tag,
                 "tmax": "forcings/tmax" + tag}
 
+    def write_csf_inputs(self, inputdir, nsteps=None):
+        """Write every static map and the daily forcing stacks as PCRaster CSF files under `inputdir`, laid out exactly
+        as the reference expects them (clone.map ... forcings/prec0000.001)."""
+        from . import csf
+        os.makedirs(os.path.join(inputdir, "forcings"), exist_ok=True)
+        for name, arr in self.static_maps().items():
+            csf.write_map(os.path.join(inputdir, name), np.ascontiguousarray(arr), cellsize=self.cellsize)
+        for t in range(1, (nsteps or self.nsteps) + 1):
+            f = self.forcing(t)
+            for key, name in self.forcing_map_names(t).items():
+                csf.write_map(os.path.join(inputdir, name), f[key], cellsize=self.cellsize)
+
     # ------------------------------------------------------------------------------------------
     def write_inputs(self, inputdir, outputdir=None):
         """Write sphy_config.cfg, reporting.csv and lookup tables under `inputdir`; return cfg path."""

@@ -204,3 +204,30 @@ def test_reporting_outputs_match_reference():
     back, info = csf.read_map(path)
     assert np.array_equal(back, got["TotR.map"], equal_nan=True) and info["cellsize"] == model.cellsize
     model.close()
+
+
+def test_csf_input_directory_matches_in_memory_source():
+    """Forcing ingest from PCRaster CSF map stacks on disk (DirMapSource: clone.map, forcings/prec0000.001 ...) gives
+    the same run as the in-memory source; the cell size comes from the clone map's header."""
+    import datetime
+    import tempfile
+    import torch
+    from sphy_b200 import synth
+    from sphy_b200.model import DirMapSource, SphyModel
+    cat = synth.make_catchment(40, 36, seed=12, nsteps=6, snow=True, start=datetime.date(2001, 4, 1), zrange=(1500.0, 5200.0),
+                               params=dict(SubWater=470.0, RootDepthFlat=150.0, Pscale=2.5, Toffset=9.0))
+    a = make_model(cat)
+    tmp = tempfile.mkdtemp(prefix="sphy_csf_")
+    cfg = cat.write_inputs(os.path.join(tmp, "in"), os.path.join(tmp, "out"))
+    cat.write_csf_inputs(os.path.join(tmp, "in"), 6)
+    b = SphyModel(cfg, DirMapSource(os.path.join(tmp, "in")), route_method="levels")
+    assert b.cellsize == cat.cellsize
+    b.initial()
+    for _ in range(6):
+        a.dynamic()
+        b.dynamic()
+    torch.cuda.synchronize()
+    for k in ("RootWater", "SubWater", "SnowStore", "Gw", "QRAold"):
+        assert torch.equal(getattr(a, k), getattr(b, k)), k
+    a.close()
+    b.close()
