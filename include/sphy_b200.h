@@ -267,7 +267,9 @@ typedef struct {
 } sphy_reslake;
 
 int sphy_route_reslake_step(sphy_ctx *ctx, const sphy_reslake *rl, const float *totr_mm, float *q_state,
-                            sphy_param kx, float one_minus_kx, int day_of_year, void *stream);
+                            sphy_param kx, float one_minus_kx, int day_of_year,
+                            int method /* SPHY_ROUTE_LEVELS (bit-exact) or SPHY_ROUTE_SCAN; structures listed by ascending cell */,
+                            void *stream);
 
 /* Open-water evaporation and precipitation on lakes/reservoirs (modules/advanced_routing.py:167-196, ETOpenWaterFLAG):
  * StorRES -= min(areatotal(ETOpenWater*cellarea*openWaterFrac, class)*0.001, StorRES); += areatotal(Precip*...)*0.001.

@@ -117,7 +117,7 @@ SYMBOLS = {
     "sphy_accuflux": (C.c_int, [P, P, P, P, C.c_int, P]),
     "sphy_upstream": (C.c_int, [P, P, P, P]),
     "sphy_reslake_openwater": (C.c_int, [P, C.POINTER(ResLake), C.POINTER(OpenWater), P]),
-    "sphy_route_reslake_step": (C.c_int, [P, C.POINTER(ResLake), P, P, SphyParam, C.c_float, C.c_int, P]),
+    "sphy_route_reslake_step": (C.c_int, [P, C.POINTER(ResLake), P, P, SphyParam, C.c_float, C.c_int, C.c_int, P]),
 }
 
 ABI_STRUCTS = (SphyParam, WbParams, WbState, WbForcing, WbOut, GlacTable, GlacOut, ResLake, OpenWater)

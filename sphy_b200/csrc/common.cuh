@@ -67,6 +67,9 @@ struct sphy_ctx {
     int32_t ra_table_cap = 0;
     float *tmp_n[4] = {nullptr, nullptr, nullptr, nullptr};
     bool qout_zeroed = false;
+    double *cut_work = nullptr;    // scan path with lakes/reservoirs: range sums of the cut cells
+    int cut_work_cap = 0;
+    int32_t *cut_ptr = nullptr;    // per-tile ranges of the cut-cell list
     std::string err;
 };
 
@@ -91,6 +94,15 @@ constexpr int ROUTE_WIDE_LEVEL = 2048;   // levels with at least this many cells
 #define SPHY_LAUNCH_CHECK(ctx) SPHY_CUDA(ctx, cudaGetLastError())
 
 static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+template <typename T>
+static inline int dev_alloc_once(sphy_ctx *ctx, T **p, size_t count)
+{
+    if (*p) return SPHY_OK;
+    if (count == 0) count = 1;
+    SPHY_CUDA(ctx, cudaMalloc((void **)p, count * sizeof(T)));
+    return SPHY_OK;
+}
 
 template <typename T>
 static inline int dev_alloc(sphy_ctx *ctx, T **p, size_t count)

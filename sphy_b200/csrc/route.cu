@@ -179,6 +179,8 @@ int route_levels_run(sphy_ctx *ctx, SweepArgs &a, cudaStream_t st)
 
 int route_scan_run(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm, float *const *q_state, sphy_param kx,
                    float one_m_kx, cudaStream_t st);   // route_scan.cu
+int route_scan_run_adv(sphy_ctx *ctx, float *material_m3day, float *q_state, sphy_param kx, float one_m_kx, const float *qfrac,
+                       const float *qout_dense, float *qday, int n_cut, const int32_t *cut_cell_dev, double *cut_work, cudaStream_t st);
 
 extern "C" int sphy_route_step(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm, float *const *q_state,
                                sphy_param kx, float one_minus_kx, int method, void *stream)
@@ -310,6 +312,7 @@ __global__ void k_rl_upstream_add(sphy_reslake rl, const int32_t *__restrict__ d
     if (first) m[r] = (float)s + m[r];
 }
 
+// qday is indexed by routing position (level sweep: pos != NULL) or by cell (scan path: pos == NULL)
 __global__ void k_rl_post(sphy_reslake rl, const int32_t *__restrict__ don_ptr, const int32_t *__restrict__ don_idx,
                           const int32_t *__restrict__ pos, const float *__restrict__ qday)
 {
@@ -317,7 +320,7 @@ __global__ void k_rl_post(sphy_reslake rl, const int32_t *__restrict__ don_ptr, 
     if (j >= rl.n_struct) return;
     const int32_t c = rl.cell[j];
     double s = 0.0;
-    for (int32_t q = don_ptr[c]; q < don_ptr[c + 1]; ++q) s += (double)qday[pos[don_idx[q]]];
+    for (int32_t q = don_ptr[c]; q < don_ptr[c + 1]; ++q) s += (double)qday[pos ? pos[don_idx[q]] : don_idx[q]];
     const float qin = (float)s;                                 // upstream(ldd, Q) at the structure cell
     rl.Qin[j] = qin;
     rl.StorRES[j] = (rl.StorRES[j] - rl.Qout[j]) + qin;         // advanced_routing.py:36
@@ -326,7 +329,7 @@ __global__ void k_rl_post(sphy_reslake rl, const int32_t *__restrict__ don_ptr, 
 }  // namespace
 
 extern "C" int sphy_route_reslake_step(sphy_ctx *ctx, const sphy_reslake *rl, const float *totr, float *q_state, sphy_param kx,
-                                       float one_minus_kx, int doy, void *stream)
+                                       float one_minus_kx, int doy, int method, void *stream)
 {
     if (!ctx || !rl || !totr || !q_state) return SPHY_E_INVALID;
     if (!ctx->ldd_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_route_reslake_step before sphy_ldd_build");
@@ -349,6 +352,23 @@ extern "C" int sphy_route_reslake_step(sphy_ctx *ctx, const sphy_reslake *rl, co
         k_rl_upstream_add<<<div_up(ns, 128), 128, 0, st>>>(*rl, ctx->down, ctx->don_ptr, ctx->don_idx, rl->qfrac, qout_dense, m);
     }
     SPHY_LAUNCH_CHECK(ctx);
+    if (method == SPHY_ROUTE_SCAN) {
+        // structures are listed by ascending cell index == ascending DFS rank, which the cut corrections rely on
+        if (ctx->order_mode != SPHY_ORDER_DFS) SPHY_FAIL(ctx, SPHY_E_STATE, "SPHY_ROUTE_SCAN needs SPHY_ORDER_DFS");
+        if (ctx->cut_work_cap < ns) {
+            int rc0 = dev_alloc(ctx, &ctx->cut_work, (size_t)(ns > 0 ? ns : 1));
+            if (rc0 != SPHY_OK) return rc0;
+            ctx->cut_work_cap = ns;
+        }
+        int rc1 = route_scan_run_adv(ctx, m, q_state, kx, one_minus_kx, rl->qfrac, qout_dense, ctx->qsorted, ns, rl->cell, ctx->cut_work, st);
+        if (rc1 != SPHY_OK) return rc1;
+        if (ns > 0) {
+            k_rl_post<<<div_up(ns, 128), 128, 0, st>>>(*rl, ctx->don_ptr, ctx->don_idx, nullptr, ctx->qsorted);
+            SPHY_LAUNCH_CHECK(ctx);
+        }
+        return SPHY_OK;
+    }
+    if (method != SPHY_ROUTE_LEVELS) SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_route_reslake_step: unknown method %d", method);
     SweepArgs a = {};
     a.ncomp = 1;
     a.mode = MODE_ADV;

@@ -43,6 +43,13 @@ struct ScanArgs {
     double *send;                         // [ncomp][stride]: range total, then range-local inclusive prefix at pub_e[j]
     const double *gathered;               // [world][ncomp][stride]
     int32_t stride, rank, world;
+    // lakes / reservoirs (advanced_routing.ROUT): material is already m3/day, cut cells take the structure outflow
+    int adv;
+    const float *frac;                    // dense QFRAC (0 at lake / reservoir cells)
+    const float *qout_dense;              // dense structure outflow, m3/day
+    float *qday;                          // dense blended Q, m3/day (what upstream(ldd, Q) reads at the structures)
+    const int32_t *cut_cell, *cut_ptr;    // cut cells (ascending) and their per-tile ranges
+    const double *cut_corr;               // float64 material placed at each cut cell (see route_scan_run_adv)
     sphy_param kx;
     float one_m_kx, cellarea;
     int64_t n;
@@ -50,6 +57,15 @@ struct ScanArgs {
 };
 
 __device__ __forceinline__ float to_m3s(float mm, float cellarea) { return ((mm * 0.001f) * cellarea) / 86400.0f; }
+
+// recession blend of one cell: routing.py:28, or advanced_routing.py:31-37 on a lake/reservoir network
+__device__ __forceinline__ float blend(const ScanArgs &a, int64_t cell, float f, float qold, float kx, float omk)
+{
+    if (!a.adv) return omk * f + kx * qold;
+    const float qd = __ldg(a.frac + cell) == 0.0f ? __ldg(a.qout_dense + cell) : omk * f + ((qold * 24.0f) * 3600.0f) * kx;
+    a.qday[cell] = qd;
+    return qd / 86400.0f;
+}
 
 // guarded 128-bit tile loads (4 consecutive cells per thread)
 __device__ __forceinline__ void load_sizes(const ScanArgs &a, int64_t base, int32_t sz[SCAN_ITEMS])
@@ -120,7 +136,16 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_main(const __grid_cons
             if (c > 0) load_comp(a, c, base, mm, q);
             double v[SCAN_ITEMS];
 #pragma unroll
-            for (int j = 0; j < SCAN_ITEMS; ++j) v[j] = base + j < a.n ? (double)to_m3s(mm[j], a.cellarea) : 0.0;
+            for (int j = 0; j < SCAN_ITEMS; ++j)
+                v[j] = base + j < a.n ? (a.adv ? (double)mm[j] : (double)to_m3s(mm[j], a.cellarea)) : 0.0;
+            if (a.adv) {                                       // float64 corrections at the cut cells of this tile
+                for (int32_t k = __ldg(a.cut_ptr + t); k < __ldg(a.cut_ptr + t + 1); ++k) {
+                    const int off = (int)(__ldg(a.cut_cell + k) - tbase) - lo;
+#pragma unroll
+                    for (int j = 0; j < SCAN_ITEMS; ++j)
+                        if (off == j) v[j] += a.cut_corr[k];
+                }
+            }
             double total;
             BlockScan(tmp).InclusiveSum(v, v, total);
 #pragma unroll
@@ -134,7 +159,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_main(const __grid_cons
                     const float f = (float)(Ls[(int)(e - tbase)] - before);
                     const float kx = a.kx.map ? kxv[j] : a.kx.value;
                     const float omk = a.kx.map ? 1.0f - kx : a.one_m_kx;
-                    q[j] = omk * f + kx * q[j];                // routing.py:28
+                    q[j] = blend(a, base + j, f, q[j], kx, omk);
                 }                                              // else: crossing cell, left to k_scan_cross
                 before = v[j];
             }
@@ -181,7 +206,7 @@ __global__ void __launch_bounds__(256) k_scan_cross(const __grid_constant__ Scan
                          a.park_end[(int64_t)c * (a.n_cross + a.n_pub) + k];
         const float f = (float)s;
         float *qs = a.qstate[c];
-        qs[r] = omk * f + kx * qs[r];                          // routing.py:28
+        qs[r] = blend(a, r, f, qs[r], kx, omk);
     }
 }
 
@@ -212,7 +237,7 @@ __global__ void k_scan_remote(const __grid_constant__ ScanArgs a)
         for (int u = a.rank + 1; u < q; ++u) s += a.gathered[((int64_t)u * a.ncomp + c) * a.stride];   // whole ranks in between
         s += a.gathered[((int64_t)q * a.ncomp + c) * a.stride + 1 + slot];        // start of rank q's range .. range end
         float *qs = a.qstate[c];
-        qs[r] = omk * (float)s + kx * qs[r];                                      // routing.py:28
+        qs[r] = blend(a, r, (float)s, qs[r], kx, omk);
     }
 }
 
@@ -400,6 +425,68 @@ int route_scan_run(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm, floa
     if (rc != SPHY_OK) return rc;
     int rc2 = scan_launch_local(ctx, a, st);
     if (rc2 != SPHY_OK) return rc2;
+    SPHY_LAUNCH_CHECK(ctx);
+    return SPHY_OK;
+}
+
+// ---- accufractionflux with QFRAC in {0,1} (lakes / reservoirs) on the scan path ---------------------------------
+// A cut cell passes nothing downstream, i.e. its whole upstream range must vanish from every range that contains it.
+// With R'(c) = (range sum of c) - sum of R'(c') over the cut cells c' strictly inside c's range, placing the material
+// -R'(c) at position c makes every plain range sum equal the accufractionflux (and the cut cell's own flux 0).
+namespace {
+
+// one CTA per cut cell: REAL8 sum of the material over its upstream range
+__global__ void __launch_bounds__(256) k_cut_range_sums(const int32_t *__restrict__ cut_cell, const int32_t *__restrict__ sub_size,
+                                                        const float *__restrict__ m, double *__restrict__ R)
+{
+    typedef cub::BlockReduce<double, 256> Reduce;
+    __shared__ typename Reduce::TempStorage tmp;
+    const int64_t c = cut_cell[blockIdx.x];
+    const int64_t e = c + sub_size[c];
+    double s = 0.0;
+    for (int64_t i = c + threadIdx.x; i < e; i += 256) s += (double)m[i];
+    s = Reduce(tmp).Sum(s);
+    if (threadIdx.x == 0) R[blockIdx.x] = s;
+}
+
+// cut cells are listed by ascending index, so nested cuts come after the cut that contains them: walk backwards
+__global__ void k_cut_corrections(const int32_t *__restrict__ cut_cell, const int32_t *__restrict__ sub_size, int n_cut, double *R)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    for (int j = n_cut - 1; j >= 0; --j) {
+        const int64_t c = cut_cell[j], e = c + sub_size[c];
+        double r = R[j];
+        for (int k = j + 1; k < n_cut && cut_cell[k] < e; ++k) r += R[k];      // R[k] already holds -R'(c_k)
+        R[j] = -r;                                                             // the material placed at the cut cell
+    }
+}
+
+}  // namespace
+
+int route_scan_run_adv(sphy_ctx *ctx, float *material_m3day, float *q_state, sphy_param kx, float one_m_kx, const float *qfrac,
+                       const float *qout_dense, float *qday, int n_cut, const int32_t *cut_cell_dev, double *cut_work, cudaStream_t st)
+{
+    if (ctx->partitioned) SPHY_FAIL(ctx, SPHY_E_STATE, "lake/reservoir routing is not available on a partitioned context");
+    ScanArgs a;
+    const float *mm[1] = {material_m3day};
+    float *qq[1] = {q_state};
+    int rc = scan_prepare(ctx, 1, mm, qq, kx, one_m_kx, st, a);
+    if (rc != SPHY_OK) return rc;
+    if ((rc = dev_alloc_once(ctx, &ctx->cut_ptr, (size_t)ctx->n_tiles + 1)) != SPHY_OK) return rc;
+    if (n_cut > 0) {
+        k_cut_range_sums<<<n_cut, 256, 0, st>>>(cut_cell_dev, ctx->sub_size_loc, material_m3day, cut_work);
+        k_cut_corrections<<<1, 32, 0, st>>>(cut_cell_dev, ctx->sub_size_loc, n_cut, cut_work);
+    }
+    k_tile_lower_bound<<<div_up(ctx->n_tiles + 1, 256), 256, 0, st>>>(cut_cell_dev, n_cut, ctx->n_tiles, ctx->cut_ptr);
+    a.cut_cell = cut_cell_dev;
+    a.cut_ptr = ctx->cut_ptr;
+    a.cut_corr = cut_work;
+    a.adv = 1;
+    a.frac = qfrac;
+    a.qout_dense = qout_dense;
+    a.qday = qday;
+    rc = scan_launch_local(ctx, a, st);
+    if (rc != SPHY_OK) return rc;
     SPHY_LAUNCH_CHECK(ctx);
     return SPHY_OK;
 }

@@ -997,7 +997,7 @@ class SphyModel:
     def _route_reslake(self, TotR):
         """advanced_routing.dynamic (modules/advanced_routing.py:134-217) incl. lakes.QLake / reservoirs.QRes."""
         self._ck(self.lib.sphy_route_reslake_step(self._ctx, C.byref(self._rl_struct), TotR.data_ptr(), self.QRAold.data_ptr(),
-                                                  self._kx, C.c_float(self._one_m_kx), self._doy, self._stream()),
+                                                  self._kx, C.c_float(self._one_m_kx), self._doy, self.route_method, self._stream()),
                  "sphy_route_reslake_step")
         if self.ETOpenWaterFLAG == 1:                                                          # advanced_routing.py:167-196
             ow = _lib.OpenWater(self._ow_ptr.data_ptr(), self._ow_cell.data_ptr(), self._ow_frac_dev.data_ptr(),
