@@ -30,6 +30,14 @@ ALG_BYTES_WB = 92                      # SURVEY 8d formula, n_forcing 4 + n_para
 ALG_BYTES_ROUTE = 24                   # per routed component
 
 
+def k1_traffic_per_cell():
+    """dram__bytes_read.sum + dram__bytes_write.sum per cell of the K1 launch, from the committed ncu --set full capture."""
+    try:
+        return float(json.load(open(os.path.join(ROOT, "profiles", "r1_k1_traffic.json")))["dram_bytes_per_cell"])
+    except Exception:
+        return None
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -268,8 +276,10 @@ def main():
                    if ALG_BYTES_WB * n > 4 * 126e6 else "working set fits L2: throughput only, no roofline claim",
                    "forcing_ring_days": args.ring, "setup_s": round(setup_s, 1)},
         "roofline": {"kernel": "k_wb_step (fused vertical water balance)", "bound": "hbm", "achieved": ach, "peak": peak,
-                     "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                     "alg_bytes_per_cell": ALG_BYTES_WB, "kernel_ms": wb_ms, "route_ms": rt_ms},
+                     "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak,
+                     "traffic": (k1_traffic_per_cell() * n if k1_traffic_per_cell() else None),
+                     "traffic_note": "bytes per launch = ncu dram bytes per cell (profiles/r1_k1_traffic.json, 36e6-cell capture) x cells",
+                     "alg_bytes_per_cell": ALG_BYTES_WB, "alg_bytes_per_launch": ALG_BYTES_WB * n, "kernel_ms": wb_ms, "route_ms": rt_ms},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_val, "unit": "Mcell-timesteps/s", "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": d2h // e2e_steps,
                 "steps": e2e_steps},
