@@ -67,6 +67,7 @@ struct sphy_ctx {
     int32_t ra_table_cap = 0;
     float *tmp_n[4] = {nullptr, nullptr, nullptr, nullptr};
     bool qout_zeroed = false;
+    bool sweep_attr_set = false;
     double *cut_work = nullptr;    // scan path with lakes/reservoirs: range sums of the cut cells
     int cut_work_cap = 0;
     int32_t *cut_ptr = nullptr;    // per-tile ranges of the cut-cell list

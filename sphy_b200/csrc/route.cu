@@ -41,29 +41,36 @@ __device__ __forceinline__ float material(const SweepArgs &a, int c, int32_t i)
     return q;
 }
 
-// finish a cell: fraction cut, store flux, recession blend
-__device__ __forceinline__ float finish(const SweepArgs &a, int c, int64_t k, int32_t i, double tot)
+// what `finish` needs from global memory for one cell (component 0 can have it prefetched a level ahead)
+struct CellIn {
+    float fr, kx, qold, qout;
+};
+
+__device__ __forceinline__ CellIn load_cell_in(const SweepArgs &a, int c, int32_t i)
 {
-    float f;
-    float fr = 1.0f;
-    if (a.frac) {
-        fr = __ldg(a.frac + i);
-        f = (float)((double)fr * tot);
-    } else {
-        f = (float)tot;
-    }
+    CellIn ci;
+    ci.fr = a.frac ? __ldg(a.frac + i) : 1.0f;
+    ci.kx = a.kx.map ? __ldg(a.kx.map + i) : a.kx.value;
+    ci.qold = a.mode == MODE_PLAIN ? 0.0f : a.qstate[c][i];
+    ci.qout = (a.mode == MODE_ADV && ci.fr == 0.0f) ? __ldg(a.qout_dense + i) : 0.0f;
+    return ci;
+}
+
+// finish a cell: fraction cut, store flux, recession blend
+__device__ __forceinline__ float finish(const SweepArgs &a, int c, int64_t k, int32_t i, double tot, const CellIn &ci)
+{
+    const float f = a.frac ? (float)((double)ci.fr * tot) : (float)tot;
     a.acc[(int64_t)c * a.n + k] = f;
     if (a.mode == MODE_PLAIN) {
         if (a.flux_out[c]) a.flux_out[c][i] = f;
     } else {
-        const float kx = a.kx.map ? __ldg(a.kx.map + i) : a.kx.value;
-        const float omk = a.kx.map ? 1.0f - kx : a.one_m_kx;
+        const float omk = a.kx.map ? 1.0f - ci.kx : a.one_m_kx;
         float *qs = a.qstate[c];
         if (a.mode == MODE_ROUT) {
-            qs[i] = omk * f + kx * qs[i];                                      // routing.py:28
+            qs[i] = omk * f + ci.kx * ci.qold;                                 // routing.py:28
         } else {
             // advanced_routing.py:31-37: Q = QFRAC==0 ? Qout : (1-kx)*Q + (Qold*24*3600)*kx ; Q/86400 is the state
-            float qd = fr == 0.0f ? __ldg(a.qout_dense + i) : omk * f + ((qs[i] * 24.0f) * 3600.0f) * kx;
+            const float qd = ci.fr == 0.0f ? ci.qout : omk * f + ((ci.qold * 24.0f) * 3600.0f) * ci.kx;
             a.qday[k] = qd;
             qs[i] = qd / 86400.0f;
         }
@@ -82,49 +89,107 @@ __global__ void __launch_bounds__(256) k_sweep_wide(const __grid_constant__ Swee
         double s = (double)material(a, c, i);
         const float *acc = a.acc + (int64_t)c * a.n;
         for (int32_t q = b; q < e; ++q) s += (double)acc[__ldg(a.dpos + q)];
-        finish(a, c, k, i, s);
+        finish(a, c, k, i, s, load_cell_in(a, c, i));
     }
 }
 
 constexpr int NARROW_THREADS = 1024;
 constexpr int FRONT_CAP = ROUTE_WIDE_LEVEL;   // max cells of a narrow level
 
-// a run of narrow levels [l0, l0+nl) walked by one CTA
+constexpr int SMALL_LEVEL = NARROW_THREADS / 8;   // levels up to 128 cells: 8 donor lanes per cell, software-pipelined
+
+// A run of narrow levels [l0, l0+nl) walked by ONE CTA (the latency chain of the sweep: ~10^4 dependent levels).
+//  * small levels (<= 128 cells, the long tail): 8 lanes per cell fetch the donors in parallel and reduce with warp
+//    shuffles.  Everything that does not depend on the previous level -- the cell index, its donor position, the
+//    material, the old discharge, donors from older levels -- is prefetched one level ahead, so the dependent part
+//    of a level is: shared-memory read of the frontier -> 3 shuffles -> REAL8 add -> store -> __syncthreads.
+//  * medium levels (129 .. 2047 cells): one thread per cell, sequential donor loop.
+// The fluxes of the previous level (the frontier) are staged in shared memory; older ones come from global memory.
 __global__ void __launch_bounds__(NARROW_THREADS) k_sweep_narrow(const __grid_constant__ SweepArgs a, int32_t l0, int32_t nl)
 {
     extern __shared__ float front[];     // [2][ncomp][FRONT_CAP] fluxes of the previous / current level
     const int tid = threadIdx.x;
     const int sub = tid & 7;             // donor lane
-    const int slot = tid >> 3;           // cell slot (128 cells per pass)
+    const int slot = tid >> 3;           // cell slot (128 cells)
     const int ncomp = a.ncomp;
+    const int32_t lend = l0 + nl;
     int cur = 0;
     int32_t prev_begin = -1, prev_end = -1;
-    for (int32_t l = l0; l < l0 + nl; ++l) {
-        const int32_t kb = __ldg(a.level_ptr + l), ke = __ldg(a.level_ptr + l + 1);
+    int32_t kb = __ldg(a.level_ptr + l0), ke = __ldg(a.level_ptr + l0 + 1);
+    // pipeline registers: the small level about to be processed
+    bool pf = false;
+    int32_t p_i = 0, p_dp = -1;
+    float p_old = 0.0f, p_mat = 0.0f;
+    bool p_old_valid = false;
+    CellIn p_ci = {1.0f, 0.0f, 0.0f, 0.0f};
+    for (int32_t l = l0; l < lend; ++l) {
+        const int32_t nlev = ke - kb;
+        const int32_t nkb = ke, nke = (l + 1 < lend) ? __ldg(a.level_ptr + l + 2) : ke;    // the next level of this run
         float *fcur = front + (size_t)cur * ncomp * FRONT_CAP;
         const float *fprev = front + (size_t)(cur ^ 1) * ncomp * FRONT_CAP;
-        for (int32_t base = kb; base < ke; base += NARROW_THREADS / 8) {
-            const int32_t k = base + slot;
-            const bool live = k < ke;
-            int32_t i = 0, dp = -1;
+        // ---- stage 1: this level's independent inputs (prefetched during the previous level when possible) ---------
+        int32_t i = p_i, dp = p_dp;
+        float old0 = p_old, mat0 = p_mat;
+        bool old0_valid = p_old_valid;
+        CellIn ci0 = p_ci;
+        const bool small = nlev <= SMALL_LEVEL;
+        const bool live = small && slot < nlev;
+        if (small && !pf) {
+            i = 0; dp = -1; old0_valid = false;
             if (live) {
+                const int32_t k = kb + slot;
                 i = __ldg(a.order + k);
                 const int32_t b = __ldg(a.dpos_ptr + k), e = __ldg(a.dpos_ptr + k + 1);
                 if (b + sub < e) dp = __ldg(a.dpos + b + sub);
+                if (sub == 0) { mat0 = material(a, 0, i); ci0 = load_cell_in(a, 0, i); }
             }
+        }
+        // ---- stage 2: issue the next level's independent loads now; they complete while this level computes --------
+        pf = false;
+        if (l + 1 < lend && nke - nkb <= SMALL_LEVEL) {
+            pf = true;
+            p_i = 0; p_dp = -1; p_old_valid = false;
+            if (slot < nke - nkb) {
+                const int32_t k2 = nkb + slot;
+                p_i = __ldg(a.order + k2);
+                const int32_t b2 = __ldg(a.dpos_ptr + k2), e2 = __ldg(a.dpos_ptr + k2 + 1);
+                if (b2 + sub < e2) {
+                    p_dp = __ldg(a.dpos + b2 + sub);
+                    if (p_dp < kb) { p_old = a.acc[p_dp]; p_old_valid = true; }   // donor older than this level: final already
+                }
+                if (sub == 0) { p_mat = material(a, 0, p_i); p_ci = load_cell_in(a, 0, p_i); }
+            }
+        }
+        // ---- stage 3: the dependent part ----------------------------------------------------------------------------
+        if (small) {
             for (int c = 0; c < ncomp; ++c) {
                 double s = 0.0;
                 if (dp >= 0) {
                     if (dp >= prev_begin && dp < prev_end) s = (double)fprev[c * FRONT_CAP + (dp - prev_begin)];
+                    else if (c == 0 && old0_valid) s = (double)old0;
                     else s = (double)a.acc[(int64_t)c * a.n + dp];
                 }
-                // warp-shuffle reduction over the 8 donor lanes of the cell
-                s += __shfl_xor_sync(0xffffffffu, s, 4, 8);
+                s += __shfl_xor_sync(0xffffffffu, s, 4, 8);       // warp-shuffle reduction over the 8 donor lanes
                 s += __shfl_xor_sync(0xffffffffu, s, 2, 8);
                 s += __shfl_xor_sync(0xffffffffu, s, 1, 8);
                 if (live && sub == 0) {
-                    s += (double)material(a, c, i);
-                    float f = finish(a, c, k, i, s);
+                    s += (double)(c == 0 ? mat0 : material(a, c, i));
+                    const float f = finish(a, c, kb + slot, i, s, c == 0 ? ci0 : load_cell_in(a, c, i));
+                    fcur[c * FRONT_CAP + slot] = f;
+                }
+            }
+        } else {
+            for (int32_t k = kb + tid; k < ke; k += NARROW_THREADS) {
+                const int32_t ic = __ldg(a.order + k);
+                const int32_t b = __ldg(a.dpos_ptr + k), e = __ldg(a.dpos_ptr + k + 1);
+                for (int c = 0; c < ncomp; ++c) {
+                    double s = (double)material(a, c, ic);
+                    for (int32_t q = b; q < e; ++q) {
+                        const int32_t d = __ldg(a.dpos + q);
+                        s += (d >= prev_begin && d < prev_end) ? (double)fprev[c * FRONT_CAP + (d - prev_begin)]
+                                                               : (double)a.acc[(int64_t)c * a.n + d];
+                    }
+                    const float f = finish(a, c, k, ic, s, load_cell_in(a, c, ic));
                     fcur[c * FRONT_CAP + (k - kb)] = f;
                 }
             }
@@ -132,6 +197,8 @@ __global__ void __launch_bounds__(NARROW_THREADS) k_sweep_narrow(const __grid_co
         prev_begin = kb;
         prev_end = ke;
         cur ^= 1;
+        kb = nkb;
+        ke = nke;
         __syncthreads();
     }
 }
@@ -159,11 +226,10 @@ int route_levels_run(sphy_ctx *ctx, SweepArgs &a, cudaStream_t st)
     a.n = ctx->n;
     a.cellarea = ctx->cellarea;
     const size_t smem = (size_t)2 * a.ncomp * FRONT_CAP * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->sweep_attr_set) {        // per context (= per device): opt in to the large dynamic shared memory once
         SPHY_CUDA(ctx, cudaFuncSetAttribute(k_sweep_narrow, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             2 * ROUTE_MAX_COMP * FRONT_CAP * (int)sizeof(float)));
-        attr_set = true;
+        ctx->sweep_attr_set = true;
     }
     for (const RoutePlanSeg &seg : ctx->plan) {
         if (seg.n_levels == 1 && ctx->h_level_ptr[seg.first_level + 1] - ctx->h_level_ptr[seg.first_level] >= FRONT_CAP) {

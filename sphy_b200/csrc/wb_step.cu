@@ -1,7 +1,5 @@
 // wb_step.cu -- K1 host side: day scalars, the per-day Ra table, init-time derived maps, launch.
 // Device code lives in wb_kernel.cuh (instantiated in wb_inst_*.cu).
-#include <stdlib.h>
-
 #include "wb_kernel.cuh"
 
 using namespace wb;
@@ -128,8 +126,7 @@ extern "C" int sphy_wb_step(sphy_ctx *ctx, const sphy_wb_params *p, const sphy_w
                          p->e_root.map || p->sub_field.map || p->sub_sat.map || p->e_sub.map || p->caprise_max.map ||
                          p->kc.map || p->gw_sat.map || p->base_thresh.map || p->e_delta.map || p->e_alpha.map ||
                          p->h_den.map || p->seepage.map);
-    static const int cpt_env = getenv("SPHY_WB_CPT") ? atoi(getenv("SPHY_WB_CPT")) : 0;
-    const int cpt = cpt_env == 2 ? 2 : 4;                       // cells per thread (128-bit vs 64-bit accesses)
+    const int cpt = 4;                                          // cells per thread (128-bit accesses; see wb_kernel.cuh)
     wb_kernel_t kern = snow ? (ground ? wb_pick_11(infil, ra, diag, usoil, cpt) : wb_pick_10(infil, ra, diag, usoil, cpt))
                             : (ground ? wb_pick_01(infil, ra, diag, usoil, cpt) : wb_pick_00(infil, ra, diag, usoil, cpt));
     if (!kern) SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_wb_step: no kernel for this switch combination");
