@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_main(const __grid_cons
 {
     typedef cub::BlockScan<double, SCAN_THREADS, cub::BLOCK_SCAN_WARP_SCANS> BlockScan;
     __shared__ typename BlockScan::TempStorage tmp;
-    __shared__ double Ls2[2][SCAN_TILE];   // double buffered: no barrier is needed between consecutive tiles
+    __shared__ double Ls[SCAN_TILE];
     const int lo = threadIdx.x * SCAN_ITEMS;
     int32_t t = blockIdx.x;
     if (t >= a.ntiles) return;
@@ -110,11 +110,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_main(const __grid_cons
     float mm_n[SCAN_ITEMS], q_n[SCAN_ITEMS];
     load_sizes(a, (int64_t)t * SCAN_TILE + lo, sz_n);
     load_comp(a, 0, (int64_t)t * SCAN_TILE + lo, mm_n, q_n);
-    int32_t cb_n = __ldg(a.cross_ptr + t), ce_n = __ldg(a.cross_ptr + t + 1);
-    int32_t eb_n = __ldg(a.end_ptr + t), ee_n = __ldg(a.end_ptr + t + 1);
-    int buf = 0;
-    for (; t < a.ntiles; t += gridDim.x, buf ^= 1) {
-        double *Ls = Ls2[buf];
+    for (; t < a.ntiles; t += gridDim.x) {
         const int64_t tbase = (int64_t)t * SCAN_TILE;
         const int64_t base = tbase + lo;
         const int64_t tend = min(tbase + (int64_t)SCAN_TILE, a.n);   // one past the last cell of the tile
@@ -123,19 +119,18 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_main(const __grid_cons
         float q[SCAN_ITEMS], mm[SCAN_ITEMS];
 #pragma unroll
         for (int j = 0; j < SCAN_ITEMS; ++j) { sz[j] = sz_n[j]; mm[j] = mm_n[j]; q[j] = q_n[j]; }
-        const int32_t cb = cb_n, ce = ce_n, eb = eb_n, ee = ee_n;
         const int32_t tn = t + gridDim.x;
         if (tn < a.ntiles) {                                   // prefetch the next tile of this CTA
             load_sizes(a, (int64_t)tn * SCAN_TILE + lo, sz_n);
             load_comp(a, 0, (int64_t)tn * SCAN_TILE + lo, mm_n, q_n);
-            cb_n = __ldg(a.cross_ptr + tn); ce_n = __ldg(a.cross_ptr + tn + 1);
-            eb_n = __ldg(a.end_ptr + tn); ee_n = __ldg(a.end_ptr + tn + 1);
         }
         float kxv[SCAN_ITEMS];
         if (a.kx.map) {
 #pragma unroll
             for (int j = 0; j < SCAN_ITEMS; ++j) kxv[j] = base + j < a.n ? __ldg(a.kx.map + base + j) : 0.0f;
         }
+        const int32_t cb = __ldg(a.cross_ptr + t), ce = __ldg(a.cross_ptr + t + 1);
+        const int32_t eb = __ldg(a.end_ptr + t), ee = __ldg(a.end_ptr + t + 1);
         for (int c = 0; c < a.ncomp; ++c) {
             float *qs = a.qstate[c];
             if (c > 0) load_comp(a, c, base, mm, q);
@@ -184,7 +179,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_main(const __grid_cons
             for (int32_t j = eb + threadIdx.x; j < ee; j += SCAN_THREADS)
                 pe[__ldg(a.end_k + j)] = Ls[(int)(__ldg(a.end_e + j) - tbase)];
             if (threadIdx.x == 0) a.tile_tot[(int64_t)c * (a.ntiles + 1) + t] = total;
-            if (c + 1 < a.ncomp) __syncthreads();              // the same buffer is reused by the next component
+            __syncthreads();
         }
     }
 }
