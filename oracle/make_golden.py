@@ -42,6 +42,10 @@ CASES = {
     "c1_noground": (dict(nrows=12, ncols=10, seed=13, ground=False, params=WET), 40),
     # three soil classes: distributed soil parameters
     "c1_soilcls": (dict(nrows=12, ncols=10, seed=14, soil_classes=3, params=WETK), 40),
+    # ETREF_FLAG = 1: ETref read from a map series instead of Hargreaves
+    "c1_etref": (dict(nrows=12, ncols=10, seed=17, etref_input=True, params=WET), 40),
+    # a non-rectangular catchment: MV outside the clone mask, cells at the rim drain out of the map
+    "c1_masked": (dict(nrows=14, ncols=12, seed=18, mask="disk", rout_components=True, params=WET), 40),
     # plant water stress (ET.ks) instead of the wilting-point reduction
     "c1_pws": (dict(nrows=12, ncols=10, seed=15, pws=True, params=WET), 40),
     # reporting.csv driven outputs (utilities/reporting.py): month / year / final maps, averages, long-term sums, TSS
@@ -79,7 +83,8 @@ def build_case(name):
 def make(name):
     cat, nsteps = build_case(name)
     ref = run_reference(cat, nsteps)
-    forcing = {k: np.stack([cat.forcing(t)[k] for t in range(1, nsteps + 1)]) for k in ("prec", "tavg", "tmin", "tmax")}
+    fkeys = ("prec", "tavg", "tmin", "tmax") + (("etref",) if cat.etref_input else ())
+    forcing = {k: np.stack([cat.forcing(t)[k] for t in range(1, nsteps + 1)]) for k in fkeys}
     payload = {"meta": np.array(json.dumps(dict(case=name, nsteps=nsteps, kwargs=CASES[name][0])))}
     for k, v in cat.static_maps().items():
         payload["map/" + k] = v

@@ -75,7 +75,16 @@ def run_reference(cat, nsteps=None, dtype=np.float32, keep_table=False, quiet=Tr
     inp = os.path.join(tmp, "in")
     out = os.path.join(tmp, "out")
     cfg = cat.write_inputs(inp, out)
+    mask = getattr(cat, "mask", None)
     for name, arr in cat.static_maps().items():
+        arr = np.asarray(arr)
+        if mask is not None and name != "clone.map":          # PCRaster maps carry MV outside the catchment
+            if arr.dtype == np.float32:
+                arr = np.where(mask, arr, np.float32(np.nan)).astype(np.float32)
+            elif arr.dtype == np.uint8:
+                arr = np.where(mask, arr, 255).astype(np.uint8)
+            elif arr.dtype == np.int32:
+                arr = np.where(mask, arr, -2147483648).astype(np.int32)
         shim.register_map(os.path.join(inp, name), arr)
     cache = {}
 

@@ -121,7 +121,8 @@ def _table_col(rows, col):
 # ----------------------------------------------------------------------------------------------
 class SphyModel:
     def __init__(self, cfg, maps: MapSource, device="cuda:0", route_method="scan", diagnostics=False,
-                 collect_tss=True, cell_order="dfs", rank=0, world=1, share_from=None, reporting=False, write_outputs=False):
+                 collect_tss=True, cell_order="dfs", rank=0, world=1, share_from=None, reporting=False, write_outputs=False,
+                 ra_mode="auto"):
         if not torch.cuda.is_available():
             raise RuntimeError("SphyModel needs a CUDA device (B200); there is no CPU fallback")
         self.lib = _lib.load()
@@ -136,6 +137,7 @@ class SphyModel:
         self.cell_order_mode = {"rowmajor": _lib.ORDER_ROWMAJOR, "dfs": _lib.ORDER_DFS}[cell_order]
         if self.route_method == _lib.ROUTE_SCAN and self.cell_order_mode != _lib.ORDER_DFS:
             raise ValueError("route_method='scan' needs cell_order='dfs'")
+        self.ra_mode = ra_mode           # auto | table (latitude classes) | cell (per-cell sin/cos/tan maps)
         self.rank, self.world = int(rank), int(world)
         if self.world > 1 and (self.route_method != _lib.ROUTE_SCAN):
             raise ValueError("multi-GPU partitioning needs route_method='scan'")
@@ -745,7 +747,9 @@ class SphyModel:
                 inv, uniq = pd.factorize(np.ascontiguousarray(self.Lat), sort=False)
             except ImportError:
                 uniq, inv = np.unique(self.Lat, return_inverse=True)
-            if len(uniq) <= 65536:
+            if self.ra_mode == "table" and len(uniq) > 65536:
+                raise ValueError("ra_mode='table' needs at most 65536 distinct latitudes")
+            if (len(uniq) <= 65536 and self.ra_mode != "cell"):
                 P.ra_mode = _lib.RA_TABLE
                 self._lat_class = self._dev(inv.astype(np.uint16))
                 self._lat_unique = self._dev(uniq.astype(np.float32))

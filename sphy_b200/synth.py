@@ -131,6 +131,8 @@ class Catchment:
     report_daily: tuple = ()
     pws: bool = False                    # plant water stress (ET.ks, PWS_FLAG)
     report_opts: dict = field(default_factory=dict)   # reporting.csv: name -> (map, avg, timeseries) option strings
+    etref_input: bool = False            # ETREF_FLAG = 1: ETref map series instead of Hargreaves (sphy.py:814)
+    mask: np.ndarray | None = None       # clone mask (True = inside the catchment); None = the whole rectangle
 
     # ------------------------------------------------------------------------------------------
     @property
@@ -155,14 +157,18 @@ class Catchment:
         else:
             rng.gamma(0.8, 12.0)
             prec = np.zeros((self.nrows, self.ncols), np.float32)
-        return dict(prec=prec, tavg=tavg, tmin=tmin, tmax=tmax)
+        out = dict(prec=prec, tavg=tavg, tmin=tmin, tmax=tmax)
+        if self.etref_input:
+            out["etref"] = np.clip(np.float32(0.12) * (tavg + np.float32(12.0)), 0, None).astype(np.float32)
+        return out
 
     # ------------------------------------------------------------------------------------------
     def static_maps(self):
         """name (relative to inputdir) -> ndarray; dtype decides the PCRaster value scale
         (bool -> boolean, uint8 -> ldd, int32 -> nominal, float32 -> scalar)."""
         m = {
-            "clone.map": np.broadcast_to(np.bool_(True), (self.nrows, self.ncols)),
+            "clone.map": (np.broadcast_to(np.bool_(True), (self.nrows, self.ncols)) if self.mask is None
+                          else np.asarray(self.mask, np.bool_)),
             "dem.map": np.asarray(self.dem, np.float32),
             "slope.map": np.asarray(self.slope, np.float32),
             "stations.map": np.asarray(self.locations, np.int32),
@@ -184,9 +190,11 @@ class Catchment:
         return m
 
     def forcing_map_names(self, day):
-        tag = _name_t(day)
-        return {"prec": "forcings/prec" + tag, "tavg": "forcings/tavg" + tag, "tmin": "forcings/tmin" + tag,
-                "tmax": "forcings/tmax" + tag}
+        from .csf import stack_name
+        names = {k: stack_name("forcings/" + k, day) for k in ("prec", "tavg", "tmin", "tmax")}
+        if self.etref_input:
+            names["etref"] = stack_name("forcings/etref", day)
+        return names
 
     def write_csf_inputs(self, inputdir, nsteps=None):
         """Write every static map and the daily forcing stacks as PCRaster CSF files under `inputdir`, laid out exactly
@@ -359,7 +367,7 @@ Tair = forcings/tavg
 Tcorr_fact = {p['Tcorr_fact']}
 tempNetcdfFLAG = 0
 [ETREF]
-ETREF_FLAG = 0
+ETREF_FLAG = {1 if self.etref_input else 0}
 ETref = forcings/etref
 Lat = latitude.map
 Gsc = {p['Gsc']}
@@ -446,7 +454,7 @@ def make_catchment(nrows, ncols, cellsize=250.0, seed=1, nsteps=365, snow=False,
                    reservoirs=False, lakes=False, ground=True, routing=True, infil_excess=0,
                    rout_components=False, outlets="single", start=datetime.date(2001, 1, 1),
                    n_res_simple=0, n_res_adv=0, n_lakes=0, open_water=False, params=None,
-                   report_daily=(), soil_classes=1, zrange=None, pws=False, report_opts=None):
+                   report_daily=(), soil_classes=1, zrange=None, pws=False, report_opts=None, etref_input=False, mask=None):
     """Build one of the BASELINE.json synthetic configurations."""
     p = dict(DEFAULT_PARAMS)
     if params:
@@ -480,7 +488,15 @@ def make_catchment(nrows, ncols, cellsize=250.0, seed=1, nsteps=365, snow=False,
     cat = Catchment(nrows=nrows, ncols=ncols, cellsize=float(cellsize), seed=seed, dem=raw, ldd=ldd, slope=slope,
                     lat=lat, flags=flags, params=p, start=start, nsteps=nsteps, locations=locations,
                     soil_maps=soil_maps, rout_components=rout_components, infil_excess=infil_excess,
-                    report_daily=tuple(report_daily), pws=bool(pws), report_opts=dict(report_opts or {}))
+                    report_daily=tuple(report_daily), pws=bool(pws), report_opts=dict(report_opts or {}),
+                    etref_input=bool(etref_input))
+    if mask == "disk":                    # a non-rectangular catchment: everything outside the disk is MV
+        rr, cc = np.ogrid[:nrows, :ncols]
+        inside = ((rr - (nrows - 1) / 2.0) / (nrows / 2.0)) ** 2 + ((cc - (ncols - 1) / 2.0) / (ncols / 2.0)) ** 2 <= 1.0
+        inside[nrows - 1, (ncols - 1) // 2] = True
+        cat.mask = inside
+        cat.ldd = np.where(inside, cat.ldd, 255).astype(np.uint8)
+        cat.locations = np.where(inside, cat.locations, 0).astype(np.int32)
     if glacier:
         _add_glaciers(cat, rng)
     if reservoirs or lakes:

