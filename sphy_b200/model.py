@@ -326,8 +326,10 @@ class SphyModel:
         return np.ascontiguousarray(flat, dtype=dtype)
 
     def _dev(self, arr, dtype=None):
-        t = torch.from_numpy(np.ascontiguousarray(arr if dtype is None else np.asarray(arr, dtype=dtype))).to(self.device)
-        return t
+        a = np.ascontiguousarray(arr if dtype is None else np.asarray(arr, dtype=dtype))
+        if not a.flags.writeable:
+            a = a.copy()
+        return torch.from_numpy(a).to(self.device)
 
     def _full(self, value, dtype=torch.float32):
         return torch.full((self.n,), float(value), dtype=dtype, device=self.device)
