@@ -47,7 +47,7 @@ const char *sphy_last_error(const sphy_ctx *ctx);
 int sphy_sm_count(const sphy_ctx *ctx);
 /* sizeof() of the ABI structs, so foreign-language bindings can verify their layout without a GPU:
  * 0 sphy_param, 1 sphy_wb_params, 2 sphy_wb_state, 3 sphy_wb_forcing, 4 sphy_wb_out, 5 sphy_glac_table,
- * 6 sphy_glac_out, 7 sphy_reslake, 8 sphy_openwater */
+ * 6 sphy_glac_out, 7 sphy_reslake, 8 sphy_openwater, 9 sphy_veg */
 size_t sphy_abi_sizeof(int which);
 
 /* ---- K3: LDD -> integer structures (once per run) ------------------------------------------
@@ -190,6 +190,28 @@ enum {
 };
 int sphy_module_op(sphy_ctx *ctx, int op, const sphy_param *in, int n_in, float *const *out, int n_out, int64_t count,
                    float k0, int day_of_year, void *stream);
+
+/* Dynamic vegetation (modules/dynamic_veg.py:27-128, DynVegFLAG = 1): NDVI -> Kc, LAI, canopy storage Smax; canopy
+ * interception turns the day's precipitation into effective precipitation.  Runs BEFORE the glacier and water-balance
+ * kernels (sphy.py:820-822) and produces the three maps they then consume: ETref (Hargreaves, or the input series),
+ * the per-cell crop coefficient and the effective precipitation -- sphy_wb_step is called with SPHY_WB_ETREF_INPUT,
+ * kc = Kc map, prec = PrecipEff and pcorr = 1.  The latitude / k0 / pcorr / tcorr fields are taken from `p`. */
+typedef struct {
+    const float *ndvi;               /* NDVI of the day (the caller keeps the previous map when a day is missing) */
+    const float *prec, *tavg, *tmin, *tmax, *etref_in;   /* raw forcing; etref_in replaces Hargreaves when non-NULL */
+    sphy_param lai_max, open_water_frac;
+    /* cfg floats folded on the host exactly like the reference's Python expressions (dynamic_veg.py:30-40) */
+    float sr_min;                    /* REAL4((1+NDVImin)/(1-NDVImin)) */
+    float sr_range;                  /* REAL4(SR_max - SR_min) */
+    float fpar_range;                /* REAL4(FPARmax - FPARmin) */
+    float log_one_m_fparmax;         /* REAL4(log10(REAL4(1 - FPARmax))) */
+    float kc_min, kc_range;          /* REAL4(KCmin), REAL4(KCmax - KCmin) */
+    float ndvi_min, ndvi_range;      /* REAL4(NDVImin), REAL4(NDVImax - NDVImin) */
+    float *Scanopy;                  /* canopy storage, in/out */
+    float *ETref, *Kc, *PrecipEff;   /* outputs consumed by sphy_glac_step / sphy_wb_step */
+    float *LAI, *Int;                /* optional outputs (reporting: LAI, TotIntF) */
+} sphy_veg;
+int sphy_veg_step(sphy_ctx *ctx, const sphy_wb_params *p, const sphy_veg *v, int day_of_year, void *stream);
 
 /* K1 alone does not need the LDD: declare the number of active cells directly */
 int sphy_set_ncells(sphy_ctx *ctx, int64_t n);

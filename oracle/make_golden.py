@@ -22,7 +22,7 @@ from .run_reference import run_reference
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
-REPORT = ("TotRF", "TotETactF", "TotETref", "Infil", "wbal", "TotRootRF", "TotRootDF", "TotRootPF", "TotSubPF",
+REPORT = ("LAI", "TotIntF", "TotPrecEF", "StorCanop", "TotRF", "TotETactF", "TotETref", "Infil", "wbal", "TotRootRF", "TotRootDF", "TotRootPF", "TotSubPF",
           "TotCapRF", "TotBaseRF", "TotSnowRF", "TotGlacRF", "TotGlacMelt", "TotSnowMelt", "StorSnow", "QallRAtot")
 
 # wetter / shallower than the cfg defaults so that saturation, runoff, drainage, percolation, baseflow and the
@@ -46,6 +46,10 @@ CASES = {
     "c1_etref": (dict(nrows=12, ncols=10, seed=17, etref_input=True, params=WET), 40),
     # a non-rectangular catchment: MV outside the clone mask, cells at the rim drain out of the map
     "c1_masked": (dict(nrows=14, ncols=12, seed=18, mask="disk", rout_components=True, params=WET), 40),
+    # dynamic vegetation: NDVI map series -> Kc, LAI, canopy interception (modules/dynamic_veg.py)
+    "c1_dynveg": (dict(nrows=12, ncols=10, seed=19, dynveg=True, params=WET, start=(2001, 4, 1)), 50),
+    "c2_dynveg_snow": (dict(nrows=12, ncols=10, seed=23, dynveg=True, snow=True, glacier=True, params=GLAC, start=(2001, 4, 15),
+                            zrange=(1500.0, 5200.0)), 50),
     # plant water stress (ET.ks) instead of the wilting-point reduction
     "c1_pws": (dict(nrows=12, ncols=10, seed=15, pws=True, params=WET), 40),
     # reporting.csv driven outputs (utilities/reporting.py): month / year / final maps, averages, long-term sums, TSS
@@ -83,7 +87,7 @@ def build_case(name):
 def make(name):
     cat, nsteps = build_case(name)
     ref = run_reference(cat, nsteps)
-    fkeys = ("prec", "tavg", "tmin", "tmax") + (("etref",) if cat.etref_input else ())
+    fkeys = ("prec", "tavg", "tmin", "tmax") + (("etref",) if cat.etref_input else ()) + (("ndvi",) if cat.dynveg else ())
     forcing = {k: np.stack([cat.forcing(t)[k] for t in range(1, nsteps + 1)]) for k in fkeys}
     payload = {"meta": np.array(json.dumps(dict(case=name, nsteps=nsteps, kwargs=CASES[name][0])))}
     for k, v in cat.static_maps().items():

@@ -26,7 +26,7 @@ STATE_ATTRS = (
     "RootWater", "SubWater", "CapRise", "RootDrain", "GwRecharge", "Gw", "BaseR", "H_gw", "SubDrain",
     "SnowStore", "SnowWatStore", "TotalSnowStore", "SoilWater",
     "QRAold", "RootRRAold", "RootDRAold", "RainRAold", "SnowRAold", "GlacRAold", "BaseRAold",
-    "StorRES", "RootRR", "RootDR", "RainR", "SnowR", "GlacR", "SnowSoil", "waterbalanceTot", "GlacFrac",
+    "StorRES", "RootRR", "RootDR", "RainR", "SnowR", "GlacR", "SnowSoil", "waterbalanceTot", "GlacFrac", "Scanopy", "Kc",
 )
 
 _REF_MODULE_PREFIXES = ("ET", "rootzone", "subzone", "hargreaves", "modules", "utilities")

@@ -74,6 +74,14 @@ class OpenWater(C.Structure):
     _fields_ = [("ow_ptr", P), ("ow_cell", P), ("open_water_frac", P), ("et_open_water", P), ("prec", P), ("pcorr", C.c_float)]
 
 
+class Veg(C.Structure):
+    _fields_ = ([(k, P) for k in ("ndvi", "prec", "tavg", "tmin", "tmax", "etref_in")]
+                + [("lai_max", SphyParam), ("open_water_frac", SphyParam)]
+                + [(k, C.c_float) for k in ("sr_min", "sr_range", "fpar_range", "log_one_m_fparmax", "kc_min", "kc_range", "ndvi_min",
+                                            "ndvi_range")]
+                + [(k, P) for k in ("Scanopy", "ETref", "Kc", "PrecipEff", "LAI", "Int")])
+
+
 RL_NPAR = 23
 WB_SNOW, WB_GROUND, WB_INFIL_EXCESS, WB_PWS, WB_ETREF_INPUT = 1, 2, 4, 8, 16
 RA_TABLE, RA_CELL = 0, 1
@@ -107,6 +115,7 @@ SYMBOLS = {
     "sphy_map_unary": (C.c_int, [P, C.c_int, P, P, C.c_int64, P]),
     "sphy_set_ncells": (C.c_int, [P, C.c_int64]),
     "sphy_module_op": (C.c_int, [P, C.c_int, C.POINTER(SphyParam), C.c_int, C.POINTER(P), C.c_int, C.c_int64, C.c_float, C.c_int, P]),
+    "sphy_veg_step": (C.c_int, [P, C.POINTER(WbParams), C.POINTER(Veg), C.c_int, P]),
     "sphy_wb_step": (C.c_int, [P, C.POINTER(WbParams), C.POINTER(WbState), C.POINTER(WbForcing), C.POINTER(WbOut),
                                C.c_int, P]),
     "sphy_glac_step": (C.c_int, [P, C.POINTER(GlacTable), P, P, C.c_float, C.c_float, C.POINTER(GlacOut), P]),
@@ -120,7 +129,7 @@ SYMBOLS = {
     "sphy_route_reslake_step": (C.c_int, [P, C.POINTER(ResLake), P, P, SphyParam, C.c_float, C.c_int, C.c_int, P]),
 }
 
-ABI_STRUCTS = (SphyParam, WbParams, WbState, WbForcing, WbOut, GlacTable, GlacOut, ResLake, OpenWater)
+ABI_STRUCTS = (SphyParam, WbParams, WbState, WbForcing, WbOut, GlacTable, GlacOut, ResLake, OpenWater, Veg)
 
 _LIB = None
 

@@ -145,6 +145,7 @@ extern "C" size_t sphy_abi_sizeof(int which)
         case 6: return sizeof(sphy_glac_out);
         case 7: return sizeof(sphy_reslake);
         case 8: return sizeof(sphy_openwater);
+        case 9: return sizeof(sphy_veg);
         default: return 0;
     }
 }

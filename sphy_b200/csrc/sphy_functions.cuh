@@ -50,6 +50,27 @@ __device__ __forceinline__ float etreddry(float rootwater, float rootdry, float 
     return fmaxf(fminf((rootwater - rootdry) / (rootwilt - rootdry), 1.0f), 0.0f);
 }
 
+// ---- modules/dynamic_veg.py ---------------------------------------------------------------------------------
+// Veg_function (dynamic_veg.py:27-40) with the cfg floats folded on the host; ndvi already limited to 0.999
+__device__ __forceinline__ void Veg_function(float ndvi, float lai_max, float sr_min, float sr_range, float fpar_range,
+                                             float log_one_m_fparmax, float kc_min, float kc_range, float ndvi_min, float ndvi_range,
+                                             float &Kc, float &Smax, float &LAI)
+{
+    const float SR = (1.0f + ndvi) / (1.0f - ndvi);
+    const float FPAR = fminf(((SR - sr_min) / sr_range) * fpar_range, 0.95f);
+    LAI = (lai_max * (float)log10((double)(1.0f - FPAR))) / log_one_m_fparmax;
+    Smax = (0.935f + 0.498f * LAI) - 0.00575f * (LAI * LAI);
+    Kc = kc_min + kc_range * fmaxf(fminf((ndvi - ndvi_min) / ndvi_range, 1.0f), 0.0f);
+}
+// Inter_function (dynamic_veg.py:44-49)
+__device__ __forceinline__ void Inter_function(float S, float Smax, float Etr, float &Int, float &PreT, float &Sout)
+{
+    PreT = fmaxf(0.0f, S - Smax);
+    S = S - PreT;
+    Int = fminf(1.5f * Etr, S);
+    Sout = S - Int;
+}
+
 // ---- modules/snow.py -------------------------------------------------------------------------------------
 // PotSnowMelt (snow.py:27-33); melt_cos[h-1] = REAL4(cos(3.1415*h/12))
 __device__ __forceinline__ float PotSnowMelt(float temp, float tempmax, float ddfs, const float *melt_cos)

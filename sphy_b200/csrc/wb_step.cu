@@ -152,6 +152,84 @@ extern "C" int sphy_set_ncells(sphy_ctx *ctx, int64_t n)
 }
 
 
+// ---- dynamic vegetation (modules/dynamic_veg.py) --------------------------------------------------------------------
+namespace {
+
+struct VegArgs {
+    sphy_veg v;
+    DayScalars d;
+    float pcorr, tcorr;
+    int ra;                      // 0 table, 1 cell, 2 etref input
+    const uint16_t *lat_class;
+    const float *ra_table, *sin_lat, *cos_lat, *tan_lat;
+    int64_t n;
+};
+
+__global__ void k_veg_step(const __grid_constant__ VegArgs a)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const sphy_veg &v = a.v;
+    const float Precip = __ldg(v.prec + i) / a.pcorr;                        // sphy.py:757
+    float ETref;
+    if (a.ra == 2) {
+        ETref = __ldg(v.etref_in + i);
+    } else {
+        const float Temp = __ldg(v.tavg + i) + a.tcorr, TempMin = __ldg(v.tmin + i) + a.tcorr, TempMax = __ldg(v.tmax + i) + a.tcorr;
+        const float Ra = a.ra == 0 ? __ldg(a.ra_table + __ldg(a.lat_class + i))
+                                   : extrarad(__ldg(a.sin_lat + i), __ldg(a.cos_lat + i), __ldg(a.tan_lat + i), a.d);
+        ETref = sf::Hargreaves(a.d.hg_c, Ra, Temp, TempMax, TempMin);
+    }
+    const float ndvi = fminf(__ldg(v.ndvi + i), 0.999f);                     // dynamic_veg.py:84
+    const float lai_max = v.lai_max.map ? __ldg(v.lai_max.map + i) : v.lai_max.value;
+    float Kc, Smax, LAI, Int, PreT, S;
+    sf::Veg_function(ndvi, lai_max, v.sr_min, v.sr_range, v.fpar_range, v.log_one_m_fparmax, v.kc_min, v.kc_range, v.ndvi_min,
+                     v.ndvi_range, Kc, Smax, LAI);
+    sf::Inter_function(v.Scanopy[i] + Precip, Smax, ETref, Int, PreT, S);    // dynamic_veg.py:108-110
+    v.Scanopy[i] = S;
+    v.ETref[i] = ETref;
+    v.Kc[i] = Kc;
+    v.PrecipEff[i] = PreT;
+    if (v.LAI) v.LAI[i] = LAI;
+    if (v.Int) v.Int[i] = v.open_water_frac.map ? Int * (1.0f - __ldg(v.open_water_frac.map + i)) : Int;
+}
+
+}  // namespace
+
+extern "C" int sphy_veg_step(sphy_ctx *ctx, const sphy_wb_params *p, const sphy_veg *v, int doy, void *stream_)
+{
+    if (!ctx || !p || !v) return SPHY_E_INVALID;
+    if (ctx->n <= 0) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_veg_step: no active cells");
+    if (!v->ndvi || !v->prec || !v->Scanopy || !v->ETref || !v->Kc || !v->PrecipEff)
+        SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_veg_step: missing mandatory map");
+    if (!v->etref_in && (!v->tavg || !v->tmin || !v->tmax)) SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_veg_step: missing temperature forcing");
+    cudaStream_t st = (cudaStream_t)stream_;
+    VegArgs a = {};
+    a.v = *v;
+    a.pcorr = p->pcorr;
+    a.tcorr = p->tcorr;
+    a.d = day_scalars(doy, p->k0);
+    a.n = ctx->n;
+    a.ra = v->etref_in ? 2 : p->ra_mode;
+    if (a.ra == SPHY_RA_TABLE) {
+        if (!p->lat_class || !p->lat_unique_deg || p->n_lat_unique <= 0) SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_veg_step: latitude classes missing");
+        if (ctx->ra_table_cap < p->n_lat_unique) {
+            int rc = dev_alloc(ctx, &ctx->ra_table, (size_t)p->n_lat_unique);
+            if (rc != SPHY_OK) return rc;
+            ctx->ra_table_cap = p->n_lat_unique;
+        }
+        k_ra_table<<<div_up(p->n_lat_unique, 128), 128, 0, st>>>(p->lat_unique_deg, p->n_lat_unique, a.d, ctx->ra_table);
+        a.ra_table = ctx->ra_table;
+        a.lat_class = p->lat_class;
+    } else if (a.ra == SPHY_RA_CELL) {
+        if (!p->sin_lat || !p->cos_lat || !p->tan_lat) SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_veg_step: latitude maps missing");
+        a.sin_lat = p->sin_lat; a.cos_lat = p->cos_lat; a.tan_lat = p->tan_lat;
+    }
+    k_veg_step<<<div_up(ctx->n, 256), 256, 0, st>>>(a);
+    SPHY_LAUNCH_CHECK(ctx);
+    return SPHY_OK;
+}
+
 // ---- the reference's per-cell process functions, one at a time -----------------------------------------------------
 // sphy_module_op keeps the module call signatures of the reference usable on device maps (sphy_b200/modules/*.py):
 // the same __device__ functions the fused kernel composes, evaluated one whole-map pass per call like PCRaster does.

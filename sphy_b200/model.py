@@ -157,9 +157,8 @@ class SphyModel:
         if self.GlacFLAG == 1:
             self.SnowFLAG = 1
             self.GroundFLAG = 1
-        for flag, what in ((self.DynVegFLAG, "dynamic vegetation"), (self.SedFLAG, "sediment")):
-            if flag:
-                raise NotImplementedError(f"{what} is outside the B200 hot path (SURVEY.md section 2)")
+        if self.SedFLAG:
+            raise NotImplementedError("sediment is outside the B200 hot path (SURVEY.md section 2)")
         self.inpath = config.get("DIRS", "inputdir")
         self.outpath = config.get("DIRS", "outputdir")
         # -- timing, sphy.py:90-110
@@ -396,9 +395,19 @@ class SphyModel:
             self.SubDrainVel = self.SubKsat * self.Slope                                      # sphy.py:237
         # land use / crop coefficient, sphy.py:254-281
         self.LandUse = cn(self._readmap(cfg.get("LANDUSE", "LandUse")), np.int32)
-        if cfg.getint("LANDUSE", "KCstatic") != 1:
-            raise NotImplementedError("Kc map series (KCstatic = 0) is not supported yet")
-        self.Kc = self._lookup_column_table(os.path.join(self.inpath, cfg.get("LANDUSE", "CropFac")), self.LandUse)
+        if self.DynVegFLAG == 1:                                                               # dynamic_veg.py:52-63
+            self.ndvi = cfg.get("DYNVEG", "NDVI")
+            self.LAImax = self._lookup_column_table(os.path.join(self.inpath, cfg.get("DYNVEG", "LAImax")), self.LandUse)
+            for k in ("NDVImax", "NDVImin", "NDVIbase", "KCmax", "KCmin", "FPARmax", "FPARmin"):
+                try:
+                    setattr(self, k, cfg.getfloat("DYNVEG", k))
+                except ValueError:
+                    raise NotImplementedError(f"[DYNVEG] {k} as a map is not supported yet") from None
+            self.Kc = None                         # per-cell map produced by sphy_veg_step every day
+        else:
+            if cfg.getint("LANDUSE", "KCstatic") != 1:
+                raise NotImplementedError("Kc map series (KCstatic = 0) is not supported yet")
+            self.Kc = self._lookup_column_table(os.path.join(self.inpath, cfg.get("LANDUSE", "CropFac")), self.LandUse)
         self.PlantWaterStressFLAG = cfg.getint("PWS", "PWS_FLAG")
         self.PMap = (self._lookup_column_table(os.path.join(self.inpath, cfg.get("PWS", "PFactor")), self.LandUse)
                      if self.PlantWaterStressFLAG == 1 else None)
@@ -511,6 +520,7 @@ class SphyModel:
             self.TotalSnowStore = self.SnowStore + self.SnowWatStore
         else:
             self.SnowStore = self.SnowWatStore = self.TotalSnowStore = None
+        self.Scanopy = self._full(0.0) if self.DynVegFLAG == 1 else None                       # dynamic_veg.py:66-72
         self.GlacFrac = None
         if self.GlacFLAG == 1:
             self._glacier_initial()
@@ -740,7 +750,7 @@ class SphyModel:
             flags |= _lib.WB_INFIL_EXCESS
         if self.PlantWaterStressFLAG == 1:
             flags |= _lib.WB_PWS
-        if self.ETREF_FLAG == 1:
+        if self.ETREF_FLAG == 1 or self.DynVegFLAG == 1:   # with dynamic vegetation ETref comes from sphy_veg_step
             flags |= _lib.WB_ETREF_INPUT
         P.flags = flags
         if self.ETREF_FLAG == 0:
@@ -766,11 +776,15 @@ class SphyModel:
                 P.sin_lat, P.cos_lat, P.tan_lat = (t.data_ptr() for t in self._lat_trig)
             P.k0 = float(f32(((24 * 60) / math.pi) * self.Gsc))                              # hargreaves.py:32-33
         P.pcorr, P.tcorr = float(f32(self.Pcorr)), float(f32(self.Tcorr))
+        self._pcorr = P.pcorr
         pr = self._param
+        if self.DynVegFLAG == 1:
+            self._prepare_veg_struct(P)
         P.root_field, P.root_sat, P.root_dry, P.root_wilt = pr(self.RootField), pr(self.RootSat), pr(self.RootDry), pr(self.RootWilt)
         P.root_ksat, P.root_drainvel, P.e_root = pr(self.RootKsat), pr(self.RootDrainVel), pr(self._e_root)
         P.sub_field, P.sub_sat, P.e_sub = pr(self.SubField), pr(self.SubSat), pr(self._e_sub)
-        P.caprise_max, P.kc = pr(self.CapRiseMax), pr(self.Kc)
+        P.caprise_max = pr(self.CapRiseMax)
+        P.kc = pr(self.Kc) if self.DynVegFLAG != 1 else SphyParam(self._veg_maps["Kc"].data_ptr(), 0.0)
         if self.PMap is not None:
             P.pmap = pr(self.PMap)
         if self.GlacFrac is not None:
@@ -842,6 +856,51 @@ class SphyModel:
             else:                                          # cfg float: Python-double subtraction, then REAL4 (routing.py:28)
                 self._one_m_kx = float(f32(1 - self.kx))
 
+    def _prepare_veg_struct(self, P):
+        """sphy_veg: cfg floats folded like the reference's Python expressions (dynamic_veg.py:30-40).  The veg kernel
+        keeps the raw Pcorr/Tcorr and latitude fields; K1 and the glacier kernel then see pcorr = 1 because they consume
+        the effective precipitation."""
+        Pv = _lib.WbParams()
+        C.memmove(C.byref(Pv), C.byref(P), C.sizeof(P))
+        self._vegP = Pv
+        P.pcorr = 1.0
+        z = lambda: torch.zeros(self.n, dtype=torch.float32, device=self.device)  # noqa: E731
+        self._veg_maps = {k: z() for k in ("ETref", "Kc", "PrecipEff", "LAI", "Int")}
+        self._ndvi_old = torch.full((self.n,), float(f32((self.NDVImax + self.NDVImin) / 2)), dtype=torch.float32,
+                                    device=self.device)                                      # dynamic_veg.py:70
+        V = _lib.Veg()
+        V.lai_max = self._param(self.LAImax)
+        if self.openWaterFrac is not None:
+            V.open_water_frac = SphyParam(self._ow_frac_dev.data_ptr(), 0.0)
+        sr_max = (1 + self.NDVImax) / (1 - self.NDVImax)
+        sr_min = (1 + self.NDVImin) / (1 - self.NDVImin)
+        V.sr_min, V.sr_range = float(f32(sr_min)), float(f32(sr_max - sr_min))
+        V.fpar_range = float(f32(self.FPARmax - self.FPARmin))
+        V.log_one_m_fparmax = float(f32(np.log10(np.float64(f32(1 - self.FPARmax)))))
+        V.kc_min, V.kc_range = float(f32(self.KCmin)), float(f32(self.KCmax - self.KCmin))
+        V.ndvi_min, V.ndvi_range = float(f32(self.NDVImin)), float(f32(self.NDVImax - self.NDVImin))
+        V.Scanopy = self.Scanopy.data_ptr()
+        for k, t in self._veg_maps.items():
+            setattr(V, k, t.data_ptr())
+        self._veg = V
+
+    def _veg_step(self, f, doy):
+        """dynamic_veg.dynamic (modules/dynamic_veg.py:76-128) -> ETref, Kc and effective precipitation maps."""
+        V = self._veg
+        ndvi = f.get("ndvi")
+        if ndvi is None:                                                                       # dynamic_veg.py:78-82
+            ndvi = self._ndvi_old
+        elif ndvi is not self._ndvi_old:
+            self._ndvi_old.copy_(ndvi, non_blocking=True)
+        V.ndvi = self._ndvi_old.data_ptr()
+        V.prec, V.tavg = f["prec"].data_ptr(), f["tavg"].data_ptr()
+        if self.ETREF_FLAG == 1:
+            V.etref_in = f["etref"].data_ptr()
+        else:
+            V.tmin, V.tmax = f["tmin"].data_ptr(), f["tmax"].data_ptr()
+        self._ck(self.lib.sphy_veg_step(self._ctx, C.byref(self._vegP), C.byref(V), doy, self._stream()), "sphy_veg_step")
+        return self._veg_maps
+
     # -- forcing ---------------------------------------------------------------------------------------
     def set_device_forcing(self, fn):
         """fn(counter) -> dict of compact float32 CUDA tensors (prec, tavg, tmin, tmax[, etref]) already resident in HBM."""
@@ -864,6 +923,8 @@ class SphyModel:
             pre = {"prec": self.Prec, "tavg": self.Tair, "etref": self.ETref}
         else:
             pre = {"prec": self.Prec, "tavg": self.Tair, "tmin": self.Tmin, "tmax": self.Tmax}
+        if self.DynVegFLAG == 1:
+            pre["ndvi"] = self.ndvi
         return {k: csf.stack_name(v, counter) for k, v in pre.items()}
 
     def _ingest(self, counter):
@@ -874,6 +935,8 @@ class SphyModel:
         if self._forcing_dev is not None:
             return self._forcing_dev(counter)
         keys = ("prec", "tavg", "etref") if self.ETREF_FLAG == 1 else ("prec", "tavg", "tmin", "tmax")
+        if self.DynVegFLAG == 1 and self._forcing_host is None:
+            keys = keys + ("ndvi",)
         if self._fdev is None:
             self._fdev = {k: torch.empty(self.n, dtype=torch.float32, device=self.device) for k in keys}
         if self._forcing_host is not None:
@@ -881,11 +944,18 @@ class SphyModel:
         if self._staging is None:
             self._staging = {k: torch.empty(self.n, dtype=torch.float32).pin_memory() for k in keys}
         names = self._forcing_names(counter)
+        out = dict(self._fdev)
         for k in keys:
-            src = np.asarray(self.maps.read(names[k]), np.float32).ravel()
+            try:
+                src = np.asarray(self.maps.read(names[k]), np.float32).ravel()
+            except (KeyError, FileNotFoundError):
+                if k != "ndvi":
+                    raise
+                out.pop("ndvi")                    # no NDVI map for this day: keep the previous one, dynamic_veg.py:78-82
+                continue
             self._staging[k].numpy()[:] = src if self.full_raster else src[self.flat_active]
             self._fdev[k].copy_(self._staging[k], non_blocking=True)
-        return self._fdev
+        return out
 
     def _ingest_host(self, counter, keys):
         compact = self.full_raster or self._forcing_host_compact
@@ -939,6 +1009,13 @@ class SphyModel:
             F.tmin, F.tmax = f["tmin"].data_ptr(), f["tmax"].data_ptr()
         doy = julian(self.curdate)
         self._doy = doy
+        self._prec_raw = f["prec"]
+        if self.DynVegFLAG == 1:                                                               # sphy.py:820-822
+            v = self._veg_step(f, doy)
+            f = dict(f, prec=v["PrecipEff"], etref=v["ETref"])
+            F.prec, F.etref = f["prec"].data_ptr(), f["etref"].data_ptr()
+            if self.ETREF_FLAG != 1 and self.SnowFLAG != 1:
+                F.tmin = F.tmax = None
         if self.GlacFLAG == 1:                                                                 # sphy.py:843-853
             a = self._glacier_step(f["tavg"], f["prec"])
             F.TotalSnowStore_GLAC, F.SnowR_GLAC = a["TotalSnowStore_GLAC"].data_ptr(), a["SnowR_GLAC"].data_ptr()
@@ -1007,7 +1084,7 @@ class SphyModel:
                  "sphy_route_reslake_step")
         if self.ETOpenWaterFLAG == 1:                                                          # advanced_routing.py:167-196
             ow = _lib.OpenWater(self._ow_ptr.data_ptr(), self._ow_cell.data_ptr(), self._ow_frac_dev.data_ptr(),
-                                self.out["ETOpenWater"].data_ptr(), self._prec_ptr, self._wbP.pcorr)
+                                self.out["ETOpenWater"].data_ptr(), self._prec_ptr, self._pcorr)
             self._ck(self.lib.sphy_reslake_openwater(self._ctx, C.byref(self._rl_struct), C.byref(ow), self._stream()),
                      "sphy_reslake_openwater")
         return self.QRAold
@@ -1053,6 +1130,17 @@ class SphyModel:
             if plain:
                 d.update(TotPrecF=lambda: o["Precip"], TotETrefF=lambda: o["ETref"], TotRainF=lambda: o["Rain"],
                          TotETact=lambda: o["ETact"], TotRootPF=lambda: o["RootPerc"])
+        if self.DynVegFLAG == 1:                                   # dynamic_veg.py:100-126; TotPrec is the RAW precipitation
+            vm = self._veg_maps
+            raw = lambda: self._prec_raw / f32(self._pcorr)  # noqa: E731  (sphy.py:757-763)
+            d["TotPrec"] = raw
+            d["LAI"] = lambda: vm["LAI"]
+            if o and plain:
+                d["TotPrecF"] = raw
+            if self.GlacFLAG != 1:
+                d.update(TotIntF=lambda: vm["Int"], TotPrecEF=lambda: vm["PrecipEff"])
+            if self.openWaterFrac is None:
+                d["StorCanop"] = lambda: self.Scanopy
         d["TotRF"] = lambda: self.TotR
         if self.RootRR is not None:
             d.update(TotRootRF=lambda: self.RootRR, TotRootDF=lambda: self.RootDR, TotRainRF=lambda: self.RainR)

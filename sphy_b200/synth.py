@@ -131,6 +131,7 @@ class Catchment:
     report_daily: tuple = ()
     pws: bool = False                    # plant water stress (ET.ks, PWS_FLAG)
     report_opts: dict = field(default_factory=dict)   # reporting.csv: name -> (map, avg, timeseries) option strings
+    dynveg: bool = False                 # DynVegFLAG = 1: NDVI map series -> Kc, LAI, canopy interception (modules/dynamic_veg.py)
     etref_input: bool = False            # ETREF_FLAG = 1: ETref map series instead of Hargreaves (sphy.py:814)
     mask: np.ndarray | None = None       # clone mask (True = inside the catchment); None = the whole rectangle
 
@@ -160,6 +161,10 @@ class Catchment:
         out = dict(prec=prec, tavg=tavg, tmin=tmin, tmax=tmax)
         if self.etref_input:
             out["etref"] = np.clip(np.float32(0.12) * (tavg + np.float32(12.0)), 0, None).astype(np.float32)
+        if self.dynveg:
+            season_v = 0.35 + 0.25 * np.sin(2.0 * np.pi * (doy - 120) / 365.0)
+            out["ndvi"] = np.clip(season_v + 0.15 * _smooth_noise(rng, self.nrows, self.ncols, 6)
+                                  + 0.05 * rng.standard_normal((self.nrows, self.ncols)), -0.05, 0.95).astype(np.float32)
         return out
 
     # ------------------------------------------------------------------------------------------
@@ -194,6 +199,8 @@ class Catchment:
         names = {k: stack_name("forcings/" + k, day) for k in ("prec", "tavg", "tmin", "tmax")}
         if self.etref_input:
             names["etref"] = stack_name("forcings/etref", day)
+        if self.dynveg:
+            names["ndvi"] = stack_name("forcings/ndvi", day)
         return names
 
     def write_csf_inputs(self, inputdir, nsteps=None):
@@ -220,6 +227,8 @@ class Catchment:
             fh.write(f"1 {p['Kc']}\n")
         with open(os.path.join(inputdir, "paved.tbl"), "w") as fh:
             fh.write("1 0.0\n")
+        with open(os.path.join(inputdir, "laimax.tbl"), "w") as fh:
+            fh.write(f"1 {p.get('LAImax', 5.5)}\n")
         with open(os.path.join(inputdir, "depletion.tbl"), "w") as fh:
             fh.write(f"1 {p.get('PFactor', 0.5)}\n")
         with open(os.path.join(inputdir, "reporting.csv"), "w") as fh:
@@ -254,7 +263,7 @@ SnowFLAG = {f['SnowFLAG']}
 RoutFLAG = {f['RoutFLAG']}
 LakeFLAG = {f['LakeFLAG']}
 ResFLAG = {f['ResFLAG']}
-DynVegFLAG = 0
+DynVegFLAG = {1 if self.dynveg else 0}
 GroundFLAG = {f['GroundFLAG']}
 SedFLAG = 0
 SedTransFLAG = 0
@@ -330,6 +339,16 @@ LandUse = landuse.map
 KCstatic = 1
 CropFac = kc.tbl
 KC =
+[DYNVEG]
+NDVI = forcings/ndvi
+NDVImax = 0.65
+NDVImin = 0.1
+NDVIbase = 0.15
+KCmax = 1.5
+KCmin = 0.5
+LAImax = laimax.tbl
+FPARmax = 0.95
+FPARmin = 0.001
 [PWS]
 PWS_FLAG = {1 if self.pws else 0}
 PFactor = depletion.tbl
@@ -429,6 +448,7 @@ _SOIL_FILES = dict(RootFieldMap="root_field.map", RootSatMap="root_sat.map", Roo
 
 # (reporting name, file prefix) pairs -- the names `reporting.reporting()` is called with on the hot path
 _REPORT_VARS = [
+    ("LAI", "LAI"), ("TotIntF", "IntF"), ("TotPrecEF", "PrecEF"), ("StorCanop", "Canop"),
     ("wbal", "wbal"), ("TotPrec", "Prec"), ("TotPrecF", "PrecF"), ("TotRain", "Rain"), ("TotRainF", "RainF"),
     ("TotETref", "ETr"), ("TotETrefF", "ETrF"), ("TotETpot", "ETp"), ("TotETpotF", "ETpF"), ("TotETact", "ETa"),
     ("TotETactF", "ETaF"), ("PlantStress", "PStr"), ("TotSnow", "Snow"), ("TotSnowF", "SnowF"),
@@ -454,7 +474,7 @@ def make_catchment(nrows, ncols, cellsize=250.0, seed=1, nsteps=365, snow=False,
                    reservoirs=False, lakes=False, ground=True, routing=True, infil_excess=0,
                    rout_components=False, outlets="single", start=datetime.date(2001, 1, 1),
                    n_res_simple=0, n_res_adv=0, n_lakes=0, open_water=False, params=None,
-                   report_daily=(), soil_classes=1, zrange=None, pws=False, report_opts=None, etref_input=False, mask=None):
+                   report_daily=(), soil_classes=1, zrange=None, pws=False, report_opts=None, etref_input=False, mask=None, dynveg=False):
     """Build one of the BASELINE.json synthetic configurations."""
     p = dict(DEFAULT_PARAMS)
     if params:
@@ -489,7 +509,7 @@ def make_catchment(nrows, ncols, cellsize=250.0, seed=1, nsteps=365, snow=False,
                     lat=lat, flags=flags, params=p, start=start, nsteps=nsteps, locations=locations,
                     soil_maps=soil_maps, rout_components=rout_components, infil_excess=infil_excess,
                     report_daily=tuple(report_daily), pws=bool(pws), report_opts=dict(report_opts or {}),
-                    etref_input=bool(etref_input))
+                    etref_input=bool(etref_input), dynveg=bool(dynveg))
     if mask == "disk":                    # a non-rectangular catchment: everything outside the disk is MV
         rr, cc = np.ogrid[:nrows, :ncols]
         inside = ((rr - (nrows - 1) / 2.0) / (nrows / 2.0)) ** 2 + ((cc - (ncols - 1) / 2.0) / (ncols / 2.0)) ** 2 <= 1.0

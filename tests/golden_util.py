@@ -13,7 +13,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 # golden state name -> attribute on the model objects (oracle port and SphyModel share the reference's names)
 STATE_KEYS = ("RootWater", "SubWater", "CapRise", "RootDrain", "GwRecharge", "Gw", "BaseR", "H_gw", "SubDrain",
               "SnowStore", "SnowWatStore", "TotalSnowStore", "SoilWater", "QRAold", "StorRES", "RootRR", "RootDR",
-              "RainR", "SnowR", "GlacR", "waterbalanceTot", "GlacFrac")
+              "RainR", "SnowR", "GlacR", "waterbalanceTot", "GlacFrac", "Scanopy")
 COMP_KEYS = ("RootRRAold", "RootDRAold", "RainRAold", "SnowRAold", "GlacRAold", "BaseRAold")
 # daily report file prefix -> key in the models' per-step `out` dict
 REPORT_KEYS = {"TotR": "TotR", "ETr": "ETref", "ETaF": "ActETact", "Infil": "Infil", "wbal": "wbal"}

@@ -94,6 +94,8 @@ def test_model_matches_reference_golden(name, order, route):
           params=dict(SubWater=470.0, RootDepthFlat=150.0, Pscale=2.5, Toffset=15.0, RootKsat=12.0)), 20),
     (dict(nrows=200, ncols=240, seed=7, cellsize=1000.0, reservoirs=True, lakes=True, n_res_simple=6, n_res_adv=4,
           n_lakes=5, infil_excess=1, params=dict(SubWater=470.0, RootDepthFlat=150.0, Pscale=2.5)), 20),
+    (dict(nrows=190, ncols=230, seed=8, dynveg=True, snow=True, zrange=(800.0, 4200.0),
+          params=dict(SubWater=470.0, RootDepthFlat=150.0, Pscale=2.5, Toffset=12.0)), 20),
 ])
 def test_model_matches_oracle_port(kw, nsteps, route_method="levels"):
     """Seeded catchments too large for fixtures: CUDA path vs oracle/sphy_port.py on the same inputs."""
@@ -112,6 +114,8 @@ def test_model_matches_oracle_port(kw, nsteps, route_method="levels"):
         keys += ["SnowStore", "SnowWatStore", "TotalSnowStore"]
     if cat.flags["ResFLAG"] or cat.flags["LakeFLAG"]:
         keys += ["StorRES"]
+    if cat.flags.get("DynVegFLAG"):
+        keys += ["Scanopy"]
     nb = tot = 0
     for t in range(1, nsteps + 1):
         port.dynamic({k: g(v) for k, v in cat.forcing(t).items()})
