@@ -114,7 +114,7 @@ def test_model_matches_oracle_port(kw, nsteps, route_method="levels"):
         keys += ["SnowStore", "SnowWatStore", "TotalSnowStore"]
     if cat.flags["ResFLAG"] or cat.flags["LakeFLAG"]:
         keys += ["StorRES"]
-    if cat.flags.get("DynVegFLAG"):
+    if cat.dynveg:
         keys += ["Scanopy"]
     nb = tot = 0
     for t in range(1, nsteps + 1):
