@@ -252,6 +252,9 @@ int sphy_glac_step(sphy_ctx *ctx, const sphy_glac_table *t, const float *tavg, c
 int sphy_route_step(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm, float *const *q_state, sphy_param kx,
                     float one_minus_kx /* REAL4(1-kx) when kx is a scalar: Python-double subtraction, routing.py:28 */,
                     int method, void *stream);
+/* Cells per scan-routing tile (a compile-time constant of the library); partition ranges must start on a tile. */
+int sphy_scan_tile_cells(void);
+
 /* Multi-GPU (one context per GPU, each built on the whole LDD): restrict this context to the contiguous device-index
  * range [cell_begin, cell_end) of the DFS order (cell_begin on a 1024-cell tile).  After the call every compact map
  * and sphy_ncells() refer to the local cells only.  pub_e: local indices at which other ranks' upstream ranges end

@@ -115,6 +115,7 @@ SYMBOLS = {
     "sphy_map_unary": (C.c_int, [P, C.c_int, P, P, C.c_int64, P]),
     "sphy_set_ncells": (C.c_int, [P, C.c_int64]),
     "sphy_module_op": (C.c_int, [P, C.c_int, C.POINTER(SphyParam), C.c_int, C.POINTER(P), C.c_int, C.c_int64, C.c_float, C.c_int, P]),
+    "sphy_scan_tile_cells": (C.c_int, []),
     "sphy_veg_step": (C.c_int, [P, C.POINTER(WbParams), C.POINTER(Veg), C.c_int, P]),
     "sphy_wb_step": (C.c_int, [P, C.POINTER(WbParams), C.POINTER(WbState), C.POINTER(WbForcing), C.POINTER(WbOut),
                                C.c_int, P]),

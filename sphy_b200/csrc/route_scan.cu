@@ -21,7 +21,11 @@
 namespace {
 
 constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_ITEMS = 4;
+#ifndef SPHY_SCAN_ITEMS
+#define SPHY_SCAN_ITEMS 4
+#endif
+constexpr int SCAN_ITEMS = SPHY_SCAN_ITEMS;            // cells per thread (4 or 8)
+constexpr int SCAN_MIN_CTAS = SCAN_ITEMS == 4 ? 4 : 2;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;   // 1024 cells
 
 struct ScanArgs {
@@ -51,12 +55,11 @@ struct ScanArgs {
     const int32_t *cut_cell, *cut_ptr;    // cut cells (ascending) and their per-tile ranges
     const double *cut_corr;               // float64 material placed at each cut cell (see route_scan_run_adv)
     sphy_param kx;
-    float one_m_kx, cellarea;
+    float one_m_kx;
+    double to_m3s;                        // mm/day -> m3/s: 0.001 * cellarea / 86400 (routing.py:26)
     int64_t n;
     int32_t ntiles;
 };
-
-__device__ __forceinline__ float to_m3s(float mm, float cellarea) { return ((mm * 0.001f) * cellarea) / 86400.0f; }
 
 // recession blend of one cell: routing.py:28, or advanced_routing.py:31-37 on a lake/reservoir network
 __device__ __forceinline__ float blend(const ScanArgs &a, int64_t cell, float f, float qold, float kx, float omk)
@@ -67,80 +70,90 @@ __device__ __forceinline__ float blend(const ScanArgs &a, int64_t cell, float f,
     return qd / 86400.0f;
 }
 
-// guarded 128-bit tile loads (4 consecutive cells per thread)
-__device__ __forceinline__ void load_sizes(const ScanArgs &a, int64_t base, int32_t sz[SCAN_ITEMS])
+// tile loads: SCAN_ITEMS consecutive cells per thread as 128-bit vectors; `p` points at the tile, `len` = cells in it
+template <typename T, typename V>
+__device__ __forceinline__ void load_items(const T *__restrict__ p, int lo, int len, T fill, T out[SCAN_ITEMS])
 {
-    if (base + SCAN_ITEMS <= a.n) {
-        const int4 s0 = __ldg(reinterpret_cast<const int4 *>(a.sub_size + base));
-        sz[0] = s0.x; sz[1] = s0.y; sz[2] = s0.z; sz[3] = s0.w;
+    if (lo + SCAN_ITEMS <= len) {
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS / 4; ++i) {
+            const V x = __ldg(reinterpret_cast<const V *>(p + lo) + i);
+            out[4 * i] = x.x; out[4 * i + 1] = x.y; out[4 * i + 2] = x.z; out[4 * i + 3] = x.w;
+        }
     } else {
 #pragma unroll
-        for (int j = 0; j < SCAN_ITEMS; ++j) sz[j] = base + j < a.n ? __ldg(a.sub_size + base + j) : 1;
+        for (int j = 0; j < SCAN_ITEMS; ++j) out[j] = lo + j < len ? __ldg(p + lo + j) : fill;
     }
 }
-__device__ __forceinline__ void load_comp(const ScanArgs &a, int c, int64_t base, float mm[SCAN_ITEMS], float q[SCAN_ITEMS])
+// Qold is rewritten by this kernel: plain loads, not the read-only path
+__device__ __forceinline__ void load_state(const float *p, int lo, int len, float out[SCAN_ITEMS])
 {
-    const float *m = a.m[c];
-    const float *qs = a.qstate[c];
-    if (base + SCAN_ITEMS <= a.n) {
-        const float4 x = __ldg(reinterpret_cast<const float4 *>(m + base));
-        mm[0] = x.x; mm[1] = x.y; mm[2] = x.z; mm[3] = x.w;
-        const float4 u = *reinterpret_cast<const float4 *>(qs + base);
-        q[0] = u.x; q[1] = u.y; q[2] = u.z; q[3] = u.w;
+    if (lo + SCAN_ITEMS <= len) {
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS / 4; ++i) {
+            const float4 x = reinterpret_cast<const float4 *>(p + lo)[i];
+            out[4 * i] = x.x; out[4 * i + 1] = x.y; out[4 * i + 2] = x.z; out[4 * i + 3] = x.w;
+        }
     } else {
 #pragma unroll
-        for (int j = 0; j < SCAN_ITEMS; ++j) {
-            mm[j] = base + j < a.n ? __ldg(m + base + j) : 0.0f;
-            q[j] = base + j < a.n ? qs[base + j] : 0.0f;
-        }
+        for (int j = 0; j < SCAN_ITEMS; ++j) out[j] = lo + j < len ? p[lo + j] : 0.0f;
     }
 }
 
 // main pass: persistent CTAs walk the tiles; the loads of the next tile are issued before the current one is
-// scanned, so the HBM latency hides behind the block scan and the shared-memory phase
-__global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_main(const __grid_constant__ ScanArgs a)
+// scanned, so the HBM latency hides behind the block scan and the shared-memory phase.  All in-tile indices are
+// 32-bit; the kernel is issue-bound, not bandwidth-bound, so the variants (lake network, per-cell kx) are
+// compiled separately and the unit conversion of routing.py:26 is one float64 multiply.
+template <bool ADV, bool KXMAP>
+__global__ void __launch_bounds__(SCAN_THREADS, SCAN_MIN_CTAS) k_scan_main(const __grid_constant__ ScanArgs a)
 {
     typedef cub::BlockScan<double, SCAN_THREADS, cub::BLOCK_SCAN_WARP_SCANS> BlockScan;
     __shared__ typename BlockScan::TempStorage tmp;
-    __shared__ double Ls[SCAN_TILE];
+    __shared__ __align__(16) double Ls[SCAN_TILE];
     const int lo = threadIdx.x * SCAN_ITEMS;
     int32_t t = blockIdx.x;
     if (t >= a.ntiles) return;
     int32_t sz_n[SCAN_ITEMS];
     float mm_n[SCAN_ITEMS], q_n[SCAN_ITEMS];
-    load_sizes(a, (int64_t)t * SCAN_TILE + lo, sz_n);
-    load_comp(a, 0, (int64_t)t * SCAN_TILE + lo, mm_n, q_n);
+    {
+        const int64_t tb = (int64_t)t * SCAN_TILE;
+        const int len = (int)min((int64_t)SCAN_TILE, a.n - tb);
+        load_items<int32_t, int4>(a.sub_size + tb, lo, len, 1, sz_n);
+        load_items<float, float4>(a.m[0] + tb, lo, len, 0.0f, mm_n);
+        load_state(a.qstate[0] + tb, lo, len, q_n);
+    }
     for (; t < a.ntiles; t += gridDim.x) {
         const int64_t tbase = (int64_t)t * SCAN_TILE;
-        const int64_t base = tbase + lo;
-        const int64_t tend = min(tbase + (int64_t)SCAN_TILE, a.n);   // one past the last cell of the tile
-        const bool full = base + SCAN_ITEMS <= a.n;
+        const int len = (int)min((int64_t)SCAN_TILE, a.n - tbase);   // cells in this tile
         int32_t sz[SCAN_ITEMS];
         float q[SCAN_ITEMS], mm[SCAN_ITEMS];
 #pragma unroll
         for (int j = 0; j < SCAN_ITEMS; ++j) { sz[j] = sz_n[j]; mm[j] = mm_n[j]; q[j] = q_n[j]; }
         const int32_t tn = t + gridDim.x;
         if (tn < a.ntiles) {                                   // prefetch the next tile of this CTA
-            load_sizes(a, (int64_t)tn * SCAN_TILE + lo, sz_n);
-            load_comp(a, 0, (int64_t)tn * SCAN_TILE + lo, mm_n, q_n);
+            const int64_t tb = (int64_t)tn * SCAN_TILE;
+            const int ln = (int)min((int64_t)SCAN_TILE, a.n - tb);
+            load_items<int32_t, int4>(a.sub_size + tb, lo, ln, 1, sz_n);
+            load_items<float, float4>(a.m[0] + tb, lo, ln, 0.0f, mm_n);
+            load_state(a.qstate[0] + tb, lo, ln, q_n);
         }
         float kxv[SCAN_ITEMS];
-        if (a.kx.map) {
-#pragma unroll
-            for (int j = 0; j < SCAN_ITEMS; ++j) kxv[j] = base + j < a.n ? __ldg(a.kx.map + base + j) : 0.0f;
-        }
+        if (KXMAP) load_items<float, float4>(a.kx.map + tbase, lo, len, 0.0f, kxv);
         const int32_t cb = __ldg(a.cross_ptr + t), ce = __ldg(a.cross_ptr + t + 1);
         const int32_t eb = __ldg(a.end_ptr + t), ee = __ldg(a.end_ptr + t + 1);
+        const int32_t tb32 = (int32_t)tbase;                   // n < 2^31 (sub_size is int32)
         for (int c = 0; c < a.ncomp; ++c) {
-            float *qs = a.qstate[c];
-            if (c > 0) load_comp(a, c, base, mm, q);
+            float *qs = a.qstate[c] + tbase;
+            if (c > 0) {
+                load_items<float, float4>(a.m[c] + tbase, lo, len, 0.0f, mm);
+                load_state(qs, lo, len, q);
+            }
             double v[SCAN_ITEMS];
 #pragma unroll
-            for (int j = 0; j < SCAN_ITEMS; ++j)
-                v[j] = base + j < a.n ? (a.adv ? (double)mm[j] : (double)to_m3s(mm[j], a.cellarea)) : 0.0;
-            if (a.adv) {                                       // float64 corrections at the cut cells of this tile
+            for (int j = 0; j < SCAN_ITEMS; ++j) v[j] = ADV ? (double)mm[j] : (double)mm[j] * a.to_m3s;   // cells past len hold 0
+            if (ADV) {                                         // float64 corrections at the cut cells of this tile
                 for (int32_t k = __ldg(a.cut_ptr + t); k < __ldg(a.cut_ptr + t + 1); ++k) {
-                    const int off = (int)(__ldg(a.cut_cell + k) - tbase) - lo;
+                    const int off = (__ldg(a.cut_cell + k) - tb32) - lo;
 #pragma unroll
                     for (int j = 0; j < SCAN_ITEMS; ++j)
                         if (off == j) v[j] += a.cut_corr[k];
@@ -149,35 +162,39 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_main(const __grid_cons
             double total;
             BlockScan(tmp).InclusiveSum(v, v, total);
 #pragma unroll
-            for (int j = 0; j < SCAN_ITEMS; ++j) Ls[lo + j] = v[j];
+            for (int i = 0; i < SCAN_ITEMS / 2; ++i) reinterpret_cast<double2 *>(Ls + lo)[i] = make_double2(v[2 * i], v[2 * i + 1]);
             __syncthreads();
             double before = lo == 0 ? 0.0 : Ls[lo - 1];        // tile-local exclusive prefix at the thread's first cell
 #pragma unroll
             for (int j = 0; j < SCAN_ITEMS; ++j) {
-                const int64_t e = base + j + sz[j] - 1;        // last cell of the upstream range
-                if (e < tend) {
-                    const float f = (float)(Ls[(int)(e - tbase)] - before);
-                    const float kx = a.kx.map ? kxv[j] : a.kx.value;
-                    const float omk = a.kx.map ? 1.0f - kx : a.one_m_kx;
-                    q[j] = blend(a, base + j, f, q[j], kx, omk);
+                const int el = lo + j + sz[j] - 1;             // last cell of the upstream range, tile-local
+                if (el < len) {
+                    const float f = (float)(Ls[el] - before);
+                    const float kx = KXMAP ? kxv[j] : a.kx.value;
+                    const float omk = KXMAP ? 1.0f - kx : a.one_m_kx;
+                    if (ADV) q[j] = blend(a, tbase + lo + j, f, q[j], kx, omk);
+                    else q[j] = omk * f + kx * q[j];           // routing.py:28
                 }                                              // else: crossing cell, left to k_scan_cross
                 before = v[j];
             }
-            if (full) {
-                *reinterpret_cast<float4 *>(qs + base) = make_float4(q[0], q[1], q[2], q[3]);
+            if (lo + SCAN_ITEMS <= len) {
+#pragma unroll
+                for (int i = 0; i < SCAN_ITEMS / 4; ++i)
+                    reinterpret_cast<float4 *>(qs + lo)[i] = make_float4(q[4 * i], q[4 * i + 1], q[4 * i + 2], q[4 * i + 3]);
             } else {
 #pragma unroll
                 for (int j = 0; j < SCAN_ITEMS; ++j)
-                    if (base + j < a.n) qs[base + j] = q[j];
+                    if (lo + j < len) qs[lo + j] = q[j];
             }
             // park what the crossing cells of / ending in this tile will need
-            double *pb = a.park_before + (int64_t)c * a.n_cross, *pe = a.park_end + (int64_t)c * (a.n_cross + a.n_pub);
-            for (int32_t k = cb + threadIdx.x; k < ce; k += SCAN_THREADS) {
-                const int off = (int)(__ldg(a.cross_r + k) - tbase);
-                pb[k] = off == 0 ? 0.0 : Ls[off - 1];
+            if (ce > cb || ee > eb) {
+                double *pb = a.park_before + (int64_t)c * a.n_cross, *pe = a.park_end + (int64_t)c * (a.n_cross + a.n_pub);
+                for (int32_t k = cb + threadIdx.x; k < ce; k += SCAN_THREADS) {
+                    const int off = __ldg(a.cross_r + k) - tb32;
+                    pb[k] = off == 0 ? 0.0 : Ls[off - 1];
+                }
+                for (int32_t j = eb + threadIdx.x; j < ee; j += SCAN_THREADS) pe[__ldg(a.end_k + j)] = Ls[__ldg(a.end_e + j) - tb32];
             }
-            for (int32_t j = eb + threadIdx.x; j < ee; j += SCAN_THREADS)
-                pe[__ldg(a.end_k + j)] = Ls[(int)(__ldg(a.end_e + j) - tbase)];
             if (threadIdx.x == 0) a.tile_tot[(int64_t)c * (a.ntiles + 1) + t] = total;
             __syncthreads();
         }
@@ -397,7 +414,7 @@ static int scan_prepare(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm,
     a.remote_slot = ctx->remote_slot;
     a.kx = kx;
     a.one_m_kx = one_m_kx;
-    a.cellarea = ctx->cellarea;
+    a.to_m3s = (0.001 * (double)ctx->cellarea) / 86400.0;
     a.n = ctx->n;
     a.ntiles = ctx->n_tiles;
     return SPHY_OK;
@@ -406,8 +423,15 @@ static int scan_prepare(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm,
 // main pass -> exclusive scan of the tile totals (cub, one call per component) -> crossing cells
 static int scan_launch_local(sphy_ctx *ctx, ScanArgs &a, cudaStream_t st)
 {
-    const int grid = ctx->n_tiles < ctx->sm_count * 4 ? ctx->n_tiles : ctx->sm_count * 4;
-    k_scan_main<<<grid, SCAN_THREADS, 0, st>>>(a);
+    const int resident = ctx->sm_count * SCAN_MIN_CTAS;
+    const int grid = ctx->n_tiles < resident ? ctx->n_tiles : resident;
+    if (a.adv) {
+        if (a.kx.map) k_scan_main<true, true><<<grid, SCAN_THREADS, 0, st>>>(a);
+        else k_scan_main<true, false><<<grid, SCAN_THREADS, 0, st>>>(a);
+    } else {
+        if (a.kx.map) k_scan_main<false, true><<<grid, SCAN_THREADS, 0, st>>>(a);
+        else k_scan_main<false, false><<<grid, SCAN_THREADS, 0, st>>>(a);
+    }
     for (int c = 0; c < a.ncomp; ++c) {
         size_t need = ctx->scan_tmp_bytes;
         SPHY_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->scan_tmp, need, ctx->scan_tile + (size_t)c * (ctx->n_tiles + 1),
@@ -492,6 +516,8 @@ int route_scan_run_adv(sphy_ctx *ctx, float *material_m3day, float *q_state, sph
 }
 
 // ---- multi-GPU -------------------------------------------------------------------------------------------------
+extern "C" int sphy_scan_tile_cells(void) { return SCAN_TILE; }
+
 extern "C" int sphy_set_partition(sphy_ctx *ctx, int64_t cell_begin, int64_t cell_end, int32_t n_pub, const int32_t *pub_e_dev,
                                   int32_t n_remote, const int32_t *remote_k_dev, const int32_t *remote_rank_dev,
                                   const int32_t *remote_slot_dev, void *stream)

@@ -32,6 +32,7 @@ def test_library_exports_every_declared_symbol(lib):
 def test_struct_layouts_match(lib):
     for which, st in enumerate(_lib.ABI_STRUCTS):
         assert lib.sphy_abi_sizeof(which) == ctypes.sizeof(st), st.__name__
+    assert lib.sphy_scan_tile_cells() == _lib.SCAN_TILE      # the host planner aligns partitions to the library's tile
 
 
 def test_no_gpu_fails_loudly(lib):
