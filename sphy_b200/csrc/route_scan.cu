@@ -21,12 +21,13 @@
 namespace {
 
 constexpr int SCAN_THREADS = 256;
-#ifndef SPHY_SCAN_ITEMS
-#define SPHY_SCAN_ITEMS 4
-#endif
-constexpr int SCAN_ITEMS = SPHY_SCAN_ITEMS;            // cells per thread (4 or 8)
-constexpr int SCAN_MIN_CTAS = SCAN_ITEMS == 4 ? 4 : 2;
-constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;   // 1024 cells
+constexpr int SCAN_WARPS = SCAN_THREADS / 32;
+constexpr int SCAN_TILE = 1024;                        // cells per tile = one warp's unit of work
+constexpr int SCAN_CHUNK = 128;                        // 32 lanes x 4 cells
+constexpr int SCAN_CHUNKS = SCAN_TILE / SCAN_CHUNK;
+constexpr int SCAN_BATCH = 4;                          // chunks whose phase-2 loads are in flight together
+constexpr int SCAN_MIN_CTAS = 3;                       // 3 x 64 KB of shared memory per SM
+constexpr int SCAN_SMEM = SCAN_WARPS * SCAN_TILE * (int)sizeof(double);
 
 struct ScanArgs {
     int ncomp;
@@ -70,133 +71,151 @@ __device__ __forceinline__ float blend(const ScanArgs &a, int64_t cell, float f,
     return qd / 86400.0f;
 }
 
-// tile loads: SCAN_ITEMS consecutive cells per thread as 128-bit vectors; `p` points at the tile, `len` = cells in it
-template <typename T, typename V>
-__device__ __forceinline__ void load_items(const T *__restrict__ p, int lo, int len, T fill, T out[SCAN_ITEMS])
-{
-    if (lo + SCAN_ITEMS <= len) {
-#pragma unroll
-        for (int i = 0; i < SCAN_ITEMS / 4; ++i) {
-            const V x = __ldg(reinterpret_cast<const V *>(p + lo) + i);
-            out[4 * i] = x.x; out[4 * i + 1] = x.y; out[4 * i + 2] = x.z; out[4 * i + 3] = x.w;
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < SCAN_ITEMS; ++j) out[j] = lo + j < len ? __ldg(p + lo + j) : fill;
-    }
-}
-// Qold is rewritten by this kernel: plain loads, not the read-only path
-__device__ __forceinline__ void load_state(const float *p, int lo, int len, float out[SCAN_ITEMS])
-{
-    if (lo + SCAN_ITEMS <= len) {
-#pragma unroll
-        for (int i = 0; i < SCAN_ITEMS / 4; ++i) {
-            const float4 x = reinterpret_cast<const float4 *>(p + lo)[i];
-            out[4 * i] = x.x; out[4 * i + 1] = x.y; out[4 * i + 2] = x.z; out[4 * i + 3] = x.w;
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < SCAN_ITEMS; ++j) out[j] = lo + j < len ? p[lo + j] : 0.0f;
-    }
-}
-
-// main pass: persistent CTAs walk the tiles; the loads of the next tile are issued before the current one is
-// scanned, so the HBM latency hides behind the block scan and the shared-memory phase.  All in-tile indices are
-// 32-bit; the kernel is issue-bound, not bandwidth-bound, so the variants (lake network, per-cell kx) are
-// compiled separately and the unit conversion of routing.py:26 is one float64 multiply.
+// main pass, warp-autonomous: every WARP owns one 1024-cell tile at a time and keeps the tile's float64 inclusive
+// prefix in its own 8 KB slice of shared memory, so there is no CTA barrier and no cross-warp traffic at all.
+//   phase 1  stream the runoff of the tile in 8 chunks of 128 cells (4 per lane, 128-bit loads all issued up front),
+//            convert to m3/s (routing.py:26; one float64 multiply), lane-serial + shuffle scan with a running carry;
+//   park     what crossing cells of / ending in this tile will need; the tile total;
+//   phase 2  stream sub_size and Qold, take the range sum of every cell whose range ends inside the tile from two
+//            shared-memory reads, blend with Qold (routing.py:28) and write Q.
+// Every array is read exactly once (16 B per cell and component).  The kernel is issue-bound, so the variants
+// (lake network, per-cell kx) are compiled separately and all in-tile indices are 32-bit.
 template <bool ADV, bool KXMAP>
 __global__ void __launch_bounds__(SCAN_THREADS, SCAN_MIN_CTAS) k_scan_main(const __grid_constant__ ScanArgs a)
 {
-    typedef cub::BlockScan<double, SCAN_THREADS, cub::BLOCK_SCAN_WARP_SCANS> BlockScan;
-    __shared__ typename BlockScan::TempStorage tmp;
-    __shared__ __align__(16) double Ls[SCAN_TILE];
-    const int lo = threadIdx.x * SCAN_ITEMS;
-    int32_t t = blockIdx.x;
-    if (t >= a.ntiles) return;
-    int32_t sz_n[SCAN_ITEMS];
-    float mm_n[SCAN_ITEMS], q_n[SCAN_ITEMS];
-    {
-        const int64_t tb = (int64_t)t * SCAN_TILE;
-        const int len = (int)min((int64_t)SCAN_TILE, a.n - tb);
-        load_items<int32_t, int4>(a.sub_size + tb, lo, len, 1, sz_n);
-        load_items<float, float4>(a.m[0] + tb, lo, len, 0.0f, mm_n);
-        load_state(a.qstate[0] + tb, lo, len, q_n);
-    }
-    for (; t < a.ntiles; t += gridDim.x) {
+    extern __shared__ __align__(16) double scan_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *Ls = scan_smem + warp * SCAN_TILE;
+    const int32_t nw = gridDim.x * SCAN_WARPS;
+    for (int32_t t = blockIdx.x * SCAN_WARPS + warp; t < a.ntiles; t += nw) {
         const int64_t tbase = (int64_t)t * SCAN_TILE;
         const int len = (int)min((int64_t)SCAN_TILE, a.n - tbase);   // cells in this tile
-        int32_t sz[SCAN_ITEMS];
-        float q[SCAN_ITEMS], mm[SCAN_ITEMS];
-#pragma unroll
-        for (int j = 0; j < SCAN_ITEMS; ++j) { sz[j] = sz_n[j]; mm[j] = mm_n[j]; q[j] = q_n[j]; }
-        const int32_t tn = t + gridDim.x;
-        if (tn < a.ntiles) {                                   // prefetch the next tile of this CTA
-            const int64_t tb = (int64_t)tn * SCAN_TILE;
-            const int ln = (int)min((int64_t)SCAN_TILE, a.n - tb);
-            load_items<int32_t, int4>(a.sub_size + tb, lo, ln, 1, sz_n);
-            load_items<float, float4>(a.m[0] + tb, lo, ln, 0.0f, mm_n);
-            load_state(a.qstate[0] + tb, lo, ln, q_n);
-        }
-        float kxv[SCAN_ITEMS];
-        if (KXMAP) load_items<float, float4>(a.kx.map + tbase, lo, len, 0.0f, kxv);
+        const bool full = len == SCAN_TILE;
+        const int32_t tb32 = (int32_t)tbase;                   // n < 2^31 (sub_size is int32)
         const int32_t cb = __ldg(a.cross_ptr + t), ce = __ldg(a.cross_ptr + t + 1);
         const int32_t eb = __ldg(a.end_ptr + t), ee = __ldg(a.end_ptr + t + 1);
-        const int32_t tb32 = (int32_t)tbase;                   // n < 2^31 (sub_size is int32)
+        int32_t kb = 0, ke = 0;
+        if (ADV) { kb = __ldg(a.cut_ptr + t); ke = __ldg(a.cut_ptr + t + 1); }
         for (int c = 0; c < a.ncomp; ++c) {
-            float *qs = a.qstate[c] + tbase;
-            if (c > 0) {
-                load_items<float, float4>(a.m[c] + tbase, lo, len, 0.0f, mm);
-                load_state(qs, lo, len, q);
-            }
-            double v[SCAN_ITEMS];
+            // ---- phase 1: float64 inclusive prefix of the tile's material -> Ls
+            const float *m = a.m[c] + tbase;
+            float4 x[SCAN_CHUNKS];
+            if (full) {
 #pragma unroll
-            for (int j = 0; j < SCAN_ITEMS; ++j) v[j] = ADV ? (double)mm[j] : (double)mm[j] * a.to_m3s;   // cells past len hold 0
-            if (ADV) {                                         // float64 corrections at the cut cells of this tile
-                for (int32_t k = __ldg(a.cut_ptr + t); k < __ldg(a.cut_ptr + t + 1); ++k) {
-                    const int off = (__ldg(a.cut_cell + k) - tb32) - lo;
-#pragma unroll
-                    for (int j = 0; j < SCAN_ITEMS; ++j)
-                        if (off == j) v[j] += a.cut_corr[k];
-                }
-            }
-            double total;
-            BlockScan(tmp).InclusiveSum(v, v, total);
-#pragma unroll
-            for (int i = 0; i < SCAN_ITEMS / 2; ++i) reinterpret_cast<double2 *>(Ls + lo)[i] = make_double2(v[2 * i], v[2 * i + 1]);
-            __syncthreads();
-            double before = lo == 0 ? 0.0 : Ls[lo - 1];        // tile-local exclusive prefix at the thread's first cell
-#pragma unroll
-            for (int j = 0; j < SCAN_ITEMS; ++j) {
-                const int el = lo + j + sz[j] - 1;             // last cell of the upstream range, tile-local
-                if (el < len) {
-                    const float f = (float)(Ls[el] - before);
-                    const float kx = KXMAP ? kxv[j] : a.kx.value;
-                    const float omk = KXMAP ? 1.0f - kx : a.one_m_kx;
-                    if (ADV) q[j] = blend(a, tbase + lo + j, f, q[j], kx, omk);
-                    else q[j] = omk * f + kx * q[j];           // routing.py:28
-                }                                              // else: crossing cell, left to k_scan_cross
-                before = v[j];
-            }
-            if (lo + SCAN_ITEMS <= len) {
-#pragma unroll
-                for (int i = 0; i < SCAN_ITEMS / 4; ++i)
-                    reinterpret_cast<float4 *>(qs + lo)[i] = make_float4(q[4 * i], q[4 * i + 1], q[4 * i + 2], q[4 * i + 3]);
+                for (int i = 0; i < SCAN_CHUNKS; ++i) x[i] = __ldg(reinterpret_cast<const float4 *>(m) + i * 32 + lane);
             } else {
 #pragma unroll
-                for (int j = 0; j < SCAN_ITEMS; ++j)
-                    if (lo + j < len) qs[lo + j] = q[j];
+                for (int i = 0; i < SCAN_CHUNKS; ++i) {
+                    const int o = i * SCAN_CHUNK + lane * 4;
+                    x[i].x = o < len ? __ldg(m + o) : 0.0f;
+                    x[i].y = o + 1 < len ? __ldg(m + o + 1) : 0.0f;
+                    x[i].z = o + 2 < len ? __ldg(m + o + 2) : 0.0f;
+                    x[i].w = o + 3 < len ? __ldg(m + o + 3) : 0.0f;
+                }
             }
-            // park what the crossing cells of / ending in this tile will need
+            double carry = 0.0;
+#pragma unroll
+            for (int i = 0; i < SCAN_CHUNKS; ++i) {
+                const int o = i * SCAN_CHUNK + lane * 4;
+                double v0, v1, v2, v3;
+                if (ADV) {
+                    v0 = (double)x[i].x; v1 = (double)x[i].y; v2 = (double)x[i].z; v3 = (double)x[i].w;
+                    for (int32_t k = kb; k < ke; ++k) {        // float64 corrections at the cut cells of this tile
+                        const int off = (__ldg(a.cut_cell + k) - tb32) - o;
+                        if (off >= 0 && off < 4) {
+                            const double corr = a.cut_corr[k];
+                            if (off == 0) v0 += corr; else if (off == 1) v1 += corr; else if (off == 2) v2 += corr; else v3 += corr;
+                        }
+                    }
+                } else {
+                    v0 = (double)x[i].x * a.to_m3s; v1 = (double)x[i].y * a.to_m3s;
+                    v2 = (double)x[i].z * a.to_m3s; v3 = (double)x[i].w * a.to_m3s;
+                }
+                v1 += v0; v2 += v1; v3 += v2;
+                double s = v3;                                 // inclusive scan of the lane totals
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const double y = __shfl_up_sync(0xffffffffu, s, d);
+                    if (lane >= d) s += y;
+                }
+                double excl = __shfl_up_sync(0xffffffffu, s, 1);
+                excl = (lane == 0 ? 0.0 : excl) + carry;
+                v0 += excl; v1 += excl; v2 += excl; v3 += excl;
+                reinterpret_cast<double2 *>(Ls + o)[0] = make_double2(v0, v1);
+                reinterpret_cast<double2 *>(Ls + o)[1] = make_double2(v2, v3);
+                carry = __shfl_sync(0xffffffffu, v3, 31);
+            }
+            __syncwarp();
+            // ---- park what the crossing cells of / ending in this tile will need
             if (ce > cb || ee > eb) {
                 double *pb = a.park_before + (int64_t)c * a.n_cross, *pe = a.park_end + (int64_t)c * (a.n_cross + a.n_pub);
-                for (int32_t k = cb + threadIdx.x; k < ce; k += SCAN_THREADS) {
+                for (int32_t k = cb + lane; k < ce; k += 32) {
                     const int off = __ldg(a.cross_r + k) - tb32;
                     pb[k] = off == 0 ? 0.0 : Ls[off - 1];
                 }
-                for (int32_t j = eb + threadIdx.x; j < ee; j += SCAN_THREADS) pe[__ldg(a.end_k + j)] = Ls[__ldg(a.end_e + j) - tb32];
+                for (int32_t j = eb + lane; j < ee; j += 32) pe[__ldg(a.end_k + j)] = Ls[__ldg(a.end_e + j) - tb32];
             }
-            if (threadIdx.x == 0) a.tile_tot[(int64_t)c * (a.ntiles + 1) + t] = total;
-            __syncthreads();
+            if (lane == 0) a.tile_tot[(int64_t)c * (a.ntiles + 1) + t] = carry;
+            // ---- phase 2: range sums of the cells whose range ends inside the tile, blended with Qold
+            const int32_t *szp = a.sub_size + tbase;
+            float *qs = a.qstate[c] + tbase;
+#pragma unroll
+            for (int h = 0; h < SCAN_CHUNKS; h += SCAN_BATCH) {
+                int4 sz[SCAN_BATCH];
+                float4 q[SCAN_BATCH], kxv[SCAN_BATCH];
+#pragma unroll
+                for (int b = 0; b < SCAN_BATCH; ++b) {
+                    const int o = (h + b) * SCAN_CHUNK + lane * 4;
+                    if (full) {
+                        sz[b] = __ldg(reinterpret_cast<const int4 *>(szp + o));
+                        q[b] = *reinterpret_cast<const float4 *>(qs + o);
+                        if (KXMAP) kxv[b] = __ldg(reinterpret_cast<const float4 *>(a.kx.map + tbase + o));
+                    } else {
+                        sz[b].x = o < len ? __ldg(szp + o) : 1;         q[b].x = o < len ? qs[o] : 0.0f;
+                        sz[b].y = o + 1 < len ? __ldg(szp + o + 1) : 1; q[b].y = o + 1 < len ? qs[o + 1] : 0.0f;
+                        sz[b].z = o + 2 < len ? __ldg(szp + o + 2) : 1; q[b].z = o + 2 < len ? qs[o + 2] : 0.0f;
+                        sz[b].w = o + 3 < len ? __ldg(szp + o + 3) : 1; q[b].w = o + 3 < len ? qs[o + 3] : 0.0f;
+                        if (KXMAP) {
+                            const float *kp = a.kx.map + tbase;
+                            kxv[b].x = o < len ? __ldg(kp + o) : 0.0f;         kxv[b].y = o + 1 < len ? __ldg(kp + o + 1) : 0.0f;
+                            kxv[b].z = o + 2 < len ? __ldg(kp + o + 2) : 0.0f; kxv[b].w = o + 3 < len ? __ldg(kp + o + 3) : 0.0f;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < SCAN_BATCH; ++b) {
+                    const int o = (h + b) * SCAN_CHUNK + lane * 4;
+                    const double2 p01 = reinterpret_cast<const double2 *>(Ls + o)[0];
+                    const double p2 = Ls[o + 2];
+                    const double p_1 = o == 0 ? 0.0 : Ls[o - 1];       // tile-local exclusive prefix at the lane's first cell
+                    auto cell = [&](int j, int32_t szj, float &qj, float kxj, double before) {
+                        const int el = o + j + szj - 1;                // last cell of the upstream range, tile-local
+                        const bool inside = el < len;                  // else: crossing cell, left to k_scan_cross
+                        const float kx = KXMAP ? kxj : a.kx.value;
+                        const float omk = KXMAP ? 1.0f - kx : a.one_m_kx;
+                        if (ADV) {
+                            if (inside) qj = blend(a, tbase + o + j, (float)(Ls[el] - before), qj, kx, omk);
+                        } else {                                       // branch-free: the kernel is issue-bound
+                            const float f = (float)(Ls[inside ? el : 0] - before);
+                            const float qn = omk * f + kx * qj;        // routing.py:28
+                            qj = inside ? qn : qj;
+                        }
+                    };
+                    cell(0, sz[b].x, q[b].x, kxv[b].x, p_1);
+                    cell(1, sz[b].y, q[b].y, kxv[b].y, p01.x);
+                    cell(2, sz[b].z, q[b].z, kxv[b].z, p01.y);
+                    cell(3, sz[b].w, q[b].w, kxv[b].w, p2);
+                    if (full) {
+                        *reinterpret_cast<float4 *>(qs + o) = q[b];
+                    } else {
+                        if (o < len) qs[o] = q[b].x;
+                        if (o + 1 < len) qs[o + 1] = q[b].y;
+                        if (o + 2 < len) qs[o + 2] = q[b].z;
+                        if (o + 3 < len) qs[o + 3] = q[b].w;
+                    }
+                }
+            }
+            __syncwarp();                                      // Ls is overwritten by the next component / tile
         }
     }
 }
@@ -424,13 +443,22 @@ static int scan_prepare(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm,
 static int scan_launch_local(sphy_ctx *ctx, ScanArgs &a, cudaStream_t st)
 {
     const int resident = ctx->sm_count * SCAN_MIN_CTAS;
-    const int grid = ctx->n_tiles < resident ? ctx->n_tiles : resident;
+    const int want = (ctx->n_tiles + SCAN_WARPS - 1) / SCAN_WARPS;       // one tile per warp
+    const int grid = want < resident ? want : resident;
+    static bool smem_opt_in = false;
+    if (!smem_opt_in) {
+        SPHY_CUDA(ctx, cudaFuncSetAttribute(k_scan_main<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM));
+        SPHY_CUDA(ctx, cudaFuncSetAttribute(k_scan_main<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM));
+        SPHY_CUDA(ctx, cudaFuncSetAttribute(k_scan_main<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM));
+        SPHY_CUDA(ctx, cudaFuncSetAttribute(k_scan_main<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM));
+        smem_opt_in = true;
+    }
     if (a.adv) {
-        if (a.kx.map) k_scan_main<true, true><<<grid, SCAN_THREADS, 0, st>>>(a);
-        else k_scan_main<true, false><<<grid, SCAN_THREADS, 0, st>>>(a);
+        if (a.kx.map) k_scan_main<true, true><<<grid, SCAN_THREADS, SCAN_SMEM, st>>>(a);
+        else k_scan_main<true, false><<<grid, SCAN_THREADS, SCAN_SMEM, st>>>(a);
     } else {
-        if (a.kx.map) k_scan_main<false, true><<<grid, SCAN_THREADS, 0, st>>>(a);
-        else k_scan_main<false, false><<<grid, SCAN_THREADS, 0, st>>>(a);
+        if (a.kx.map) k_scan_main<false, true><<<grid, SCAN_THREADS, SCAN_SMEM, st>>>(a);
+        else k_scan_main<false, false><<<grid, SCAN_THREADS, SCAN_SMEM, st>>>(a);
     }
     for (int c = 0; c < a.ncomp; ++c) {
         size_t need = ctx->scan_tmp_bytes;
