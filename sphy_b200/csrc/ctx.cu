@@ -32,7 +32,7 @@ extern "C" void sphy_ctx_destroy(sphy_ctx *ctx)
     void *ptrs[] = {ctx->c_cidx, ctx->c_flat_active, ctx->c_down, ctx->c_order, ctx->c_pos, ctx->c_don_ptr, ctx->c_don_idx,
                     ctx->cidx, ctx->flat_active, ctx->down, ctx->level, ctx->order, ctx->level_ptr, ctx->don_ptr,
                     ctx->don_idx, ctx->indeg, ctx->nup, ctx->pos, ctx->dpos_ptr, ctx->dpos, ctx->pre, ctx->cell_canon,
-                    ctx->sub_size, ctx->cross_r, ctx->cross_ptr, ctx->end_e, ctx->end_k, ctx->end_ptr, ctx->park_before,
+                    ctx->sub_size, ctx->cross_r, ctx->cross_e, ctx->cross_ptr, ctx->end_e, ctx->end_k, ctx->end_ptr, ctx->park_before,
                     ctx->park_end, ctx->scan_tile, ctx->scan_excl, ctx->scan_tmp, ctx->cut_work, ctx->cut_ptr, ctx->acc, ctx->qsorted, ctx->pub_e, ctx->remote_k,
                     ctx->remote_rank, ctx->remote_slot,
                     ctx->ra_table, ctx->tmp_n[0], ctx->tmp_n[1], ctx->tmp_n[2], ctx->tmp_n[3]};

@@ -25,7 +25,7 @@ constexpr int SCAN_WARPS = SCAN_THREADS / 32;
 constexpr int SCAN_TILE = 1024;                        // cells per tile = one warp's unit of work
 constexpr int SCAN_CHUNK = 128;                        // 32 lanes x 4 cells
 constexpr int SCAN_CHUNKS = SCAN_TILE / SCAN_CHUNK;
-constexpr int SCAN_BATCH = 4;                          // chunks whose phase-2 loads are in flight together
+constexpr int SCAN_BATCH = 2;                          // chunks whose phase-2 loads are in flight together
 constexpr int SCAN_MIN_CTAS = 3;                       // 3 x 64 KB of shared memory per SM
 constexpr int SCAN_SMEM = SCAN_WARPS * SCAN_TILE * (int)sizeof(double);
 
@@ -36,6 +36,7 @@ struct ScanArgs {
     const int32_t *sub_size;
     // static crossing lists (see build_cross_lists)
     const int32_t *cross_r, *cross_ptr;   // crossing cells sorted by index; per-tile ranges
+    const int32_t *cross_e;               // last cell of each crossing cell's upstream range
     const int32_t *end_e, *end_k, *end_ptr;   // their range ends sorted by index, the owning list slot, per-tile ranges
     int32_t n_cross;
     double *park_before;                  // [ncomp][n_cross] tile-local exclusive prefix at the crossing cell
@@ -62,6 +63,10 @@ struct ScanArgs {
     int32_t ntiles;
 };
 
+// shared-memory slot of tile-local cell i: within each 128-cell chunk the prefix is stored transposed (cell 4*lane+j of
+// the chunk at j*32 + lane), so that the per-lane accesses of both phases are bank-conflict free
+__device__ __forceinline__ int ls_slot(int i) { return (i & ~127) | ((i & 3) << 5) | ((i >> 2) & 31); }
+
 // recession blend of one cell: routing.py:28, or advanced_routing.py:31-37 on a lake/reservoir network
 __device__ __forceinline__ float blend(const ScanArgs &a, int64_t cell, float f, float qold, float kx, float omk)
 {
@@ -87,7 +92,31 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_MIN_CTAS) k_scan_main(const
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *Ls = scan_smem + warp * SCAN_TILE;
     const int32_t nw = gridDim.x * SCAN_WARPS;
-    for (int32_t t = blockIdx.x * SCAN_WARPS + warp; t < a.ntiles; t += nw) {
+    int32_t t = blockIdx.x * SCAN_WARPS + warp;
+    if (t >= a.ntiles) return;
+
+    // the material of tile tt, component cc: 8 x 128-bit loads per lane, all in flight together
+    auto load_x = [&](int32_t tt, int cc, float4 (&x)[SCAN_CHUNKS]) {
+        const int64_t tb = (int64_t)tt * SCAN_TILE;
+        const float *m = a.m[cc] + tb;
+        const int ln = (int)min((int64_t)SCAN_TILE, a.n - tb);
+        if (ln == SCAN_TILE) {
+#pragma unroll
+            for (int i = 0; i < SCAN_CHUNKS; ++i) x[i] = __ldg(reinterpret_cast<const float4 *>(m) + i * 32 + lane);
+        } else {
+#pragma unroll
+            for (int i = 0; i < SCAN_CHUNKS; ++i) {
+                const int o = i * SCAN_CHUNK + lane * 4;
+                x[i].x = o < ln ? __ldg(m + o) : 0.0f;
+                x[i].y = o + 1 < ln ? __ldg(m + o + 1) : 0.0f;
+                x[i].z = o + 2 < ln ? __ldg(m + o + 2) : 0.0f;
+                x[i].w = o + 3 < ln ? __ldg(m + o + 3) : 0.0f;
+            }
+        }
+    };
+    float4 x[SCAN_CHUNKS];
+    load_x(t, 0, x);
+    for (; t < a.ntiles; t += nw) {
         const int64_t tbase = (int64_t)t * SCAN_TILE;
         const int len = (int)min((int64_t)SCAN_TILE, a.n - tbase);   // cells in this tile
         const bool full = len == SCAN_TILE;
@@ -96,23 +125,35 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_MIN_CTAS) k_scan_main(const
         const int32_t eb = __ldg(a.end_ptr + t), ee = __ldg(a.end_ptr + t + 1);
         int32_t kb = 0, ke = 0;
         if (ADV) { kb = __ldg(a.cut_ptr + t); ke = __ldg(a.cut_ptr + t + 1); }
+        const int32_t *szp = a.sub_size + tbase;
         for (int c = 0; c < a.ncomp; ++c) {
-            // ---- phase 1: float64 inclusive prefix of the tile's material -> Ls
-            const float *m = a.m[c] + tbase;
-            float4 x[SCAN_CHUNKS];
-            if (full) {
+            float *qs = a.qstate[c] + tbase;
+            int4 sz[SCAN_BATCH];
+            float4 q[SCAN_BATCH], kxv[SCAN_BATCH];
+            // sub_size / Qold / kx of SCAN_BATCH chunks starting at chunk h
+            auto load_batch = [&](int h) {
 #pragma unroll
-                for (int i = 0; i < SCAN_CHUNKS; ++i) x[i] = __ldg(reinterpret_cast<const float4 *>(m) + i * 32 + lane);
-            } else {
-#pragma unroll
-                for (int i = 0; i < SCAN_CHUNKS; ++i) {
-                    const int o = i * SCAN_CHUNK + lane * 4;
-                    x[i].x = o < len ? __ldg(m + o) : 0.0f;
-                    x[i].y = o + 1 < len ? __ldg(m + o + 1) : 0.0f;
-                    x[i].z = o + 2 < len ? __ldg(m + o + 2) : 0.0f;
-                    x[i].w = o + 3 < len ? __ldg(m + o + 3) : 0.0f;
+                for (int b = 0; b < SCAN_BATCH; ++b) {
+                    const int o = (h + b) * SCAN_CHUNK + lane * 4;
+                    if (full) {
+                        sz[b] = __ldg(reinterpret_cast<const int4 *>(szp + o));
+                        q[b] = *reinterpret_cast<const float4 *>(qs + o);
+                        if (KXMAP) kxv[b] = __ldg(reinterpret_cast<const float4 *>(a.kx.map + tbase + o));
+                    } else {
+                        sz[b].x = o < len ? __ldg(szp + o) : 1;         q[b].x = o < len ? qs[o] : 0.0f;
+                        sz[b].y = o + 1 < len ? __ldg(szp + o + 1) : 1; q[b].y = o + 1 < len ? qs[o + 1] : 0.0f;
+                        sz[b].z = o + 2 < len ? __ldg(szp + o + 2) : 1; q[b].z = o + 2 < len ? qs[o + 2] : 0.0f;
+                        sz[b].w = o + 3 < len ? __ldg(szp + o + 3) : 1; q[b].w = o + 3 < len ? qs[o + 3] : 0.0f;
+                        if (KXMAP) {
+                            const float *kp = a.kx.map + tbase;
+                            kxv[b].x = o < len ? __ldg(kp + o) : 0.0f;         kxv[b].y = o + 1 < len ? __ldg(kp + o + 1) : 0.0f;
+                            kxv[b].z = o + 2 < len ? __ldg(kp + o + 2) : 0.0f; kxv[b].w = o + 3 < len ? __ldg(kp + o + 3) : 0.0f;
+                        }
+                    }
                 }
-            }
+            };
+            load_batch(0);                                     // in flight while phase 1 computes
+            // ---- phase 1: float64 inclusive prefix of the tile's material -> Ls
             double carry = 0.0;
 #pragma unroll
             for (int i = 0; i < SCAN_CHUNKS; ++i) {
@@ -141,70 +182,52 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_MIN_CTAS) k_scan_main(const
                 double excl = __shfl_up_sync(0xffffffffu, s, 1);
                 excl = (lane == 0 ? 0.0 : excl) + carry;
                 v0 += excl; v1 += excl; v2 += excl; v3 += excl;
-                reinterpret_cast<double2 *>(Ls + o)[0] = make_double2(v0, v1);
-                reinterpret_cast<double2 *>(Ls + o)[1] = make_double2(v2, v3);
+                double *row = Ls + i * SCAN_CHUNK + lane;      // transposed within the chunk, see ls_slot()
+                row[0] = v0; row[32] = v1; row[64] = v2; row[96] = v3;
                 carry = __shfl_sync(0xffffffffu, v3, 31);
             }
+            // the next material this warp will scan: in flight during parking and phase 2
+            if (c + 1 < a.ncomp) load_x(t, c + 1, x);
+            else if (t + nw < a.ntiles) load_x(t + nw, 0, x);
             __syncwarp();
             // ---- park what the crossing cells of / ending in this tile will need
             if (ce > cb || ee > eb) {
                 double *pb = a.park_before + (int64_t)c * a.n_cross, *pe = a.park_end + (int64_t)c * (a.n_cross + a.n_pub);
                 for (int32_t k = cb + lane; k < ce; k += 32) {
                     const int off = __ldg(a.cross_r + k) - tb32;
-                    pb[k] = off == 0 ? 0.0 : Ls[off - 1];
+                    pb[k] = off == 0 ? 0.0 : Ls[ls_slot(off - 1)];
                 }
-                for (int32_t j = eb + lane; j < ee; j += 32) pe[__ldg(a.end_k + j)] = Ls[__ldg(a.end_e + j) - tb32];
+                for (int32_t j = eb + lane; j < ee; j += 32) pe[__ldg(a.end_k + j)] = Ls[ls_slot(__ldg(a.end_e + j) - tb32)];
             }
             if (lane == 0) a.tile_tot[(int64_t)c * (a.ntiles + 1) + t] = carry;
             // ---- phase 2: range sums of the cells whose range ends inside the tile, blended with Qold
-            const int32_t *szp = a.sub_size + tbase;
-            float *qs = a.qstate[c] + tbase;
 #pragma unroll
             for (int h = 0; h < SCAN_CHUNKS; h += SCAN_BATCH) {
-                int4 sz[SCAN_BATCH];
-                float4 q[SCAN_BATCH], kxv[SCAN_BATCH];
+                if (h > 0) load_batch(h);
 #pragma unroll
                 for (int b = 0; b < SCAN_BATCH; ++b) {
                     const int o = (h + b) * SCAN_CHUNK + lane * 4;
-                    if (full) {
-                        sz[b] = __ldg(reinterpret_cast<const int4 *>(szp + o));
-                        q[b] = *reinterpret_cast<const float4 *>(qs + o);
-                        if (KXMAP) kxv[b] = __ldg(reinterpret_cast<const float4 *>(a.kx.map + tbase + o));
-                    } else {
-                        sz[b].x = o < len ? __ldg(szp + o) : 1;         q[b].x = o < len ? qs[o] : 0.0f;
-                        sz[b].y = o + 1 < len ? __ldg(szp + o + 1) : 1; q[b].y = o + 1 < len ? qs[o + 1] : 0.0f;
-                        sz[b].z = o + 2 < len ? __ldg(szp + o + 2) : 1; q[b].z = o + 2 < len ? qs[o + 2] : 0.0f;
-                        sz[b].w = o + 3 < len ? __ldg(szp + o + 3) : 1; q[b].w = o + 3 < len ? qs[o + 3] : 0.0f;
-                        if (KXMAP) {
-                            const float *kp = a.kx.map + tbase;
-                            kxv[b].x = o < len ? __ldg(kp + o) : 0.0f;         kxv[b].y = o + 1 < len ? __ldg(kp + o + 1) : 0.0f;
-                            kxv[b].z = o + 2 < len ? __ldg(kp + o + 2) : 0.0f; kxv[b].w = o + 3 < len ? __ldg(kp + o + 3) : 0.0f;
-                        }
-                    }
-                }
-#pragma unroll
-                for (int b = 0; b < SCAN_BATCH; ++b) {
-                    const int o = (h + b) * SCAN_CHUNK + lane * 4;
-                    const double2 p01 = reinterpret_cast<const double2 *>(Ls + o)[0];
-                    const double p2 = Ls[o + 2];
-                    const double p_1 = o == 0 ? 0.0 : Ls[o - 1];       // tile-local exclusive prefix at the lane's first cell
-                    auto cell = [&](int j, int32_t szj, float &qj, float kxj, double before) {
+                    const double *row = Ls + (h + b) * SCAN_CHUNK + lane;
+                    const double p0 = row[0], p1 = row[32], p2 = row[64], p3 = row[96];   // own inclusive prefixes
+                    const double p_1 = o == 0 ? 0.0 : (lane == 0 ? row[-1] : row[95]);     // the cell before the lane's first
+                    auto cell = [&](int j, int32_t szj, float &qj, float kxj, double before, double own) {
                         const int el = o + j + szj - 1;                // last cell of the upstream range, tile-local
                         const bool inside = el < len;                  // else: crossing cell, left to k_scan_cross
                         const float kx = KXMAP ? kxj : a.kx.value;
                         const float omk = KXMAP ? 1.0f - kx : a.one_m_kx;
+                        double pe = own;                               // headwater cell: the range is the cell itself
+                        if (inside && szj > 1) pe = Ls[ls_slot(el)];   // predicated load: fewer lanes, fewer bank conflicts
                         if (ADV) {
-                            if (inside) qj = blend(a, tbase + o + j, (float)(Ls[el] - before), qj, kx, omk);
-                        } else {                                       // branch-free: the kernel is issue-bound
-                            const float f = (float)(Ls[inside ? el : 0] - before);
-                            const float qn = omk * f + kx * qj;        // routing.py:28
+                            if (inside) qj = blend(a, tbase + o + j, (float)(pe - before), qj, kx, omk);
+                        } else {
+                            const float qn = omk * (float)(pe - before) + kx * qj;        // routing.py:28
                             qj = inside ? qn : qj;
                         }
                     };
-                    cell(0, sz[b].x, q[b].x, kxv[b].x, p_1);
-                    cell(1, sz[b].y, q[b].y, kxv[b].y, p01.x);
-                    cell(2, sz[b].z, q[b].z, kxv[b].z, p01.y);
-                    cell(3, sz[b].w, q[b].w, kxv[b].w, p2);
+                    cell(0, sz[b].x, q[b].x, kxv[b].x, p_1, p0);
+                    cell(1, sz[b].y, q[b].y, kxv[b].y, p0, p1);
+                    cell(2, sz[b].z, q[b].z, kxv[b].z, p1, p2);
+                    cell(3, sz[b].w, q[b].w, kxv[b].w, p2, p3);
                     if (full) {
                         *reinterpret_cast<float4 *>(qs + o) = q[b];
                     } else {
@@ -226,7 +249,7 @@ __global__ void __launch_bounds__(256) k_scan_cross(const __grid_constant__ Scan
     const int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= a.n_cross) return;
     const int64_t r = __ldg(a.cross_r + k);
-    const int64_t e = r + __ldg(a.sub_size + r) - 1;
+    const int64_t e = __ldg(a.cross_e + k);
     const int32_t ta = (int32_t)(r / SCAN_TILE), te = (int32_t)(e / SCAN_TILE);
     const float kx = a.kx.map ? __ldg(a.kx.map + r) : a.kx.value;
     const float omk = a.kx.map ? 1.0f - kx : a.one_m_kx;
@@ -287,11 +310,12 @@ __global__ void k_cross_flag(const int32_t *sub_size, int64_t n, uint8_t *flag)
 // sort keys of the "end" list: range ends of the crossing cells (INT32_MAX = ends on another rank: sorted last and
 // cut off), followed by the positions published for other ranks (slots n_cross + j)
 __global__ void k_cross_ends(const int32_t *cross_r, const int32_t *sub_size, int32_t nc, int64_t n, const int32_t *pub_e,
-                             int32_t n_pub, int32_t *e, int32_t *k)
+                             int32_t n_pub, int32_t *e, int32_t *k, int32_t *cross_e)
 {
     int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nc) {
         const int64_t end = (int64_t)cross_r[i] + sub_size[cross_r[i]] - 1;
+        cross_e[i] = (int32_t)end;                 // < 2^31: sub_size is int32 over the whole basin
         e[i] = end < n ? (int32_t)end : INT32_MAX;
         k[i] = i;
     } else if (i < nc + n_pub) {
@@ -345,7 +369,8 @@ static int build_cross_lists(sphy_ctx *ctx, cudaStream_t st)
     const size_t ncs = nc > 0 ? (size_t)nc : 1, nes = nend_all > 0 ? (size_t)nend_all : 1;
     int rc = SPHY_OK;
     if (e == cudaSuccess &&
-        ((rc = dev_alloc(ctx, &ctx->cross_r, ncs)) || (rc = dev_alloc(ctx, &ctx->cross_ptr, (size_t)ntiles + 1)) ||
+        ((rc = dev_alloc(ctx, &ctx->cross_r, ncs)) || (rc = dev_alloc(ctx, &ctx->cross_e, ncs)) ||
+         (rc = dev_alloc(ctx, &ctx->cross_ptr, (size_t)ntiles + 1)) ||
          (rc = dev_alloc(ctx, &ctx->end_e, nes)) || (rc = dev_alloc(ctx, &ctx->end_k, nes)) ||
          (rc = dev_alloc(ctx, &ctx->end_ptr, (size_t)ntiles + 1)))) {
         cudaFree(flag); cudaFree(sel); cudaFree(nsel); cudaFree(tmp);
@@ -356,7 +381,7 @@ static int build_cross_lists(sphy_ctx *ctx, cudaStream_t st)
         FK(cudaMalloc(&e_in, sizeof(int32_t) * nend_all));
         FK(cudaMalloc(&k_in, sizeof(int32_t) * nend_all));
         if (e == cudaSuccess) {
-            k_cross_ends<<<div_up(nend_all, 256), 256, 0, st>>>(ctx->cross_r, ctx->sub_size_loc, nc, n, ctx->pub_e, ctx->n_pub, e_in, k_in);
+            k_cross_ends<<<div_up(nend_all, 256), 256, 0, st>>>(ctx->cross_r, ctx->sub_size_loc, nc, n, ctx->pub_e, ctx->n_pub, e_in, k_in, ctx->cross_e);
             size_t need = 0;
             FK(cub::DeviceRadixSort::SortPairs(nullptr, need, e_in, ctx->end_e, k_in, ctx->end_k, nend_all, 0, 32, st));
             if (need > tb) { cudaFree(tmp); tmp = nullptr; FK(cudaMalloc(&tmp, need)); tb = need; }
@@ -416,6 +441,7 @@ static int scan_prepare(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm,
     }
     a.sub_size = ctx->sub_size_loc;
     a.cross_r = ctx->cross_r;
+    a.cross_e = ctx->cross_e;
     a.cross_ptr = ctx->cross_ptr;
     a.end_e = ctx->end_e;
     a.end_k = ctx->end_k;
