@@ -62,6 +62,10 @@ CASES = {
     # BASELINE config 2: snow + glacier, all components routed
     "c2_glac": (dict(nrows=12, ncols=10, seed=22, snow=True, glacier=True, rout_components=True, params=GLAC,
                      start=(2001, 4, 15), zrange=(1500.0, 5200.0)), 90),
+    # yearly glacier update (ice redistribution, fragments melting away) + per-glacier tables, modules/glacier.py:501-810
+    "c2_glac_retreat": (dict(nrows=12, ncols=10, seed=24, snow=True, glacier=True, params=dict(WETK, Toffset=12.0), start=(2001, 9, 20),
+                             zrange=(1500.0, 5200.0), glac_retreat=(30, 9),
+                             glac_vars=("FRAC_GLAC", "GlacMelt", "GlacR", "TotalSnowStore_GLAC", "GLAC_T")), 25),
     # BASELINE config 3: reservoirs (simple + advanced) and lakes
     "c3_res_lake": (dict(nrows=16, ncols=14, seed=31, cellsize=1000.0, reservoirs=True, lakes=True, n_res_simple=2,
                          n_res_adv=2, n_lakes=4, params=WET, start=(2001, 5, 1)), 70),
@@ -86,7 +90,7 @@ def build_case(name):
 
 def make(name):
     cat, nsteps = build_case(name)
-    ref = run_reference(cat, nsteps)
+    ref = run_reference(cat, nsteps, keep_table=bool(cat.glac_retreat or cat.glac_vars))
     fkeys = ("prec", "tavg", "tmin", "tmax") + (("etref",) if cat.etref_input else ()) + (("ndvi",) if cat.dynveg else ())
     forcing = {k: np.stack([cat.forcing(t)[k] for t in range(1, nsteps + 1)]) for k in fkeys}
     payload = {"meta": np.array(json.dumps(dict(case=name, nsteps=nsteps, kwargs=CASES[name][0])))}
@@ -103,6 +107,20 @@ def make(name):
             payload["repfile/" + k] = v
         for k, v in ref["tss_tables"].items():
             payload["tss/" + k] = v
+    if cat.glac_retreat or cat.glac_vars:
+        import io
+        import pandas as pd
+        for k, v in ref["report_files"].items():                  # GlacFrac_/GlacArea_/iceDepth_/vIce_<date>.map
+            if k.endswith(".map"):
+                payload["repfile/" + k] = v
+        for k, text in ref["csv_files"].items():
+            df = pd.read_csv(io.StringIO(text), index_col=None if k.startswith("glacTable") else 0)
+            payload["csv/" + k] = df.to_numpy(np.float64)
+            payload["csvcols/" + k] = np.asarray([str(c) for c in df.columns])
+        tabs = ref["glac_table"][1:]                               # after every dynamic() step
+        payload["glac/U_ID"] = tabs[0]["U_ID"].to_numpy(np.int64)  # the reference's row order (sort_values is not stable)
+        payload["glac/FRAC_GLAC"] = np.stack([t["FRAC_GLAC"].to_numpy(np.float64) for t in tabs])
+        payload["glac/ICE_DEPTH"] = np.stack([t["ICE_DEPTH"].to_numpy(np.float64) for t in tabs])
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     path = os.path.join(GOLDEN_DIR, name + ".npz")
     np.savez_compressed(path, **payload)

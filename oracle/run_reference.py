@@ -9,6 +9,7 @@ under tests/golden/ by `oracle/make_golden.py`.
 from __future__ import annotations
 
 import contextlib
+import glob
 import io
 import os
 import runpy
@@ -171,6 +172,11 @@ def run_reference(cat, nsteps=None, dtype=np.float32, keep_table=False, quiet=Tr
         base = os.path.basename(name)
         for t, arr in per_t.items():
             result["report_files"][base if t is None else stack_name(base, t)] = np.asarray(arr, np.float32)
+    # tables the reference wrote with pandas (per-glacier reporting, glacier table after the yearly update)
+    result["csv_files"] = {}
+    for path in sorted(glob.glob(os.path.join(out, "*.csv"))):
+        with open(path) as fh:
+            result["csv_files"][os.path.basename(path)] = fh.read()
     result["tss_tables"] = {k: np.array([[t] + list(v) for t, v in rows], np.float64) for k, rows in result["tss"].items()}
     if keep_table:
         result["glac_table"] = tables

@@ -131,6 +131,8 @@ class Catchment:
     report_daily: tuple = ()
     pws: bool = False                    # plant water stress (ET.ks, PWS_FLAG)
     report_opts: dict = field(default_factory=dict)   # reporting.csv: name -> (map, avg, timeseries) option strings
+    glac_retreat: tuple | None = None    # (day, month) of the yearly glacier update (GlacRetreat = 1, glacier.py:562-736)
+    glac_vars: tuple = ()                # per-glacier reporting (GlacID_flag = 1, glacier.py:501-559): GlacTable columns
     dynveg: bool = False                 # DynVegFLAG = 1: NDVI map series -> Kc, LAI, canopy interception (modules/dynamic_veg.py)
     etref_input: bool = False            # ETREF_FLAG = 1: ETref map series instead of Hargreaves (sphy.py:814)
     mask: np.ndarray | None = None       # clone mask (True = inside the catchment); None = the whole rectangle
@@ -363,11 +365,11 @@ GlacID = GLAC_ID.map
 DDFG = {p['DDFG']}
 DDFDG = {p['DDFDG']}
 GlacF = {p['GlacF']}
-GlacID_flag = 0
-GlacVars = FRAC_GLAC,GlacMelt
-GlacRetreat = 0
-GlacID_memerror = 1
-GlacUpdate = 30,9
+GlacID_flag = {1 if self.glac_vars else 0}
+GlacVars = {",".join(self.glac_vars) if self.glac_vars else "FRAC_GLAC,GlacMelt"}
+GlacRetreat = {1 if self.glac_retreat else 0}
+GlacID_memerror = {0 if self.glac_vars else 1}
+GlacUpdate = {"%d,%d" % tuple(self.glac_retreat) if self.glac_retreat else "30,9"}
 TLapse = tlapse.tbl
 [SNOW]
 TCrit = {p['Tcrit']}
@@ -474,7 +476,8 @@ def make_catchment(nrows, ncols, cellsize=250.0, seed=1, nsteps=365, snow=False,
                    reservoirs=False, lakes=False, ground=True, routing=True, infil_excess=0,
                    rout_components=False, outlets="single", start=datetime.date(2001, 1, 1),
                    n_res_simple=0, n_res_adv=0, n_lakes=0, open_water=False, params=None,
-                   report_daily=(), soil_classes=1, zrange=None, pws=False, report_opts=None, etref_input=False, mask=None, dynveg=False):
+                   report_daily=(), soil_classes=1, zrange=None, pws=False, report_opts=None, etref_input=False, mask=None, dynveg=False,
+                   glac_retreat=None, glac_vars=()):
     """Build one of the BASELINE.json synthetic configurations."""
     p = dict(DEFAULT_PARAMS)
     if params:
@@ -519,6 +522,15 @@ def make_catchment(nrows, ncols, cellsize=250.0, seed=1, nsteps=365, snow=False,
         cat.locations = np.where(inside, cat.locations, 0).astype(np.int32)
     if glacier:
         _add_glaciers(cat, rng)
+        cat.glac_vars = tuple(glac_vars)
+        if glac_retreat:
+            cat.glac_retreat = tuple(glac_retreat)
+            # thin ice on every fifth fragment so that some of them melt away at the update (glacier.py:713-719)
+            r2 = np.random.default_rng([seed, 991])
+            depth = cat.glac_table["ICE_DEPTH"].astype(np.float64)
+            thin = r2.random(depth.size) < 0.2
+            depth[thin] = r2.uniform(0.005, 0.12, size=int(thin.sum()))
+            cat.glac_table["ICE_DEPTH"] = depth
     if reservoirs or lakes:
         _add_reservoirs_lakes(cat, rng, nup, n_res_simple if reservoirs else 0, n_res_adv if reservoirs else 0,
                               n_lakes if lakes else 0)
