@@ -138,6 +138,10 @@ typedef struct {                     /* forcing maps of the day (sphy.py:755-809
     const float *prec, *tavg, *tmin, *tmax, *etref;
     /* glacier aggregates of the day from sphy_glac_step (NULL when GlacFLAG = 0) */
     const float *TotalSnowStore_GLAC, *SnowR_GLAC, *GlacPerc, *GlacR;
+    /* water balance diagnostics of a GlacRetreat = 1 run (sphy.py:1114-1146), all optional: the frozen oldGw map, the
+     * glacier snow store that leaves TotalSnowStore on the update day, (iceDepth - oldIceDepth) in mm on that day, the new
+     * GlacFrac map on the day after (the soil-storage term of dS uses it while the physics of that day used the old one) */
+    const float *wbal_old_gw, *wbal_snow_adjust, *wbal_ice_delta, *wbal_glac_frac;
 } sphy_wb_forcing;
 
 typedef struct {                     /* outputs; every pointer except TotR may be NULL */
@@ -240,6 +244,12 @@ typedef struct {                     /* per-cell aggregates (REAL4, written only
 
 int sphy_glac_step(sphy_ctx *ctx, const sphy_glac_table *t, const float *tavg, const float *prec, float tcorr,
                    float pcorr, const sphy_glac_out *o, void *stream);
+
+/* Per-glacier daily tables (glacier.dynamic_reporting, modules/glacier.py:501-533): FRAC_GLAC-weighted average of up to 16
+ * float64 table columns over the fragments of each glacier id (`row[row_ptr[g] .. row_ptr[g+1])`), written as REAL4
+ * to out[v * n_glac + g]; columns flagged in `is_frac` report the summed fraction instead (the FRAC_GLAC column). */
+int sphy_glac_report(sphy_ctx *ctx, int32_t n_glac, const int32_t *row_ptr, const int32_t *row, const double *frac,
+                     int32_t n_vars, const double *const *cols, const uint8_t *is_frac, float *out, void *stream);
 
 /* ---- K4: flow routing ------------------------------------------------------------------------
  * replaces routing.ROUT / routing.dynamic (modules/routing.py:25-29,70-116):

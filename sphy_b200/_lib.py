@@ -43,7 +43,7 @@ class WbState(C.Structure):
 
 class WbForcing(C.Structure):
     _fields_ = [(k, P) for k in ("prec", "tavg", "tmin", "tmax", "etref", "TotalSnowStore_GLAC", "SnowR_GLAC",
-                                 "GlacPerc", "GlacR")]
+                                 "GlacPerc", "GlacR", "wbal_old_gw", "wbal_snow_adjust", "wbal_ice_delta", "wbal_glac_frac")]
 
 
 class WbOut(C.Structure):
@@ -116,6 +116,7 @@ SYMBOLS = {
     "sphy_set_ncells": (C.c_int, [P, C.c_int64]),
     "sphy_module_op": (C.c_int, [P, C.c_int, C.POINTER(SphyParam), C.c_int, C.POINTER(P), C.c_int, C.c_int64, C.c_float, C.c_int, P]),
     "sphy_scan_tile_cells": (C.c_int, []),
+    "sphy_glac_report": (C.c_int, [P, C.c_int32, P, P, P, C.c_int32, P, P, P, P]),
     "sphy_veg_step": (C.c_int, [P, C.POINTER(WbParams), C.POINTER(Veg), C.c_int, P]),
     "sphy_wb_step": (C.c_int, [P, C.POINTER(WbParams), C.POINTER(WbState), C.POINTER(WbForcing), C.POINTER(WbOut),
                                C.c_int, P]),

@@ -97,3 +97,62 @@ extern "C" int sphy_glac_step(sphy_ctx *ctx, const sphy_glac_table *t, const flo
     SPHY_LAUNCH_CHECK(ctx);
     return SPHY_OK;
 }
+
+// ---- per-glacier daily tables (glacier.dynamic_reporting, modules/glacier.py:501-533) ------------------------------
+// FRAC_GLAC-weighted average of table columns over the fragments of every glacier id: one warp per glacier, float64
+// sums, REAL4 results (the reference casts the day's row with astype(float32)); 0 where the summed fraction is 0.
+namespace {
+
+constexpr int GLAC_REPORT_MAX_VARS = 16;
+struct GlacReportArgs {
+    const double *col[GLAC_REPORT_MAX_VARS];
+    uint8_t is_frac[GLAC_REPORT_MAX_VARS];   // the FRAC_GLAC column reports the summed fraction itself
+    int n_vars, n_glac;
+    const int32_t *row_ptr, *row;            // fragments of glacier g: row[row_ptr[g] .. row_ptr[g+1])
+    const double *frac;
+    float *out;                              // [n_vars][n_glac]
+};
+
+__global__ void k_glac_report(const __grid_constant__ GlacReportArgs a)
+{
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (g >= a.n_glac) return;
+    const int b = a.row_ptr[g], e = a.row_ptr[g + 1];
+    double fs = 0.0;
+    for (int k = b + lane; k < e; k += 32) fs += a.frac[a.row[k]];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) fs += __shfl_xor_sync(0xffffffffu, fs, d);
+    for (int v = 0; v < a.n_vars; ++v) {
+        double s = 0.0;
+        for (int k = b + lane; k < e; k += 32) {
+            const int r = a.row[k];
+            s += a.col[v][r] * a.frac[r];
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+        if (lane == 0) {
+            const double q = a.is_frac[v] ? fs : s / fs;
+            a.out[(size_t)v * a.n_glac + g] = (q != q) ? 0.0f : (float)q;          // fillna(0.0), glacier.py:524
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int sphy_glac_report(sphy_ctx *ctx, int32_t n_glac, const int32_t *row_ptr, const int32_t *row, const double *frac,
+                                int32_t n_vars, const double *const *cols, const uint8_t *is_frac, float *out, void *stream)
+{
+    if (!ctx || n_glac < 0 || n_vars < 0 || n_vars > GLAC_REPORT_MAX_VARS) return SPHY_E_INVALID;
+    if (n_glac == 0 || n_vars == 0) return SPHY_OK;
+    if (!row_ptr || !row || !frac || !cols || !is_frac || !out) SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_glac_report: null argument");
+    GlacReportArgs a = {};
+    for (int v = 0; v < n_vars; ++v) {
+        if (!cols[v]) SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_glac_report: null column %d", v);
+        a.col[v] = cols[v];
+        a.is_frac[v] = is_frac[v];
+    }
+    a.n_vars = n_vars; a.n_glac = n_glac; a.row_ptr = row_ptr; a.row = row; a.frac = frac; a.out = out;
+    k_glac_report<<<div_up((int64_t)n_glac * 32, 128), 128, 0, (cudaStream_t)stream>>>(a);
+    SPHY_LAUNCH_CHECK(ctx);
+    return SPHY_OK;
+}

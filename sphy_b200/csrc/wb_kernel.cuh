@@ -293,11 +293,21 @@ __device__ __forceinline__ void wb_cells(const WbArgs &a, int64_t i)
         // ---- water balance, sphy.py:1114-1212 (GlacRetreat = 0 branches) ----------------------------------
         if (DIAG && (a.o.wbal || a.s.waterbalanceTot)) {
             float dS = (rw - RW.v[j]) + (sw - SW.v[j]);
-            if (has_glac) dS = dS * omg;
+            // the day after a glacier update the reference forms dS with the NEW GlacFrac map (glacier.py:766, sphy.py:1137)
+            if (a.f.wbal_glac_frac && i + j < a.n) dS = dS * (one - __ldg(a.f.wbal_glac_frac + i + j));
+            else if (has_glac) dS = dS * omg;
             float wb;
             if (GROUND) {
-                dS = dS + (gw - Gw.v[j]);
-                if (SNOW) dS = dS + (tss - OldTotalSnowStore);
+                const bool live = i + j < a.n;
+                // GlacRetreat = 1 (sphy.py:1114-1146): oldGw is never advanced, the glacier snow store leaves
+                // TotalSnowStore on the update day before dS is formed, and the ice-depth change joins dS
+                const float old_gw = (a.f.wbal_old_gw && live) ? __ldg(a.f.wbal_old_gw + i + j) : Gw.v[j];
+                dS = dS + (gw - old_gw);
+                if (SNOW) {
+                    const float tss_now = (a.f.wbal_snow_adjust && live) ? tss - __ldg(a.f.wbal_snow_adjust + i + j) : tss;
+                    dS = dS + (tss_now - OldTotalSnowStore);
+                }
+                if (a.f.wbal_ice_delta && live) dS = dS + __ldg(a.f.wbal_ice_delta + i + j);
                 wb = (((Precip - ActETact) - baser) - RainR) - SnowR;
                 if (glac_in) wb = wb - g_r.v[j];
                 wb = wb - dS;

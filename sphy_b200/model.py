@@ -600,10 +600,13 @@ class SphyModel:
         lapse = pd.read_csv(os.path.join(self.inpath, cfg.get("GLACIER", "TLapse")), header=None, index_col=0, sep=" ",
                             skipinitialspace=True)
         self.TLapse = lapse.iloc[:, 0].astype(float)
-        if cfg.getint("GLACIER", "GlacRetreat") == 1:
-            raise NotImplementedError("glacier retreat is a yearly table update outside the daily hot path (SURVEY.md 8f)")
         d64 = lambda a: self._dev(np.asarray(a, np.float64))  # noqa: E731
         n_rows = len(mod)
+        self._glac_host = {k: tab[k].to_numpy() for k in ("U_ID", "MOD_ID", "GLAC_ID", "MOD_H", "GLAC_H", "DEBRIS")}
+        self._glac_host["ICE_DEPTH"] = (tab["ICE_DEPTH"].to_numpy().astype(np.float64) if "ICE_DEPTH" in tab.columns
+                                        else np.zeros(n_rows))
+        self._glac_seg = np.repeat(np.arange(len(uniq)), np.diff(seg_ptr))                    # model-cell group of each row
+        self._glac_seg_cell = seg_cell
         z64 = lambda: torch.zeros(n_rows, dtype=torch.float64, device=self.device)  # noqa: E731
         G = {"cell": self._dev(cell.astype(np.int32)), "seg_ptr": self._dev(seg_ptr), "seg_cell": self._dev(seg_cell),
              "MOD_H": d64(tab["MOD_H"]), "GLAC_H": d64(tab["GLAC_H"]), "FRAC_GLAC": d64(tab["FRAC_GLAC"]),
@@ -624,6 +627,145 @@ class SphyModel:
                                                        "TotalSnowStore_GLAC", "SnowR_GLAC", "GlacMelt", "GlacR", "GlacPerc")}
         self.GlacR = self._glac_agg["GlacR"]
         self.TotalSnowStore_GLAC = self._glac_agg["TotalSnowStore_GLAC"]
+        self._glacier_reporting_initial(tab)
+
+    def _glacier_reporting_initial(self, tab):
+        """glacier.init / initial, the parts behind dynamic_reporting (modules/glacier.py:84-110,146-154,208-252)."""
+        cfg, G = self.config, self.GlacTable
+        self.glac_files = {}                       # name -> array / DataFrame of everything written around an update
+        self.GlacID_flag = cfg.getint("GLACIER", "GlacID_flag")
+        self.GlacVars = [v.strip() for v in cfg.get("GLACIER", "GlacVars").split(",") if v.strip()]
+        self.GlacRetreat = cfg.getint("GLACIER", "GlacRetreat")
+        self.dateAfterUpdate = None
+        self._glac_wbal = None
+        G["ICE_DEPTH"] = self._dev(self._glac_host["ICE_DEPTH"])
+        self._glac_emit({"GlacFrac_" + self.startdate.strftime("%Y%m%d") + ".map": self.GlacFrac.cpu().numpy()})   # glacier.py:196-199
+        if self.GlacID_flag:
+            gid = self._glac_host["GLAC_ID"]
+            self.glacid = sorted(np.unique(gid).tolist())
+            rows = np.argsort(gid, kind="stable").astype(np.int32)
+            ptr = np.searchsorted(gid[rows], self.glacid + [self.glacid[-1] + 1]).astype(np.int32)
+            known = {k: v for k, v in G.items() if v.dtype == torch.float64}
+            missing = [v for v in self.GlacVars if v not in known]
+            if missing or len(self.GlacVars) > 16:
+                raise NotImplementedError(f"GlacVars {missing} are not kept on the device; available: {sorted(known)} (at most 16)")
+            ndays = (self.enddate - self.startdate).days + 1
+            nv, ng = len(self.GlacVars), len(self.glacid)
+            self._glac_rep = dict(rows=self._dev(rows), ptr=self._dev(ptr), nv=nv, ng=ng,
+                                  cols=(C.c_void_p * nv)(*[known[v].data_ptr() for v in self.GlacVars]),
+                                  is_frac=(C.c_uint8 * nv)(*[int(v == "FRAC_GLAC") for v in self.GlacVars]),
+                                  out=torch.zeros((ndays, nv, ng), dtype=torch.float32, device=self.device))
+        if self.GlacRetreat == 1:
+            day, month = (int(x) for x in cfg.get("GLACIER", "GlacUpdate").split(","))
+            self.GlacUpdate = {"month": month, "day": day}
+            frac, ice = tab["FRAC_GLAC"].to_numpy().astype(np.float64), self._glac_host["ICE_DEPTH"]
+            ice_map = self._by_model_cell(ice * frac)
+            area_map = self._by_model_cell(frac * float(self.cellArea))
+            tag = self.startdate.strftime("%Y%m%d")
+            self._glac_emit({"GlacArea_" + tag + ".map": area_map, "iceDepth_" + tag + ".map": ice_map,
+                             "vIce_" + tag + ".map": ice_map * area_map})
+            self._old_ice_mm = ice_map * f32(1000)                                             # glacier.py:241
+            self._ice_delta = self._full(0.0)
+
+    def _by_model_cell(self, col):
+        """groupby(MOD_ID).sum() of a float64 table column (pandas: NaN skipped) scattered to the cells as REAL4."""
+        import pandas as pd
+        sums = pd.Series(np.asarray(col, np.float64)).groupby(self._glac_seg).sum().to_numpy()
+        out = np.zeros(self.n, np.float64)
+        out[self._glac_seg_cell] = sums
+        return out.astype(np.float32)
+
+    def _glac_emit(self, files):
+        """Keep (and, with write_outputs, write) the maps / tables glacier.py reports outside reporting.csv."""
+        from . import csf
+        self.glac_files.update(files)
+        if not self.write_outputs:
+            return
+        os.makedirs(self.outpath, exist_ok=True)
+        for name, v in files.items():
+            path = os.path.join(self.outpath, name)
+            if name.endswith(".csv"):
+                v.to_csv(path, index=False)
+            else:
+                csf.write_map(path, self.to_raster(torch.from_numpy(np.ascontiguousarray(v))), cellsize=self.cellsize or 1.0)
+
+    def _glacier_reporting(self, F):
+        """glacier.dynamic_reporting (modules/glacier.py:501-810).  It only depends on the fragment table as sphy_glac_step
+        left it, so it runs BEFORE the water-balance kernel; what the reference applies to cell maps afterwards
+        (TotalSnowStore on the update day, GlacFrac the day after) is returned as a list of deferred actions."""
+        import pandas as pd
+        G, after = self.GlacTable, []
+        if self.GlacID_flag:                                                                   # glacier.py:503-533
+            r = self._glac_rep
+            day = (self.curdate - self.startdate).days
+            self._ck(self.lib.sphy_glac_report(self._ctx, r["ng"], r["ptr"].data_ptr(), r["rows"].data_ptr(),
+                                               G["FRAC_GLAC"].data_ptr(), r["nv"], r["cols"], r["is_frac"],
+                                               r["out"][day].data_ptr(), self._stream()), "sphy_glac_report")
+            if self.curdate == self.enddate and self.write_outputs:                           # glacier.py:534-538
+                os.makedirs(self.outpath, exist_ok=True)
+                for v, tbl in self.glacier_tables().items():
+                    tbl.to_csv(os.path.join(self.outpath, v + ".csv"))
+        if self.GlacRetreat != 1:
+            return after
+        if self._glac_wbal is None:                                                            # sphy.py:1114-1146: oldGw never advances
+            self._glac_wbal = self.Gw.clone()
+        F.wbal_old_gw = self._glac_wbal.data_ptr()
+        if self.curdate.month == self.GlacUpdate["month"] and self.curdate.day == self.GlacUpdate["day"]:
+            self.dateAfterUpdate = self.curdate + datetime.timedelta(days=1)                   # glacier.py:561-736
+            gid = self._glac_host["GLAC_ID"]
+            frac = G["FRAC_GLAC"].cpu().numpy()
+            ice = self._glac_host["ICE_DEPTH"]
+            snow = (G["TotalSnowStore_GLAC"] - G["AccuGlacMelt"]).cpu().numpy()
+            area = float(self.cellArea)
+            gsum = lambda x: pd.Series(x).groupby(gid).transform("sum").to_numpy()  # noqa: E731
+            with np.errstate(invalid="ignore", divide="ignore"):
+                v0 = frac * ice * area                                                         # ice volume before the update, m3
+                dmelt = snow / 1000 * frac * area                                              # snow left minus ice melted, m3
+                abl = dmelt < 0.0
+                acc, vabl = np.where(abl, 0.0, dmelt), np.where(abl, v0, 0.0)
+                dmelt_g, acc_g, vabl_g = gsum(dmelt), gsum(acc), gsum(vabl)
+                # shrinking glaciers move their accumulation down to the ablation fragments, by ice volume
+                redist = np.where((dmelt_g < 0.0) & ~abl, -acc, 0.0)
+                redist = np.where((dmelt_g < 0.0) & abl, vabl / vabl_g * acc_g, redist)
+                v1 = v0 + acc + np.where(abl, dmelt, 0.0) + redist
+                vneg, vpos = np.minimum(0.0, v1), np.maximum(0.0, v1)
+                spread = vpos / gsum(vpos) * gsum(vneg)                                        # negative volumes are shared out
+                v2 = np.maximum(0.0, v1 + np.where(np.isnan(spread), 0.0, spread))
+                ice_new = v2 / (frac * area)
+            frac_new = np.where(ice_new <= 0.0, 0.0, frac)                                     # fragments that melted away
+            self._glac_host["ICE_DEPTH"] = ice_new
+            G["FRAC_GLAC"].copy_(torch.from_numpy(frac_new))
+            G["ICE_DEPTH"].copy_(torch.from_numpy(ice_new))
+            for k in ("SnowStore_GLAC", "SnowWatStore_GLAC", "TotalSnowStore_GLAC", "AccuGlacMelt"):
+                G[k].zero_()
+            ice_mm = self._by_model_cell(ice_new * frac_new) * f32(1000)                       # sphy.py:1115-1131
+            self._ice_delta.copy_(torch.from_numpy(ice_mm - self._old_ice_mm))
+            self._old_ice_mm = ice_mm
+            F.wbal_snow_adjust = self.TotalSnowStore_GLAC.data_ptr()
+            F.wbal_ice_delta = self._ice_delta.data_ptr()
+            after.append(lambda: self.TotalSnowStore.sub_(self.TotalSnowStore_GLAC))           # glacier.py:729
+        if self.curdate == self.dateAfterUpdate:                                               # glacier.py:739-810
+            tag = self.curdate.strftime("%Y%m%d")
+            h = self._glac_host
+            frac = G["FRAC_GLAC"].cpu().numpy()
+            table = pd.DataFrame({"U_ID": h["U_ID"], "MOD_ID": h["MOD_ID"], "GLAC_ID": h["GLAC_ID"], "MOD_H": h["MOD_H"],
+                                  "GLAC_H": h["GLAC_H"], "DEBRIS": h["DEBRIS"], "FRAC_GLAC": frac, "ICE_DEPTH": h["ICE_DEPTH"]})
+            gf = self._by_model_cell(frac)
+            area_map = self._by_model_cell(frac * float(self.cellArea))
+            ice_map = self._by_model_cell(h["ICE_DEPTH"] * frac)
+            self._glac_emit({"glacTable_" + tag + ".csv": table, "GlacFrac_" + tag + ".map": gf, "GlacArea_" + tag + ".map": area_map,
+                             "iceDepth_" + tag + ".map": ice_map, "vIce_" + tag + ".map": ice_map * area_map})
+            self._glac_frac_new = self._dev(gf)
+            F.wbal_glac_frac = self._glac_frac_new.data_ptr()                                  # sphy.py:1137 already sees the new map
+            after.append(lambda: self.GlacFrac.copy_(self._glac_frac_new))                     # the physics of this day saw the old one
+        return after
+
+    def glacier_tables(self):
+        """GlacVars name -> DataFrame (dates x glacier ids, float32) like the reference's `<var>_Table` (glacier.py:98-110)."""
+        import pandas as pd
+        out = self._glac_rep["out"].cpu().numpy()
+        idx = pd.date_range(self.startdate, self.enddate, freq="D")
+        return {v: pd.DataFrame(out[:, k, :], index=idx, columns=self.glacid, dtype=np.float32) for k, v in enumerate(self.GlacVars)}
 
     # -- lakes.init/initial, reservoirs.init/initial, modules/lakes.py:162-224, reservoirs.py:90-162 ---
     def _reslake_initial(self):
@@ -1020,6 +1162,9 @@ class SphyModel:
             a = self._glacier_step(f["tavg"], f["prec"])
             F.TotalSnowStore_GLAC, F.SnowR_GLAC = a["TotalSnowStore_GLAC"].data_ptr(), a["SnowR_GLAC"].data_ptr()
             F.GlacPerc, F.GlacR = a["GlacPerc"].data_ptr(), a["GlacR"].data_ptr()
+        deferred = []
+        if self.GlacFLAG == 1 and self.RoutFLAG == 1 and not (self.LakeFLAG == 1 or self.ResFLAG == 1):
+            deferred = self._glacier_reporting(F)                                              # sphy.py:1106-1112
         prof = self._prof
         if prof is not None:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
@@ -1028,6 +1173,8 @@ class SphyModel:
                  "sphy_wb_step")
         if prof is not None:
             ev[1].record()
+        for fn in deferred:
+            fn()
         self.Q = None
         if self.LakeFLAG == 1 or self.ResFLAG == 1:                                            # sphy.py:1100-1104
             self.Q = self.advanced_routing.dynamic(self, None, None, self.config, self.TotR, None, None)

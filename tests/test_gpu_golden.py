@@ -88,6 +88,49 @@ def test_model_matches_reference_golden(name, order, route):
     model.close()
 
 
+def test_glacier_retreat_tables_and_maps():
+    """modules/glacier.py:501-810 on the device/host split: per-glacier daily tables (sphy_glac_report), the yearly ice
+    redistribution (fragments melting away), the maps and the fragment table written the day after, all against what the
+    unmodified reference produced."""
+    import torch
+    cat, z, meta = catchment_from_golden("c2_glac_retreat")
+    model = make_model(cat, diagnostics=True)
+    model.maps.forcing_fn = lambda t: golden_forcing(z, t)
+    uid = model._glac_host["U_ID"]
+    rows = np.argsort(z["glac/U_ID"])[np.argsort(np.argsort(uid))]           # reference row of each of our rows
+    for t in range(1, meta["nsteps"] + 1):
+        model.dynamic()
+        torch.cuda.synchronize()
+        assert np.allclose(model.GlacTable["FRAC_GLAC"].cpu().numpy(), z["glac/FRAC_GLAC"][t - 1][rows], rtol=1e-14, atol=0), t
+        assert np.allclose(model.GlacTable["ICE_DEPTH"].cpu().numpy(), z["glac/ICE_DEPTH"][t - 1][rows], rtol=1e-12, atol=0,
+                           equal_nan=True), t
+        for k in ("GlacFrac", "TotalSnowStore", "waterbalanceTot"):
+            want = z["state/" + k][t].ravel()[model.flat_active]
+            assert close(getattr(model, k).cpu().numpy(), want).all(), (t, k)
+    assert (model.GlacTable["FRAC_GLAC"].cpu().numpy() == 0).sum() == (z["glac/FRAC_GLAC"][-1] == 0).sum() > 0
+    tables = model.glacier_tables()
+    nb = tot = 0
+    for k in z.files:
+        if k.startswith("csv/") and not k.startswith("csv/glacTable"):
+            got, want = tables[k[4:-4]].to_numpy(), z[k].astype(np.float32)
+            assert [str(c) for c in tables[k[4:-4]].columns] == list(z["csvcols/" + k[4:]])
+            assert np.allclose(got, want, rtol=1e-6, atol=1e-30), k
+            nb += int((~bit_equal(got, want)).sum())
+            tot += got.size
+        elif k.startswith("csv/glacTable"):
+            df = model.glac_files[k[4:]]
+            assert list(df.columns) == list(z["csvcols/" + k[4:]])
+            want = z[k][np.argsort(z[k][:, 0])]
+            assert np.allclose(df.sort_values("U_ID").to_numpy(np.float64), want, rtol=1e-12, atol=0, equal_nan=True), k
+        elif k.startswith("repfile/") and k.endswith(".map") and k[8:] in model.glac_files:
+            want = z[k].ravel()[model.flat_active]
+            assert bit_equal(model.glac_files[k[8:]], want).all(), k
+            tot += 1
+    assert tot > 100 and nb <= 1e-3 * tot, (nb, tot)
+    assert sum(k.endswith(".map") for k in model.glac_files) == 8          # GlacFrac/GlacArea/iceDepth/vIce at the start and after the update
+    model.close()
+
+
 @pytest.mark.parametrize("kw,nsteps", [
     (dict(nrows=300, ncols=260, seed=5, params=dict(SubWater=470.0, RootDepthFlat=150.0, Pscale=2.5)), 25),
     (dict(nrows=257, ncols=301, seed=6, snow=True, glacier=True, rout_components=True, zrange=(1500.0, 5200.0),
