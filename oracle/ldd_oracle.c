@@ -147,6 +147,25 @@ void ldd_accuflux(const int32_t *order, const int32_t *down, int64_t n, const fl
     free(acc);
 }
 
+/* accucapacityflux / accucapacitystate [PCR-doc]: what arrives (own material + donor fluxes, formed in double like
+ * accuflux) leaves up to the cell's transport capacity; the rest stays behind as the state. */
+void ldd_accucapacity(const int32_t *order, const int32_t *down, int64_t n, const float *m, const float *cap,
+                      float *flux, float *state)
+{
+    double *acc = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    for (int64_t i = 0; i < n; ++i) acc[i] = (double)m[i];
+    for (int64_t k = 0; k < n; ++k) {
+        int32_t i = order[k];
+        double tot = acc[i];
+        float f = tot < (double)cap[i] ? (float)tot : cap[i];
+        if (!(tot == tot) || !(cap[i] == cap[i])) f = (float)(tot + (double)cap[i]);   /* MV in -> MV out */
+        flux[i] = f;
+        if (state) state[i] = (float)(tot - (double)f);
+        if (down[i] >= 0) acc[down[i]] += (double)f;
+    }
+    free(acc);
+}
+
 /* float64 twin used for error attribution (no REAL4 rounding along the path) */
 void ldd_accuflux_f64(const int32_t *order, const int32_t *down, int64_t n, const float *m,
                       const float *frac, double *flux)

@@ -35,6 +35,8 @@ def ldd_lib():
     lib.ldd_accuflux.argtypes = [P, P, ctypes.c_int64, P, P, P, P]
     lib.ldd_accuflux_f64.restype = None
     lib.ldd_accuflux_f64.argtypes = [P, P, ctypes.c_int64, P, P, P]
+    lib.ldd_accucapacity.restype = None
+    lib.ldd_accucapacity.argtypes = [P, P, ctypes.c_int64, P, P, P, P]
     lib.ldd_upstream.restype = None
     lib.ldd_upstream.argtypes = [P, P, ctypes.c_int64, P, P]
     _LIB = lib
@@ -93,6 +95,39 @@ class LddStruct:
         state = np.empty(self.n, np.float32) if want_state else None
         lib.ldd_accuflux(_p(self.order), _p(self.down), self.n, _p(m), _p(fr), _p(flux), _p(state))
         return (flux, state) if want_state else flux
+
+    def accucapacity(self, m, cap):
+        """accucapacityflux / accucapacitystate -> (flux, state), REAL4."""
+        lib = ldd_lib()
+        m = np.ascontiguousarray(m, np.float32)
+        cap = np.ascontiguousarray(cap, np.float32)
+        flux = np.empty(self.n, np.float32)
+        state = np.empty(self.n, np.float32)
+        lib.ldd_accucapacity(_p(self.order), _p(self.down), self.n, _p(m), _p(cap), _p(flux), _p(state))
+        return flux, state
+
+    def subcatchment(self, points):
+        """subcatchment(ldd, points) [PCR-doc]: every cell takes the id of the first non-zero point met on its way
+        downstream (itself included), 0 when it drains out without meeting one."""
+        pts = np.asarray(points, np.int64)
+        out = np.zeros(self.n, np.int64)
+        for k in range(self.n - 1, -1, -1):                  # outlets first
+            i = self.order[k]
+            d = self.down[i]
+            out[i] = pts[i] if pts[i] != 0 else (out[d] if d >= 0 else 0)
+        return out
+
+    def streamorder(self):
+        """streamorder(ldd) [PCR-doc]: Strahler order (headwater cells 1; two or more donors of the maximum order -> +1)."""
+        out = np.ones(self.n, np.int64)
+        for k in range(self.n):
+            i = self.order[k]
+            a, b = self.don_ptr[i], self.don_ptr[i + 1]
+            if b > a:
+                o = out[self.don_idx[a:b]]
+                mx = o.max()
+                out[i] = mx + 1 if (o == mx).sum() >= 2 else mx
+        return out
 
     def accuflux_f64(self, m, frac=None):
         lib = ldd_lib()

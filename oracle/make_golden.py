@@ -23,7 +23,8 @@ from .run_reference import run_reference
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
 REPORT = ("LAI", "TotIntF", "TotPrecEF", "StorCanop", "TotRF", "TotETactF", "TotETref", "Infil", "wbal", "TotRootRF", "TotRootDF", "TotRootPF", "TotSubPF",
-          "TotCapRF", "TotBaseRF", "TotSnowRF", "TotGlacRF", "TotGlacMelt", "TotSnowMelt", "StorSnow", "QallRAtot")
+          "TotCapRF", "TotBaseRF", "TotSnowRF", "TotGlacRF", "TotGlacMelt", "TotSnowMelt", "StorSnow", "QallRAtot",
+          "DetRn", "DetRun", "SDepFld", "SedTrans", "SedDep", "SedYld", "SedFlux", "TC")
 
 # wetter / shallower than the cfg defaults so that saturation, runoff, drainage, percolation, baseflow and the
 # ET cliff (ET.py:31) all occur inside a short run
@@ -66,6 +67,10 @@ CASES = {
     "c2_glac_retreat": (dict(nrows=12, ncols=10, seed=24, snow=True, glacier=True, params=dict(WETK, Toffset=12.0), start=(2001, 9, 20),
                              zrange=(1500.0, 5200.0), glac_retreat=(30, 9),
                              glac_vars=("FRAC_GLAC", "GlacMelt", "GlacR", "TotalSnowStore_GLAC", "GLAC_T")), 25),
+    # soil erosion (MMF, modules/mmf.py) + capacity-limited sediment transport (modules/sediment_transport.py), no reservoirs
+    "c1_sed_mmf": (dict(nrows=14, ncols=12, seed=41, sediment=True, infil_excess=1, params=WET, start=(2001, 6, 1)), 40),
+    "c2_sed_snow_veg": (dict(nrows=14, ncols=12, seed=42, sediment=dict(cc_lai=1, excl_channels=0, harvest=0), snow=True, dynveg=True,
+                             params=COLD, start=(2001, 3, 15), zrange=(1500.0, 5200.0)), 40),
     # BASELINE config 3: reservoirs (simple + advanced) and lakes
     "c3_res_lake": (dict(nrows=16, ncols=14, seed=31, cellsize=1000.0, reservoirs=True, lakes=True, n_res_simple=2,
                          n_res_adv=2, n_lakes=4, params=WET, start=(2001, 5, 1)), 70),

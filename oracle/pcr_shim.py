@@ -630,6 +630,30 @@ def accufractionstate(lddf, material, fraction):
     return _ldd_apply(lddf, lambda st, m, f: st.accuflux(m, f, want_state=True)[1], material, fraction)
 
 
+def accucapacityflux(lddf, material, capacity):
+    return _ldd_apply(lddf, lambda st, m, c: st.accucapacity(m, c)[0], material, capacity)
+
+
+def accucapacitystate(lddf, material, capacity):
+    return _ldd_apply(lddf, lambda st, m, c: st.accucapacity(m, c)[1], material, capacity)
+
+
+def subcatchment(lddf, points):
+    st = _ldd_struct(lddf)
+    pts = _to_int(_spatial(points))
+    ids = st.subcatchment(np.where(pts.ravel()[st.flat_active] == MV_I4, 0, pts.ravel()[st.flat_active]))
+    out = np.full(G.nrows * G.ncols, MV_I4, np.int32)
+    out[st.flat_active] = ids
+    return Field(out.reshape(G.nrows, G.ncols), Nominal)
+
+
+def streamorder(lddf):
+    st = _ldd_struct(lddf)
+    out = np.full(G.nrows * G.ncols, MV_I4, np.int32)
+    out[st.flat_active] = st.streamorder()
+    return Field(out.reshape(G.nrows, G.ncols), Ordinal)
+
+
 def upstream(lddf, x):
     return _ldd_apply(lddf, lambda st, v: st.upstream(v), x)
 
@@ -708,7 +732,7 @@ def make_modules():
               "atan", "abs", "pcrand", "pcror", "pcrnot", "setclone", "setglobaloption", "cellarea", "celllength",
               "cellvalue", "readmap", "report", "lookupscalar", "lookupnominal", "areatotal", "areamaximum",
               "areaminimum", "areaaverage", "clump", "accuflux", "accufractionflux", "accufractionstate",
-              "upstream", "catchmenttotal"):
+              "upstream", "catchmenttotal", "accucapacityflux", "accucapacitystate", "subcatchment", "streamorder"):
         setattr(pcr, k, this[k])
     fw = types.ModuleType("pcraster.framework")
     for k in ("DynamicModel", "DynamicFramework", "TimeoutputTimeseries", "generateNameT"):

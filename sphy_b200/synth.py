@@ -131,6 +131,7 @@ class Catchment:
     report_daily: tuple = ()
     pws: bool = False                    # plant water stress (ET.ks, PWS_FLAG)
     report_opts: dict = field(default_factory=dict)   # reporting.csv: name -> (map, avg, timeseries) option strings
+    sediment: dict | None = None         # SedFLAG = 1, MMF erosion (SedModel = 2) + capacity-limited transport: maps and tables
     glac_retreat: tuple | None = None    # (day, month) of the yearly glacier update (GlacRetreat = 1, glacier.py:562-736)
     glac_vars: tuple = ()                # per-glacier reporting (GlacID_flag = 1, glacier.py:501-559): GlacTable columns
     dynveg: bool = False                 # DynVegFLAG = 1: NDVI map series -> Kc, LAI, canopy interception (modules/dynamic_veg.py)
@@ -181,8 +182,13 @@ class Catchment:
             "stations.map": np.asarray(self.locations, np.int32),
             "ldd.map": np.asarray(self.ldd, np.uint8),
             "latitude.map": np.asarray(self.lat, np.float32),
-            "landuse.map": np.broadcast_to(np.int32(1), (self.nrows, self.ncols)),
+            "landuse.map": (np.broadcast_to(np.int32(1), (self.nrows, self.ncols)) if self.sediment is None
+                            else self.sediment["landuse"]),
         }
+        if self.sediment is not None:
+            m["rock_fraction.map"] = self.sediment["rock"]
+            m["root_sand.map"] = self.sediment["sand"]
+            m["root_clay.map"] = self.sediment["clay"]
         for k, v in self.soil_maps.items():
             m[_SOIL_FILES[k]] = np.asarray(v, np.float32)
         if self.model_id is not None:
@@ -225,14 +231,17 @@ class Catchment:
         os.makedirs(outputdir, exist_ok=True)
         p, f = self.params, self.flags
         end = self.start + datetime.timedelta(days=self.nsteps - 1)
-        with open(os.path.join(inputdir, "kc.tbl"), "w") as fh:
-            fh.write(f"1 {p['Kc']}\n")
-        with open(os.path.join(inputdir, "paved.tbl"), "w") as fh:
-            fh.write("1 0.0\n")
-        with open(os.path.join(inputdir, "laimax.tbl"), "w") as fh:
-            fh.write(f"1 {p.get('LAImax', 5.5)}\n")
-        with open(os.path.join(inputdir, "depletion.tbl"), "w") as fh:
-            fh.write(f"1 {p.get('PFactor', 0.5)}\n")
+        classes = (1,) if self.sediment is None else (1, 2, 3)
+        for fname, val in (("kc.tbl", p["Kc"]), ("paved.tbl", 0.0), ("laimax.tbl", p.get("LAImax", 5.5)),
+                           ("depletion.tbl", p.get("PFactor", 0.5))):
+            with open(os.path.join(inputdir, fname), "w") as fh:
+                for c in classes:
+                    fh.write(f"{c} {val}\n")
+        if self.sediment is not None:
+            for fname in ("mmf.tbl", "mmf_harvest.tbl"):
+                with open(os.path.join(inputdir, fname), "w") as fh:
+                    for row in self.sediment[fname]:
+                        fh.write(" ".join(repr(float(v)) for v in row) + "\n")
         with open(os.path.join(inputdir, "reporting.csv"), "w") as fh:
             fh.write("name,map,avg,timeseries,filename,comment\n")
             for name, fname in _REPORT_VARS:
@@ -267,8 +276,8 @@ LakeFLAG = {f['LakeFLAG']}
 ResFLAG = {f['ResFLAG']}
 DynVegFLAG = {1 if self.dynveg else 0}
 GroundFLAG = {f['GroundFLAG']}
-SedFLAG = 0
-SedTransFLAG = 0
+SedFLAG = {1 if self.sediment else 0}
+SedTransFLAG = {1 if self.sediment else 0}
 [DIRS]
 inputdir = {inputdir.rstrip('/')}/
 outputdir = {outputdir.rstrip('/')}/
@@ -299,6 +308,25 @@ SubSatMap = sub_sat.map
 SubKsat = sub_ksat.map
 [PEDOTRANSFER]
 PedotransferFLAG = 0
+RootSandMap = root_sand.map
+RootClayMap = root_clay.map
+[SEDIMENT]
+SedModel = 2
+RockFrac = rock_fraction.map
+exclChannelsFLAG = {int((self.sediment or {}).get("excl_channels", 1))}
+upstream_km2 = {(self.sediment or {}).get("upstream_km2", 1.0)}
+[MMF]
+MMF_table = mmf.tbl
+harvestFLAG = {int((self.sediment or {}).get("harvest", 1))}
+MMF_harvest = mmf_harvest.tbl
+CanopyCoverLAIFlag = {int((self.sediment or {}).get("cc_lai", 0))}
+{chr(10).join(f"{k} = {v!r}" for k, v in MMF_PARS.items())}
+[SEDIMENT_TRANS]
+Sed_init = 0
+upstream_km2 = {(self.sediment or {}).get("upstream_km2", 1.0)}
+{chr(10).join(f"{k} = {v!r}" for k, v in SEDTRANS_PARS.items())}
+TrapEffTab = trapefftab.tbl
+ResOrder = resorder.txt
 [SOIL_INIT]
 RootWater =
 SubWater = {p['SubWater']}
@@ -449,6 +477,12 @@ _SOIL_FILES = dict(RootFieldMap="root_field.map", RootSatMap="root_sat.map", Roo
                    SubSatMap="sub_sat.map", SubKsat="sub_ksat.map")
 
 # (reporting name, file prefix) pairs -- the names `reporting.reporting()` is called with on the hot path
+# [MMF] / [SEDIMENT_TRANS] constants of the shipped sphy_config.cfg (sphy_config.cfg:694-753,889-911)
+MMF_PARS = dict(PrecInt=30.0, K_c=0.1, K_z=0.5, K_s=0.3, DR_c=1.0, DR_z=1.6, DR_s=1.5, deltaClay=2e-6, deltaSilt=60e-6,
+                deltaSand=200e-6, manning=0.015, depthBare=0.005, depthInField=0.1, depthTC=0.25, RFR=6.0, rho_s=2650.0,
+                rho=1100.0, eta=0.0015)
+SEDTRANS_PARS = dict(TC_beta=1.4, TC_gamma=1.4, manningChannelFLAG=1, manningChannel=0.045)
+
 _REPORT_VARS = [
     ("LAI", "LAI"), ("TotIntF", "IntF"), ("TotPrecEF", "PrecEF"), ("StorCanop", "Canop"),
     ("wbal", "wbal"), ("TotPrec", "Prec"), ("TotPrecF", "PrecF"), ("TotRain", "Rain"), ("TotRainF", "RainF"),
@@ -462,6 +496,8 @@ _REPORT_VARS = [
     ("StorGroundW", "GrndW"), ("StorSnow", "SnowS"), ("StorSnowW", "SnowW"), ("SCover", "SCov"), ("GWL", "GWL"),
     ("QallRAtot", "QAll"), ("RootRRAtot", "QRoR"), ("RootDRAtot", "QRoD"), ("RainRAtot", "QRain"),
     ("SnowRAtot", "QSnow"), ("GlacRAtot", "QGlac"), ("BaseRAtot", "QBase"),
+    ("DetRn", "DetRn"), ("DetRun", "DetRun"), ("SDepFld", "SDpFld"), ("SedTrans", "STrans"), ("SedDep", "Sdep"),
+    ("SedYld", "SdYld"), ("SedFlux", "SdFlux"), ("TC", "TC"),
 ]
 
 
@@ -477,7 +513,7 @@ def make_catchment(nrows, ncols, cellsize=250.0, seed=1, nsteps=365, snow=False,
                    rout_components=False, outlets="single", start=datetime.date(2001, 1, 1),
                    n_res_simple=0, n_res_adv=0, n_lakes=0, open_water=False, params=None,
                    report_daily=(), soil_classes=1, zrange=None, pws=False, report_opts=None, etref_input=False, mask=None, dynveg=False,
-                   glac_retreat=None, glac_vars=()):
+                   glac_retreat=None, glac_vars=(), sediment=False):
     """Build one of the BASELINE.json synthetic configurations."""
     p = dict(DEFAULT_PARAMS)
     if params:
@@ -520,6 +556,8 @@ def make_catchment(nrows, ncols, cellsize=250.0, seed=1, nsteps=365, snow=False,
         cat.mask = inside
         cat.ldd = np.where(inside, cat.ldd, 255).astype(np.uint8)
         cat.locations = np.where(inside, cat.locations, 0).astype(np.int32)
+    if sediment:
+        _add_sediment(cat, seed, sediment if isinstance(sediment, dict) else {})
     if glacier:
         _add_glaciers(cat, rng)
         cat.glac_vars = tuple(glac_vars)
@@ -576,6 +614,33 @@ def _add_glaciers(cat, rng):
     cat.glac_table = {k: np.asarray(v)[perm] for k, v in cols.items()}
     cat.glac_id = glac_id.reshape(cat.nrows, cat.ncols)
     cat.tlapse = np.full(12, -0.0065)
+
+
+def _add_sediment(cat, seed, opts):
+    """Inputs of the MMF erosion model and the sediment transport module (modules/mmf.py:107-190,
+    modules/sediment_transport.py:113-214): three land-use classes (forest, cropland with a harvest window, bare /
+    no-erosion patches), soil texture in percent, rock fraction."""
+    r = np.random.default_rng([seed, 4242])
+    nr, nc = cat.nrows, cat.ncols
+    blobs = _smooth_noise(r, nr, nc, 4)
+    lu = np.where(blobs > 0.35, 3, np.where(blobs > -0.2, 2, 1)).astype(np.int32)
+    sand = np.clip(45.0 + 25.0 * _smooth_noise(r, nr, nc, 5), 10.0, 80.0).astype(np.float32)
+    clay = np.clip(22.0 + 12.0 * _smooth_noise(r, nr, nc, 5), 5.0, np.minimum(45.0, 95.0 - sand)).astype(np.float32)
+    rock = np.clip(0.12 + 0.15 * _smooth_noise(r, nr, nc, 3), 0.0, 0.6).astype(np.float32)
+    #          class PlantH NoElem Diam   CC   GC  NoEros Till n_tab NoVeg
+    mmf = [[0, 1, 2, 3, 4, 5, 6, 7, 8, 9],
+           [1, 12.0, 0.8, 0.4, 0.85, 0.6, 0, 0, 0.0, 0],
+           [2, 0.9, 150.0, 0.01, 0.5, 0.3, 0, 1, 0.0, 0],
+           [3, 0.1, 0.0, 0.0, 0.0, 0.05, 0, 0, 0.03, 1]]
+    #          class Sowing Harvest PlantH NoElem Diam  CC   GC  Till
+    day0 = cat.start.timetuple().tm_yday
+    harv = [[0, 1, 2, 3, 4, 5, 6, 7, 8],
+            [1, 0, 0, 0.0, 0.0, 0.0, 0.0, 0.0, 0],
+            [2, (day0 + 300) % 365 + 1, (day0 + 12) % 365 + 1, 0.05, 20.0, 0.005, 0.05, 0.1, 1],
+            [3, 0, 0, 0.0, 0.0, 0.0, 0.0, 0.0, 0]]
+    cat.sediment = dict(opts, landuse=lu, sand=sand, clay=clay, rock=rock)
+    cat.sediment["mmf.tbl"] = mmf
+    cat.sediment["mmf_harvest.tbl"] = harv
 
 
 def _add_reservoirs_lakes(cat, rng, nup, n_simple, n_adv, n_lakes):

@@ -16,7 +16,9 @@ STATE_KEYS = ("RootWater", "SubWater", "CapRise", "RootDrain", "GwRecharge", "Gw
               "RainR", "SnowR", "GlacR", "waterbalanceTot", "GlacFrac", "Scanopy")
 COMP_KEYS = ("RootRRAold", "RootDRAold", "RainRAold", "SnowRAold", "GlacRAold", "BaseRAold")
 # daily report file prefix -> key in the models' per-step `out` dict
-REPORT_KEYS = {"TotR": "TotR", "ETr": "ETref", "ETaF": "ActETact", "Infil": "Infil", "wbal": "wbal"}
+REPORT_KEYS = {"TotR": "TotR", "ETr": "ETref", "ETaF": "ActETact", "Infil": "Infil", "wbal": "wbal",
+               "DetRn": "DetRn", "DetRun": "DetRun", "SDpFld": "SDepFld", "STrans": "SedTrans", "Sdep": "SedDep", "SdYld": "SedYld",
+               "SdFlux": "SedFlux", "TC": "TC"}
 
 
 def golden_cases():
