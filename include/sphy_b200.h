@@ -47,7 +47,7 @@ const char *sphy_last_error(const sphy_ctx *ctx);
 int sphy_sm_count(const sphy_ctx *ctx);
 /* sizeof() of the ABI structs, so foreign-language bindings can verify their layout without a GPU:
  * 0 sphy_param, 1 sphy_wb_params, 2 sphy_wb_state, 3 sphy_wb_forcing, 4 sphy_wb_out, 5 sphy_glac_table,
- * 6 sphy_glac_out, 7 sphy_reslake, 8 sphy_openwater, 9 sphy_veg */
+ * 6 sphy_glac_out, 7 sphy_reslake, 8 sphy_openwater, 9 sphy_veg, 10 sphy_mmf */
 size_t sphy_abi_sizeof(int which);
 
 /* ---- K3: LDD -> integer structures (once per run) ------------------------------------------
@@ -216,6 +216,40 @@ typedef struct {
     float *LAI, *Int;                /* optional outputs (reporting: LAI, TotIntF) */
 } sphy_veg;
 int sphy_veg_step(sphy_ctx *ctx, const sphy_wb_params *p, const sphy_veg *v, int day_of_year, void *stream);
+
+/* K6: Morgan-Morgan-Finney soil erosion + transport capacity (SedFLAG = 1, SedModel = 2; modules/mmf.py:193-309,
+ * modules/sediment_transport.py:244-258).  Parameter maps are what mmf.init / sediment_transport.init derive once
+ * (modules/mmf.py:107-190, modules/sediment_transport.py:113-214); scalar-or-map like every other parameter.  Order of
+ * the texture classes in K / DR / v_s: clay, silt, sand. */
+typedef struct {
+    const float *prec;               /* precipitation reaching the ground (raw / pcorr, or the effective one of sphy_veg_step) */
+    float pcorr;
+    const float *q;                  /* routed discharge m3/s (q_is_discharge = 1) or TotR in mm (0), sphy.py:1217-1220 */
+    int32_t q_is_discharge;
+    const float *total_snow_store;   /* SnowFLAG = 1: snow cover protects the soil (mmf.py:220-224); else NULL */
+    const float *lai;                /* cc_mode 1 */
+    int32_t cc_mode;                 /* 0 table (+ harvest window), 1 min(1, LAI), 2 table only */
+    int32_t harvest_on, excl_channels;
+    sphy_param cos_slope, sin_slope_pow;             /* REAL4 cos(Slope), sin(Slope)**0.3 */
+    sphy_param cc_table, gc_table, plant_height, no_erosion, rock_frac;
+    sphy_param sowing, harvest, cc_harvest, gc_harvest, plant_height_harvest;
+    sphy_param clay, silt, sand, hillslope;
+    sphy_param v_field, v_field_harvest;             /* in-field flow velocity (mmf.py:175-189) */
+    sphy_param roughness, roughness_harvest;         /* v_TC / v_b (sediment_transport.py:175-205) */
+    sphy_param slope_streams_pow;                    /* SlopeStreams ** TC_gamma */
+    float K[3], DR[3], v_s[3];                       /* detachability, REAL4 of the Stokes settling velocities (mmf.py:86) */
+    float infil_alpha;               /* InfilFLAG = 1: PrecInt = DT * Alpha (mmf.py:236-237); 0 = fixed intensity */
+    float ke_const;                  /* REAL4 0.29 * (1 - 0.72 * exp(-0.05 * PrecInt)) for the fixed intensity */
+    float d_field, cell_length, tc_beta;
+    float *DetRn, *DetRun, *SDepFld; /* optional reporting outputs, ton per cell */
+    float *SedTrans;                 /* sediment taken into transport, ton per cell: the material of sphy_accucapacity */
+    float *TC;                       /* transport capacity (NULL when SedTransFLAG = 0) */
+} sphy_mmf;
+int sphy_mmf_step(sphy_ctx *ctx, const sphy_mmf *p, int day_of_year, void *stream);
+
+/* accucapacityflux / accucapacitystate (modules/sediment_transport.py:40-44): level sweep where every cell passes on at
+ * most its capacity; flux and state are optional outputs (at least one). */
+int sphy_accucapacity(sphy_ctx *ctx, const float *material, const float *capacity, float *flux, float *state, void *stream);
 
 /* K1 alone does not need the LDD: declare the number of active cells directly */
 int sphy_set_ncells(sphy_ctx *ctx, int64_t n);

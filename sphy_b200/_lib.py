@@ -82,6 +82,18 @@ class Veg(C.Structure):
                 + [(k, P) for k in ("Scanopy", "ETref", "Kc", "PrecipEff", "LAI", "Int")])
 
 
+class Mmf(C.Structure):
+    _fields_ = ([("prec", P), ("pcorr", C.c_float), ("q", P), ("q_is_discharge", C.c_int32), ("total_snow_store", P), ("lai", P),
+                 ("cc_mode", C.c_int32), ("harvest_on", C.c_int32), ("excl_channels", C.c_int32)]
+                + [(k, SphyParam) for k in ("cos_slope", "sin_slope_pow", "cc_table", "gc_table", "plant_height", "no_erosion",
+                                            "rock_frac", "sowing", "harvest", "cc_harvest", "gc_harvest", "plant_height_harvest",
+                                            "clay", "silt", "sand", "hillslope", "v_field", "v_field_harvest", "roughness",
+                                            "roughness_harvest", "slope_streams_pow")]
+                + [("K", C.c_float * 3), ("DR", C.c_float * 3), ("v_s", C.c_float * 3)]
+                + [(k, C.c_float) for k in ("infil_alpha", "ke_const", "d_field", "cell_length", "tc_beta")]
+                + [(k, P) for k in ("DetRn", "DetRun", "SDepFld", "SedTrans", "TC")])
+
+
 RL_NPAR = 23
 WB_SNOW, WB_GROUND, WB_INFIL_EXCESS, WB_PWS, WB_ETREF_INPUT = 1, 2, 4, 8, 16
 RA_TABLE, RA_CELL = 0, 1
@@ -116,6 +128,8 @@ SYMBOLS = {
     "sphy_set_ncells": (C.c_int, [P, C.c_int64]),
     "sphy_module_op": (C.c_int, [P, C.c_int, C.POINTER(SphyParam), C.c_int, C.POINTER(P), C.c_int, C.c_int64, C.c_float, C.c_int, P]),
     "sphy_scan_tile_cells": (C.c_int, []),
+    "sphy_mmf_step": (C.c_int, [P, C.POINTER(Mmf), C.c_int, P]),
+    "sphy_accucapacity": (C.c_int, [P, P, P, P, P, P]),
     "sphy_glac_report": (C.c_int, [P, C.c_int32, P, P, P, C.c_int32, P, P, P, P]),
     "sphy_veg_step": (C.c_int, [P, C.POINTER(WbParams), C.POINTER(Veg), C.c_int, P]),
     "sphy_wb_step": (C.c_int, [P, C.POINTER(WbParams), C.POINTER(WbState), C.POINTER(WbForcing), C.POINTER(WbOut),
@@ -131,7 +145,7 @@ SYMBOLS = {
     "sphy_route_reslake_step": (C.c_int, [P, C.POINTER(ResLake), P, P, SphyParam, C.c_float, C.c_int, C.c_int, P]),
 }
 
-ABI_STRUCTS = (SphyParam, WbParams, WbState, WbForcing, WbOut, GlacTable, GlacOut, ResLake, OpenWater, Veg)
+ABI_STRUCTS = (SphyParam, WbParams, WbState, WbForcing, WbOut, GlacTable, GlacOut, ResLake, OpenWater, Veg, Mmf)
 
 _LIB = None
 

@@ -146,6 +146,7 @@ extern "C" size_t sphy_abi_sizeof(int which)
         case 7: return sizeof(sphy_reslake);
         case 8: return sizeof(sphy_openwater);
         case 9: return sizeof(sphy_veg);
+        case 10: return sizeof(sphy_mmf);
         default: return 0;
     }
 }

@@ -15,7 +15,7 @@
 
 namespace {
 
-enum { MODE_PLAIN = 0, MODE_ROUT = 1, MODE_ADV = 2 };
+enum { MODE_PLAIN = 0, MODE_ROUT = 1, MODE_ADV = 2, MODE_CAPACITY = 3 };
 
 struct SweepArgs {
     int ncomp;
@@ -51,7 +51,7 @@ __device__ __forceinline__ CellIn load_cell_in(const SweepArgs &a, int c, int32_
     CellIn ci;
     ci.fr = a.frac ? __ldg(a.frac + i) : 1.0f;
     ci.kx = a.kx.map ? __ldg(a.kx.map + i) : a.kx.value;
-    ci.qold = a.mode == MODE_PLAIN ? 0.0f : a.qstate[c][i];
+    ci.qold = (a.mode == MODE_PLAIN || a.mode == MODE_CAPACITY) ? 0.0f : a.qstate[c][i];
     ci.qout = (a.mode == MODE_ADV && ci.fr == 0.0f) ? __ldg(a.qout_dense + i) : 0.0f;
     return ci;
 }
@@ -59,6 +59,15 @@ __device__ __forceinline__ CellIn load_cell_in(const SweepArgs &a, int c, int32_
 // finish a cell: fraction cut, store flux, recession blend
 __device__ __forceinline__ float finish(const SweepArgs &a, int c, int64_t k, int32_t i, double tot, const CellIn &ci)
 {
+    if (a.mode == MODE_CAPACITY) {
+        // accucapacityflux / accucapacitystate: what arrives leaves up to the transport capacity (held in `frac`),
+        // the rest stays behind (modules/sediment_transport.py:40-44)
+        const float f = tot < (double)ci.fr ? (float)tot : ci.fr;
+        a.acc[(int64_t)c * a.n + k] = f;
+        if (a.flux_out[c]) a.flux_out[c][i] = f;
+        if (a.qstate[c]) a.qstate[c][i] = (float)(tot - (double)f);
+        return f;
+    }
     const float f = a.frac ? (float)((double)ci.fr * tot) : (float)tot;
     a.acc[(int64_t)c * a.n + k] = f;
     if (a.mode == MODE_PLAIN) {
@@ -282,6 +291,21 @@ extern "C" int sphy_accuflux(sphy_ctx *ctx, const float *mat, const float *fract
     a.m[0] = mat;
     a.flux_out[0] = flux;
     a.frac = fraction;
+    return route_levels_run(ctx, a, (cudaStream_t)stream);
+}
+
+extern "C" int sphy_accucapacity(sphy_ctx *ctx, const float *mat, const float *capacity, float *flux, float *state, void *stream)
+{
+    if (!ctx || !mat || !capacity || (!flux && !state)) return SPHY_E_INVALID;
+    if (!ctx->ldd_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_accucapacity before sphy_ldd_build");
+    if (ctx->partitioned) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_accucapacity is not available on a partitioned context");
+    SweepArgs a = {};
+    a.ncomp = 1;
+    a.mode = MODE_CAPACITY;
+    a.m[0] = mat;
+    a.flux_out[0] = flux;
+    a.qstate[0] = state;
+    a.frac = capacity;
     return route_levels_run(ctx, a, (cudaStream_t)stream);
 }
 

@@ -67,6 +67,15 @@ struct ScanArgs {
 // the chunk at j*32 + lane), so that the per-lane accesses of both phases are bank-conflict free
 __device__ __forceinline__ int ls_slot(int i) { return (i & ~127) | ((i & 3) << 5) | ((i >> 2) & 31); }
 
+// Range sums are differences of float64 prefixes.  Parallel prefixes are only consistent to a few ulp of the prefix, so
+// a range without any runoff would come out as +-1e-16 x prefix instead of 0 (and a negative discharge breaks x**1.5
+// in the erosion module).  A difference inside that rounding noise IS zero as far as this method can tell.
+__device__ __forceinline__ double range_diff(double hi, double lo)
+{
+    const double d = hi - lo;
+    return fabs(d) <= 3.6e-15 * fabs(hi) ? 0.0 : d;            // 32 ulp of the minuend
+}
+
 // recession blend of one cell: routing.py:28, or advanced_routing.py:31-37 on a lake/reservoir network
 __device__ __forceinline__ float blend(const ScanArgs &a, int64_t cell, float f, float qold, float kx, float omk)
 {
@@ -218,9 +227,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_MIN_CTAS) k_scan_main(const
                         double pe = own;                               // headwater cell: the range is the cell itself
                         if (inside && szj > 1) pe = Ls[ls_slot(el)];   // predicated load: fewer lanes, fewer bank conflicts
                         if (ADV) {
-                            if (inside) qj = blend(a, tbase + o + j, (float)(pe - before), qj, kx, omk);
+                            if (inside) qj = blend(a, tbase + o + j, (float)range_diff(pe, before), qj, kx, omk);
                         } else {
-                            const float qn = omk * (float)(pe - before) + kx * qj;        // routing.py:28
+                            const float qn = omk * (float)range_diff(pe, before) + kx * qj;   // routing.py:28
                             qj = inside ? qn : qj;
                         }
                     };
@@ -258,11 +267,12 @@ __global__ void __launch_bounds__(256) k_scan_cross(const __grid_constant__ Scan
         const double *X = a.tile_excl + (int64_t)c * (a.ntiles + 1);
         if (e >= a.n) {                                        // range ends on another rank: keep the part up to the
             double *pb = a.park_before + (int64_t)c * a.n_cross + k;   // end of this rank's range for k_scan_remote
-            *pb = (T[ta] - *pb) + (X[a.ntiles] - X[ta + 1]);
+            *pb = range_diff(T[ta], *pb) + (ta + 1 < a.ntiles ? range_diff(X[a.ntiles], X[ta + 1]) : 0.0);
             continue;
         }
-        const double s = (T[ta] - a.park_before[(int64_t)c * a.n_cross + k]) + (X[te] - X[ta + 1]) +
-                         a.park_end[(int64_t)c * (a.n_cross + a.n_pub) + k];
+        // suffix of the first tile + whole tiles in between (none for most crossing cells) + prefix of the last tile
+        const double s = range_diff(T[ta], a.park_before[(int64_t)c * a.n_cross + k]) +
+                         (te > ta + 1 ? range_diff(X[te], X[ta + 1]) : 0.0) + a.park_end[(int64_t)c * (a.n_cross + a.n_pub) + k];
         const float f = (float)s;
         float *qs = a.qstate[c];
         qs[r] = blend(a, r, f, qs[r], kx, omk);

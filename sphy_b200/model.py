@@ -157,8 +157,7 @@ class SphyModel:
         if self.GlacFLAG == 1:
             self.SnowFLAG = 1
             self.GroundFLAG = 1
-        if self.SedFLAG:
-            raise NotImplementedError("sediment is outside the B200 hot path (SURVEY.md section 2)")
+        self.SedTransFLAG = g("SedTransFLAG") if config.has_option("MODULES", "SedTransFLAG") else 0
         self.inpath = config.get("DIRS", "inputdir")
         self.outpath = config.get("DIRS", "outputdir")
         # -- timing, sphy.py:90-110
@@ -202,6 +201,7 @@ class SphyModel:
         self.groundwater, self.snow, self.glacier = modules.groundwater, modules.snow, modules.glacier
         self.routing, self.advanced_routing = modules.routing, modules.advanced_routing
         self.lakes, self.reservoirs = modules.lakes, modules.reservoirs
+        self.mmf, self.sediment_transport = modules.mmf, modules.sediment_transport
 
     # ------------------------------------------------------------------------------------------
     def close(self):
@@ -357,7 +357,8 @@ class SphyModel:
         cfg = self.config
         cn = self._compact_np
         rd = lambda sec, key: cn(self._readmap(cfg.get(sec, key)))  # noqa: E731
-        if cfg.getint("PEDOTRANSFER", "PedotransferFLAG") == 1:
+        self.PedotransferFLAG = cfg.getint("PEDOTRANSFER", "PedotransferFLAG")
+        if self.PedotransferFLAG == 1:
             raise NotImplementedError("pedotransfer functions are init-time only and outside the hot path (SURVEY.md section 2)")
         sc = lambda k: f32(cfg.getfloat("SOIL_CAL", k))  # noqa: E731
         self.Slope = rd("GENERAL", "Slope")
@@ -552,6 +553,8 @@ class SphyModel:
         if self.ETOpenWaterFLAG == 1:
             self.out["ETOpenWater"] = self._full(0.0)                   # ET.ETpot(ETref, kcOpenWater), sphy.py:898
         self._prepare_wb_structs()
+        if self.SedFLAG == 1:
+            self._sediment_initial()
         # time series at `Locations` (TimeoutputTimeseries, sphy.py:683-691): cells with id > 0, ordered by id
         loc_cells = np.flatnonzero(self.Locations > 0)
         loc_cells = loc_cells[np.argsort(self.Locations[loc_cells], kind="stable")]
@@ -766,6 +769,28 @@ class SphyModel:
         out = self._glac_rep["out"].cpu().numpy()
         idx = pd.date_range(self.startdate, self.enddate, freq="D")
         return {v: pd.DataFrame(out[:, k, :], index=idx, columns=self.glacid, dtype=np.float32) for k, v in enumerate(self.GlacVars)}
+
+    # -- soil erosion and sediment transport, sphy.py:460-559 --------------------------------------------------
+    def _sediment_initial(self):
+        cfg = self.config
+        if self.world > 1:
+            raise NotImplementedError("sediment transport is not available on a partitioned basin")
+        self.SedModel = cfg.getfloat("SEDIMENT", "SedModel")
+        if self.SedModel != 2:
+            raise NotImplementedError("only the MMF erosion model (SedModel = 2) is supported; MUSLE/INCA/SHETRAN/DHSVM/HSPF are not")
+        self.RockFrac = self._compact_np(self._readmap(cfg.get("SEDIMENT", "RockFrac")))
+        self.exclChannelsFLAG = cfg.getint("SEDIMENT", "exclChannelsFLAG")
+        if self.exclChannelsFLAG == 1:                                                         # sphy.py:474-482
+            ones = torch.ones(self.n, dtype=torch.float32, device=self.device)
+            acc = torch.empty_like(ones)
+            self._ck(self.lib.sphy_accuflux(self._ctx, ones.data_ptr(), None, acc.data_ptr(), _lib.ROUTE_LEVELS, self._stream()),
+                     "sphy_accuflux")
+            up = acc.cpu().numpy() * self.cellArea / f32(10 ** 6)
+            self.Hillslope = (up <= f32(cfg.getfloat("SEDIMENT", "upstream_km2"))).astype(np.float32)
+        self.mmf.init(self, None, cfg)
+        if self.SedTransFLAG == 1:
+            self.sediment_transport.init(self, None, cfg)
+        self.mmf.prepare(self)
 
     # -- lakes.init/initial, reservoirs.init/initial, modules/lakes.py:162-224, reservoirs.py:90-162 ---
     def _reslake_initial(self):
@@ -1184,6 +1209,10 @@ class SphyModel:
             ev[2].record()
             prof["wb"].append((ev[0], ev[1]))
             prof["route"].append((ev[1], ev[2]))
+        if self.SedFLAG == 1:                                                                  # sphy.py:1214-1240
+            G = self.mmf.dynamic(self, None, f["prec"], self.Q if self.Q is not None else self.TotR)
+            if self.SedTransFLAG == 1:
+                self.sediment_transport.dynamic_mmf(self, None, None, None, G)
         if self.collect_tss and self.Q is not None and len(self.station_ids):
             self._ck(lib.sphy_sample(ctx, self.Q.data_ptr(), self._station_cells.data_ptr(), len(self.station_ids),
                                      self._station_buf.data_ptr(), st), "sphy_sample")
@@ -1288,6 +1317,12 @@ class SphyModel:
                 d.update(TotIntF=lambda: vm["Int"], TotPrecEF=lambda: vm["PrecipEff"])
             if self.openWaterFrac is None:
                 d["StorCanop"] = lambda: self.Scanopy
+        if self.SedFLAG == 1:                                      # mmf.py:259-306, sediment_transport.py:261-275
+            so = self.sed_out
+            d.update(DetRn=lambda: so["DetRn"], DetRun=lambda: so["DetRun"], SDepFld=lambda: so["SDepFld"],
+                     SedTrans=lambda: so["SedTrans"])
+            if self.SedTransFLAG == 1:
+                d.update(TC=lambda: so["TC"], SedDep=lambda: so["SedDep"], SedYld=lambda: so["SedDep"], SedFlux=lambda: so["SedFlux"])
         d["TotRF"] = lambda: self.TotR
         if self.RootRR is not None:
             d.update(TotRootRF=lambda: self.RootRR, TotRootDF=lambda: self.RootDR, TotRainRF=lambda: self.RainR)

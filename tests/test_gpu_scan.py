@@ -101,3 +101,39 @@ def test_scan_routing_matches_oracle(shape, ncomp, kxmap, seed):
             # the scan path must be at least as close to the float64 oracle as 1e-6 relative
             assert (np.abs(sc - q_64[c]) <= 2e-6 * np.abs(q_64[c]) + 1e-12).all()
     lib.sphy_ctx_destroy(ctx)
+
+
+def test_scan_routing_dry_regions_are_exactly_zero():
+    """Range sums are differences of float64 prefixes; a sub-catchment without runoff must still route exactly 0 (never a
+    +-1e-16 residue, never a negative discharge -- modules/mmf.py:56 raises the routed runoff to the power 1.5)."""
+    import torch
+    from oracle.ldd_oracle import LddStruct
+    from sphy_b200 import _lib, synth
+    lib = _lib.load()
+    cellsize = 250.0
+    _, _, ldd, _ = synth.make_dem_ldd(500, 420, cellsize, seed=9, outlets="single")
+    st = LddStruct(ldd)
+    n = st.n
+    ctx = _ctx(lib, torch, ldd, cellsize)
+    t = torch.empty(n, dtype=torch.int32, device="cuda")
+    _lib.check(lib, ctx, lib.sphy_ldd_export(ctx, b"cell_order", t.data_ptr(), n * 4, None), "cell_order")
+    torch.cuda.synchronize()
+    canon = t.cpu().numpy().astype(np.int64)
+    rng = np.random.default_rng(9)
+    rows = st.flat_active // 420
+    mm = (rng.gamma(0.8, 40.0, n) * (rng.random(n) < 0.6)).astype(np.float32)
+    mm[(rows < 230) | (rng.random(n) < 0.3)] = 0.0                          # a dry half plus scattered dry cells
+    mm_d = torch.from_numpy(mm[canon]).cuda()
+    q = torch.zeros(n, device="cuda")
+    src, dst = (C.c_void_p * 1)(mm_d.data_ptr()), (C.c_void_p * 1)(q.data_ptr())
+    kx = _lib.SphyParam(None, 0.0)
+    _lib.check(lib, ctx, lib.sphy_route_step(ctx, 1, src, dst, kx, C.c_float(1.0), _lib.ROUTE_SCAN, None), "route")
+    torch.cuda.synchronize()
+    got = np.empty(n, np.float32)
+    got[canon] = q.cpu().numpy()
+    want = st.accuflux((mm * np.float32(0.001) * (np.float32(cellsize) * np.float32(cellsize))) / np.float32(86400))
+    assert (want == 0).sum() > n // 4
+    assert (got >= 0).all()
+    assert (got[want == 0] == 0).all()
+    assert (np.abs(got - want) <= 1e-5 * want).all()
+    lib.sphy_ctx_destroy(ctx)
