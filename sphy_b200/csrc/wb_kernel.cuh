@@ -86,26 +86,95 @@ __device__ __forceinline__ float extrarad(float sinl, float cosl, float tanl, co
     return sf::extrarad(sinl, cosl, tanl, d.k0dr, d.sin_delta, d.cos_delta, d.tan_delta);
 }
 
+constexpr int WB_THREADS = 128;
+
+// ---- asynchronous prefetch of the next tile (cp.async, one 16-byte slot per stream and thread) ------------------
+// The kernel is a grid-stride loop; without prefetch a thread's ~14 loads are only in flight while it waits for them,
+// not while it computes and stores.  With PF every thread copies the inputs of its NEXT tile into its own shared-
+// memory slots right after it has moved the current ones into registers, so HBM requests are outstanding during the
+// whole compute/store phase.  A thread only ever reads its own slots: no barrier, just cp.async.wait_group.
+enum { S_PREC, S_TAVG, S_T1 /* tmin | etref */, S_T2 /* tmax */, S_LAT, S_RW, S_SW, S_CAPR, S_RDRAIN,
+       S_G0 /* GwRecharge | SubDrain */, S_G1, S_G2, S_G3, S_SN0, S_SN1, S_SN2, S_DVEL, S_COUNT };
+
+__device__ __forceinline__ void cp_async16(float4 *dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(float4 *dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ V4 pf_get(const float4 *pf, int slot)
+{
+    const float4 t = pf[slot * WB_THREADS];
+    return V4{{t.x, t.y, t.z, t.w}};
+}
+
+// issue the copies of the 4 cells starting at cell i (same stream set as the load phase of wb_cells below)
+template <bool SNOW, bool GROUND, int RA>
+__device__ __forceinline__ void pf_issue(const WbArgs &a, int64_t i, float4 *pf)
+{
+#define PF_CP(slot, ptr) cp_async16(pf + (slot) * WB_THREADS, (ptr) + i)
+    PF_CP(S_PREC, a.f.prec);
+    PF_CP(S_TAVG, a.f.tavg);
+    if (RA == 2) {
+        PF_CP(S_T1, a.f.etref);
+        if (SNOW) PF_CP(S_T2, a.f.tmax);
+    } else {
+        PF_CP(S_T1, a.f.tmin);
+        PF_CP(S_T2, a.f.tmax);
+    }
+    if (RA == 0) cp_async8(pf + S_LAT * WB_THREADS, a.p.lat_class + i);
+    PF_CP(S_RW, a.s.RootWater);
+    PF_CP(S_SW, a.s.SubWater);
+    PF_CP(S_CAPR, a.s.CapRise);
+    PF_CP(S_RDRAIN, a.s.RootDrain);
+    if (GROUND) {
+        PF_CP(S_G0, a.s.GwRecharge);
+        PF_CP(S_G1, a.s.Gw);
+        PF_CP(S_G2, a.s.BaseR);
+        PF_CP(S_G3, a.s.H_gw);
+    } else {
+        PF_CP(S_G0, a.s.SubDrain);
+    }
+    if (SNOW) {
+        PF_CP(S_SN0, a.s.SnowStore);
+        PF_CP(S_SN1, a.s.SnowWatStore);
+        PF_CP(S_SN2, a.s.TotalSnowStore);
+    }
+    if (a.p.root_drainvel.map) PF_CP(S_DVEL, a.p.root_drainvel.map);
+#undef PF_CP
+    cp_async_commit();
+}
+
 // ---- the per-cell physics, W cells per call --------------------------------------------------------
-template <bool SNOW, bool GROUND, bool INFIL, int RA /*0 table, 1 cell, 2 etref input*/, bool DIAG, bool USOIL, int W>
-__device__ __forceinline__ void wb_cells(const WbArgs &a, int64_t i)
+template <bool SNOW, bool GROUND, bool INFIL, int RA /*0 table, 1 cell, 2 etref input*/, bool DIAG, bool USOIL, int W, bool PF = false>
+__device__ __forceinline__ void wb_cells(const WbArgs &a, int64_t i, float4 *pf = nullptr, int64_t i_next = -1)
 {
     using L = Lanes<W>;
     const sphy_wb_params &p = a.p;
+    static_assert(!PF || W == 4, "the prefetch path moves 4 cells per thread");
+    if (PF) cp_async_wait_all();                       // this tile's inputs have landed in the thread's slots
+#define IN(slot, ptr) (PF ? pf_get(pf, slot) : L::in(ptr, i))
+#define INRW(slot, ptr) (PF ? pf_get(pf, slot) : L::inrw(ptr, i))
     // ---- loads (all issued up front: ~14 independent 128-bit requests per thread) -------------------
-    V4 prec = L::in(a.f.prec, i), tavg = L::in(a.f.tavg, i);
+    V4 prec = IN(S_PREC, a.f.prec), tavg = IN(S_TAVG, a.f.tavg);
     V4 tmin, tmax, etref_in, ra;
     if (RA == 2) {
-        etref_in = L::in(a.f.etref, i);
+        etref_in = IN(S_T1, a.f.etref);
     } else {
-        tmin = L::in(a.f.tmin, i);
-        tmax = L::in(a.f.tmax, i);
+        tmin = IN(S_T1, a.f.tmin);
+        tmax = IN(S_T2, a.f.tmax);
     }
-    if (SNOW && RA == 2) tmax = L::in(a.f.tmax, i);
+    if (SNOW && RA == 2) tmax = IN(S_T2, a.f.tmax);
     V4 sinl, cosl, tanl;
     if (RA == 0) {
         if (W == 4) {
-            uint2 c = __ldg(reinterpret_cast<const uint2 *>(p.lat_class + i));
+            uint2 c;
+            if (PF) c = *reinterpret_cast<const uint2 *>(pf + S_LAT * WB_THREADS);
+            else c = __ldg(reinterpret_cast<const uint2 *>(p.lat_class + i));
             ra.v[0] = __ldg(a.ra_table + (c.x & 0xffffu));
             ra.v[1] = __ldg(a.ra_table + (c.x >> 16));
             ra.v[2] = __ldg(a.ra_table + (c.y & 0xffffu));
@@ -122,21 +191,21 @@ __device__ __forceinline__ void wb_cells(const WbArgs &a, int64_t i)
         cosl = L::in(p.cos_lat, i);
         tanl = L::in(p.tan_lat, i);
     }
-    V4 RW = L::inrw(a.s.RootWater, i), SW = L::inrw(a.s.SubWater, i), CapRise = L::inrw(a.s.CapRise, i),
-       RootDrain = L::inrw(a.s.RootDrain, i);
+    V4 RW = INRW(S_RW, a.s.RootWater), SW = INRW(S_SW, a.s.SubWater), CapRise = INRW(S_CAPR, a.s.CapRise),
+       RootDrain = INRW(S_RDRAIN, a.s.RootDrain);
     V4 GwRecharge, Gw, BaseR, H_gw, SubDrain, SnowStore, SnowWatStore, TotalSnowStore;
     if (GROUND) {
-        GwRecharge = L::inrw(a.s.GwRecharge, i);
-        Gw = L::inrw(a.s.Gw, i);
-        BaseR = L::inrw(a.s.BaseR, i);
-        H_gw = L::inrw(a.s.H_gw, i);
+        GwRecharge = INRW(S_G0, a.s.GwRecharge);
+        Gw = INRW(S_G1, a.s.Gw);
+        BaseR = INRW(S_G2, a.s.BaseR);
+        H_gw = INRW(S_G3, a.s.H_gw);
     } else {
-        SubDrain = L::inrw(a.s.SubDrain, i);
+        SubDrain = INRW(S_G0, a.s.SubDrain);
     }
     if (SNOW) {
-        SnowStore = L::inrw(a.s.SnowStore, i);
-        SnowWatStore = L::inrw(a.s.SnowWatStore, i);
-        TotalSnowStore = L::inrw(a.s.TotalSnowStore, i);
+        SnowStore = INRW(S_SN0, a.s.SnowStore);
+        SnowWatStore = INRW(S_SN1, a.s.SnowWatStore);
+        TotalSnowStore = INRW(S_SN2, a.s.TotalSnowStore);
     }
     // soil / groundwater parameters: USOIL = every one of them is a scalar (uniform soils, the cfg defaults):
     // they are then read straight from the kernel-parameter constant bank and cost no registers and no bytes
@@ -147,7 +216,11 @@ __device__ __forceinline__ void wb_cells(const WbArgs &a, int64_t i)
         sub_field = L::par(p.sub_field, i); sub_sat = L::par(p.sub_sat, i); e_sub = L::par(p.e_sub, i);
         capmax = L::par(p.caprise_max, i); kc = L::par(p.kc, i);
     }
-    V4 drainvel = L::par(p.root_drainvel, i);
+    V4 drainvel = (PF && p.root_drainvel.map) ? pf_get(pf, S_DVEL) : L::par(p.root_drainvel, i);
+#undef IN
+#undef INRW
+    // the slots are free again: start the copies of this thread's next tile (in flight while this one is computed)
+    if (PF && i_next >= 0) pf_issue<SNOW, GROUND, RA>(a, i_next, pf);
 #define PV(vec, par) (USOIL ? p.par.value : vec.v[j])
     const bool has_glac = p.glac_frac.map != nullptr;
     const bool has_ow = p.open_water_frac.map != nullptr;
@@ -392,8 +465,6 @@ __device__ __forceinline__ void wb_cells(const WbArgs &a, int64_t i)
     }
 }
 
-constexpr int WB_THREADS = 128;
-
 template <bool SNOW, bool GROUND, bool INFIL, int RA, bool DIAG, bool USOIL, int CPT>
 __global__ void __launch_bounds__(WB_THREADS) k_wb_step(const __grid_constant__ WbArgs a)
 {
@@ -406,7 +477,37 @@ __global__ void __launch_bounds__(WB_THREADS) k_wb_step(const __grid_constant__ 
     if (blockIdx.x == 0 && threadIdx.x < (a.n - tail0)) wb_cells<SNOW, GROUND, INFIL, RA, DIAG, USOIL, 1>(a, tail0 + threadIdx.x);
 }
 
+// the same kernel with the next tile prefetched through shared memory (S_COUNT 16-byte slots per thread)
+constexpr int WB_PF_SMEM = S_COUNT * WB_THREADS * (int)sizeof(float4);
+
+template <bool SNOW, bool GROUND, bool INFIL, int RA, bool USOIL>
+__global__ void __launch_bounds__(WB_THREADS) k_wb_step_pf(const __grid_constant__ WbArgs a)
+{
+    extern __shared__ float4 pf_smem[];
+    float4 *pf = pf_smem + threadIdx.x;
+    const int64_t ng = a.n / 4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (q < ng) pf_issue<SNOW, GROUND, RA>(a, q * 4, pf);
+    for (; q < ng; q += stride) {
+        const int64_t qn = q + stride;
+        wb_cells<SNOW, GROUND, INFIL, RA, false, USOIL, 4, true>(a, q * 4, pf, qn < ng ? qn * 4 : -1);
+    }
+    const int64_t tail0 = ng * 4;
+    if (blockIdx.x == 0 && threadIdx.x < (a.n - tail0)) wb_cells<SNOW, GROUND, INFIL, RA, false, USOIL, 1>(a, tail0 + threadIdx.x);
+}
+
 typedef void (*wb_kernel_t)(const WbArgs);
+
+template <bool S, bool G, bool U>
+wb_kernel_t pick_sgu_pf(bool infil, int ra)
+{
+#define SPHY_WB_CASE(I, R) if (infil == I && ra == R) return k_wb_step_pf<S, G, I, R, U>;
+    SPHY_WB_CASE(false, 0) SPHY_WB_CASE(false, 1) SPHY_WB_CASE(false, 2)
+    SPHY_WB_CASE(true, 0) SPHY_WB_CASE(true, 1) SPHY_WB_CASE(true, 2)
+#undef SPHY_WB_CASE
+    return nullptr;
+}
 
 template <bool S, bool G, bool U, int CPT>
 wb_kernel_t pick_sgu(bool infil, int ra, bool diag)
@@ -420,9 +521,11 @@ wb_kernel_t pick_sgu(bool infil, int ra, bool diag)
     return nullptr;
 }
 
+// cpt < 0 selects the prefetching variant (no diagnostics)
 template <bool S, bool G>
 wb_kernel_t pick_sg(bool infil, int ra, bool diag, bool usoil, int cpt)
 {
+    if (cpt < 0) return diag ? nullptr : (usoil ? pick_sgu_pf<S, G, true>(infil, ra) : pick_sgu_pf<S, G, false>(infil, ra));
     // measured on B200 (profiles/r1_k1_variants.md): 4 cells/thread at 96 registers (5 CTAs/SM) beats both
     // 2 cells/thread (80 registers) and a 6-CTA register cap (spills), so only CPT = 4 is instantiated
     (void)cpt;

@@ -131,13 +131,28 @@ extern "C" int sphy_wb_step(sphy_ctx *ctx, const sphy_wb_params *p, const sphy_w
                             : (ground ? wb_pick_01(infil, ra, diag, usoil, cpt) : wb_pick_00(infil, ra, diag, usoil, cpt));
     if (!kern) SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_wb_step: no kernel for this switch combination");
     const int64_t n4 = (a.n + cpt - 1) / cpt;
-    int occ = 0;
-    SPHY_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WB_THREADS, 0));
-    if (occ < 1) occ = 1;
     int64_t want = (n4 + WB_THREADS - 1) / WB_THREADS;
+    // large grids without diagnostics: the variant that prefetches every thread's next tile with cp.async
+    // worthwhile once every CTA walks several tiles
+    const char *pf_env = getenv("SPHY_WB_PREFETCH");             // 0 = off, 2 = also on small grids (tests)
+    const bool pf_enabled = !(pf_env && pf_env[0] == '0');
+    const bool pf_force = pf_env && pf_env[0] == '2';
+    size_t smem = 0;
+    if (pf_enabled && !diag && (pf_force || want >= (int64_t)ctx->sm_count * 16)) {
+        wb_kernel_t pf = snow ? (ground ? wb_pick_11(infil, ra, diag, usoil, -1) : wb_pick_10(infil, ra, diag, usoil, -1))
+                              : (ground ? wb_pick_01(infil, ra, diag, usoil, -1) : wb_pick_00(infil, ra, diag, usoil, -1));
+        if (pf) {
+            SPHY_CUDA(ctx, cudaFuncSetAttribute(pf, cudaFuncAttributeMaxDynamicSharedMemorySize, WB_PF_SMEM));
+            kern = pf;
+            smem = WB_PF_SMEM;
+        }
+    }
+    int occ = 0;
+    SPHY_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WB_THREADS, smem));
+    if (occ < 1) occ = 1;
     int64_t cap = (int64_t)ctx->sm_count * occ;
     int grid = (int)(want < cap ? (want > 0 ? want : 1) : cap);
-    kern<<<grid, WB_THREADS, 0, st>>>(a);
+    kern<<<grid, WB_THREADS, smem, st>>>(a);
     SPHY_LAUNCH_CHECK(ctx);
     return SPHY_OK;
 }

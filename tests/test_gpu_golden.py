@@ -188,6 +188,37 @@ def test_model_matches_oracle_port(kw, nsteps, route_method="levels"):
     model.close()
 
 
+@pytest.mark.parametrize("case", [0, 1, 3])
+def test_prefetch_kernel_variant_matches_oracle_port(case, monkeypatch):
+    """The cp.async-prefetching variant of the water-balance kernel (what large grids run, no diagnostics) must be
+    bit-identical too: force it on the seeded catchments and compare the states with the oracle port."""
+    import datetime
+    import torch
+    from oracle.sphy_port import PortInputs, PortModel
+    from sphy_b200 import synth
+    monkeypatch.setenv("SPHY_WB_PREFETCH", "2")
+    kw, nsteps = test_model_matches_oracle_port.pytestmark[0].args[1][case]
+    cat = synth.make_catchment(nsteps=nsteps, start=datetime.date(2001, 5, 1), **kw)
+    inp = PortInputs(cat)
+    port = PortModel(inp)
+    model = make_model(cat, diagnostics=False)
+    g = inp.lddst.gather
+    keys = ["RootWater", "SubWater", "CapRise", "RootDrain", "GwRecharge", "Gw", "BaseR", "H_gw", "QRAold"]
+    if cat.flags["SnowFLAG"]:
+        keys += ["SnowStore", "SnowWatStore", "TotalSnowStore"]
+    if cat.dynveg:
+        keys += ["Scanopy"]
+    for t in range(1, nsteps + 1):
+        port.dynamic({k: g(v) for k, v in cat.forcing(t).items()})
+        model.dynamic()
+        torch.cuda.synchronize()
+        for k in keys:
+            got = model_attr(model, k).cpu().numpy()
+            want = getattr(port, k)[model.cell_order]
+            assert bit_equal(got, want).all(), f"t={t} {k}: {int((~bit_equal(got, want)).sum())} cells are not bit-identical"
+    model.close()
+
+
 def test_reservoirs_lakes_with_scan_routing_match_oracle_port():
     """BASELINE config 3 physics on the fast path: accufractionflux by cut corrections on the scan."""
     test_model_matches_oracle_port(dict(nrows=220, ncols=260, seed=17, cellsize=1000.0, reservoirs=True, lakes=True, n_res_simple=8,
