@@ -51,6 +51,9 @@ CASES = {
     "c1_dynveg": (dict(nrows=12, ncols=10, seed=19, dynveg=True, params=WET, start=(2001, 4, 1)), 50),
     "c2_dynveg_snow": (dict(nrows=12, ncols=10, seed=23, dynveg=True, snow=True, glacier=True, params=GLAC, start=(2001, 4, 15),
                             zrange=(1500.0, 5200.0)), 50),
+    # crop-coefficient and seepage map series with missing days (sphy.py:824-830, 992-1000)
+    "c1_kc_seep_series": (dict(nrows=12, ncols=10, seed=26, ground=False, kc_series=True, seep_series=True, params=WET), 30),
+    "c1_kc_series": (dict(nrows=12, ncols=10, seed=27, kc_series=True, params=WET), 30),
     # plant water stress (ET.ks) instead of the wilting-point reduction
     "c1_pws": (dict(nrows=12, ncols=10, seed=15, pws=True, params=WET), 40),
     # reporting.csv driven outputs (utilities/reporting.py): month / year / final maps, averages, long-term sums, TSS
@@ -98,6 +101,10 @@ def make(name):
     ref = run_reference(cat, nsteps, keep_table=bool(cat.glac_retreat or cat.glac_vars))
     fkeys = ("prec", "tavg", "tmin", "tmax") + (("etref",) if cat.etref_input else ()) + (("ndvi",) if cat.dynveg else ())
     forcing = {k: np.stack([cat.forcing(t)[k] for t in range(1, nsteps + 1)]) for k in fkeys}
+    nan_map = np.full((cat.nrows, cat.ncols), np.nan, np.float32)           # series with gaps: NaN map = no file that day
+    for k, on in (("kc", cat.kc_series), ("seep", cat.seep_series)):
+        if on:
+            forcing[k] = np.stack([cat.forcing(t).get(k, nan_map) for t in range(1, nsteps + 1)])
     payload = {"meta": np.array(json.dumps(dict(case=name, nsteps=nsteps, kwargs=CASES[name][0])))}
     for k, v in cat.static_maps().items():
         payload["map/" + k] = v

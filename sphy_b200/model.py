@@ -389,9 +389,12 @@ class SphyModel:
             for k in ("GwDepth", "GwSat", "deltaGw", "BaseThresh", "alphaGw", "YieldGw"):
                 setattr(self, k, self._scalar_or_map("GROUNDW_PARS", k))
         else:
-            if cfg.get("SOILPARS", "SeepStatic").strip() in ("", "0"):
-                raise NotImplementedError("seepage map series (SeepStatic = 0) is not supported yet")
-            self.SeePage = self._scalar_or_map("SOILPARS", "SeePage")
+            self.SeepStatFLAG = cfg.getint("SOILPARS", "SeepStatic")                           # sphy.py:220-229
+            if self.SeepStatFLAG == 0:
+                self.Seepmaps = cfg.get("SOILPARS", "SeePage")
+                self.SeePage = None                # daily map series, sphy.py:992-1000
+            else:
+                self.SeePage = self._scalar_or_map("SOILPARS", "SeePage")
             self.GWL_base = self._scalar_or_map("SOILPARS", "GWL_base")
             self.SubDrainVel = self.SubKsat * self.Slope                                      # sphy.py:237
         # land use / crop coefficient, sphy.py:254-281
@@ -406,9 +409,12 @@ class SphyModel:
                     raise NotImplementedError(f"[DYNVEG] {k} as a map is not supported yet") from None
             self.Kc = None                         # per-cell map produced by sphy_veg_step every day
         else:
-            if cfg.getint("LANDUSE", "KCstatic") != 1:
-                raise NotImplementedError("Kc map series (KCstatic = 0) is not supported yet")
-            self.Kc = self._lookup_column_table(os.path.join(self.inpath, cfg.get("LANDUSE", "CropFac")), self.LandUse)
+            self.KcStatFLAG = cfg.getint("LANDUSE", "KCstatic")                                # sphy.py:268-275
+            if self.KcStatFLAG == 1:
+                self.Kc = self._lookup_column_table(os.path.join(self.inpath, cfg.get("LANDUSE", "CropFac")), self.LandUse)
+            else:
+                self.Kcmaps = cfg.get("LANDUSE", "KC")
+                self.Kc = None                     # daily map series; the last map read is kept over gaps (sphy.py:824-830)
         self.PlantWaterStressFLAG = cfg.getint("PWS", "PWS_FLAG")
         self.PMap = (self._lookup_column_table(os.path.join(self.inpath, cfg.get("PWS", "PFactor")), self.LandUse)
                      if self.PlantWaterStressFLAG == 1 else None)
@@ -951,7 +957,14 @@ class SphyModel:
         P.root_ksat, P.root_drainvel, P.e_root = pr(self.RootKsat), pr(self.RootDrainVel), pr(self._e_root)
         P.sub_field, P.sub_sat, P.e_sub = pr(self.SubField), pr(self.SubSat), pr(self._e_sub)
         P.caprise_max = pr(self.CapRiseMax)
-        P.kc = pr(self.Kc) if self.DynVegFLAG != 1 else SphyParam(self._veg_maps["Kc"].data_ptr(), 0.0)
+        self._series = {}                          # optional daily map series: key -> (stack prefix, device map holding the last one read)
+        if self.DynVegFLAG == 1:
+            P.kc = SphyParam(self._veg_maps["Kc"].data_ptr(), 0.0)
+        elif self.Kc is None:
+            self._series["kc"] = (self.Kcmaps, self._full(1.0))                                # KcOld = 1, sphy.py:611-613
+            P.kc = SphyParam(self._series["kc"][1].data_ptr(), 0.0)
+        else:
+            P.kc = pr(self.Kc)
         if self.PMap is not None:
             P.pmap = pr(self.PMap)
         if self.GlacFrac is not None:
@@ -977,7 +990,12 @@ class SphyModel:
                 h_den = f32(800 * yg * ag)                                                     # groundwater.py:45
             P.e_delta, P.e_alpha, P.h_den = pr(e_delta), pr(e_alpha), pr(h_den)
         else:
-            P.seepage, P.sub_drainvel = pr(self.SeePage), pr(self.SubDrainVel)
+            if self.SeePage is None:
+                self._series["seep"] = (self.Seepmaps, self._full(0.0))                        # SeepOld = 0, sphy.py:628-629
+                P.seepage = SphyParam(self._series["seep"][1].data_ptr(), 0.0)
+            else:
+                P.seepage = pr(self.SeePage)
+            P.sub_drainvel = pr(self.SubDrainVel)
         if self.SnowFLAG == 1:
             P.tcrit, P.snow_sc, P.ddfs = float(f32(self.Tcrit)), float(f32(self.SnowSC)), float(f32(self.DDFS))
             P.snow_f, P.one_minus_snow_f = float(f32(self.SnowF)), float(f32(1 - self.SnowF))
@@ -1092,6 +1110,8 @@ class SphyModel:
             pre = {"prec": self.Prec, "tavg": self.Tair, "tmin": self.Tmin, "tmax": self.Tmax}
         if self.DynVegFLAG == 1:
             pre["ndvi"] = self.ndvi
+        for k, (prefix, _) in self._series.items():
+            pre[k] = prefix
         return {k: csf.stack_name(v, counter) for k, v in pre.items()}
 
     def _ingest(self, counter):
@@ -1102,8 +1122,9 @@ class SphyModel:
         if self._forcing_dev is not None:
             return self._forcing_dev(counter)
         keys = ("prec", "tavg", "etref") if self.ETREF_FLAG == 1 else ("prec", "tavg", "tmin", "tmax")
-        if self.DynVegFLAG == 1 and self._forcing_host is None:
-            keys = keys + ("ndvi",)
+        optional = (("ndvi",) if self.DynVegFLAG == 1 else ()) + tuple(self._series)           # series that may have gaps
+        if self._forcing_host is None:
+            keys = keys + optional
         if self._fdev is None:
             self._fdev = {k: torch.empty(self.n, dtype=torch.float32, device=self.device) for k in keys}
         if self._forcing_host is not None:
@@ -1116,9 +1137,9 @@ class SphyModel:
             try:
                 src = np.asarray(self.maps.read(names[k]), np.float32).ravel()
             except (KeyError, FileNotFoundError):
-                if k != "ndvi":
+                if k not in optional:
                     raise
-                out.pop("ndvi")                    # no NDVI map for this day: keep the previous one, dynamic_veg.py:78-82
+                out.pop(k)                         # no map for this day: the previous one is kept (dynamic_veg.py:78-82, sphy.py:824-830)
                 continue
             self._staging[k].numpy()[:] = src if self.full_raster else src[self.flat_active]
             self._fdev[k].copy_(self._staging[k], non_blocking=True)
@@ -1177,6 +1198,9 @@ class SphyModel:
         doy = julian(self.curdate)
         self._doy = doy
         self._prec_raw = f["prec"]
+        for k, (_, last) in self._series.items():                                              # sphy.py:824-830, 992-1000
+            if f.get(k) is not None and f[k] is not last:
+                last.copy_(f[k], non_blocking=True)
         if self.DynVegFLAG == 1:                                                               # sphy.py:820-822
             v = self._veg_step(f, doy)
             f = dict(f, prec=v["PrecipEff"], etref=v["ETref"])

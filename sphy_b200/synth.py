@@ -131,6 +131,8 @@ class Catchment:
     report_daily: tuple = ()
     pws: bool = False                    # plant water stress (ET.ks, PWS_FLAG)
     report_opts: dict = field(default_factory=dict)   # reporting.csv: name -> (map, avg, timeseries) option strings
+    kc_series: bool = False              # KCstatic = 0: crop-coefficient map series with gaps (sphy.py:824-830)
+    seep_series: bool = False            # SeepStatic = 0 (GroundFLAG = 0): seepage map series with gaps (sphy.py:992-1000)
     sediment: dict | None = None         # SedFLAG = 1, MMF erosion (SedModel = 2) + capacity-limited transport: maps and tables
     glac_retreat: tuple | None = None    # (day, month) of the yearly glacier update (GlacRetreat = 1, glacier.py:562-736)
     glac_vars: tuple = ()                # per-glacier reporting (GlacID_flag = 1, glacier.py:501-559): GlacTable columns
@@ -164,6 +166,10 @@ class Catchment:
         out = dict(prec=prec, tavg=tavg, tmin=tmin, tmax=tmax)
         if self.etref_input:
             out["etref"] = np.clip(np.float32(0.12) * (tavg + np.float32(12.0)), 0, None).astype(np.float32)
+        if self.kc_series and day % 3 == 2:                      # gaps: the previous map (1 before the first) is kept
+            out["kc"] = np.clip(0.9 + 0.3 * _smooth_noise(rng, self.nrows, self.ncols, 4), 0.3, 1.4).astype(np.float32)
+        if self.seep_series and day % 4 == 0:
+            out["seep"] = np.clip(0.4 + 0.4 * _smooth_noise(rng, self.nrows, self.ncols, 4), 0.0, 1.5).astype(np.float32)
         if self.dynveg:
             season_v = 0.35 + 0.25 * np.sin(2.0 * np.pi * (doy - 120) / 365.0)
             out["ndvi"] = np.clip(season_v + 0.15 * _smooth_noise(rng, self.nrows, self.ncols, 6)
@@ -209,6 +215,10 @@ class Catchment:
             names["etref"] = stack_name("forcings/etref", day)
         if self.dynveg:
             names["ndvi"] = stack_name("forcings/ndvi", day)
+        if self.kc_series and day % 3 == 2:
+            names["kc"] = stack_name("forcings/kc", day)
+        if self.seep_series and day % 4 == 0:
+            names["seep"] = stack_name("forcings/seep", day)
         return names
 
     def write_csf_inputs(self, inputdir, nsteps=None):
@@ -343,8 +353,8 @@ RootKsatFrac = 1
 RootDepthFlat = {p['RootDepthFlat']}
 SubDepthFlat = {p['SubDepthFlat']}
 CapRiseMax = {p['CapRiseMax']}
-SeepStatic = 1
-SeePage = {p['SeePage']}
+SeepStatic = {0 if self.seep_series else 1}
+SeePage = {"forcings/seep" if self.seep_series else p['SeePage']}
 GWL_base = {p['GWL_base']}
 [INFILTRATION]
 Infil_excess = {self.infil_excess}
@@ -366,9 +376,9 @@ Gw = {p['Gw']}
 H_gw = {p['H_gw']}
 [LANDUSE]
 LandUse = landuse.map
-KCstatic = 1
+KCstatic = {0 if self.kc_series else 1}
 CropFac = kc.tbl
-KC =
+KC = {"forcings/kc" if self.kc_series else ""}
 [DYNVEG]
 NDVI = forcings/ndvi
 NDVImax = 0.65
@@ -513,7 +523,8 @@ def make_catchment(nrows, ncols, cellsize=250.0, seed=1, nsteps=365, snow=False,
                    rout_components=False, outlets="single", start=datetime.date(2001, 1, 1),
                    n_res_simple=0, n_res_adv=0, n_lakes=0, open_water=False, params=None,
                    report_daily=(), soil_classes=1, zrange=None, pws=False, report_opts=None, etref_input=False, mask=None, dynveg=False,
-                   glac_retreat=None, glac_vars=(), sediment=False):
+                   glac_retreat=None, glac_vars=(), sediment=False, kc_series=False,
+                   seep_series=False):
     """Build one of the BASELINE.json synthetic configurations."""
     p = dict(DEFAULT_PARAMS)
     if params:
@@ -548,7 +559,8 @@ def make_catchment(nrows, ncols, cellsize=250.0, seed=1, nsteps=365, snow=False,
                     lat=lat, flags=flags, params=p, start=start, nsteps=nsteps, locations=locations,
                     soil_maps=soil_maps, rout_components=rout_components, infil_excess=infil_excess,
                     report_daily=tuple(report_daily), pws=bool(pws), report_opts=dict(report_opts or {}),
-                    etref_input=bool(etref_input), dynveg=bool(dynveg))
+                    etref_input=bool(etref_input), dynveg=bool(dynveg), kc_series=bool(kc_series),
+                    seep_series=bool(seep_series))
     if mask == "disk":                    # a non-rectangular catchment: everything outside the disk is MV
         rr, cc = np.ogrid[:nrows, :ncols]
         inside = ((rr - (nrows - 1) / 2.0) / (nrows / 2.0)) ** 2 + ((cc - (ncols - 1) / 2.0) / (ncols / 2.0)) ** 2 <= 1.0
