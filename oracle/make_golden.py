@@ -74,6 +74,9 @@ CASES = {
     "c1_sed_mmf": (dict(nrows=14, ncols=12, seed=41, sediment=True, infil_excess=1, params=WET, start=(2001, 6, 1)), 40),
     "c2_sed_snow_veg": (dict(nrows=14, ncols=12, seed=42, sediment=dict(cc_lai=1, excl_channels=0, harvest=0), snow=True, dynveg=True,
                              params=COLD, start=(2001, 3, 15), zrange=(1500.0, 5200.0)), 40),
+    # sediment trapped in reservoirs, sub-catchments routed in the steps of resorder.txt (sediment_transport.py:46-107)
+    "c3_sed_reservoirs": (dict(nrows=18, ncols=16, seed=47, cellsize=500.0, sediment=dict(upstream_km2=2.0), infil_excess=1,
+                               reservoirs=True, n_res_simple=3, n_res_adv=2, params=WET, start=(2001, 6, 1)), 25),
     # BASELINE config 3: reservoirs (simple + advanced) and lakes
     "c3_res_lake": (dict(nrows=16, ncols=14, seed=31, cellsize=1000.0, reservoirs=True, lakes=True, n_res_simple=2,
                          n_res_adv=2, n_lakes=4, params=WET, start=(2001, 5, 1)), 70),

@@ -144,11 +144,17 @@ def run_reference(cat, nsteps=None, dtype=np.float32, keep_table=False, quiet=Tr
         return _orig_setitem(self, key, value)
 
     _pd.DataFrame.__setitem__ = _setitem
+    # modules/sediment_transport.py:164-166 still uses the `np.int` alias NumPy removed in 1.24
+    _had_np_int = hasattr(np, "int")
+    if not _had_np_int:
+        np.int = int
     try:
         with (contextlib.redirect_stdout(sink) if quiet else contextlib.nullcontext()):
             runpy.run_path(os.path.join(REFERENCE_DIR, "sphy.py"), run_name="__main__")
     finally:
         _pd.DataFrame.__setitem__ = _orig_setitem
+        if not _had_np_int:
+            del np.int
         os.chdir(old_cwd)
         sys.argv = old_argv
         sys.path[:] = old_path

@@ -191,6 +191,8 @@ class Catchment:
             "landuse.map": (np.broadcast_to(np.int32(1), (self.nrows, self.ncols)) if self.sediment is None
                             else self.sediment["landuse"]),
         }
+        if self.sediment is not None and "reservoirs" in self.sediment:
+            m["reservoirs_nominal.map"] = self.sediment["reservoirs"]
         if self.sediment is not None:
             m["rock_fraction.map"] = self.sediment["rock"]
             m["root_sand.map"] = self.sediment["sand"]
@@ -247,6 +249,14 @@ class Catchment:
             with open(os.path.join(inputdir, fname), "w") as fh:
                 for c in classes:
                     fh.write(f"{c} {val}\n")
+        if self.sediment is not None and "reservoirs" in self.sediment:
+            with open(os.path.join(inputdir, "trapefftab.tbl"), "w") as fh:
+                for rid, eff in self.sediment["trap_eff"]:
+                    fh.write(f"{rid} {eff}\n")
+            with open(os.path.join(inputdir, "resorder.txt"), "w") as fh:
+                fh.write("order\tsteps\n")
+                for rid, step in self.sediment["res_order"]:
+                    fh.write(f"{rid}\t{step}\n")
         if self.sediment is not None:
             for fname in ("mmf.tbl", "mmf_harvest.tbl"):
                 with open(os.path.join(inputdir, fname), "w") as fh:
@@ -448,6 +458,7 @@ LakeSH = lake_sh.tbl
 LakeHS = lake_hs.tbl
 [RESERVOIR]
 ResId = res_id.map
+reservoirs = reservoirs_nominal.map
 ResFuncStor = res_funcstor.tbl
 {'ResSimple = res_simple.tbl' if 'res_simple.tbl' in self.res_tables else ''}
 {'ResAdv = res_adv.tbl' if 'res_adv.tbl' in self.res_tables else ''}
@@ -595,6 +606,8 @@ def make_catchment(nrows, ncols, cellsize=250.0, seed=1, nsteps=365, snow=False,
                     ow[r0:r1, c0:c1] = np.maximum(ow[r0:r1, c0:c1], blk)
                     ow[r, c] = np.float32(rng.uniform(0.5, 0.9))
             cat.open_water_frac = ow
+    if sediment and reservoirs:
+        _add_sediment_reservoirs(cat, seed)
     return cat
 
 
@@ -653,6 +666,45 @@ def _add_sediment(cat, seed, opts):
     cat.sediment = dict(opts, landuse=lu, sand=sand, clay=clay, rock=rock)
     cat.sediment["mmf.tbl"] = mmf
     cat.sediment["mmf_harvest.tbl"] = harv
+
+
+def _add_sediment_reservoirs(cat, seed):
+    """Reservoir inputs of the sediment transport module (modules/sediment_transport.py:138-188): the extent map, the
+    trapping efficiencies and resorder.txt (reservoir id -> routing step; upstream reservoirs get earlier steps)."""
+    r = np.random.default_rng([seed, 5151])
+    rid = cat.res_id.ravel()
+    cells = np.flatnonzero(rid > 0)
+    dr = {1: (1, -1), 2: (1, 0), 3: (1, 1), 4: (0, -1), 6: (0, 1), 7: (-1, -1), 8: (-1, 0), 9: (-1, 1)}
+    ldd = cat.ldd
+    down = {}
+    for g in range(cat.ncell):
+        code = int(ldd.ravel()[g])
+        if code in dr:
+            rr, cc = divmod(g, cat.ncols)
+            r2, c2 = rr + dr[code][0], cc + dr[code][1]
+            if 0 <= r2 < cat.nrows and 0 <= c2 < cat.ncols:
+                down[g] = r2 * cat.ncols + c2
+    extent = np.zeros(cat.ncell, np.int32)
+    for g in cells:                                   # the dam cell plus its direct donors
+        extent[g] = rid[g]
+        for u, d in down.items():
+            if d == g and rid[u] == 0:
+                extent[u] = rid[g]
+    step = {}
+    for g in cells:                                   # number of reservoirs further upstream decides the step
+        step[int(rid[g])] = 0
+    for g in cells:
+        c = down.get(int(g))
+        depth = 0
+        while c is not None:
+            if rid[c] > 0:
+                depth += 1
+                step[int(rid[c])] = max(step[int(rid[c])], depth)
+            c = down.get(c)
+    ids = sorted(step)
+    cat.sediment["reservoirs"] = extent.reshape(cat.nrows, cat.ncols)
+    cat.sediment["trap_eff"] = [(i, round(float(r.uniform(0.5, 0.95)), 3)) for i in ids]
+    cat.sediment["res_order"] = [(i, step[i]) for i in ids]
 
 
 def _add_reservoirs_lakes(cat, rng, nup, n_simple, n_adv, n_lakes):
