@@ -47,7 +47,7 @@ const char *sphy_last_error(const sphy_ctx *ctx);
 int sphy_sm_count(const sphy_ctx *ctx);
 /* sizeof() of the ABI structs, so foreign-language bindings can verify their layout without a GPU:
  * 0 sphy_param, 1 sphy_wb_params, 2 sphy_wb_state, 3 sphy_wb_forcing, 4 sphy_wb_out, 5 sphy_glac_table,
- * 6 sphy_glac_out, 7 sphy_reslake, 8 sphy_openwater, 9 sphy_veg, 10 sphy_mmf */
+ * 6 sphy_glac_out, 7 sphy_reslake, 8 sphy_openwater, 9 sphy_veg, 10 sphy_mmf, 11 sphy_sedres */
 size_t sphy_abi_sizeof(int which);
 
 /* ---- K3: LDD -> integer structures (once per run) ------------------------------------------
@@ -250,6 +250,23 @@ int sphy_mmf_step(sphy_ctx *ctx, const sphy_mmf *p, int day_of_year, void *strea
 /* accucapacityflux / accucapacitystate (modules/sediment_transport.py:40-44): level sweep where every cell passes on at
  * most its capacity; flux and state are optional outputs (at least one). */
 int sphy_accucapacity(sphy_ctx *ctx, const float *material, const float *capacity, float *flux, float *state, void *stream);
+
+/* Sediment transport through reservoirs (modules/sediment_transport.py:46-107): sub-catchments are routed in the steps
+ * of resorder.txt.  Reservoirs are listed in the reference's iteration order (step, then position in the file). */
+typedef struct {
+    int32_t n_res, n_steps;                 /* n_steps = max(step) + 1 */
+    const int32_t *res_cell, *res_down;     /* [n_res] dam cell and the cell below it (-1 = none), device indices */
+    const int32_t *res_step;                /* [n_res] */
+    const int32_t *down_finish_seq;         /* [n_res] iteration at which the sub-catchment of res_down is finished (INT32_MAX = never) */
+    const float *trap_eff, *outflow_eff;    /* [n_res] */
+    const int32_t *finish_step;             /* [N] step at which the cell's sub-catchment is finished (INT32_MAX = never) */
+    const int32_t *extent;                  /* [N] > 0 inside a reservoir: unlimited transport capacity */
+    const int32_t *step_last_seq_host;      /* HOST array [n_steps]: last iteration index of steps <= k (-1 = none yet) */
+    float *sed_trans, *tc_route, *cap_flux, *cap_state;   /* [N] work maps */
+    float *outflow;                         /* [n_res] work */
+} sphy_sedres;
+int sphy_sed_reservoir_route(sphy_ctx *ctx, const sphy_sedres *r, const float *sed, const float *tc, float *yield, float *dep,
+                             float *flux, void *stream);
 
 /* K1 alone does not need the LDD: declare the number of active cells directly */
 int sphy_set_ncells(sphy_ctx *ctx, int64_t n);

@@ -94,6 +94,12 @@ class Mmf(C.Structure):
                 + [(k, P) for k in ("DetRn", "DetRun", "SDepFld", "SedTrans", "TC")])
 
 
+class SedRes(C.Structure):
+    _fields_ = ([("n_res", C.c_int32), ("n_steps", C.c_int32)]
+                + [(k, P) for k in ("res_cell", "res_down", "res_step", "down_finish_seq", "trap_eff", "outflow_eff", "finish_step",
+                                    "extent", "step_last_seq_host", "sed_trans", "tc_route", "cap_flux", "cap_state", "outflow")])
+
+
 RL_NPAR = 23
 WB_SNOW, WB_GROUND, WB_INFIL_EXCESS, WB_PWS, WB_ETREF_INPUT = 1, 2, 4, 8, 16
 RA_TABLE, RA_CELL = 0, 1
@@ -130,6 +136,7 @@ SYMBOLS = {
     "sphy_scan_tile_cells": (C.c_int, []),
     "sphy_mmf_step": (C.c_int, [P, C.POINTER(Mmf), C.c_int, P]),
     "sphy_accucapacity": (C.c_int, [P, P, P, P, P, P]),
+    "sphy_sed_reservoir_route": (C.c_int, [P, C.POINTER(SedRes), P, P, P, P, P, P]),
     "sphy_glac_report": (C.c_int, [P, C.c_int32, P, P, P, C.c_int32, P, P, P, P]),
     "sphy_veg_step": (C.c_int, [P, C.POINTER(WbParams), C.POINTER(Veg), C.c_int, P]),
     "sphy_wb_step": (C.c_int, [P, C.POINTER(WbParams), C.POINTER(WbState), C.POINTER(WbForcing), C.POINTER(WbOut),
@@ -145,7 +152,7 @@ SYMBOLS = {
     "sphy_route_reslake_step": (C.c_int, [P, C.POINTER(ResLake), P, P, SphyParam, C.c_float, C.c_int, C.c_int, P]),
 }
 
-ABI_STRUCTS = (SphyParam, WbParams, WbState, WbForcing, WbOut, GlacTable, GlacOut, ResLake, OpenWater, Veg, Mmf)
+ABI_STRUCTS = (SphyParam, WbParams, WbState, WbForcing, WbOut, GlacTable, GlacOut, ResLake, OpenWater, Veg, Mmf, SedRes)
 
 _LIB = None
 

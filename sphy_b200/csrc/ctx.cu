@@ -147,6 +147,7 @@ extern "C" size_t sphy_abi_sizeof(int which)
         case 8: return sizeof(sphy_openwater);
         case 9: return sizeof(sphy_veg);
         case 10: return sizeof(sphy_mmf);
+        case 11: return sizeof(sphy_sedres);
         default: return 0;
     }
 }

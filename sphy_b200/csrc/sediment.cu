@@ -92,3 +92,88 @@ extern "C" int sphy_mmf_step(sphy_ctx *ctx, const sphy_mmf *p, int day_of_year, 
     SPHY_LAUNCH_CHECK(ctx);
     return SPHY_OK;
 }
+
+// ---- sediment transport through reservoirs (modules/sediment_transport.py:46-107) -----------------------------------
+// The reference routes the sub-catchments of the reservoirs step by step (resorder.txt): capacity sweep, then per
+// reservoir of the step: trapped yield, the sub-catchment is marked finished and emptied, the untrapped part is
+// handed to the cell below the dam.  Here every step is: sphy_accucapacity sweep -> k_sedres_collect (one thread per
+// reservoir) -> k_sedres_update (per cell: accumulate flux / deposition, rebuild the material of the next sweep) ->
+// k_sedres_outflows (the few dam outflows, added in the reference's order by ONE thread so that sums are identical).
+// An outflow added at iteration g survives in the material as long as the sub-catchment of its target cell has not been
+// finished by a LATER iteration (the reference zeroes every finished sub-catchment again at each iteration).
+namespace {
+
+__global__ void k_sedres_prepare(const sphy_sedres r, const float *sed, const float *tc, int64_t n, float *yield, float *dep, float *flux)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    r.sed_trans[i] = sed[i];
+    r.tc_route[i] = r.extent[i] > 0 ? 1e10f : tc[i];            // sediment_transport.py:57
+    yield[i] = 0.0f; dep[i] = 0.0f; flux[i] = 0.0f;
+}
+
+__global__ void k_sedres_collect(const sphy_sedres r, int step, float *yield)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= r.n_res || r.res_step[s] != step) return;
+    const float f = r.cap_flux[r.res_cell[s]];
+    yield[r.res_cell[s]] = f * r.trap_eff[s];                   // sediment_transport.py:79
+    r.outflow[s] = f * r.outflow_eff[s];                        // sediment_transport.py:87
+}
+
+__global__ void k_sedres_update(const sphy_sedres r, const float *sed, int step, int64_t n, float *dep, float *flux)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int fs = r.finish_step[i];
+    const float finished = fs <= step ? 1.0f : 0.0f, now = fs == step ? 1.0f : 0.0f;
+    flux[i] = r.cap_flux[i] * finished + flux[i];               // sediment_transport.py:93
+    dep[i] = dep[i] + r.cap_state[i] * now;                     // sediment_transport.py:96
+    r.sed_trans[i] = fs <= step ? 0.0f : sed[i];                // sediment_transport.py:85 (outflows are added next)
+}
+
+__global__ void k_sedres_outflows(const sphy_sedres r, int last_seq)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    for (int s = 0; s <= last_seq; ++s) {                       // reservoirs are stored in iteration order
+        const int x = r.res_down[s];
+        if (x < 0) continue;
+        if (s == last_seq || r.down_finish_seq[s] > last_seq) r.sed_trans[x] = r.sed_trans[x] + r.outflow[s];
+    }
+}
+
+__global__ void k_sedres_final(const sphy_sedres r, int last_step, int64_t n, float *flux)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float finished = r.finish_step[i] <= last_step ? 1.0f : 0.0f;
+    flux[i] = r.cap_flux[i] * (1.0f - finished) + flux[i];      // sediment_transport.py:103
+}
+
+}  // namespace
+
+extern "C" int sphy_sed_reservoir_route(sphy_ctx *ctx, const sphy_sedres *r, const float *sed, const float *tc, float *yield,
+                                        float *dep, float *flux, void *stream)
+{
+    if (!ctx || !r || !sed || !tc || !yield || !dep || !flux) return SPHY_E_INVALID;
+    if (!ctx->ldd_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_sed_reservoir_route before sphy_ldd_build");
+    if (r->n_res < 0 || r->n_steps < 1 || !r->finish_step || !r->extent || !r->sed_trans || !r->tc_route || !r->cap_flux ||
+        !r->cap_state || !r->step_last_seq_host)
+        SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_sed_reservoir_route: incomplete sphy_sedres");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = ctx->n;
+    const int grid = (int)div_up(n, 256);
+    k_sedres_prepare<<<grid, 256, 0, st>>>(*r, sed, tc, n, yield, dep, flux);
+    for (int step = 0; step < r->n_steps; ++step) {
+        int rc = sphy_accucapacity(ctx, r->sed_trans, r->tc_route, r->cap_flux, r->cap_state, stream);
+        if (rc != SPHY_OK) return rc;
+        if (r->n_res > 0) k_sedres_collect<<<(int)div_up(r->n_res, 128), 128, 0, st>>>(*r, step, yield);
+        k_sedres_update<<<grid, 256, 0, st>>>(*r, sed, step, n, dep, flux);
+        if (r->step_last_seq_host[step] >= 0) k_sedres_outflows<<<1, 32, 0, st>>>(*r, r->step_last_seq_host[step]);
+    }
+    int rc = sphy_accucapacity(ctx, r->sed_trans, r->tc_route, r->cap_flux, nullptr, stream);
+    if (rc != SPHY_OK) return rc;
+    k_sedres_final<<<grid, 256, 0, st>>>(*r, r->n_steps - 1, n, flux);
+    SPHY_LAUNCH_CHECK(ctx);
+    return SPHY_OK;
+}

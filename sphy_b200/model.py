@@ -1346,7 +1346,7 @@ class SphyModel:
             d.update(DetRn=lambda: so["DetRn"], DetRun=lambda: so["DetRun"], SDepFld=lambda: so["SDepFld"],
                      SedTrans=lambda: so["SedTrans"])
             if self.SedTransFLAG == 1:
-                d.update(TC=lambda: so["TC"], SedDep=lambda: so["SedDep"], SedYld=lambda: so["SedDep"], SedFlux=lambda: so["SedFlux"])
+                d.update(TC=lambda: so["TC"], SedDep=lambda: so["SedDep"], SedYld=lambda: so["SedYld"], SedFlux=lambda: so["SedFlux"])
         d["TotRF"] = lambda: self.TotR
         if self.RootRR is not None:
             d.update(TotRootRF=lambda: self.RootRR, TotRootDF=lambda: self.RootDR, TotRainRF=lambda: self.RainR)

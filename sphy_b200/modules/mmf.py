@@ -62,8 +62,11 @@ def init(self, pcr, config):
     path = os.path.join(self.inpath, config.get("MMF", "MMF_table"))
     for j, k in enumerate(TABLE_COLS):
         setattr(self, k, _matrix_lookup(path, j + 1, self.LandUse))
-    if self.ResFLAG == 1:
-        raise NotImplementedError("soil erosion with reservoirs (mmf.py:140-146, sediment_transport.py:46-107) is not supported yet")
+    if self.ResFLAG == 1:                                                                     # mmf.py:133-140
+        if self.ETOpenWaterFLAG == 1:
+            raise NotImplementedError("soil erosion with open-water classes as reservoir extent (mmf.py:135-137) is not supported yet")
+        self.Reservoirs = self._compact_np(self._readmap(config.get("RESERVOIR", "reservoirs")), np.int32)
+        self.NoErosion = np.minimum(self.NoErosion + self.Reservoirs.astype(np.float32), f32(1))
     self.harvest_FLAG = config.getfloat("MMF", "harvestFLAG")
     if self.harvest_FLAG:
         path = os.path.join(self.inpath, config.get("MMF", "MMF_harvest"))
@@ -133,6 +136,7 @@ def prepare(self):
         P.tc_beta = float(f32(self.TC_beta))
         for k in ("TC", "SedDep", "SedFlux"):
             self.sed_out[k] = self._full(0.0)
+        self.sed_out["SedYld"] = self._full(0.0) if self.ResFLAG == 1 else self.sed_out["SedDep"]   # sediment_transport.py:43
         P.TC = self.sed_out["TC"].data_ptr()
     self._mmfP = P
 

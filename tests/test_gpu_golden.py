@@ -69,7 +69,7 @@ def test_model_matches_reference_golden(name, order, route):
                               f"{np.nanmax(np.abs(got - want) / np.maximum(np.abs(want), 1e-30)):.3e}")
             not_bit_equal += int((~bit_equal(got, want)).sum())
             checked += got.size
-        sed = {"DetRn": "DetRn", "DetRun": "DetRun", "SDpFld": "SDepFld", "STrans": "SedTrans", "Sdep": "SedDep", "SdYld": "SedDep",
+        sed = {"DetRn": "DetRn", "DetRun": "DetRun", "SDpFld": "SDepFld", "STrans": "SedTrans", "Sdep": "SedDep", "SdYld": "SedYld",
                "SdFlux": "SedFlux", "TC": "TC"} if model.SedFLAG == 1 else {}
         for rk, ok_ in (("TotR", None), ("ETr", "ETref"), ("ETaF", "ActETact"), ("Infil", "Infil"), ("wbal", "wbal")) + tuple(sed.items()):
             if "report/" + rk not in z.files:
