@@ -44,6 +44,7 @@ struct sphy_ctx {
     std::vector<RoutePlanSeg> plan;
     // scan routing (route_scan.cu): static lists of the cells whose index range crosses a tile boundary + workspaces
     bool scan_ready = false;
+    bool scan_smem_opt_in = false;
     int32_t *cross_r = nullptr, *cross_e = nullptr, *cross_ptr = nullptr, *end_e = nullptr, *end_k = nullptr, *end_ptr = nullptr;
     int32_t n_cross = 0;
     double *park_before = nullptr, *park_end = nullptr;

@@ -481,13 +481,12 @@ static int scan_launch_local(sphy_ctx *ctx, ScanArgs &a, cudaStream_t st)
     const int resident = ctx->sm_count * SCAN_MIN_CTAS;
     const int want = (ctx->n_tiles + SCAN_WARPS - 1) / SCAN_WARPS;       // one tile per warp
     const int grid = want < resident ? want : resident;
-    static bool smem_opt_in = false;
-    if (!smem_opt_in) {
+    if (!ctx->scan_smem_opt_in) {                              // per context: the attribute is per device
         SPHY_CUDA(ctx, cudaFuncSetAttribute(k_scan_main<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM));
         SPHY_CUDA(ctx, cudaFuncSetAttribute(k_scan_main<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM));
         SPHY_CUDA(ctx, cudaFuncSetAttribute(k_scan_main<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM));
         SPHY_CUDA(ctx, cudaFuncSetAttribute(k_scan_main<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM));
-        smem_opt_in = true;
+        ctx->scan_smem_opt_in = true;
     }
     if (a.adv) {
         if (a.kx.map) k_scan_main<true, true><<<grid, SCAN_THREADS, SCAN_SMEM, st>>>(a);
