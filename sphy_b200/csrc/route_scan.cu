@@ -253,29 +253,53 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_MIN_CTAS) k_scan_main(const
 }
 
 // cells whose upstream range crosses a tile boundary
+constexpr int CROSS_ILP = 4;       // crossing cells per thread: four independent gather chains in flight
+
 __global__ void __launch_bounds__(256) k_scan_cross(const __grid_constant__ ScanArgs a)
 {
-    const int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= a.n_cross) return;
-    const int64_t r = __ldg(a.cross_r + k);
-    const int64_t e = __ldg(a.cross_e + k);
-    const int32_t ta = (int32_t)(r / SCAN_TILE), te = (int32_t)(e / SCAN_TILE);
-    const float kx = a.kx.map ? __ldg(a.kx.map + r) : a.kx.value;
-    const float omk = a.kx.map ? 1.0f - kx : a.one_m_kx;
+    const int32_t k0 = blockIdx.x * (256 * CROSS_ILP) + threadIdx.x;
+    int32_t r[CROSS_ILP], e[CROSS_ILP];
+    bool ok[CROSS_ILP];
+#pragma unroll
+    for (int j = 0; j < CROSS_ILP; ++j) {
+        const int32_t k = k0 + j * 256;
+        ok[j] = k < a.n_cross;
+        r[j] = ok[j] ? __ldg(a.cross_r + k) : 0;
+        e[j] = ok[j] ? __ldg(a.cross_e + k) : 0;
+    }
     for (int c = 0; c < a.ncomp; ++c) {
         const double *T = a.tile_tot + (int64_t)c * (a.ntiles + 1);
         const double *X = a.tile_excl + (int64_t)c * (a.ntiles + 1);
-        if (e >= a.n) {                                        // range ends on another rank: keep the part up to the
-            double *pb = a.park_before + (int64_t)c * a.n_cross + k;   // end of this rank's range for k_scan_remote
-            *pb = range_diff(T[ta], *pb) + (ta + 1 < a.ntiles ? range_diff(X[a.ntiles], X[ta + 1]) : 0.0);
-            continue;
-        }
-        // suffix of the first tile + whole tiles in between (none for most crossing cells) + prefix of the last tile
-        const double s = range_diff(T[ta], a.park_before[(int64_t)c * a.n_cross + k]) +
-                         (te > ta + 1 ? range_diff(X[te], X[ta + 1]) : 0.0) + a.park_end[(int64_t)c * (a.n_cross + a.n_pub) + k];
-        const float f = (float)s;
+        double *PB = a.park_before + (int64_t)c * a.n_cross;
+        const double *PE = a.park_end + (int64_t)c * (a.n_cross + a.n_pub);
         float *qs = a.qstate[c];
-        qs[r] = blend(a, r, f, qs[r], kx, omk);
+        double tt[CROSS_ILP], pb[CROSS_ILP], pe[CROSS_ILP];
+        float qold[CROSS_ILP], kx[CROSS_ILP];
+#pragma unroll
+        for (int j = 0; j < CROSS_ILP; ++j) {                  // all gathers first
+            const int32_t k = k0 + j * 256;
+            const bool local = ok[j] && e[j] < a.n;
+            tt[j] = ok[j] ? T[r[j] / SCAN_TILE] : 0.0;
+            pb[j] = ok[j] ? PB[k] : 0.0;
+            pe[j] = local ? PE[k] : 0.0;
+            qold[j] = local ? qs[r[j]] : 0.0f;
+            kx[j] = (ok[j] && a.kx.map) ? __ldg(a.kx.map + r[j]) : a.kx.value;
+        }
+#pragma unroll
+        for (int j = 0; j < CROSS_ILP; ++j) {
+            if (!ok[j]) continue;
+            const int32_t k = k0 + j * 256;
+            const int32_t ta = r[j] / SCAN_TILE, te = e[j] / SCAN_TILE;
+            if (e[j] >= a.n) {                                 // range ends on another rank: keep the part up to the end
+                PB[k] = range_diff(tt[j], pb[j]) +             // of this rank's range for k_scan_remote
+                        (ta + 1 < a.ntiles ? range_diff(X[a.ntiles], X[ta + 1]) : 0.0);
+                continue;
+            }
+            // suffix of the first tile + whole tiles in between (none for most crossing cells) + prefix of the last tile
+            const double s = range_diff(tt[j], pb[j]) + (te > ta + 1 ? range_diff(X[te], X[ta + 1]) : 0.0) + pe[j];
+            const float omk = a.kx.map ? 1.0f - kx[j] : a.one_m_kx;
+            qs[r[j]] = blend(a, r[j], (float)s, qold[j], kx[j], omk);
+        }
     }
 }
 
@@ -500,7 +524,7 @@ static int scan_launch_local(sphy_ctx *ctx, ScanArgs &a, cudaStream_t st)
         SPHY_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->scan_tmp, need, ctx->scan_tile + (size_t)c * (ctx->n_tiles + 1),
                                                      ctx->scan_excl + (size_t)c * (ctx->n_tiles + 1), ctx->n_tiles + 1, st));
     }
-    if (ctx->n_cross > 0) k_scan_cross<<<div_up(ctx->n_cross, 256), 256, 0, st>>>(a);
+    if (ctx->n_cross > 0) k_scan_cross<<<div_up(ctx->n_cross, 256 * CROSS_ILP), 256, 0, st>>>(a);
     return SPHY_OK;
 }
 
