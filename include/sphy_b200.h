@@ -338,10 +338,10 @@ int sphy_upstream(sphy_ctx *ctx, const float *x, float *out, void *stream);
 
 /* ---- K5 + routing with lakes/reservoirs ------------------------------------------------------
  * replaces advanced_routing.dynamic / ROUT (modules/advanced_routing.py:27-38,134-217), lakes.UpdateLakeHStore /
- * QLake (modules/lakes.py:28-158, no measured levels) and reservoirs.QRes/QSimple/QAdv (modules/reservoirs.py:26-86).
+ * QLake (modules/lakes.py:28-158, incl. the assimilation of measured lake levels) and reservoirs.QRes/QSimple/QAdv (modules/reservoirs.py:26-86).
  * Structures are listed once (n_struct cells with QFRAC == 0); kind 1 = simple reservoir, 2 = advanced reservoir,
  * 3 = lake.  par[k][j]: parameter k of structure j (see reslake.cu for the column layout). */
-#define SPHY_RL_NPAR 23
+#define SPHY_RL_NPAR 30
 typedef struct {
     int32_t n_struct;
     const int32_t *cell;             /* compact cell of each structure */
@@ -350,6 +350,10 @@ typedef struct {
     const float *qfrac;              /* dense N-cell QFRAC map (0 at structures, 1 elsewhere; lakes.py:224) */
     float *StorRES;                  /* [n_struct] in/out, m3 */
     float *Qout, *Qin;               /* [n_struct] outputs of the step, m3/day */
+    /* measured lake levels (lakes.py:28-97): NULL on days without a level map; else the level at every structure (NaN =
+     * not measured) and which lakes are gauged (the `updatelakelevel` map) */
+    const float *lake_level;
+    const int32_t *update_level;
 } sphy_reslake;
 
 int sphy_route_reslake_step(sphy_ctx *ctx, const sphy_reslake *rl, const float *totr_mm, float *q_state,

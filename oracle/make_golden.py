@@ -85,6 +85,9 @@ CASES = {
                           n_lakes=2, open_water=True, params=WET, start=(2001, 6, 1)), 50),
     "c3_res_only": (dict(nrows=14, ncols=12, seed=32, cellsize=1000.0, reservoirs=True, n_res_simple=2, n_res_adv=1,
                          params=WETK), 40),
+    # measured lake levels replace the storage of gauged lakes on the days a level map exists (lakes.py:28-97)
+    "c3_lake_levels": (dict(nrows=16, ncols=14, seed=35, cellsize=1000.0, reservoirs=True, lakes=True, n_res_simple=1, n_res_adv=1,
+                            n_lakes=4, lake_levels=True, params=WET, start=(2001, 5, 1)), 30),
     "c3_lake_only": (dict(nrows=14, ncols=12, seed=33, cellsize=1000.0, lakes=True, n_lakes=4, params=WET), 40),
 }
 
@@ -105,7 +108,7 @@ def make(name):
     fkeys = ("prec", "tavg", "tmin", "tmax") + (("etref",) if cat.etref_input else ()) + (("ndvi",) if cat.dynveg else ())
     forcing = {k: np.stack([cat.forcing(t)[k] for t in range(1, nsteps + 1)]) for k in fkeys}
     nan_map = np.full((cat.nrows, cat.ncols), np.nan, np.float32)           # series with gaps: NaN map = no file that day
-    for k, on in (("kc", cat.kc_series), ("seep", cat.seep_series)):
+    for k, on in (("kc", cat.kc_series), ("seep", cat.seep_series), ("llev", cat.lake_levels)):
         if on:
             forcing[k] = np.stack([cat.forcing(t).get(k, nan_map) for t in range(1, nsteps + 1)])
     payload = {"meta": np.array(json.dumps(dict(case=name, nsteps=nsteps, kwargs=CASES[name][0])))}

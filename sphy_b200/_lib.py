@@ -67,7 +67,7 @@ class GlacOut(C.Structure):
 
 class ResLake(C.Structure):
     _fields_ = [("n_struct", C.c_int32), ("cell", P), ("kind", P), ("par", P), ("qfrac", P), ("StorRES", P),
-                ("Qout", P), ("Qin", P)]
+                ("Qout", P), ("Qin", P), ("lake_level", P), ("update_level", P)]
 
 
 class OpenWater(C.Structure):
@@ -100,7 +100,7 @@ class SedRes(C.Structure):
                                     "extent", "step_last_seq_host", "sed_trans", "tc_route", "cap_flux", "cap_state", "outflow")])
 
 
-RL_NPAR = 23
+RL_NPAR = 30
 WB_SNOW, WB_GROUND, WB_INFIL_EXCESS, WB_PWS, WB_ETREF_INPUT = 1, 2, 4, 8, 16
 RA_TABLE, RA_CELL = 0, 1
 ROUTE_LEVELS, ROUTE_SCAN = 0, 1

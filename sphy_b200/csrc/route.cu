@@ -327,8 +327,10 @@ enum {
     RL_KR = 0, RL_B, RL_SMAX,                                   // simple reservoir (reservoirs.py:62-70)
     RL_EVOL, RL_PVOL, RL_MAXFL, RL_DEMFL, RL_FLSTART, RL_FLEND,  // advanced reservoir (reservoirs.py:26-58)
     RL_HS_FUNC, RL_HS_EXPA, RL_HS_EXPB, RL_HS_B, RL_HS_A1, RL_HS_A2, RL_HS_A3,   // lake h(S) (lakes.py:98-131)
-    RL_QH_FUNC, RL_QH_EXPA, RL_QH_EXPB, RL_QH_B,                // lake Q(h); a1..a3 follow in rows 20..22
+    RL_QH_FUNC, RL_QH_EXPA, RL_QH_EXPB, RL_QH_B, RL_QH_A1, RL_QH_A2, RL_QH_A3,   // lake Q(h) (lakes.py:133-158)
+    RL_SH_FUNC, RL_SH_EXPA, RL_SH_EXPB, RL_SH_B, RL_SH_A1, RL_SH_A2, RL_SH_A3,   // lake S(h), measured levels (lakes.py:37-63)
 };
+static_assert(RL_SH_A3 + 1 == SPHY_RL_NPAR, "parameter rows of sphy_reslake.par");
 
 __device__ __forceinline__ float dpowf(float x, float y) { return (float)pow((double)x, (double)y); }
 __device__ __forceinline__ float dexpf(float x) { return (float)exp((double)x); }
@@ -351,6 +353,15 @@ __global__ void k_rl_pre(sphy_reslake rl, const float *__restrict__ totr, float 
     float S = rl.StorRES[j] + vol_factor * totr[c];             // advanced_routing.py:136-138
     float q = 0.0f;
     const int kind = rl.kind[j];
+    // a measured-level map exists for this day (lakes.UpdateLakeHStore, lakes.py:28-97): gauged lakes with a defined
+    // level take their storage from S(h); then the WHOLE storage map is clamped at 0 (reservoirs included, lakes.py:65)
+    float measured = nanf("");
+    if (rl.lake_level) {
+        if (kind == 3 && rl.update_level[j] != 0) measured = rl.lake_level[j];
+        if (measured == measured)
+            S = lake_fun(P(RL_SH_FUNC), P(RL_SH_EXPA), P(RL_SH_EXPB), P(RL_SH_B), P(RL_SH_A1), P(RL_SH_A2), P(RL_SH_A3), measured);
+        S = fmaxf(S, 0.0f);
+    }
     if (kind == 1) {                                            // QSimple
         q = fmaxf(fminf((P(RL_KR) * S) * dpowf(S / P(RL_SMAX), P(RL_B)), S), S - P(RL_SMAX));
     } else if (kind == 2) {                                     // QAdv
@@ -363,8 +374,9 @@ __global__ void k_rl_pre(sphy_reslake rl, const float *__restrict__ totr, float 
         const float den = P(RL_EVOL) - P(RL_PVOL);
         q = fmaxf(flood ? (P(RL_MAXFL) * avail) / den : (P(RL_DEMFL) * avail) / den, S - P(RL_EVOL));
     } else if (kind == 3) {                                     // lake: level from storage, Q from level
-        const float h = lake_fun(P(RL_HS_FUNC), P(RL_HS_EXPA), P(RL_HS_EXPB), P(RL_HS_B), P(RL_HS_A1), P(RL_HS_A2), P(RL_HS_A3), S);
-        const float qh = lake_fun(P(RL_QH_FUNC), P(RL_QH_EXPA), P(RL_QH_EXPB), P(RL_QH_B), P(20), P(21), P(22), h);
+        const float h = measured == measured ? measured
+                                             : lake_fun(P(RL_HS_FUNC), P(RL_HS_EXPA), P(RL_HS_EXPB), P(RL_HS_B), P(RL_HS_A1), P(RL_HS_A2), P(RL_HS_A3), S);
+        const float qh = lake_fun(P(RL_QH_FUNC), P(RL_QH_EXPA), P(RL_QH_EXPB), P(RL_QH_B), P(RL_QH_A1), P(RL_QH_A2), P(RL_QH_A3), h);
         q = (fmaxf(0.0f, qh) * 3600.0f) * 24.0f;                // lakes.py:155-157
     }
     rl.StorRES[j] = S;

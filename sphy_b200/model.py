@@ -822,13 +822,17 @@ class SphyModel:
                 col[16] = _table_col(T["LakeFunc"], 1).get(lid, np.nan)                        # QH func
                 qh = [_table_col(T["LakeQH"], j + 1).get(lid, np.nan) for j in range(6)]
                 col[17], col[18], col[19], col[20], col[21], col[22] = qh
+                col[23] = _table_col(T["LakeFunc"], 2).get(lid, np.nan)                        # SH func (measured levels)
+                for j in range(6):
+                    col[24 + j] = _table_col(T["LakeSH"], j + 1).get(lid, np.nan)              # exp_a exp_b pol_b a1 a2 a3
                 rows[int(c)] = (3, col)
+            self._lake_update = None                                                           # lakes.py:205-213
             if cfg.has_option("LAKE", "updatelakelevel") and cfg.get("LAKE", "updatelakelevel").strip():
                 try:
-                    self._readmap(cfg.get("LAKE", "updatelakelevel"))
-                    raise NotImplementedError("assimilation of measured lake levels is not supported yet")
-                except FileNotFoundError:
-                    pass
+                    self._lake_update = self._compact_np(self._readmap(cfg.get("LAKE", "updatelakelevel")), np.float32) != 0
+                    self.LLevel = cfg.get("LAKE", "LakeFile")
+                except (FileNotFoundError, KeyError, configparser.Error):
+                    self._lake_update = None
         if self.ResFLAG == 1:
             res_id = np.maximum(self._compact_np(self._readmap(cfg.get("RESERVOIR", "ResId")), np.int32), 0)
             fs = _read_matrix_table(os.path.join(self.inpath, cfg.get("RESERVOIR", "ResFuncStor")))
@@ -870,11 +874,17 @@ class SphyModel:
                     "StorRES": self._dev(stor[cells] if ns else np.zeros(1, np.float32)),
                     "Qout": torch.zeros(max(ns, 1), dtype=torch.float32, device=self.device),
                     "Qin": torch.zeros(max(ns, 1), dtype=torch.float32, device=self.device)}
+        if self.LakeFLAG == 1 and self._lake_update is not None:
+            upd = np.broadcast_to(self._lake_update, (n,))[cells].astype(np.int32) if ns else np.zeros(1, np.int32)
+            self._rl["update_level"] = self._dev(upd)
+            self._rl["lake_level"] = torch.zeros(max(ns, 1), dtype=torch.float32, device=self.device)
+            self._rl["cells64"] = self._dev(cells.astype(np.int64) if ns else np.zeros(1, np.int64))
         if self.ETOpenWaterFLAG == 1:
             self._openwater_initial(cells)
         r = self._rl
         self._rl_struct = _lib.ResLake(ns, r["cell"].data_ptr(), r["kind"].data_ptr(), r["par"].data_ptr(),
-                                       self.QFRAC.data_ptr(), r["StorRES"].data_ptr(), r["Qout"].data_ptr(), r["Qin"].data_ptr())
+                                       self.QFRAC.data_ptr(), r["StorRES"].data_ptr(), r["Qout"].data_ptr(), r["Qin"].data_ptr(),
+                                       None, r["update_level"].data_ptr() if "update_level" in r else None)
 
     def _openwater_initial(self, struct_cells):
         """sphy.py:425-431: 8-connected clumps of the open-water mask, each labelled with the largest ResID inside;
@@ -1001,6 +1011,8 @@ class SphyModel:
             P.snow_f, P.one_minus_snow_f = float(f32(self.SnowF)), float(f32(1 - self.SnowF))
             for h in range(1, 25):                                                             # snow.py:30 (3.1415)
                 P.melt_cos[h - 1] = float(f32(math.cos(float(f32(3.1415 * h / 12)))))
+        if self.LakeFLAG == 1 and getattr(self, "_lake_update", None) is not None:
+            self._series["llev"] = (self.LLevel, None)         # measured lake levels: used on the day they exist only
         self._wbP = P
         ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
         S = _lib.WbState()
@@ -1199,8 +1211,15 @@ class SphyModel:
         self._doy = doy
         self._prec_raw = f["prec"]
         for k, (_, last) in self._series.items():                                              # sphy.py:824-830, 992-1000
-            if f.get(k) is not None and f[k] is not last:
+            if last is not None and f.get(k) is not None and f[k] is not last:
                 last.copy_(f[k], non_blocking=True)
+        if "llev" in self._series:                                                             # lakes.py:31-36
+            lev = f.get("llev")
+            if lev is not None:
+                torch.index_select(lev, 0, self._rl["cells64"], out=self._rl["lake_level"])   # plumbing: levels at the structures
+                self._rl_struct.lake_level = self._rl["lake_level"].data_ptr()
+            else:
+                self._rl_struct.lake_level = None
         if self.DynVegFLAG == 1:                                                               # sphy.py:820-822
             v = self._veg_step(f, doy)
             f = dict(f, prec=v["PrecipEff"], etref=v["ETref"])

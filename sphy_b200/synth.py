@@ -133,6 +133,7 @@ class Catchment:
     report_opts: dict = field(default_factory=dict)   # reporting.csv: name -> (map, avg, timeseries) option strings
     kc_series: bool = False              # KCstatic = 0: crop-coefficient map series with gaps (sphy.py:824-830)
     seep_series: bool = False            # SeepStatic = 0 (GroundFLAG = 0): seepage map series with gaps (sphy.py:992-1000)
+    lake_levels: bool = False            # measured lake levels update the lake storage on some days (lakes.py:28-97)
     sediment: dict | None = None         # SedFLAG = 1, MMF erosion (SedModel = 2) + capacity-limited transport: maps and tables
     glac_retreat: tuple | None = None    # (day, month) of the yearly glacier update (GlacRetreat = 1, glacier.py:562-736)
     glac_vars: tuple = ()                # per-glacier reporting (GlacID_flag = 1, glacier.py:501-559): GlacTable columns
@@ -170,6 +171,13 @@ class Catchment:
             out["kc"] = np.clip(0.9 + 0.3 * _smooth_noise(rng, self.nrows, self.ncols, 4), 0.3, 1.4).astype(np.float32)
         if self.seep_series and day % 4 == 0:
             out["seep"] = np.clip(0.4 + 0.4 * _smooth_noise(rng, self.nrows, self.ncols, 4), 0.0, 1.5).astype(np.float32)
+        if self.lake_levels and self.lake_id is not None and day % 5 == 3:
+            lev = np.full((self.nrows, self.ncols), np.nan, np.float32)        # MV where nothing was measured
+            for r_, c_ in zip(*np.nonzero(self.lake_id > 0)):
+                lid = int(self.lake_id[r_, c_])
+                if lid % 2 == 1 and not (lid == 3 and day % 10 == 3):          # lake 3 has gaps in its record
+                    lev[r_, c_] = np.float32(2.0 * rng.uniform(0.85, 1.15))
+            out["llev"] = lev
         if self.dynveg:
             season_v = 0.35 + 0.25 * np.sin(2.0 * np.pi * (doy - 120) / 365.0)
             out["ndvi"] = np.clip(season_v + 0.15 * _smooth_noise(rng, self.nrows, self.ncols, 6)
@@ -208,6 +216,8 @@ class Catchment:
             m["lake_id.map"] = self.lake_id.astype(np.int32)
         if self.open_water_frac is not None:
             m["openwater_frac.map"] = self.open_water_frac.astype(np.float32)
+        if self.lake_levels and self.lake_id is not None:
+            m["update_lakelevel.map"] = (self.lake_id % 2 == 1)               # boolean: lakes with a gauge
         return m
 
     def forcing_map_names(self, day):
@@ -217,6 +227,8 @@ class Catchment:
             names["etref"] = stack_name("forcings/etref", day)
         if self.dynveg:
             names["ndvi"] = stack_name("forcings/ndvi", day)
+        if self.lake_levels and self.lake_id is not None and day % 5 == 3:
+            names["llev"] = stack_name("forcings/llev", day)
         if self.kc_series and day % 3 == 2:
             names["kc"] = stack_name("forcings/kc", day)
         if self.seep_series and day % 4 == 0:
@@ -451,6 +463,8 @@ Rout_components = 1
 [ROUT_INIT]
 {rout_init}[LAKE]
 LakeId = lake_id.map
+{"updatelakelevel = update_lakelevel.map" if self.lake_levels else ""}
+{"LakeFile = forcings/llev" if self.lake_levels else ""}
 LakeStor = lake_stor.tbl
 LakeFunc = lake_function.tbl
 LakeQH = lake_qh.tbl
@@ -535,7 +549,7 @@ def make_catchment(nrows, ncols, cellsize=250.0, seed=1, nsteps=365, snow=False,
                    n_res_simple=0, n_res_adv=0, n_lakes=0, open_water=False, params=None,
                    report_daily=(), soil_classes=1, zrange=None, pws=False, report_opts=None, etref_input=False, mask=None, dynveg=False,
                    glac_retreat=None, glac_vars=(), sediment=False, kc_series=False,
-                   seep_series=False):
+                   seep_series=False, lake_levels=False):
     """Build one of the BASELINE.json synthetic configurations."""
     p = dict(DEFAULT_PARAMS)
     if params:
@@ -571,7 +585,7 @@ def make_catchment(nrows, ncols, cellsize=250.0, seed=1, nsteps=365, snow=False,
                     soil_maps=soil_maps, rout_components=rout_components, infil_excess=infil_excess,
                     report_daily=tuple(report_daily), pws=bool(pws), report_opts=dict(report_opts or {}),
                     etref_input=bool(etref_input), dynveg=bool(dynveg), kc_series=bool(kc_series),
-                    seep_series=bool(seep_series))
+                    seep_series=bool(seep_series), lake_levels=bool(lake_levels))
     if mask == "disk":                    # a non-rectangular catchment: everything outside the disk is MV
         rr, cc = np.ogrid[:nrows, :ncols]
         inside = ((rr - (nrows - 1) / 2.0) / (nrows / 2.0)) ** 2 + ((cc - (ncols - 1) / 2.0) / (ncols / 2.0)) ** 2 <= 1.0

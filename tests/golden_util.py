@@ -48,7 +48,7 @@ def catchment_from_golden(name):
 def golden_forcing(z, t):
     """Stored forcing rasters of model step t (1-based)."""
     out = {k[len("forcing/"):]: z[k][t - 1] for k in z.files if k.startswith("forcing/")}
-    for k in ("kc", "seep"):                                   # map series with gaps: an all-NaN map stands for "no file"
+    for k in ("kc", "seep", "llev"):                                   # map series with gaps: an all-NaN map stands for "no file"
         if k in out and np.isnan(out[k]).all():
             del out[k]
     return out
