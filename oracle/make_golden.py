@@ -54,6 +54,9 @@ CASES = {
     # crop-coefficient and seepage map series with missing days (sphy.py:824-830, 992-1000)
     "c1_kc_seep_series": (dict(nrows=12, ncols=10, seed=26, ground=False, kc_series=True, seep_series=True, params=WET), 30),
     "c1_kc_series": (dict(nrows=12, ncols=10, seed=27, kc_series=True, params=WET), 30),
+    # soil hydraulic properties from texture (PedotransferFLAG = 1, utilities/pedotransfer.py), also feeding the erosion model
+    "c1_pedotransfer": (dict(nrows=12, ncols=10, seed=28, pedotransfer=True, params=WET), 30),
+    "c1_pedo_sed": (dict(nrows=12, ncols=10, seed=29, pedotransfer=True, sediment=True, params=WET, start=(2001, 6, 1)), 25),
     # plant water stress (ET.ks) instead of the wilting-point reduction
     "c1_pws": (dict(nrows=12, ncols=10, seed=15, pws=True, params=WET), 40),
     # reporting.csv driven outputs (utilities/reporting.py): month / year / final maps, averages, long-term sums, TSS

@@ -358,17 +358,22 @@ class SphyModel:
         cn = self._compact_np
         rd = lambda sec, key: cn(self._readmap(cfg.get(sec, key)))  # noqa: E731
         self.PedotransferFLAG = cfg.getint("PEDOTRANSFER", "PedotransferFLAG")
-        if self.PedotransferFLAG == 1:
-            raise NotImplementedError("pedotransfer functions are init-time only and outside the hot path (SURVEY.md section 2)")
         sc = lambda k: f32(cfg.getfloat("SOIL_CAL", k))  # noqa: E731
         self.Slope = rd("GENERAL", "Slope")
         self.Locations = cn(self._readmap(cfg.get("GENERAL", "locations")), np.int32)
-        RootFieldMap = rd("SOIL", "RootFieldMap") * sc("RootFieldFrac")                     # sphy.py:173-192
-        RootSatMap = rd("SOIL", "RootSatMap") * sc("RootSatFrac")
-        RootDryMap = rd("SOIL", "RootDryMap") * sc("RootDryFrac")
-        RootWiltMap = rd("SOIL", "RootWiltMap") * sc("RootWiltFrac")
-        self.RootKsat = rd("SOIL", "RootKsat") * sc("RootKsatFrac")
-        SubSatMap, SubFieldMap, self.SubKsat = rd("SOIL", "SubSatMap"), rd("SOIL", "SubFieldMap"), rd("SOIL", "SubKsat")
+        if self.PedotransferFLAG == 1:                                                         # sphy.py:163-171
+            from .modules import pedotransfer
+            self.pedotransfer = pedotransfer
+            pedotransfer.init(self, None, cfg)
+            RootFieldMap, RootSatMap, RootDryMap, RootWiltMap = self.RootFieldMap, self.RootSatMap, self.RootDryMap, self.RootWiltMap
+            SubSatMap, SubFieldMap = self.SubSatMap, self.SubFieldMap
+        else:
+            RootFieldMap = rd("SOIL", "RootFieldMap") * sc("RootFieldFrac")                 # sphy.py:173-192
+            RootSatMap = rd("SOIL", "RootSatMap") * sc("RootSatFrac")
+            RootDryMap = rd("SOIL", "RootDryMap") * sc("RootDryFrac")
+            RootWiltMap = rd("SOIL", "RootWiltMap") * sc("RootWiltFrac")
+            self.RootKsat = rd("SOIL", "RootKsat") * sc("RootKsatFrac")
+            SubSatMap, SubFieldMap, self.SubKsat = rd("SOIL", "SubSatMap"), rd("SOIL", "SubFieldMap"), rd("SOIL", "SubKsat")
         self.RootDrainVel = self.RootKsat * self.Slope                                        # sphy.py:198
         for k in ("CapRiseMax", "RootDepthFlat", "SubDepthFlat"):                              # sphy.py:201-206
             setattr(self, k, self._scalar_or_map("SOILPARS", k))

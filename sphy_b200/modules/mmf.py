@@ -48,12 +48,11 @@ def FlowVelocity(self, pcr, manning, waterDepth):
 
 def init(self, pcr, config):
     """mmf.init (mmf.py:107-190)."""
-    if self.PedotransferFLAG != 0:
-        raise NotImplementedError("pedotransfer functions are not supported: give RootSandMap / RootClayMap")
-    rd = lambda k: self._compact_np(self._readmap(config.get("PEDOTRANSFER", k)))  # noqa: E731
-    self.RootSandMap = rd("RootSandMap") / f32(100)
-    self.RootClayMap = rd("RootClayMap") / f32(100)
-    self.RootSiltMap = f32(1) - self.RootSandMap - self.RootClayMap
+    if self.PedotransferFLAG == 0:                                                            # mmf.py:109-112
+        rd = lambda k: self._compact_np(self._readmap(config.get("PEDOTRANSFER", k)))  # noqa: E731
+        self.RootSandMap = rd("RootSandMap") / f32(100)
+        self.RootClayMap = rd("RootClayMap") / f32(100)
+        self.RootSiltMap = f32(1) - self.RootSandMap - self.RootClayMap
     try:
         self.PrecInt = config.getfloat("MMF", "PrecInt")
     except ValueError:

@@ -133,6 +133,7 @@ class Catchment:
     report_opts: dict = field(default_factory=dict)   # reporting.csv: name -> (map, avg, timeseries) option strings
     kc_series: bool = False              # KCstatic = 0: crop-coefficient map series with gaps (sphy.py:824-830)
     seep_series: bool = False            # SeepStatic = 0 (GroundFLAG = 0): seepage map series with gaps (sphy.py:992-1000)
+    pedotransfer: dict | None = None     # PedotransferFLAG = 1: soil hydraulic properties from sand/clay/organic matter (utilities/pedotransfer.py)
     lake_levels: bool = False            # measured lake levels update the lake storage on some days (lakes.py:28-97)
     sediment: dict | None = None         # SedFLAG = 1, MMF erosion (SedModel = 2) + capacity-limited transport: maps and tables
     glac_retreat: tuple | None = None    # (day, month) of the yearly glacier update (GlacRetreat = 1, glacier.py:562-736)
@@ -199,6 +200,10 @@ class Catchment:
             "landuse.map": (np.broadcast_to(np.int32(1), (self.nrows, self.ncols)) if self.sediment is None
                             else self.sediment["landuse"]),
         }
+        if self.pedotransfer is not None:
+            for k, v in self.pedotransfer.items():
+                if isinstance(v, np.ndarray):
+                    m[k + ".map"] = v
         if self.sediment is not None and "reservoirs" in self.sediment:
             m["reservoirs_nominal.map"] = self.sediment["reservoirs"]
         if self.sediment is not None:
@@ -339,9 +344,15 @@ SubFieldMap = sub_field.map
 SubSatMap = sub_sat.map
 SubKsat = sub_ksat.map
 [PEDOTRANSFER]
-PedotransferFLAG = 0
+PedotransferFLAG = {1 if self.pedotransfer else 0}
 RootSandMap = root_sand.map
 RootClayMap = root_clay.map
+RootOMMap = root_OM.map
+RootBulkMap = 1
+SubSandMap = sub_sand.map
+SubClayMap = sub_clay.map
+SubOMMap = sub_OM.map
+SubBulkMap = sub_bulk.map
 [SEDIMENT]
 SedModel = 2
 RockFrac = rock_fraction.map
@@ -549,7 +560,7 @@ def make_catchment(nrows, ncols, cellsize=250.0, seed=1, nsteps=365, snow=False,
                    n_res_simple=0, n_res_adv=0, n_lakes=0, open_water=False, params=None,
                    report_daily=(), soil_classes=1, zrange=None, pws=False, report_opts=None, etref_input=False, mask=None, dynveg=False,
                    glac_retreat=None, glac_vars=(), sediment=False, kc_series=False,
-                   seep_series=False, lake_levels=False):
+                   seep_series=False, lake_levels=False, pedotransfer=False):
     """Build one of the BASELINE.json synthetic configurations."""
     p = dict(DEFAULT_PARAMS)
     if params:
@@ -593,8 +604,17 @@ def make_catchment(nrows, ncols, cellsize=250.0, seed=1, nsteps=365, snow=False,
         cat.mask = inside
         cat.ldd = np.where(inside, cat.ldd, 255).astype(np.uint8)
         cat.locations = np.where(inside, cat.locations, 0).astype(np.int32)
+    if pedotransfer:                      # texture in percent, organic matter in % weight, bulk-density factor
+        r3 = np.random.default_rng([seed, 606])
+        tex = lambda mean, amp, lo, hi: np.clip(mean + amp * _smooth_noise(r3, nrows, ncols, 5), lo, hi).astype(np.float32)  # noqa: E731
+        cat.pedotransfer = dict(root_sand=tex(45.0, 20.0, 15.0, 75.0), root_clay=tex(22.0, 8.0, 8.0, 20.0 + 15.0),
+                                root_OM=tex(2.5, 1.0, 0.5, 5.0), sub_sand=tex(50.0, 20.0, 15.0, 80.0),
+                                sub_clay=tex(20.0, 8.0, 5.0, 35.0), sub_OM=tex(1.0, 0.5, 0.1, 3.0),
+                                sub_bulk=tex(1.02, 0.05, 0.9, 1.15))
     if sediment:
         _add_sediment(cat, seed, sediment if isinstance(sediment, dict) else {})
+        if cat.pedotransfer is not None:  # one texture for both modules
+            cat.sediment["sand"], cat.sediment["clay"] = cat.pedotransfer["root_sand"], cat.pedotransfer["root_clay"]
     if glacier:
         _add_glaciers(cat, rng)
         cat.glac_vars = tuple(glac_vars)
