@@ -336,6 +336,16 @@ int sphy_accuflux(sphy_ctx *ctx, const float *material, const float *fraction /*
                   void *stream);
 int sphy_upstream(sphy_ctx *ctx, const float *x, float *out, void *stream);
 
+/* The same exchange over peer memory (NVLink P2P through CUDA IPC) instead of an NCCL all-gather: every rank stores its
+ * block straight into the peers' receive buffers and releases a per-peer flag; a bounded wait acquires the flags of all
+ * peers.  sphy_p2p_setup_local allocates this rank's buffers (`pitch` >= ncomp * stride float64 per rank) and returns two
+ * 64-byte CUDA IPC handles; the host exchanges them (any transport) and calls sphy_p2p_connect with all of them, ordered by
+ * rank.  Per step: sphy_route_scan_begin -> sphy_route_scan_exchange_p2p -> sphy_route_scan_finish(gathered_dev = NULL). */
+int sphy_p2p_setup_local(sphy_ctx *ctx, int world, int64_t pitch, unsigned char *handle_recv64, unsigned char *handle_flags64);
+int sphy_p2p_connect(sphy_ctx *ctx, int rank, int world, const unsigned char *handles_recv, const unsigned char *handles_flags);
+int sphy_route_scan_exchange_p2p(sphy_ctx *ctx, int ncomp, const double *send_dev, int32_t stride, void *stream);
+int sphy_p2p_timed_out(sphy_ctx *ctx, void *stream);
+
 /* ---- K5 + routing with lakes/reservoirs ------------------------------------------------------
  * replaces advanced_routing.dynamic / ROUT (modules/advanced_routing.py:27-38,134-217), lakes.UpdateLakeHStore /
  * QLake (modules/lakes.py:28-158, incl. the assimilation of measured lake levels) and reservoirs.QRes/QSimple/QAdv (modules/reservoirs.py:26-86).

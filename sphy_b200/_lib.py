@@ -104,6 +104,7 @@ RL_NPAR = 30
 WB_SNOW, WB_GROUND, WB_INFIL_EXCESS, WB_PWS, WB_ETREF_INPUT = 1, 2, 4, 8, 16
 RA_TABLE, RA_CELL = 0, 1
 ROUTE_LEVELS, ROUTE_SCAN = 0, 1
+ROUTE_MAX_COMP = 8                    # routed components per call (csrc/common.cuh)
 ORDER_ROWMAJOR, ORDER_DFS = 0, 1
 SCAN_TILE = 1024                      # cells per scan-routing tile (csrc/route_scan.cu)
 OPS = ("EXTRARAD", "HARGREAVES", "ETPOT", "ETACT", "KS", "POTSNOWMELT", "ACTSNOWMELT", "SNOWSTOREUPDATE", "MAXSNOWWATSTORAGE",
@@ -134,6 +135,10 @@ SYMBOLS = {
     "sphy_set_ncells": (C.c_int, [P, C.c_int64]),
     "sphy_module_op": (C.c_int, [P, C.c_int, C.POINTER(SphyParam), C.c_int, C.POINTER(P), C.c_int, C.c_int64, C.c_float, C.c_int, P]),
     "sphy_scan_tile_cells": (C.c_int, []),
+    "sphy_p2p_setup_local": (C.c_int, [P, C.c_int, C.c_int64, P, P]),
+    "sphy_p2p_connect": (C.c_int, [P, C.c_int, C.c_int, P, P]),
+    "sphy_route_scan_exchange_p2p": (C.c_int, [P, C.c_int, P, C.c_int32, P]),
+    "sphy_p2p_timed_out": (C.c_int, [P, P]),
     "sphy_mmf_step": (C.c_int, [P, C.POINTER(Mmf), C.c_int, P]),
     "sphy_accucapacity": (C.c_int, [P, P, P, P, P, P]),
     "sphy_sed_reservoir_route": (C.c_int, [P, C.POINTER(SedRes), P, P, P, P, P, P]),

@@ -45,6 +45,13 @@ struct sphy_ctx {
     // scan routing (route_scan.cu): static lists of the cells whose index range crosses a tile boundary + workspaces
     bool scan_ready = false;
     bool scan_smem_opt_in = false;
+    // confluence exchange over peer memory (route_scan.cu)
+    double *p2p_recv = nullptr, **p2p_peer_recv = nullptr;
+    long long *p2p_flags = nullptr, **p2p_peer_flags = nullptr;
+    void *p2p_opened[128] = {};
+    int p2p_nopened = 0, p2p_world = 0, p2p_rank = 0;
+    int64_t p2p_pitch = 0;
+    long long p2p_step = 0;
     int32_t *cross_r = nullptr, *cross_e = nullptr, *cross_ptr = nullptr, *end_e = nullptr, *end_k = nullptr, *end_ptr = nullptr;
     int32_t n_cross = 0;
     double *park_before = nullptr, *park_end = nullptr;

@@ -38,6 +38,10 @@ extern "C" void sphy_ctx_destroy(sphy_ctx *ctx)
                     ctx->ra_table, ctx->tmp_n[0], ctx->tmp_n[1], ctx->tmp_n[2], ctx->tmp_n[3]};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    for (int i = 0; i < ctx->p2p_nopened; ++i) cudaIpcCloseMemHandle(ctx->p2p_opened[i]);
+    void *p2p[] = {ctx->p2p_recv, ctx->p2p_flags, ctx->p2p_peer_recv, ctx->p2p_peer_flags};
+    for (void *p : p2p)
+        if (p) cudaFree(p);
     delete ctx;
 }
 

@@ -49,6 +49,7 @@ struct ScanArgs {
     double *send;                         // [ncomp][stride]: range total, then range-local inclusive prefix at pub_e[j]
     const double *gathered;               // [world][ncomp][stride]
     int32_t stride, rank, world;
+    int64_t rank_pitch;                   // elements between two ranks' blocks in `gathered`
     // lakes / reservoirs (advanced_routing.ROUT): material is already m3/day, cut cells take the structure outflow
     int adv;
     const float *frac;                    // dense QFRAC (0 at lake / reservoir cells)
@@ -327,8 +328,8 @@ __global__ void k_scan_remote(const __grid_constant__ ScanArgs a)
     const float omk = a.kx.map ? 1.0f - kx : a.one_m_kx;
     for (int c = 0; c < a.ncomp; ++c) {
         double s = a.park_before[(int64_t)c * a.n_cross + k];                     // r .. end of this rank's range
-        for (int u = a.rank + 1; u < q; ++u) s += a.gathered[((int64_t)u * a.ncomp + c) * a.stride];   // whole ranks in between
-        s += a.gathered[((int64_t)q * a.ncomp + c) * a.stride + 1 + slot];        // start of rank q's range .. range end
+        for (int u = a.rank + 1; u < q; ++u) s += a.gathered[(int64_t)u * a.rank_pitch + (int64_t)c * a.stride];   // whole ranks in between
+        s += a.gathered[(int64_t)q * a.rank_pitch + (int64_t)c * a.stride + 1 + slot];        // start of rank q's range .. range end
         float *qs = a.qstate[c];
         qs[r] = blend(a, r, (float)s, qs[r], kx, omk);
     }
@@ -662,18 +663,141 @@ extern "C" int sphy_route_scan_begin(sphy_ctx *ctx, int ncomp, const float *cons
 extern "C" int sphy_route_scan_finish(sphy_ctx *ctx, int ncomp, float *const *q_state, sphy_param kx, float one_minus_kx,
                                       const double *gathered_dev, int32_t stride, int rank, int world, void *stream)
 {
-    if (!ctx || !q_state || !gathered_dev || ncomp < 1 || ncomp > ROUTE_MAX_COMP || rank < 0 || rank >= world) return SPHY_E_INVALID;
+    if (!ctx || !q_state || ncomp < 1 || ncomp > ROUTE_MAX_COMP || rank < 0 || rank >= world) return SPHY_E_INVALID;
+    if (!gathered_dev && !ctx->p2p_recv) SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_route_scan_finish: no gathered buffer and no peer exchange set up");
     if (!ctx->scan_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_route_scan_finish before sphy_route_scan_begin");
     if (ctx->n_remote == 0) return SPHY_OK;
     cudaStream_t st = (cudaStream_t)stream;
     ScanArgs a;
     int rc = scan_prepare(ctx, ncomp, nullptr, q_state, kx, one_minus_kx, st, a);
     if (rc != SPHY_OK) return rc;
-    a.gathered = gathered_dev;
+    if (gathered_dev) {
+        a.gathered = gathered_dev;
+        a.rank_pitch = (int64_t)ncomp * stride;
+    } else {                                      // what the peers stored into this rank's buffer (sphy_route_scan_exchange_p2p)
+        const int parity = (int)((ctx->p2p_step - 1) & 1);
+        a.gathered = ctx->p2p_recv + (size_t)parity * ctx->p2p_world * ctx->p2p_pitch;
+        a.rank_pitch = ctx->p2p_pitch;
+    }
     a.stride = stride;
     a.rank = rank;
     a.world = world;
     k_scan_remote<<<div_up(ctx->n_remote, 256), 256, 0, st>>>(a);
     SPHY_LAUNCH_CHECK(ctx);
     return SPHY_OK;
+}
+
+// ---- confluence exchange over peer memory (NVLink P2P) instead of an NCCL all-gather -------------------------------------
+// The message is a few thousand float64 per rank and purely latency-bound.  Every rank owns a receive buffer
+// [2 parities][world][pitch] and a flag per peer, allocated with cudaMalloc and opened on the other ranks through CUDA
+// IPC.  Per step: k_p2p_push (one CTA per peer) stores this rank's block straight into every peer's buffer and
+// releases `flag[rank] = step` with system scope; k_p2p_wait acquires the flags of all peers before the trunk cells
+// are finished.  Double buffering by step parity is enough: a rank can only be one exchange ahead of a peer, because
+// its next push comes after a wait on that peer's current flag.  The wait is bounded (no hang if a peer dies).
+namespace {
+
+__global__ void __launch_bounds__(256) k_p2p_push(const double *__restrict__ send, int count, double *const *peer_recv,
+                                                   long long *const *peer_flags, int rank, int world, int64_t pitch, int parity,
+                                                   long long step)
+{
+    const int p = blockIdx.x;
+    double *dst = peer_recv[p] + ((size_t)parity * world + rank) * pitch;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = send[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(peer_flags[p] + rank), "l"(step) : "memory");
+}
+
+__global__ void k_p2p_wait(const long long *flags, int world, long long step, int *timed_out)
+{
+    const int q = threadIdx.x;
+    if (q >= world) return;
+    long long v = 0;
+    for (long long it = 0; it < 40000000LL; ++it) {             // ~ 4 s of 100 ns naps, then give up
+        asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(flags + q) : "memory");
+        if (v >= step) return;
+        __nanosleep(100);
+    }
+    *timed_out = 1;
+}
+
+}  // namespace
+
+extern "C" int sphy_p2p_setup_local(sphy_ctx *ctx, int world, int64_t pitch, unsigned char *handle_recv64, unsigned char *handle_flags64)
+{
+    if (!ctx || world < 2 || world > 64 || pitch < 1 || !handle_recv64 || !handle_flags64) return SPHY_E_INVALID;
+    if (ctx->p2p_recv) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_p2p_setup_local: already set up");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    const size_t nrecv = (size_t)2 * world * pitch;
+    SPHY_CUDA(ctx, cudaMalloc(&ctx->p2p_recv, nrecv * sizeof(double)));
+    SPHY_CUDA(ctx, cudaMalloc(&ctx->p2p_flags, (size_t)(world + 1) * sizeof(long long)));   // + the time-out word
+    SPHY_CUDA(ctx, cudaMemset(ctx->p2p_recv, 0, nrecv * sizeof(double)));
+    SPHY_CUDA(ctx, cudaMemset(ctx->p2p_flags, 0, (size_t)(world + 1) * sizeof(long long)));
+    SPHY_CUDA(ctx, cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    SPHY_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->p2p_recv));
+    memcpy(handle_recv64, &h, 64);
+    SPHY_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->p2p_flags));
+    memcpy(handle_flags64, &h, 64);
+    ctx->p2p_world = world;
+    ctx->p2p_pitch = pitch;
+    return SPHY_OK;
+}
+
+extern "C" int sphy_p2p_connect(sphy_ctx *ctx, int rank, int world, const unsigned char *handles_recv, const unsigned char *handles_flags)
+{
+    if (!ctx || !handles_recv || !handles_flags || rank < 0 || rank >= world) return SPHY_E_INVALID;
+    if (!ctx->p2p_recv || world != ctx->p2p_world) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_p2p_connect before sphy_p2p_setup_local");
+    double *recv[64];
+    long long *flags[64];
+    for (int p = 0; p < world; ++p) {
+        if (p == rank) {
+            recv[p] = ctx->p2p_recv;
+            flags[p] = ctx->p2p_flags;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        void *ptr = nullptr;
+        memcpy(&h, handles_recv + (size_t)p * 64, 64);
+        SPHY_CUDA(ctx, cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        recv[p] = (double *)ptr;
+        memcpy(&h, handles_flags + (size_t)p * 64, 64);
+        SPHY_CUDA(ctx, cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        flags[p] = (long long *)ptr;
+        ctx->p2p_opened[ctx->p2p_nopened++] = recv[p];
+        ctx->p2p_opened[ctx->p2p_nopened++] = flags[p];
+    }
+    SPHY_CUDA(ctx, cudaMalloc(&ctx->p2p_peer_recv, sizeof(double *) * world));
+    SPHY_CUDA(ctx, cudaMalloc(&ctx->p2p_peer_flags, sizeof(long long *) * world));
+    SPHY_CUDA(ctx, cudaMemcpy(ctx->p2p_peer_recv, recv, sizeof(double *) * world, cudaMemcpyHostToDevice));
+    SPHY_CUDA(ctx, cudaMemcpy(ctx->p2p_peer_flags, flags, sizeof(long long *) * world, cudaMemcpyHostToDevice));
+    ctx->p2p_rank = rank;
+    ctx->p2p_step = 0;
+    return SPHY_OK;
+}
+
+extern "C" int sphy_route_scan_exchange_p2p(sphy_ctx *ctx, int ncomp, const double *send_dev, int32_t stride, void *stream)
+{
+    if (!ctx || !send_dev || ncomp < 1 || ncomp > ROUTE_MAX_COMP) return SPHY_E_INVALID;
+    if (!ctx->p2p_peer_recv) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_route_scan_exchange_p2p before sphy_p2p_connect");
+    const int64_t count = (int64_t)ncomp * stride;
+    if (count > ctx->p2p_pitch) SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_route_scan_exchange_p2p: %lld values exceed the buffer pitch", (long long)count);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long step = ++ctx->p2p_step;
+    const int parity = (int)((step - 1) & 1);
+    k_p2p_push<<<ctx->p2p_world, 256, 0, st>>>(send_dev, (int)count, ctx->p2p_peer_recv, ctx->p2p_peer_flags, ctx->p2p_rank,
+                                               ctx->p2p_world, ctx->p2p_pitch, parity, step);
+    k_p2p_wait<<<1, 64, 0, st>>>(ctx->p2p_flags, ctx->p2p_world, step, reinterpret_cast<int *>(ctx->p2p_flags + ctx->p2p_world));
+    SPHY_LAUNCH_CHECK(ctx);
+    return SPHY_OK;
+}
+
+// 1 if a bounded wait of sphy_route_scan_exchange_p2p gave up since the last call (synchronises the stream)
+extern "C" int sphy_p2p_timed_out(sphy_ctx *ctx, void *stream)
+{
+    if (!ctx || !ctx->p2p_flags) return 0;
+    long long w = 0;
+    if (cudaMemcpyAsync(&w, ctx->p2p_flags + ctx->p2p_world, sizeof(w), cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess) return 1;
+    if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) return 1;
+    return w != 0;
 }

@@ -207,6 +207,8 @@ class SphyModel:
     def close(self):
         if getattr(self, "_ctx", None):
             torch.cuda.synchronize(self.device)
+            if getattr(self, "_mg_p2p", False) and self.lib.sphy_p2p_timed_out(self._ctx, self._stream()):
+                raise RuntimeError("a peer-memory confluence exchange timed out: discharges of this run are not valid")
             if self._owns_ctx:
                 self.lib.sphy_ctx_destroy(self._ctx)
             self._ctx = None
@@ -1335,12 +1337,41 @@ class SphyModel:
         if getattr(self, "_mg_send", None) is None or self._mg_send.shape[0] != nc:
             self._mg_send = torch.zeros((nc, self._mg_stride), dtype=torch.float64, device=self.device)
             self._mg_recv = torch.zeros((self.world, nc, self._mg_stride), dtype=torch.float64, device=self.device)
+        if getattr(self, "_mg_p2p", None) is None:
+            self._mg_p2p = self._p2p_connect()
         self._ck(self.lib.sphy_route_scan_begin(self._ctx, nc, srcp, dstp, self._kx, C.c_float(self._one_m_kx),
                                                 self._mg_send.data_ptr(), self._mg_stride, st), "sphy_route_scan_begin")
-        dist.all_gather_into_tensor(self._mg_recv.view(-1), self._mg_send.view(-1))
+        if self._mg_p2p:                           # stores into the peers' buffers over NVLink + flags, no collective call
+            self._ck(self.lib.sphy_route_scan_exchange_p2p(self._ctx, nc, self._mg_send.data_ptr(), self._mg_stride, st),
+                     "sphy_route_scan_exchange_p2p")
+            gathered = None
+        else:
+            dist.all_gather_into_tensor(self._mg_recv.view(-1), self._mg_send.view(-1))
+            gathered = self._mg_recv.data_ptr()
         self._ck(self.lib.sphy_route_scan_finish(self._ctx, nc, dstp, self._kx, C.c_float(self._one_m_kx),
-                                                 self._mg_recv.data_ptr(), self._mg_stride, self.rank, self.world, st),
+                                                 gathered, self._mg_stride, self.rank, self.world, st),
                  "sphy_route_scan_finish")
+
+    def _p2p_connect(self):
+        """Set up the peer-memory confluence exchange (CUDA IPC handles exchanged once through torch.distributed).  Falls
+        back to the NCCL all-gather when SPHY_MG_EXCHANGE=nccl, on a non-NCCL backend or if any rank cannot open its peers."""
+        import torch.distributed as dist
+        if os.environ.get("SPHY_MG_EXCHANGE", "p2p").lower() != "p2p" or dist.get_backend() != "nccl":
+            return False
+        h = (C.c_ubyte * 128)()
+        rc = self.lib.sphy_p2p_setup_local(self._ctx, self.world, _lib.ROUTE_MAX_COMP * self._mg_stride,
+                                           C.cast(h, C.c_void_p), C.c_void_p(C.addressof(h) + 64))
+        mine = torch.tensor(list(bytes(h)) + [int(rc == 0)], dtype=torch.uint8, device=self.device)
+        every = torch.empty(self.world * 129, dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(every, mine)
+        every = every.cpu().numpy().reshape(self.world, 129)
+        ok = bool(every[:, 128].all())
+        if ok:
+            recv_h, flag_h = every[:, :64].tobytes(), every[:, 64:128].tobytes()
+            ok = self.lib.sphy_p2p_connect(self._ctx, self.rank, self.world, recv_h, flag_h) == 0
+        agree = torch.tensor([int(ok)], dtype=torch.int32, device=self.device)
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+        return bool(agree.item())
 
     def reportable(self):
         """reporting.csv variable name -> callable giving the device map of the day (utilities/reporting.py call sites in

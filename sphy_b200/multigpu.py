@@ -166,8 +166,10 @@ def bench_main(args, rank, world):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": bench.workload_name(args.size), "cells": n_global, "cells_per_gpu": n_local,
-                       "partition": f"{world} contiguous DFS-order ranges (sub-basins + trunk pieces), per-step all-gather of "
-                                    f"{model._mg_stride} float64 per rank (confluence exchange over NCCL)",
+                       "partition": f"{world} contiguous DFS-order ranges (sub-basins + trunk pieces), per-step exchange of "
+                                    f"{model._mg_stride} float64 per rank (confluence inflows; "
+                                    + ("stores into peer memory over NVLink + flags" if getattr(model, "_mg_p2p", False)
+                                       else "NCCL all-gather") + ")",
                        "routing": "scan", "forcing_ring_days": args.ring, "setup_s": round(setup_s, 1),
                        "l2": "per-GPU per-step working set %.2f GB (larger than the 126 MB L2)" % (bench.ALG_BYTES_WB * n_local / 1e9)},
             "roofline": {"kernel": "k_wb_step (fused vertical water balance), rank 0", "bound": "hbm", "achieved": ach, "peak": peak,
