@@ -82,3 +82,83 @@ def test_water_balance_closes_on_a_large_raster():
     torch.cuda.synchronize()
     assert torch.isfinite(model.QRAold).all() and float(model.QRAold.min().item()) >= 0.0
     model.close()
+
+
+def test_full_size_basin_properties(monkeypatch):
+    """BASELINE config 4 at its full size (10 000 x 10 000 = 1e8 cells), where no CPU oracle can follow: (i) the prefetching
+    water-balance kernel that large grids run is bit-identical with the plain one, (ii) scan routing agrees with the
+    bit-exact level sweep, never goes negative and routes exactly 0 out of dry sub-catchments, (iii) at kx = 0 the
+    discharge at the outlet is the basin's total runoff (mass conservation through 18 000 levels)."""
+    import torch
+    import bench
+    from sphy_b200 import _lib
+    from sphy_b200.model import CatchmentSource, SphyModel
+    size = int(os.environ.get("SPHY_TEST_FULL_SIZE", "10000"))
+    cat = bench.make_case(size)
+    tmp = tempfile.mkdtemp(prefix="sphy_full_")
+    cfg = cat.write_inputs(os.path.join(tmp, "in"), os.path.join(tmp, "out"))
+    a = SphyModel(cfg, CatchmentSource(cat), route_method="scan", collect_tss=False)
+    a.initial()
+    b = SphyModel(cfg, CatchmentSource(cat), route_method="levels", collect_tss=False, share_from=a)   # same context, own states
+    b.initial()
+    n = a.n
+    assert n == size * size
+    dem = torch.from_numpy(a._compact_np(cat.dem)).to(a.device)
+    ring = bench.device_forcing_ring(torch, dem, 2, seed=99)
+    del dem
+    a.set_device_forcing(lambda t: ring[t % 2])
+    b.set_device_forcing(lambda t: ring[t % 2])
+    keys = ("RootWater", "SubWater", "CapRise", "RootDrain", "GwRecharge", "Gw", "BaseR", "H_gw", "TotR")
+    for step in range(3):
+        monkeypatch.setenv("SPHY_WB_PREFETCH", "1")
+        a.dynamic()
+        monkeypatch.setenv("SPHY_WB_PREFETCH", "0")
+        b.dynamic()
+        torch.cuda.synchronize()
+        for k in keys:                                                        # (i)
+            assert torch.equal(getattr(a, k), getattr(b, k)), f"step {step}: {k} differs between the two kernel variants"
+        qa, qb = a.QRAold.double(), b.QRAold.double()                       # (ii)
+        rel = (qa - qb).abs() / qb.abs().clamp_min(1e-9)
+        # Along 18 000-cell flow paths the reference formulation rounds to REAL4 at every cell: its own distance from
+        # exact arithmetic reaches ~1e-5 on the main stem (measured below, (iv)), and that is what separates the two
+        # paths here -- a handful of main-stem cells may sit just above 1e-5, everything else far below.
+        assert rel.max().item() <= 3e-5, f"step {step}: scan vs level sweep differ by {rel.max().item():.2e}"
+        assert int((rel > 1e-5).sum().item()) <= 1e-5 * n, f"step {step}: {int((rel > 1e-5).sum().item())} cells beyond 1e-5"
+        assert float(a.QRAold.min().item()) >= 0.0
+        assert bool((a.QRAold[b.QRAold == 0] == 0).all())
+    # (iii) mass conservation of the scan routing at full size: kx = 0, runoff 0.5 mm everywhere (sums exactly in float64)
+    lib = a.lib
+    m = torch.full((n,), 0.5, device=a.device)
+    q = torch.zeros(n, device=a.device)
+    src, dst = (C.c_void_p * 1)(m.data_ptr()), (C.c_void_p * 1)(q.data_ptr())
+    _lib.check(lib, a._ctx, lib.sphy_route_step(a._ctx, 1, src, dst, _lib.SphyParam(None, 0.0), C.c_float(1.0), _lib.ROUTE_SCAN,
+                                                None), "route")
+    torch.cuda.synchronize()
+    want = np.float32((np.float32(0.5) * np.float32(0.001) * np.float32(250.0 * 250.0)) / np.float32(86400.0))
+    assert abs(float(q.max().item()) - float(want) * n) <= 1e-6 * float(want) * n
+    # (iv) error attribution at full size against exact (float64) accumulation from the CPU oracle: the level sweep is
+    # bit-identical with the REAL4-per-cell reference arithmetic, the scan is within 1e-6 of exact arithmetic
+    from oracle.ldd_oracle import LddStruct
+    st = LddStruct(np.asarray(cat.ldd, np.uint8))
+    g = torch.Generator(device="cuda").manual_seed(3)
+    mm = (8.0 * torch.rand(n, device="cuda", generator=g) * (torch.rand(n, device="cuda", generator=g) < 0.6)).float().contiguous()
+    src = (C.c_void_p * 1)(mm.data_ptr())
+    out = {}
+    for name, method in (("levels", _lib.ROUTE_LEVELS), ("scan", _lib.ROUTE_SCAN)):
+        q.zero_()
+        _lib.check(lib, a._ctx, lib.sphy_route_step(a._ctx, 1, src, dst, _lib.SphyParam(None, 0.0), C.c_float(1.0), method, None), name)
+        torch.cuda.synchronize()
+        out[name] = np.empty(n, np.float32)
+        out[name][a.cell_order] = q.cpu().numpy()
+    mm_c = np.empty(n, np.float32)
+    mm_c[a.cell_order] = mm.cpu().numpy()
+    rr = (mm_c * np.float32(0.001) * np.float32(250.0 * 250.0)) / np.float32(86400)
+    exact = st.accuflux_f64(rr)
+    assert np.array_equal(out["levels"], st.accuflux(rr)), "the level sweep must stay bit-identical with the REAL4 oracle at 1e8 cells"
+    den = np.maximum(np.abs(exact), 1e-12)
+    err_scan = float(np.max(np.abs(out["scan"] - exact) / den))
+    err_ref = float(np.max(np.abs(out["levels"] - exact) / den))
+    print(f"full size: scan {err_scan:.2e}, REAL4-per-cell reference arithmetic {err_ref:.2e} from exact accumulation")
+    assert err_scan <= 1e-6 and err_scan < err_ref
+    b.close()
+    a.close()
