@@ -14,6 +14,11 @@ struct RoutePlanSeg {
     int32_t n_levels;      // 1 for a wide level (grid launch), >1 for a run of narrow levels (one CTA)
 };
 
+struct SweepPlanSeg {
+    int32_t first_level, n_levels;
+    int32_t threads;       // 0: one wide level (grid launch); else the CTA size of k_sweep_narrow for this run
+};
+
 struct sphy_ctx {
     int device = 0;
     int nrows = 0, ncols = 0;
@@ -42,6 +47,7 @@ struct sphy_ctx {
     int32_t *pos = nullptr, *dpos_ptr = nullptr, *dpos = nullptr;
     std::vector<int32_t> h_level_ptr;
     std::vector<RoutePlanSeg> plan;
+    std::vector<SweepPlanSeg> sweep_plan;   // route.cu: the narrow runs cut by CTA size
     // scan routing (route_scan.cu): static lists of the cells whose index range crosses a tile boundary + workspaces
     bool scan_ready = false;
     bool scan_smem_opt_in = false;
@@ -75,7 +81,9 @@ struct sphy_ctx {
     int32_t ra_table_cap = 0;
     float *tmp_n[4] = {nullptr, nullptr, nullptr, nullptr};
     bool qout_zeroed = false;
-    bool sweep_attr_set = false;
+    bool sweep_attr_set = false, sweep_rec_ready = false;
+    int32_t *sweep_rec = nullptr;   // route.cu: static donor records of the tail levels
+    int32_t sweep_rec_k0 = 0;
     double *cut_work = nullptr;    // scan path with lakes/reservoirs: range sums of the cut cells
     int cut_work_cap = 0;
     int32_t *cut_ptr = nullptr;    // per-tile ranges of the cut-cell list

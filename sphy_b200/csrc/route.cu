@@ -11,6 +11,9 @@
 //     shared memory so the dependent read does not go back to L2.
 // All routed components (total + up to 6 fractions, routing.py:81-101) share one sweep: the index
 // structures are read once.
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -28,6 +31,8 @@ struct SweepArgs {
     float *acc;                          // [ncomp][n] flux in routing order
     float *qday;                         // MODE_ADV: [n] blended Q in m3/day, routing order
     const int32_t *order, *dpos_ptr, *dpos, *level_ptr;
+    const int32_t *rec;                  // static donor records of the tail (k_sweep_records), positions >= rec_k0
+    int32_t rec_k0;
     sphy_param kx;
     float one_m_kx;
     float cellarea;
@@ -102,20 +107,46 @@ __global__ void __launch_bounds__(256) k_sweep_wide(const __grid_constant__ Swee
     }
 }
 
-constexpr int NARROW_THREADS = 1024;
-constexpr int FRONT_CAP = ROUTE_WIDE_LEVEL;   // max cells of a narrow level
+constexpr int SMALL_LEVEL_MAX = 1024 / 8;   // levels up to 128 cells: 8 donor lanes per cell, software-pipelined
 
-constexpr int SMALL_LEVEL = NARROW_THREADS / 8;   // levels up to 128 cells: 8 donor lanes per cell, software-pipelined
+// static donor records of the tail: rec[(k - k0) * 8 + s] = routing position of donor s of the cell at routing position
+// k (or -1), for every position k >= k0 (the first level with <= SMALL_LEVEL cells).  One coalesced load replaces the
+// dpos_ptr -> dpos chain on the latency-critical path of the narrow sweep.
+__global__ void k_sweep_records(const int32_t *__restrict__ dpos_ptr, const int32_t *__restrict__ dpos, int64_t k0, int64_t n,
+                                int32_t *__restrict__ rec)
+{
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= (n - k0) * 8) return;
+    const int64_t k = k0 + (t >> 3);
+    const int s = (int)(t & 7);
+    const int32_t b = __ldg(dpos_ptr + k), e = __ldg(dpos_ptr + k + 1);
+    rec[t] = b + s < e ? __ldg(dpos + b + s) : -1;
+}
 
 // A run of narrow levels [l0, l0+nl) walked by ONE CTA (the latency chain of the sweep: ~10^4 dependent levels).
 //  * small levels (<= 128 cells, the long tail): 8 lanes per cell fetch the donors in parallel and reduce with warp
-//    shuffles.  Everything that does not depend on the previous level -- the cell index, its donor position, the
-//    material, the old discharge, donors from older levels -- is prefetched one level ahead, so the dependent part
-//    of a level is: shared-memory read of the frontier -> 3 shuffles -> REAL8 add -> store -> __syncthreads.
+//    shuffles.  Everything that does not depend on the previous level is prefetched in a two-level software pipeline:
+//      level l+2: cell index and donor record (static arrays, one hop);
+//      level l+1: material, old discharge, kx/fraction, and the fluxes of donors older than level l (final already);
+//      level l  : shared-memory read of the previous level's frontier -> 3 shuffles -> REAL8 add -> store -> barrier.
+//    so a level costs one memory latency instead of a chain of four dependent loads.
 //  * medium levels (129 .. 2047 cells): one thread per cell, sequential donor loop.
 // The fluxes of the previous level (the frontier) are staged in shared memory; older ones come from global memory.
-__global__ void __launch_bounds__(NARROW_THREADS) k_sweep_narrow(const __grid_constant__ SweepArgs a, int32_t l0, int32_t nl)
+struct LevelRegs {            // what one lane holds for one small level in flight
+    int32_t i, dp;            // cell (lane sub == 0 uses it), donor position of this lane
+    float old, mat;
+    bool valid, old_valid;    // valid: hop 1 done; old_valid: the donor was final when hop 2 ran
+    CellIn ci;
+};
+
+// THREADS = 1024 (any narrow level), 256 or 32 (runs whose levels all have <= THREADS/8 cells: the long tail of a river
+// network has 1-4 cells per level, and a 32-warp CTA would spend its time issuing the idle warps' loop bodies).
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_sweep_narrow(const __grid_constant__ SweepArgs a, int32_t l0, int32_t nl)
 {
+    constexpr int NARROW_THREADS = THREADS;
+    constexpr int SMALL_LEVEL = THREADS / 8;
+    constexpr int FRONT_CAP = THREADS == 1024 ? ROUTE_WIDE_LEVEL : THREADS / 8;
     extern __shared__ float front[];     // [2][ncomp][FRONT_CAP] fluxes of the previous / current level
     const int tid = threadIdx.x;
     const int sub = tid & 7;             // donor lane
@@ -124,66 +155,57 @@ __global__ void __launch_bounds__(NARROW_THREADS) k_sweep_narrow(const __grid_co
     const int32_t lend = l0 + nl;
     int cur = 0;
     int32_t prev_begin = -1, prev_end = -1;
-    int32_t kb = __ldg(a.level_ptr + l0), ke = __ldg(a.level_ptr + l0 + 1);
-    // pipeline registers: the small level about to be processed
-    bool pf = false;
-    int32_t p_i = 0, p_dp = -1;
-    float p_old = 0.0f, p_mat = 0.0f;
-    bool p_old_valid = false;
-    CellIn p_ci = {1.0f, 0.0f, 0.0f, 0.0f};
+    // level boundaries k[l], k[l+1], k[l+2], k[l+3] (loaded ahead: they sit on the prefetch path)
+    auto lp = [&](int32_t l) { return __ldg(a.level_ptr + (l < lend ? l : lend)); };
+    int32_t kb = lp(l0), ke = lp(l0 + 1), k2 = lp(l0 + 2), k3 = lp(l0 + 3);
+    LevelRegs A = {}, B = {};            // A: level l+2 (hop 1 done), B: level l+1 (hops 1 and 2 done) -- after the shifts below
+    // hop 1 of level `lev` = positions [b, e): cell index + donor record
+    auto hop1 = [&](int32_t b, int32_t e, LevelRegs &r) {
+        r.valid = false; r.old_valid = false; r.i = 0; r.dp = -1;
+        if (e - b > SMALL_LEVEL || e <= b || b < a.rec_k0) return;
+        r.valid = true;
+        if (slot < e - b) {
+            const int32_t k = b + slot;
+            r.i = __ldg(a.order + k);
+            r.dp = __ldg(a.rec + ((int64_t)(k - a.rec_k0) << 3) + sub);
+        }
+    };
+    // hop 2 of the level whose hop 1 is in r; `final_below`: donors at positions < final_below are final and in global memory
+    auto hop2 = [&](int32_t b, int32_t e, int32_t final_below, LevelRegs &r) {
+        if (!r.valid || slot >= e - b) return;
+        if (r.dp >= 0 && r.dp < final_below) { r.old = a.acc[r.dp]; r.old_valid = true; }
+        if (sub == 0) { r.mat = material(a, 0, r.i); r.ci = load_cell_in(a, 0, r.i); }
+    };
+    // fill the pipeline: level l0 completely (nothing is in flight yet), level l0+1 hop 1
+    LevelRegs Cr = {};
+    hop1(kb, ke, Cr);
+    hop2(kb, ke, kb, Cr);                // every donor of the run's first level is older than the run
+    hop1(ke, k2, B);
     for (int32_t l = l0; l < lend; ++l) {
         const int32_t nlev = ke - kb;
-        const int32_t nkb = ke, nke = (l + 1 < lend) ? __ldg(a.level_ptr + l + 2) : ke;    // the next level of this run
         float *fcur = front + (size_t)cur * ncomp * FRONT_CAP;
         const float *fprev = front + (size_t)(cur ^ 1) * ncomp * FRONT_CAP;
-        // ---- stage 1: this level's independent inputs (prefetched during the previous level when possible) ---------
-        int32_t i = p_i, dp = p_dp;
-        float old0 = p_old, mat0 = p_mat;
-        bool old0_valid = p_old_valid;
-        CellIn ci0 = p_ci;
-        const bool small = nlev <= SMALL_LEVEL;
-        const bool live = small && slot < nlev;
-        if (small && !pf) {
-            i = 0; dp = -1; old0_valid = false;
-            if (live) {
-                const int32_t k = kb + slot;
-                i = __ldg(a.order + k);
-                const int32_t b = __ldg(a.dpos_ptr + k), e = __ldg(a.dpos_ptr + k + 1);
-                if (b + sub < e) dp = __ldg(a.dpos + b + sub);
-                if (sub == 0) { mat0 = material(a, 0, i); ci0 = load_cell_in(a, 0, i); }
-            }
-        }
-        // ---- stage 2: issue the next level's independent loads now; they complete while this level computes --------
-        pf = false;
-        if (l + 1 < lend && nke - nkb <= SMALL_LEVEL) {
-            pf = true;
-            p_i = 0; p_dp = -1; p_old_valid = false;
-            if (slot < nke - nkb) {
-                const int32_t k2 = nkb + slot;
-                p_i = __ldg(a.order + k2);
-                const int32_t b2 = __ldg(a.dpos_ptr + k2), e2 = __ldg(a.dpos_ptr + k2 + 1);
-                if (b2 + sub < e2) {
-                    p_dp = __ldg(a.dpos + b2 + sub);
-                    if (p_dp < kb) { p_old = a.acc[p_dp]; p_old_valid = true; }   // donor older than this level: final already
-                }
-                if (sub == 0) { p_mat = material(a, 0, p_i); p_ci = load_cell_in(a, 0, p_i); }
-            }
-        }
-        // ---- stage 3: the dependent part ----------------------------------------------------------------------------
+        // ---- issue: hop 1 of level l+2, hop 2 of level l+1 (its donors below kb are final; those in level l come from smem)
+        hop1(k2, k3, A);
+        hop2(ke, k2, kb, B);
+        const int32_t k4 = lp(l + 4);
+        // ---- the dependent part of level l ----------------------------------------------------------------------------
+        const bool small = Cr.valid;
         if (small) {
+            const bool live = slot < nlev;
             for (int c = 0; c < ncomp; ++c) {
                 double s = 0.0;
-                if (dp >= 0) {
-                    if (dp >= prev_begin && dp < prev_end) s = (double)fprev[c * FRONT_CAP + (dp - prev_begin)];
-                    else if (c == 0 && old0_valid) s = (double)old0;
-                    else s = (double)a.acc[(int64_t)c * a.n + dp];
+                if (Cr.dp >= 0) {
+                    if (Cr.dp >= prev_begin && Cr.dp < prev_end) s = (double)fprev[c * FRONT_CAP + (Cr.dp - prev_begin)];
+                    else if (c == 0 && Cr.old_valid) s = (double)Cr.old;
+                    else s = (double)a.acc[(int64_t)c * a.n + Cr.dp];
                 }
                 s += __shfl_xor_sync(0xffffffffu, s, 4, 8);       // warp-shuffle reduction over the 8 donor lanes
                 s += __shfl_xor_sync(0xffffffffu, s, 2, 8);
                 s += __shfl_xor_sync(0xffffffffu, s, 1, 8);
                 if (live && sub == 0) {
-                    s += (double)(c == 0 ? mat0 : material(a, c, i));
-                    const float f = finish(a, c, kb + slot, i, s, c == 0 ? ci0 : load_cell_in(a, c, i));
+                    s += (double)(c == 0 ? Cr.mat : material(a, c, Cr.i));
+                    const float f = finish(a, c, kb + slot, Cr.i, s, c == 0 ? Cr.ci : load_cell_in(a, c, Cr.i));
                     fcur[c * FRONT_CAP + slot] = f;
                 }
             }
@@ -206,8 +228,8 @@ __global__ void __launch_bounds__(NARROW_THREADS) k_sweep_narrow(const __grid_co
         prev_begin = kb;
         prev_end = ke;
         cur ^= 1;
-        kb = nkb;
-        ke = nke;
+        kb = ke; ke = k2; k2 = k3; k3 = k4;
+        Cr = B; B = A;
         __syncthreads();
     }
 }
@@ -234,18 +256,79 @@ int route_levels_run(sphy_ctx *ctx, SweepArgs &a, cudaStream_t st)
     a.acc = ctx->acc;
     a.n = ctx->n;
     a.cellarea = ctx->cellarea;
-    const size_t smem = (size_t)2 * a.ncomp * FRONT_CAP * sizeof(float);
+    if (!ctx->sweep_rec_ready) {          // once: donor records of every position from the first small level onwards
+        int64_t k0 = ctx->n;
+        const int nlv = (int)ctx->h_level_ptr.size() - 1;
+        const auto size_of = [&](int l) { return ctx->h_level_ptr[l + 1] - ctx->h_level_ptr[l]; };
+        for (int l = 0; l < nlv; ++l)
+            if (size_of(l) <= SMALL_LEVEL_MAX) { k0 = ctx->h_level_ptr[l]; break; }
+        if (ctx->n - k0 > (int64_t)1 << 25) k0 = ctx->n;      // keep the table under 1 GB: beyond that the tail is not a tail
+        ctx->sweep_rec_k0 = (int32_t)k0;
+        if (k0 < ctx->n) {
+            int rc = dev_alloc(ctx, &ctx->sweep_rec, (size_t)(ctx->n - k0) * 8);
+            if (rc != SPHY_OK) return rc;
+            k_sweep_records<<<div_up((ctx->n - k0) * 8, 256), 256, 0, st>>>(ctx->dpos_ptr, ctx->dpos, k0, ctx->n, ctx->sweep_rec);
+        }
+        // launch plan of the sweep: the runs of narrow levels are cut into sub-runs by CTA size
+        ctx->sweep_plan.clear();
+        for (const RoutePlanSeg &seg : ctx->plan) {
+            if (seg.n_levels == 1 && size_of(seg.first_level) >= ROUTE_WIDE_LEVEL) {
+                ctx->sweep_plan.push_back({seg.first_level, 1, 0});
+                continue;
+            }
+            const auto cls = [&](int l) {
+                const int sz = size_of(l);
+                if (ctx->h_level_ptr[l] < k0) return 1024;
+                return sz <= 4 ? 32 : (sz <= 32 ? 256 : 1024);
+            };
+            int l = seg.first_level;
+            const int lend = seg.first_level + seg.n_levels;
+            while (l < lend) {
+                // a sub-run keeps the CTA size of its first level; levels that need a larger CTA end it, and so does a
+                // stretch of at least 8 levels that would all fit a smaller one (short dips are not worth a launch)
+                const int t = cls(l);
+                int e = l + 1;
+                while (e < lend && cls(e) <= t) {
+                    if (cls(e) < t) {
+                        int j = e;
+                        while (j < lend && j - e < 8 && cls(j) < t) ++j;
+                        if (j - e >= 8) break;
+                    }
+                    ++e;
+                }
+                ctx->sweep_plan.push_back({l, e - l, t});
+                l = e;
+            }
+        }
+        if (getenv("SPHY_DEBUG_PLAN")) {
+            int nseg[4] = {0, 0, 0, 0}, nlev[4] = {0, 0, 0, 0};
+            for (const SweepPlanSeg &q : ctx->sweep_plan) {
+                const int c = q.threads == 0 ? 0 : (q.threads == 1024 ? 1 : (q.threads == 256 ? 2 : 3));
+                ++nseg[c];
+                nlev[c] += q.n_levels;
+            }
+            fprintf(stderr, "sweep plan: wide %d launches; 1024-thread %d runs / %d levels; 256-thread %d / %d; 32-thread %d / %d\n",
+                    nseg[0], nseg[1], nlev[1], nseg[2], nlev[2], nseg[3], nlev[3]);
+        }
+        ctx->sweep_rec_ready = true;
+    }
+    a.rec = ctx->sweep_rec;
+    a.rec_k0 = ctx->sweep_rec_k0;
     if (!ctx->sweep_attr_set) {        // per context (= per device): opt in to the large dynamic shared memory once
-        SPHY_CUDA(ctx, cudaFuncSetAttribute(k_sweep_narrow, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            2 * ROUTE_MAX_COMP * FRONT_CAP * (int)sizeof(float)));
+        SPHY_CUDA(ctx, cudaFuncSetAttribute(k_sweep_narrow<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            2 * ROUTE_MAX_COMP * ROUTE_WIDE_LEVEL * (int)sizeof(float)));
         ctx->sweep_attr_set = true;
     }
-    for (const RoutePlanSeg &seg : ctx->plan) {
-        if (seg.n_levels == 1 && ctx->h_level_ptr[seg.first_level + 1] - ctx->h_level_ptr[seg.first_level] >= FRONT_CAP) {
+    for (const SweepPlanSeg &seg : ctx->sweep_plan) {
+        if (seg.threads == 0) {
             const int32_t k0 = ctx->h_level_ptr[seg.first_level], k1 = ctx->h_level_ptr[seg.first_level + 1];
             k_sweep_wide<<<div_up(k1 - k0, 256), 256, 0, st>>>(a, k0, k1);
+        } else if (seg.threads == 1024) {
+            k_sweep_narrow<1024><<<1, 1024, (size_t)2 * a.ncomp * ROUTE_WIDE_LEVEL * sizeof(float), st>>>(a, seg.first_level, seg.n_levels);
+        } else if (seg.threads == 256) {
+            k_sweep_narrow<256><<<1, 256, (size_t)2 * a.ncomp * 32 * sizeof(float), st>>>(a, seg.first_level, seg.n_levels);
         } else {
-            k_sweep_narrow<<<1, NARROW_THREADS, smem, st>>>(a, seg.first_level, seg.n_levels);
+            k_sweep_narrow<32><<<1, 32, (size_t)2 * a.ncomp * 4 * sizeof(float), st>>>(a, seg.first_level, seg.n_levels);
         }
     }
     SPHY_LAUNCH_CHECK(ctx);
