@@ -123,6 +123,33 @@ __global__ void k_sweep_records(const int32_t *__restrict__ dpos_ptr, const int3
     rec[t] = b + s < e ? __ldg(dpos + b + s) : -1;
 }
 
+// The tail levels are latency-bound (one memory round trip per level), and what they read -- materials, old discharges,
+// donor records, the fluxes of tributary outlets -- is scattered and was evicted from L2 by the streaming kernels before.
+// One massively parallel pass pulls those lines into the 126 MB L2 right before the serial walk starts, so that the
+// walk's round trips are L2 hits instead of HBM accesses.
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+__global__ void k_sweep_warm(const __grid_constant__ SweepArgs a)
+{
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= (a.n - a.rec_k0) * 8) return;
+    const int64_t k = a.rec_k0 + (t >> 3);
+    const int sub = (int)(t & 7);
+    const int32_t dp = __ldg(a.rec + t);
+    if (dp >= 0 && dp < a.rec_k0)                               // donors inside the tail are produced by the walk itself
+        for (int c = 0; c < a.ncomp; ++c) prefetch_l2(a.acc + (int64_t)c * a.n + dp);
+    if (sub == 0) {
+        const int32_t i = __ldg(a.order + k);
+        for (int c = 0; c < a.ncomp; ++c) {
+            prefetch_l2(a.m[c] + i);
+            if (a.qstate[c]) prefetch_l2(a.qstate[c] + i);
+        }
+        if (a.kx.map) prefetch_l2(a.kx.map + i);
+        if (a.frac) prefetch_l2(a.frac + i);
+        if (a.qout_dense) prefetch_l2(a.qout_dense + i);
+    }
+}
+
 // A run of narrow levels [l0, l0+nl) walked by ONE CTA (the latency chain of the sweep: ~10^4 dependent levels).
 //  * small levels (<= 128 cells, the long tail): 8 lanes per cell fetch the donors in parallel and reduce with warp
 //    shuffles.  Everything that does not depend on the previous level is prefetched in a two-level software pipeline:
@@ -319,7 +346,12 @@ int route_levels_run(sphy_ctx *ctx, SweepArgs &a, cudaStream_t st)
                                             2 * ROUTE_MAX_COMP * ROUTE_WIDE_LEVEL * (int)sizeof(float)));
         ctx->sweep_attr_set = true;
     }
+    bool warmed = false;
     for (const SweepPlanSeg &seg : ctx->sweep_plan) {
+        if (!warmed && a.rec && ctx->h_level_ptr[seg.first_level] >= a.rec_k0) {     // the tail starts here
+            k_sweep_warm<<<div_up((a.n - a.rec_k0) * 8, 256), 256, 0, st>>>(a);
+            warmed = true;
+        }
         if (seg.threads == 0) {
             const int32_t k0 = ctx->h_level_ptr[seg.first_level], k1 = ctx->h_level_ptr[seg.first_level + 1];
             k_sweep_wide<<<div_up(k1 - k0, 256), 256, 0, st>>>(a, k0, k1);
