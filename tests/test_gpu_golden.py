@@ -301,6 +301,35 @@ def test_reporting_outputs_match_reference():
     model.close()
 
 
+@pytest.mark.parametrize("name,names", [
+    ("c1_sed_mmf", {"DetRn": "DetRn", "DetRun": "DetRun", "SDepFld": "SDpFld", "SedTrans": "STrans", "SedDep": "Sdep", "SedYld": "SdYld",
+                    "SedFlux": "SdFlux", "TC": "TC"}),
+    ("c1_dynveg", {"LAI": "LAI", "TotIntF": "IntF", "TotPrecEF": "PrecEF", "StorCanop": "Canop", "TotPrec": "Prec"}),
+])
+def test_daily_reporting_of_widened_modules(name, names):
+    """The reporting engine (reporting.csv, option D) hands out the maps of the dynamic-vegetation and sediment modules
+    under the reference's variable names and file prefixes: compared with what the reference reported day by day."""
+    import torch
+    from sphy_b200.csf import stack_name
+    cat, z, meta = catchment_from_golden(name)
+    cat.report_daily = tuple(names)
+    model = make_model(cat, reporting=True)
+    model.maps.forcing_fn = lambda t: golden_forcing(z, t)
+    for _ in range(meta["nsteps"]):
+        model.dynamic()
+    torch.cuda.synchronize()
+    checked = 0
+    for var, prefix in names.items():
+        if "report/" + prefix not in z.files:
+            continue
+        for t in range(1, meta["nsteps"] + 1):
+            got = model.report.maps[stack_name(prefix, t)]
+            assert close(got, z["report/" + prefix][t - 1]).all(), f"{var} day {t}"
+            checked += 1
+    assert checked >= 3 * meta["nsteps"]
+    model.close()
+
+
 def test_csf_input_directory_matches_in_memory_source():
     """Forcing ingest from PCRaster CSF map stacks on disk (DirMapSource: clone.map, forcings/prec0000.001 ...) gives
     the same run as the in-memory source; the cell size comes from the clone map's header."""
