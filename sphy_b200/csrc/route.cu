@@ -261,6 +261,96 @@ __global__ void __launch_bounds__(THREADS) k_sweep_narrow(const __grid_constant_
     }
 }
 
+// ---- deep-pipelined walk of the tail ------------------------------------------------------------------------------------
+// Levels of at most CELLS = 4 * WARPS cells, one routed component.  A level costs one memory round trip as long as it
+// consumes what was requested one level earlier, so the requests are issued D = 8 (dependent data) and 2 D = 16 (static
+// records) levels ahead with cp.async into 16-entry shared-memory rings -- no registers are held across levels:
+//   iteration l:  hop 2 of level l+8  (material, old discharge, kx / fraction of its cells; fluxes of donors that are final, i.e.
+//                                      below level l -- younger donors are at most 8 levels back and sit in the flux ring)
+//                 compute level l     (8 donor lanes per cell, shuffle reduction in REAL8, recession blend, flux ring)
+//                 hop 1 of level l+16 (cell index and donor record from the static arrays)
+// Every cp.async result is consumed by the lane that requested it; only the flux ring crosses lanes (one barrier per level).
+__device__ __forceinline__ void cp_async4(void *dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_sweep_tail(const __grid_constant__ SweepArgs a, int32_t l0, int32_t nl)
+{
+    constexpr int T = WARPS * 32, CELLS = T / 8, D = 8, SLOTS = 2 * D, RINGP = CELLS * SLOTS;
+    __shared__ int32_t s_dp[SLOTS][T];
+    __shared__ float s_old[SLOTS][T];
+    __shared__ int32_t s_i[SLOTS][CELLS];
+    __shared__ float s_mat[SLOTS][CELLS], s_qold[SLOTS][CELLS], s_kx[SLOTS][CELLS], s_fr[SLOTS][CELLS], s_qout[SLOTS][CELLS];
+    __shared__ float ringf[RINGP];       // fluxes of the last RINGP routing positions (tail positions are consecutive)
+    const int tid = threadIdx.x, sub = tid & 7, slot = tid >> 3;
+    const int32_t lend = l0 + nl;
+    auto KB = [&](int32_t l) { return __ldg(a.level_ptr + (l < l0 ? l0 : (l > lend ? lend : l))); };
+    auto barrier = [&]() { if (WARPS == 1) __syncwarp(); else __syncthreads(); };
+    const bool has_qold = a.mode == MODE_ROUT || a.mode == MODE_ADV;
+    for (int32_t l = l0 - 2 * D; l < lend; ++l) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(D - 1) : "memory");      // the requests of iteration l - D have landed
+        // ---- hop 2 of level x = l + D: its donors below level l are final and in global memory
+        const int32_t x = l + D;
+        if (x >= l0 && x < lend) {
+            const int32_t kbx = KB(x), nx = KB(x + 1) - kbx, final_below = KB(l);
+            if (slot < nx) {
+                const int sx = x & (SLOTS - 1);
+                const int32_t dp = s_dp[sx][tid];
+                if (dp >= 0 && dp < final_below) cp_async4(&s_old[sx][tid], a.acc + dp);
+                if (sub == 0) {
+                    const int32_t i = s_i[sx][slot];
+                    cp_async4(&s_mat[sx][slot], a.m[0] + i);
+                    if (has_qold) cp_async4(&s_qold[sx][slot], a.qstate[0] + i);
+                    if (a.kx.map) cp_async4(&s_kx[sx][slot], a.kx.map + i);
+                    if (a.frac) cp_async4(&s_fr[sx][slot], a.frac + i);
+                    if (a.mode == MODE_ADV) cp_async4(&s_qout[sx][slot], a.qout_dense + i);
+                }
+            }
+        }
+        // ---- level l
+        if (l >= l0) {
+            const int32_t kb = KB(l), nlev = KB(l + 1) - kb, fetched_below = KB(l - D);
+            const int sl = l & (SLOTS - 1);
+            double s = 0.0;
+            if (slot < nlev) {
+                const int32_t dp = s_dp[sl][tid];
+                if (dp >= 0) s = dp < fetched_below ? (double)s_old[sl][tid] : (double)ringf[dp & (RINGP - 1)];
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 4, 8);           // warp-shuffle reduction over the 8 donor lanes
+            s += __shfl_xor_sync(0xffffffffu, s, 2, 8);
+            s += __shfl_xor_sync(0xffffffffu, s, 1, 8);
+            if (slot < nlev && sub == 0) {
+                const int32_t i = s_i[sl][slot];
+                float mat = s_mat[sl][slot];
+                if (a.mode == MODE_ROUT) mat = ((mat * 0.001f) * a.cellarea) / 86400.0f;      // routing.py:26
+                CellIn ci;
+                ci.fr = a.frac ? s_fr[sl][slot] : 1.0f;
+                ci.kx = a.kx.map ? s_kx[sl][slot] : a.kx.value;
+                ci.qold = has_qold ? s_qold[sl][slot] : 0.0f;
+                ci.qout = (a.mode == MODE_ADV && ci.fr == 0.0f) ? s_qout[sl][slot] : 0.0f;
+                const float f = finish(a, 0, kb + slot, i, s + (double)mat, ci);
+                ringf[(kb + slot) & (RINGP - 1)] = f;
+            }
+        }
+        // ---- hop 1 of level y = l + 2 D: static records (its ring entry was the one of level l, consumed above)
+        const int32_t y = l + 2 * D;
+        if (y >= l0 && y < lend) {
+            const int32_t kby = KB(y), ny = KB(y + 1) - kby;
+            if (slot < ny) {
+                const int sy = y & (SLOTS - 1);
+                const int32_t k = kby + slot;
+                cp_async4(&s_dp[sy][tid], a.rec + ((int64_t)(k - a.rec_k0) << 3) + sub);
+                if (sub == 0) cp_async4(&s_i[sy][slot], a.order + k);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        barrier();
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 __global__ void k_upstream(const float *__restrict__ x, const int32_t *__restrict__ don_ptr, const int32_t *__restrict__ don_idx,
                            int64_t n, float *__restrict__ out)
 {
@@ -347,6 +437,8 @@ int route_levels_run(sphy_ctx *ctx, SweepArgs &a, cudaStream_t st)
         ctx->sweep_attr_set = true;
     }
     bool warmed = false;
+    const char *deep_env = getenv("SPHY_SWEEP_DEEP");           // 0 = the two-level pipeline for every narrow run
+    const bool deep = !(deep_env && deep_env[0] == '0');
     for (const SweepPlanSeg &seg : ctx->sweep_plan) {
         if (!warmed && a.rec && ctx->h_level_ptr[seg.first_level] >= a.rec_k0) {     // the tail starts here
             k_sweep_warm<<<div_up((a.n - a.rec_k0) * 8, 256), 256, 0, st>>>(a);
@@ -358,9 +450,11 @@ int route_levels_run(sphy_ctx *ctx, SweepArgs &a, cudaStream_t st)
         } else if (seg.threads == 1024) {
             k_sweep_narrow<1024><<<1, 1024, (size_t)2 * a.ncomp * ROUTE_WIDE_LEVEL * sizeof(float), st>>>(a, seg.first_level, seg.n_levels);
         } else if (seg.threads == 256) {
-            k_sweep_narrow<256><<<1, 256, (size_t)2 * a.ncomp * 32 * sizeof(float), st>>>(a, seg.first_level, seg.n_levels);
+            if (a.ncomp == 1 && deep) k_sweep_tail<8><<<1, 256, 0, st>>>(a, seg.first_level, seg.n_levels);
+            else k_sweep_narrow<256><<<1, 256, (size_t)2 * a.ncomp * 32 * sizeof(float), st>>>(a, seg.first_level, seg.n_levels);
         } else {
-            k_sweep_narrow<32><<<1, 32, (size_t)2 * a.ncomp * 4 * sizeof(float), st>>>(a, seg.first_level, seg.n_levels);
+            if (a.ncomp == 1 && deep) k_sweep_tail<1><<<1, 32, 0, st>>>(a, seg.first_level, seg.n_levels);
+            else k_sweep_narrow<32><<<1, 32, (size_t)2 * a.ncomp * 4 * sizeof(float), st>>>(a, seg.first_level, seg.n_levels);
         }
     }
     SPHY_LAUNCH_CHECK(ctx);
