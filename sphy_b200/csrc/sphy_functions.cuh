@@ -8,6 +8,10 @@
 
 namespace sf {
 
+// x / d for x >= 0 that is very often exactly 0 (no excess water, a dry day): the IEEE division takes its slow path for a
+// zero numerator, and 0 / d is +0 for every d > 0 -- same bits, no division
+__device__ __forceinline__ float div_often_zero(float x, float d) { return (x == 0.0f && d > 0.0f) ? 0.0f : x / d; }
+
 // double-evaluated transcendentals stored as REAL4 (assumption A2, see oracle/pcr_shim.py)
 __device__ __forceinline__ float d_acos(float x) { return (float)acos((double)x); }
 __device__ __forceinline__ float d_sin(float x) { return (float)sin((double)x); }
@@ -79,7 +83,7 @@ __device__ __forceinline__ float PotSnowMelt(float temp, float tempmax, float dd
     const float dT = tempmax - temp;
 #pragma unroll
     for (int h = 0; h < 24; ++h) thour = thour + fmaxf(0.0f, temp + dT * melt_cos[h]);
-    return (thour * ddfs) / 24.0f;
+    return div_often_zero(thour * ddfs, 24.0f);
 }
 __device__ __forceinline__ float ActSnowMelt(float snowstore, float potmelt) { return fminf(snowstore, potmelt); }   // :37-39
 __device__ __forceinline__ float SnowStoreUpdate(float snowstore, float snow, float actmelt, float temp, float snowwatstore)
@@ -125,7 +129,7 @@ __device__ __forceinline__ float RootDrainage(float rootwater, float rootdrain, 
                                               float e_root)
 {
     const float rootexcess = fmaxf(rootwater - rootfield, 0.0f);
-    const float rootlat = (rootexcess / (rootsat - rootfield)) * drainvel;
+    const float rootlat = div_often_zero(rootexcess, rootsat - rootfield) * drainvel;
     return fmaxf(fminf(rootexcess, rootlat * (1.0f - e_root) + rootdrain * e_root), 0.0f);
 }
 // RootPercolation (rootzone.py:78-85)
@@ -164,7 +168,7 @@ __device__ __forceinline__ float SubDrainage(float subwater, float subfield, flo
                                              float e_sub)
 {                                                                                                      // subzone.py:45-51
     const float subexcess = fmaxf(subwater - subfield, 0.0f);
-    const float sublateral = (subexcess / (subsat - subfield)) * drainvel;
+    const float sublateral = div_often_zero(subexcess, subsat - subfield) * drainvel;
     const float s = (sublateral + subdrainage) * (1.0f - e_sub);
     return fmaxf(fminf(s, subwater), 0.0f);
 }
@@ -182,7 +186,7 @@ __device__ __forceinline__ float BaseFlow(float gw, float baser, float gwrecharg
 }
 __device__ __forceinline__ float HLevel(float Hgw, float e_alpha, float gwrecharge, float h_den)
 {                                                                                                      // groundwater.py:43-47
-    return (Hgw * e_alpha) + ((gwrecharge * (1.0f - e_alpha)) / h_den);
+    return (Hgw * e_alpha) + div_often_zero(gwrecharge * (1.0f - e_alpha), h_den);
 }
 
 // ---- modules/routing.py -----------------------------------------------------------------------------------------

@@ -260,7 +260,7 @@ __device__ __forceinline__ void wb_cells(const WbArgs &a, int64_t i, float4 *pf 
         const float ss0 = SNOW ? SnowStore.v[j] : 0.0f;
         const float SnowFrac = ss0 > 0.0f ? omg : 0.0f;                    // sphy.py:732
         const float RainFrac = ss0 == 0.0f ? omg : 0.0f;                   // sphy.py:733
-        const float Precip = prec.v[j] / p.pcorr;                          // sphy.py:757 (divides)
+        const float Precip = sf::div_often_zero(prec.v[j], p.pcorr);       // sphy.py:757 (divides); dry days
         const float Temp = tavg.v[j] + p.tcorr;
         float TempMax = 0.0f, ETref;
         if (RA == 2) {
@@ -318,11 +318,9 @@ __device__ __forceinline__ void wb_cells(const WbArgs &a, int64_t i, float4 *pf 
         const float ssat = PV(sub_sat, sub_sat);
         const float tP = sf::RootPercolation(rw, sw, rfield, er, ssat);
         const float RootOut = tD + tP;
-        float newD, newP;
-        sf::CalcFrac(rw, rfield, tD, tP, newD, newP);
         const bool over = RootOut > ex;                                    // sphy.py:976-978
-        const float rdrain = over ? newD : tD;
-        const float rootperc = over ? newP : tP;
+        float rdrain = tD, rootperc = tP;
+        if (over) sf::CalcFrac(rw, rfield, tD, tP, rdrain, rootperc);      // only then used; elsewhere it is 0/0 (IEEE slow path)
         rw = rw - (rdrain + rootperc);
         // ---- subzone, sphy.py:991-1056 + subzone.py ----------------------------------------------------
         sw = sw + rootperc;
