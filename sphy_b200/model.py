@@ -1142,8 +1142,8 @@ class SphyModel:
             return self._forcing_dev(counter)
         keys = ("prec", "tavg", "etref") if self.ETREF_FLAG == 1 else ("prec", "tavg", "tmin", "tmax")
         optional = (("ndvi",) if self.DynVegFLAG == 1 else ()) + tuple(self._series)           # series that may have gaps
-        if self._forcing_host is None:
-            keys = keys + optional
+        self._optional_keys = optional
+        keys = keys + optional
         if self._fdev is None:
             self._fdev = {k: torch.empty(self.n, dtype=torch.float32, device=self.device) for k in keys}
         if self._forcing_host is not None:
@@ -1180,25 +1180,29 @@ class SphyModel:
             except (IndexError, KeyError, FileNotFoundError):
                 return
             cs.wait_stream(main)                 # the buffer's previous contents have been consumed
+            present = []
             with torch.cuda.stream(cs):
                 for k in keys:
+                    if k in self._optional_keys and host.get(k) is None:
+                        continue                 # a map series without a map for this day
                     self._hbuf[slot][k].copy_(host[k], non_blocking=True)
+                    present.append(k)
                 ev = torch.cuda.Event()
                 ev.record(cs)
-            self._hready[slot] = (t, ev)
+            self._hready[slot] = (t, ev, present)
 
         slot = counter % 2
         if self._hready[slot] is None or self._hready[slot][0] != counter:
             upload(counter, slot)
         main.wait_event(self._hready[slot][1])
-        buf = self._hbuf[slot]
+        buf, present = self._hbuf[slot], self._hready[slot][2]
         if compact:
-            out = buf
+            out = {k: buf[k] for k in present}
         else:
-            for k in keys:
+            for k in present:
                 self._ck(self.lib.sphy_gather_f32(self._ctx, buf[k].data_ptr(), self._fdev[k].data_ptr(), self._stream()),
                          "sphy_gather_f32")
-            out = self._fdev
+            out = {k: self._fdev[k] for k in present}
         upload(counter + 1, 1 - slot)            # prefetch tomorrow while today computes
         return out
 

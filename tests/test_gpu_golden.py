@@ -330,6 +330,32 @@ def test_daily_reporting_of_widened_modules(name, names):
     model.close()
 
 
+@pytest.mark.parametrize("name", ["c1_base", "c1_dynveg", "c1_kc_series"])
+def test_host_forcing_upload_path_matches_map_source(name):
+    """set_host_forcing: pinned host rasters uploaded on a copy stream (double buffered, day t+1 in flight while day t
+    computes) and compacted into device order on the GPU must give the same run as reading the maps, including the map
+    series that have no map on some days."""
+    import torch
+    cat, z, meta = catchment_from_golden(name)
+    a = make_model(cat, route_method="scan")
+    a.maps.forcing_fn = lambda t: golden_forcing(z, t)
+    b = make_model(cat, route_method="scan")
+
+    def host(t):
+        if t > meta["nsteps"]:
+            raise IndexError(t)
+        return {k: torch.from_numpy(np.ascontiguousarray(v, np.float32).ravel()).pin_memory() for k, v in golden_forcing(z, t).items()}
+    b.set_host_forcing(host)
+    for t in range(1, meta["nsteps"] + 1):
+        a.dynamic()
+        b.dynamic()
+        torch.cuda.synchronize()
+        for k in ("RootWater", "SubWater", "Gw", "QRAold"):
+            assert torch.equal(getattr(a, k), getattr(b, k)), f"{name} t={t} {k}"
+    a.close()
+    b.close()
+
+
 def test_csf_input_directory_matches_in_memory_source():
     """Forcing ingest from PCRaster CSF map stacks on disk (DirMapSource: clone.map, forcings/prec0000.001 ...) gives
     the same run as the in-memory source; the cell size comes from the clone map's header."""
