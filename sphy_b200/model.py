@@ -593,6 +593,8 @@ class SphyModel:
     def _glacier_initial(self):
         import pandas as pd
         cfg = self.config
+        if self.world > 1:
+            raise NotImplementedError("the glacier fragment table is not split across ranks yet: run glacier basins on one GPU")
         tab = pd.read_csv(os.path.join(self.inpath, cfg.get("GLACIER", "GlacTable")))
         tab = tab.sort_values(by="MOD_ID", kind="stable").reset_index(drop=True)
         model_id = np.asarray(self._readmap(cfg.get("GLACIER", "ModelID"))).ravel()
