@@ -84,6 +84,31 @@ def plan(sub_size, world, tile=TILE):
 
 
 # ----------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local):
+    """Pin this process to the CPUs next to its GPU (NVML's CPU affinity of the device) before any pinned host buffer is
+    allocated: first-touch then places the staging memory on the GPU's own NUMA node, which is what the per-rank
+    host->device uploads of the end-to-end path run from.  Best effort: any failure leaves the affinity untouched."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(local).uuid)
+            handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = [w * 64 + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def bench_main(args, rank, world):
     """bench.py for N > 1: the BASELINE config-4 basin split across `world` GPUs (strong scaling)."""
     import torch
@@ -95,6 +120,7 @@ def bench_main(args, rank, world):
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
+    numa_cpus = bind_to_gpu_numa_node(local)
     dist.init_process_group("nccl", device_id=dev)
     t_setup = time.time()
     cat = bench.make_case(args.size)
@@ -171,6 +197,7 @@ def bench_main(args, rank, world):
                                     + ("stores into peer memory over NVLink + flags" if getattr(model, "_mg_p2p", False)
                                        else "NCCL all-gather") + ")",
                        "routing": "scan", "forcing_ring_days": args.ring, "setup_s": round(setup_s, 1),
+                       "host_affinity": f"rank 0 bound to the {numa_cpus} CPUs NVML lists next to its GPU" if numa_cpus else "unchanged",
                        "l2": "per-GPU per-step working set %.2f GB (larger than the 126 MB L2)" % (bench.ALG_BYTES_WB * n_local / 1e9)},
             "roofline": {"kernel": "k_wb_step (fused vertical water balance), rank 0", "bound": "hbm", "achieved": ach, "peak": peak,
                          "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak, "traffic": None,
