@@ -383,6 +383,32 @@ def test_csf_input_directory_matches_in_memory_source():
     b.close()
 
 
+def test_run_script_writes_the_reference_outputs():
+    """`python -m sphy_b200 sphy_config.cfg` (the reference's `python sphy.py sphy_config.cfg`): CSF inputs on disk in,
+    reported CSF maps and .tss files out."""
+    import datetime
+    import subprocess
+    import sys
+    import tempfile
+    from sphy_b200 import csf, synth
+    cat = synth.make_catchment(30, 26, seed=13, nsteps=5, start=datetime.date(2001, 6, 1), report_daily=("TotRF",),
+                               report_opts={"QallRAtot": ("D", "NONE", "D")}, params=dict(SubWater=470.0, RootDepthFlat=150.0, Pscale=2.5))
+    tmp = tempfile.mkdtemp(prefix="sphy_cli_")
+    cfg = cat.write_inputs(os.path.join(tmp, "in"), os.path.join(tmp, "out"))
+    cat.write_csf_inputs(os.path.join(tmp, "in"), 5)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "sphy_b200", cfg], cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "Simulation succesfully completed" in r.stdout
+    out = os.path.join(tmp, "out")
+    files = sorted(os.listdir(out))
+    assert any(f.endswith(".tss") for f in files), files
+    maps = [f for f in files if f.startswith("QAll") and not f.endswith(".tss")]
+    assert len(maps) == 5, files
+    arr, info = csf.read_map(os.path.join(out, maps[-1]))
+    assert arr.shape == (30, 26) and info["cellsize"] == cat.cellsize and np.isfinite(arr).all() and (arr >= 0).all() and arr.max() > 0
+
+
 def test_per_cell_latitude_mode_matches_table_mode():
     """SPHY_RA_CELL (per-cell sin/cos/tan(lat) maps, projected grids with > 65536 distinct latitudes) and SPHY_RA_TABLE
     (latitude classes) evaluate the same double-precision transcendentals: identical results."""
