@@ -70,3 +70,15 @@ def test_product_does_not_import_the_oracle():
 def test_built_for_sm100a_only():
     flags = " ".join(_build.NVCC_FLAGS)
     assert "arch=compute_100a,code=sm_100a" in flags and "-fmad=false" in flags
+
+
+def test_every_entry_point_is_documented_for_integrators():
+    """INTEGRATION.md names, for every exported entry point, the reference interface it replaces."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "sphy_b200.h")).read()
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    syms = sorted(set(re.findall(r"\b(sphy_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(syms) > 30
+    missing = [s for s in syms if s not in doc]
+    assert not missing, missing
