@@ -80,6 +80,10 @@ CASES = {
     # sediment trapped in reservoirs, sub-catchments routed in the steps of resorder.txt (sediment_transport.py:46-107)
     "c3_sed_reservoirs": (dict(nrows=18, ncols=16, seed=47, cellsize=500.0, sediment=dict(upstream_km2=2.0), infil_excess=1,
                                reservoirs=True, n_res_simple=3, n_res_adv=2, params=WET, start=(2001, 6, 1)), 25),
+    # MUSLE soil loss (SedModel = 1, modules/musle.py), K-factor from a map / from texture (pedotransfer)
+    "c1_sed_musle": (dict(nrows=12, ncols=10, seed=44, sediment=dict(model=1), infil_excess=1, params=WET, start=(2001, 6, 1)), 25),
+    "c1_sed_musle_pedo": (dict(nrows=12, ncols=10, seed=45, sediment=dict(model=1, P_USLE=0.8), pedotransfer=True, infil_excess=1,
+                               params=WET, start=(2001, 6, 1)), 25),
     # BASELINE config 3: reservoirs (simple + advanced) and lakes
     "c3_res_lake": (dict(nrows=16, ncols=14, seed=31, cellsize=1000.0, reservoirs=True, lakes=True, n_res_simple=2,
                          n_res_adv=2, n_lakes=4, params=WET, start=(2001, 5, 1)), 70),

@@ -206,6 +206,8 @@ class Catchment:
                     m[k + ".map"] = v
         if self.sediment is not None and "reservoirs" in self.sediment:
             m["reservoirs_nominal.map"] = self.sediment["reservoirs"]
+        if self.sediment is not None and int(self.sediment.get("model", 2)) == 1 and self.pedotransfer is None:
+            m["k_usle.map"] = self.sediment["k_usle"]
         if self.sediment is not None:
             m["rock_fraction.map"] = self.sediment["rock"]
             m["root_sand.map"] = self.sediment["sand"]
@@ -275,7 +277,7 @@ class Catchment:
                 for rid, step in self.sediment["res_order"]:
                     fh.write(f"{rid}\t{step}\n")
         if self.sediment is not None:
-            for fname in ("mmf.tbl", "mmf_harvest.tbl"):
+            for fname in ("mmf.tbl", "mmf_harvest.tbl", "musle.tbl"):
                 with open(os.path.join(inputdir, fname), "w") as fh:
                     for row in self.sediment[fname]:
                         fh.write(" ".join(repr(float(v)) for v in row) + "\n")
@@ -314,7 +316,7 @@ ResFLAG = {f['ResFLAG']}
 DynVegFLAG = {1 if self.dynveg else 0}
 GroundFLAG = {f['GroundFLAG']}
 SedFLAG = {1 if self.sediment else 0}
-SedTransFLAG = {1 if self.sediment else 0}
+SedTransFLAG = {1 if (self.sediment and int(self.sediment.get("model", 2)) == 2) else 0}
 [DIRS]
 inputdir = {inputdir.rstrip('/')}/
 outputdir = {outputdir.rstrip('/')}/
@@ -354,10 +356,14 @@ SubClayMap = sub_clay.map
 SubOMMap = sub_OM.map
 SubBulkMap = sub_bulk.map
 [SEDIMENT]
-SedModel = 2
+SedModel = {int((self.sediment or {}).get("model", 2))}
 RockFrac = rock_fraction.map
 exclChannelsFLAG = {int((self.sediment or {}).get("excl_channels", 1))}
 upstream_km2 = {(self.sediment or {}).get("upstream_km2", 1.0)}
+[MUSLE]
+K_USLE = {"" if self.pedotransfer else "k_usle.map"}
+P_USLE = {(self.sediment or {}).get("P_USLE", 1)}
+musle_table = musle.tbl
 [MMF]
 MMF_table = mmf.tbl
 harvestFLAG = {int((self.sediment or {}).get("harvest", 1))}
@@ -700,6 +706,9 @@ def _add_sediment(cat, seed, opts):
     cat.sediment = dict(opts, landuse=lu, sand=sand, clay=clay, rock=rock)
     cat.sediment["mmf.tbl"] = mmf
     cat.sediment["mmf_harvest.tbl"] = harv
+    #            class C-factor retardance N (modules/musle.py:115-119)
+    cat.sediment["musle.tbl"] = [[0, 1, 2], [1, 0.003, 0.6], [2, 0.2, 0.2], [3, 0.45, 0.05]]
+    cat.sediment["k_usle"] = np.clip(0.03 + 0.015 * _smooth_noise(r, nr, nc, 4), 0.005, 0.07).astype(np.float32)
 
 
 def _add_sediment_reservoirs(cat, seed):
