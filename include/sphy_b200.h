@@ -190,6 +190,8 @@ enum {
     SPHY_OP_HLEVEL,              /* groundwater.HLevel         :43-47 */
     SPHY_OP_SNOW_DYNAMIC,        /* snow.dynamic               modules/snow.py:110-187   (6 outputs) */
     SPHY_OP_GROUNDWATER_DYNAMIC, /* groundwater.dynamic        modules/groundwater.py:90-125 (4 outputs) */
+    SPHY_OP_MUSLE,               /* musle.q_peak + musle.MUSLE modules/musle.py:29-46,143-150: in Q|TotR, Alpha_tc, Tc, K, C, P, LS,
+                                    CFRG, cellarea, ha_area, q_is_discharge -> sediment yield, ton per cell */
     SPHY_OP_COUNT
 };
 int sphy_module_op(sphy_ctx *ctx, int op, const sphy_param *in, int n_in, float *const *out, int n_out, int64_t count,

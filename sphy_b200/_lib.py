@@ -110,7 +110,7 @@ SCAN_TILE = 1024                      # cells per scan-routing tile (csrc/route_
 OPS = ("EXTRARAD", "HARGREAVES", "ETPOT", "ETACT", "KS", "POTSNOWMELT", "ACTSNOWMELT", "SNOWSTOREUPDATE", "MAXSNOWWATSTORAGE",
        "SNOWWATSTORAGE", "TOTSNOWSTORAGE", "SNOWR", "ROOTRUNOFF_SAT", "ROOTRUNOFF_INFIL", "ROOTDRAINAGE", "ROOTPERCOLATION",
        "CALCFRAC", "CAPILRISE", "SUBPERCOLATION", "SUBDRAINAGE", "GWRECHARGE", "BASEFLOW", "HLEVEL", "SNOW_DYNAMIC",
-       "GROUNDWATER_DYNAMIC")
+       "GROUNDWATER_DYNAMIC", "MUSLE")
 OP = {name: i for i, name in enumerate(OPS)}
 UNARY_EXP_NEG_INV, UNARY_SIN_DEG, UNARY_COS_DEG, UNARY_TAN_DEG, UNARY_EXP_NEG = 0, 1, 2, 3, 4
 

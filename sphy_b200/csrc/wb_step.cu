@@ -283,6 +283,14 @@ __global__ void k_module_op(const __grid_constant__ OpArgs a)
             SnowR = (SnowR * I(13)) * I(14);
             r0 = Rain; r1 = SnowR; r2 = SnowSoil; r3 = ss; r4 = sws; r5 = tss;
         } break;
+        case SPHY_OP_MUSLE: {                          // musle.dynamic, modules/musle.py:29-46,143-150
+            // in: Q (m3/s) or TotR (mm), Alpha_tc, Tc, K_USLE, C_USLE, P_USLE, LS_USLE, CFRG, cellarea, ha_area, q_is_discharge
+            const float area = I(8);
+            const float Runoff = I(10) != 0.0f ? (((I(0) * 3600.0f) * 24.0f) / area) * 1000.0f : I(0);       // sphy.py:1217-1220
+            const float q_peak = ((I(1) * Runoff) * area) / (3600000.0f * I(2));
+            const float sed = ((((((11.8f * sf::d_pow((Runoff * q_peak) * I(9), 0.56f)) * I(3)) * I(4)) * I(5)) * I(6)) * I(7));
+            r0 = (sed / 10000.0f) * area;
+        } break;
         case SPHY_OP_GROUNDWATER_DYNAMIC: {            // groundwater.dynamic, modules/groundwater.py:90-125
             // in: e_delta GwRecharge ActSubPerc GlacPerc Gw BaseR BaseThresh e_alpha H_gw h_den (1-openWaterFrac)
             // out: GwRecharge Gw BaseR H_gw

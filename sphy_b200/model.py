@@ -201,7 +201,7 @@ class SphyModel:
         self.groundwater, self.snow, self.glacier = modules.groundwater, modules.snow, modules.glacier
         self.routing, self.advanced_routing = modules.routing, modules.advanced_routing
         self.lakes, self.reservoirs = modules.lakes, modules.reservoirs
-        self.mmf, self.sediment_transport = modules.mmf, modules.sediment_transport
+        self.mmf, self.musle, self.sediment_transport = modules.mmf, modules.musle, modules.sediment_transport
 
     # ------------------------------------------------------------------------------------------
     def close(self):
@@ -791,9 +791,16 @@ class SphyModel:
         if self.world > 1:
             raise NotImplementedError("sediment transport is not available on a partitioned basin")
         self.SedModel = cfg.getfloat("SEDIMENT", "SedModel")
-        if self.SedModel != 2:
-            raise NotImplementedError("only the MMF erosion model (SedModel = 2) is supported; MUSLE/INCA/SHETRAN/DHSVM/HSPF are not")
+        if self.SedModel not in (1, 2):
+            raise NotImplementedError("erosion models MUSLE (1) and MMF (2) are supported; INCA/SHETRAN/DHSVM/HSPF are not")
         self.RockFrac = self._compact_np(self._readmap(cfg.get("SEDIMENT", "RockFrac")))
+        if self.SedModel == 1:                                                                 # sphy.py:485-493
+            if self.SedTransFLAG == 1:
+                raise NotImplementedError("sediment transport after MUSLE: sediment_transport.dynamic_musle reads undefined names "
+                                          "(modules/sediment_transport.py:227-241) and cannot run in the reference either")
+            self.musle.init(self, None, cfg)
+            self.sed_out = {}
+            return
         self.exclChannelsFLAG = cfg.getint("SEDIMENT", "exclChannelsFLAG")
         if self.exclChannelsFLAG == 1:                                                         # sphy.py:474-482
             ones = torch.ones(self.n, dtype=torch.float32, device=self.device)
@@ -1265,7 +1272,9 @@ class SphyModel:
             ev[2].record()
             prof["wb"].append((ev[0], ev[1]))
             prof["route"].append((ev[1], ev[2]))
-        if self.SedFLAG == 1:                                                                  # sphy.py:1214-1240
+        if self.SedFLAG == 1 and self.SedModel == 1:                                           # sphy.py:1222-1225
+            self.musle.dynamic(self, None, self.Q if self.Q is not None else self.TotR)
+        elif self.SedFLAG == 1:                                                                # sphy.py:1214-1240
             G = self.mmf.dynamic(self, None, f["prec"], self.Q if self.Q is not None else self.TotR)
             if self.SedTransFLAG == 1:
                 self.sediment_transport.dynamic_mmf(self, None, None, None, G)
@@ -1404,8 +1413,9 @@ class SphyModel:
                 d["StorCanop"] = lambda: self.Scanopy
         if self.SedFLAG == 1:                                      # mmf.py:259-306, sediment_transport.py:261-275
             so = self.sed_out
-            d.update(DetRn=lambda: so["DetRn"], DetRun=lambda: so["DetRun"], SDepFld=lambda: so["SDepFld"],
-                     SedTrans=lambda: so["SedTrans"])
+            d["SedTrans"] = lambda: so["SedTrans"]
+            if self.SedModel == 2:
+                d.update(DetRn=lambda: so["DetRn"], DetRun=lambda: so["DetRun"], SDepFld=lambda: so["SDepFld"])
             if self.SedTransFLAG == 1:
                 d.update(TC=lambda: so["TC"], SedDep=lambda: so["SedDep"], SedYld=lambda: so["SedYld"], SedFlux=lambda: so["SedFlux"])
         d["TotRF"] = lambda: self.TotR

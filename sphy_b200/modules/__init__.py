@@ -96,5 +96,5 @@ def exp_neg(x):
     return float(f32(math.exp(float(f32(-x)))))
 
 
-from . import (ET, advanced_routing, glacier, groundwater, hargreaves, lakes, mmf, pedotransfer, reservoirs, rootzone, routing,  # noqa: E402,F401
+from . import (ET, advanced_routing, glacier, groundwater, hargreaves, lakes, mmf, musle, pedotransfer, reservoirs, rootzone, routing,  # noqa: E402,F401
                sediment_transport, snow, subzone)
