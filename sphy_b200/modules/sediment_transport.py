@@ -17,34 +17,29 @@ def _canonical(self):
     return to_canon, to_dev
 
 
-def subcatchment(self, points_dev):
-    """pcr.subcatchment(ldd, points): every cell takes the id of the first non-zero point on its way downstream.
-    Level by level from the outlets, over the canonical LDD structures; returns the ids by device index."""
-    to_canon, to_dev = _canonical(self)
-    down = self.ldd_structure("down").cpu().numpy().astype(np.int64)
-    order = self.ldd_structure("order").cpu().numpy().astype(np.int64)
-    lptr = self.ldd_structure("level_ptr").cpu().numpy().astype(np.int64)
-    pts = np.asarray(points_dev, np.int64)[to_dev]
-    out = np.zeros(self.n + 1, np.int64)                         # slot n: "drains out of the map"
-    for lv in range(len(lptr) - 2, -1, -1):
-        c = order[lptr[lv]:lptr[lv + 1]]
-        d = np.where(down[c] >= 0, down[c], self.n)
+def subcatchment_levels(down, order, level_ptr, points):
+    """pcr.subcatchment(ldd, points) over the canonical LDD structures (`down` receiver or -1, `order` cells by level,
+    `level_ptr`): every cell takes the id of the first non-zero point on its way downstream.  Level by level from the
+    outlets, vectorised per level."""
+    n = len(down)
+    pts = np.asarray(points, np.int64)
+    out = np.zeros(n + 1, np.int64)                              # slot n: "drains out of the map"
+    for lv in range(len(level_ptr) - 2, -1, -1):
+        c = order[level_ptr[lv]:level_ptr[lv + 1]]
+        d = np.where(down[c] >= 0, down[c], n)
         out[c] = np.where(pts[c] != 0, pts[c], out[d])
-    return out[:self.n][to_canon]
+    return out[:n]
 
 
-def streamorder(self):
-    """pcr.streamorder(ldd): Strahler order, level by level from the headwaters; by device index."""
-    to_canon, _ = _canonical(self)
-    down = self.ldd_structure("down").cpu().numpy().astype(np.int64)
-    order = self.ldd_structure("order").cpu().numpy().astype(np.int64)
-    lptr = self.ldd_structure("level_ptr").cpu().numpy().astype(np.int64)
-    n = self.n
+def streamorder_levels(down, order, level_ptr):
+    """pcr.streamorder(ldd): Strahler order (headwater cells 1; two or more donors of the maximum order -> +1), level by
+    level from the headwaters."""
+    n = len(down)
     mx = np.zeros(n, np.int64)      # largest donor order seen so far
     cnt = np.zeros(n, np.int64)     # how many donors have it
     so = np.ones(n, np.int64)
-    for lv in range(len(lptr) - 1):
-        c = order[lptr[lv]:lptr[lv + 1]]
+    for lv in range(len(level_ptr) - 1):
+        c = order[level_ptr[lv]:level_ptr[lv + 1]]
         so[c] = np.where(mx[c] == 0, 1, np.where(cnt[c] >= 2, mx[c] + 1, mx[c]))
         c = c[down[c] >= 0]
         d, o = down[c], so[c]
@@ -54,7 +49,23 @@ def streamorder(self):
         raised = np.unique(d[mx[d] > before])
         cnt[raised] = 0
         np.add.at(cnt, d, (o == mx[d]).astype(np.int64))
-    return so[to_canon]
+    return so
+
+
+def _structures(self):
+    return (self.ldd_structure("down").cpu().numpy().astype(np.int64), self.ldd_structure("order").cpu().numpy().astype(np.int64),
+            self.ldd_structure("level_ptr").cpu().numpy().astype(np.int64))
+
+
+def subcatchment(self, points_dev):
+    """pcr.subcatchment for maps in device cell order (the LDD structures are exported in canonical numbering)."""
+    to_canon, to_dev = _canonical(self)
+    return subcatchment_levels(*_structures(self), np.asarray(points_dev, np.int64)[to_dev])[to_canon]
+
+
+def streamorder(self):
+    to_canon, _ = _canonical(self)
+    return streamorder_levels(*_structures(self))[to_canon]
 
 
 def init(self, pcr, config, csv=None, np_=None):
