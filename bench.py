@@ -26,8 +26,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 PARAMS = dict(SubWater=470.0)          # cfg defaults except a wet subsoil, so percolation/baseflow are active from day 1
-ALG_BYTES_WB = 92                      # SURVEY 8d formula, n_forcing 4 + n_param_maps 2 (lat class, drain velocity) + 2*8 state + TotR
-ALG_BYTES_ROUTE = 24                   # per routed component
+ALG_BYTES_WB = 88                      # 4 * (n_forcing 4 + n_param_maps 1 + 2 * n_state 8 + n_out 1) -- what `achieved` is quoted on
+STREAM_BYTES_WB = 90                   # what this instance streams: 4 forcing, 8 state in + 8 out, TotR, drain velocity, 2-byte latitude class
+ALG_BYTES_SCAN = 16                    # k_scan_main per routed component: runoff, sub_size, Qold in, Q out
 
 
 def k1_traffic_per_cell():
@@ -93,24 +94,63 @@ def make_case(size, seed=1, cellsize=250.0, nsteps=365):
                                 start=datetime.date(2001, 6, 1))
 
 
-def device_forcing_ring(torch, dem_dev, ring, seed):
-    """Synthetic daily forcing generated directly in HBM (SURVEY 8d formulas; wet days every other day)."""
-    g = torch.Generator(device=dem_dev.device)
-    g.manual_seed(seed)
+def _hash_uniform(torch, idx, key):
+    """Counter-based uniform numbers in [0, 1): a splitmix64-style integer hash of (global cell index, key).  Every value
+    depends only on the cell's GLOBAL device index, so 1, 2, 4 or 8 ranks generate bit-identical forcing for the same cell."""
+    m = (1 << 63) - 1
+    x = idx * -7046029254386353131 + (key * 0x632BE59BD9B4E019 & m)          # int64 arithmetic wraps
+    x = (x ^ ((x >> 30) & ((1 << 34) - 1))) * -4658895280553007687
+    x = (x ^ ((x >> 27) & ((1 << 37) - 1))) * -7723592293110705685
+    x = x ^ ((x >> 31) & ((1 << 33) - 1))
+    return ((x >> 40) & 0xFFFFFF).to(torch.float32) * (1.0 / 16777216.0)
+
+
+def _hash_normal(torch, idx, key):
+    """Approximately N(0, 1): sum of four hashed uniforms (Irwin-Hall), exact integer hashing + a few float32 adds."""
+    s = _hash_uniform(torch, idx, 4 * key) + _hash_uniform(torch, idx, 4 * key + 1)
+    s = s + _hash_uniform(torch, idx, 4 * key + 2) + _hash_uniform(torch, idx, 4 * key + 3)
+    return (s - 2.0) * 1.7320508
+
+
+def device_forcing_ring(torch, dem_dev, ring, seed, cell_begin=0):
+    """Synthetic daily forcing generated directly in HBM (SURVEY 8d formulas; wet days every other day).  `cell_begin` is
+    the global device index of this rank's first cell: the forcing of a cell does not depend on the partitioning."""
     days = []
     n = dem_dev.numel()
+    idx = torch.arange(cell_begin, cell_begin + n, dtype=torch.int64, device=dem_dev.device)
     for d in range(ring):
         doy = 152 + d
+        key = seed * 64 + d * 4
         season = 10.0 * math.sin(2.0 * math.pi * (doy - 105) / 365.0)
-        tavg = (12.0 - 6.5e-3 * (dem_dev - 1000.0) + season + torch.randn(n, device=dem_dev.device, generator=g)).float()
-        tmax = tavg + 5.0 + 2.0 * torch.rand(n, device=dem_dev.device, generator=g)
-        tmin = tavg - 5.0 - 2.0 * torch.rand(n, device=dem_dev.device, generator=g)
+        tavg = (12.0 - 6.5e-3 * (dem_dev - 1000.0) + season + _hash_normal(torch, idx, key)).float()
+        tmax = tavg + 5.0 + 2.0 * _hash_uniform(torch, idx, 16 * key + 1001)
+        tmin = tavg - 5.0 - 2.0 * _hash_uniform(torch, idx, 16 * key + 1002)
         if d % 2 == 0:
-            prec = (8.0 * torch.clamp(1.0 + 0.3 * torch.randn(n, device=dem_dev.device, generator=g), min=0.0)).float()
+            prec = (8.0 * torch.clamp(1.0 + 0.3 * _hash_normal(torch, idx, key + 3), min=0.0)).float()
         else:
             prec = torch.zeros(n, device=dem_dev.device)
         days.append(dict(prec=prec.contiguous(), tavg=tavg.contiguous(), tmin=tmin.contiguous(), tmax=tmax.contiguous()))
+    del idx
     return days
+
+
+def discharge_check(torch, model, dist=None):
+    """What makes bench lines at different GPU counts comparable: discharge at the outlet (global cell 0 of the DFS order),
+    the sum and the maximum of the discharge map, and the sum over the first eighth of the cells (rank 0's range on 8
+    GPUs, inside rank 0's range for any smaller count), all in float64."""
+    from sphy_b200 import multigpu
+    q = model.QRAold.double()
+    n_glob = model.n_global
+    lo = model.part_range[0] if getattr(model, "part_range", None) else 0
+    first = int(multigpu.partition_bounds(n_glob, 8)[1]) if n_glob >= 8 * multigpu.TILE else n_glob
+    hi_local = max(0, min(first - lo, q.numel()))
+    vals = torch.stack([q.sum(), q[:hi_local].sum(), q[0] if lo == 0 else q.new_zeros(())])
+    mx = q.max().reshape(1)
+    if dist is not None:
+        dist.all_reduce(vals, op=dist.ReduceOp.SUM)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    v = vals.cpu().tolist()
+    return {"outlet_q": v[2], "sum_q": v[0], "sum_q_first_eighth": v[1], "max_q": float(mx.item()), "timestep": int(model.timestep)}
 
 
 def cpu_port_rate(size, steps, seed=1):
@@ -267,6 +307,7 @@ def main():
         model.dynamic()
     torch.cuda.synchronize()
     model.enable_profiling(True)
+    model.lib.sphy_route_profile(model._ctx, 1)
     sampler = ClockSampler(0)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -285,6 +326,8 @@ def main():
     value = n * args.steps / (ms_total * 1e-3) / 1e6
     peak, peak_kind = measured_peak()
     ach = ALG_BYTES_WB * n / (wb_ms * 1e-3) / 1e9
+    check = discharge_check(torch, model)
+    rprof = route_profile(model)
 
     # ---- e2e: host buffers, H2D of the day's forcing + D2H of station discharges inside the timed region ----
     # host side holds RASTERS (what readmap delivers); the model copies them H2D and compacts them into device order
@@ -328,12 +371,14 @@ def main():
                "host_cores_available": os.cpu_count()}
 
     # my kernels per step: k_ra_table, k_wb_step, k_sample + routing (3 scan kernels, or one launch per plan segment)
-    nlaunch_step = 3 + (3 if args.route == "scan" else len(model_plan(model)))
+    # (scan: main, tile-total scan, crossing cells + publish, drift, apply for the trunk cells)
+    nlaunch_step = 3 + ((3 + (3 if model.trunk_cells else 0)) if args.route == "scan" else len(model_plan(model)))
     line = {
         "metric": "Mcell-timesteps/s", "value": value, "unit": "Mcell-timesteps/s", "n_gpus": 1, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.size), "cells": n, "levels": model.nlevels, "routing": args.route,
+                   "trunk_cells": getattr(model, "trunk_cells", 0),
                    "l2": "per-step working set %.1f GB >> 126 MB L2 (inputs larger than L2, no flush needed)" % (ALG_BYTES_WB * n / 1e9)
                    if ALG_BYTES_WB * n > 4 * 126e6 else "working set fits L2: throughput only, no roofline claim",
                    "forcing_ring_days": args.ring, "setup_s": round(setup_s, 1)},
@@ -341,7 +386,10 @@ def main():
                      "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak,
                      "traffic": (k1_traffic_per_cell() * n if k1_traffic_per_cell() else None),
                      "traffic_note": "bytes per launch = ncu dram bytes per cell (profiles/r1_k1_traffic.json, 36e6-cell capture) x cells",
-                     "alg_bytes_per_cell": ALG_BYTES_WB, "alg_bytes_per_launch": ALG_BYTES_WB * n, "kernel_ms": wb_ms, "route_ms": rt_ms},
+                     "alg_bytes_per_cell": ALG_BYTES_WB, "alg_bytes_per_launch": ALG_BYTES_WB * n, "kernel_ms": wb_ms, "route_ms": rt_ms,
+                     "streamed_bytes_per_cell": STREAM_BYTES_WB, "achieved_on_streamed_bytes": STREAM_BYTES_WB * n / (wb_ms * 1e-3) / 1e9},
+        "roofline_route": scan_roofline(rprof, n, 1, peak),
+        "check": check,
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_val, "unit": "Mcell-timesteps/s", "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": d2h // e2e_steps,
                 "steps": e2e_steps},
@@ -350,6 +398,26 @@ def main():
     }
     print(json.dumps(line))
     model.close()
+
+
+def route_profile(model):
+    """Average per-step device time of the scan routing's phases (CUDA events recorded by the library on the launching
+    stream): main pass, tile-crossing cells, trunk cells."""
+    import ctypes as C
+    if model.route_method != 1:
+        return None
+    out = (C.c_float * 4)()
+    cnt = C.c_int(0)
+    model.lib.sphy_route_profile_read(model._ctx, out, C.byref(cnt))
+    return {"scan_main_ms": out[0], "totals_cross_ms": out[1], "trunk_ms": out[2], "steps": cnt.value} if cnt.value else None
+
+
+def scan_roofline(rprof, n, ncomp, peak):
+    if not rprof:
+        return None
+    ach = ALG_BYTES_SCAN * ncomp * n / (rprof["scan_main_ms"] * 1e-3) / 1e9
+    return dict(rprof, kernel="k_scan_main (float64 tile prefix + range sums + recession blend)", bound="hbm", achieved=ach, peak=peak,
+                unit="GB/s", frac=ach / peak, alg_bytes_per_cell=ALG_BYTES_SCAN * ncomp, traffic=None)
 
 
 def model_plan(model):

@@ -315,20 +315,42 @@ int sphy_glac_report(sphy_ctx *ctx, int32_t n_glac, const int32_t *row_ptr, cons
 int sphy_route_step(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm, float *const *q_state, sphy_param kx,
                     float one_minus_kx /* REAL4(1-kx) when kx is a scalar: Python-double subtraction, routing.py:28 */,
                     int method, void *stream);
+/* Optional per-phase device timing of SPHY_ROUTE_SCAN (what bench.py's second roofline entry is measured with): while
+ * enabled every routing step records four CUDA events on its stream; sphy_route_profile_read synchronises on the last
+ * one and returns the mean milliseconds per step of {main pass, tile totals + crossing cells, trunk cells (incl. the
+ * exchange on a partitioned context), whole routing} and the number of steps seen, then clears the record. */
+int sphy_route_profile(sphy_ctx *ctx, int enable);
+int sphy_route_profile_read(sphy_ctx *ctx, float *ms4, int *steps);
 /* Cells per scan-routing tile (a compile-time constant of the library); partition ranges must start on a tile. */
 int sphy_scan_tile_cells(void);
 
+/* Trunk list of the scan path.  The reference rounds every cell's accuflux sum to REAL4 (PCRaster, routing.py:27); along
+ * the ~10^4-cell main stem of a 10^8-cell basin those roundings add up to ~1e-5 of the flux, which exact float64 range
+ * sums do not contain.  sphy_trunk_select lists the downstream-closed set {level >= min_level or sub_size >= min_cells}
+ * (both thresholds must exceed the 1024-cell scan tile) -- plus, with world > 1, every cell whose upstream range crosses
+ * one of the rank bounds (world + 1 host values, tile-aligned) -- by ascending device index (= DFS pre-order of the trunk
+ * tree; global indices, identical on every rank).  Listed cells are finished from PUBLISHED prefixes: the context
+ * publishes its range total and the range-local inclusive prefix at the positions in `pub_pos` (local indices, ascending);
+ * entry s of the list reads the global prefix just before its cell at (before_rank[s], before_slot[s]) (rank -1 = none)
+ * and at the end of its upstream range at (end_rank[s], end_slot[s]).  Trunk entries additionally carry the reference's
+ * rounding drift as a second linear accumulation over the list (csrc/route_scan.cu: k_trunk_drift), which keeps
+ * SPHY_ROUTE_SCAN within 1e-5 of the REAL4-per-cell arithmetic at any basin size.  The plan is host logic
+ * (sphy_b200/multigpu.py: plan_trunk) over the small exported arrays "cell", "sub_size" (int32), "is_trunk" (uint8),
+ * "last" (int32) and "donors" (8 x int32 per entry).  With a plan installed sphy_route_step(SPHY_ROUTE_SCAN) uses it. */
+int sphy_trunk_select(sphy_ctx *ctx, int32_t min_level, int64_t min_cells, int world, const int64_t *bounds_host,
+                      int64_t *count_out, void *stream);
+int sphy_trunk_export(sphy_ctx *ctx, const char *name, void *dst_dev, size_t dst_bytes, void *stream);
+int sphy_trunk_set_plan(sphy_ctx *ctx, int32_t n_pub, const int32_t *pub_pos_dev, const int32_t *before_rank_dev,
+                        const int32_t *before_slot_dev, const int32_t *end_rank_dev, const int32_t *end_slot_dev,
+                        int32_t stride /* >= 1 + max n_pub over the ranks */, int rank, int world, void *stream);
+
 /* Multi-GPU (one context per GPU, each built on the whole LDD): restrict this context to the contiguous device-index
  * range [cell_begin, cell_end) of the DFS order (cell_begin on a 1024-cell tile).  After the call every compact map
- * and sphy_ncells() refer to the local cells only.  pub_e: local indices at which other ranks' upstream ranges end
- * (ascending); remote_*: for each local cell whose range ends on another rank (ascending), its slot in this
- * context's tile-crossing list, the rank that owns the range end, and the slot in that rank's pub_e.  The lists are
- * planned on the host (sphy_b200/multigpu.py) from the "sub_size" export.  The per-step confluence exchange is
+ * and sphy_ncells() refer to the local cells only.  Call order: sphy_trunk_select(world, bounds) -> sphy_set_partition ->
+ * sphy_trunk_set_plan.  The per-step confluence exchange is
  *   sphy_route_scan_begin -> all-gather of `send` (stride doubles per component and rank) -> sphy_route_scan_finish
  * and replaces the single-GPU sphy_route_step (modules/routing.py:25-29) on a partitioned context. */
-int sphy_set_partition(sphy_ctx *ctx, int64_t cell_begin, int64_t cell_end, int32_t n_pub, const int32_t *pub_e_dev,
-                       int32_t n_remote, const int32_t *remote_k_dev, const int32_t *remote_rank_dev,
-                       const int32_t *remote_slot_dev, void *stream);
+int sphy_set_partition(sphy_ctx *ctx, int64_t cell_begin, int64_t cell_end, void *stream);
 int sphy_route_scan_begin(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm, float *const *q_state, sphy_param kx,
                           float one_minus_kx, double *send_dev, int32_t stride, void *stream);
 int sphy_route_scan_finish(sphy_ctx *ctx, int ncomp, float *const *q_state, sphy_param kx, float one_minus_kx,

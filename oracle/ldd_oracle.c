@@ -166,6 +166,23 @@ void ldd_accucapacity(const int32_t *order, const int32_t *down, int64_t n, cons
     free(acc);
 }
 
+/* The other candidate for PCRaster's accumulation arithmetic (assumption A1 as first written): the inflow of a
+ * cell is a REAL4 variable to which the donors' fluxes are added one by one, in traversal order (here: routing order =
+ * level, then cell index), each add rounded to REAL4.  Identical to ldd_accuflux wherever a cell has at most one donor;
+ * at confluences it rounds once per donor instead of once per cell.  Unverifiable without a PCRaster build; kept so
+ * that every routing path can report its distance to both candidate reference models. */
+void ldd_accuflux_f32inc(const int32_t *order, const int32_t *down, int64_t n, const float *m, float *flux)
+{
+    for (int64_t i = 0; i < n; ++i) flux[i] = m[i];
+    for (int64_t k = 0; k < n; ++k) {
+        int32_t i = order[k];
+        if (down[i] >= 0) {
+            volatile float s = flux[down[i]] + flux[i];      /* one REAL4 add per donor */
+            flux[down[i]] = s;
+        }
+    }
+}
+
 /* float64 twin used for error attribution (no REAL4 rounding along the path) */
 void ldd_accuflux_f64(const int32_t *order, const int32_t *down, int64_t n, const float *m,
                       const float *frac, double *flux)

@@ -35,6 +35,8 @@ def ldd_lib():
     lib.ldd_accuflux.argtypes = [P, P, ctypes.c_int64, P, P, P, P]
     lib.ldd_accuflux_f64.restype = None
     lib.ldd_accuflux_f64.argtypes = [P, P, ctypes.c_int64, P, P, P]
+    lib.ldd_accuflux_f32inc.restype = None
+    lib.ldd_accuflux_f32inc.argtypes = [P, P, ctypes.c_int64, P, P]
     lib.ldd_accucapacity.restype = None
     lib.ldd_accucapacity.argtypes = [P, P, ctypes.c_int64, P, P, P, P]
     lib.ldd_upstream.restype = None
@@ -135,6 +137,14 @@ class LddStruct:
         fr = None if frac is None else np.ascontiguousarray(frac, np.float32)
         flux = np.empty(self.n, np.float64)
         lib.ldd_accuflux_f64(_p(self.order), _p(self.down), self.n, _p(m), _p(fr), _p(flux))
+        return flux
+
+    def accuflux_f32inc(self, m):
+        """accuflux with REAL4 adds donor by donor in routing order (the second candidate reference model)."""
+        lib = ldd_lib()
+        m = np.ascontiguousarray(m, np.float32)
+        flux = np.empty(self.n, np.float32)
+        lib.ldd_accuflux_f32inc(_p(self.order), _p(self.down), self.n, _p(m), _p(flux))
         return flux
 
     def upstream(self, x):

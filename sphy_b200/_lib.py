@@ -135,6 +135,8 @@ SYMBOLS = {
     "sphy_set_ncells": (C.c_int, [P, C.c_int64]),
     "sphy_module_op": (C.c_int, [P, C.c_int, C.POINTER(SphyParam), C.c_int, C.POINTER(P), C.c_int, C.c_int64, C.c_float, C.c_int, P]),
     "sphy_scan_tile_cells": (C.c_int, []),
+    "sphy_route_profile": (C.c_int, [P, C.c_int]),
+    "sphy_route_profile_read": (C.c_int, [P, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "sphy_p2p_setup_local": (C.c_int, [P, C.c_int, C.c_int64, P, P]),
     "sphy_p2p_connect": (C.c_int, [P, C.c_int, C.c_int, P, P]),
     "sphy_route_scan_exchange_p2p": (C.c_int, [P, C.c_int, P, C.c_int32, P]),
@@ -148,7 +150,10 @@ SYMBOLS = {
                                C.c_int, P]),
     "sphy_glac_step": (C.c_int, [P, C.POINTER(GlacTable), P, P, C.c_float, C.c_float, C.POINTER(GlacOut), P]),
     "sphy_route_step": (C.c_int, [P, C.c_int, C.POINTER(P), C.POINTER(P), SphyParam, C.c_float, C.c_int, P]),
-    "sphy_set_partition": (C.c_int, [P, C.c_int64, C.c_int64, C.c_int32, P, C.c_int32, P, P, P, P]),
+    "sphy_set_partition": (C.c_int, [P, C.c_int64, C.c_int64, P]),
+    "sphy_trunk_select": (C.c_int, [P, C.c_int32, C.c_int64, C.c_int, P, C.POINTER(C.c_int64), P]),
+    "sphy_trunk_export": (C.c_int, [P, C.c_char_p, P, C.c_size_t, P]),
+    "sphy_trunk_set_plan": (C.c_int, [P, C.c_int32, P, P, P, P, P, C.c_int32, C.c_int, C.c_int, P]),
     "sphy_route_scan_begin": (C.c_int, [P, C.c_int, C.POINTER(P), C.POINTER(P), SphyParam, C.c_float, P, C.c_int32, P]),
     "sphy_route_scan_finish": (C.c_int, [P, C.c_int, C.POINTER(P), SphyParam, C.c_float, P, C.c_int32, C.c_int, C.c_int, P]),
     "sphy_accuflux": (C.c_int, [P, P, P, P, C.c_int, P]),

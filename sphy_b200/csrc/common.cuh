@@ -71,9 +71,25 @@ struct sphy_ctx {
     bool partitioned = false;
     int64_t part_begin = 0, n_global = 0;
     int32_t *sub_size_loc = nullptr, *flat_loc = nullptr;   // views into sub_size / flat_active at part_begin
-    int32_t n_pub = 0, n_remote = 0;
-    int32_t *pub_e = nullptr;                                // local indices other ranks' ranges end at (ascending)
-    int32_t *remote_k = nullptr, *remote_rank = nullptr, *remote_slot = nullptr;   // per remote-ending crossing cell
+    int32_t n_pub = 0;
+    int32_t *pub_e = nullptr;                                // local indices whose range-local prefix this rank publishes (ascending)
+    // trunk list (route_scan.cu): the cells that are finished from published prefixes instead of the tile-crossing list --
+    // the downstream-closed set {level >= min_level or sub_size >= min_cells} that carries the reference's REAL4 rounding
+    // drift, plus (partitioned basin) every cell whose upstream range crosses a rank boundary.  Global device indices,
+    // ascending (= DFS pre-order of the trunk tree); identical on every rank.
+    int32_t sl_n = 0;
+    int32_t *sl_cell = nullptr, *sl_sub = nullptr, *sl_last = nullptr, *sl_tdon = nullptr;   // sl_tdon: 8 slots per entry, -1 padded
+    uint8_t *sl_trunk = nullptr;                             // 1: drift applies (0: listed only because its range leaves the rank)
+    bool sl_plan = false;
+    int32_t *sl_brank = nullptr, *sl_bslot = nullptr, *sl_erank = nullptr, *sl_eslot = nullptr;   // (rank, pub slot) of j-1 and of the range end
+    int32_t sl_stride = 0, sl_rank = 0, sl_world = 1, sl_nblk = 0;
+    int sl_comp_cap = 0;
+    double *sl_E = nullptr, *sl_Gl = nullptr, *sl_BS = nullptr, *sl_BP = nullptr;   // [ncomp][sl_n] / [ncomp][sl_nblk] workspaces
+    double *sl_V = nullptr;                                  // unpartitioned context: the published prefixes [ncomp][sl_stride]
+    unsigned *sl_counter = nullptr;
+    // optional per-phase timing of the scan routing (sphy_route_profile): events recorded on the launching stream
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev;                        // 4 per step: before main, after main, after cross, after trunk
     // workspaces
     float *acc = nullptr;          // [ROUTE_MAX_COMP][n] accumulated flux in routing order
     float *qsorted = nullptr;      // scratch [ROUTE_MAX_COMP][n]

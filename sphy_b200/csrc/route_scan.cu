@@ -43,13 +43,11 @@ struct ScanArgs {
     double *park_end;                     // [ncomp][n_cross] tile-local inclusive prefix at its range end
     double *tile_tot;                     // [ncomp][ntiles+1] tile totals (+ a trailing 0 so the scan yields the grand total)
     double *tile_excl;                    // [ncomp][ntiles+1] exclusive prefix of the totals
-    // multi-GPU (partitioned context)
-    int32_t n_pub, n_remote;
-    const int32_t *pub_e, *remote_k, *remote_rank, *remote_slot;
+    // published prefixes (trunk cells; on a partitioned basin they are what the ranks exchange)
+    int32_t n_pub;
+    const int32_t *pub_e;
     double *send;                         // [ncomp][stride]: range total, then range-local inclusive prefix at pub_e[j]
-    const double *gathered;               // [world][ncomp][stride]
-    int32_t stride, rank, world;
-    int64_t rank_pitch;                   // elements between two ranks' blocks in `gathered`
+    int32_t stride;
     // lakes / reservoirs (advanced_routing.ROUT): material is already m3/day, cut cells take the structure outflow
     int adv;
     const float *frac;                    // dense QFRAC (0 at lake / reservoir cells)
@@ -271,7 +269,7 @@ __global__ void __launch_bounds__(256) k_scan_cross(const __grid_constant__ Scan
     for (int c = 0; c < a.ncomp; ++c) {
         const double *T = a.tile_tot + (int64_t)c * (a.ntiles + 1);
         const double *X = a.tile_excl + (int64_t)c * (a.ntiles + 1);
-        double *PB = a.park_before + (int64_t)c * a.n_cross;
+        const double *PB = a.park_before + (int64_t)c * a.n_cross;
         const double *PE = a.park_end + (int64_t)c * (a.n_cross + a.n_pub);
         float *qs = a.qstate[c];
         double tt[CROSS_ILP], pb[CROSS_ILP], pe[CROSS_ILP];
@@ -279,23 +277,16 @@ __global__ void __launch_bounds__(256) k_scan_cross(const __grid_constant__ Scan
 #pragma unroll
         for (int j = 0; j < CROSS_ILP; ++j) {                  // all gathers first
             const int32_t k = k0 + j * 256;
-            const bool local = ok[j] && e[j] < a.n;
             tt[j] = ok[j] ? T[r[j] / SCAN_TILE] : 0.0;
             pb[j] = ok[j] ? PB[k] : 0.0;
-            pe[j] = local ? PE[k] : 0.0;
-            qold[j] = local ? qs[r[j]] : 0.0f;
+            pe[j] = ok[j] ? PE[k] : 0.0;
+            qold[j] = ok[j] ? qs[r[j]] : 0.0f;
             kx[j] = (ok[j] && a.kx.map) ? __ldg(a.kx.map + r[j]) : a.kx.value;
         }
 #pragma unroll
         for (int j = 0; j < CROSS_ILP; ++j) {
             if (!ok[j]) continue;
-            const int32_t k = k0 + j * 256;
             const int32_t ta = r[j] / SCAN_TILE, te = e[j] / SCAN_TILE;
-            if (e[j] >= a.n) {                                 // range ends on another rank: keep the part up to the end
-                PB[k] = range_diff(tt[j], pb[j]) +             // of this rank's range for k_scan_remote
-                        (ta + 1 < a.ntiles ? range_diff(X[a.ntiles], X[ta + 1]) : 0.0);
-                continue;
-            }
             // suffix of the first tile + whole tiles in between (none for most crossing cells) + prefix of the last tile
             const double s = range_diff(tt[j], pb[j]) + (te > ta + 1 ? range_diff(X[te], X[ta + 1]) : 0.0) + pe[j];
             const float omk = a.kx.map ? 1.0f - kx[j] : a.one_m_kx;
@@ -304,8 +295,8 @@ __global__ void __launch_bounds__(256) k_scan_cross(const __grid_constant__ Scan
     }
 }
 
-// multi-GPU: what the other ranks need from this one -- the range total and the range-local inclusive prefix at
-// every position one of their trunk cells' upstream range ends at
+// the range total and the range-local inclusive prefix at every published position (what the trunk cells are finished
+// from; on a partitioned basin this block is the "confluence inflow" message of the rank)
 __global__ void k_scan_publish(const __grid_constant__ ScanArgs a)
 {
     const int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -317,21 +308,112 @@ __global__ void k_scan_publish(const __grid_constant__ ScanArgs a)
     }
 }
 
-// multi-GPU: finish the cells whose upstream range ends on another rank, after the all-gather
-__global__ void k_scan_remote(const __grid_constant__ ScanArgs a)
+// ---- trunk cells: exact range sums + the reference's REAL4 rounding drift -----------------------------------------------
+// The reference (PCRaster accuflux, oracle/ldd_oracle.c) rounds every cell's sum to REAL4, a_c = rnd(m_c + sum_d a_d).
+// Along the ~10^4-cell main stem of a 10^8-cell basin those roundings add up to ~1e-5 of the flux, which an exact
+// (float64) range sum E_c does not contain.  The drift is itself (almost) linear: with r_c = rnd(E_c), the local term
+//     g_c = rnd(E_c + sum_{trunk donors t} (r_t - E_t)) - r_c          (a small multiple of ulp(r_c), mostly 0 or +-1 ulp)
+// is what cell c's own rounding adds given exactly-rounded inputs, rounding commutes with shifts by whole ulps, and
+// therefore a_c = rnd(r_c + D_c) with D_c = sum of g over the trunk cells upstream of c -- again a subtree range sum, over the
+// trunk list in its DFS order.  Deviations from the sequential recurrence (binade crossings, confluences of unequal binades)
+// are O(1 ulp) per event and do not amplify.  The sums of g are exact in float64 (multiples of REAL4 ulps), so the
+// result does not depend on the block decomposition or the number of ranks.
+struct TrunkArgs {
+    int32_t m, nblk;
+    const int32_t *cell, *last, *tdon;
+    const uint8_t *trunk;
+    const int32_t *brank, *bslot, *erank, *eslot;
+    double *E, *Gl, *BS, *BP;
+    unsigned *counter;
+    const double *gathered;               // [world][rank_pitch]: per rank [ncomp][stride] published blocks
+    int64_t rank_pitch, part_begin;
+    int32_t stride, world;
+};
+
+constexpr int TRUNK_BLOCK = 512;
+
+__global__ void __launch_bounds__(TRUNK_BLOCK) k_trunk_drift(const __grid_constant__ ScanArgs a, const __grid_constant__ TrunkArgs t)
 {
-    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n_remote) return;
-    const int32_t k = a.remote_k[i], q = a.remote_rank[i], slot = a.remote_slot[i];
-    const int64_t r = a.cross_r[k];
+    typedef cub::BlockScan<double, TRUNK_BLOCK> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    __shared__ double base[64];
+    __shared__ bool is_last;
+    const int tid = threadIdx.x;
+    const int32_t s = blockIdx.x * TRUNK_BLOCK + tid;
+    for (int c = 0; c < a.ncomp; ++c) {
+        __syncthreads();
+        if (tid < t.world) {                                   // global prefix at the start of every rank's range
+            double b = 0.0;
+            for (int u = 0; u < tid; ++u) b += t.gathered[(int64_t)u * t.rank_pitch + (int64_t)c * t.stride];
+            base[tid] = b;
+        }
+        __syncthreads();
+        const double *V = t.gathered + (int64_t)c * t.stride + 1;
+        auto eval = [&](int32_t e) {                           // exact accumulated flux of trunk entry e
+            const int32_t er = __ldg(t.erank + e), br = __ldg(t.brank + e);
+            const double hi = base[er] + V[(int64_t)er * t.rank_pitch + __ldg(t.eslot + e)];
+            const double lo = br < 0 ? 0.0 : base[br] + V[(int64_t)br * t.rank_pitch + __ldg(t.bslot + e)];
+            return range_diff(hi, lo);
+        };
+        double g = 0.0;
+        if (s < t.m) {
+            const double E = eval(s);
+            t.E[(int64_t)c * t.m + s] = E;
+            if (t.trunk[s]) {
+                double X = E;
+                for (int k = 0; k < 8; ++k) {
+                    const int32_t ts = __ldg(t.tdon + (int64_t)s * 8 + k);
+                    if (ts < 0) break;
+                    const double Et = eval(ts);
+                    X += (double)(float)Et - Et;               // the donor hands over rnd(E_t), not E_t
+                }
+                g = (double)(float)X - (double)(float)E;
+            }
+        }
+        double incl, total;
+        Scan(tmp).InclusiveSum(g, incl, total);
+        if (s < t.m) t.Gl[(int64_t)c * t.m + s] = incl;
+        if (tid == 0) t.BS[(int64_t)c * t.nblk + blockIdx.x] = total;
+    }
+    // the last block to finish turns the block totals into their exclusive prefix
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = atomicAdd(t.counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int c = 0; c < a.ncomp; ++c) {
+        double carry = 0.0;
+        for (int32_t b0 = 0; b0 < t.nblk; b0 += TRUNK_BLOCK) {
+            const int32_t b = b0 + tid;
+            const double v = b < t.nblk ? __ldcg(t.BS + (int64_t)c * t.nblk + b) : 0.0;
+            double ex, tot;
+            __syncthreads();
+            Scan(tmp).ExclusiveSum(v, ex, tot);
+            if (b < t.nblk) t.BP[(int64_t)c * t.nblk + b] = carry + ex;
+            carry += tot;
+        }
+    }
+    if (tid == 0) *t.counter = 0u;
+}
+
+__global__ void __launch_bounds__(256) k_trunk_apply(const __grid_constant__ ScanArgs a, const __grid_constant__ TrunkArgs t)
+{
+    const int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= t.m) return;
+    const int64_t r = (int64_t)__ldg(t.cell + s) - t.part_begin;
+    if (r < 0 || r >= a.n) return;                             // another rank's cell
     const float kx = a.kx.map ? __ldg(a.kx.map + r) : a.kx.value;
     const float omk = a.kx.map ? 1.0f - kx : a.one_m_kx;
+    const bool drift = t.trunk[s] != 0;
+    const int32_t l = __ldg(t.last + s);
     for (int c = 0; c < a.ncomp; ++c) {
-        double s = a.park_before[(int64_t)c * a.n_cross + k];                     // r .. end of this rank's range
-        for (int u = a.rank + 1; u < q; ++u) s += a.gathered[(int64_t)u * a.rank_pitch + (int64_t)c * a.stride];   // whole ranks in between
-        s += a.gathered[(int64_t)q * a.rank_pitch + (int64_t)c * a.stride + 1 + slot];        // start of rank q's range .. range end
+        const double *Gl = t.Gl + (int64_t)c * t.m, *BP = t.BP + (int64_t)c * t.nblk;
+        double D = 0.0;
+        if (drift) D = (BP[l / TRUNK_BLOCK] + Gl[l]) - (s > 0 ? BP[(s - 1) / TRUNK_BLOCK] + Gl[s - 1] : 0.0);
+        const float f = (float)((double)(float)t.E[(int64_t)c * t.m + s] + D);
         float *qs = a.qstate[c];
-        qs[r] = blend(a, r, (float)s, qs[r], kx, omk);
+        qs[r] = omk * f + kx * qs[r];                          // routing.py:28
     }
 }
 
@@ -340,6 +422,15 @@ __global__ void k_cross_flag(const int32_t *sub_size, int64_t n, uint8_t *flag)
 {
     int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (r < n) flag[r] = (r / SCAN_TILE) != ((r + sub_size[r] - 1) / SCAN_TILE);
+}
+
+// trunk cells are finished by k_trunk_drift / k_trunk_apply, not by k_scan_cross
+__global__ void k_cross_unflag_trunk(const int32_t *sl_cell, int32_t m, int64_t part_begin, int64_t n, uint8_t *flag)
+{
+    const int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= m) return;
+    const int64_t r = (int64_t)sl_cell[s] - part_begin;
+    if (r >= 0 && r < n) flag[r] = 0;
 }
 
 // sort keys of the "end" list: range ends of the crossing cells (INT32_MAX = ends on another rank: sorted last and
@@ -392,6 +483,8 @@ static int build_cross_lists(sphy_ctx *ctx, cudaStream_t st)
     int32_t nc = 0;
     if (e == cudaSuccess) {
         k_cross_flag<<<div_up(n, 256), 256, 0, st>>>(ctx->sub_size_loc, n, flag);
+        if (ctx->sl_plan && ctx->sl_n > 0)
+            k_cross_unflag_trunk<<<div_up(ctx->sl_n, 256), 256, 0, st>>>(ctx->sl_cell, ctx->sl_n, ctx->part_begin, n, flag);
         cub::CountingInputIterator<int32_t> counting(0);
         FK(cub::DeviceSelect::Flagged(nullptr, tb, counting, flag, sel, nsel, (int)n, st));
         FK(cudaMalloc(&tmp, tb));
@@ -487,11 +580,7 @@ static int scan_prepare(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm,
     a.tile_tot = ctx->scan_tile;
     a.tile_excl = ctx->scan_excl;
     a.n_pub = ctx->n_pub;
-    a.n_remote = ctx->n_remote;
     a.pub_e = ctx->pub_e;
-    a.remote_k = ctx->remote_k;
-    a.remote_rank = ctx->remote_rank;
-    a.remote_slot = ctx->remote_slot;
     a.kx = kx;
     a.one_m_kx = one_m_kx;
     a.to_m3s = (0.001 * (double)ctx->cellarea) / 86400.0;
@@ -501,6 +590,15 @@ static int scan_prepare(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm,
 }
 
 // main pass -> exclusive scan of the tile totals (cub, one call per component) -> crossing cells
+static void prof_mark(sphy_ctx *ctx, cudaStream_t st)
+{
+    if (!ctx->prof_on || ctx->prof_ev.size() >= 4 * 4096) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    ctx->prof_ev.push_back(e);
+}
+
 static int scan_launch_local(sphy_ctx *ctx, ScanArgs &a, cudaStream_t st)
 {
     const int resident = ctx->sm_count * SCAN_MIN_CTAS;
@@ -513,6 +611,7 @@ static int scan_launch_local(sphy_ctx *ctx, ScanArgs &a, cudaStream_t st)
         SPHY_CUDA(ctx, cudaFuncSetAttribute(k_scan_main<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM));
         ctx->scan_smem_opt_in = true;
     }
+    prof_mark(ctx, st);
     if (a.adv) {
         if (a.kx.map) k_scan_main<true, true><<<grid, SCAN_THREADS, SCAN_SMEM, st>>>(a);
         else k_scan_main<true, false><<<grid, SCAN_THREADS, SCAN_SMEM, st>>>(a);
@@ -520,12 +619,59 @@ static int scan_launch_local(sphy_ctx *ctx, ScanArgs &a, cudaStream_t st)
         if (a.kx.map) k_scan_main<false, true><<<grid, SCAN_THREADS, SCAN_SMEM, st>>>(a);
         else k_scan_main<false, false><<<grid, SCAN_THREADS, SCAN_SMEM, st>>>(a);
     }
+    prof_mark(ctx, st);
     for (int c = 0; c < a.ncomp; ++c) {
         size_t need = ctx->scan_tmp_bytes;
         SPHY_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->scan_tmp, need, ctx->scan_tile + (size_t)c * (ctx->n_tiles + 1),
                                                      ctx->scan_excl + (size_t)c * (ctx->n_tiles + 1), ctx->n_tiles + 1, st));
     }
     if (ctx->n_cross > 0) k_scan_cross<<<div_up(ctx->n_cross, 256 * CROSS_ILP), 256, 0, st>>>(a);
+    prof_mark(ctx, st);
+    return SPHY_OK;
+}
+
+// workspaces of the trunk kernels for `ncomp` routed components
+static int trunk_prepare(sphy_ctx *ctx, int ncomp, cudaStream_t st)
+{
+    if (ctx->sl_comp_cap >= ncomp) return SPHY_OK;
+    int rc;
+    const size_t m = ctx->sl_n > 0 ? (size_t)ctx->sl_n : 1, nb = ctx->sl_nblk > 0 ? (size_t)ctx->sl_nblk : 1;
+    if ((rc = dev_alloc(ctx, &ctx->sl_E, ncomp * m)) || (rc = dev_alloc(ctx, &ctx->sl_Gl, ncomp * m)) ||
+        (rc = dev_alloc(ctx, &ctx->sl_BS, ncomp * nb)) || (rc = dev_alloc(ctx, &ctx->sl_BP, ncomp * nb)) ||
+        (rc = dev_alloc(ctx, &ctx->sl_V, (size_t)ncomp * ctx->sl_stride)) || (rc = dev_alloc_once(ctx, &ctx->sl_counter, 1)))
+        return rc;
+    SPHY_CUDA(ctx, cudaMemsetAsync(ctx->sl_counter, 0, sizeof(unsigned), st));
+    ctx->sl_comp_cap = ncomp;
+    return SPHY_OK;
+}
+
+// finish the trunk cells of this context from the published blocks of all ranks
+static int trunk_finish(sphy_ctx *ctx, const ScanArgs &a, const double *gathered, int64_t rank_pitch, cudaStream_t st)
+{
+    if (ctx->sl_n == 0) return SPHY_OK;
+    TrunkArgs t = {};
+    t.m = ctx->sl_n;
+    t.nblk = ctx->sl_nblk;
+    t.cell = ctx->sl_cell;
+    t.last = ctx->sl_last;
+    t.tdon = ctx->sl_tdon;
+    t.trunk = ctx->sl_trunk;
+    t.brank = ctx->sl_brank;
+    t.bslot = ctx->sl_bslot;
+    t.erank = ctx->sl_erank;
+    t.eslot = ctx->sl_eslot;
+    t.E = ctx->sl_E;
+    t.Gl = ctx->sl_Gl;
+    t.BS = ctx->sl_BS;
+    t.BP = ctx->sl_BP;
+    t.counter = ctx->sl_counter;
+    t.gathered = gathered;
+    t.rank_pitch = rank_pitch;
+    t.part_begin = ctx->part_begin;
+    t.stride = ctx->sl_stride;
+    t.world = ctx->sl_world;
+    k_trunk_drift<<<ctx->sl_nblk, TRUNK_BLOCK, 0, st>>>(a, t);
+    k_trunk_apply<<<div_up(ctx->sl_n, 256), 256, 0, st>>>(a, t);
     return SPHY_OK;
 }
 
@@ -535,8 +681,18 @@ int route_scan_run(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm, floa
     ScanArgs a;
     int rc = scan_prepare(ctx, ncomp, runoff_mm, q_state, kx, one_m_kx, st, a);
     if (rc != SPHY_OK) return rc;
+    if (ctx->sl_plan && (rc = trunk_prepare(ctx, ncomp, st)) != SPHY_OK) return rc;
+    if (ctx->sl_plan) {
+        a.send = ctx->sl_V;
+        a.stride = ctx->sl_stride;
+    }
     int rc2 = scan_launch_local(ctx, a, st);
     if (rc2 != SPHY_OK) return rc2;
+    if (ctx->sl_plan && ctx->sl_n > 0) {
+        k_scan_publish<<<div_up(ctx->n_pub > 0 ? ctx->n_pub : 1, 256), 256, 0, st>>>(a);
+        if ((rc = trunk_finish(ctx, a, ctx->sl_V, (int64_t)ncomp * ctx->sl_stride, st)) != SPHY_OK) return rc;
+    }
+    prof_mark(ctx, st);
     SPHY_LAUNCH_CHECK(ctx);
     return SPHY_OK;
 }
@@ -579,6 +735,8 @@ int route_scan_run_adv(sphy_ctx *ctx, float *material_m3day, float *q_state, sph
                        const float *qout_dense, float *qday, int n_cut, const int32_t *cut_cell_dev, double *cut_work, cudaStream_t st)
 {
     if (ctx->partitioned) SPHY_FAIL(ctx, SPHY_E_STATE, "lake/reservoir routing is not available on a partitioned context");
+    if (ctx->sl_plan && ctx->sl_n > 0)
+        SPHY_FAIL(ctx, SPHY_E_STATE, "lake/reservoir routing on the scan path does not take a trunk plan (sphy_trunk_set_plan)");
     ScanArgs a;
     const float *mm[1] = {material_m3day};
     float *qq[1] = {q_state};
@@ -603,40 +761,237 @@ int route_scan_run_adv(sphy_ctx *ctx, float *material_m3day, float *q_state, sph
     return SPHY_OK;
 }
 
+// ---- per-phase timing ------------------------------------------------------------------------------------------------
+extern "C" int sphy_route_profile(sphy_ctx *ctx, int enable)
+{
+    if (!ctx) return SPHY_E_INVALID;
+    for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
+    ctx->prof_ev.clear();
+    ctx->prof_on = enable != 0;
+    return SPHY_OK;
+}
+
+// mean milliseconds per step of: the main pass, tile totals + crossing cells (+ publish), everything after that up to the
+// end of the trunk kernels (on a partitioned context this includes the exchange), and the whole routing call(s)
+extern "C" int sphy_route_profile_read(sphy_ctx *ctx, float *ms4, int *steps)
+{
+    if (!ctx || !ms4 || !steps) return SPHY_E_INVALID;
+    const size_t k = ctx->prof_ev.size() / 4;
+    *steps = (int)k;
+    ms4[0] = ms4[1] = ms4[2] = ms4[3] = 0.0f;
+    if (k == 0) return SPHY_OK;
+    SPHY_CUDA(ctx, cudaEventSynchronize(ctx->prof_ev[4 * k - 1]));
+    double acc[4] = {0, 0, 0, 0};
+    for (size_t i = 0; i < k; ++i) {
+        float t = 0.0f;
+        for (int j = 0; j < 3; ++j) {
+            SPHY_CUDA(ctx, cudaEventElapsedTime(&t, ctx->prof_ev[4 * i + j], ctx->prof_ev[4 * i + j + 1]));
+            acc[j] += t;
+        }
+        SPHY_CUDA(ctx, cudaEventElapsedTime(&t, ctx->prof_ev[4 * i], ctx->prof_ev[4 * i + 3]));
+        acc[3] += t;
+    }
+    for (int j = 0; j < 4; ++j) ms4[j] = (float)(acc[j] / (double)k);
+    for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
+    ctx->prof_ev.clear();
+    return SPHY_OK;
+}
+
 // ---- multi-GPU -------------------------------------------------------------------------------------------------
 extern "C" int sphy_scan_tile_cells(void) { return SCAN_TILE; }
 
-extern "C" int sphy_set_partition(sphy_ctx *ctx, int64_t cell_begin, int64_t cell_end, int32_t n_pub, const int32_t *pub_e_dev,
-                                  int32_t n_remote, const int32_t *remote_k_dev, const int32_t *remote_rank_dev,
-                                  const int32_t *remote_slot_dev, void *stream)
+extern "C" int sphy_set_partition(sphy_ctx *ctx, int64_t cell_begin, int64_t cell_end, void *stream)
 {
     if (!ctx) return SPHY_E_INVALID;
     if (!ctx->ldd_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_set_partition before sphy_ldd_build");
     if (ctx->order_mode != SPHY_ORDER_DFS) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_set_partition needs SPHY_ORDER_DFS");
     if (ctx->partitioned) SPHY_FAIL(ctx, SPHY_E_STATE, "context is already partitioned");
-    if (cell_begin < 0 || cell_end > ctx->n_global || cell_begin >= cell_end || (cell_begin % SCAN_TILE) != 0 || n_pub < 0 ||
-        n_remote < 0 || (n_pub > 0 && !pub_e_dev) || (n_remote > 0 && (!remote_k_dev || !remote_rank_dev || !remote_slot_dev)))
-        SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_set_partition: bad range or lists (the range must start on a %d-cell tile)", SCAN_TILE);
-    cudaStream_t st = (cudaStream_t)stream;
-    int rc;
-    if ((rc = dev_alloc(ctx, &ctx->pub_e, (size_t)n_pub)) || (rc = dev_alloc(ctx, &ctx->remote_k, (size_t)n_remote)) ||
-        (rc = dev_alloc(ctx, &ctx->remote_rank, (size_t)n_remote)) || (rc = dev_alloc(ctx, &ctx->remote_slot, (size_t)n_remote)))
-        return rc;
-    if (n_pub) SPHY_CUDA(ctx, cudaMemcpyAsync(ctx->pub_e, pub_e_dev, sizeof(int32_t) * n_pub, cudaMemcpyDeviceToDevice, st));
-    if (n_remote) {
-        SPHY_CUDA(ctx, cudaMemcpyAsync(ctx->remote_k, remote_k_dev, sizeof(int32_t) * n_remote, cudaMemcpyDeviceToDevice, st));
-        SPHY_CUDA(ctx, cudaMemcpyAsync(ctx->remote_rank, remote_rank_dev, sizeof(int32_t) * n_remote, cudaMemcpyDeviceToDevice, st));
-        SPHY_CUDA(ctx, cudaMemcpyAsync(ctx->remote_slot, remote_slot_dev, sizeof(int32_t) * n_remote, cudaMemcpyDeviceToDevice, st));
-    }
-    SPHY_CUDA(ctx, cudaStreamSynchronize(st));
-    ctx->n_pub = n_pub;
-    ctx->n_remote = n_remote;
+    if (cell_begin < 0 || cell_end > ctx->n_global || cell_begin >= cell_end || (cell_begin % SCAN_TILE) != 0)
+        SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_set_partition: bad range (it must start on a %d-cell tile)", SCAN_TILE);
+    (void)stream;
     ctx->part_begin = cell_begin;
     ctx->n = cell_end - cell_begin;
     ctx->sub_size_loc = ctx->sub_size + cell_begin;
     ctx->flat_loc = ctx->flat_active + cell_begin;
     ctx->partitioned = true;
     ctx->scan_ready = false;
+    ctx->scan_comp_cap = 0;
+    ctx->sl_plan = false;
+    return SPHY_OK;
+}
+
+// ---- trunk list ------------------------------------------------------------------------------------------------------
+namespace {
+
+struct RankBounds { int32_t world; int64_t b[65]; };
+
+__device__ __forceinline__ int rank_of(const RankBounds &rb, int64_t j)
+{
+    int q = 0;
+    while (q + 1 < rb.world && j >= rb.b[q + 1]) ++q;
+    return q;
+}
+
+// 0: ordinary cell, 1: listed because its upstream range leaves its rank, 2: trunk (carries the rounding drift)
+__global__ void k_trunk_flag(const int32_t *__restrict__ sub_size, const int32_t *__restrict__ level, const int32_t *__restrict__ cell_canon,
+                             int64_t n, int32_t min_level, int64_t min_cells, const __grid_constant__ RankBounds rb, uint8_t *flag)
+{
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int32_t sz = sub_size[j];
+    uint8_t f = 0;
+    if (sz >= min_cells || level[cell_canon[j]] >= min_level) f = 2;
+    else if (rb.world > 1 && rank_of(rb, j) != rank_of(rb, j + sz - 1)) f = 1;
+    flag[j] = f;
+}
+
+__device__ __forceinline__ int32_t lower_bound_i32(const int32_t *a, int32_t n, int64_t key)
+{
+    int32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const int32_t mid = (lo + hi) >> 1;
+        if (a[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void k_trunk_entries(const int32_t *__restrict__ sl_cell, int32_t m, const int32_t *__restrict__ sub_size,
+                                const uint8_t *__restrict__ flag, const int32_t *__restrict__ don_ptr, const int32_t *__restrict__ don_idx,
+                                int32_t *sl_sub, int32_t *sl_last, uint8_t *sl_trunk, int32_t *sl_tdon)
+{
+    const int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= m) return;
+    const int32_t j = sl_cell[s];
+    const int32_t sz = sub_size[j];
+    sl_sub[s] = sz;
+    sl_trunk[s] = flag[j] == 2;
+    sl_last[s] = lower_bound_i32(sl_cell, m, (int64_t)j + sz) - 1;        // last listed cell inside the upstream range (>= s)
+    int k = 0;
+    if (flag[j] == 2)
+        for (int32_t q = don_ptr[j]; q < don_ptr[j + 1]; ++q) {
+            const int32_t d = don_idx[q];
+            if (flag[d] == 2 && k < 8) sl_tdon[(int64_t)s * 8 + k++] = lower_bound_i32(sl_cell, m, d);
+        }
+    for (; k < 8; ++k) sl_tdon[(int64_t)s * 8 + k] = -1;
+}
+
+}  // namespace
+
+extern "C" int sphy_trunk_select(sphy_ctx *ctx, int32_t min_level, int64_t min_cells, int world, const int64_t *bounds_host,
+                                 int64_t *count_out, void *stream)
+{
+    if (!ctx || !count_out || world < 1 || world > 64 || (world > 1 && !bounds_host)) return SPHY_E_INVALID;
+    if (!ctx->ldd_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_trunk_select before sphy_ldd_build");
+    if (ctx->order_mode != SPHY_ORDER_DFS) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_trunk_select needs SPHY_ORDER_DFS");
+    // a trunk cell must leave its scan tile (the main pass skips exactly those cells): sub_size > SCAN_TILE
+    if (min_level < SCAN_TILE || min_cells <= SCAN_TILE)
+        SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_trunk_select: thresholds must exceed the %d-cell scan tile", SCAN_TILE);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = ctx->n_global;
+    RankBounds rb = {};
+    rb.world = world;
+    for (int q = 0; q <= world; ++q) rb.b[q] = world > 1 ? bounds_host[q] : (q == 0 ? 0 : n);
+    if (world > 1) {
+        if (rb.b[0] != 0 || rb.b[world] != n) SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_trunk_select: bounds must cover [0, %lld)", (long long)n);
+        for (int q = 0; q < world; ++q)
+            if (rb.b[q] >= rb.b[q + 1] || rb.b[q] % SCAN_TILE) SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_trunk_select: bounds must ascend on tile starts");
+    }
+    uint8_t *flag = nullptr;
+    int32_t *sel = nullptr, *nsel = nullptr;
+    void *tmp = nullptr;
+    size_t tb = 0;
+    int32_t m = 0;
+    cudaError_t e = cudaSuccess;
+#define FK(call) do { if (e == cudaSuccess) e = (call); } while (0)
+    FK(cudaMalloc(&flag, (size_t)n));
+    FK(cudaMalloc(&sel, sizeof(int32_t) * n));
+    FK(cudaMalloc(&nsel, sizeof(int32_t)));
+    if (e == cudaSuccess) {
+        k_trunk_flag<<<div_up(n, 256), 256, 0, st>>>(ctx->sub_size, ctx->level, ctx->cell_canon, n, min_level, min_cells, rb, flag);
+        cub::CountingInputIterator<int32_t> counting(0);
+        FK(cub::DeviceSelect::Flagged(nullptr, tb, counting, flag, sel, nsel, (int)n, st));
+        FK(cudaMalloc(&tmp, tb));
+        FK(cub::DeviceSelect::Flagged(tmp, tb, counting, flag, sel, nsel, (int)n, st));
+        FK(cudaMemcpyAsync(&m, nsel, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        FK(cudaStreamSynchronize(st));
+    }
+    int rc = SPHY_OK;
+    if (e == cudaSuccess) {
+        const size_t ms = m > 0 ? (size_t)m : 1;
+        if ((rc = dev_alloc(ctx, &ctx->sl_cell, ms)) || (rc = dev_alloc(ctx, &ctx->sl_sub, ms)) || (rc = dev_alloc(ctx, &ctx->sl_last, ms)) ||
+            (rc = dev_alloc(ctx, &ctx->sl_trunk, ms)) || (rc = dev_alloc(ctx, &ctx->sl_tdon, ms * 8))) {
+            cudaFree(flag); cudaFree(sel); cudaFree(nsel); cudaFree(tmp);
+            return rc;
+        }
+        if (m > 0) {
+            FK(cudaMemcpyAsync(ctx->sl_cell, sel, sizeof(int32_t) * m, cudaMemcpyDeviceToDevice, st));
+            if (e == cudaSuccess)
+                k_trunk_entries<<<div_up(m, 256), 256, 0, st>>>(ctx->sl_cell, m, ctx->sub_size, flag, ctx->don_ptr, ctx->don_idx,
+                                                               ctx->sl_sub, ctx->sl_last, ctx->sl_trunk, ctx->sl_tdon);
+            FK(cudaGetLastError());
+            FK(cudaStreamSynchronize(st));
+        }
+    }
+#undef FK
+    cudaFree(flag); cudaFree(sel); cudaFree(nsel); cudaFree(tmp);
+    if (e != cudaSuccess) SPHY_FAIL(ctx, SPHY_E_CUDA, "sphy_trunk_select: %s", cudaGetErrorString(e));
+    ctx->sl_n = m;
+    ctx->sl_nblk = div_up(m, TRUNK_BLOCK);
+    ctx->sl_plan = false;
+    ctx->sl_comp_cap = 0;
+    *count_out = m;
+    return SPHY_OK;
+}
+
+extern "C" int sphy_trunk_export(sphy_ctx *ctx, const char *name, void *dst, size_t dst_bytes, void *stream)
+{
+    if (!ctx || !name || !dst) return SPHY_E_INVALID;
+    const std::string k(name);
+    const void *src = nullptr;
+    size_t bytes = 0;
+    const size_t m = (size_t)ctx->sl_n;
+    if (k == "cell") { src = ctx->sl_cell; bytes = 4 * m; }
+    else if (k == "sub_size") { src = ctx->sl_sub; bytes = 4 * m; }
+    else if (k == "last") { src = ctx->sl_last; bytes = 4 * m; }
+    else if (k == "donors") { src = ctx->sl_tdon; bytes = 32 * m; }
+    else if (k == "is_trunk") { src = ctx->sl_trunk; bytes = m; }
+    else SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_trunk_export: unknown array '%s'", name);
+    if (dst_bytes < bytes) SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_trunk_export(%s): need %zu bytes, got %zu", name, bytes, dst_bytes);
+    if (bytes) SPHY_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return SPHY_OK;
+}
+
+extern "C" int sphy_trunk_set_plan(sphy_ctx *ctx, int32_t n_pub, const int32_t *pub_pos_dev, const int32_t *before_rank_dev,
+                                   const int32_t *before_slot_dev, const int32_t *end_rank_dev, const int32_t *end_slot_dev,
+                                   int32_t stride, int rank, int world, void *stream)
+{
+    if (!ctx || n_pub < 0 || (n_pub > 0 && !pub_pos_dev) || stride < 1 + n_pub || rank < 0 || rank >= world || world > 64)
+        return SPHY_E_INVALID;
+    const int32_t m = ctx->sl_n;
+    if (m > 0 && (!before_rank_dev || !before_slot_dev || !end_rank_dev || !end_slot_dev)) return SPHY_E_INVALID;
+    if (!ctx->ldd_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_trunk_set_plan before sphy_ldd_build");
+    if ((world > 1) != ctx->partitioned) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_trunk_set_plan: world %d on a%s context", world, ctx->partitioned ? " partitioned" : "n unpartitioned");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    const size_t ms = m > 0 ? (size_t)m : 1;
+    if ((rc = dev_alloc(ctx, &ctx->pub_e, (size_t)n_pub)) || (rc = dev_alloc(ctx, &ctx->sl_brank, ms)) || (rc = dev_alloc(ctx, &ctx->sl_bslot, ms)) ||
+        (rc = dev_alloc(ctx, &ctx->sl_erank, ms)) || (rc = dev_alloc(ctx, &ctx->sl_eslot, ms)))
+        return rc;
+    if (n_pub) SPHY_CUDA(ctx, cudaMemcpyAsync(ctx->pub_e, pub_pos_dev, sizeof(int32_t) * n_pub, cudaMemcpyDeviceToDevice, st));
+    if (m > 0) {
+        SPHY_CUDA(ctx, cudaMemcpyAsync(ctx->sl_brank, before_rank_dev, sizeof(int32_t) * m, cudaMemcpyDeviceToDevice, st));
+        SPHY_CUDA(ctx, cudaMemcpyAsync(ctx->sl_bslot, before_slot_dev, sizeof(int32_t) * m, cudaMemcpyDeviceToDevice, st));
+        SPHY_CUDA(ctx, cudaMemcpyAsync(ctx->sl_erank, end_rank_dev, sizeof(int32_t) * m, cudaMemcpyDeviceToDevice, st));
+        SPHY_CUDA(ctx, cudaMemcpyAsync(ctx->sl_eslot, end_slot_dev, sizeof(int32_t) * m, cudaMemcpyDeviceToDevice, st));
+    }
+    SPHY_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->n_pub = n_pub;
+    ctx->sl_stride = stride;
+    ctx->sl_rank = rank;
+    ctx->sl_world = world;
+    ctx->sl_plan = true;
+    ctx->sl_comp_cap = 0;
+    ctx->scan_ready = false;                      // the tile-crossing list is rebuilt without the trunk cells
     ctx->scan_comp_cap = 0;
     return SPHY_OK;
 }
@@ -646,11 +1001,13 @@ extern "C" int sphy_route_scan_begin(sphy_ctx *ctx, int ncomp, const float *cons
 {
     if (!ctx || !runoff_mm || !q_state || !send_dev || ncomp < 1 || ncomp > ROUTE_MAX_COMP) return SPHY_E_INVALID;
     if (!ctx->ldd_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_route_scan_begin before sphy_ldd_build");
-    if (stride < 1 + ctx->n_pub) SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_route_scan_begin: stride %d < 1 + n_pub %d", stride, ctx->n_pub);
+    if (!ctx->sl_plan) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_route_scan_begin before sphy_trunk_set_plan");
+    if (stride != ctx->sl_stride) SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_route_scan_begin: stride %d != planned %d", stride, ctx->sl_stride);
     cudaStream_t st = (cudaStream_t)stream;
     ScanArgs a;
     int rc = scan_prepare(ctx, ncomp, runoff_mm, q_state, kx, one_minus_kx, st, a);
     if (rc != SPHY_OK) return rc;
+    if ((rc = trunk_prepare(ctx, ncomp, st)) != SPHY_OK) return rc;
     a.send = send_dev;
     a.stride = stride;
     rc = scan_launch_local(ctx, a, st);
@@ -665,24 +1022,23 @@ extern "C" int sphy_route_scan_finish(sphy_ctx *ctx, int ncomp, float *const *q_
 {
     if (!ctx || !q_state || ncomp < 1 || ncomp > ROUTE_MAX_COMP || rank < 0 || rank >= world) return SPHY_E_INVALID;
     if (!gathered_dev && !ctx->p2p_recv) SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_route_scan_finish: no gathered buffer and no peer exchange set up");
-    if (!ctx->scan_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_route_scan_finish before sphy_route_scan_begin");
-    if (ctx->n_remote == 0) return SPHY_OK;
+    if (!ctx->scan_ready || !ctx->sl_plan) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_route_scan_finish before sphy_route_scan_begin");
+    if (stride != ctx->sl_stride || rank != ctx->sl_rank || world != ctx->sl_world)
+        SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_route_scan_finish: stride/rank/world differ from the plan");
+    if (ctx->sl_n == 0) return SPHY_OK;
     cudaStream_t st = (cudaStream_t)stream;
     ScanArgs a;
     int rc = scan_prepare(ctx, ncomp, nullptr, q_state, kx, one_minus_kx, st, a);
     if (rc != SPHY_OK) return rc;
-    if (gathered_dev) {
-        a.gathered = gathered_dev;
-        a.rank_pitch = (int64_t)ncomp * stride;
-    } else {                                      // what the peers stored into this rank's buffer (sphy_route_scan_exchange_p2p)
+    const double *gathered = gathered_dev;
+    int64_t pitch = (int64_t)ncomp * stride;
+    if (!gathered) {                              // what the peers stored into this rank's buffer (sphy_route_scan_exchange_p2p)
         const int parity = (int)((ctx->p2p_step - 1) & 1);
-        a.gathered = ctx->p2p_recv + (size_t)parity * ctx->p2p_world * ctx->p2p_pitch;
-        a.rank_pitch = ctx->p2p_pitch;
+        gathered = ctx->p2p_recv + (size_t)parity * ctx->p2p_world * ctx->p2p_pitch;
+        pitch = ctx->p2p_pitch;
     }
-    a.stride = stride;
-    a.rank = rank;
-    a.world = world;
-    k_scan_remote<<<div_up(ctx->n_remote, 256), 256, 0, st>>>(a);
+    if ((rc = trunk_finish(ctx, a, gathered, pitch, st)) != SPHY_OK) return rc;
+    prof_mark(ctx, st);
     SPHY_LAUNCH_CHECK(ctx);
     return SPHY_OK;
 }

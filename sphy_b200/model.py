@@ -122,7 +122,7 @@ def _table_col(rows, col):
 class SphyModel:
     def __init__(self, cfg, maps: MapSource, device="cuda:0", route_method="scan", diagnostics=False,
                  collect_tss=True, cell_order="dfs", rank=0, world=1, share_from=None, reporting=False, write_outputs=False,
-                 ra_mode="auto"):
+                 ra_mode="auto", scan_drift=True):
         if not torch.cuda.is_available():
             raise RuntimeError("SphyModel needs a CUDA device (B200); there is no CPU fallback")
         self.lib = _lib.load()
@@ -137,6 +137,7 @@ class SphyModel:
         self.cell_order_mode = {"rowmajor": _lib.ORDER_ROWMAJOR, "dfs": _lib.ORDER_DFS}[cell_order]
         if self.route_method == _lib.ROUTE_SCAN and self.cell_order_mode != _lib.ORDER_DFS:
             raise ValueError("route_method='scan' needs cell_order='dfs'")
+        self.scan_drift = bool(scan_drift)   # scan routing: carry the reference's REAL4 rounding drift on the trunk cells
         self.ra_mode = ra_mode           # auto | table (latitude classes) | cell (per-cell sin/cos/tan maps)
         self.rank, self.world = int(rank), int(world)
         if self.world > 1 and (self.route_method != _lib.ROUTE_SCAN):
@@ -240,7 +241,7 @@ class SphyModel:
             o = self._share_from
             for k in ("n", "n_global", "nlevels", "flat_active", "cell_order", "full_raster", "_cidx_host"):
                 setattr(self, k, getattr(o, k))
-            for k in ("part_range", "_mg_stride", "_mg_plan"):
+            for k in ("part_range", "_mg_stride", "trunk_cells"):
                 if hasattr(o, k):
                     setattr(self, k, getattr(o, k))
             return
@@ -262,8 +263,8 @@ class SphyModel:
                      "sphy_ldd_export")
             self.cell_order = flat.cpu().numpy().astype(np.int64)       # device cell index -> canonical compact index
             self.n_global = self.n
-            if self.world > 1:
-                self._partition(flat)
+            if self.route_method == _lib.ROUTE_SCAN:
+                self._install_trunk()
         else:
             self.flat_active = np.flatnonzero(self.clone_mask.ravel())
             self.cell_order = np.arange(self.flat_active.size)
@@ -278,28 +279,51 @@ class SphyModel:
         self._cidx_host = np.full(self.nrows * self.ncols, -1, np.int64)
         self._cidx_host[self.flat_active] = np.arange(self.n)
 
-    def _partition(self, scratch):
-        """Restrict this rank to its contiguous DFS-order range (sphy_b200/multigpu.py plans the exchange lists)."""
+    def _install_trunk(self):
+        """Scan routing: list the trunk cells (sphy_trunk_select), restrict a multi-GPU rank to its contiguous DFS-order
+        range, and install the exchange plan (sphy_b200/multigpu.py: plan_trunk).  On one GPU the trunk only carries the
+        reference's REAL4 rounding drift; on a partitioned basin it is also what crosses the rank boundaries."""
         from . import multigpu
-        if self.ResFLAG == 1 or self.LakeFLAG == 1:
+        adv = self.ResFLAG == 1 or self.LakeFLAG == 1
+        if self.world > 1 and adv:
             raise NotImplementedError("lakes/reservoirs are not supported on a partitioned basin yet")
-        self._ck(self.lib.sphy_ldd_export(self._ctx, b"sub_size", scratch.data_ptr(), scratch.numel() * 4, self._stream()),
-                 "sphy_ldd_export")
-        sub_size = scratch.cpu().numpy()
-        bounds, ranks, stride = multigpu.plan(sub_size, self.world)
-        me = ranks[self.rank]
-        lo, hi = int(bounds[self.rank]), int(bounds[self.rank + 1])
-        d = {k: self._dev(np.ascontiguousarray(me[k], np.int32)) for k in ("pub_e", "remote_k", "remote_rank", "remote_slot")}
+        self.trunk_cells = 0
+        if adv or (self.world == 1 and not self.scan_drift):
+            return                                   # accufractionflux cuts / plain float64 range sums
+        big = 2 ** 31 - 1
+        min_level = int(os.environ.get("SPHY_TRUNK_MIN_LEVEL", multigpu.TRUNK_MIN_LEVEL)) if self.scan_drift else big
+        min_cells = int(os.environ.get("SPHY_TRUNK_MIN_CELLS", multigpu.TRUNK_MIN_CELLS)) if self.scan_drift else 2 ** 40
+        bounds = multigpu.partition_bounds(self.n, self.world) if self.world > 1 else np.array([0, self.n], np.int64)
+        barr = (C.c_int64 * len(bounds))(*[int(b) for b in bounds])
+        m = C.c_int64(0)
+        self._ck(self.lib.sphy_trunk_select(self._ctx, min_level, min_cells, self.world, barr, C.byref(m), self._stream()),
+                 "sphy_trunk_select")
+        m = int(m.value)
+        self.trunk_cells = m
+
+        def export(name, dtype, per=1):
+            t = torch.empty(max(m * per, 1), dtype=dtype, device=self.device)
+            self._ck(self.lib.sphy_trunk_export(self._ctx, name.encode(), t.data_ptr(), t.numel() * t.element_size(), self._stream()),
+                     "sphy_trunk_export")
+            return t[:m * per].cpu().numpy()
+
+        if self.world > 1:
+            lo, hi = int(bounds[self.rank]), int(bounds[self.rank + 1])
+            self._ck(self.lib.sphy_set_partition(self._ctx, lo, hi, self._stream()), "sphy_set_partition")
+            self.part_range = (lo, hi)
+            self.flat_active = self.flat_active[lo:hi]
+            self.cell_order = self.cell_order[lo:hi]
+            self.n = hi - lo
+        elif m == 0:
+            return
+        plan = multigpu.plan_trunk(export("cell", torch.int32), export("sub_size", torch.int32), bounds)
+        d = {k: self._dev(np.ascontiguousarray(plan[k], np.int32)) for k in ("before_rank", "before_slot", "end_rank", "end_slot")}
+        pub = self._dev(np.ascontiguousarray(plan["pub"][self.rank], np.int32))
         ptr = lambda t: t.data_ptr() if t.numel() else None  # noqa: E731
-        self._ck(self.lib.sphy_set_partition(self._ctx, lo, hi, len(me["pub_e"]), ptr(d["pub_e"]), len(me["remote_k"]),
-                                             ptr(d["remote_k"]), ptr(d["remote_rank"]), ptr(d["remote_slot"]), self._stream()),
-                 "sphy_set_partition")
-        self.part_range = (lo, hi)
-        self.flat_active = self.flat_active[lo:hi]
-        self.cell_order = self.cell_order[lo:hi]
-        self.n = hi - lo
-        self._mg_stride = int(stride)
-        self._mg_plan = me
+        self._ck(self.lib.sphy_trunk_set_plan(self._ctx, int(pub.numel()), ptr(pub), ptr(d["before_rank"]), ptr(d["before_slot"]),
+                                              ptr(d["end_rank"]), ptr(d["end_slot"]), int(plan["stride"]), self.rank, self.world,
+                                              self._stream()), "sphy_trunk_set_plan")
+        self._mg_stride = int(plan["stride"])
 
     def ldd_structure(self, name):
         """Device copy of one Appendix-C structure (bit-exact parity checks)."""

@@ -35,52 +35,52 @@ def partition_bounds(n, world, tile=TILE):
     return b
 
 
-def plan(sub_size, world, tile=TILE):
-    """Exchange plan for every rank from the global `sub_size` (upstream cell count by device index, DFS order).
+# default thresholds of the trunk list (sphy_trunk_select): every cell with at least this many upstream levels / cells
+# carries the reference's REAL4 rounding drift.  Both must exceed the scan tile.
+TRUNK_MIN_LEVEL = 1024
+TRUNK_MIN_CELLS = 1 << 18
 
-    Returns (bounds, ranks) where ranks[p] is a dict with
-      pub_e        int32  local indices (ascending) whose range-local inclusive prefix rank p publishes
-      remote_k     int32  for each local cell whose range ends on another rank (ascending index): its slot in rank p's
-                          tile-crossing list (all local cells whose range leaves their tile, ascending)
-      remote_rank  int32  rank owning the end of that range
-      remote_slot  int32  slot of that end in the owner's pub_e
-      remote_r     int64  local index of those cells (for tests)
+
+def plan_trunk(cell, sub_size, bounds):
+    """Exchange plan of the trunk list (pure host logic over the small exported arrays).
+
+    cell      int  global device indices of the listed cells, ascending (sphy_trunk_export "cell")
+    sub_size  int  their upstream cell counts                          (sphy_trunk_export "sub_size")
+    bounds    int  world + 1 partition bounds (partition_bounds), [0, n] for one GPU
+
+    A listed cell j is finished from two global prefixes of the routed material: the one just before it (position
+    j - 1, none for j = 0) and the one at the end of its upstream range (position j + sub_size - 1).  Every rank
+    publishes the range-local prefix at the positions that fall into its range.  Returns a dict with
+      pub          list of int32 arrays: per rank the published positions as LOCAL indices, ascending and unique
+      before_rank  int32 [m]  rank publishing the prefix before entry s (-1: none)
+      before_slot  int32 [m]  its slot in that rank's `pub`
+      end_rank / end_slot     the same for the end of the upstream range
+      stride       1 + the longest `pub` (slot 0 of a rank's block carries the range total)
     """
-    sub_size = np.asarray(sub_size)
-    n = sub_size.size
-    b = partition_bounds(n, world, tile)
-    ranks = [dict() for _ in range(world)]
-    wanted = [[] for _ in range(world)]                 # global end indices requested from each owner
-    per_rank_remote = []
-    for p in range(world):
-        lo, hi = int(b[p]), int(b[p + 1])
-        size = sub_size[lo:hi].astype(np.int64)
-        r_loc = np.arange(hi - lo, dtype=np.int64)
-        e_glob = lo + r_loc + size - 1
-        leaves_tile = (r_loc // tile) != ((r_loc + size - 1) // tile)
-        cross_list = np.flatnonzero(leaves_tile)        # == the C side's list (ascending)
-        remote = np.flatnonzero(e_glob >= hi)
-        owner = np.searchsorted(b, e_glob[remote], side="right") - 1
-        per_rank_remote.append((remote, e_glob[remote], owner, cross_list))
-        for q in np.unique(owner):
-            wanted[int(q)].append(e_glob[remote][owner == q])
-    pub_global = []
-    for q in range(world):
-        ends = np.unique(np.concatenate(wanted[q])) if wanted[q] else np.zeros(0, np.int64)
-        pub_global.append(ends)
-        ranks[q]["pub_e"] = (ends - b[q]).astype(np.int32)
-    for p in range(world):
-        remote, e_glob, owner, cross_list = per_rank_remote[p]
-        slot = np.zeros(remote.size, np.int64)
-        for q in np.unique(owner):
-            sel = owner == q
-            slot[sel] = np.searchsorted(pub_global[int(q)], e_glob[sel])
-        ranks[p]["remote_r"] = remote
-        ranks[p]["remote_k"] = np.searchsorted(cross_list, remote).astype(np.int32)
-        ranks[p]["remote_rank"] = owner.astype(np.int32)
-        ranks[p]["remote_slot"] = slot.astype(np.int32)
-    stride = 1 + max(len(r["pub_e"]) for r in ranks)
-    return b, ranks, stride
+    cell = np.asarray(cell, np.int64)
+    sub_size = np.asarray(sub_size, np.int64)
+    bounds = np.asarray(bounds, np.int64)
+    world = bounds.size - 1
+    before, end = cell - 1, cell + sub_size - 1
+    has_b = before >= 0
+    pos = np.unique(np.concatenate([before[has_b], end]))
+    owner = np.searchsorted(bounds, pos, side="right") - 1
+    first = np.searchsorted(pos, bounds[:-1])                  # start of each rank's segment of `pos`
+    seg_end = np.append(first[1:], pos.size)
+    pub = [(pos[first[q]:seg_end[q]] - bounds[q]).astype(np.int32) for q in range(world)]
+
+    def locate(p):
+        idx = np.searchsorted(pos, p)
+        rk = owner[idx]
+        return rk.astype(np.int32), (idx - first[rk]).astype(np.int32)
+
+    er, es = locate(end) if cell.size else (np.zeros(0, np.int32), np.zeros(0, np.int32))
+    br = np.full(cell.size, -1, np.int32)
+    bs = np.zeros(cell.size, np.int32)
+    if has_b.any():
+        br[has_b], bs[has_b] = locate(before[has_b])
+    return dict(pub=pub, before_rank=br, before_slot=bs, end_rank=er, end_slot=es,
+                stride=1 + max(len(p) for p in pub))
 
 
 # ----------------------------------------------------------------------------------------------
@@ -130,7 +130,7 @@ def bench_main(args, rank, world):
     model.initial()
     n_local, n_global = model.n, model.n_global
     dem_dev = torch.from_numpy(model._compact_np(cat.dem)).to(dev)
-    ring = bench.device_forcing_ring(torch, dem_dev, args.ring, seed=1234 + rank)
+    ring = bench.device_forcing_ring(torch, dem_dev, args.ring, seed=1234, cell_begin=model.part_range[0])
     del dem_dev
     torch.cuda.synchronize()
     dist.barrier()
@@ -154,6 +154,7 @@ def bench_main(args, rank, world):
     for _ in range(max(args.warmup, 3)):
         model.dynamic()
     model.enable_profiling(True)
+    model.lib.sphy_route_profile(model._ctx, 1)
     sampler = bench.ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -163,6 +164,8 @@ def bench_main(args, rank, world):
     rt_ms = float(np.mean([a.elapsed_time(b) for a, b in model._prof["route"]]))
     model.enable_profiling(False)
     value = n_global * args.steps / (ms_total * 1e-3) / 1e6
+    check = bench.discharge_check(torch, model, dist)
+    rprof = bench.route_profile(model)
 
     # e2e: every rank copies its own cells' forcing from pinned host memory each step, reads its stations back
     host_ring = [{k: v.cpu().pin_memory() for k, v in day.items()} for day in ring[:2]]
@@ -196,12 +199,15 @@ def bench_main(args, rank, world):
                                     f"{model._mg_stride} float64 per rank (confluence inflows; "
                                     + ("stores into peer memory over NVLink + flags" if getattr(model, "_mg_p2p", False)
                                        else "NCCL all-gather") + ")",
-                       "routing": "scan", "forcing_ring_days": args.ring, "setup_s": round(setup_s, 1),
+                       "routing": "scan", "trunk_cells": model.trunk_cells, "forcing_ring_days": args.ring, "setup_s": round(setup_s, 1),
                        "host_affinity": f"rank 0 bound to the {numa_cpus} CPUs NVML lists next to its GPU" if numa_cpus else "unchanged",
                        "l2": "per-GPU per-step working set %.2f GB (larger than the 126 MB L2)" % (bench.ALG_BYTES_WB * n_local / 1e9)},
             "roofline": {"kernel": "k_wb_step (fused vertical water balance), rank 0", "bound": "hbm", "achieved": ach, "peak": peak,
                          "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                         "alg_bytes_per_cell": bench.ALG_BYTES_WB, "kernel_ms": wb_ms, "route_ms": rt_ms},
+                         "alg_bytes_per_cell": bench.ALG_BYTES_WB, "kernel_ms": wb_ms, "route_ms": rt_ms,
+                         "streamed_bytes_per_cell": bench.STREAM_BYTES_WB},
+            "roofline_route": bench.scan_roofline(rprof, n_local, 1, peak),
+            "check": check,
             "cpu_baseline": None,
             "e2e": {"value": e2e_val, "unit": "Mcell-timesteps/s", "h2d_bytes_per_step": 16 * n_global,
                     "d2h_bytes_per_step": d2h // e2e_steps, "steps": e2e_steps},

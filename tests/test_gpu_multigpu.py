@@ -26,9 +26,41 @@ def _export(lib, torch, ctx, name, n):
     return t.cpu().numpy().astype(np.int64)
 
 
-@pytest.mark.parametrize("world,shape,outlets,ncomp", [(2, (300, 260), "single", 1), (3, (420, 380), "single", 2),
-                                                       (4, (500, 610), "border", 2), (8, (640, 700), "single", 1)])
-def test_partitioned_scan_matches_single_context(world, shape, outlets, ncomp):
+def _trunk_arrays(lib, torch, ctx, m):
+    from sphy_b200 import _lib
+    out = {}
+    for name, dt, per in (("cell", torch.int32, 1), ("sub_size", torch.int32, 1), ("is_trunk", torch.uint8, 1), ("last", torch.int32, 1),
+                          ("donors", torch.int32, 8)):
+        t = torch.empty(max(m * per, 1), dtype=dt, device="cuda")
+        _lib.check(lib, ctx, lib.sphy_trunk_export(ctx, name.encode(), t.data_ptr(), t.numel() * t.element_size(), None), name)
+        torch.cuda.synchronize()
+        out[name] = t[:m * per].cpu().numpy()
+    return out
+
+
+def install_plan(lib, torch, ctx, bounds, rank, world, min_level, min_cells):
+    """sphy_trunk_select -> [sphy_set_partition] -> plan_trunk -> sphy_trunk_set_plan, as SphyModel._install_trunk does."""
+    from sphy_b200 import _lib, multigpu
+    barr = (C.c_int64 * len(bounds))(*[int(b) for b in bounds])
+    m = C.c_int64(0)
+    _lib.check(lib, ctx, lib.sphy_trunk_select(ctx, min_level, min_cells, world, barr, C.byref(m), None), "trunk_select")
+    m = int(m.value)
+    arr = _trunk_arrays(lib, torch, ctx, m)
+    if world > 1:
+        _lib.check(lib, ctx, lib.sphy_set_partition(ctx, int(bounds[rank]), int(bounds[rank + 1]), None), "set_partition")
+    plan = multigpu.plan_trunk(arr["cell"], arr["sub_size"], bounds)
+    d = {k: torch.from_numpy(np.ascontiguousarray(plan[k], np.int32)).cuda() for k in ("before_rank", "before_slot", "end_rank", "end_slot")}
+    pub = torch.from_numpy(np.ascontiguousarray(plan["pub"][rank], np.int32)).cuda()
+    ptr = lambda t: t.data_ptr() if t.numel() else None  # noqa: E731
+    _lib.check(lib, ctx, lib.sphy_trunk_set_plan(ctx, int(pub.numel()), ptr(pub), ptr(d["before_rank"]), ptr(d["before_slot"]),
+                                                 ptr(d["end_rank"]), ptr(d["end_slot"]), int(plan["stride"]), rank, world, None),
+               "trunk_set_plan")
+    return plan, arr
+
+
+@pytest.mark.parametrize("world,shape,outlets,ncomp,trunk", [(2, (300, 260), "single", 1, False), (3, (420, 380), "single", 2, True),
+                                                             (4, (500, 610), "border", 2, False), (8, (640, 700), "single", 1, True)])
+def test_partitioned_scan_matches_single_context(world, shape, outlets, ncomp, trunk):
     import torch
     from oracle.ldd_oracle import LddStruct
     from sphy_b200 import _lib, multigpu, synth
@@ -37,21 +69,21 @@ def test_partitioned_scan_matches_single_context(world, shape, outlets, ncomp):
     _, _, ldd, _ = synth.make_dem_ldd(shape[0], shape[1], cellsize, seed=world, outlets=outlets)
     st = LddStruct(ldd)
     n = st.n
+    min_level, min_cells = (1024, 1100) if trunk else (2 ** 31 - 1, 2 ** 40)      # with / without rounding-drift cells
     ref = _ctx(lib, torch, ldd, cellsize)
     canon = _export(lib, torch, ref, "cell_order", n)
-    sub_size = _export(lib, torch, ref, "sub_size", n)
-    bounds, ranks, stride = multigpu.plan(sub_size, world)
+    _, ref_arr = install_plan(lib, torch, ref, np.array([0, n]), 0, 1, min_level, min_cells)
+    assert (len(ref_arr["cell"]) > 0) == trunk
+    bounds = multigpu.partition_bounds(n, world)
     parts = []
+    stride = None
     for p in range(world):
         ctx = _ctx(lib, torch, ldd, cellsize)
-        me = ranks[p]
-        d = {k: torch.from_numpy(np.ascontiguousarray(me[k], np.int32)).cuda() for k in ("pub_e", "remote_k", "remote_rank", "remote_slot")}
-        ptr = lambda t: t.data_ptr() if t.numel() else None  # noqa: E731
-        _lib.check(lib, ctx, lib.sphy_set_partition(ctx, int(bounds[p]), int(bounds[p + 1]), len(me["pub_e"]), ptr(d["pub_e"]),
-                                                    len(me["remote_k"]), ptr(d["remote_k"]), ptr(d["remote_rank"]),
-                                                    ptr(d["remote_slot"]), None), "set_partition")
+        plan, arr = install_plan(lib, torch, ctx, bounds, p, world, min_level, min_cells)
+        stride = int(plan["stride"])
         assert lib.sphy_ncells(ctx) == bounds[p + 1] - bounds[p]
-        parts.append((ctx, d))
+        assert set(ref_arr["cell"][ref_arr["is_trunk"] != 0]) == set(arr["cell"][arr["is_trunk"] != 0])   # the same trunk at any split
+        parts.append((ctx, None))
     kx = _lib.SphyParam(None, 0.971)
     one_m = float(np.float32(1 - 0.971))
     rng = np.random.default_rng(world)
@@ -90,7 +122,8 @@ def test_partitioned_scan_matches_single_context(world, shape, outlets, ncomp):
             q64[c] = float(np.float32(one_m)) * st.accuflux_f64(rr) + float(np.float32(0.971)) * q64[c]
             want = q64[c][canon]
             assert np.all(np.abs(got - want) <= 2e-6 * np.abs(want) + 1e-12), f"step {step} comp {c}: partitioned vs float64 oracle"
-            assert np.all(np.abs(got - single) <= 1e-6 * np.abs(single) + 1e-12), f"step {step} comp {c}: partitioned vs single context"
+            # the split only shows through the float64 prefixes: a rare REAL4 ulp, never more (the drift sums are exact)
+            assert np.all(np.abs(got - single) <= 2.5e-7 * np.abs(single) + 1e-12), f"step {step} comp {c}: partitioned vs single context"
     # a partitioned context refuses the whole-basin entry points
     assert lib.sphy_upstream(parts[0][0], mm_dev[0].data_ptr(), q_ref[0].data_ptr(), None) == -4
     for ctx, _ in parts:

@@ -137,3 +137,52 @@ def test_scan_routing_dry_regions_are_exactly_zero():
     assert (got[want == 0] == 0).all()
     assert (np.abs(got - want) <= 1e-5 * want).all()
     lib.sphy_ctx_destroy(ctx)
+
+
+@pytest.mark.parametrize("uniform", [False, True])
+def test_trunk_drift_follows_the_real4_reference(uniform):
+    """With a trunk plan installed the scan path carries the reference's per-cell REAL4 rounding drift on the listed cells
+    (csrc/route_scan.cu: k_trunk_drift).  Spatially uniform runoff is the hard case: the reference's roundings are biased
+    and its accumulated flux drifts away from exact arithmetic, which plain float64 range sums cannot follow."""
+    import torch
+    from oracle.ldd_oracle import LddStruct
+    from sphy_b200 import _lib, synth
+    from tests.test_gpu_multigpu import install_plan
+    lib = _lib.load()
+    cellsize = 250.0
+    _, _, ldd, _ = synth.make_dem_ldd(1500, 1400, cellsize, seed=4, outlets="single")
+    st = LddStruct(ldd)
+    n = st.n
+    plain, trunk = _ctx(lib, torch, ldd, cellsize), _ctx(lib, torch, ldd, cellsize)
+    _, arr = install_plan(lib, torch, trunk, np.array([0, n]), 0, 1, 1024, 1100)
+    listed = arr["cell"][arr["is_trunk"] != 0].astype(np.int64)
+    assert listed.size > 1000
+    t = torch.empty(n, dtype=torch.int32, device="cuda")
+    _lib.check(lib, plain, lib.sphy_ldd_export(plain, b"cell_order", t.data_ptr(), n * 4, None), "cell_order")
+    torch.cuda.synchronize()
+    canon = t.cpu().numpy().astype(np.int64)
+    rng = np.random.default_rng(4)
+    mm = np.full(n, 3.3, np.float32) if uniform else (rng.gamma(0.8, 4.0, n) * (rng.random(n) < 0.7)).astype(np.float32)
+    mm_d = torch.from_numpy(mm[canon]).cuda()
+    want = st.accuflux((mm * np.float32(0.001) * (np.float32(cellsize) * np.float32(cellsize))) / np.float32(86400))[canon].astype(np.float64)
+    kx = _lib.SphyParam(None, 0.0)
+    err = {}
+    for name, ctx in (("plain", plain), ("trunk", trunk)):
+        q = torch.zeros(n, device="cuda")
+        src, dst = (C.c_void_p * 1)(mm_d.data_ptr()), (C.c_void_p * 1)(q.data_ptr())
+        _lib.check(lib, ctx, lib.sphy_route_step(ctx, 1, src, dst, kx, C.c_float(1.0), _lib.ROUTE_SCAN, None), "route")
+        torch.cuda.synchronize()
+        got = q.cpu().numpy().astype(np.float64)
+        err[name] = np.abs(got - want) / np.maximum(want, 1e-30)
+    print(f"uniform={uniform}: listed {listed.size}; on the listed cells plain {err['plain'][listed].max():.2e} -> trunk "
+          f"{err['trunk'][listed].max():.2e}; elsewhere {np.delete(err['trunk'], listed).max():.2e}")
+    rest = np.ones(n, bool)
+    rest[listed] = False
+    assert np.array_equal(err["plain"][rest], err["trunk"][rest])           # the ordinary cells are untouched
+    assert err["trunk"].max() <= 1e-5
+    # the listed cells inherit what their (uncorrected) tributaries deliver, but add nothing of their own
+    assert err["trunk"][listed].max() <= max(err["trunk"][rest].max(), 3e-7) * 1.05
+    if uniform:
+        assert err["trunk"][listed].max() < 0.7 * err["plain"][listed].max()
+    lib.sphy_ctx_destroy(plain)
+    lib.sphy_ctx_destroy(trunk)

@@ -1,6 +1,8 @@
-"""CPU: the host-side logic of the multi-GPU path -- partition planning (sphy_b200/multigpu.py) and the per-step
-confluence exchange -- with world_size 2 over gloo (and 1..5 ranks emulated in-process), against the oracle's
-float64 accuflux.  The kernels themselves are covered by tests/test_gpu_multigpu.py."""
+"""CPU: the host-side logic of the scan routing's trunk list and of the multi-GPU path -- partition bounds, the exchange
+plan (sphy_b200/multigpu.py: plan_trunk) and the per-step confluence exchange -- with world_size 2 over gloo (and 1..5
+ranks emulated in-process), against the oracle: float64 accuflux for the ordinary cells, and the REAL4-per-cell
+accuflux (oracle/ldd_oracle.c) for what the rounding-drift accumulation on the trunk cells has to reproduce.
+The kernels themselves are covered by tests/test_gpu_multigpu.py and tests/test_gpu_scan.py."""
 import os
 
 import numpy as np
@@ -8,20 +10,41 @@ import pytest
 
 from oracle.ldd_oracle import LddStruct
 from sphy_b200 import multigpu, synth
-from tests.mgpu_util import dfs_order, rank_begin, rank_finish
+from tests.mgpu_util import device_order_structures, dfs_order, rank_begin, trunk_finish, trunk_select
 
 
-def _case(nrows, ncols, seed, outlets="single"):
+def _case(nrows, ncols, seed, outlets="single", uniform=False):
     _, _, ldd, _ = synth.make_dem_ldd(nrows, ncols, 100.0, seed=seed, outlets=outlets)
     st = LddStruct(ldd)
     pre, sub_size = dfs_order(st)
+    down, level = device_order_structures(st, pre)
     rng = np.random.default_rng(seed)
-    m = (rng.gamma(0.8, 3.0, st.n) * (rng.random(st.n) < 0.7)).astype(np.float32)
-    want = np.empty(st.n)
-    want[pre] = st.accuflux_f64(m)                  # oracle, reordered to device (DFS) order
+    m = (np.full(st.n, 3.3) if uniform else rng.gamma(0.8, 3.0, st.n) * (rng.random(st.n) < 0.7)).astype(np.float32)
+    exact, real4 = np.empty(st.n), np.empty(st.n, np.float32)
+    exact[pre] = st.accuflux_f64(m)                 # oracle, reordered to device (DFS) order
+    real4[pre] = st.accuflux(m)                     # the reference's REAL4-per-cell arithmetic
     vals = np.empty(st.n, np.float32)
     vals[pre] = m
-    return sub_size, vals, want
+    return dict(sub_size=sub_size, down=down, level=level, vals=vals, exact=exact, real4=real4, n=st.n)
+
+
+def _route(case, world, min_level, min_cells, exchange=None):
+    """Every rank's begin -> exchange -> finish; returns the routed REAL4 map of the whole basin and the listed cells."""
+    n, sub_size = case["n"], case["sub_size"]
+    b = multigpu.partition_bounds(n, world) if world > 1 else np.array([0, n], np.int64)
+    cell, sub, is_trunk, last, parent_slot = trunk_select(sub_size, case["level"], case["down"], min_level, min_cells, b)
+    plan = multigpu.plan_trunk(cell, sub, b)
+    out = np.empty(n, np.float32)
+    sends = []
+    for p in range(world):
+        lo, hi = int(b[p]), int(b[p + 1])
+        mine = cell[(cell >= lo) & (cell < hi)] - lo
+        acc, send = rank_begin(case["vals"][lo:hi], sub_size[lo:hi], plan["pub"][p], mine)
+        out[lo:hi] = acc.astype(np.float32)
+        sends.append(send)
+    gathered = exchange(sends, plan["stride"]) if exchange else sends
+    out[cell] = trunk_finish(plan, gathered, is_trunk, last, parent_slot)
+    return out, cell, plan
 
 
 def test_bounds_are_tile_aligned_and_balanced():
@@ -36,19 +59,41 @@ def test_bounds_are_tile_aligned_and_balanced():
 @pytest.mark.parametrize("world", [1, 2, 3, 5])
 @pytest.mark.parametrize("shape,outlets", [((150, 130), "single"), ((170, 140), "border")])
 def test_plan_and_exchange_emulated(world, shape, outlets):
-    sub_size, vals, want = _case(shape[0], shape[1], seed=world + 3, outlets=outlets)
-    b, ranks, stride = multigpu.plan(sub_size, world)
-    assert len(ranks) == world and stride >= 1
-    begun = [rank_begin(vals[b[p]:b[p + 1]], sub_size[b[p]:b[p + 1]], ranks[p], stride) for p in range(world)]
-    gathered = [x[1] for x in begun]
-    got = np.concatenate([rank_finish(begun[p][0], begun[p][2], ranks[p], p, gathered) for p in range(world)])
+    """No trunk (thresholds out of reach): the listed cells are exactly those whose range leaves their rank, and the
+    result is the float64 accumulation rounded once -- whatever the number of ranks."""
+    case = _case(shape[0], shape[1], seed=world + 3, outlets=outlets)
+    got, cell, plan = _route(case, world, 10 ** 9, 10 ** 12)
     assert not np.isnan(got).any()
-    assert np.allclose(got, want, rtol=1e-9, atol=1e-9)
+    assert np.allclose(got, case["exact"], rtol=2e-7, atol=1e-9)
+    assert (cell.size == 0) == (world == 1)
     for p in range(world):                           # plan invariants
-        me = ranks[p]
-        assert (np.diff(me["pub_e"]) > 0).all() if len(me["pub_e"]) > 1 else True
-        assert (me["remote_rank"] > p).all()         # ranges only ever extend to higher ranks (pre-order)
-        assert len(me["remote_k"]) == len(me["remote_rank"]) == len(me["remote_slot"])
+        pub = plan["pub"][p]
+        assert (np.diff(pub) > 0).all() if len(pub) > 1 else True
+        assert plan["stride"] >= 1 + len(pub)
+    assert (plan["end_rank"] >= plan["before_rank"]).all()           # ranges only ever extend to higher ranks (pre-order)
+
+
+@pytest.mark.parametrize("uniform", [False, True])
+@pytest.mark.parametrize("world", [1, 3])
+def test_rounding_drift_follows_the_real4_reference(world, uniform):
+    """The reference rounds every cell's sum to REAL4.  With (nearly) equal runoff everywhere those roundings are biased
+    and the reference drifts away from exact accumulation; the trunk accumulation must follow it, independent of the
+    number of ranks."""
+    case = _case(500, 450, seed=3, uniform=uniform)
+    den = np.maximum(np.abs(case["real4"]), 1e-30)
+    plain = np.max(np.abs(case["exact"].astype(np.float32).astype(np.float64) - case["real4"]) / den)
+    got, cell, _ = _route(case, world, 16, 64)
+    err = np.max(np.abs(got.astype(np.float64) - case["real4"]) / den)
+    assert cell.size > 30000
+    assert err <= 5e-7, err
+    if uniform:
+        assert plain > 2e-6 and err < 0.25 * plain
+    one, _, _ = _route(case, 1, 16, 64)
+    # the drift sums are exact, so the split only shows through the float64 prefixes: at most one REAL4 ulp, rarely
+    # (the absolute term covers the cancellation noise of this emulation's rank-wide np.cumsum on tiny fluxes; the kernels
+    # use tile-local prefixes for the ordinary cells)
+    diff = np.abs(got.astype(np.float64) - one)
+    assert (diff <= 1.3e-7 * den + 1e-10).all() and np.mean(diff > 0) < 1e-3
 
 
 def _worker(rank, world, port, ret):
@@ -57,14 +102,20 @@ def _worker(rank, world, port, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    sub_size, vals, want = _case(200, 160, seed=7)
-    b, ranks, stride = multigpu.plan(sub_size, world)
-    lo, hi = b[rank], b[rank + 1]
-    acc, send, partial = rank_begin(vals[lo:hi], sub_size[lo:hi], ranks[rank], stride)
-    recv = torch.zeros(world * stride, dtype=torch.float64)
-    dist.all_gather_into_tensor(recv, torch.from_numpy(send))          # the per-step confluence exchange
-    got = rank_finish(acc, partial, ranks[rank], rank, recv.numpy().reshape(world, stride))
-    ok = bool(np.allclose(got, want[lo:hi], rtol=1e-9, atol=1e-9)) and not np.isnan(got).any()
+    case = _case(200, 160, seed=7)
+
+    def exchange(sends, stride):
+        mine = np.zeros(stride)
+        mine[:sends[rank].size] = sends[rank]                          # this process only owns its own rank's block
+        recv = torch.zeros(world * stride, dtype=torch.float64)
+        dist.all_gather_into_tensor(recv, torch.from_numpy(mine))      # the per-step confluence exchange
+        return list(recv.numpy().reshape(world, stride))
+
+    got, cell, _ = _route(case, world, 32, 256, exchange=exchange)
+    b = multigpu.partition_bounds(case["n"], world)
+    lo, hi = int(b[rank]), int(b[rank + 1])
+    den = np.maximum(np.abs(case["real4"]), 1e-30)
+    ok = bool(np.max(np.abs(got[lo:hi].astype(np.float64) - case["real4"][lo:hi]) / den[lo:hi]) <= 5e-7) and cell.size > 0
     flag = torch.tensor([1 if ok else 0])
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
