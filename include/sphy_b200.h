@@ -192,6 +192,9 @@ enum {
     SPHY_OP_GROUNDWATER_DYNAMIC, /* groundwater.dynamic        modules/groundwater.py:90-125 (4 outputs) */
     SPHY_OP_MUSLE,               /* musle.q_peak + musle.MUSLE modules/musle.py:29-46,143-150: in Q|TotR, Alpha_tc, Tc, K, C, P, LS,
                                     CFRG, cellarea, ha_area, q_is_discharge -> sediment yield, ton per cell */
+    SPHY_OP_ADV_BLEND,           /* advanced_routing.ROUT, the blend   modules/advanced_routing.py:31-33: in accufractionflux, qold, qout,
+                                    QFRAC, kx, REAL4(1-kx) or NaN -> Q [m3/day] */
+    SPHY_OP_ADV_FINISH,          /* advanced_routing.ROUT, the rest    :34-38: in Q, upstream(Q), QFRAC, sres, qout -> sres, Q [m3/s], Qin */
     SPHY_OP_COUNT
 };
 int sphy_module_op(sphy_ctx *ctx, int op, const sphy_param *in, int n_in, float *const *out, int n_out, int64_t count,
@@ -360,14 +363,16 @@ int sphy_accuflux(sphy_ctx *ctx, const float *material, const float *fraction /*
                   void *stream);
 int sphy_upstream(sphy_ctx *ctx, const float *x, float *out, void *stream);
 
-/* The same exchange over peer memory (NVLink P2P through CUDA IPC) instead of an NCCL all-gather: every rank stores its
- * block straight into the peers' receive buffers and releases a per-peer flag; a bounded wait acquires the flags of all
- * peers.  sphy_p2p_setup_local allocates this rank's buffers (`pitch` >= ncomp * stride float64 per rank) and returns two
- * 64-byte CUDA IPC handles; the host exchanges them (any transport) and calls sphy_p2p_connect with all of them, ordered by
- * rank.  Per step: sphy_route_scan_begin -> sphy_route_scan_exchange_p2p -> sphy_route_scan_finish(gathered_dev = NULL). */
+/* The same exchange over peer memory (NVLink P2P through CUDA IPC) instead of an NCCL all-gather: the publishing blocks of
+ * sphy_route_scan_begin store this rank's block straight into the peers' receive buffers and release a per-peer flag; the
+ * trunk kernel of sphy_route_scan_finish acquires the flags of all peers (bounded wait, SPHY_P2P_TIMEOUT_S seconds,
+ * default 30: a dead peer yields NaN discharges on the trunk cells and sphy_p2p_timed_out() != 0, not a hang).  The step
+ * counter lives in device memory.  sphy_p2p_setup_local allocates this rank's buffers (`pitch` >= ncomp * stride float64
+ * per rank) and returns two 64-byte CUDA IPC handles; the host exchanges them (any transport) and calls sphy_p2p_connect
+ * with all of them, ordered by rank.  Once connected, per step: sphy_route_scan_begin(send_dev = NULL) ->
+ * sphy_route_scan_finish(gathered_dev = NULL); no host call in between. */
 int sphy_p2p_setup_local(sphy_ctx *ctx, int world, int64_t pitch, unsigned char *handle_recv64, unsigned char *handle_flags64);
 int sphy_p2p_connect(sphy_ctx *ctx, int rank, int world, const unsigned char *handles_recv, const unsigned char *handles_flags);
-int sphy_route_scan_exchange_p2p(sphy_ctx *ctx, int ncomp, const double *send_dev, int32_t stride, void *stream);
 int sphy_p2p_timed_out(sphy_ctx *ctx, void *stream);
 
 /* ---- K5 + routing with lakes/reservoirs ------------------------------------------------------
@@ -409,6 +414,15 @@ typedef struct {
     float pcorr;
 } sphy_openwater;
 int sphy_reslake_openwater(sphy_ctx *ctx, const sphy_reslake *rl, const sphy_openwater *ow, void *stream);
+
+/* The lake / reservoir functions one at a time over the structure table (n_struct values in, n_struct values out; NaN
+ * where a function does not apply to a structure's kind) -- what the module-signature shims call:
+ *   UPDATE_LAKE  lakes.UpdateLakeHStore  modules/lakes.py:28-132  -> lake level (rl->StorRES of gauged lakes is updated when
+ *                                                                   rl->lake_level holds the day's measured levels)
+ *   QLAKE        lakes.QLake             modules/lakes.py:136-158   in: lake level -> outflow [m3/day], 0 for non-lakes
+ *   QSIMPLE / QADV / QRES  reservoirs.QSimple / QAdv / QRes  modules/reservoirs.py:26-86 -> outflow [m3/day] from rl->StorRES */
+enum { SPHY_RL_OP_UPDATE_LAKE = 0, SPHY_RL_OP_QLAKE, SPHY_RL_OP_QSIMPLE, SPHY_RL_OP_QADV, SPHY_RL_OP_QRES, SPHY_RL_OP_COUNT };
+int sphy_reslake_op(sphy_ctx *ctx, const sphy_reslake *rl, int op, int day_of_year, const float *in, float *out, void *stream);
 
 #ifdef __cplusplus
 }

@@ -101,6 +101,7 @@ class SedRes(C.Structure):
 
 
 RL_NPAR = 30
+RL_OP_UPDATE_LAKE, RL_OP_QLAKE, RL_OP_QSIMPLE, RL_OP_QADV, RL_OP_QRES = range(5)
 WB_SNOW, WB_GROUND, WB_INFIL_EXCESS, WB_PWS, WB_ETREF_INPUT = 1, 2, 4, 8, 16
 RA_TABLE, RA_CELL = 0, 1
 ROUTE_LEVELS, ROUTE_SCAN = 0, 1
@@ -110,7 +111,7 @@ SCAN_TILE = 1024                      # cells per scan-routing tile (csrc/route_
 OPS = ("EXTRARAD", "HARGREAVES", "ETPOT", "ETACT", "KS", "POTSNOWMELT", "ACTSNOWMELT", "SNOWSTOREUPDATE", "MAXSNOWWATSTORAGE",
        "SNOWWATSTORAGE", "TOTSNOWSTORAGE", "SNOWR", "ROOTRUNOFF_SAT", "ROOTRUNOFF_INFIL", "ROOTDRAINAGE", "ROOTPERCOLATION",
        "CALCFRAC", "CAPILRISE", "SUBPERCOLATION", "SUBDRAINAGE", "GWRECHARGE", "BASEFLOW", "HLEVEL", "SNOW_DYNAMIC",
-       "GROUNDWATER_DYNAMIC", "MUSLE")
+       "GROUNDWATER_DYNAMIC", "MUSLE", "ADV_BLEND", "ADV_FINISH")
 OP = {name: i for i, name in enumerate(OPS)}
 UNARY_EXP_NEG_INV, UNARY_SIN_DEG, UNARY_COS_DEG, UNARY_TAN_DEG, UNARY_EXP_NEG = 0, 1, 2, 3, 4
 
@@ -139,7 +140,6 @@ SYMBOLS = {
     "sphy_route_profile_read": (C.c_int, [P, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "sphy_p2p_setup_local": (C.c_int, [P, C.c_int, C.c_int64, P, P]),
     "sphy_p2p_connect": (C.c_int, [P, C.c_int, C.c_int, P, P]),
-    "sphy_route_scan_exchange_p2p": (C.c_int, [P, C.c_int, P, C.c_int32, P]),
     "sphy_p2p_timed_out": (C.c_int, [P, P]),
     "sphy_mmf_step": (C.c_int, [P, C.POINTER(Mmf), C.c_int, P]),
     "sphy_accucapacity": (C.c_int, [P, P, P, P, P, P]),
@@ -159,6 +159,7 @@ SYMBOLS = {
     "sphy_accuflux": (C.c_int, [P, P, P, P, C.c_int, P]),
     "sphy_upstream": (C.c_int, [P, P, P, P]),
     "sphy_reslake_openwater": (C.c_int, [P, C.POINTER(ResLake), C.POINTER(OpenWater), P]),
+    "sphy_reslake_op": (C.c_int, [P, C.POINTER(ResLake), C.c_int, C.c_int, P, P, P]),
     "sphy_route_reslake_step": (C.c_int, [P, C.POINTER(ResLake), P, P, SphyParam, C.c_float, C.c_int, C.c_int, P]),
 }
 

@@ -57,7 +57,6 @@ struct sphy_ctx {
     void *p2p_opened[128] = {};
     int p2p_nopened = 0, p2p_world = 0, p2p_rank = 0;
     int64_t p2p_pitch = 0;
-    long long p2p_step = 0;
     int32_t *cross_r = nullptr, *cross_e = nullptr, *cross_ptr = nullptr, *end_e = nullptr, *end_k = nullptr, *end_ptr = nullptr;
     int32_t n_cross = 0;
     double *park_before = nullptr, *park_end = nullptr;

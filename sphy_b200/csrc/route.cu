@@ -552,45 +552,100 @@ __device__ float lake_fun(float fn, float ea, float eb, float pb, float a1, floa
     return (((a3 * dpowf(x, 3.0f)) + (a2 * dpowf(x, 2.0f))) + a1 * x) + pb;
 }
 
+// per-structure parameter access
+struct RLPar {
+    const float *par;
+    int ns, j;
+    __device__ __forceinline__ float operator()(int row) const { return par[(size_t)row * ns + j]; }
+};
+
+// lakes.UpdateLakeHStore, first half (lakes.py:37-65): a gauged lake with a defined level takes its storage from S(h);
+// then the WHOLE storage map is clamped at 0 (reservoirs included).  Only on days with a level map.
+__device__ __forceinline__ float rl_storage_from_level(const RLPar &P, float S, float measured)
+{
+    if (measured == measured)
+        S = lake_fun(P(RL_SH_FUNC), P(RL_SH_EXPA), P(RL_SH_EXPB), P(RL_SH_B), P(RL_SH_A1), P(RL_SH_A2), P(RL_SH_A3), measured);
+    return fmaxf(S, 0.0f);
+}
+// lakes.UpdateLakeHStore, second half (lakes.py:66-131): the level, measured or h(S)
+__device__ __forceinline__ float rl_lake_level(const RLPar &P, float S, float measured)
+{
+    return measured == measured ? measured
+                                : lake_fun(P(RL_HS_FUNC), P(RL_HS_EXPA), P(RL_HS_EXPB), P(RL_HS_B), P(RL_HS_A1), P(RL_HS_A2), P(RL_HS_A3), S);
+}
+// lakes.QLake (lakes.py:136-158), m3/day
+__device__ __forceinline__ float rl_qlake(const RLPar &P, float h)
+{
+    const float qh = lake_fun(P(RL_QH_FUNC), P(RL_QH_EXPA), P(RL_QH_EXPB), P(RL_QH_B), P(RL_QH_A1), P(RL_QH_A2), P(RL_QH_A3), h);
+    return (fmaxf(0.0f, qh) * 3600.0f) * 24.0f;
+}
+// reservoirs.QSimple (reservoirs.py:62-70)
+__device__ __forceinline__ float rl_qsimple(const RLPar &P, float S)
+{
+    return fmaxf(fminf((P(RL_KR) * S) * dpowf(S / P(RL_SMAX), P(RL_B)), S), S - P(RL_SMAX));
+}
+// reservoirs.QAdv (reservoirs.py:26-58)
+__device__ __forceinline__ float rl_qadv(const RLPar &P, float S, int doy)
+{
+    const float D = (float)doy, fs = P(RL_FLSTART), fe = P(RL_FLEND);
+    bool flood;
+    if (fs < fe) flood = D >= fs && D <= fe;
+    else if (D >= fe) flood = D >= fs;
+    else flood = D <= fe ? D <= fs : false;
+    const float avail = fmaxf(S - P(RL_PVOL), 0.0f);
+    const float den = P(RL_EVOL) - P(RL_PVOL);
+    return fmaxf(flood ? (P(RL_MAXFL) * avail) / den : (P(RL_DEMFL) * avail) / den, S - P(RL_EVOL));
+}
+
 __global__ void k_rl_pre(sphy_reslake rl, const float *__restrict__ totr, float vol_factor, int doy, float *__restrict__ qout_dense)
 {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= rl.n_struct) return;
-    const int ns = rl.n_struct;
     const int32_t c = rl.cell[j];
-    auto P = [&](int row) { return rl.par[(size_t)row * ns + j]; };
+    const RLPar P = {rl.par, rl.n_struct, j};
     float S = rl.StorRES[j] + vol_factor * totr[c];             // advanced_routing.py:136-138
     float q = 0.0f;
     const int kind = rl.kind[j];
-    // a measured-level map exists for this day (lakes.UpdateLakeHStore, lakes.py:28-97): gauged lakes with a defined
-    // level take their storage from S(h); then the WHOLE storage map is clamped at 0 (reservoirs included, lakes.py:65)
     float measured = nanf("");
-    if (rl.lake_level) {
+    if (rl.lake_level) {                                        // a measured-level map exists for this day
         if (kind == 3 && rl.update_level[j] != 0) measured = rl.lake_level[j];
-        if (measured == measured)
-            S = lake_fun(P(RL_SH_FUNC), P(RL_SH_EXPA), P(RL_SH_EXPB), P(RL_SH_B), P(RL_SH_A1), P(RL_SH_A2), P(RL_SH_A3), measured);
-        S = fmaxf(S, 0.0f);
+        S = rl_storage_from_level(P, S, measured);
     }
-    if (kind == 1) {                                            // QSimple
-        q = fmaxf(fminf((P(RL_KR) * S) * dpowf(S / P(RL_SMAX), P(RL_B)), S), S - P(RL_SMAX));
-    } else if (kind == 2) {                                     // QAdv
-        const float D = (float)doy, fs = P(RL_FLSTART), fe = P(RL_FLEND);
-        bool flood;
-        if (fs < fe) flood = D >= fs && D <= fe;
-        else if (D >= fe) flood = D >= fs;
-        else flood = D <= fe ? D <= fs : false;
-        const float avail = fmaxf(S - P(RL_PVOL), 0.0f);
-        const float den = P(RL_EVOL) - P(RL_PVOL);
-        q = fmaxf(flood ? (P(RL_MAXFL) * avail) / den : (P(RL_DEMFL) * avail) / den, S - P(RL_EVOL));
-    } else if (kind == 3) {                                     // lake: level from storage, Q from level
-        const float h = measured == measured ? measured
-                                             : lake_fun(P(RL_HS_FUNC), P(RL_HS_EXPA), P(RL_HS_EXPB), P(RL_HS_B), P(RL_HS_A1), P(RL_HS_A2), P(RL_HS_A3), S);
-        const float qh = lake_fun(P(RL_QH_FUNC), P(RL_QH_EXPA), P(RL_QH_EXPB), P(RL_QH_B), P(RL_QH_A1), P(RL_QH_A2), P(RL_QH_A3), h);
-        q = (fmaxf(0.0f, qh) * 3600.0f) * 24.0f;                // lakes.py:155-157
-    }
+    if (kind == 1) q = rl_qsimple(P, S);
+    else if (kind == 2) q = rl_qadv(P, S, doy);
+    else if (kind == 3) q = rl_qlake(P, rl_lake_level(P, S, measured));
     rl.StorRES[j] = S;
     rl.Qout[j] = q;
     qout_dense[c] = q;
+}
+
+// the same functions one at a time, over the structure table (what sphy_b200/modules/lakes.py and reservoirs.py call)
+__global__ void k_rl_op(sphy_reslake rl, int op, int doy, const float *__restrict__ in, float *__restrict__ out)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= rl.n_struct) return;
+    const RLPar P = {rl.par, rl.n_struct, j};
+    const int kind = rl.kind[j];
+    float S = rl.StorRES[j];
+    float r = nanf("");
+    switch (op) {
+        case SPHY_RL_OP_UPDATE_LAKE: {                          // lakes.UpdateLakeHStore -> LakeLevel (StorRES updated in place)
+            float measured = nanf("");
+            if (rl.lake_level) {
+                if (kind == 3 && rl.update_level[j] != 0) measured = rl.lake_level[j];
+                const float S1 = rl_storage_from_level(P, S, measured);
+                if (kind == 3) rl.StorRES[j] = S = S1;          // lakes.py:132: only lake cells keep the new storage
+            }
+            if (kind == 3) r = rl_lake_level(P, S, measured);
+            break;
+        }
+        case SPHY_RL_OP_QLAKE: r = kind == 3 ? rl_qlake(P, in[j]) : 0.0f; break;            // cover(Qout, 0), lakes.py:157
+        case SPHY_RL_OP_QSIMPLE: if (kind == 1) r = rl_qsimple(P, S); break;
+        case SPHY_RL_OP_QADV: if (kind == 2) r = rl_qadv(P, S, doy); break;
+        case SPHY_RL_OP_QRES: r = kind == 1 ? rl_qsimple(P, S) : (kind == 2 ? rl_qadv(P, S, doy) : 0.0f); break;
+        default: break;
+    }
+    out[j] = r;
 }
 
 __global__ void k_rl_material(const float *__restrict__ totr, const float *__restrict__ qfrac, float vol_factor, int64_t n,
@@ -738,3 +793,15 @@ extern "C" int sphy_reslake_openwater(sphy_ctx *ctx, const sphy_reslake *rl, con
     SPHY_LAUNCH_CHECK(ctx);
     return SPHY_OK;
 }
+
+extern "C" int sphy_reslake_op(sphy_ctx *ctx, const sphy_reslake *rl, int op, int day_of_year, const float *in, float *out, void *stream)
+{
+    if (!ctx || !rl || !out || op < 0 || op >= SPHY_RL_OP_COUNT) return SPHY_E_INVALID;
+    if (rl->n_struct <= 0) return SPHY_OK;
+    if (!rl->cell || !rl->kind || !rl->par || !rl->StorRES || (op == SPHY_RL_OP_QLAKE && !in))
+        SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_reslake_op: incomplete structure table or missing input");
+    k_rl_op<<<div_up(rl->n_struct, 128), 128, 0, (cudaStream_t)stream>>>(*rl, op, day_of_year, in, out);
+    SPHY_LAUNCH_CHECK(ctx);
+    return SPHY_OK;
+}
+

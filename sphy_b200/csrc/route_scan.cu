@@ -14,6 +14,7 @@
 // Small subtrees never see the global magnitude, so relative accuracy holds for tiny fluxes too.  The float64
 // range sums have no per-cell REAL4 rounding along the flow path, hence this path agrees with the level sweep /
 // the oracle to ~1e-6 relative (tested at 1e-5), not bit-for-bit; the level sweep stays the bit-exact path.
+#include <cstdlib>
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -254,9 +255,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_MIN_CTAS) k_scan_main(const
 // cells whose upstream range crosses a tile boundary
 constexpr int CROSS_ILP = 4;       // crossing cells per thread: four independent gather chains in flight
 
-__global__ void __launch_bounds__(256) k_scan_cross(const __grid_constant__ ScanArgs a)
+__device__ __forceinline__ void scan_cross_block(const ScanArgs &a, int32_t block)
 {
-    const int32_t k0 = blockIdx.x * (256 * CROSS_ILP) + threadIdx.x;
+    const int32_t k0 = block * (256 * CROSS_ILP) + threadIdx.x;
     int32_t r[CROSS_ILP], e[CROSS_ILP];
     bool ok[CROSS_ILP];
 #pragma unroll
@@ -295,16 +296,65 @@ __global__ void __launch_bounds__(256) k_scan_cross(const __grid_constant__ Scan
     }
 }
 
-// the range total and the range-local inclusive prefix at every published position (what the trunk cells are finished
-// from; on a partitioned basin this block is the "confluence inflow" message of the rank)
-__global__ void k_scan_publish(const __grid_constant__ ScanArgs a)
+// Confluence exchange over peer memory (NVLink P2P, CUDA IPC; set up by sphy_p2p_setup_local / sphy_p2p_connect).  Every
+// rank owns a receive buffer [2 parities][world][pitch] and, in `local`, one flag per peer followed by a time-out word, the
+// exchange step counter and a block counter.  The publishing blocks store this rank's values straight into every peer's
+// buffer; the last of them releases flag[rank] = step on every peer with system scope.  The trunk kernel acquires the
+// flags of all peers before it reads the blocks (bounded: a dead peer yields NaN discharges and an error, not a hang) and
+// advances the step counter when it is done.  Double buffering by step parity is enough: a rank can only be one exchange
+// ahead of a peer, because its next push comes after a wait on that peer's current flag.  The step counter lives in device
+// memory, so the whole step can be replayed from a CUDA graph.
+struct P2PArgs {
+    int on;                               // 0: no peer exchange (one GPU, or the NCCL all-gather done by the host)
+    int rank, world;
+    double *const *peer_recv;
+    long long *const *peer_flags;
+    long long *local;                     // this rank's flags[world], time-out word, step counter, block counter
+    double *recv;                         // this rank's receive buffer
+    int64_t pitch;
+    long long max_naps;
+};
+
+// One launch finishes the ordinary tile-crossing cells (blocks [0, n_cross_blocks)) and publishes the range total and the
+// range-local inclusive prefix at every published position (the remaining blocks) -- what the trunk cells are finished
+// from; on a partitioned basin that block is the "confluence inflow" message of the rank.
+__global__ void __launch_bounds__(256) k_scan_cross_pub(const __grid_constant__ ScanArgs a, const __grid_constant__ P2PArgs p,
+                                                        int n_cross_blocks)
 {
-    const int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    for (int c = 0; c < a.ncomp; ++c) {
-        const double *X = a.tile_excl + (int64_t)c * (a.ntiles + 1);
-        double *out = a.send + (int64_t)c * a.stride;
-        if (j == 0) out[0] = X[a.ntiles];
-        if (j < a.n_pub) out[1 + j] = X[a.pub_e[j] / SCAN_TILE] + a.park_end[(int64_t)c * (a.n_cross + a.n_pub) + a.n_cross + j];
+    if ((int)blockIdx.x < n_cross_blocks) {
+        scan_cross_block(a, blockIdx.x);
+        return;
+    }
+    const int32_t i = (blockIdx.x - n_cross_blocks) * 256 + threadIdx.x;      // 0: the range total, 1 + j: position j
+    long long step = 0;
+    size_t slot = 0;
+    if (p.on) {
+        step = *reinterpret_cast<const volatile long long *>(p.local + p.world + 1) + 1;
+        slot = ((size_t)((step - 1) & 1) * p.world + p.rank) * p.pitch;
+    }
+    if (i <= a.n_pub) {
+        for (int c = 0; c < a.ncomp; ++c) {
+            const double *X = a.tile_excl + (int64_t)c * (a.ntiles + 1);
+            const double v = i == 0 ? X[a.ntiles]
+                                    : X[a.pub_e[i - 1] / SCAN_TILE] + a.park_end[(int64_t)c * (a.n_cross + a.n_pub) + a.n_cross + i - 1];
+            const int64_t o = (int64_t)c * a.stride + i;
+            if (a.send) a.send[o] = v;
+            if (p.on)
+                for (int q = 0; q < p.world; ++q) p.peer_recv[q][slot + o] = v;
+        }
+    }
+    if (!p.on) return;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned *counter = reinterpret_cast<unsigned *>(p.local + p.world + 2);
+        const unsigned nblk = gridDim.x - n_cross_blocks;
+        if (atomicAdd(counter, 1u) == nblk - 1) {             // every publishing block has stored and fenced
+            *counter = 0u;
+            __threadfence_system();
+            for (int q = 0; q < p.world; ++q)
+                asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p.peer_flags[q] + p.rank), "l"(step) : "memory");
+        }
     }
 }
 
@@ -328,6 +378,8 @@ struct TrunkArgs {
     const double *gathered;               // [world][rank_pitch]: per rank [ncomp][stride] published blocks
     int64_t rank_pitch, part_begin;
     int32_t stride, world;
+    const int *timed_out;                 // peer-memory exchange: set when a bounded flag wait gave up (else NULL)
+    P2PArgs p2p;
 };
 
 constexpr int TRUNK_BLOCK = 512;
@@ -340,15 +392,31 @@ __global__ void __launch_bounds__(TRUNK_BLOCK) k_trunk_drift(const __grid_consta
     __shared__ bool is_last;
     const int tid = threadIdx.x;
     const int32_t s = blockIdx.x * TRUNK_BLOCK + tid;
+    const double *gathered = t.gathered;
+    long long step = 0;
+    if (t.p2p.on) {                                            // acquire the blocks the peers stored into this rank's buffer
+        const P2PArgs &p = t.p2p;
+        step = *reinterpret_cast<const volatile long long *>(p.local + p.world + 1) + 1;
+        if (tid < p.world) {
+            long long v = 0, it = 0;
+            for (; it < p.max_naps; ++it) {
+                asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p.local + tid) : "memory");
+                if (v >= step) break;
+                __nanosleep(100);
+            }
+            if (it >= p.max_naps) *reinterpret_cast<volatile int *>(p.local + p.world) = 1;
+        }
+        gathered = p.recv + (size_t)((step - 1) & 1) * p.world * p.pitch;
+    }
     for (int c = 0; c < a.ncomp; ++c) {
         __syncthreads();
         if (tid < t.world) {                                   // global prefix at the start of every rank's range
             double b = 0.0;
-            for (int u = 0; u < tid; ++u) b += t.gathered[(int64_t)u * t.rank_pitch + (int64_t)c * t.stride];
+            for (int u = 0; u < tid; ++u) b += gathered[(int64_t)u * t.rank_pitch + (int64_t)c * t.stride];
             base[tid] = b;
         }
         __syncthreads();
-        const double *V = t.gathered + (int64_t)c * t.stride + 1;
+        const double *V = gathered + (int64_t)c * t.stride + 1;
         auto eval = [&](int32_t e) {                           // exact accumulated flux of trunk entry e
             const int32_t er = __ldg(t.erank + e), br = __ldg(t.brank + e);
             const double hi = base[er] + V[(int64_t)er * t.rank_pitch + __ldg(t.eslot + e)];
@@ -394,7 +462,10 @@ __global__ void __launch_bounds__(TRUNK_BLOCK) k_trunk_drift(const __grid_consta
             carry += tot;
         }
     }
-    if (tid == 0) *t.counter = 0u;
+    if (tid == 0) {
+        *t.counter = 0u;
+        if (t.p2p.on) *(t.p2p.local + t.p2p.world + 1) = step;    // this exchange is consumed: the next push may overwrite its parity
+    }
 }
 
 __global__ void __launch_bounds__(256) k_trunk_apply(const __grid_constant__ ScanArgs a, const __grid_constant__ TrunkArgs t)
@@ -407,13 +478,44 @@ __global__ void __launch_bounds__(256) k_trunk_apply(const __grid_constant__ Sca
     const float omk = a.kx.map ? 1.0f - kx : a.one_m_kx;
     const bool drift = t.trunk[s] != 0;
     const int32_t l = __ldg(t.last + s);
+    // a peer that never delivered its block: make the failure visible in the data instead of routing stale prefixes
+    const bool dead = t.timed_out && *reinterpret_cast<const volatile int *>(t.timed_out) != 0;
     for (int c = 0; c < a.ncomp; ++c) {
         const double *Gl = t.Gl + (int64_t)c * t.m, *BP = t.BP + (int64_t)c * t.nblk;
         double D = 0.0;
         if (drift) D = (BP[l / TRUNK_BLOCK] + Gl[l]) - (s > 0 ? BP[(s - 1) / TRUNK_BLOCK] + Gl[s - 1] : 0.0);
         const float f = (float)((double)(float)t.E[(int64_t)c * t.m + s] + D);
         float *qs = a.qstate[c];
-        qs[r] = omk * f + kx * qs[r];                          // routing.py:28
+        qs[r] = dead ? nanf("") : omk * f + kx * qs[r];        // routing.py:28
+    }
+}
+
+// exclusive prefix of the tile totals (ntiles + 1 entries per component: the trailing 0 makes X[ntiles] the range total);
+// one CTA per component: for ranges of at most 4096 tiles (small basins, where launches dominate) one launch instead of
+// a library scan per component; larger ranges use cub's single-pass scan
+__global__ void __launch_bounds__(1024) k_tile_scan(const double *__restrict__ tot, double *__restrict__ excl, int32_t count)
+{
+    typedef cub::BlockScan<double, 1024> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    const double *T = tot + (int64_t)blockIdx.x * count;
+    double *X = excl + (int64_t)blockIdx.x * count;
+    constexpr int PER = 4;
+    double carry = 0.0;
+    for (int32_t b0 = 0; b0 < count; b0 += 1024 * PER) {
+        double v[PER], ex[PER], total;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int32_t i = b0 + threadIdx.x * PER + k;
+            v[k] = i < count ? T[i] : 0.0;
+        }
+        __syncthreads();
+        Scan(tmp).ExclusiveSum(v, ex, total);
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int32_t i = b0 + threadIdx.x * PER + k;
+            if (i < count) X[i] = carry + ex[k];
+        }
+        carry += total;
     }
 }
 
@@ -599,7 +701,29 @@ static void prof_mark(sphy_ctx *ctx, cudaStream_t st)
     ctx->prof_ev.push_back(e);
 }
 
-static int scan_launch_local(sphy_ctx *ctx, ScanArgs &a, cudaStream_t st)
+static P2PArgs p2p_args(const sphy_ctx *ctx, bool on)
+{
+    P2PArgs p = {};
+    if (!on) return p;
+    static const long long max_naps = [] {
+        const char *e = getenv("SPHY_P2P_TIMEOUT_S");
+        const double sec = e ? atof(e) : 30.0;
+        return (long long)((sec > 0.01 ? sec : 0.01) * 1e7);  // 100 ns naps
+    }();
+    p.on = 1;
+    p.rank = ctx->p2p_rank;
+    p.world = ctx->p2p_world;
+    p.peer_recv = ctx->p2p_peer_recv;
+    p.peer_flags = ctx->p2p_peer_flags;
+    p.local = ctx->p2p_flags;
+    p.recv = ctx->p2p_recv;
+    p.pitch = ctx->p2p_pitch;
+    p.max_naps = max_naps;
+    return p;
+}
+
+// main pass -> exclusive scan of the tile totals -> crossing cells + publishing (+ push into the peers' buffers)
+static int scan_launch_local(sphy_ctx *ctx, ScanArgs &a, cudaStream_t st, bool publish = false, bool push = false)
 {
     const int resident = ctx->sm_count * SCAN_MIN_CTAS;
     const int want = (ctx->n_tiles + SCAN_WARPS - 1) / SCAN_WARPS;       // one tile per warp
@@ -620,12 +744,18 @@ static int scan_launch_local(sphy_ctx *ctx, ScanArgs &a, cudaStream_t st)
         else k_scan_main<false, false><<<grid, SCAN_THREADS, SCAN_SMEM, st>>>(a);
     }
     prof_mark(ctx, st);
-    for (int c = 0; c < a.ncomp; ++c) {
-        size_t need = ctx->scan_tmp_bytes;
-        SPHY_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->scan_tmp, need, ctx->scan_tile + (size_t)c * (ctx->n_tiles + 1),
-                                                     ctx->scan_excl + (size_t)c * (ctx->n_tiles + 1), ctx->n_tiles + 1, st));
+    if (ctx->n_tiles + 1 <= 4 * 1024) {                        // small ranges: one CTA per component, one launch
+        k_tile_scan<<<a.ncomp, 1024, 0, st>>>(ctx->scan_tile, ctx->scan_excl, ctx->n_tiles + 1);
+    } else {                                                   // single-pass decoupled look-back scan of the library
+        for (int c = 0; c < a.ncomp; ++c) {
+            size_t need = ctx->scan_tmp_bytes;
+            SPHY_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->scan_tmp, need, ctx->scan_tile + (size_t)c * (ctx->n_tiles + 1),
+                                                         ctx->scan_excl + (size_t)c * (ctx->n_tiles + 1), ctx->n_tiles + 1, st));
+        }
     }
-    if (ctx->n_cross > 0) k_scan_cross<<<div_up(ctx->n_cross, 256 * CROSS_ILP), 256, 0, st>>>(a);
+    const int ncb = div_up(ctx->n_cross, 256 * CROSS_ILP);
+    const int npb = publish ? div_up(ctx->n_pub + 1, 256) : 0;
+    if (ncb + npb > 0) k_scan_cross_pub<<<ncb + npb, 256, 0, st>>>(a, p2p_args(ctx, push), ncb);
     prof_mark(ctx, st);
     return SPHY_OK;
 }
@@ -646,7 +776,7 @@ static int trunk_prepare(sphy_ctx *ctx, int ncomp, cudaStream_t st)
 }
 
 // finish the trunk cells of this context from the published blocks of all ranks
-static int trunk_finish(sphy_ctx *ctx, const ScanArgs &a, const double *gathered, int64_t rank_pitch, cudaStream_t st)
+static int trunk_finish(sphy_ctx *ctx, const ScanArgs &a, const double *gathered, int64_t rank_pitch, cudaStream_t st, bool p2p = false)
 {
     if (ctx->sl_n == 0) return SPHY_OK;
     TrunkArgs t = {};
@@ -670,6 +800,8 @@ static int trunk_finish(sphy_ctx *ctx, const ScanArgs &a, const double *gathered
     t.part_begin = ctx->part_begin;
     t.stride = ctx->sl_stride;
     t.world = ctx->sl_world;
+    t.p2p = p2p_args(ctx, p2p);
+    t.timed_out = p2p ? reinterpret_cast<const int *>(ctx->p2p_flags + ctx->p2p_world) : nullptr;
     k_trunk_drift<<<ctx->sl_nblk, TRUNK_BLOCK, 0, st>>>(a, t);
     k_trunk_apply<<<div_up(ctx->sl_n, 256), 256, 0, st>>>(a, t);
     return SPHY_OK;
@@ -686,12 +818,10 @@ int route_scan_run(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm, floa
         a.send = ctx->sl_V;
         a.stride = ctx->sl_stride;
     }
-    int rc2 = scan_launch_local(ctx, a, st);
+    const bool trunk = ctx->sl_plan && ctx->sl_n > 0;
+    int rc2 = scan_launch_local(ctx, a, st, trunk);
     if (rc2 != SPHY_OK) return rc2;
-    if (ctx->sl_plan && ctx->sl_n > 0) {
-        k_scan_publish<<<div_up(ctx->n_pub > 0 ? ctx->n_pub : 1, 256), 256, 0, st>>>(a);
-        if ((rc = trunk_finish(ctx, a, ctx->sl_V, (int64_t)ncomp * ctx->sl_stride, st)) != SPHY_OK) return rc;
-    }
+    if (trunk && (rc = trunk_finish(ctx, a, ctx->sl_V, (int64_t)ncomp * ctx->sl_stride, st)) != SPHY_OK) return rc;
     prof_mark(ctx, st);
     SPHY_LAUNCH_CHECK(ctx);
     return SPHY_OK;
@@ -999,7 +1129,8 @@ extern "C" int sphy_trunk_set_plan(sphy_ctx *ctx, int32_t n_pub, const int32_t *
 extern "C" int sphy_route_scan_begin(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm, float *const *q_state, sphy_param kx,
                                      float one_minus_kx, double *send_dev, int32_t stride, void *stream)
 {
-    if (!ctx || !runoff_mm || !q_state || !send_dev || ncomp < 1 || ncomp > ROUTE_MAX_COMP) return SPHY_E_INVALID;
+    if (!ctx || !runoff_mm || !q_state || ncomp < 1 || ncomp > ROUTE_MAX_COMP) return SPHY_E_INVALID;
+    if (!send_dev && !ctx->p2p_peer_recv) SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_route_scan_begin: no send buffer and no peer exchange set up");
     if (!ctx->ldd_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_route_scan_begin before sphy_ldd_build");
     if (!ctx->sl_plan) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_route_scan_begin before sphy_trunk_set_plan");
     if (stride != ctx->sl_stride) SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_route_scan_begin: stride %d != planned %d", stride, ctx->sl_stride);
@@ -1008,11 +1139,13 @@ extern "C" int sphy_route_scan_begin(sphy_ctx *ctx, int ncomp, const float *cons
     int rc = scan_prepare(ctx, ncomp, runoff_mm, q_state, kx, one_minus_kx, st, a);
     if (rc != SPHY_OK) return rc;
     if ((rc = trunk_prepare(ctx, ncomp, st)) != SPHY_OK) return rc;
+    const bool push = send_dev == nullptr;                 // no host-side gather: the publishing blocks push into the peers' buffers
+    if (push && (int64_t)ncomp * stride > ctx->p2p_pitch)
+        SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_route_scan_begin: %lld values exceed the peer buffer pitch", (long long)ncomp * stride);
     a.send = send_dev;
     a.stride = stride;
-    rc = scan_launch_local(ctx, a, st);
+    rc = scan_launch_local(ctx, a, st, ctx->sl_n > 0, push && ctx->sl_n > 0);
     if (rc != SPHY_OK) return rc;
-    k_scan_publish<<<div_up(ctx->n_pub > 0 ? ctx->n_pub : 1, 256), 256, 0, st>>>(a);
     SPHY_LAUNCH_CHECK(ctx);
     return SPHY_OK;
 }
@@ -1030,55 +1163,15 @@ extern "C" int sphy_route_scan_finish(sphy_ctx *ctx, int ncomp, float *const *q_
     ScanArgs a;
     int rc = scan_prepare(ctx, ncomp, nullptr, q_state, kx, one_minus_kx, st, a);
     if (rc != SPHY_OK) return rc;
-    const double *gathered = gathered_dev;
-    int64_t pitch = (int64_t)ncomp * stride;
-    if (!gathered) {                              // what the peers stored into this rank's buffer (sphy_route_scan_exchange_p2p)
-        const int parity = (int)((ctx->p2p_step - 1) & 1);
-        gathered = ctx->p2p_recv + (size_t)parity * ctx->p2p_world * ctx->p2p_pitch;
-        pitch = ctx->p2p_pitch;
-    }
-    if ((rc = trunk_finish(ctx, a, gathered, pitch, st)) != SPHY_OK) return rc;
+    // gathered_dev == NULL: what the peers stored into this rank's buffer (the trunk kernel acquires their flags first)
+    const bool p2p = gathered_dev == nullptr;
+    if ((rc = trunk_finish(ctx, a, gathered_dev, p2p ? ctx->p2p_pitch : (int64_t)ncomp * stride, st, p2p)) != SPHY_OK) return rc;
     prof_mark(ctx, st);
     SPHY_LAUNCH_CHECK(ctx);
     return SPHY_OK;
 }
 
-// ---- confluence exchange over peer memory (NVLink P2P) instead of an NCCL all-gather -------------------------------------
-// The message is a few thousand float64 per rank and purely latency-bound.  Every rank owns a receive buffer
-// [2 parities][world][pitch] and a flag per peer, allocated with cudaMalloc and opened on the other ranks through CUDA
-// IPC.  Per step: k_p2p_push (one CTA per peer) stores this rank's block straight into every peer's buffer and
-// releases `flag[rank] = step` with system scope; k_p2p_wait acquires the flags of all peers before the trunk cells
-// are finished.  Double buffering by step parity is enough: a rank can only be one exchange ahead of a peer, because
-// its next push comes after a wait on that peer's current flag.  The wait is bounded (no hang if a peer dies).
-namespace {
-
-__global__ void __launch_bounds__(256) k_p2p_push(const double *__restrict__ send, int count, double *const *peer_recv,
-                                                   long long *const *peer_flags, int rank, int world, int64_t pitch, int parity,
-                                                   long long step)
-{
-    const int p = blockIdx.x;
-    double *dst = peer_recv[p] + ((size_t)parity * world + rank) * pitch;
-    for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = send[i];
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(peer_flags[p] + rank), "l"(step) : "memory");
-}
-
-__global__ void k_p2p_wait(const long long *flags, int world, long long step, int *timed_out)
-{
-    const int q = threadIdx.x;
-    if (q >= world) return;
-    long long v = 0;
-    for (long long it = 0; it < 40000000LL; ++it) {             // ~ 4 s of 100 ns naps, then give up
-        asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(flags + q) : "memory");
-        if (v >= step) return;
-        __nanosleep(100);
-    }
-    *timed_out = 1;
-}
-
-}  // namespace
-
+// ---- confluence exchange over peer memory: set-up (the per-step part is in k_scan_cross_pub / k_trunk_drift) ---------------
 extern "C" int sphy_p2p_setup_local(sphy_ctx *ctx, int world, int64_t pitch, unsigned char *handle_recv64, unsigned char *handle_flags64)
 {
     if (!ctx || world < 2 || world > 64 || pitch < 1 || !handle_recv64 || !handle_flags64) return SPHY_E_INVALID;
@@ -1086,9 +1179,9 @@ extern "C" int sphy_p2p_setup_local(sphy_ctx *ctx, int world, int64_t pitch, uns
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
     const size_t nrecv = (size_t)2 * world * pitch;
     SPHY_CUDA(ctx, cudaMalloc(&ctx->p2p_recv, nrecv * sizeof(double)));
-    SPHY_CUDA(ctx, cudaMalloc(&ctx->p2p_flags, (size_t)(world + 1) * sizeof(long long)));   // + the time-out word
+    SPHY_CUDA(ctx, cudaMalloc(&ctx->p2p_flags, (size_t)(world + 3) * sizeof(long long)));   // + time-out word, step counter, block counter
     SPHY_CUDA(ctx, cudaMemset(ctx->p2p_recv, 0, nrecv * sizeof(double)));
-    SPHY_CUDA(ctx, cudaMemset(ctx->p2p_flags, 0, (size_t)(world + 1) * sizeof(long long)));
+    SPHY_CUDA(ctx, cudaMemset(ctx->p2p_flags, 0, (size_t)(world + 3) * sizeof(long long)));
     SPHY_CUDA(ctx, cudaDeviceSynchronize());
     cudaIpcMemHandle_t h;
     SPHY_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->p2p_recv));
@@ -1128,27 +1221,10 @@ extern "C" int sphy_p2p_connect(sphy_ctx *ctx, int rank, int world, const unsign
     SPHY_CUDA(ctx, cudaMemcpy(ctx->p2p_peer_recv, recv, sizeof(double *) * world, cudaMemcpyHostToDevice));
     SPHY_CUDA(ctx, cudaMemcpy(ctx->p2p_peer_flags, flags, sizeof(long long *) * world, cudaMemcpyHostToDevice));
     ctx->p2p_rank = rank;
-    ctx->p2p_step = 0;
     return SPHY_OK;
 }
 
-extern "C" int sphy_route_scan_exchange_p2p(sphy_ctx *ctx, int ncomp, const double *send_dev, int32_t stride, void *stream)
-{
-    if (!ctx || !send_dev || ncomp < 1 || ncomp > ROUTE_MAX_COMP) return SPHY_E_INVALID;
-    if (!ctx->p2p_peer_recv) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_route_scan_exchange_p2p before sphy_p2p_connect");
-    const int64_t count = (int64_t)ncomp * stride;
-    if (count > ctx->p2p_pitch) SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_route_scan_exchange_p2p: %lld values exceed the buffer pitch", (long long)count);
-    cudaStream_t st = (cudaStream_t)stream;
-    const long long step = ++ctx->p2p_step;
-    const int parity = (int)((step - 1) & 1);
-    k_p2p_push<<<ctx->p2p_world, 256, 0, st>>>(send_dev, (int)count, ctx->p2p_peer_recv, ctx->p2p_peer_flags, ctx->p2p_rank,
-                                               ctx->p2p_world, ctx->p2p_pitch, parity, step);
-    k_p2p_wait<<<1, 64, 0, st>>>(ctx->p2p_flags, ctx->p2p_world, step, reinterpret_cast<int *>(ctx->p2p_flags + ctx->p2p_world));
-    SPHY_LAUNCH_CHECK(ctx);
-    return SPHY_OK;
-}
-
-// 1 if a bounded wait of sphy_route_scan_exchange_p2p gave up since the last call (synchronises the stream)
+// 1 if a bounded flag wait of the peer-memory exchange gave up since the last call (synchronises the stream)
 extern "C" int sphy_p2p_timed_out(sphy_ctx *ctx, void *stream)
 {
     if (!ctx || !ctx->p2p_flags) return 0;

@@ -327,6 +327,18 @@ __global__ void k_module_op(const __grid_constant__ OpArgs a)
         case SPHY_OP_SUBPERCOLATION: r0 = sf::SubPercolation(I(0), I(1), I(2), I(3), I(4)); break;     // subwater subfield e_sub gw gwsat
         case SPHY_OP_SUBDRAINAGE: r0 = sf::SubDrainage(I(0), I(1), I(2), I(3), I(4), I(5)); break;     // subwater subfield subsat drainvel subdrainage e_sub
         case SPHY_OP_GWRECHARGE: r0 = sf::GroundWaterRecharge(I(0), I(1), I(2) + I(3)); break;         // e_delta gwrecharge subperc glacperc
+        case SPHY_OP_ADV_BLEND: {                      // advanced_routing.ROUT, advanced_routing.py:31-33: the recession blend [m3/day]
+            // in: accufractionflux  qold[m3/s]  qout[m3/day]  QFRAC  kx  (1-kx) as REAL4 (NaN: kx is a map, form it per cell)
+            const float omk = I(5) == I(5) ? I(5) : 1.0f - I(4);
+            r0 = I(3) == 0.0f ? I(2) : omk * I(0) + ((I(1) * 24.0f) * 3600.0f) * I(4);
+        } break;
+        case SPHY_OP_ADV_FINISH: {                     // advanced_routing.py:34-38
+            // in: Q[m3/day]  upstream(ldd, Q)  QFRAC  sres  qout        out: sres  Q[m3/s]  Qin
+            const float qin = I(2) == 0.0f ? I(1) : 0.0f;
+            r0 = (I(3) - I(4)) + qin;
+            r1 = I(0) / 86400.0f;
+            r2 = qin;
+        } break;
         case SPHY_OP_BASEFLOW: r0 = sf::BaseFlow(I(0), I(1), I(2), I(3), I(4)); break;                 // gw baser gwrecharge basethresh e_alpha
         case SPHY_OP_HLEVEL: r0 = sf::HLevel(I(0), I(1), I(2), I(3)); break;                           // Hgw e_alpha gwrecharge h_den
         default: break;

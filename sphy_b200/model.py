@@ -208,8 +208,7 @@ class SphyModel:
     def close(self):
         if getattr(self, "_ctx", None):
             torch.cuda.synchronize(self.device)
-            if getattr(self, "_mg_p2p", False) and self.lib.sphy_p2p_timed_out(self._ctx, self._stream()):
-                raise RuntimeError("a peer-memory confluence exchange timed out: discharges of this run are not valid")
+            self.check_exchange()
             if self._owns_ctx:
                 self.lib.sphy_ctx_destroy(self._ctx)
             self._ctx = None
@@ -217,8 +216,16 @@ class SphyModel:
     def __del__(self):
         try:
             self.close()
+        except RuntimeError:
+            raise                          # a timed-out confluence exchange must not pass silently (Python reports it)
         except Exception:
             pass
+
+    def check_exchange(self):
+        """Raise if a peer-memory confluence exchange gave up waiting for a peer since the last check (synchronises)."""
+        if getattr(self, "_mg_p2p", False) and self.lib.sphy_p2p_timed_out(self._ctx, self._stream()):
+            raise RuntimeError("a peer-memory confluence exchange timed out: discharges of this run are not valid "
+                               "(the trunk cells of the affected steps hold NaN)")
 
     def _ck(self, rc, what):
         _lib.check(self.lib, self._ctx, rc, what)
@@ -535,19 +542,8 @@ class SphyModel:
         self.SubWater = self._state(self._init_value("SOIL_INIT", "SubWater", self.SubField))
         self.CapRise = self._state(self._init_value("SOIL_INIT", "CapRise"))
         self.RootDrain = self._state(self._init_value("SOIL_INIT", "RootDrain"))
-        if self.GroundFLAG == 1:                                                               # groundwater.py:61-86
-            self.GwRecharge = self._state(self._init_value("GROUNDW_INIT", "GwRecharge"))
-            self.BaseR = self._state(self._init_value("GROUNDW_INIT", "BaseR"))
-            self.Gw = self._state(self._init_value("GROUNDW_INIT", "Gw"))
-            h0 = self._init_value("GROUNDW_INIT", "H_gw")
-            parts = (self.RootDepthFlat, self.SubDepthFlat, self.GwDepth, h0)
-            if any(isinstance(x, np.ndarray) for x in parts):
-                a = [x if isinstance(x, np.ndarray) else f32(x) for x in parts]
-                hg = np.maximum((a[0] + a[1] + a[2]) / f32(1000) - a[3], f32(0)).astype(np.float32)
-            else:
-                hg = f32(max((parts[0] + parts[1] + parts[2]) / 1000 - parts[3], 0))
-            self.H_gw = self._state(hg)
-            self.SubDrain = None
+        if self.GroundFLAG == 1:
+            self.groundwater.initial(self, None, cfg)                                          # groundwater.py:61-86
         else:
             self.SubDrain = self._state(self._init_value("SOIL_INIT", "SubDrain"))
             self.BaseR = self._full(0.0)
@@ -563,18 +559,11 @@ class SphyModel:
         if self.GlacFLAG == 1:
             self._glacier_initial()
         self._zeros = self._full(0.0)
-        if self.RoutFLAG == 1 or self.ResFLAG == 1 or self.LakeFLAG == 1:                      # routing.py:42-66
-            self.QRAold = self._state(self._init_value("ROUT_INIT", "QRA_init", 0.0))
-            self.RA_FLAG = {}
-            for c in COMPONENTS:
-                v = self._init_value("ROUT_INIT", c + "RA_init")
-                self.RA_FLAG[c] = v is not None
-                if v is not None:
-                    setattr(self, c + "RAold", self._state(v))
         if self.LakeFLAG == 1 or self.ResFLAG == 1:
-            self._reslake_initial()
-            for c in COMPONENTS:          # advanced_routing.initial: every component flag ends up False (quirk Q9)
-                self.RA_FLAG[c] = False
+            self.advanced_routing.initial(self, None, cfg)                                     # advanced_routing.py:51-130
+            self._reslake_initial()                                                            # lakes / reservoirs .init + .initial
+        elif self.RoutFLAG == 1:
+            self.routing.initial(self, None, cfg)                                              # routing.py:42-66
         self.waterbalanceTot = self._full(0.0) if self.diagnostics else None
         # per-step outputs (device maps)
         self.TotR = self._full(0.0)
@@ -1307,6 +1296,8 @@ class SphyModel:
                                      self._station_buf.data_ptr(), st), "sphy_sample")
             self.tss["QallRAtot"].append(self._station_buf[: len(self.station_ids)].clone())
         self.timestep += 1
+        if self.world > 1 and (self.timestep % 32 == 0 or self.report is not None):
+            self.check_exchange()          # before anything of this step leaves the device (reports, every 32 steps otherwise)
         if self.report is not None:
             self.report.step()
         self.curdate = self.curdate + datetime.timedelta(days=1)
@@ -1379,11 +1370,10 @@ class SphyModel:
         if getattr(self, "_mg_p2p", None) is None:
             self._mg_p2p = self._p2p_connect()
         self._ck(self.lib.sphy_route_scan_begin(self._ctx, nc, srcp, dstp, self._kx, C.c_float(self._one_m_kx),
-                                                self._mg_send.data_ptr(), self._mg_stride, st), "sphy_route_scan_begin")
-        if self._mg_p2p:                           # stores into the peers' buffers over NVLink + flags, no collective call
-            self._ck(self.lib.sphy_route_scan_exchange_p2p(self._ctx, nc, self._mg_send.data_ptr(), self._mg_stride, st),
-                     "sphy_route_scan_exchange_p2p")
-            gathered = None
+                                                None if self._mg_p2p else self._mg_send.data_ptr(), self._mg_stride, st),
+                 "sphy_route_scan_begin")
+        if self._mg_p2p:                           # the publishing blocks stored into the peers' buffers over NVLink and raised
+            gathered = None                        # their flags; the trunk kernel waits for the peers' flags: no collective call
         else:
             dist.all_gather_into_tensor(self._mg_recv.view(-1), self._mg_send.view(-1))
             gathered = self._mg_recv.data_ptr()

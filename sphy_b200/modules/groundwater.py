@@ -29,8 +29,20 @@ def init(self, pcr, config):
 
 
 def initial(self, pcr, config):
-    """groundwater.py:61-86 (SphyModel.initial performs it together with the other states)."""
-    raise NotImplementedError("use SphyModel.initial(): the groundwater states are created with the other state maps")
+    """groundwater.py:61-86: GwRecharge, BaseR, Gw and the groundwater table height H_gw from the cfg values or maps."""
+    f32 = np.float32
+    self.GwRecharge = self._state(self._init_value("GROUNDW_INIT", "GwRecharge"))
+    self.BaseR = self._state(self._init_value("GROUNDW_INIT", "BaseR"))
+    self.Gw = self._state(self._init_value("GROUNDW_INIT", "Gw"))
+    h0 = self._init_value("GROUNDW_INIT", "H_gw")
+    parts = (self.RootDepthFlat, self.SubDepthFlat, self.GwDepth, h0)
+    if any(isinstance(x, np.ndarray) for x in parts):
+        a = [x if isinstance(x, np.ndarray) else f32(x) for x in parts]
+        hg = np.maximum((a[0] + a[1] + a[2]) / f32(1000) - a[3], f32(0)).astype(np.float32)
+    else:
+        hg = f32(max((parts[0] + parts[1] + parts[2]) / 1000 - parts[3], 0))
+    self.H_gw = self._state(hg)
+    self.SubDrain = None
 
 
 def dynamic(self, pcr, ActSubPerc, GlacPerc):

@@ -35,8 +35,15 @@ def init(self, pcr, config):
 
 
 def initial(self, pcr, config):
-    """routing.py:42-66 (performed inside SphyModel.initial)."""
-    raise NotImplementedError("use SphyModel.initial(): QRAold and the component states are created with the other state maps")
+    """routing.py:42-66: initial routed discharge and, for every `<comp>RA_init` given in the cfg, the component state."""
+    from ..model import COMPONENTS
+    self.QRAold = self._state(self._init_value("ROUT_INIT", "QRA_init", 0.0))
+    self.RA_FLAG = {}
+    for c in COMPONENTS:
+        v = self._init_value("ROUT_INIT", c + "RA_init")
+        self.RA_FLAG[c] = v is not None
+        if v is not None:
+            setattr(self, c + "RAold", self._state(v))
 
 
 def dynamic(self, pcr, TotR):

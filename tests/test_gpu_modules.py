@@ -134,3 +134,88 @@ def test_routing_rout_signature(env):
     same(got, want)
     got_scan = routing.ROUT(None, env["dev"](q[m.cell_order]), env["dev"](old[m.cell_order]), None, 0.971).cpu().numpy()
     assert np.allclose(got_scan, want, rtol=1e-5, atol=1e-12)
+
+
+@pytest.fixture(scope="module")
+def lake_env():
+    """A catchment with simple + advanced reservoirs and lakes (BASELINE config 3 physics in miniature) next to its oracle port."""
+    import torch
+    from oracle.sphy_port import PortInputs, PortModel
+    from sphy_b200 import synth
+    from sphy_b200.model import CatchmentSource, SphyModel
+    cat = synth.make_catchment(nrows=200, ncols=240, seed=7, cellsize=1000.0, reservoirs=True, lakes=True, n_res_simple=6, n_res_adv=4,
+                               n_lakes=5, nsteps=6, start=datetime.date(2001, 5, 1),
+                               params=dict(SubWater=470.0, RootDepthFlat=150.0, Pscale=2.5))
+    tmp = tempfile.mkdtemp(prefix="sphy_lake_")
+    cfg = cat.write_inputs(os.path.join(tmp, "in"), os.path.join(tmp, "out"))
+    model = SphyModel(cfg, CatchmentSource(cat), route_method="levels")
+    model.initial()
+    inp = PortInputs(cat)
+    port = PortModel(inp)
+    g = inp.lddst.gather
+    for t in range(1, 4):                                     # a few days so that storages and discharges are not the initial ones
+        port.dynamic({k: g(v) for k, v in cat.forcing(t).items()})
+        model.dynamic()
+    torch.cuda.synchronize()
+    yield dict(model=model, port=port, inp=inp, cat=cat, torch=torch)
+    model.close()
+
+
+def test_lake_and_reservoir_function_signatures(lake_env):
+    """lakes.UpdateLakeHStore / QLake(self, pcr, LakeLevel) and reservoirs.QSimple / QAdv / QRes(self, pcr) as callable
+    functions with the reference's signatures (modules/lakes.py:28-158, modules/reservoirs.py:26-86), bit-exact against the
+    port's restatement at the structure cells."""
+    m, port, inp = lake_env["model"], lake_env["port"], lake_env["inp"]
+    order = m.cell_order
+    pos = np.empty(m.n, np.int64)
+    pos[order] = np.arange(m.n)                                # canonical cell -> device index
+    same(m.StorRES, port.StorRES[order])
+    lake_cells, res_cells = pos[inp.lake["cells"]], pos[inp.res["cells"]]
+    level, stor = m.lakes.UpdateLakeHStore(m, None, None)
+    same(stor, port.StorRES[order])
+    want_level = port._lakefun(inp.lake, "HS", port.StorRES[inp.lake["cells"]])
+    same(level[lake_env["torch"].from_numpy(lake_cells).cuda()], want_level)
+    outside = np.ones(m.n, bool)
+    outside[lake_cells] = False
+    assert np.isnan(level.cpu().numpy()[outside]).all()        # MV outside the lakes, like the reference's lookups on LakeID
+    q = m.lakes.QLake(m, None, level).cpu().numpy()
+    assert bit_equal(q[lake_cells], port.QLake()).all() and (q[outside] == 0).all()
+    port.curdate = m.curdate                                   # reservoirs.QAdv reads the day of the year
+    m._doy = int(m.curdate.timetuple().tm_yday)
+    qres = m.reservoirs.QRes(m, None).cpu().numpy()
+    assert bit_equal(qres[res_cells], port.QRes()).all()
+    func = inp.res["func"]
+    qs, qa = m.reservoirs.QSimple(m, None).cpu().numpy()[res_cells], m.reservoirs.QAdv(m, None).cpu().numpy()[res_cells]
+    assert bit_equal(qs[func == 1], port.QRes()[func == 1]).all() and np.isnan(qs[func != 1]).all()
+    assert bit_equal(qa[func == 2], port.QRes()[func == 2]).all() and np.isnan(qa[func != 2]).all()
+
+
+def test_advanced_routing_rout_signature(lake_env):
+    """advanced_routing.ROUT(self, pcr, rvolume, qold, qout, sres) with externally supplied maps (modules/advanced_routing.py:27-38)
+    against the same arithmetic restated with the oracle's accufractionflux / upstream."""
+    m, inp, torch = lake_env["model"], lake_env["inp"], lake_env["torch"]
+    st = inp.lddst
+    order = m.cell_order
+    rng = np.random.default_rng(5)
+    f32 = np.float32
+    cut = m.QFRAC.cpu().numpy() == 0                           # device order
+    rv = (rng.gamma(0.8, 5e4, m.n)).astype(f32)
+    qold = rng.uniform(0, 30, m.n).astype(f32)
+    qout = np.where(cut, rng.uniform(0, 5e5, m.n), 0).astype(f32)
+    sres = np.where(cut, rng.uniform(1e6, 5e7, m.n), 0).astype(f32)
+    d = lambda a: torch.from_numpy(a).cuda()  # noqa: E731
+    sres_n, q, qin = m.advanced_routing.ROUT(m, None, d(rv), d(qold), d(qout), d(sres))
+    canon = lambda a: a_canon(a, order)  # noqa: E731
+    kx = f32(m._kx.value)
+    acc = st.accuflux(canon(rv), canon(m.QFRAC.cpu().numpy()))
+    qd = np.where(canon(cut), canon(qout), f32(m._one_m_kx) * acc + (canon(qold) * f32(24) * f32(3600)) * kx).astype(f32)
+    want_qin = np.where(canon(cut), st.upstream(qd), f32(0)).astype(f32)
+    same(q, (qd / f32(24 * 3600))[order])
+    same(qin, want_qin[order])
+    same(sres_n, (canon(sres) - canon(qout) + want_qin)[order])
+
+
+def a_canon(a, order):
+    out = np.empty_like(a)
+    out[order] = a
+    return out
