@@ -276,6 +276,16 @@ int sphy_sed_reservoir_route(sphy_ctx *ctx, const sphy_sedres *r, const float *s
 /* K1 alone does not need the LDD: declare the number of active cells directly */
 int sphy_set_ncells(sphy_ctx *ctx, int64_t n);
 
+/* CUDA-graph replay of a step: the only per-day kernel arguments of sphy_wb_step are the day-of-year scalars of
+ * hargreaves.extrarad (hargreaves.py:25-34).  sphy_day_scalars evaluates them on the host exactly as the reference does
+ * (Python double -> REAL4 -> libm double -> REAL4) into out5 = {k0*dr, sin/cos/tan(delta), 0.0023*0.408}; with a device
+ * block installed (5 floats, caller-owned; NULL uninstalls) the Ra table kernel reads them from there and ignores
+ * `day_of_year`, so a captured graph stays valid for any day (SPHY_RA_TABLE or SPHY_WB_ETREF_INPUT only). */
+int sphy_day_scalars(int day_of_year, float k0, float *out5);
+int sphy_set_day_block(sphy_ctx *ctx, const float *dev5);
+/* block_dev[0..5) = table_dev[*counter_dev][0..5); ++*counter_dev -- the head of a replayable step: the day advances on the
+ * device, so the host never rewrites memory that a queued step still has to read */
+int sphy_day_table_step(sphy_ctx *ctx, const float *table_dev, int n_rows, int *counter_dev, float *block_dev, void *stream);
 int sphy_wb_step(sphy_ctx *ctx, const sphy_wb_params *p, const sphy_wb_state *s, const sphy_wb_forcing *f,
                  const sphy_wb_out *o, int day_of_year, void *stream);
 

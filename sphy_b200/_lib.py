@@ -146,6 +146,9 @@ SYMBOLS = {
     "sphy_sed_reservoir_route": (C.c_int, [P, C.POINTER(SedRes), P, P, P, P, P, P]),
     "sphy_glac_report": (C.c_int, [P, C.c_int32, P, P, P, C.c_int32, P, P, P, P]),
     "sphy_veg_step": (C.c_int, [P, C.POINTER(WbParams), C.POINTER(Veg), C.c_int, P]),
+    "sphy_day_scalars": (C.c_int, [C.c_int, C.c_float, C.POINTER(C.c_float)]),
+    "sphy_set_day_block": (C.c_int, [P, P]),
+    "sphy_day_table_step": (C.c_int, [P, P, C.c_int, P, P, P]),
     "sphy_wb_step": (C.c_int, [P, C.POINTER(WbParams), C.POINTER(WbState), C.POINTER(WbForcing), C.POINTER(WbOut),
                                C.c_int, P]),
     "sphy_glac_step": (C.c_int, [P, C.POINTER(GlacTable), P, P, C.c_float, C.c_float, C.POINTER(GlacOut), P]),

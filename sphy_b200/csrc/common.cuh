@@ -93,6 +93,7 @@ struct sphy_ctx {
     float *acc = nullptr;          // [ROUTE_MAX_COMP][n] accumulated flux in routing order
     float *qsorted = nullptr;      // scratch [ROUTE_MAX_COMP][n]
     float *ra_table = nullptr;     // per-day Ra by latitude class
+    const float *day_block = nullptr;   // caller-owned device copy of the day-of-year scalars (sphy_set_day_block), or NULL
     int32_t ra_table_cap = 0;
     float *tmp_n[4] = {nullptr, nullptr, nullptr, nullptr};
     bool qout_zeroed = false;

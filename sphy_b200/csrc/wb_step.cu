@@ -15,6 +15,27 @@ __global__ void k_ra_table(const float *__restrict__ lat_deg, int n, DayScalars 
     ra[u] = extrarad(sinl, cosl, tanl, d);
 }
 
+// the same with the day scalars read from a device block (sphy_set_day_block): nothing in the launch depends on the day,
+// so a CUDA graph of the step can be replayed for any day
+__global__ void k_ra_table_dev(const float *__restrict__ lat_deg, int n, const DayScalars *__restrict__ dp, float *__restrict__ ra)
+{
+    int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n) return;
+    const DayScalars d = *dp;
+    float latrad = lat_deg[u] * 0.017453292519943295f;
+    float sinl = (float)sin((double)latrad), cosl = (float)cos((double)latrad), tanl = (float)tan((double)latrad);
+    ra[u] = extrarad(sinl, cosl, tanl, d);
+}
+
+__global__ void k_day_select(const float *__restrict__ table, int n_rows, int *counter, float *__restrict__ block)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    int t = *counter;
+    if (t >= n_rows) t = n_rows - 1;
+    for (int k = 0; k < 5; ++k) block[k] = table[(size_t)t * 5 + k];
+    *counter = t + 1;
+}
+
 __global__ void k_map_unary(int op, const float *__restrict__ in, float *__restrict__ out, int64_t n)
 {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -51,6 +72,30 @@ static DayScalars day_scalars(int doy, float k0)
     d.tan_delta = (float)tan((double)delta);
     d.hg_c = (float)(0.0023 * 0.408);
     return d;
+}
+
+extern "C" int sphy_day_scalars(int day_of_year, float k0, float *out5)
+{
+    if (!out5) return SPHY_E_INVALID;
+    const DayScalars d = day_scalars(day_of_year, k0);
+    out5[0] = d.k0dr; out5[1] = d.sin_delta; out5[2] = d.cos_delta; out5[3] = d.tan_delta; out5[4] = d.hg_c;
+    return SPHY_OK;
+}
+
+extern "C" int sphy_day_table_step(sphy_ctx *ctx, const float *table_dev, int n_rows, int *counter_dev, float *block_dev, void *stream)
+{
+    if (!ctx || !table_dev || n_rows < 1 || !counter_dev || !block_dev) return SPHY_E_INVALID;
+    k_day_select<<<1, 32, 0, (cudaStream_t)stream>>>(table_dev, n_rows, counter_dev, block_dev);
+    SPHY_LAUNCH_CHECK(ctx);
+    return SPHY_OK;
+}
+
+extern "C" int sphy_set_day_block(sphy_ctx *ctx, const float *dev5)
+{
+    if (!ctx) return SPHY_E_INVALID;
+    static_assert(sizeof(DayScalars) == 5 * sizeof(float), "day block layout");
+    ctx->day_block = dev5;
+    return SPHY_OK;
 }
 
 extern "C" int sphy_map_unary(sphy_ctx *ctx, int op, const float *in, float *out, int64_t count, void *stream)
@@ -116,9 +161,15 @@ extern "C" int sphy_wb_step(sphy_ctx *ctx, const sphy_wb_params *p, const sphy_w
             if (rc != SPHY_OK) return rc;
             ctx->ra_table_cap = p->n_lat_unique;
         }
-        k_ra_table<<<div_up(p->n_lat_unique, 128), 128, 0, st>>>(p->lat_unique_deg, p->n_lat_unique, a.d, ctx->ra_table);
+        if (ctx->day_block)
+            k_ra_table_dev<<<div_up(p->n_lat_unique, 128), 128, 0, st>>>(p->lat_unique_deg, p->n_lat_unique,
+                                                                        reinterpret_cast<const DayScalars *>(ctx->day_block), ctx->ra_table);
+        else
+            k_ra_table<<<div_up(p->n_lat_unique, 128), 128, 0, st>>>(p->lat_unique_deg, p->n_lat_unique, a.d, ctx->ra_table);
         SPHY_LAUNCH_CHECK(ctx);
         a.ra_table = ctx->ra_table;
+    } else if (ra == SPHY_RA_CELL && ctx->day_block) {
+        SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_wb_step: a device day block (sphy_set_day_block) needs SPHY_RA_TABLE or ETref input");
     }
     const bool diag = s->waterbalanceTot || o->ETref || o->ETact || o->ActETact || o->Infil || o->Rain || o->RootPerc ||
                       o->SubPerc || o->wbal || o->ETOpenWater || o->Precip;

@@ -119,6 +119,67 @@ def _table_col(rows, col):
 
 
 # ----------------------------------------------------------------------------------------------
+class StepGraph:
+    """CUDA graphs of the device step of one model or of a whole list of models sharing a context (ensemble members).
+
+    Nothing in a captured step may depend on the day through a kernel argument.  The day-of-year scalars of the Ra table
+    therefore come from a device table with one row per remaining day of the run (evaluated on the host like the reference
+    does, sphy_day_scalars); a one-thread kernel at the head of every device step copies the row of the current day into
+    the block the Ra kernel reads and advances a device-side day counter -- the host never touches memory a queued step
+    still has to read."""
+
+    @staticmethod
+    def state(model):
+        ndays = max((model.enddate.date() - model.curdate.date()).days + 1, 1) + 400      # + slack for runs past `enddate`
+        k0 = float(getattr(model._wbP, "k0", 0.0))
+        rows = np.zeros((ndays, 5), np.float32)
+        out = (C.c_float * 5)()
+        cache = {}
+        for i in range(ndays):
+            doy = julian(model.curdate + datetime.timedelta(days=i))
+            if doy not in cache:
+                model._ck(model.lib.sphy_day_scalars(doy, C.c_float(k0), out), "sphy_day_scalars")
+                cache[doy] = list(out)
+            rows[i] = cache[doy]
+        table = torch.from_numpy(rows).to(model.device)
+        block = torch.zeros(8, dtype=torch.float32, device=model.device)
+        counter = torch.zeros(1, dtype=torch.int32, device=model.device)
+        model._ck(model.lib.sphy_set_day_block(model._ctx, block.data_ptr()), "sphy_set_day_block")
+        return {"graphs": {}, "seen": set(), "table": table, "block": block, "counter": counter, "ndays": ndays, "model": model,
+                "steps": 0}
+
+    @staticmethod
+    def run(st, models, forcings, doy, capture=True):
+        """One device step of every model: eagerly the first time a set of forcing buffers is seen (or when `capture` is
+        off), from a graph after that."""
+        lead = st["model"]
+        st["steps"] += 1
+        if st["steps"] > st["ndays"]:
+            raise RuntimeError("the day table of the CUDA-graph mode is exhausted: call enable_graphs() again")
+        key = tuple(v.data_ptr() for f in forcings for _, v in sorted(f.items()))
+
+        def body():
+            lead._ck(lead.lib.sphy_day_table_step(lead._ctx, st["table"].data_ptr(), st["ndays"], st["counter"].data_ptr(),
+                                                  st["block"].data_ptr(), lead._stream()), "sphy_day_table_step")
+            for m, f in zip(models, forcings):
+                m._device_step(f, doy)
+
+        g = st["graphs"].get(key) if capture else None
+        if g is not None:
+            g.replay()
+        elif not capture or key not in st["seen"]:
+            st["seen"].add(key)
+            body()                                   # first sight: run eagerly (lazy allocations, attribute opt-ins happen here)
+        else:
+            torch.cuda.synchronize(lead.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                body()
+            st["graphs"][key] = g
+            g.replay()                               # capturing executes nothing
+
+
+# ----------------------------------------------------------------------------------------------
 class SphyModel:
     def __init__(self, cfg, maps: MapSource, device="cuda:0", route_method="scan", diagnostics=False,
                  collect_tss=True, cell_order="dfs", rank=0, world=1, share_from=None, reporting=False, write_outputs=False,
@@ -601,6 +662,9 @@ class SphyModel:
         self._copy_stream = None
         self._staging = None
         self._prof = None
+        self._graphs = None
+        if os.environ.get("SPHY_GRAPHS", "0") == "1":
+            self.enable_graphs(True)
 
     # -- glacier.init + glacier.initial, modules/glacier.py:52-252 ------------------------------------
     def _glacier_initial(self):
@@ -1230,9 +1294,25 @@ class SphyModel:
 
     # -- dynamic(), sphy.py:719-1263 ------------------------------------------------------------------------
     def dynamic(self):
+        f, doy = self._pre_step()
+        if self._graphs is not None:
+            StepGraph.run(self._graphs, [self], [f], doy, capture=self._graph_ok())
+        else:
+            self._device_step(f, doy)
+        return self._post_step()
+
+    def _pre_step(self):
+        """Host bookkeeping of one step and the day's forcing as compact device maps."""
         self.counter += 1
-        lib, ctx, st = self.lib, self._ctx, self._stream()
         f = self._ingest(self.counter)
+        doy = julian(self.curdate)
+        self._doy = doy
+        return f, doy
+
+    def _device_step(self, f, doy):
+        """Everything of one daily step that runs on the device (sphy.py:732-1240): [vegetation] -> [glaciers] -> fused
+        vertical water balance -> routing -> [erosion / sediment transport].  No host synchronisation."""
+        lib, ctx, st = self.lib, self._ctx, self._stream()
         F = _lib.WbForcing()
         F.prec, F.tavg = f["prec"].data_ptr(), f["tavg"].data_ptr()
         self._prec_ptr = F.prec
@@ -1240,8 +1320,6 @@ class SphyModel:
             F.etref = f["etref"].data_ptr()
         else:
             F.tmin, F.tmax = f["tmin"].data_ptr(), f["tmax"].data_ptr()
-        doy = julian(self.curdate)
-        self._doy = doy
         self._prec_raw = f["prec"]
         for k, (_, last) in self._series.items():                                              # sphy.py:824-830, 992-1000
             if last is not None and f.get(k) is not None and f[k] is not last:
@@ -1291,9 +1369,12 @@ class SphyModel:
             G = self.mmf.dynamic(self, None, f["prec"], self.Q if self.Q is not None else self.TotR)
             if self.SedTransFLAG == 1:
                 self.sediment_transport.dynamic_mmf(self, None, None, None, G)
+
+    def _post_step(self):
+        """Time series at the stations, reporting, the date."""
         if self.collect_tss and self.Q is not None and len(self.station_ids):
-            self._ck(lib.sphy_sample(ctx, self.Q.data_ptr(), self._station_cells.data_ptr(), len(self.station_ids),
-                                     self._station_buf.data_ptr(), st), "sphy_sample")
+            self._ck(self.lib.sphy_sample(self._ctx, self.Q.data_ptr(), self._station_cells.data_ptr(), len(self.station_ids),
+                                          self._station_buf.data_ptr(), self._stream()), "sphy_sample")
             self.tss["QallRAtot"].append(self._station_buf[: len(self.station_ids)].clone())
         self.timestep += 1
         if self.world > 1 and (self.timestep % 32 == 0 or self.report is not None):
@@ -1302,6 +1383,26 @@ class SphyModel:
             self.report.step()
         self.curdate = self.curdate + datetime.timedelta(days=1)
         return self.Q if self.Q is not None else self.TotR
+
+    # -- CUDA-graph replay of the device step ------------------------------------------------------------------
+    def enable_graphs(self, on=True):
+        """Replay the device part of dynamic() from a CUDA graph (one graph per set of forcing buffers, captured the second
+        time the set is seen).  Launch-bound runs -- small catchments, ensembles, a basin split over many GPUs -- then cost
+        one graph launch per step instead of a chain of Python -> ctypes -> kernel launches.  The only per-day kernel
+        arguments, the day-of-year scalars of the Ra table, come from a device table indexed by a device-side day counter;
+        the peer-exchange step counter already lives on the device.  Steps the graph cannot express (glaciers,
+        vegetation, lakes/reservoirs, sediment, map series, profiling, the NCCL exchange) keep running eagerly."""
+        if on and not (self.ETREF_FLAG == 1 or self._wbP.ra_mode == _lib.RA_TABLE) or self.DynVegFLAG == 1:
+            return                                   # per-cell latitude maps / the vegetation kernel take the day as an argument
+        if not on and self._graphs is not None:
+            self._ck(self.lib.sphy_set_day_block(self._ctx, None), "sphy_set_day_block")
+        self._graphs = StepGraph.state(self) if on else None
+
+    def _graph_ok(self):
+        return (self.DynVegFLAG != 1 and self.GlacFLAG != 1 and self.ResFLAG != 1 and self.LakeFLAG != 1 and self.SedFLAG != 1
+                and not self._series and self._prof is None and self.ETOpenWaterFLAG != 1
+                and (self.ETREF_FLAG == 1 or self._wbP.ra_mode == _lib.RA_TABLE)
+                and (self.world == 1 or getattr(self, "_mg_p2p", None) is True))
 
     def _glacier_step(self, tavg, prec):
         """glacier.dynamic (modules/glacier.py:256-498) on the raw forcing maps of the day -> per-cell aggregates."""
