@@ -226,6 +226,16 @@ def default_ref_procs():
     return max(1, min(avail, 32))
 
 
+def pcraster_probe():
+    """SURVEY 8c, last row: if a real PCRaster build happens to be importable on this box, say so -- it would pin the
+    accumulation arithmetic the oracle can only assume (A1).  It never is in this image; the answer is recorded either way."""
+    try:
+        import pcraster  # noqa: F401
+        return {"importable": True, "version": getattr(pcraster, "__version__", "unknown")}
+    except Exception as e:                                    # noqa: BLE001
+        return {"importable": False, "why": type(e).__name__}
+
+
 def run_reference(args):
     size = args.ref_size
     steps = max(1, args.steps)
@@ -239,7 +249,7 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.size), "sample": sample},
         "cpu_baseline": {"value": rate, "unit": "Mcell-timesteps/s", "cores": procs, "kind": "port", "sample": sample,
-                         "host_cores_available": os.cpu_count(),
+                         "host_cores_available": os.cpu_count(), "pcraster": pcraster_probe(),
                          "note": "PCRaster and SPHY are single-threaded, so every core runs its own sub-catchment; PCRaster is not "
                                  "installable here, so this is the NumPy-shim restatement of the reference algorithm, not PCRaster"},
         "e2e": {"value": rate, "unit": "Mcell-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -368,7 +378,7 @@ def main():
         cpu = {"value": rate, "unit": "Mcell-timesteps/s", "cores": procs, "kind": "port",
                "sample": f"{procs} independent {args.ref_size}x{args.ref_size} sub-catchments (one per host core), 3 daily steps each, "
                          f"oracle port (NumPy float32, one pass per operation)",
-               "host_cores_available": os.cpu_count()}
+               "host_cores_available": os.cpu_count(), "pcraster": pcraster_probe()}
 
     # my kernels per step: k_ra_table, k_wb_step, k_sample + routing (3 scan kernels, or one launch per plan segment)
     # (scan: main, tile-total scan, crossing cells + publish, drift, apply for the trunk cells)

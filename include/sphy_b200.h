@@ -121,8 +121,10 @@ typedef struct {
      * h_den = REAL4(800*YieldGw*alphaGw) */
     sphy_param gw_sat, base_thresh, e_delta, e_alpha, h_den;
     sphy_param seepage;             /* GroundFLAG == 0 (sphy.py:1004) */
-    /* snow (modules/snow.py:84-90) */
-    float tcrit, snow_sc, ddfs, snow_f, one_minus_snow_f;
+    /* snow (modules/snow.py:84-90): scalar-or-map like the reference reads them (readmap first, getfloat otherwise);
+     * one_minus_snow_f = REAL4(1 - SnowF) for a cfg float (Python-double subtraction), formed per cell for a map */
+    sphy_param tcrit, snow_sc, ddfs, snow_f;
+    float one_minus_snow_f;
     float melt_cos[24];             /* REAL4(cos(3.1415*h/12)), h = 1..24 (snow.py:30) */
 } sphy_wb_params;
 
@@ -286,6 +288,8 @@ int sphy_set_day_block(sphy_ctx *ctx, const float *dev5);
 /* block_dev[0..5) = table_dev[*counter_dev][0..5); ++*counter_dev -- the head of a replayable step: the day advances on the
  * device, so the host never rewrites memory that a queued step still has to read */
 int sphy_day_table_step(sphy_ctx *ctx, const float *table_dev, int n_rows, int *counter_dev, float *block_dev, void *stream);
+/* day_of_year < 0: the context's per-day Ra table (SPHY_RA_TABLE) is already up to date -- ensemble members sharing a
+ * context and a latitude map compute it once per day, not once per member. */
 int sphy_wb_step(sphy_ctx *ctx, const sphy_wb_params *p, const sphy_wb_state *s, const sphy_wb_forcing *f,
                  const sphy_wb_out *o, int day_of_year, void *stream);
 
@@ -328,6 +332,10 @@ int sphy_glac_report(sphy_ctx *ctx, int32_t n_glac, const int32_t *row_ptr, cons
 int sphy_route_step(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm, float *const *q_state, sphy_param kx,
                     float one_minus_kx /* REAL4(1-kx) when kx is a scalar: Python-double subtraction, routing.py:28 */,
                     int method, void *stream);
+/* The same routing (SPHY_ROUTE_SCAN) for up to 8 runoff maps with a recession coefficient each -- the members of a
+ * forcing/parameter ensemble on one basin (BASELINE config 5): one pass reads the index structures once for all of them. */
+int sphy_route_step_members(sphy_ctx *ctx, int nmaps, const float *const *runoff_mm, float *const *q_state,
+                            const sphy_param *kx, const float *one_minus_kx, void *stream);
 /* Optional per-phase device timing of SPHY_ROUTE_SCAN (what bench.py's second roofline entry is measured with): while
  * enabled every routing step records four CUDA events on its stream; sphy_route_profile_read synchronises on the last
  * one and returns the mean milliseconds per step of {main pass, tile totals + crossing cells, trunk cells (incl. the

@@ -31,7 +31,7 @@ class WbParams(C.Structure):
         ("paved_frac", SphyParam),
         ("gw_sat", SphyParam), ("base_thresh", SphyParam), ("e_delta", SphyParam), ("e_alpha", SphyParam),
         ("h_den", SphyParam), ("seepage", SphyParam),
-        ("tcrit", C.c_float), ("snow_sc", C.c_float), ("ddfs", C.c_float), ("snow_f", C.c_float),
+        ("tcrit", SphyParam), ("snow_sc", SphyParam), ("ddfs", SphyParam), ("snow_f", SphyParam),
         ("one_minus_snow_f", C.c_float), ("melt_cos", C.c_float * 24),
     ]
 
@@ -153,6 +153,7 @@ SYMBOLS = {
                                C.c_int, P]),
     "sphy_glac_step": (C.c_int, [P, C.POINTER(GlacTable), P, P, C.c_float, C.c_float, C.POINTER(GlacOut), P]),
     "sphy_route_step": (C.c_int, [P, C.c_int, C.POINTER(P), C.POINTER(P), SphyParam, C.c_float, C.c_int, P]),
+    "sphy_route_step_members": (C.c_int, [P, C.c_int, C.POINTER(P), C.POINTER(P), C.POINTER(SphyParam), C.POINTER(C.c_float), P]),
     "sphy_set_partition": (C.c_int, [P, C.c_int64, C.c_int64, P]),
     "sphy_trunk_select": (C.c_int, [P, C.c_int32, C.c_int64, C.c_int, P, C.POINTER(C.c_int64), P]),
     "sphy_trunk_export": (C.c_int, [P, C.c_char_p, P, C.c_size_t, P]),

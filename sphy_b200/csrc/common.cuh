@@ -100,6 +100,11 @@ struct sphy_ctx {
     bool sweep_attr_set = false, sweep_rec_ready = false;
     int32_t *sweep_rec = nullptr;   // route.cu: static donor records of the tail levels
     int32_t sweep_rec_k0 = 0;
+    // route.cu: the narrow end of the level order as heavy-path chains (k_sweep_chains)
+    bool chains_ready = false;
+    int32_t chain_k0 = 0, n_chains = 0, chain_level0 = 0;
+    int64_t n_chain_cells = 0;
+    int32_t *chain_start = nullptr, *chain_k = nullptr, *chain_cell = nullptr, *chain_don = nullptr;
     double *cut_work = nullptr;    // scan path with lakes/reservoirs: range sums of the cut cells
     int cut_work_cap = 0;
     int32_t *cut_ptr = nullptr;    // per-tile ranges of the cut-cell list

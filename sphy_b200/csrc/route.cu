@@ -12,6 +12,8 @@
 // All routed components (total + up to 6 fractions, routing.py:81-101) share one sweep: the index
 // structures are read once.
 #include <cstdio>
+
+#include <cub/cub.cuh>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -59,6 +61,13 @@ __device__ __forceinline__ CellIn load_cell_in(const SweepArgs &a, int c, int32_
     ci.qold = (a.mode == MODE_PLAIN || a.mode == MODE_CAPACITY) ? 0.0f : a.qstate[c][i];
     ci.qout = (a.mode == MODE_ADV && ci.fr == 0.0f) ? __ldg(a.qout_dense + i) : 0.0f;
     return ci;
+}
+
+// what leaves a cell given what arrived (REAL8 sum): the REAL4 flux handed to the receiver
+__device__ __forceinline__ float flux_of(int mode, bool has_frac, double tot, float fr)
+{
+    if (mode == MODE_CAPACITY) return tot < (double)fr ? (float)tot : fr;
+    return has_frac ? (float)((double)fr * tot) : (float)tot;
 }
 
 // finish a cell: fraction cut, store flux, recession blend
@@ -351,6 +360,160 @@ __global__ void __launch_bounds__(WARPS * 32) k_sweep_tail(const __grid_constant
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+// ---- the narrow end of the level order as heavy-path chains --------------------------------------------------------------
+// Level widths never increase, so from the first level of at most CHAIN_MAX cells on (`level0`, routing position k0) the
+// rest of the basin -- 17 000 of the 18 000 levels of the 10 000 x 10 000 basin, but only 0.5 % of its cells -- is a
+// forest of at most CHAIN_MAX "chains": every cell of level > level0 continues the chain of its HEAVY donor, the donor
+// that sets its level (lowest routing position among the donors of level - 1); its other donors either lie below k0
+// (final before the walk starts) or are the last cells of other chains.  One warp walks one chain in blocks of 32 cells:
+//   parallel part    lane j gathers what cell j receives apart from its heavy donor: own material + the fluxes of the
+//                    other donors (a donor inside the tail is awaited: its flux slot holds a sentinel until written);
+//   sequential part  32 steps of  tot = lateral_j + flux_{j-1};  flux_j = REAL4(tot)  -- the only truly serial work of
+//                    the whole sweep: one shuffle-fed float64 add and one conversion per cell, every lane redundantly;
+//   parallel part    lane j finishes cell j (store, recession blend) exactly like the level kernels do.
+// The REAL8 sum of a cell adds the same terms as everywhere else (order does not matter: assumption A1), so the result
+// stays bit-identical with the oracle -- a level costs ~40 cycles of latency instead of a CTA barrier and 300 instructions.
+constexpr int CHAIN_MAX = 1024;
+constexpr unsigned FLUX_PENDING = 0xFFFFFFFFu;      // no arithmetic produces this NaN payload
+
+struct ChainArgs {
+    int32_t n_chains, k0;
+    const int32_t *start;      // [n_chains + 1] first slot of every chain
+    const int32_t *k;          // [slots] routing position
+    const int32_t *cell;       // [slots] cell (device order)
+    const int32_t *don;        // [slots][8] routing positions of the donors other than the heavy one, -1 padded
+};
+
+__device__ __forceinline__ float load_flux_wait(const float *p)
+{
+    unsigned v;
+    for (;;) {
+        asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+        if (v != FLUX_PENDING) break;
+        __nanosleep(40);
+    }
+    return __uint_as_float(v);
+}
+
+constexpr int CHAIN_WARPS = 4;
+
+__global__ void __launch_bounds__(CHAIN_WARPS * 32) k_sweep_chains(const __grid_constant__ SweepArgs a, const __grid_constant__ ChainArgs ch)
+{
+    const int lane = threadIdx.x & 31;
+    const int32_t w = blockIdx.x * CHAIN_WARPS + (threadIdx.x >> 5);
+    if (w >= ch.n_chains) return;
+    const int32_t s0 = __ldg(ch.start + w), len = __ldg(ch.start + w + 1) - s0;
+    const bool has_frac = a.frac != nullptr;
+    double prev[ROUTE_MAX_COMP];
+#pragma unroll
+    for (int c = 0; c < ROUTE_MAX_COMP; ++c) prev[c] = 0.0;
+    // static record of this lane's cell in the next block (one hop ahead of the flux gathers)
+    int32_t nk = 0, ni = 0, nd[8];
+    auto hop1 = [&](int32_t b) {
+        const bool v = b + lane < len;
+        const int32_t s = s0 + b + lane;
+        nk = v ? __ldg(ch.k + s) : 0;
+        ni = v ? __ldg(ch.cell + s) : 0;
+        const int4 d0 = v ? __ldg(reinterpret_cast<const int4 *>(ch.don + (int64_t)s * 8)) : make_int4(-1, -1, -1, -1);
+        const int4 d1 = v ? __ldg(reinterpret_cast<const int4 *>(ch.don + (int64_t)s * 8) + 1) : make_int4(-1, -1, -1, -1);
+        nd[0] = d0.x; nd[1] = d0.y; nd[2] = d0.z; nd[3] = d0.w; nd[4] = d1.x; nd[5] = d1.y; nd[6] = d1.z; nd[7] = d1.w;
+    };
+    hop1(0);
+    for (int32_t b = 0; b < len; b += 32) {
+        const int cnt = min(32, len - b);
+        const bool valid = lane < cnt;
+        const int32_t k = nk, i = ni;
+        int32_t d[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = nd[j];
+        if (b + 32 < len) hop1(b + 32);
+        // ---- parallel: lateral inflow of every cell of the block
+        double lat[ROUTE_MAX_COMP];
+        CellIn ci[ROUTE_MAX_COMP];
+        for (int c = 0; c < a.ncomp; ++c) {
+            double s = 0.0;
+            if (valid) {
+                s = (double)material(a, c, i);
+                ci[c] = load_cell_in(a, c, i);
+                const float *acc = a.acc + (int64_t)c * a.n;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (d[j] >= 0) s += (double)(d[j] >= ch.k0 ? load_flux_wait(acc + d[j]) : acc[d[j]]);
+            }
+            lat[c] = s;
+        }
+        // ---- sequential: the chain itself
+        double mytot[ROUTE_MAX_COMP];
+        for (int j = 0; j < cnt; ++j) {
+            for (int c = 0; c < a.ncomp; ++c) {
+                const double lj = __shfl_sync(0xffffffffu, lat[c], j);
+                const float frj = (has_frac || a.mode == MODE_CAPACITY) ? __shfl_sync(0xffffffffu, ci[c].fr, j) : 1.0f;
+                const double tot = lj + prev[c];
+                if (lane == j) mytot[c] = tot;
+                prev[c] = (double)flux_of(a.mode, has_frac, tot, frj);
+            }
+        }
+        // ---- parallel: store, blend
+        if (valid)
+            for (int c = 0; c < a.ncomp; ++c) finish(a, c, k, i, mytot[c], ci[c]);
+    }
+}
+
+// chain construction (once): heavy donor of every tail position, successor links
+__global__ void k_chain_links(const int32_t *__restrict__ level_ptr, int32_t nlevels, const int32_t *__restrict__ dpos_ptr,
+                              const int32_t *__restrict__ dpos, int32_t k0, int64_t n, int32_t *__restrict__ heavy, int32_t *__restrict__ next)
+{
+    const int64_t k = k0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    // level of routing position k: last l with level_ptr[l] <= k
+    int32_t lo = 0, hi = nlevels;
+    while (hi - lo > 1) {
+        const int32_t mid = (lo + hi) >> 1;
+        if (level_ptr[mid] <= k) lo = mid; else hi = mid;
+    }
+    const int32_t below_b = lo > 0 ? level_ptr[lo - 1] : 0, below_e = level_ptr[lo];      // positions of level - 1
+    int32_t h = -1;
+    for (int32_t q = dpos_ptr[k]; q < dpos_ptr[k + 1]; ++q) {
+        const int32_t dp = dpos[q];
+        if (dp >= k0 && dp >= below_b && dp < below_e && (h < 0 || dp < h)) h = dp;
+    }
+    heavy[k - k0] = h;
+    if (h >= 0) next[h - k0] = (int32_t)k;
+}
+
+// one thread per chain (they start at the positions of level0): number the cells along the chain
+__global__ void k_chain_walk(const int32_t *__restrict__ next, int32_t k0, int32_t n_chains, int32_t *__restrict__ chain_of,
+                             int32_t *__restrict__ idx_in, int32_t *__restrict__ len)
+{
+    const int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chains) return;
+    int32_t k = k0 + c, l = 0;
+    while (k >= 0) {
+        chain_of[k - k0] = c;
+        idx_in[k - k0] = l++;
+        k = next[k - k0];
+    }
+    len[c] = l;
+}
+
+__global__ void k_chain_tables(const int32_t *__restrict__ order, const int32_t *__restrict__ dpos_ptr, const int32_t *__restrict__ dpos,
+                               const int32_t *__restrict__ heavy, const int32_t *__restrict__ chain_of, const int32_t *__restrict__ idx_in,
+                               const int32_t *__restrict__ start, int32_t k0, int64_t n, int32_t *__restrict__ ck, int32_t *__restrict__ ccell,
+                               int32_t *__restrict__ cdon)
+{
+    const int64_t k = k0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int32_t s = start[chain_of[k - k0]] + idx_in[k - k0];
+    ck[s] = (int32_t)k;
+    ccell[s] = order[k];
+    int j = 0;
+    for (int32_t q = dpos_ptr[k]; q < dpos_ptr[k + 1]; ++q) {
+        const int32_t dp = dpos[q];
+        if (dp != heavy[k - k0] && j < 8) cdon[(int64_t)s * 8 + j++] = dp;
+    }
+    for (; j < 8; ++j) cdon[(int64_t)s * 8 + j] = -1;
+}
+
 __global__ void k_upstream(const float *__restrict__ x, const int32_t *__restrict__ don_ptr, const int32_t *__restrict__ don_idx,
                            int64_t n, float *__restrict__ out)
 {
@@ -363,9 +526,69 @@ __global__ void k_upstream(const float *__restrict__ x, const int32_t *__restric
 
 }  // namespace
 
+// one-time construction of the chain tables (synchronises)
+static int build_chains(sphy_ctx *ctx, cudaStream_t st)
+{
+    ctx->chains_ready = true;
+    ctx->n_chains = 0;
+    const char *env = getenv("SPHY_SWEEP_CHAINS");              // 0 = keep the level-by-level kernels for the narrow levels
+    if (env && env[0] == '0') return SPHY_OK;
+    const int nlv = (int)ctx->h_level_ptr.size() - 1;
+    int l0 = -1;
+    for (int l = 0; l < nlv; ++l)
+        if (ctx->h_level_ptr[l + 1] - ctx->h_level_ptr[l] <= CHAIN_MAX) { l0 = l; break; }
+    if (l0 < 0) return SPHY_OK;
+    const int32_t k0 = ctx->h_level_ptr[l0];
+    const int64_t T = ctx->n - k0;
+    const int32_t nch = ctx->h_level_ptr[l0 + 1] - k0;
+    if (T <= 0 || nch <= 0 || T > ((int64_t)1 << 26)) return SPHY_OK;
+    int32_t *heavy = nullptr, *next = nullptr, *chain_of = nullptr, *idx_in = nullptr, *len = nullptr;
+    void *tmp = nullptr;
+    size_t tb = 0;
+    cudaError_t e = cudaSuccess;
+#define FK(call) do { if (e == cudaSuccess) e = (call); } while (0)
+    FK(cudaMalloc(&heavy, sizeof(int32_t) * T));
+    FK(cudaMalloc(&next, sizeof(int32_t) * T));
+    FK(cudaMalloc(&chain_of, sizeof(int32_t) * T));
+    FK(cudaMalloc(&idx_in, sizeof(int32_t) * T));
+    FK(cudaMalloc(&len, sizeof(int32_t) * (nch + 1)));
+    int rc = SPHY_OK;
+    if (e == cudaSuccess &&
+        ((rc = dev_alloc(ctx, &ctx->chain_start, (size_t)nch + 1)) || (rc = dev_alloc(ctx, &ctx->chain_k, (size_t)T)) ||
+         (rc = dev_alloc(ctx, &ctx->chain_cell, (size_t)T)) || (rc = dev_alloc(ctx, &ctx->chain_don, (size_t)T * 8)))) {
+        cudaFree(heavy); cudaFree(next); cudaFree(chain_of); cudaFree(idx_in); cudaFree(len);
+        return rc;
+    }
+    if (e == cudaSuccess) {
+        FK(cudaMemsetAsync(next, 0xFF, sizeof(int32_t) * T, st));
+        FK(cudaMemsetAsync(len + nch, 0, sizeof(int32_t), st));
+        k_chain_links<<<div_up(T, 256), 256, 0, st>>>(ctx->level_ptr, ctx->nlevels, ctx->dpos_ptr, ctx->dpos, k0, ctx->n, heavy, next);
+        k_chain_walk<<<div_up(nch, 128), 128, 0, st>>>(next, k0, nch, chain_of, idx_in, len);
+        FK(cub::DeviceScan::ExclusiveSum(nullptr, tb, len, ctx->chain_start, nch + 1, st));
+        FK(cudaMalloc(&tmp, tb));
+        FK(cub::DeviceScan::ExclusiveSum(tmp, tb, len, ctx->chain_start, nch + 1, st));
+        k_chain_tables<<<div_up(T, 256), 256, 0, st>>>(ctx->order, ctx->dpos_ptr, ctx->dpos, heavy, chain_of, idx_in, ctx->chain_start, k0,
+                                                      ctx->n, ctx->chain_k, ctx->chain_cell, ctx->chain_don);
+        FK(cudaGetLastError());
+        FK(cudaStreamSynchronize(st));
+    }
+#undef FK
+    cudaFree(heavy); cudaFree(next); cudaFree(chain_of); cudaFree(idx_in); cudaFree(len); cudaFree(tmp);
+    if (e != cudaSuccess) SPHY_FAIL(ctx, SPHY_E_CUDA, "build_chains: %s", cudaGetErrorString(e));
+    ctx->chain_k0 = k0;
+    ctx->chain_level0 = l0;
+    ctx->n_chains = nch;
+    ctx->n_chain_cells = T;
+    return SPHY_OK;
+}
+
 // run the level sweep described by `a` following the launch plan built in ldd_build.cu
 int route_levels_run(sphy_ctx *ctx, SweepArgs &a, cudaStream_t st)
 {
+    if (!ctx->chains_ready) {
+        int rc = build_chains(ctx, st);
+        if (rc != SPHY_OK) return rc;
+    }
     a.order = ctx->order;
     a.dpos_ptr = ctx->dpos_ptr;
     a.dpos = ctx->dpos;
@@ -439,7 +662,10 @@ int route_levels_run(sphy_ctx *ctx, SweepArgs &a, cudaStream_t st)
     bool warmed = false;
     const char *deep_env = getenv("SPHY_SWEEP_DEEP");           // 0 = the two-level pipeline for every narrow run
     const bool deep = !(deep_env && deep_env[0] == '0');
-    for (const SweepPlanSeg &seg : ctx->sweep_plan) {
+    const int32_t level_end = ctx->n_chains > 0 ? ctx->chain_level0 : (int32_t)ctx->h_level_ptr.size() - 1;   // chains take over here
+    for (SweepPlanSeg seg : ctx->sweep_plan) {
+        if (seg.first_level >= level_end) break;
+        if (seg.first_level + seg.n_levels > level_end) seg.n_levels = level_end - seg.first_level;
         if (!warmed && a.rec && ctx->h_level_ptr[seg.first_level] >= a.rec_k0) {     // the tail starts here
             k_sweep_warm<<<div_up((a.n - a.rec_k0) * 8, 256), 256, 0, st>>>(a);
             warmed = true;
@@ -456,6 +682,12 @@ int route_levels_run(sphy_ctx *ctx, SweepArgs &a, cudaStream_t st)
             if (a.ncomp == 1 && deep) k_sweep_tail<1><<<1, 32, 0, st>>>(a, seg.first_level, seg.n_levels);
             else k_sweep_narrow<32><<<1, 32, (size_t)2 * a.ncomp * 4 * sizeof(float), st>>>(a, seg.first_level, seg.n_levels);
         }
+    }
+    if (ctx->n_chains > 0) {
+        ChainArgs ch = {ctx->n_chains, ctx->chain_k0, ctx->chain_start, ctx->chain_k, ctx->chain_cell, ctx->chain_don};
+        for (int c = 0; c < a.ncomp; ++c)                      // flux slots of the tail: pending until a chain writes them
+            SPHY_CUDA(ctx, cudaMemsetAsync(a.acc + (int64_t)c * a.n + ctx->chain_k0, 0xFF, sizeof(float) * ctx->n_chain_cells, st));
+        k_sweep_chains<<<div_up(ctx->n_chains, CHAIN_WARPS), CHAIN_WARPS * 32, 0, st>>>(a, ch);
     }
     SPHY_LAUNCH_CHECK(ctx);
     return SPHY_OK;

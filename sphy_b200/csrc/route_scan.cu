@@ -56,8 +56,8 @@ struct ScanArgs {
     float *qday;                          // dense blended Q, m3/day (what upstream(ldd, Q) reads at the structures)
     const int32_t *cut_cell, *cut_ptr;    // cut cells (ascending) and their per-tile ranges
     const double *cut_corr;               // float64 material placed at each cut cell (see route_scan_run_adv)
-    sphy_param kx;
-    float one_m_kx;
+    sphy_param kxc[ROUTE_MAX_COMP];       // recession coefficient per routed map (ensemble members route together, each with its own kx)
+    float omkc[ROUTE_MAX_COMP];           // REAL4(1 - kx) when kx is a scalar
     double to_m3s;                        // mm/day -> m3/s: 0.001 * cellarea / 86400 (routing.py:26)
     int64_t n;
     int32_t ntiles;
@@ -147,14 +147,14 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_MIN_CTAS) k_scan_main(const
                     if (full) {
                         sz[b] = __ldg(reinterpret_cast<const int4 *>(szp + o));
                         q[b] = *reinterpret_cast<const float4 *>(qs + o);
-                        if (KXMAP) kxv[b] = __ldg(reinterpret_cast<const float4 *>(a.kx.map + tbase + o));
+                        if (KXMAP) kxv[b] = __ldg(reinterpret_cast<const float4 *>(a.kxc[c].map + tbase + o));
                     } else {
                         sz[b].x = o < len ? __ldg(szp + o) : 1;         q[b].x = o < len ? qs[o] : 0.0f;
                         sz[b].y = o + 1 < len ? __ldg(szp + o + 1) : 1; q[b].y = o + 1 < len ? qs[o + 1] : 0.0f;
                         sz[b].z = o + 2 < len ? __ldg(szp + o + 2) : 1; q[b].z = o + 2 < len ? qs[o + 2] : 0.0f;
                         sz[b].w = o + 3 < len ? __ldg(szp + o + 3) : 1; q[b].w = o + 3 < len ? qs[o + 3] : 0.0f;
                         if (KXMAP) {
-                            const float *kp = a.kx.map + tbase;
+                            const float *kp = a.kxc[c].map + tbase;
                             kxv[b].x = o < len ? __ldg(kp + o) : 0.0f;         kxv[b].y = o + 1 < len ? __ldg(kp + o + 1) : 0.0f;
                             kxv[b].z = o + 2 < len ? __ldg(kp + o + 2) : 0.0f; kxv[b].w = o + 3 < len ? __ldg(kp + o + 3) : 0.0f;
                         }
@@ -222,8 +222,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_MIN_CTAS) k_scan_main(const
                     auto cell = [&](int j, int32_t szj, float &qj, float kxj, double before, double own) {
                         const int el = o + j + szj - 1;                // last cell of the upstream range, tile-local
                         const bool inside = el < len;                  // else: crossing cell, left to k_scan_cross
-                        const float kx = KXMAP ? kxj : a.kx.value;
-                        const float omk = KXMAP ? 1.0f - kx : a.one_m_kx;
+                        const float kx = KXMAP ? kxj : a.kxc[c].value;
+                        const float omk = KXMAP ? 1.0f - kx : a.omkc[c];
                         double pe = own;                               // headwater cell: the range is the cell itself
                         if (inside && szj > 1) pe = Ls[ls_slot(el)];   // predicated load: fewer lanes, fewer bank conflicts
                         if (ADV) {
@@ -282,7 +282,7 @@ __device__ __forceinline__ void scan_cross_block(const ScanArgs &a, int32_t bloc
             pb[j] = ok[j] ? PB[k] : 0.0;
             pe[j] = ok[j] ? PE[k] : 0.0;
             qold[j] = ok[j] ? qs[r[j]] : 0.0f;
-            kx[j] = (ok[j] && a.kx.map) ? __ldg(a.kx.map + r[j]) : a.kx.value;
+            kx[j] = (ok[j] && a.kxc[c].map) ? __ldg(a.kxc[c].map + r[j]) : a.kxc[c].value;
         }
 #pragma unroll
         for (int j = 0; j < CROSS_ILP; ++j) {
@@ -290,7 +290,7 @@ __device__ __forceinline__ void scan_cross_block(const ScanArgs &a, int32_t bloc
             const int32_t ta = r[j] / SCAN_TILE, te = e[j] / SCAN_TILE;
             // suffix of the first tile + whole tiles in between (none for most crossing cells) + prefix of the last tile
             const double s = range_diff(tt[j], pb[j]) + (te > ta + 1 ? range_diff(X[te], X[ta + 1]) : 0.0) + pe[j];
-            const float omk = a.kx.map ? 1.0f - kx[j] : a.one_m_kx;
+            const float omk = a.kxc[c].map ? 1.0f - kx[j] : a.omkc[c];
             qs[r[j]] = blend(a, r[j], (float)s, qold[j], kx[j], omk);
         }
     }
@@ -474,8 +474,6 @@ __global__ void __launch_bounds__(256) k_trunk_apply(const __grid_constant__ Sca
     if (s >= t.m) return;
     const int64_t r = (int64_t)__ldg(t.cell + s) - t.part_begin;
     if (r < 0 || r >= a.n) return;                             // another rank's cell
-    const float kx = a.kx.map ? __ldg(a.kx.map + r) : a.kx.value;
-    const float omk = a.kx.map ? 1.0f - kx : a.one_m_kx;
     const bool drift = t.trunk[s] != 0;
     const int32_t l = __ldg(t.last + s);
     // a peer that never delivered its block: make the failure visible in the data instead of routing stale prefixes
@@ -485,6 +483,8 @@ __global__ void __launch_bounds__(256) k_trunk_apply(const __grid_constant__ Sca
         double D = 0.0;
         if (drift) D = (BP[l / TRUNK_BLOCK] + Gl[l]) - (s > 0 ? BP[(s - 1) / TRUNK_BLOCK] + Gl[s - 1] : 0.0);
         const float f = (float)((double)(float)t.E[(int64_t)c * t.m + s] + D);
+        const float kx = a.kxc[c].map ? __ldg(a.kxc[c].map + r) : a.kxc[c].value;
+        const float omk = a.kxc[c].map ? 1.0f - kx : a.omkc[c];
         float *qs = a.qstate[c];
         qs[r] = dead ? nanf("") : omk * f + kx * qs[r];        // routing.py:28
     }
@@ -683,8 +683,10 @@ static int scan_prepare(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm,
     a.tile_excl = ctx->scan_excl;
     a.n_pub = ctx->n_pub;
     a.pub_e = ctx->pub_e;
-    a.kx = kx;
-    a.one_m_kx = one_m_kx;
+    for (int c = 0; c < ncomp; ++c) {
+        a.kxc[c] = kx;
+        a.omkc[c] = one_m_kx;
+    }
     a.to_m3s = (0.001 * (double)ctx->cellarea) / 86400.0;
     a.n = ctx->n;
     a.ntiles = ctx->n_tiles;
@@ -737,10 +739,10 @@ static int scan_launch_local(sphy_ctx *ctx, ScanArgs &a, cudaStream_t st, bool p
     }
     prof_mark(ctx, st);
     if (a.adv) {
-        if (a.kx.map) k_scan_main<true, true><<<grid, SCAN_THREADS, SCAN_SMEM, st>>>(a);
+        if (a.kxc[0].map) k_scan_main<true, true><<<grid, SCAN_THREADS, SCAN_SMEM, st>>>(a);
         else k_scan_main<true, false><<<grid, SCAN_THREADS, SCAN_SMEM, st>>>(a);
     } else {
-        if (a.kx.map) k_scan_main<false, true><<<grid, SCAN_THREADS, SCAN_SMEM, st>>>(a);
+        if (a.kxc[0].map) k_scan_main<false, true><<<grid, SCAN_THREADS, SCAN_SMEM, st>>>(a);
         else k_scan_main<false, false><<<grid, SCAN_THREADS, SCAN_SMEM, st>>>(a);
     }
     prof_mark(ctx, st);
@@ -822,6 +824,40 @@ int route_scan_run(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm, floa
     int rc2 = scan_launch_local(ctx, a, st, trunk);
     if (rc2 != SPHY_OK) return rc2;
     if (trunk && (rc = trunk_finish(ctx, a, ctx->sl_V, (int64_t)ncomp * ctx->sl_stride, st)) != SPHY_OK) return rc;
+    prof_mark(ctx, st);
+    SPHY_LAUNCH_CHECK(ctx);
+    return SPHY_OK;
+}
+
+// several runoff maps with a recession coefficient each: ensemble members sharing one LDD route in one pass, so the index
+// stream (sub_size, the crossing and trunk lists) is read once for all of them
+extern "C" int sphy_route_step_members(sphy_ctx *ctx, int nmaps, const float *const *runoff_mm, float *const *q_state,
+                                       const sphy_param *kx, const float *one_minus_kx, void *stream)
+{
+    if (!ctx || !runoff_mm || !q_state || !kx || !one_minus_kx || nmaps < 1 || nmaps > ROUTE_MAX_COMP) return SPHY_E_INVALID;
+    if (!ctx->ldd_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_route_step_members before sphy_ldd_build");
+    if (ctx->partitioned) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_route_step_members is not available on a partitioned context");
+    for (int c = 0; c < nmaps; ++c) {
+        if (!runoff_mm[c] || !q_state[c]) SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_route_step_members: map %d is NULL", c);
+        if ((kx[c].map != nullptr) != (kx[0].map != nullptr))
+            SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_route_step_members: kx must be a map for every member or for none");
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    ScanArgs a;
+    int rc = scan_prepare(ctx, nmaps, runoff_mm, q_state, kx[0], one_minus_kx[0], st, a);
+    if (rc != SPHY_OK) return rc;
+    for (int c = 0; c < nmaps; ++c) {
+        a.kxc[c] = kx[c];
+        a.omkc[c] = one_minus_kx[c];
+    }
+    if (ctx->sl_plan && (rc = trunk_prepare(ctx, nmaps, st)) != SPHY_OK) return rc;
+    if (ctx->sl_plan) {
+        a.send = ctx->sl_V;
+        a.stride = ctx->sl_stride;
+    }
+    const bool trunk = ctx->sl_plan && ctx->sl_n > 0;
+    if ((rc = scan_launch_local(ctx, a, st, trunk)) != SPHY_OK) return rc;
+    if (trunk && (rc = trunk_finish(ctx, a, ctx->sl_V, (int64_t)nmaps * ctx->sl_stride, st)) != SPHY_OK) return rc;
     prof_mark(ctx, st);
     SPHY_LAUNCH_CHECK(ctx);
     return SPHY_OK;

@@ -243,6 +243,15 @@ __device__ __forceinline__ void wb_cells(const WbArgs &a, int64_t i, float4 *pf 
         if (!USOIL) seep = L::par(p.seepage, i);
         sub_drainvel = L::par(p.sub_drainvel, i);
     }
+    // snow parameters: scalars in every cfg the reference ships; maps are honoured (modules/snow.py:84-90)
+    V4 tcrit_m, snow_sc_m, ddfs_m, snow_f_m;
+    if (SNOW) {
+        if (p.tcrit.map) tcrit_m = L::in(p.tcrit.map, i);
+        if (p.snow_sc.map) snow_sc_m = L::in(p.snow_sc.map, i);
+        if (p.ddfs.map) ddfs_m = L::in(p.ddfs.map, i);
+        if (p.snow_f.map) snow_f_m = L::in(p.snow_f.map, i);
+    }
+#define PS(par) (p.par.map ? par##_m.v[j] : p.par.value)
     const bool pws = (p.flags & SPHY_WB_PWS) != 0;
     if (pws) pmap = L::par(p.pmap, i);
     if (INFIL) paved = L::par(p.paved_frac, i);
@@ -277,12 +286,13 @@ __device__ __forceinline__ void wb_cells(const WbArgs &a, int64_t i, float4 *pf 
         float ss = ss0, sws = 0.0f;
         if (SNOW) {
             sws = SnowWatStore.v[j];
-            const float Snow = Temp >= p.tcrit ? 0.0f : Precip;
-            Rain = Temp < p.tcrit ? 0.0f : Precip;
-            const float PotSnowMelt = TempMax < 0.0f ? 0.0f : sf::PotSnowMelt(Temp, TempMax, p.ddfs, p.melt_cos);
+            const float tcrit = PS(tcrit);
+            const float Snow = Temp >= tcrit ? 0.0f : Precip;
+            Rain = Temp < tcrit ? 0.0f : Precip;
+            const float PotSnowMelt = TempMax < 0.0f ? 0.0f : sf::PotSnowMelt(Temp, TempMax, PS(ddfs), p.melt_cos);
             const float ActSnowMelt = sf::ActSnowMelt(ss, PotSnowMelt);
             ss = sf::SnowStoreUpdate(ss, Snow, ActSnowMelt, Temp, sws);
-            const float MaxSWS = sf::MaxSnowWatStorage(p.snow_sc, ss);
+            const float MaxSWS = sf::MaxSnowWatStorage(PS(snow_sc), ss);
             const float OldSWS = sws;
             sws = sf::SnowWatStorage(TempMax, MaxSWS, sws, ActSnowMelt, Rain);          // tested on Tmax (quirk Q5)
             OldTotalSnowStore = TotalSnowStore.v[j];
@@ -290,8 +300,9 @@ __device__ __forceinline__ void wb_cells(const WbArgs &a, int64_t i, float4 *pf 
             if (glac_in) tss = tss + g_tss.v[j];
             SnowR = sf::SnowR(sws, MaxSWS, ActSnowMelt, Rain, OldSWS, SnowFrac);
             if (glac_in) SnowR = SnowR + g_snowr.v[j];
-            SnowSoil = SnowR * p.snow_f;
-            SnowR = SnowR * p.one_minus_snow_f;
+            const float snow_f = PS(snow_f);
+            SnowSoil = SnowR * snow_f;
+            SnowR = SnowR * (p.snow_f.map ? 1.0f - snow_f : p.one_minus_snow_f);
             if (has_ow) SnowR = SnowR * omow;
         }
         const float ETpot = sf::ETpot(ETref, PV(kc, kc));                  // ET.py:24-26
@@ -425,6 +436,7 @@ __device__ __forceinline__ void wb_cells(const WbArgs &a, int64_t i, float4 *pf 
         }
     }
 #undef PV
+#undef PS
     // ---- stores ----------------------------------------------------------------------------------------
     L::out(a.s.RootWater, i, RW);
     L::out(a.s.SubWater, i, SW);

@@ -161,7 +161,9 @@ extern "C" int sphy_wb_step(sphy_ctx *ctx, const sphy_wb_params *p, const sphy_w
             if (rc != SPHY_OK) return rc;
             ctx->ra_table_cap = p->n_lat_unique;
         }
-        if (ctx->day_block)
+        if (doy < 0)
+            ;                                                   // another member of the ensemble refreshed this context's table today
+        else if (ctx->day_block)
             k_ra_table_dev<<<div_up(p->n_lat_unique, 128), 128, 0, st>>>(p->lat_unique_deg, p->n_lat_unique,
                                                                         reinterpret_cast<const DayScalars *>(ctx->day_block), ctx->ra_table);
         else

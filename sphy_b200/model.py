@@ -98,6 +98,21 @@ def name_t(t):
     return (s[:8] + "." + s[8:])[4:]
 
 
+def _clone_mask(clone):
+    """Active cells of the clone map: non-zero and not a missing value.  PCRaster's MV is NaN for REAL4, the most negative
+    value for INT4 (-2147483648), 255 for UINT1 and -128 for INT1 -- all of which `astype(bool)` would read as active."""
+    clone = np.asarray(clone)
+    if clone.dtype == bool:
+        return clone
+    if np.issubdtype(clone.dtype, np.floating):
+        return np.isfinite(clone) & (clone != 0)
+    mv = {np.dtype(np.int32): -2147483648, np.dtype(np.uint8): 255, np.dtype(np.int8): -128, np.dtype(np.int64): -2147483648}
+    mask = clone != 0
+    if clone.dtype in mv:
+        mask &= clone != mv[clone.dtype]
+    return mask
+
+
 def julian(date):
     """utilities/timecalc.py:24-29"""
     return date.toordinal() - datetime.date(date.year, 1, 1).toordinal() + 1
@@ -149,7 +164,7 @@ class StepGraph:
                 "steps": 0}
 
     @staticmethod
-    def run(st, models, forcings, doy, capture=True):
+    def run(st, models, forcings, doy, capture=True, step_fn=None):
         """One device step of every model: eagerly the first time a set of forcing buffers is seen (or when `capture` is
         off), from a graph after that."""
         lead = st["model"]
@@ -161,8 +176,11 @@ class StepGraph:
         def body():
             lead._ck(lead.lib.sphy_day_table_step(lead._ctx, st["table"].data_ptr(), st["ndays"], st["counter"].data_ptr(),
                                                   st["block"].data_ptr(), lead._stream()), "sphy_day_table_step")
-            for m, f in zip(models, forcings):
-                m._device_step(f, doy)
+            if step_fn is not None:
+                step_fn(models, forcings, doy)
+            else:
+                for m, f in zip(models, forcings):
+                    m._device_step(f, doy)
 
         g = st["graphs"].get(key) if capture else None
         if g is not None:
@@ -233,7 +251,7 @@ class SphyModel:
         # -- clone, sphy.py:141-145
         clone = np.asarray(self._readmap(config.get("GENERAL", "mask")))
         self.nrows, self.ncols = clone.shape
-        self.clone_mask = clone.astype(bool)
+        self.clone_mask = _clone_mask(clone)
         self.cellsize = float(config.get("GENERAL", "cellsize")) if config.has_option("GENERAL", "cellsize") else None
         if self.cellsize is None:
             self.cellsize = float(getattr(maps, "cellsize", 0) or 0) or None
@@ -533,10 +551,11 @@ class SphyModel:
         else:
             self.ETref = cfg.get("ETREF", "ETref")
         if self.SnowFLAG == 1:                                                                 # snow.py:84-90
-            for k in ("Tcrit", "SnowSC", "DDFS", "SnowF", "SnowCth"):
+            for k in ("Tcrit", "SnowSC", "DDFS", "SnowF", "SnowCth"):                          # map first, float otherwise
                 v = self._scalar_or_map("SNOW", k)
-                if isinstance(v, np.ndarray):
-                    raise NotImplementedError(f"[SNOW] {k} as a map is not supported yet")
+                if isinstance(v, np.ndarray) and v.ndim > 0 and self.GlacFLAG == 1:
+                    # glacier.py:285-372 mixes these with pandas table columns: a map cannot work there in the reference either
+                    raise ValueError(f"[SNOW] {k} as a map cannot be combined with GlacFLAG = 1 (modules/glacier.py:285)")
                 setattr(self, k, v)
             if self.ETREF_FLAG == 1:
                 raise ValueError("SnowFLAG = 1 needs ETREF_FLAG = 0: TempMax is only defined on that branch "
@@ -689,8 +708,11 @@ class SphyModel:
         seg_cell = cell[first].astype(np.int32)
         for k in ("DDFG", "DDFDG", "GlacF"):
             v = self._scalar_or_map("GLACIER", k)
-            if isinstance(v, np.ndarray):
-                raise NotImplementedError(f"[GLACIER] {k} as a map is not supported yet")
+            if isinstance(v, np.ndarray) and v.ndim > 0:
+                # glacier.dynamic multiplies these with pandas table columns (modules/glacier.py:28-48,374-420): a PCRaster
+                # map cannot be used there in the reference either
+                raise ValueError(f"[GLACIER] {k} must be a number: the reference applies it to the fragment table, not to a map")
+            v = float(v)
             setattr(self, k, v)
         lapse = pd.read_csv(os.path.join(self.inpath, cfg.get("GLACIER", "TLapse")), header=None, index_col=0, sep=" ",
                             skipinitialspace=True)
@@ -1100,8 +1122,10 @@ class SphyModel:
                 P.seepage = pr(self.SeePage)
             P.sub_drainvel = pr(self.SubDrainVel)
         if self.SnowFLAG == 1:
-            P.tcrit, P.snow_sc, P.ddfs = float(f32(self.Tcrit)), float(f32(self.SnowSC)), float(f32(self.DDFS))
-            P.snow_f, P.one_minus_snow_f = float(f32(self.SnowF)), float(f32(1 - self.SnowF))
+            P.tcrit, P.snow_sc, P.ddfs, P.snow_f = pr(self.Tcrit), pr(self.SnowSC), pr(self.DDFS), pr(self.SnowF)
+            if not P.snow_f.map:                               # a cfg float: Python-double subtraction, then REAL4 (snow.py:182)
+                sf_ = self.SnowF
+                P.one_minus_snow_f = (float(f32(1) - f32(P.snow_f.value)) if isinstance(sf_, np.ndarray) else float(f32(1 - sf_)))
             for h in range(1, 25):                                                             # snow.py:30 (3.1415)
                 P.melt_cos[h - 1] = float(f32(math.cos(float(f32(3.1415 * h / 12)))))
         if self.LakeFLAG == 1 and getattr(self, "_lake_update", None) is not None:
@@ -1234,8 +1258,13 @@ class SphyModel:
             self._fdev = {k: torch.empty(self.n, dtype=torch.float32, device=self.device) for k in keys}
         if self._forcing_host is not None:
             return self._ingest_host(counter, keys)
-        if self._staging is None:
-            self._staging = {k: torch.empty(self.n, dtype=torch.float32).pin_memory() for k in keys}
+        if self._staging is None:            # two pinned sets: the host may refill one while the other's upload is still queued
+            self._staging = [{k: torch.empty(self.n, dtype=torch.float32).pin_memory() for k in keys} for _ in range(2)]
+            self._staging_ev = [None, None]
+        slot = counter % 2
+        if self._staging_ev[slot] is not None:
+            self._staging_ev[slot].synchronize()               # the upload that last used this set has completed
+        staging = self._staging[slot]
         names = self._forcing_names(counter)
         out = dict(self._fdev)
         for k in keys:
@@ -1246,8 +1275,11 @@ class SphyModel:
                     raise
                 out.pop(k)                         # no map for this day: the previous one is kept (dynamic_veg.py:78-82, sphy.py:824-830)
                 continue
-            self._staging[k].numpy()[:] = src if self.full_raster else src[self.flat_active]
-            self._fdev[k].copy_(self._staging[k], non_blocking=True)
+            staging[k].numpy()[:] = src if self.full_raster else src[self.flat_active]
+            self._fdev[k].copy_(staging[k], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._staging_ev[slot] = ev
         return out
 
     def _ingest_host(self, counter, keys):
@@ -1280,6 +1312,8 @@ class SphyModel:
         slot = counter % 2
         if self._hready[slot] is None or self._hready[slot][0] != counter:
             upload(counter, slot)
+        if self._hready[slot] is None or self._hready[slot][0] != counter:
+            raise FileNotFoundError(f"no forcing for time step {counter}: the host forcing source has no entry for it")
         main.wait_event(self._hready[slot][1])
         buf, present = self._hbuf[slot], self._hready[slot][2]
         if compact:
@@ -1309,9 +1343,11 @@ class SphyModel:
         self._doy = doy
         return f, doy
 
-    def _device_step(self, f, doy):
+    def _device_step(self, f, doy, route=True, ra_table=True):
         """Everything of one daily step that runs on the device (sphy.py:732-1240): [vegetation] -> [glaciers] -> fused
-        vertical water balance -> routing -> [erosion / sediment transport].  No host synchronisation."""
+        vertical water balance -> routing -> [erosion / sediment transport].  No host synchronisation.  `route=False`
+        leaves plain routing to the caller (an Ensemble routes its members together); `ra_table=False` reuses the context's
+        per-day Ra table (computed by another member sharing the latitude map)."""
         lib, ctx, st = self.lib, self._ctx, self._stream()
         F = _lib.WbForcing()
         F.prec, F.tavg = f["prec"].data_ptr(), f["tavg"].data_ptr()
@@ -1348,8 +1384,8 @@ class SphyModel:
         if prof is not None:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             ev[0].record()
-        self._ck(lib.sphy_wb_step(ctx, C.byref(self._wbP), C.byref(self._wbS), C.byref(F), C.byref(self._wbO), doy, st),
-                 "sphy_wb_step")
+        self._ck(lib.sphy_wb_step(ctx, C.byref(self._wbP), C.byref(self._wbS), C.byref(F), C.byref(self._wbO),
+                                  doy if ra_table else -1, st), "sphy_wb_step")
         if prof is not None:
             ev[1].record()
         for fn in deferred:
@@ -1357,8 +1393,10 @@ class SphyModel:
         self.Q = None
         if self.LakeFLAG == 1 or self.ResFLAG == 1:                                            # sphy.py:1100-1104
             self.Q = self.advanced_routing.dynamic(self, None, None, self.config, self.TotR, None, None)
-        elif self.RoutFLAG == 1:                                                               # sphy.py:1107-1108
+        elif self.RoutFLAG == 1 and route:                                                     # sphy.py:1107-1108
             self.Q = self.routing.dynamic(self, None, self.TotR)
+        elif self.RoutFLAG == 1:
+            self.Q = self.QRAold
         if prof is not None:
             ev[2].record()
             prof["wb"].append((ev[0], ev[1]))

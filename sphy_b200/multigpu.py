@@ -221,6 +221,84 @@ def bench_main(args, rank, world):
 
 
 # ----------------------------------------------------------------------------------------------
+class Ensemble:
+    """The members of a forcing/parameter ensemble that live on one GPU (BASELINE config 5): independent SphyModels sharing
+    one context, i.e. one set of LDD structures.  One ensemble step runs every member's fused water-balance kernel and
+    then routes the members in groups of up to 8 maps per pass (sphy_route_step_members): sub_size, the crossing and the
+    trunk lists are read once per group instead of once per member.  With `graphs` the whole ensemble step -- a few hundred
+    launches -- is replayed from one CUDA graph, which removes the per-member Python / ctypes / launch chain that
+    otherwise bounds this workload."""
+
+    GROUP = _lib.ROUTE_MAX_COMP
+
+    def __init__(self, members, graphs=True):
+        from .model import StepGraph
+        if not members:
+            raise ValueError("an ensemble needs at least one member")
+        lead = members[0]
+        if any(m._ctx is not lead._ctx for m in members):
+            raise ValueError("ensemble members must share one context (share_from=)")
+        self.members = list(members)
+        # members route together when they use plain total-flow routing on the scan path with scalar or per-cell kx alike
+        self.grouped = all(m.RoutFLAG == 1 and m.ResFLAG != 1 and m.LakeFLAG != 1 and m.route_method == _lib.ROUTE_SCAN
+                           and m.world == 1 and not any(m.RA_FLAG.values()) and bool(m._kx.map) == bool(lead._kx.map)
+                           for m in members)
+        # members that share the latitude classes (same ETref mode) take the Ra table of the lead member
+        self.shared_ra = all(m.ETREF_FLAG == lead.ETREF_FLAG and m.DynVegFLAG != 1 and
+                             (m.ETREF_FLAG == 1 or (m._wbP.ra_mode == _lib.RA_TABLE and np.array_equal(m.Lat, lead.Lat)))
+                             for m in members)
+        self.streams = None
+        self.state = StepGraph.state(lead) if graphs and lead._graphs is None else lead._graphs
+        if graphs and self.state is None:
+            raise ValueError("this configuration cannot be replayed from a graph (per-cell latitude maps or dynamic vegetation)")
+
+    def dynamic(self):
+        from .model import StepGraph
+        pre = [m._pre_step() for m in self.members]
+        doy = pre[0][1]
+        if any(p[1] != doy for p in pre):
+            raise ValueError("ensemble members must be on the same date")
+        forcings = [p[0] for p in pre]
+        if self.state is not None:
+            StepGraph.run(self.state, self.members, forcings, doy, capture=all(m._graph_ok() for m in self.members),
+                          step_fn=self._device_step)
+        else:
+            self._device_step(self.members, forcings, doy)
+        return [m._post_step() for m in self.members]
+
+    def _device_step(self, models, forcings, doy):
+        import ctypes as C
+
+        import torch
+        lead = models[0]
+        # the members' water-balance kernels are independent: spread them over a few streams so that the drain of one
+        # overlaps the ramp-up of the next (inside a captured graph these become parallel branches)
+        if self.streams is None:
+            self.streams = [torch.cuda.Stream(device=lead.device) for _ in range(3)]
+        main = torch.cuda.current_stream(lead.device)
+        lead._device_step(forcings[0], doy, route=not self.grouped)
+        ready = torch.cuda.Event()
+        ready.record(main)                                     # the Ra table of the day is in place
+        for st in self.streams:
+            st.wait_event(ready)
+        for j, (m, f) in enumerate(zip(models[1:], forcings[1:])):
+            with torch.cuda.stream(self.streams[j % len(self.streams)] if self.grouped else main):
+                m._device_step(f, doy, route=not self.grouped, ra_table=not self.shared_ra)
+        for st in self.streams:
+            main.wait_stream(st)
+        if not self.grouped:
+            return
+        for g0 in range(0, len(models), self.GROUP):
+            grp = models[g0:g0 + self.GROUP]
+            k = len(grp)
+            src = (C.c_void_p * k)(*[m.TotR.data_ptr() for m in grp])
+            dst = (C.c_void_p * k)(*[m.QRAold.data_ptr() for m in grp])
+            kx = (_lib.SphyParam * k)(*[m._kx for m in grp])
+            omk = (C.c_float * k)(*[m._one_m_kx for m in grp])
+            lead._ck(lead.lib.sphy_route_step_members(lead._ctx, k, src, dst, kx, omk, lead._stream()), "sphy_route_step_members")
+
+
+# ----------------------------------------------------------------------------------------------
 def ensemble_main(args, rank, world):
     """BASELINE config 5: a forcing/parameter ensemble on the 2000 x 2000 basin, members sharded across the GPUs.
     Members are independent: no data-path collective (only the timing barrier / max-over-ranks)."""
@@ -265,9 +343,10 @@ def ensemble_main(args, rank, world):
     torch.cuda.synchronize()
     setup_s = time.time() - t_setup
 
+    ens = Ensemble(members, graphs=os.environ.get("SPHY_ENSEMBLE_GRAPHS", "1") == "1")
+
     def step_all():
-        for model in members:
-            model.dynamic()
+        ens.dynamic()
 
     for _ in range(max(args.warmup, 3)):
         step_all()
@@ -292,8 +371,10 @@ def ensemble_main(args, rank, world):
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"{total}-member forcing/parameter ensemble on the {size}x{size} 1 km basin (BASELINE config 5), "
                                        f"members sharded across {world} GPU(s), LDD structures shared per GPU, no collective",
-                           "cells_per_member": n, "members_per_gpu": len(mine), "setup_s": round(setup_s, 1)},
-                "gpu_launches": 6 * args.steps * total}
+                           "cells_per_member": n, "members_per_gpu": len(mine), "setup_s": round(setup_s, 1),
+                           "routing": f"members routed {Ensemble.GROUP} maps per pass" if ens.grouped else "one pass per member",
+                           "cuda_graph": ens.state is not None},
+                "gpu_launches": (2 * total + 5 * -(-total // Ensemble.GROUP)) * args.steps}
         print(json.dumps(line), flush=True)
     for model in reversed(members):
         model.close()

@@ -34,3 +34,13 @@ def test_tss_file(tmp_path):
     csf.write_tss(p, [1, 2], [(1, [0.5, 1.5]), (2, [0.25, 2.0])])
     lines = open(p).read().splitlines()
     assert lines[:5] == ["timeseries scalar", "3", "timestep", "1", "2"] and len(lines) == 7
+
+
+def test_clone_mask_excludes_missing_values():
+    """PCRaster treats MV in the clone as outside the catchment, whatever the clone's value scale (sphy.py:141-145)."""
+    import numpy as np
+    from sphy_b200.model import _clone_mask
+    assert _clone_mask(np.array([[1.0, np.nan], [0.0, 2.5]], np.float32)).tolist() == [[True, False], [False, True]]
+    assert _clone_mask(np.array([[1, -2147483648], [0, 7]], np.int32)).tolist() == [[True, False], [False, True]]
+    assert _clone_mask(np.array([[1, 255], [0, 1]], np.uint8)).tolist() == [[True, False], [False, True]]
+    assert _clone_mask(np.array([[True, False]])).tolist() == [[True, False]]

@@ -99,11 +99,15 @@ def test_config5_two_ensemble_members_2000x2000():
         members.append(make_model(cat, route_method="scan", share_from=members[0] if members else None))
         ports.append(PortModel(PortInputs(cat)))
     assert members[1]._ctx is members[0]._ctx
+    from sphy_b200.multigpu import Ensemble
+    ens = Ensemble(members, graphs=True)          # members routed together (sphy_route_step_members), step replayed from a graph
+    assert ens.grouped
     g = PortInputs(cats[0]).lddst.gather
     for t in range(1, 7):
-        for model, port, cat in zip(members, ports, cats):
-            model.dynamic()
+        ens.dynamic()
+        for port, cat in zip(ports, cats):
             port.dynamic({k: g(v) for k, v in cat.forcing(t).items()})
+    assert len(ens.state["graphs"]) == 1          # steps 3..6 were graph replays
     torch.cuda.synchronize()
     for model, port in zip(members, ports):
         for k in STATES:

@@ -232,6 +232,29 @@ def test_model_with_scan_routing_matches_oracle_port():
                                         params=dict(SubWater=470.0, RootDepthFlat=150.0, Pscale=2.5)), 15, route_method="scan")
 
 
+def test_cuda_graph_replay_is_bit_identical():
+    """enable_graphs(): the device step replayed from a CUDA graph (day-of-year scalars from the device day table) gives
+    bit-identical states and discharges to the eager launch chain, across a year boundary of the Ra table."""
+    import datetime
+    import torch
+    from sphy_b200 import synth
+    cat = synth.make_catchment(nrows=150, ncols=130, seed=11, nsteps=40, start=datetime.date(2001, 12, 10),
+                               params=dict(SubWater=470.0, RootDepthFlat=150.0, Pscale=2.5))
+    eager = make_model(cat, route_method="scan")
+    graph = make_model(cat, route_method="scan")
+    graph.enable_graphs(True)
+    for t in range(40):
+        eager.dynamic()
+        graph.dynamic()
+    torch.cuda.synchronize()
+    assert len(graph._graphs["graphs"]) >= 1
+    for k in ("RootWater", "SubWater", "Gw", "BaseR", "H_gw", "QRAold", "TotR"):
+        assert torch.equal(getattr(eager, k), getattr(graph, k)), k
+    assert torch.equal(torch.stack(eager.tss["QallRAtot"]), torch.stack(graph.tss["QallRAtot"]))
+    graph.close()
+    eager.close()
+
+
 def test_ensemble_members_share_one_context():
     """BASELINE config 5 in miniature: members with perturbed kx / alphaGw / deltaGw and their own forcing share the
     LDD structures of one context and still match the oracle member by member."""
@@ -462,3 +485,50 @@ def test_ragged_sizes_and_kx_map():
             want = port.QRAold[model.cell_order]
             assert (bit_equal(q, want).all() if route == "levels" else close(q, want).all()), (shape, route)
             model.close()
+
+
+def test_snow_parameters_as_maps():
+    """modules/snow.py:84-90 reads Tcrit, SnowSC, DDFS and SnowF as maps first and as cfg floats otherwise.  The vertical
+    balance is per-cell, so a run with two-valued parameter maps must reproduce, cell by cell and bit for bit, the
+    scalar run of whichever value the cell carries."""
+    import configparser
+    import datetime
+    import torch
+    from sphy_b200 import synth
+    from sphy_b200.model import CatchmentSource, SphyModel
+    cat = synth.make_catchment(nrows=90, ncols=110, seed=21, nsteps=12, snow=True, start=datetime.date(2001, 3, 1),
+                               zrange=(1500.0, 5200.0), params=dict(SubWater=470.0, RootDepthFlat=150.0, Pscale=2.5, Toffset=9.0))
+    tmp = tempfile.mkdtemp(prefix="sphy_snowmap_")
+    cfg_path = cat.write_inputs(os.path.join(tmp, "in"), os.path.join(tmp, "out"))
+    vals = {"Tcrit": (2.0, 2.75), "SnowSC": (0.5, 0.25), "DDFS": (6.0, 4.5), "SnowF": (0.4, 0.15)}
+    west = np.zeros((90, 110), bool)
+    west[:, :55] = True
+
+    def run(variant):
+        cfg = configparser.RawConfigParser()
+        cfg.read(cfg_path)
+        src = CatchmentSource(cat)
+        for k, (a, b) in vals.items():
+            if variant == "maps":
+                src.maps[k.lower() + "_map"] = np.where(west, np.float32(a), np.float32(b)).astype(np.float32)
+                cfg.set("SNOW", k, k.lower() + "_map")
+            else:
+                cfg.set("SNOW", k, repr(a if variant == "west" else b))
+        m = SphyModel(cfg, src, route_method="levels")
+        m.initial()
+        for _ in range(12):
+            m.dynamic()
+        torch.cuda.synchronize()
+        out = {k: getattr(m, k).cpu().numpy() for k in ("SnowStore", "SnowWatStore", "TotalSnowStore", "RootWater", "SubWater", "Gw", "TotR")}
+        is_west = west.ravel()[m.flat_active]
+        m.close()
+        return out, is_west
+
+    maps, is_west = run("maps")
+    w, _ = run("west")
+    e, _ = run("east")
+    assert maps["SnowStore"].max() > 0
+    for k in maps:
+        assert bit_equal(maps[k][is_west], w[k][is_west]).all(), k
+        assert bit_equal(maps[k][~is_west], e[k][~is_west]).all(), k
+    assert not bit_equal(w["TotR"], e["TotR"]).all()           # the two parameter sets do differ
