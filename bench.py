@@ -153,6 +153,28 @@ def discharge_check(torch, model, dist=None):
     return {"outlet_q": v[2], "sum_q": v[0], "sum_q_first_eighth": v[1], "max_q": float(mx.item()), "timestep": int(model.timestep)}
 
 
+def h2d_ceiling(torch, dev, dist=None, nbytes=1 << 30, reps=3):
+    """Aggregate host->device bandwidth of this box for the e2e path's pattern: one pinned cudaMemcpyAsync per GPU, all
+    GPUs at once (GB/s summed over the ranks)."""
+    src = torch.empty(nbytes // 4, dtype=torch.float32).pin_memory()
+    dst = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+    dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    world = 1
+    if dist is not None:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        world = dist.get_world_size()
+    del src, dst
+    return world * reps * nbytes / float(dt.item()) / 1e9
+
+
 def cpu_port_rate(size, steps, seed=1):
     """Oracle port (NumPy restatement of the reference algorithm, 1 thread) on a bounded sample: Mcell-steps/s."""
     from oracle.sphy_port import PortInputs, PortModel
@@ -322,11 +344,16 @@ def main():
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    profiled = os.environ.get("SPHY_BENCH_PROFILE") == "1"     # ncu --profile-from-start off: capture the timed steps only
+    if profiled:
+        torch.cuda.cudart().cudaProfilerStart()
     e0.record()
     for _ in range(args.steps):
         model.dynamic()
     e1.record()
     torch.cuda.synchronize()
+    if profiled:
+        torch.cuda.cudart().cudaProfilerStop()
     clocks = sampler.stop()
     ms_total = e0.elapsed_time(e1)
     ms_step = ms_total / args.steps
@@ -352,6 +379,7 @@ def main():
             del raster
         host_ring.append(hd)
     del fa
+    h2d_ceiling_gbs = h2d_ceiling(torch, dev)
     model.set_device_forcing(None)
     model.set_host_forcing(lambda t: host_ring[t % len(host_ring)])
     e2e_steps = max(3, min(args.steps, 10))
@@ -401,8 +429,10 @@ def main():
         "roofline_route": scan_roofline(rprof, n, 1, peak),
         "check": check,
         "cpu_baseline": cpu,
-        "e2e": {"value": e2e_val, "unit": "Mcell-timesteps/s", "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": d2h // e2e_steps,
-                "steps": e2e_steps},
+        "e2e": {"value": e2e_val, "unit": "Mcell-timesteps/s", "h2d_bytes_per_step": 4 * model.h2d_bytes_per_map,
+                "d2h_bytes_per_step": d2h // e2e_steps, "steps": e2e_steps,
+                "h2d_achieved_gbs": 4 * model.h2d_bytes_per_map * e2e_steps / e2e_s / 1e9, "h2d_ceiling_gbs": h2d_ceiling_gbs,
+                "note": "ceiling = one pinned cudaMemcpyAsync of 1 GiB, measured in this run"},
         "gpu_launches": nlaunch_step * args.steps,
         "clocks": clocks,
     }

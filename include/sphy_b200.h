@@ -367,8 +367,9 @@ int sphy_trunk_set_plan(sphy_ctx *ctx, int32_t n_pub, const int32_t *pub_pos_dev
 
 /* Multi-GPU (one context per GPU, each built on the whole LDD): restrict this context to the contiguous device-index
  * range [cell_begin, cell_end) of the DFS order (cell_begin on a 1024-cell tile).  After the call every compact map
- * and sphy_ncells() refer to the local cells only.  Call order: sphy_trunk_select(world, bounds) -> sphy_set_partition ->
- * sphy_trunk_set_plan.  The per-step confluence exchange is
+ * and sphy_ncells() refer to the local cells only, and every whole-basin structure and workspace of the context is
+ * released (memory per rank scales with N / world; sphy_ldd_export and the level sweep are no longer available).
+ * Call order: sphy_trunk_select(world, bounds) -> sphy_set_partition -> sphy_trunk_set_plan.  The per-step confluence exchange is
  *   sphy_route_scan_begin -> all-gather of `send` (stride doubles per component and rank) -> sphy_route_scan_finish
  * and replaces the single-GPU sphy_route_step (modules/routing.py:25-29) on a partitioned context. */
 int sphy_set_partition(sphy_ctx *ctx, int64_t cell_begin, int64_t cell_end, void *stream);

@@ -498,6 +498,7 @@ extern "C" int sphy_ldd_export(sphy_ctx *ctx, const char *name, void *dst, size_
 {
     if (!ctx || !name || !dst) return SPHY_E_INVALID;
     if (!ctx->ldd_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_ldd_export before sphy_ldd_build");
+    if (ctx->partitioned) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_ldd_export: the whole-basin structures were released by sphy_set_partition");
     cudaStream_t st = (cudaStream_t)stream_;
     std::string k(name);
     const void *src = nullptr;

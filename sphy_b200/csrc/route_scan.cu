@@ -974,11 +974,34 @@ extern "C" int sphy_set_partition(sphy_ctx *ctx, int64_t cell_begin, int64_t cel
     if (ctx->partitioned) SPHY_FAIL(ctx, SPHY_E_STATE, "context is already partitioned");
     if (cell_begin < 0 || cell_end > ctx->n_global || cell_begin >= cell_end || (cell_begin % SCAN_TILE) != 0)
         SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_set_partition: bad range (it must start on a %d-cell tile)", SCAN_TILE);
-    (void)stream;
+    // Keep only this rank's slice of what the partitioned path reads (sub_size for the scan, flat_active for the raster
+    // gather) and release every whole-basin structure and workspace: the level-sweep order / donor tables and their
+    // [8][N] flux workspaces, the canonical Appendix-C arrays, the raster index.  Memory per rank then scales with N / world.
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t nl = cell_end - cell_begin;
+    int32_t *sub_l = nullptr, *flat_l = nullptr;
+    SPHY_CUDA(ctx, cudaMalloc(&sub_l, sizeof(int32_t) * nl));
+    SPHY_CUDA(ctx, cudaMalloc(&flat_l, sizeof(int32_t) * nl));
+    SPHY_CUDA(ctx, cudaMemcpyAsync(sub_l, ctx->sub_size + cell_begin, sizeof(int32_t) * nl, cudaMemcpyDeviceToDevice, st));
+    SPHY_CUDA(ctx, cudaMemcpyAsync(flat_l, ctx->flat_active + cell_begin, sizeof(int32_t) * nl, cudaMemcpyDeviceToDevice, st));
+    SPHY_CUDA(ctx, cudaStreamSynchronize(st));
+    void **whole[] = {(void **)&ctx->c_cidx, (void **)&ctx->c_flat_active, (void **)&ctx->c_down, (void **)&ctx->c_order, (void **)&ctx->c_pos,
+                      (void **)&ctx->c_don_ptr, (void **)&ctx->c_don_idx, (void **)&ctx->cidx, (void **)&ctx->flat_active, (void **)&ctx->down,
+                      (void **)&ctx->level, (void **)&ctx->order, (void **)&ctx->don_ptr, (void **)&ctx->don_idx, (void **)&ctx->indeg,
+                      (void **)&ctx->nup, (void **)&ctx->pos, (void **)&ctx->dpos_ptr, (void **)&ctx->dpos, (void **)&ctx->pre,
+                      (void **)&ctx->cell_canon, (void **)&ctx->sub_size, (void **)&ctx->acc, (void **)&ctx->qsorted, (void **)&ctx->sweep_rec,
+                      (void **)&ctx->tmp_n[0], (void **)&ctx->tmp_n[1], (void **)&ctx->tmp_n[2], (void **)&ctx->tmp_n[3],
+                      (void **)&ctx->chain_start, (void **)&ctx->chain_k, (void **)&ctx->chain_cell, (void **)&ctx->chain_don};
+    for (void **pp : whole) {
+        if (*pp) cudaFree(*pp);
+        *pp = nullptr;
+    }
+    ctx->sub_size = sub_l;                        // owned (freed with the context); the _loc views are what the kernels read
+    ctx->flat_active = flat_l;
+    ctx->sub_size_loc = sub_l;
+    ctx->flat_loc = flat_l;
     ctx->part_begin = cell_begin;
-    ctx->n = cell_end - cell_begin;
-    ctx->sub_size_loc = ctx->sub_size + cell_begin;
-    ctx->flat_loc = ctx->flat_active + cell_begin;
+    ctx->n = nl;
     ctx->partitioned = true;
     ctx->scan_ready = false;
     ctx->scan_comp_cap = 0;
@@ -1049,6 +1072,7 @@ extern "C" int sphy_trunk_select(sphy_ctx *ctx, int32_t min_level, int64_t min_c
     if (!ctx || !count_out || world < 1 || world > 64 || (world > 1 && !bounds_host)) return SPHY_E_INVALID;
     if (!ctx->ldd_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_trunk_select before sphy_ldd_build");
     if (ctx->order_mode != SPHY_ORDER_DFS) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_trunk_select needs SPHY_ORDER_DFS");
+    if (ctx->partitioned) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_trunk_select after sphy_set_partition (it needs the whole-basin structures)");
     // a trunk cell must leave its scan tile (the main pass skips exactly those cells): sub_size > SCAN_TILE
     if (min_level < SCAN_TILE || min_cells <= SCAN_TILE)
         SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_trunk_select: thresholds must exceed the %d-cell scan tile", SCAN_TILE);

@@ -1283,14 +1283,24 @@ class SphyModel:
         return out
 
     def _ingest_host(self, counter, keys):
+        """Pinned host rasters -> device -> compact maps.  A partitioned rank uploads only the band of raster rows that
+        contains its cells (a contiguous slice of the pinned raster) and gathers its cells out of that band."""
         compact = self.full_raster or self._forcing_host_compact
-        size = self.n if compact else self.nrows * self.ncols
         main = torch.cuda.current_stream(self.device)
         if self._copy_stream is None:
+            if compact:
+                self._band = (0, self.n)
+            else:
+                r0 = int(self.flat_active.min()) // self.ncols if self.n else 0
+                r1 = int(self.flat_active.max()) // self.ncols + 1 if self.n else 1
+                self._band = (r0 * self.ncols, r1 * self.ncols)
+            size = self._band[1] - self._band[0]
             self._copy_stream = torch.cuda.Stream(device=self.device)
             self._hbuf = [{k: torch.empty(size, dtype=torch.float32, device=self.device) for k in keys} for _ in range(2)]
             self._hready = [None, None]          # (counter, event) of the upload sitting in each buffer
+            self.h2d_bytes_per_map = size * 4
         cs = self._copy_stream
+        b0, b1 = self._band
 
         def upload(t, slot):
             try:
@@ -1303,7 +1313,7 @@ class SphyModel:
                 for k in keys:
                     if k in self._optional_keys and host.get(k) is None:
                         continue                 # a map series without a map for this day
-                    self._hbuf[slot][k].copy_(host[k], non_blocking=True)
+                    self._hbuf[slot][k].copy_(host[k] if compact else host[k][b0:b1], non_blocking=True)
                     present.append(k)
                 ev = torch.cuda.Event()
                 ev.record(cs)
@@ -1319,8 +1329,8 @@ class SphyModel:
         if compact:
             out = {k: buf[k] for k in present}
         else:
-            for k in present:
-                self._ck(self.lib.sphy_gather_f32(self._ctx, buf[k].data_ptr(), self._fdev[k].data_ptr(), self._stream()),
+            for k in present:                    # raster index -> band index: the gather reads raster[flat_active[i]]
+                self._ck(self.lib.sphy_gather_f32(self._ctx, buf[k].data_ptr() - 4 * b0, self._fdev[k].data_ptr(), self._stream()),
                          "sphy_gather_f32")
             out = {k: self._fdev[k] for k in present}
         upload(counter + 1, 1 - slot)            # prefetch tomorrow while today computes
