@@ -76,6 +76,11 @@ int sphy_ldd_export(sphy_ctx *ctx, const char *name, void *dst_dev, size_t dst_b
 /* raster <-> compact (readmap / report side of the boundary): out[k] = raster[cell k] and back */
 int sphy_gather_f32(sphy_ctx *ctx, const float *raster_dev, float *compact_dev, void *stream);
 int sphy_scatter_f32(sphy_ctx *ctx, const float *compact_dev, float *raster_dev, float fill, void *stream);
+/* out[dst_idx[e]] = src[src_idx[e]], e < count, src_idx ascending.  `src` may be a PINNED HOST raster (unified addressing):
+ * the device then pulls only the cells it owns out of the host raster (pcr.readmap's result, sphy.py:756) over PCIe, which
+ * is what lets a partitioned basin ingest rasters at the aggregate host->device bandwidth of the box. */
+int sphy_gather_indexed_f32(sphy_ctx *ctx, const float *src, const int32_t *src_idx_dev, const int32_t *dst_idx_dev,
+                            int64_t count, float *out_dev, void *stream);
 /* reporting accumulators (utilities/reporting.py:24-95): acc = acc + x (divisor == 0) or acc + x/divisor, and
  * out = in/divisor, each one REAL4 operation per cell like the reference's `tot + var`, `var / dim`, `tot / ydays` */
 int sphy_map_accumulate(sphy_ctx *ctx, float *acc, const float *x, float divisor, int64_t count, void *stream);

@@ -72,6 +72,29 @@ __global__ void k_scatter(const float *__restrict__ comp, const int32_t *__restr
         raster[g] = i >= 0 ? comp[i] : fill;
     }
 }
+// out[dst[e]] = src[src_idx[e]] with src_idx ascending: `src` may be PINNED HOST memory (unified addressing), in which case
+// the device pulls exactly the cells it owns out of the host raster over PCIe -- consecutive raster cells of one rank
+// coalesce into full 128-byte reads -- instead of receiving the whole raster and compacting it afterwards
+__global__ void __launch_bounds__(256) k_gather_indexed(const float *__restrict__ src, const int32_t *__restrict__ src_idx,
+                                                        const int32_t *__restrict__ dst_idx, int64_t n, float *__restrict__ out)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e0 < n; e0 += 4 * stride) {
+        float v[4];
+        int32_t d[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                          // four independent reads in flight per thread
+            const int64_t e = e0 + k * stride;
+            if (e < n) {
+                v[k] = src[__ldg(src_idx + e)];
+                d[k] = __ldg(dst_idx + e);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (e0 + k * stride < n) out[d[k]] = v[k];
+    }
+}
 __global__ void k_sample(const float *__restrict__ map, const int32_t *__restrict__ cells, int n, float *__restrict__ out)
 {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -84,6 +107,18 @@ extern "C" int sphy_gather_f32(sphy_ctx *ctx, const float *raster, float *compac
     if (!ctx || !raster || !compact) return SPHY_E_INVALID;
     if (!ctx->ldd_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_gather_f32 before sphy_ldd_build");
     k_gather<<<div_up(ctx->n, 256), 256, 0, (cudaStream_t)stream>>>(raster, ctx->flat_loc, ctx->n, compact);
+    SPHY_LAUNCH_CHECK(ctx);
+    return SPHY_OK;
+}
+
+extern "C" int sphy_gather_indexed_f32(sphy_ctx *ctx, const float *src, const int32_t *src_idx_dev, const int32_t *dst_idx_dev,
+                                       int64_t count, float *out_dev, void *stream)
+{
+    if (!ctx || !src || !src_idx_dev || !dst_idx_dev || !out_dev || count < 0) return SPHY_E_INVALID;
+    if (count == 0) return SPHY_OK;
+    const int64_t want = (count + 1023) / 1024;
+    const int grid = (int)(want < (int64_t)ctx->sm_count * 8 ? want : (int64_t)ctx->sm_count * 8);
+    k_gather_indexed<<<grid, 256, 0, (cudaStream_t)stream>>>(src, src_idx_dev, dst_idx_dev, count, out_dev);
     SPHY_LAUNCH_CHECK(ctx);
     return SPHY_OK;
 }

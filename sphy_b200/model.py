@@ -689,10 +689,17 @@ class SphyModel:
     def _glacier_initial(self):
         import pandas as pd
         cfg = self.config
-        if self.world > 1:
-            raise NotImplementedError("the glacier fragment table is not split across ranks yet: run glacier basins on one GPU")
         tab = pd.read_csv(os.path.join(self.inpath, cfg.get("GLACIER", "GlacTable")))
         tab = tab.sort_values(by="MOD_ID", kind="stable").reset_index(drop=True)
+        if self.world > 1:
+            # a partitioned basin: every rank keeps the fragments of its own cells (the fragment physics and the per-cell
+            # aggregation are local); the per-glacier tables and the yearly retreat work on whole glaciers and are not split
+            if cfg.getint("GLACIER", "GlacID_flag") or cfg.getint("GLACIER", "GlacRetreat"):
+                raise NotImplementedError("per-glacier tables / glacier retreat are not available on a partitioned basin")
+            model_id0 = np.asarray(self._readmap(cfg.get("GLACIER", "ModelID"))).ravel()
+            lookup0 = {int(v): i for i, v in enumerate(model_id0)}
+            mine = np.array([self._cidx_host[lookup0[int(m)]] >= 0 if int(m) in lookup0 else False for m in tab["MOD_ID"]], bool)
+            tab = tab[mine].reset_index(drop=True)
         model_id = np.asarray(self._readmap(cfg.get("GLACIER", "ModelID"))).ravel()
         lookup = {int(v): i for i, v in enumerate(model_id)}                                   # ModelID_1d == ID
         mod = tab["MOD_ID"].to_numpy().astype(np.int64)
@@ -1283,24 +1290,22 @@ class SphyModel:
         return out
 
     def _ingest_host(self, counter, keys):
-        """Pinned host rasters -> device -> compact maps.  A partitioned rank uploads only the band of raster rows that
-        contains its cells (a contiguous slice of the pinned raster) and gathers its cells out of that band."""
-        compact = self.full_raster or self._forcing_host_compact
+        """Pinned host rasters -> compact device maps.  The device pulls exactly its own cells out of the pinned raster
+        (sphy_gather_indexed_f32 over unified addressing, cells visited in raster order so that the PCIe reads coalesce)
+        on a copy stream, double buffered: day t+1 is fetched while day t computes.  A partitioned rank therefore moves
+        1 / world of every raster, with the host holding plain rasters as `readmap` delivers them."""
+        compact = self._forcing_host_compact
         main = torch.cuda.current_stream(self.device)
         if self._copy_stream is None:
-            if compact:
-                self._band = (0, self.n)
-            else:
-                r0 = int(self.flat_active.min()) // self.ncols if self.n else 0
-                r1 = int(self.flat_active.max()) // self.ncols + 1 if self.n else 1
-                self._band = (r0 * self.ncols, r1 * self.ncols)
-            size = self._band[1] - self._band[0]
             self._copy_stream = torch.cuda.Stream(device=self.device)
-            self._hbuf = [{k: torch.empty(size, dtype=torch.float32, device=self.device) for k in keys} for _ in range(2)]
+            self._hbuf = [{k: torch.empty(self.n, dtype=torch.float32, device=self.device) for k in keys} for _ in range(2)]
             self._hready = [None, None]          # (counter, event) of the upload sitting in each buffer
-            self.h2d_bytes_per_map = size * 4
+            self.h2d_bytes_per_map = self.n * 4
+            if not compact:
+                order = np.argsort(self.flat_active, kind="stable")
+                self._pull_src = self._dev(self.flat_active[order].astype(np.int32))     # raster index, ascending
+                self._pull_dst = self._dev(order.astype(np.int32))                       # device cell of each
         cs = self._copy_stream
-        b0, b1 = self._band
 
         def upload(t, slot):
             try:
@@ -1313,11 +1318,18 @@ class SphyModel:
                 for k in keys:
                     if k in self._optional_keys and host.get(k) is None:
                         continue                 # a map series without a map for this day
-                    self._hbuf[slot][k].copy_(host[k] if compact else host[k][b0:b1], non_blocking=True)
+                    if compact:
+                        self._hbuf[slot][k].copy_(host[k], non_blocking=True)
+                    else:
+                        if not host[k].is_pinned():
+                            raise ValueError("set_host_forcing: the host rasters must be pinned (torch.Tensor.pin_memory())")
+                        self._ck(self.lib.sphy_gather_indexed_f32(self._ctx, host[k].data_ptr(), self._pull_src.data_ptr(),
+                                                                  self._pull_dst.data_ptr(), self.n, self._hbuf[slot][k].data_ptr(),
+                                                                  C.c_void_p(cs.cuda_stream)), "sphy_gather_indexed_f32")
                     present.append(k)
                 ev = torch.cuda.Event()
                 ev.record(cs)
-            self._hready[slot] = (t, ev, present)
+            self._hready[slot] = (t, ev, present, host)     # `host` stays referenced until the slot is reused: the pull reads it asynchronously
 
         slot = counter % 2
         if self._hready[slot] is None or self._hready[slot][0] != counter:
@@ -1326,13 +1338,7 @@ class SphyModel:
             raise FileNotFoundError(f"no forcing for time step {counter}: the host forcing source has no entry for it")
         main.wait_event(self._hready[slot][1])
         buf, present = self._hbuf[slot], self._hready[slot][2]
-        if compact:
-            out = {k: buf[k] for k in present}
-        else:
-            for k in present:                    # raster index -> band index: the gather reads raster[flat_active[i]]
-                self._ck(self.lib.sphy_gather_f32(self._ctx, buf[k].data_ptr() - 4 * b0, self._fdev[k].data_ptr(), self._stream()),
-                         "sphy_gather_f32")
-            out = {k: self._fdev[k] for k in present}
+        out = {k: buf[k] for k in present}
         upload(counter + 1, 1 - slot)            # prefetch tomorrow while today computes
         return out
 

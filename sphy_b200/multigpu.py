@@ -167,9 +167,8 @@ def bench_main(args, rank, world):
     check = bench.discharge_check(torch, model, dist)
     rprof = bench.route_profile(model)
 
-    # e2e: the host holds forcing RASTERS (what readmap delivers); every rank uploads the band of raster rows that contains
-    # its cells from pinned memory each step, compacts it into device order on the GPU and reads its stations back --
-    # the same raster -> device path as on one GPU
+    # e2e: the host holds forcing RASTERS (what readmap delivers) in pinned memory; every rank pulls its own cells out of
+    # them each step (sphy_gather_indexed_f32) and reads its stations back -- the same raster -> device path as on one GPU
     fa = torch.from_numpy(model.flat_active).to(dev)
     host_ring = []
     for day in ring[:2]:
@@ -228,9 +227,9 @@ def bench_main(args, rank, world):
             "e2e": {"value": e2e_val, "unit": "Mcell-timesteps/s", "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": d2h // e2e_steps, "steps": e2e_steps,
                     "h2d_achieved_gbs": h2d_bytes * e2e_steps / float(dt.item()) / 1e9, "h2d_ceiling_gbs": h2d_ceiling,
-                    "note": "every rank uploads the band of raster rows holding its cells (all ranks together: "
-                            f"{h2d_bytes / (16.0 * model.nrows * model.ncols):.2f} x the raster); ceiling = concurrent pinned "
-                            "cudaMemcpyAsync of 1 GiB per GPU"},
+                    "note": "every rank pulls its own cells out of pinned host rasters (all ranks together: "
+                            f"{h2d_bytes / (16.0 * model.nrows * model.ncols):.2f} x the raster, algorithmic bytes); ceiling = "
+                            "concurrent pinned cudaMemcpyAsync of 1 GiB per GPU"},
             "gpu_launches": 9 * args.steps * world,
             "clocks": clocks,
         }

@@ -32,6 +32,8 @@ def main():
     ap.add_argument("--cols", type=int, default=1300)
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--bench-size", type=int, default=0, help="use bench.py's basin of this size and its device forcing instead")
+    ap.add_argument("--glacier", action="store_true", help="snow and glacier modules on (BASELINE config 2 physics): the fragment "
+                                                           "table is split by rank")
     args = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -42,9 +44,13 @@ def main():
         cat = bench.make_case(args.bench_size)
         comps = ("QRAold",)
     else:
+        extra = dict(snow=True, glacier=True, zrange=(1500.0, 5200.0)) if args.glacier else {}
+        par = dict(SubWater=470.0, RootDepthFlat=150.0, Pscale=2.5)
+        if args.glacier:
+            par.update(Toffset=15.0, RootKsat=12.0)
         cat = synth.make_catchment(nrows=args.rows, ncols=args.cols, seed=77, nsteps=args.steps, start=datetime.date(2001, 5, 1),
-                                   rout_components=True, params=dict(SubWater=470.0, RootDepthFlat=150.0, Pscale=2.5))
-        comps = ("QRAold", "RootRRAold", "BaseRAold")
+                                   rout_components=True, params=par, **extra)
+        comps = ("QRAold", "RootRRAold", "BaseRAold") + (("GlacRAold", "SnowRAold") if args.glacier else ())
     tmp = tempfile.mkdtemp(prefix=f"sphy_mgcheck_r{rank}_")
     cfg = cat.write_inputs(os.path.join(tmp, "in"), os.path.join(tmp, "out"))
     kw = dict(device=str(dev), collect_tss=False)
@@ -77,6 +83,8 @@ def main():
             vs_levels = max(vs_levels, float(((a - c).abs() / c.abs().clamp_min(1e-12)).max().item()))
             whole_vs_levels = max(whole_vs_levels, float(((b - c).abs() / c.abs().clamp_min(1e-12)).max().item()))
         assert torch.equal(part.RootWater, whole.RootWater[lo:hi]), "water balance must not depend on the split"
+        if args.glacier:
+            assert torch.equal(part.TotalSnowStore, whole.TotalSnowStore[lo:hi]) and torch.equal(part.GlacR, whole.GlacR[lo:hi])
     mode = "p2p" if part._mg_p2p else "nccl"
     w = torch.tensor([vs_whole, vs_levels, whole_vs_levels], device=dev, dtype=torch.float64)
     dist.all_reduce(w, op=dist.ReduceOp.MAX)
@@ -84,7 +92,7 @@ def main():
     check1 = bench.discharge_check(torch, whole)
     part.check_exchange()
     if rank == 0:
-        print(json.dumps({"tool": "check_multigpu", "world": world, "exchange": mode, "cells": whole.n, "steps": args.steps,
+        print(json.dumps({"tool": "check_multigpu", "world": world, "exchange": mode, "cells": whole.n, "steps": args.steps, "glacier": bool(args.glacier),
                           "trunk_cells_partitioned": part.trunk_cells, "trunk_cells_one_gpu": whole.trunk_cells,
                           "worst_rel_partitioned_vs_one_gpu": float(w[0]), "worst_rel_partitioned_vs_level_sweep": float(w[1]),
                           "worst_rel_one_gpu_scan_vs_level_sweep": float(w[2]), "check_partitioned": check, "check_one_gpu": check1}),
