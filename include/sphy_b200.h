@@ -76,6 +76,12 @@ int sphy_ldd_export(sphy_ctx *ctx, const char *name, void *dst_dev, size_t dst_b
 /* raster <-> compact (readmap / report side of the boundary): out[k] = raster[cell k] and back */
 int sphy_gather_f32(sphy_ctx *ctx, const float *raster_dev, float *compact_dev, void *stream);
 int sphy_scatter_f32(sphy_ctx *ctx, const float *compact_dev, float *raster_dev, float fill, void *stream);
+/* NetCDF forcing (utilities/netcdf2PCraster.py:167-197): the daily scipy.interpolate.griddata(method="linear") of the coarse
+ * forcing grid onto the model cells as one gather -- out[i] = REAL4(sum_k w3[3i+k] * z[idx3[3i+k]]) in float64, with the
+ * triangle and barycentric weights of every cell computed once on the host (they do not change from day to day);
+ * idx3[3i] < 0 = outside the convex hull -> NaN (the reference's -9999 / MV). */
+int sphy_interp_linear(sphy_ctx *ctx, const double *z_dev, const int32_t *idx3_dev, const double *w3_dev, int64_t count,
+                       float *out_dev, void *stream);
 /* out[dst_idx[e]] = src[src_idx[e]], e < count, src_idx ascending.  `src` may be a PINNED HOST raster (unified addressing):
  * the device then pulls only the cells it owns out of the host raster (pcr.readmap's result, sphy.py:756) over PCIe, which
  * is what lets a partitioned basin ingest rasters at the aggregate host->device bandwidth of the box. */

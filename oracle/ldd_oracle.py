@@ -24,7 +24,9 @@ def ldd_lib():
     so = os.path.join(out_dir, "libldd_oracle.so")
     if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
         os.makedirs(out_dir, exist_ok=True)
-        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-o", so, src])
+        tmp = so + f".tmp{os.getpid()}"                        # several processes may build at once: publish atomically
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-o", tmp, src])
+        os.replace(tmp, so)
     lib = ctypes.CDLL(so)
     P = ctypes.c_void_p
     lib.ldd_compact.restype = ctypes.c_int64

@@ -24,11 +24,29 @@ NVCC_FLAGS = [
 ]
 
 
-def _newer(target, sources):
-    if not os.path.exists(target):
+def _digest(sources, flags=()):
+    import hashlib
+    h = hashlib.sha256(" ".join(flags).encode())
+    for s in sorted(sources):
+        h.update(os.path.basename(s).encode())
+        with open(s, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def _newer(target, sources, flags=()):
+    """Is `target` the build of exactly these sources?  Decided by a content digest kept next to it -- file times do not
+    survive the copy onto a GPU box, and a spurious rebuild there costs half a minute per process."""
+    stamp = target + ".stamp"
+    if not os.path.exists(target) or not os.path.exists(stamp):
         return False
-    t = os.path.getmtime(target)
-    return all(os.path.getmtime(s) <= t for s in sources)
+    with open(stamp) as fh:
+        return fh.read().strip() == _digest(sources, flags)
+
+
+def _stamp(target, sources, flags=()):
+    with open(target + ".stamp", "w") as fh:
+        fh.write(_digest(sources, flags))
 
 
 def cuda_sources():
@@ -38,13 +56,39 @@ def cuda_sources():
     return srcs, deps
 
 
+class _BuildLock:
+    """Inter-process lock around the in-tree builds: the ranks of a torchrun launch all import the package at once, and a
+    rank must never dlopen a library another rank is still linking."""
+
+    def __init__(self, name):
+        self.path = os.path.join(PKG, name)
+
+    def __enter__(self):
+        import fcntl
+        self.fh = open(self.path, "w")
+        fcntl.flock(self.fh, fcntl.LOCK_EX)
+        return self
+
+    def __exit__(self, *exc):
+        import fcntl
+        fcntl.flock(self.fh, fcntl.LOCK_UN)
+        self.fh.close()
+
+
 def build_cuda(force=False, verbose=False):
-    """Compile every csrc/*.cu to an object (in parallel) and link libsphy_b200.so."""
+    """Compile every csrc/*.cu to an object (in parallel) and link libsphy_b200.so (atomically, under a file lock)."""
+    srcs, deps = cuda_sources()
+    if not force and _newer(CUDA_LIB, srcs + deps, NVCC_FLAGS):
+        return CUDA_LIB
+    with _BuildLock(".build.lock"):
+        if not force and _newer(CUDA_LIB, srcs + deps, NVCC_FLAGS):    # another process built it while this one waited
+            return CUDA_LIB
+        return _build_cuda_locked(srcs, deps, force, verbose)
+
+
+def _build_cuda_locked(srcs, deps, force, verbose):
     from concurrent.futures import ThreadPoolExecutor
 
-    srcs, deps = cuda_sources()
-    if not force and _newer(CUDA_LIB, srcs + deps):
-        return CUDA_LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libsphy_b200.so (no CPU fallback exists)")
@@ -54,12 +98,13 @@ def build_cuda(force=False, verbose=False):
 
     def compile_one(src):
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
-        if not force and _newer(obj, [src] + deps):
+        if not force and _newer(obj, [src] + deps, cflags):
             return obj, ""
         cmd = [nvcc] + cflags + (["-Xptxas=-v"] if verbose else []) + ["-I", INCLUDE, "-I", CSRC, "-c", "-o", obj, src]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s" % (src, r.stderr))
+        _stamp(obj, [src] + deps, cflags)
         return obj, r.stderr
 
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
@@ -69,7 +114,10 @@ def build_cuda(force=False, verbose=False):
             if log:
                 print(log)
     objs = [o for o, _ in results]
-    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", CUDA_LIB] + objs)
+    tmp = CUDA_LIB + f".tmp{os.getpid()}"
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp] + objs)
+    os.replace(tmp, CUDA_LIB)                                  # readers see the old library or the complete new one
+    _stamp(CUDA_LIB, srcs + deps, NVCC_FLAGS)
     return CUDA_LIB
 
 
@@ -77,7 +125,13 @@ def build_hostgen(force=False):
     src = os.path.join(CSRC, "hostgen.c")
     if not force and _newer(HOSTGEN_LIB, [src]):
         return HOSTGEN_LIB
-    subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-o", HOSTGEN_LIB, src, "-lm"])
+    with _BuildLock(".build.lock"):
+        if not force and _newer(HOSTGEN_LIB, [src]):
+            return HOSTGEN_LIB
+        tmp = HOSTGEN_LIB + f".tmp{os.getpid()}"
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-o", tmp, src, "-lm"])
+        os.replace(tmp, HOSTGEN_LIB)
+        _stamp(HOSTGEN_LIB, [src])
     return HOSTGEN_LIB
 
 

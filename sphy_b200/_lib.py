@@ -129,6 +129,7 @@ SYMBOLS = {
     "sphy_ldd_export": (C.c_int, [P, C.c_char_p, P, C.c_size_t, P]),
     "sphy_gather_f32": (C.c_int, [P, P, P, P]),
     "sphy_gather_indexed_f32": (C.c_int, [P, P, P, P, C.c_int64, P, P]),
+    "sphy_interp_linear": (C.c_int, [P, P, P, P, C.c_int64, P, P]),
     "sphy_scatter_f32": (C.c_int, [P, P, P, C.c_float, P]),
     "sphy_sample": (C.c_int, [P, P, P, C.c_int, P, P]),
     "sphy_map_accumulate": (C.c_int, [P, P, P, C.c_float, C.c_int64, P]),

@@ -95,6 +95,21 @@ __global__ void __launch_bounds__(256) k_gather_indexed(const float *__restrict_
             if (e0 + k * stride < n) out[d[k]] = v[k];
     }
 }
+// piecewise-linear interpolation of scattered / gridded values onto the cells: out = REAL4( sum_k w[3i+k] * z[idx[3i+k]] ) in
+// float64 in the order k = 0, 1, 2 -- what scipy's LinearNDInterpolator (griddata(method="linear")) evaluates per target
+// point; idx < 0 marks a cell outside the convex hull of the source points (missing value)
+__global__ void k_interp_linear(const double *__restrict__ z, const int32_t *__restrict__ idx, const double *__restrict__ w, int64_t n,
+                                float *__restrict__ out)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t i0 = idx[3 * i];
+    if (i0 < 0) { out[i] = nanf(""); return; }
+    double s = w[3 * i] * z[i0];
+    s = s + w[3 * i + 1] * z[idx[3 * i + 1]];
+    s = s + w[3 * i + 2] * z[idx[3 * i + 2]];
+    out[i] = (float)s;
+}
 __global__ void k_sample(const float *__restrict__ map, const int32_t *__restrict__ cells, int n, float *__restrict__ out)
 {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -119,6 +134,16 @@ extern "C" int sphy_gather_indexed_f32(sphy_ctx *ctx, const float *src, const in
     const int64_t want = (count + 1023) / 1024;
     const int grid = (int)(want < (int64_t)ctx->sm_count * 8 ? want : (int64_t)ctx->sm_count * 8);
     k_gather_indexed<<<grid, 256, 0, (cudaStream_t)stream>>>(src, src_idx_dev, dst_idx_dev, count, out_dev);
+    SPHY_LAUNCH_CHECK(ctx);
+    return SPHY_OK;
+}
+
+extern "C" int sphy_interp_linear(sphy_ctx *ctx, const double *z_dev, const int32_t *idx3_dev, const double *w3_dev, int64_t count,
+                                  float *out_dev, void *stream)
+{
+    if (!ctx || !z_dev || !idx3_dev || !w3_dev || !out_dev || count < 0) return SPHY_E_INVALID;
+    if (count == 0) return SPHY_OK;
+    k_interp_linear<<<div_up(count, 256), 256, 0, (cudaStream_t)stream>>>(z_dev, idx3_dev, w3_dev, count, out_dev);
     SPHY_LAUNCH_CHECK(ctx);
     return SPHY_OK;
 }

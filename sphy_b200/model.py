@@ -536,18 +536,28 @@ class SphyModel:
         self.PMap = (self._lookup_column_table(os.path.join(self.inpath, cfg.get("PWS", "PFactor")), self.LandUse)
                      if self.PlantWaterStressFLAG == 1 else None)
         # climate, sphy.py:305-370
-        for k in ("precNetcdfFLAG", "tempNetcdfFLAG"):
-            if cfg.has_option("CLIMATE", k) and cfg.getint("CLIMATE", k) == 1:
-                raise NotImplementedError("NetCDF forcing is outside the hot path (SURVEY.md section 2)")
-        self.Prec = cfg.get("CLIMATE", "Prec")                                                # map-stack prefixes, sphy.py:318,334
-        self.Tair = cfg.get("CLIMATE", "Tair")
+        flag = lambda sec, k: int(cfg.has_option(sec, k) and cfg.get(sec, k).strip() != "" and cfg.getint(sec, k) == 1)  # noqa: E731
+        # forcing key -> (reference forcing name, cfg section) of the variables fed from NetCDF (sphy.py:309-363)
+        self._nc_cfg = {}
+        if flag("CLIMATE", "precNetcdfFLAG"):
+            self._nc_cfg["prec"] = ("Prec", "CLIMATE")
+        if flag("CLIMATE", "tempNetcdfFLAG"):
+            self._nc_cfg["tavg"] = ("Temp", "CLIMATE")
+        if flag("ETREF", "TminNetcdfFLAG"):
+            self._nc_cfg["tmin"] = ("Tmin", "ETREF")
+        if flag("ETREF", "TmaxNetcdfFLAG"):
+            self._nc_cfg["tmax"] = ("Tmax", "ETREF")
+        self._nc = {}
+        self.Prec = cfg.get("CLIMATE", "Prec") if "prec" not in self._nc_cfg else None         # map-stack prefixes, sphy.py:318,334
+        self.Tair = cfg.get("CLIMATE", "Tair") if "tavg" not in self._nc_cfg else None
         self.Pcorr = cfg.getfloat("CLIMATE", "Pcorr_fact")
         self.Tcorr = cfg.getfloat("CLIMATE", "Tcorr_fact")
         self.ETREF_FLAG = cfg.getint("ETREF", "ETREF_FLAG")
         if self.ETREF_FLAG == 0:
             self.Lat = rd("ETREF", "Lat")
             self.Gsc = cfg.getfloat("ETREF", "Gsc")
-            self.Tmin, self.Tmax = cfg.get("ETREF", "Tmin"), cfg.get("ETREF", "Tmax")
+            self.Tmin = cfg.get("ETREF", "Tmin") if "tmin" not in self._nc_cfg else None
+            self.Tmax = cfg.get("ETREF", "Tmax") if "tmax" not in self._nc_cfg else None
         else:
             self.ETref = cfg.get("ETREF", "ETref")
         if self.SnowFLAG == 1:                                                                 # snow.py:84-90
@@ -1248,7 +1258,7 @@ class SphyModel:
             pre["ndvi"] = self.ndvi
         for k, (prefix, _) in self._series.items():
             pre[k] = prefix
-        return {k: csf.stack_name(v, counter) for k, v in pre.items()}
+        return {k: csf.stack_name(v, counter) for k, v in pre.items() if v is not None}
 
     def _ingest(self, counter):
         """The day's forcing as compact device maps.  Three sources: maps already resident in HBM
@@ -1275,6 +1285,12 @@ class SphyModel:
         names = self._forcing_names(counter)
         out = dict(self._fdev)
         for k in keys:
+            if k in self._nc_cfg:                  # NetCDF forcing: interpolated on the device (netcdf2PCraster.netcdf2pcrDynamic)
+                if k not in self._nc:
+                    from .netcdf_forcing import NetcdfForcing
+                    self._nc[k] = NetcdfForcing(self, *self._nc_cfg[k])
+                out[k] = self._nc[k].day(self.curdate)
+                continue
             try:
                 src = np.asarray(self.maps.read(names[k]), np.float32).ravel()
             except (KeyError, FileNotFoundError):

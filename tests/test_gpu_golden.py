@@ -532,3 +532,83 @@ def test_snow_parameters_as_maps():
         assert bit_equal(maps[k][is_west], w[k][is_west]).all(), k
         assert bit_equal(maps[k][~is_west], e[k][~is_west]).all(), k
     assert not bit_equal(w["TotR"], e["TotR"]).all()           # the two parameter sets do differ
+
+
+def test_netcdf_forcing_matches_griddata():
+    """precNetcdfFLAG / tempNetcdfFLAG / TminNetcdfFLAG / TmaxNetcdfFLAG = 1 (sphy.py:309-363): the forcing comes from NetCDF
+    grids interpolated onto the model cells.  The device path (static Delaunay weights + sphy_interp_linear) must deliver what
+    the reference's per-day scipy.interpolate.griddata(method="linear") call delivers (utilities/netcdf2PCraster.py:167-197),
+    and a run fed that way must equal a run fed the interpolated maps directly."""
+    import configparser
+    import datetime
+    import torch
+    from scipy.interpolate import griddata
+    from scipy.io import netcdf_file
+    from sphy_b200 import synth
+    from sphy_b200.model import CatchmentSource, SphyModel
+    nsteps, nrows, ncols, cs = 5, 80, 100, 250.0
+    start = datetime.date(2001, 6, 1)
+    cat = synth.make_catchment(nrows=nrows, ncols=ncols, cellsize=cs, seed=31, nsteps=nsteps, start=start,
+                               params=dict(SubWater=470.0, RootDepthFlat=150.0, Pscale=2.5))
+    tmp = tempfile.mkdtemp(prefix="sphy_nc_")
+    cfg_path = cat.write_inputs(os.path.join(tmp, "in"), os.path.join(tmp, "out"))
+    xul, yul = 500000.0, 4200000.0
+    X = np.arange(xul - 8000.0, xul + ncols * cs + 8000.0, 2000.0)
+    Y = np.arange(yul - nrows * cs - 8000.0, yul + 8000.0, 2000.0)
+    rng = np.random.default_rng(31)
+    fields = {"prec": ("pr", 8.0 * rng.random((nsteps, Y.size, X.size))), "tavg": ("tas", 12.0 + 3.0 * rng.standard_normal((nsteps, Y.size, X.size)))}
+    fields["tmin"] = ("tasmin", fields["tavg"][1] - 5.0 - rng.random((nsteps, Y.size, X.size)))
+    fields["tmax"] = ("tasmax", fields["tavg"][1] + 5.0 + rng.random((nsteps, Y.size, X.size)))
+    fields["prec"][1][2, 3, 4] = -9999.0                                    # a missing node on day 3: dropped and re-triangulated
+    path = os.path.join(tmp, "forcing.nc")
+    f = netcdf_file(path, "w")
+    f.createDimension("time", nsteps); f.createDimension("y", Y.size); f.createDimension("x", X.size)
+    tv = f.createVariable("time", "f8", ("time",)); tv[:] = np.arange(nsteps, dtype=np.float64); tv.units = "days since 2001-06-01 00:00:00"
+    f.createVariable("x", "f8", ("x",))[:] = X
+    f.createVariable("y", "f8", ("y",))[:] = Y
+    for _, (name, arr) in fields.items():
+        f.createVariable(name, "f8", ("time", "y", "x"))[:] = arr
+    f.close()
+    cfg = configparser.RawConfigParser()
+    cfg.read(cfg_path)
+    for key, sec, forcing in (("prec", "CLIMATE", "Prec"), ("tavg", "CLIMATE", "Temp"), ("tmin", "ETREF", "Tmin"), ("tmax", "ETREF", "Tmax")):
+        cfg.set(sec, {"Prec": "precNetcdfFLAG", "Temp": "tempNetcdfFLAG", "Tmin": "TminNetcdfFLAG", "Tmax": "TmaxNetcdfFLAG"}[forcing], "1")
+        cfg.set(sec, forcing + "Netcdf", path)
+        cfg.set(sec, forcing + "NetcdfInput", f"{fields[key][0]},x,y,linear,1.0,epsg:32630,epsg:32630")
+    src = CatchmentSource(cat)
+    src.georef = (xul, yul)
+    nc_model = SphyModel(cfg, src, route_method="levels")
+    nc_model.initial()
+    # what the reference computes per day (netcdf2PCraster.py:132-148, 167-197) -> REAL4 rasters, fed as plain maps
+    gx, gy = np.meshgrid(X, Y)
+    xi, yi = np.meshgrid(np.arange(xul + cs * 0.5, (xul + cs * 0.5) + ncols * cs, cs),
+                         np.flipud(np.arange((yul + cs * 0.5) - nrows * cs, yul + cs * 0.5, cs)))
+    cfg2 = configparser.RawConfigParser()
+    cfg2.read(cfg_path)
+    want = {}
+
+    def forcing(t):
+        out = {}
+        for key, (_, arr) in fields.items():
+            z = arr[t - 1].ravel()
+            z = np.where(z <= -9999, np.nan, z)
+            ok = ~np.isnan(z)
+            out[key] = griddata((gx.ravel()[ok], gy.ravel()[ok]), z[ok], (xi, yi), method="linear").astype(np.float32)
+        want[t] = out
+        return out
+
+    ref_model = SphyModel(cfg2, CatchmentSource(cat), route_method="levels")
+    ref_model.maps.forcing_fn = forcing
+    ref_model.initial()
+    for t in range(1, nsteps + 1):
+        f_nc = nc_model._ingest(nc_model.counter + 1)
+        for key in fields:
+            got = nc_model.to_raster(f_nc[key])
+            assert bit_equal(got, want.setdefault(t, forcing(t))[key]).all(), (t, key)
+        nc_model.dynamic()
+        ref_model.dynamic()
+    torch.cuda.synchronize()
+    for k in ("RootWater", "SubWater", "Gw", "QRAold", "TotR"):
+        assert torch.equal(getattr(nc_model, k), getattr(ref_model, k)), k
+    nc_model.close()
+    ref_model.close()
