@@ -297,6 +297,8 @@ def main():
     ap.add_argument("--route", default=os.environ.get("SPHY_BENCH_ROUTE", "scan"), choices=["levels", "scan"])
     ap.add_argument("--ring", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="route day t strictly before the water balance of day t + 1 "
+                                                              "(default: the routing runs on a second stream underneath it)")
     ap.add_argument("--workload", default="basin", choices=["basin", "ensemble"],
                     help="basin: BASELINE config 4 (default, the headline); ensemble: BASELINE config 5")
     ap.add_argument("--members", type=int, default=64)
@@ -324,7 +326,8 @@ def main():
     cat = make_case(args.size)
     tmp = tempfile.mkdtemp(prefix="sphy_bench_")
     cfg = cat.write_inputs(os.path.join(tmp, "in"), os.path.join(tmp, "out"))
-    model = SphyModel(cfg, CatchmentSource(cat), device="cuda:0", route_method=args.route, diagnostics=False)
+    model = SphyModel(cfg, CatchmentSource(cat), device="cuda:0", route_method=args.route, diagnostics=False,
+                      overlap_routing=not args.no_overlap)
     model.initial()
     n = model.n
     dem_dev = torch.from_numpy(model._compact_np(cat.dem)).to(dev)
@@ -350,6 +353,7 @@ def main():
     e0.record()
     for _ in range(args.steps):
         model.dynamic()
+    model.sync()                                               # the routing stream's last step is inside the timed region
     e1.record()
     torch.cuda.synchronize()
     if profiled:
@@ -391,6 +395,7 @@ def main():
     d2h = 0
     for _ in range(e2e_steps):
         model.dynamic()
+        model.sync()
         q = model.tss["QallRAtot"][-1].cpu()          # device -> host read of the step's result (.tss sample)
         d2h += q.numel() * 4
     torch.cuda.synchronize()
@@ -416,7 +421,7 @@ def main():
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.size), "cells": n, "levels": model.nlevels, "routing": args.route,
-                   "trunk_cells": getattr(model, "trunk_cells", 0),
+                   "trunk_cells": getattr(model, "trunk_cells", 0), "overlap_routing": model._ovl is not None,
                    "l2": "per-step working set %.1f GB >> 126 MB L2 (inputs larger than L2, no flush needed)" % (ALG_BYTES_WB * n / 1e9)
                    if ALG_BYTES_WB * n > 4 * 126e6 else "working set fits L2: throughput only, no roofline claim",
                    "forcing_ring_days": args.ring, "setup_s": round(setup_s, 1)},

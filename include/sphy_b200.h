@@ -347,6 +347,12 @@ int sphy_route_step(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm, flo
  * forcing/parameter ensemble on one basin (BASELINE config 5): one pass reads the index structures once for all of them. */
 int sphy_route_step_members(sphy_ctx *ctx, int nmaps, const float *const *runoff_mm, float *const *q_state,
                             const sphy_param *kx, const float *one_minus_kx, void *stream);
+/* The caller runs the routing of step t on a second stream while the water-balance kernel of step t + 1 occupies the GPU
+ * (nothing in the vertical balance reads the routed discharge): every routing kernel behind the main pass then uses CTAs
+ * small enough to be resident next to it (the tile totals are scanned by 128-thread blocks in two levels instead of by the
+ * library), and `main_pass_event` (a cudaEvent_t of the caller, may be NULL) is recorded on the routing stream right
+ * behind the bandwidth-bound main pass, so that the caller can start the next water-balance kernel exactly then. */
+int sphy_set_overlap_tail(sphy_ctx *ctx, int on, void *main_pass_event);
 /* Optional per-phase device timing of SPHY_ROUTE_SCAN (what bench.py's second roofline entry is measured with): while
  * enabled every routing step records four CUDA events on its stream; sphy_route_profile_read synchronises on the last
  * one and returns the mean milliseconds per step of {main pass, tile totals + crossing cells, trunk cells (incl. the

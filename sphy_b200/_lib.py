@@ -138,6 +138,7 @@ SYMBOLS = {
     "sphy_set_ncells": (C.c_int, [P, C.c_int64]),
     "sphy_module_op": (C.c_int, [P, C.c_int, C.POINTER(SphyParam), C.c_int, C.POINTER(P), C.c_int, C.c_int64, C.c_float, C.c_int, P]),
     "sphy_scan_tile_cells": (C.c_int, []),
+    "sphy_set_overlap_tail": (C.c_int, [P, C.c_int, P]),
     "sphy_route_profile": (C.c_int, [P, C.c_int]),
     "sphy_route_profile_read": (C.c_int, [P, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "sphy_p2p_setup_local": (C.c_int, [P, C.c_int, C.c_int64, P, P]),

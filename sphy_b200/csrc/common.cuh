@@ -51,6 +51,10 @@ struct sphy_ctx {
     // scan routing (route_scan.cu): static lists of the cells whose index range crosses a tile boundary + workspaces
     bool scan_ready = false;
     bool scan_smem_opt_in = false;
+    bool overlap_tail = false;     // sphy_set_overlap_tail: the routing tail runs under the next step's water-balance kernel
+    void *main_pass_event = nullptr;   // caller's cudaEvent_t recorded right behind the main pass (or NULL)
+    double *scan_base = nullptr;   // [ncomp][nblocks] second level of the tile-total prefix (small-CTA scan)
+    unsigned *scan_counter = nullptr;
     // confluence exchange over peer memory (route_scan.cu)
     double *p2p_recv = nullptr, **p2p_peer_recv = nullptr;
     long long *p2p_flags = nullptr, **p2p_peer_flags = nullptr;

@@ -43,7 +43,9 @@ struct ScanArgs {
     double *park_before;                  // [ncomp][n_cross] tile-local exclusive prefix at the crossing cell
     double *park_end;                     // [ncomp][n_cross] tile-local inclusive prefix at its range end
     double *tile_tot;                     // [ncomp][ntiles+1] tile totals (+ a trailing 0 so the scan yields the grand total)
-    double *tile_excl;                    // [ncomp][ntiles+1] exclusive prefix of the totals
+    double *tile_excl;                    // [ncomp][ntiles+1] exclusive prefix of the totals (within 1024-entry blocks when tile_base != NULL)
+    const double *tile_base;              // [ncomp][nblocks] exclusive prefix of the block totals, or NULL
+    int32_t tile_nb;
     // published prefixes (trunk cells; on a partitioned basin they are what the ranks exchange)
     int32_t n_pub;
     const int32_t *pub_e;
@@ -74,6 +76,13 @@ __device__ __forceinline__ double range_diff(double hi, double lo)
 {
     const double d = hi - lo;
     return fabs(d) <= 3.6e-15 * fabs(hi) ? 0.0 : d;            // 32 ulp of the minuend
+}
+
+// exclusive prefix of the tile totals at tile t of component c (two-level when the small-CTA scan produced it)
+__device__ __forceinline__ double tile_prefix(const ScanArgs &a, int c, int32_t t)
+{
+    const double x = a.tile_excl[(int64_t)c * (a.ntiles + 1) + t];
+    return a.tile_base ? x + a.tile_base[(int64_t)c * a.tile_nb + (t >> 10)] : x;
 }
 
 // recession blend of one cell: routing.py:28, or advanced_routing.py:31-37 on a lake/reservoir network
@@ -254,22 +263,25 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_MIN_CTAS) k_scan_main(const
 
 // cells whose upstream range crosses a tile boundary
 constexpr int CROSS_ILP = 4;       // crossing cells per thread: four independent gather chains in flight
+// The kernels behind the main pass run 128-thread CTAs with a modest register budget, so that one CTA of them fits on an SM
+// next to the resident CTAs of the NEXT step's water-balance kernel: with SphyModel(overlap_routing=True) this latency-bound
+// tail (tile totals, crossing cells, publish / peer push, flag wait, trunk kernels) runs on its own stream underneath it.
+constexpr int TAIL_THREADS = 128;
 
 __device__ __forceinline__ void scan_cross_block(const ScanArgs &a, int32_t block)
 {
-    const int32_t k0 = block * (256 * CROSS_ILP) + threadIdx.x;
+    const int32_t k0 = block * (TAIL_THREADS * CROSS_ILP) + threadIdx.x;
     int32_t r[CROSS_ILP], e[CROSS_ILP];
     bool ok[CROSS_ILP];
 #pragma unroll
     for (int j = 0; j < CROSS_ILP; ++j) {
-        const int32_t k = k0 + j * 256;
+        const int32_t k = k0 + j * TAIL_THREADS;
         ok[j] = k < a.n_cross;
         r[j] = ok[j] ? __ldg(a.cross_r + k) : 0;
         e[j] = ok[j] ? __ldg(a.cross_e + k) : 0;
     }
     for (int c = 0; c < a.ncomp; ++c) {
         const double *T = a.tile_tot + (int64_t)c * (a.ntiles + 1);
-        const double *X = a.tile_excl + (int64_t)c * (a.ntiles + 1);
         const double *PB = a.park_before + (int64_t)c * a.n_cross;
         const double *PE = a.park_end + (int64_t)c * (a.n_cross + a.n_pub);
         float *qs = a.qstate[c];
@@ -277,7 +289,7 @@ __device__ __forceinline__ void scan_cross_block(const ScanArgs &a, int32_t bloc
         float qold[CROSS_ILP], kx[CROSS_ILP];
 #pragma unroll
         for (int j = 0; j < CROSS_ILP; ++j) {                  // all gathers first
-            const int32_t k = k0 + j * 256;
+            const int32_t k = k0 + j * TAIL_THREADS;
             tt[j] = ok[j] ? T[r[j] / SCAN_TILE] : 0.0;
             pb[j] = ok[j] ? PB[k] : 0.0;
             pe[j] = ok[j] ? PE[k] : 0.0;
@@ -289,7 +301,7 @@ __device__ __forceinline__ void scan_cross_block(const ScanArgs &a, int32_t bloc
             if (!ok[j]) continue;
             const int32_t ta = r[j] / SCAN_TILE, te = e[j] / SCAN_TILE;
             // suffix of the first tile + whole tiles in between (none for most crossing cells) + prefix of the last tile
-            const double s = range_diff(tt[j], pb[j]) + (te > ta + 1 ? range_diff(X[te], X[ta + 1]) : 0.0) + pe[j];
+            const double s = range_diff(tt[j], pb[j]) + (te > ta + 1 ? range_diff(tile_prefix(a, c, te), tile_prefix(a, c, ta + 1)) : 0.0) + pe[j];
             const float omk = a.kxc[c].map ? 1.0f - kx[j] : a.omkc[c];
             qs[r[j]] = blend(a, r[j], (float)s, qold[j], kx[j], omk);
         }
@@ -318,14 +330,14 @@ struct P2PArgs {
 // One launch finishes the ordinary tile-crossing cells (blocks [0, n_cross_blocks)) and publishes the range total and the
 // range-local inclusive prefix at every published position (the remaining blocks) -- what the trunk cells are finished
 // from; on a partitioned basin that block is the "confluence inflow" message of the rank.
-__global__ void __launch_bounds__(256) k_scan_cross_pub(const __grid_constant__ ScanArgs a, const __grid_constant__ P2PArgs p,
+__global__ void __launch_bounds__(TAIL_THREADS, 5) k_scan_cross_pub(const __grid_constant__ ScanArgs a, const __grid_constant__ P2PArgs p,
                                                         int n_cross_blocks)
 {
     if ((int)blockIdx.x < n_cross_blocks) {
         scan_cross_block(a, blockIdx.x);
         return;
     }
-    const int32_t i = (blockIdx.x - n_cross_blocks) * 256 + threadIdx.x;      // 0: the range total, 1 + j: position j
+    const int32_t i = (blockIdx.x - n_cross_blocks) * TAIL_THREADS + threadIdx.x;      // 0: the range total, 1 + j: position j
     long long step = 0;
     size_t slot = 0;
     if (p.on) {
@@ -334,9 +346,8 @@ __global__ void __launch_bounds__(256) k_scan_cross_pub(const __grid_constant__ 
     }
     if (i <= a.n_pub) {
         for (int c = 0; c < a.ncomp; ++c) {
-            const double *X = a.tile_excl + (int64_t)c * (a.ntiles + 1);
-            const double v = i == 0 ? X[a.ntiles]
-                                    : X[a.pub_e[i - 1] / SCAN_TILE] + a.park_end[(int64_t)c * (a.n_cross + a.n_pub) + a.n_cross + i - 1];
+            const double v = i == 0 ? tile_prefix(a, c, a.ntiles)
+                                    : tile_prefix(a, c, a.pub_e[i - 1] / SCAN_TILE) + a.park_end[(int64_t)c * (a.n_cross + a.n_pub) + a.n_cross + i - 1];
             const int64_t o = (int64_t)c * a.stride + i;
             if (a.send) a.send[o] = v;
             if (p.on)
@@ -382,9 +393,9 @@ struct TrunkArgs {
     P2PArgs p2p;
 };
 
-constexpr int TRUNK_BLOCK = 512;
+constexpr int TRUNK_BLOCK = TAIL_THREADS;
 
-__global__ void __launch_bounds__(TRUNK_BLOCK) k_trunk_drift(const __grid_constant__ ScanArgs a, const __grid_constant__ TrunkArgs t)
+__global__ void __launch_bounds__(TRUNK_BLOCK, 5) k_trunk_drift(const __grid_constant__ ScanArgs a, const __grid_constant__ TrunkArgs t)
 {
     typedef cub::BlockScan<double, TRUNK_BLOCK> Scan;
     __shared__ typename Scan::TempStorage tmp;
@@ -468,7 +479,7 @@ __global__ void __launch_bounds__(TRUNK_BLOCK) k_trunk_drift(const __grid_consta
     }
 }
 
-__global__ void __launch_bounds__(256) k_trunk_apply(const __grid_constant__ ScanArgs a, const __grid_constant__ TrunkArgs t)
+__global__ void __launch_bounds__(TAIL_THREADS, 5) k_trunk_apply(const __grid_constant__ ScanArgs a, const __grid_constant__ TrunkArgs t)
 {
     const int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= t.m) return;
@@ -493,15 +504,16 @@ __global__ void __launch_bounds__(256) k_trunk_apply(const __grid_constant__ Sca
 // exclusive prefix of the tile totals (ntiles + 1 entries per component: the trailing 0 makes X[ntiles] the range total);
 // one CTA per component: for ranges of at most 4096 tiles (small basins, where launches dominate) one launch instead of
 // a library scan per component; larger ranges use cub's single-pass scan
-__global__ void __launch_bounds__(1024) k_tile_scan(const double *__restrict__ tot, double *__restrict__ excl, int32_t count)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_tile_scan(const double *__restrict__ tot, double *__restrict__ excl, int32_t count)
 {
-    typedef cub::BlockScan<double, 1024> Scan;
+    typedef cub::BlockScan<double, THREADS> Scan;
     __shared__ typename Scan::TempStorage tmp;
     const double *T = tot + (int64_t)blockIdx.x * count;
     double *X = excl + (int64_t)blockIdx.x * count;
     constexpr int PER = 4;
     double carry = 0.0;
-    for (int32_t b0 = 0; b0 < count; b0 += 1024 * PER) {
+    for (int32_t b0 = 0; b0 < count; b0 += THREADS * PER) {
         double v[PER], ex[PER], total;
 #pragma unroll
         for (int k = 0; k < PER; ++k) {
@@ -517,6 +529,53 @@ __global__ void __launch_bounds__(1024) k_tile_scan(const double *__restrict__ t
         }
         carry += total;
     }
+}
+
+// The same scan for the overlapped tail: blocks of 128 threads scan 1024 entries each (local exclusive prefix) and the last
+// block to finish turns the block totals into their exclusive prefix; readers add the two levels (tile_prefix).  Small
+// CTAs, many of them: they fit next to the resident CTAs of the water-balance kernel and still finish in microseconds.
+__global__ void __launch_bounds__(TAIL_THREADS) k_tile_scan_small(const double *__restrict__ tot, double *__restrict__ excl, int32_t count,
+                                                                  double *__restrict__ base, int32_t nb, unsigned *counter)
+{
+    typedef cub::BlockScan<double, TAIL_THREADS> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    __shared__ bool is_last;
+    constexpr int PER = 1024 / TAIL_THREADS;
+    const int c = blockIdx.y;
+    const double *T = tot + (int64_t)c * count;
+    double *X = excl + (int64_t)c * count;
+    double v[PER], ex[PER], total;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int32_t i = blockIdx.x * 1024 + threadIdx.x * PER + k;
+        v[k] = i < count ? T[i] : 0.0;
+    }
+    Scan(tmp).ExclusiveSum(v, ex, total);
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int32_t i = blockIdx.x * 1024 + threadIdx.x * PER + k;
+        if (i < count) X[i] = ex[k];
+    }
+    if (threadIdx.x == 0) base[(int64_t)c * nb + blockIdx.x] = total;          // the block total, replaced by the prefix below
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(counter, 1u) == gridDim.x * gridDim.y - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int cc = 0; cc < (int)gridDim.y; ++cc) {
+        double carry = 0.0;
+        for (int32_t b0 = 0; b0 < nb; b0 += TAIL_THREADS) {
+            const int32_t b = b0 + threadIdx.x;
+            const double bt = b < nb ? __ldcg(base + (int64_t)cc * nb + b) : 0.0;
+            double e, t2;
+            __syncthreads();
+            Scan(tmp).ExclusiveSum(bt, e, t2);
+            if (b < nb) base[(int64_t)cc * nb + b] = carry + e;
+            carry += t2;
+        }
+    }
+    if (threadIdx.x == 0) *counter = 0u;
 }
 
 // ---- one-time construction of the crossing lists ---------------------------------------------------------
@@ -650,6 +709,10 @@ static int scan_prepare(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm,
             (rc = dev_alloc(ctx, &ctx->scan_excl, (size_t)ncomp * (ctx->n_tiles + 1))))
             return rc;
         SPHY_CUDA(ctx, cudaMemsetAsync(ctx->scan_tile, 0, sizeof(double) * (size_t)ncomp * (ctx->n_tiles + 1), st));
+        if ((rc = dev_alloc(ctx, &ctx->scan_base, (size_t)ncomp * div_up(ctx->n_tiles + 1, 1024))) ||
+            (rc = dev_alloc_once(ctx, &ctx->scan_counter, 1)))
+            return rc;
+        SPHY_CUDA(ctx, cudaMemsetAsync(ctx->scan_counter, 0, sizeof(unsigned), st));
         size_t need = 0;
         SPHY_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, need, ctx->scan_tile, ctx->scan_excl, ctx->n_tiles + 1, st));
         if (need > ctx->scan_tmp_bytes) {
@@ -746,8 +809,15 @@ static int scan_launch_local(sphy_ctx *ctx, ScanArgs &a, cudaStream_t st, bool p
         else k_scan_main<false, false><<<grid, SCAN_THREADS, SCAN_SMEM, st>>>(a);
     }
     prof_mark(ctx, st);
-    if (ctx->n_tiles + 1 <= 4 * 1024) {                        // small ranges: one CTA per component, one launch
-        k_tile_scan<<<a.ncomp, 1024, 0, st>>>(ctx->scan_tile, ctx->scan_excl, ctx->n_tiles + 1);
+    if (ctx->main_pass_event) SPHY_CUDA(ctx, cudaEventRecord((cudaEvent_t)ctx->main_pass_event, st));
+    if (ctx->overlap_tail) {                                   // small CTAs that fit beside the next water-balance kernel
+        const int nb = div_up(ctx->n_tiles + 1, 1024);
+        k_tile_scan_small<<<dim3(nb, a.ncomp), TAIL_THREADS, 0, st>>>(ctx->scan_tile, ctx->scan_excl, ctx->n_tiles + 1, ctx->scan_base, nb,
+                                                                      ctx->scan_counter);
+        a.tile_base = ctx->scan_base;
+        a.tile_nb = nb;
+    } else if (ctx->n_tiles + 1 <= 4 * 1024) {                 // small ranges: one CTA per component, one launch
+        k_tile_scan<1024><<<a.ncomp, 1024, 0, st>>>(ctx->scan_tile, ctx->scan_excl, ctx->n_tiles + 1);
     } else {                                                   // single-pass decoupled look-back scan of the library
         for (int c = 0; c < a.ncomp; ++c) {
             size_t need = ctx->scan_tmp_bytes;
@@ -755,9 +825,9 @@ static int scan_launch_local(sphy_ctx *ctx, ScanArgs &a, cudaStream_t st, bool p
                                                          ctx->scan_excl + (size_t)c * (ctx->n_tiles + 1), ctx->n_tiles + 1, st));
         }
     }
-    const int ncb = div_up(ctx->n_cross, 256 * CROSS_ILP);
-    const int npb = publish ? div_up(ctx->n_pub + 1, 256) : 0;
-    if (ncb + npb > 0) k_scan_cross_pub<<<ncb + npb, 256, 0, st>>>(a, p2p_args(ctx, push), ncb);
+    const int ncb = div_up(ctx->n_cross, TAIL_THREADS * CROSS_ILP);
+    const int npb = publish ? div_up(ctx->n_pub + 1, TAIL_THREADS) : 0;
+    if (ncb + npb > 0) k_scan_cross_pub<<<ncb + npb, TAIL_THREADS, 0, st>>>(a, p2p_args(ctx, push), ncb);
     prof_mark(ctx, st);
     return SPHY_OK;
 }
@@ -805,7 +875,7 @@ static int trunk_finish(sphy_ctx *ctx, const ScanArgs &a, const double *gathered
     t.p2p = p2p_args(ctx, p2p);
     t.timed_out = p2p ? reinterpret_cast<const int *>(ctx->p2p_flags + ctx->p2p_world) : nullptr;
     k_trunk_drift<<<ctx->sl_nblk, TRUNK_BLOCK, 0, st>>>(a, t);
-    k_trunk_apply<<<div_up(ctx->sl_n, 256), 256, 0, st>>>(a, t);
+    k_trunk_apply<<<div_up(ctx->sl_n, TAIL_THREADS), TAIL_THREADS, 0, st>>>(a, t);
     return SPHY_OK;
 }
 
@@ -924,6 +994,14 @@ int route_scan_run_adv(sphy_ctx *ctx, float *material_m3day, float *q_state, sph
     rc = scan_launch_local(ctx, a, st);
     if (rc != SPHY_OK) return rc;
     SPHY_LAUNCH_CHECK(ctx);
+    return SPHY_OK;
+}
+
+extern "C" int sphy_set_overlap_tail(sphy_ctx *ctx, int on, void *main_pass_event)
+{
+    if (!ctx) return SPHY_E_INVALID;
+    ctx->overlap_tail = on != 0;
+    ctx->main_pass_event = on ? main_pass_event : nullptr;
     return SPHY_OK;
 }
 

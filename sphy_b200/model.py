@@ -201,7 +201,7 @@ class StepGraph:
 class SphyModel:
     def __init__(self, cfg, maps: MapSource, device="cuda:0", route_method="scan", diagnostics=False,
                  collect_tss=True, cell_order="dfs", rank=0, world=1, share_from=None, reporting=False, write_outputs=False,
-                 ra_mode="auto", scan_drift=True):
+                 ra_mode="auto", scan_drift=True, overlap_routing=False):
         if not torch.cuda.is_available():
             raise RuntimeError("SphyModel needs a CUDA device (B200); there is no CPU fallback")
         self.lib = _lib.load()
@@ -216,6 +216,10 @@ class SphyModel:
         self.cell_order_mode = {"rowmajor": _lib.ORDER_ROWMAJOR, "dfs": _lib.ORDER_DFS}[cell_order]
         if self.route_method == _lib.ROUTE_SCAN and self.cell_order_mode != _lib.ORDER_DFS:
             raise ValueError("route_method='scan' needs cell_order='dfs'")
+        # overlap_routing: route day t on a second stream while the water-balance kernel of day t + 1 runs (nothing in the
+        # vertical balance reads the routed discharge).  Routed maps (QRAold, the .tss samples) are then only valid after
+        # sync(); everything else behaves as before.  Plain total-flow scan routing only; otherwise silently sequential.
+        self.overlap_routing = bool(overlap_routing)
         self.scan_drift = bool(scan_drift)   # scan routing: carry the reference's REAL4 rounding drift on the trunk cells
         self.ra_mode = ra_mode           # auto | table (latitude classes) | cell (per-cell sin/cos/tan maps)
         self.rank, self.world = int(rank), int(world)
@@ -286,6 +290,7 @@ class SphyModel:
     # ------------------------------------------------------------------------------------------
     def close(self):
         if getattr(self, "_ctx", None):
+            self.sync()
             torch.cuda.synchronize(self.device)
             self.check_exchange()
             if self._owns_ctx:
@@ -302,6 +307,7 @@ class SphyModel:
 
     def check_exchange(self):
         """Raise if a peer-memory confluence exchange gave up waiting for a peer since the last check (synchronises)."""
+        self.sync()
         if getattr(self, "_mg_p2p", False) and self.lib.sphy_p2p_timed_out(self._ctx, self._stream()):
             raise RuntimeError("a peer-memory confluence exchange timed out: discharges of this run are not valid "
                                "(the trunk cells of the affected steps hold NaN)")
@@ -669,6 +675,15 @@ class SphyModel:
         if self.ETOpenWaterFLAG == 1:
             self.out["ETOpenWater"] = self._full(0.0)                   # ET.ETpot(ETref, kcOpenWater), sphy.py:898
         self._prepare_wb_structs()
+        self._ovl = None
+        if (self.overlap_routing and self.RoutFLAG == 1 and self.ResFLAG != 1 and self.LakeFLAG != 1 and self.SedFLAG != 1
+                and self.GlacFLAG != 1 and self.route_method == _lib.ROUTE_SCAN and not any(self.RA_FLAG.values())
+                and not self.diagnostics and self._share_from is None):
+            lo, hi = torch.cuda.Stream.priority_range()
+            ev = torch.cuda.Event()
+            ev.record()                                        # materialises the cudaEvent_t the library records behind the main pass
+            self._ovl = {"stream": torch.cuda.Stream(device=self.device, priority=hi), "main_pass": ev}
+            self._ck(self.lib.sphy_set_overlap_tail(self._ctx, 1, C.c_void_p(ev.cuda_event)), "sphy_set_overlap_tail")
         if self.SedFLAG == 1:
             self._sediment_initial()
         # time series at `Locations` (TimeoutputTimeseries, sphy.py:683-691): cells with id > 0, ordered by id
@@ -1413,6 +1428,8 @@ class SphyModel:
         if self.GlacFLAG == 1 and self.RoutFLAG == 1 and not (self.LakeFLAG == 1 or self.ResFLAG == 1):
             deferred = self._glacier_reporting(F)                                              # sphy.py:1106-1112
         prof = self._prof
+        if self._ovl is not None and route:
+            return self._device_step_overlapped(F, doy, ra_table)
         if prof is not None:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             ev[0].record()
@@ -1440,12 +1457,47 @@ class SphyModel:
             if self.SedTransFLAG == 1:
                 self.sediment_transport.dynamic_mmf(self, None, None, None, G)
 
+    def _device_step_overlapped(self, F, doy, ra_table):
+        """The water-balance kernel of this day on the current stream, its routing on the routing stream.  Only the main
+        pass of the routing is bandwidth-bound; everything behind it (tile totals, crossing cells, publish / peer push, the
+        wait for the other ranks, the trunk kernels) is a latency-bound tail of small kernels.  The next day's water-balance
+        kernel starts as soon as the main pass is done (an event the library records right behind it -- the main pass is
+        also the only reader of TotR) and the tail runs underneath it, in CTAs small enough to be co-resident."""
+        o = self._ovl
+        main, rt = torch.cuda.current_stream(self.device), o["stream"]
+        main.wait_event(o["main_pass"])                        # the main pass of the previous day's routing has finished
+        prof = self._prof
+        if prof is not None:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record(main)
+        self._ck(self.lib.sphy_wb_step(self._ctx, C.byref(self._wbP), C.byref(self._wbS), C.byref(F), C.byref(self._wbO),
+                                       doy if ra_table else -1, self._stream()), "sphy_wb_step")
+        done = torch.cuda.Event()
+        done.record(main)
+        if prof is not None:
+            ev[1].record(main)
+        with torch.cuda.stream(rt):
+            rt.wait_event(done)
+            if prof is not None:
+                ev[2].record(rt)
+            self.Q = self.routing.dynamic(self, None, self.TotR)
+            if prof is not None:
+                ev[3].record(rt)
+                prof["wb"].append((ev[0], ev[1]))
+                prof["route"].append((ev[2], ev[3]))
+
+    def sync(self):
+        """Make the routed maps of the last step visible to the current stream (only needed with overlap_routing)."""
+        if getattr(self, "_ovl", None) is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self._ovl["stream"])
+
     def _post_step(self):
         """Time series at the stations, reporting, the date."""
         if self.collect_tss and self.Q is not None and len(self.station_ids):
-            self._ck(self.lib.sphy_sample(self._ctx, self.Q.data_ptr(), self._station_cells.data_ptr(), len(self.station_ids),
-                                          self._station_buf.data_ptr(), self._stream()), "sphy_sample")
-            self.tss["QallRAtot"].append(self._station_buf[: len(self.station_ids)].clone())
+            with torch.cuda.stream(self._ovl["stream"] if self._ovl is not None else torch.cuda.current_stream(self.device)):
+                self._ck(self.lib.sphy_sample(self._ctx, self.Q.data_ptr(), self._station_cells.data_ptr(), len(self.station_ids),
+                                              self._station_buf.data_ptr(), self._stream()), "sphy_sample")
+                self.tss["QallRAtot"].append(self._station_buf[: len(self.station_ids)].clone())
         self.timestep += 1
         if self.world > 1 and (self.timestep % 32 == 0 or self.report is not None):
             self.check_exchange()          # before anything of this step leaves the device (reports, every 32 steps otherwise)
@@ -1469,7 +1521,7 @@ class SphyModel:
         self._graphs = StepGraph.state(self) if on else None
 
     def _graph_ok(self):
-        return (self.DynVegFLAG != 1 and self.GlacFLAG != 1 and self.ResFLAG != 1 and self.LakeFLAG != 1 and self.SedFLAG != 1
+        return (self._ovl is None and self.DynVegFLAG != 1 and self.GlacFLAG != 1 and self.ResFLAG != 1 and self.LakeFLAG != 1 and self.SedFLAG != 1
                 and not self._series and self._prof is None and self.ETOpenWaterFLAG != 1
                 and (self.ETREF_FLAG == 1 or self._wbP.ra_mode == _lib.RA_TABLE)
                 and (self.world == 1 or getattr(self, "_mg_p2p", None) is True))

@@ -126,7 +126,8 @@ def bench_main(args, rank, world):
     cat = bench.make_case(args.size)
     tmp = tempfile.mkdtemp(prefix=f"sphy_bench_r{rank}_")
     cfg = cat.write_inputs(os.path.join(tmp, "in"), os.path.join(tmp, "out"))
-    model = SphyModel(cfg, CatchmentSource(cat), device=str(dev), route_method="scan", diagnostics=False, rank=rank, world=world)
+    model = SphyModel(cfg, CatchmentSource(cat), device=str(dev), route_method="scan", diagnostics=False, rank=rank, world=world,
+                      overlap_routing=not args.no_overlap)
     model.initial()
     n_local, n_global = model.n, model.n_global
     dem_dev = torch.from_numpy(model._compact_np(cat.dem)).to(dev)
@@ -143,6 +144,7 @@ def bench_main(args, rank, world):
         e0.record()
         for _ in range(nsteps):
             model.dynamic()
+        model.sync()                                           # the routing stream's last step is inside the timed region
         e1.record()
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -193,6 +195,7 @@ def bench_main(args, rank, world):
     for _ in range(e2e_steps):
         model.dynamic()
         if model.tss["QallRAtot"]:
+            model.sync()
             q = model.tss["QallRAtot"][-1].cpu()
             d2h += q.numel() * 4
     torch.cuda.synchronize()
@@ -214,7 +217,7 @@ def bench_main(args, rank, world):
                                     f"{model._mg_stride} float64 per rank (confluence inflows; "
                                     + ("stores into peer memory over NVLink + flags" if getattr(model, "_mg_p2p", False)
                                        else "NCCL all-gather") + ")",
-                       "routing": "scan", "trunk_cells": model.trunk_cells, "forcing_ring_days": args.ring, "setup_s": round(setup_s, 1),
+                       "routing": "scan", "trunk_cells": model.trunk_cells, "overlap_routing": model._ovl is not None, "forcing_ring_days": args.ring, "setup_s": round(setup_s, 1),
                        "host_affinity": f"rank 0 bound to the {numa_cpus} CPUs NVML lists next to its GPU" if numa_cpus else "unchanged",
                        "l2": "per-GPU per-step working set %.2f GB (larger than the 126 MB L2)" % (bench.ALG_BYTES_WB * n_local / 1e9)},
             "roofline": {"kernel": "k_wb_step (fused vertical water balance), rank 0", "bound": "hbm", "achieved": ach, "peak": peak,

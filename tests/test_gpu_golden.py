@@ -612,3 +612,28 @@ def test_netcdf_forcing_matches_griddata():
         assert torch.equal(getattr(nc_model, k), getattr(ref_model, k)), k
     nc_model.close()
     ref_model.close()
+
+
+def test_overlapped_routing_is_bit_identical(monkeypatch):
+    """overlap_routing=True: the routing of day t runs on a second stream underneath the water-balance kernel of day t + 1
+    (two TotR maps, small-CTA tail kernels, sphy_set_overlap_tail).  Same states, same discharge, same station series."""
+    import datetime
+    import torch
+    from sphy_b200 import synth
+    monkeypatch.setenv("SPHY_WB_PREFETCH", "2")
+    monkeypatch.setenv("SPHY_TRUNK_MIN_CELLS", "1100")
+    cat = synth.make_catchment(nrows=420, ncols=380, seed=13, nsteps=30, start=datetime.date(2001, 6, 1),
+                               params=dict(SubWater=470.0, RootDepthFlat=150.0, Pscale=2.5))
+    seq = make_model(cat, route_method="scan")
+    ovl = make_model(cat, route_method="scan", overlap_routing=True)
+    assert ovl._ovl is not None and ovl.trunk_cells > 0
+    for _ in range(30):
+        seq.dynamic()
+        ovl.dynamic()
+    ovl.sync()
+    torch.cuda.synchronize()
+    for k in ("RootWater", "SubWater", "Gw", "BaseR", "H_gw", "QRAold", "TotR"):
+        assert torch.equal(getattr(seq, k), getattr(ovl, k)), k
+    assert torch.equal(torch.stack(seq.tss["QallRAtot"]), torch.stack(ovl.tss["QallRAtot"]))
+    ovl.close()
+    seq.close()

@@ -131,8 +131,9 @@ def test_partitioned_scan_matches_single_context(world, shape, outlets, ncomp, t
     lib.sphy_ctx_destroy(ref)
 
 
-@pytest.mark.parametrize("exchange,glacier", [("p2p", False), ("nccl", False), ("p2p", True)])
-def test_real_two_gpu_exchange(exchange, glacier):
+@pytest.mark.parametrize("exchange,glacier,overlap", [("p2p", False, False), ("nccl", False, False), ("p2p", True, False),
+                                                      ("p2p", False, True), ("nccl", False, True)])
+def test_real_two_gpu_exchange(exchange, glacier, overlap):
     """Two real ranks (one per GPU) under torch.distributed.run: both confluence exchanges -- stores into peer memory over
     NVLink with flags, and the NCCL all-gather -- against the unpartitioned basin and the level sweep
     (tools/check_multigpu.py).  Skipped where only one GPU is visible."""
@@ -145,12 +146,12 @@ def test_real_two_gpu_exchange(exchange, glacier):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    port = 29600 + (os.getpid() % 300) + (0 if exchange == "p2p" else 301) + (602 if glacier else 0)
+    port = 29600 + (os.getpid() % 300) + (0 if exchange == "p2p" else 301) + (602 if glacier else 0) + (1203 if overlap else 0)
     env = dict(os.environ, SPHY_MG_EXCHANGE=exchange)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", str(port), os.path.join(root, "tools", "check_multigpu.py"), "--rows", "1500", "--cols", "1300",
-                        "--steps", "4"] + (["--glacier"] if glacier else []), env=env, capture_output=True, text=True, timeout=900, cwd=root)
+                        "--steps", "4"] + (["--glacier"] if glacier else []) + (["--overlap"] if overlap else []), env=env, capture_output=True, text=True, timeout=900, cwd=root)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith('{"tool"')][-1])
-    assert line["exchange"] == exchange and line["world"] == 2
+    assert line["exchange"] == exchange and line["world"] == 2 and line["overlap_routing"] == overlap
     assert line["worst_rel_partitioned_vs_one_gpu"] <= 3e-7 and line["worst_rel_partitioned_vs_level_sweep"] <= 1e-5

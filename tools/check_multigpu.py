@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--bench-size", type=int, default=0, help="use bench.py's basin of this size and its device forcing instead")
     ap.add_argument("--glacier", action="store_true", help="snow and glacier modules on (BASELINE config 2 physics): the fragment "
                                                            "table is split by rank")
+    ap.add_argument("--overlap", action="store_true", help="partitioned model with overlap_routing=True (routing on a second stream)")
     args = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -49,8 +50,8 @@ def main():
         if args.glacier:
             par.update(Toffset=15.0, RootKsat=12.0)
         cat = synth.make_catchment(nrows=args.rows, ncols=args.cols, seed=77, nsteps=args.steps, start=datetime.date(2001, 5, 1),
-                                   rout_components=True, params=par, **extra)
-        comps = ("QRAold", "RootRRAold", "BaseRAold") + (("GlacRAold", "SnowRAold") if args.glacier else ())
+                                   rout_components=not args.overlap, params=par, **extra)
+        comps = ("QRAold",) if args.overlap else ("QRAold", "RootRRAold", "BaseRAold") + (("GlacRAold", "SnowRAold") if args.glacier else ())
     tmp = tempfile.mkdtemp(prefix=f"sphy_mgcheck_r{rank}_")
     cfg = cat.write_inputs(os.path.join(tmp, "in"), os.path.join(tmp, "out"))
     kw = dict(device=str(dev), collect_tss=False)
@@ -58,7 +59,7 @@ def main():
     whole.initial()
     lev = SphyModel(cfg, CatchmentSource(cat), route_method="levels", share_from=whole, **kw)
     lev.initial()
-    part = SphyModel(cfg, CatchmentSource(cat), route_method="scan", rank=rank, world=world, **kw)
+    part = SphyModel(cfg, CatchmentSource(cat), route_method="scan", rank=rank, world=world, overlap_routing=args.overlap, **kw)
     part.initial()
     lo, hi = part.part_range
     if args.bench_size:
@@ -74,6 +75,7 @@ def main():
         whole.dynamic()
         lev.dynamic()
         part.dynamic()
+        part.sync()
         torch.cuda.synchronize()
         for k in comps:
             a = getattr(part, k).double()
@@ -92,7 +94,7 @@ def main():
     check1 = bench.discharge_check(torch, whole)
     part.check_exchange()
     if rank == 0:
-        print(json.dumps({"tool": "check_multigpu", "world": world, "exchange": mode, "cells": whole.n, "steps": args.steps, "glacier": bool(args.glacier),
+        print(json.dumps({"tool": "check_multigpu", "world": world, "exchange": mode, "cells": whole.n, "steps": args.steps, "glacier": bool(args.glacier), "overlap_routing": part._ovl is not None,
                           "trunk_cells_partitioned": part.trunk_cells, "trunk_cells_one_gpu": whole.trunk_cells,
                           "worst_rel_partitioned_vs_one_gpu": float(w[0]), "worst_rel_partitioned_vs_level_sweep": float(w[1]),
                           "worst_rel_one_gpu_scan_vs_level_sweep": float(w[2]), "check_partitioned": check, "check_one_gpu": check1}),
