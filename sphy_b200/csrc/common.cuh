@@ -109,6 +109,10 @@ struct sphy_ctx {
     int32_t chain_k0 = 0, n_chains = 0, chain_level0 = 0;
     int64_t n_chain_cells = 0;
     int32_t *chain_start = nullptr, *chain_k = nullptr, *chain_cell = nullptr, *chain_don = nullptr;
+    int32_t *chain_ids = nullptr;  // short chains first, then the long ones (a CTA each)
+    int32_t n_chains_short = 0, n_chains_long = 0;
+    int32_t mid_level0 = -1;       // levels [mid_level0, chain_level0) run in one cooperative launch (k_sweep_mid); -1: none
+    int mid_grid = 0;
     double *cut_work = nullptr;    // scan path with lakes/reservoirs: range sums of the cut cells
     int cut_work_cap = 0;
     int32_t *cut_ptr = nullptr;    // per-tile ranges of the cut-cell list

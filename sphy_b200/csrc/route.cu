@@ -13,10 +13,13 @@
 // structures are read once.
 #include <cstdio>
 
+#include <cooperative_groups.h>
 #include <cub/cub.cuh>
 #include <cstdlib>
 
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -378,6 +381,7 @@ constexpr unsigned FLUX_PENDING = 0xFFFFFFFFu;      // no arithmetic produces th
 
 struct ChainArgs {
     int32_t n_chains, k0;
+    const int32_t *ids;        // chains handled by this launch (n_chains of them)
     const int32_t *start;      // [n_chains + 1] first slot of every chain
     const int32_t *k;          // [slots] routing position
     const int32_t *cell;       // [slots] cell (device order)
@@ -400,8 +404,9 @@ constexpr int CHAIN_WARPS = 4;
 __global__ void __launch_bounds__(CHAIN_WARPS * 32) k_sweep_chains(const __grid_constant__ SweepArgs a, const __grid_constant__ ChainArgs ch)
 {
     const int lane = threadIdx.x & 31;
-    const int32_t w = blockIdx.x * CHAIN_WARPS + (threadIdx.x >> 5);
-    if (w >= ch.n_chains) return;
+    const int32_t wi = blockIdx.x * CHAIN_WARPS + (threadIdx.x >> 5);
+    if (wi >= ch.n_chains) return;
+    const int32_t w = __ldg(ch.ids + wi);
     const int32_t s0 = __ldg(ch.start + w), len = __ldg(ch.start + w + 1) - s0;
     const bool has_frac = a.frac != nullptr;
     double prev[ROUTE_MAX_COMP];
@@ -456,6 +461,120 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32) k_sweep_chains(const __grid_
         // ---- parallel: store, blend
         if (valid)
             for (int c = 0; c < a.ncomp; ++c) finish(a, c, k, i, mytot[c], ci[c]);
+    }
+}
+
+// Long chains (the main stem: 17 000 cells) with WARP SPECIALISATION: what bounds a chain is the serial float64 add +
+// conversion per cell, ~30 cycles -- but a single warp that also gathers the lateral inflows and finishes the cells spends
+// ~1000 instructions at ~10 cycles each per block of 32 cells.  Here one CTA walks one chain: four producer/finisher
+// warps take every fourth block (gather the laterals into a shared-memory slot, later finish the block's cells from the
+// totals), and ONE consumer warp does nothing but the serial recurrence, block after block, out of shared memory.
+// Slot s belongs to producer warp s: ready[s] = b + 1 announces the laterals of block b, done[s] = b + 1 its totals.
+constexpr int CHAIN_PROD = 4;
+constexpr int CHAIN_LONG = 64;             // chains longer than this get a CTA of their own
+
+__global__ void __launch_bounds__((CHAIN_PROD + 1) * 32) k_sweep_chain_long(const __grid_constant__ SweepArgs a,
+                                                                            const __grid_constant__ ChainArgs ch)
+{
+    __shared__ double s_lat[CHAIN_PROD][ROUTE_MAX_COMP][32];
+    __shared__ double s_tot[CHAIN_PROD][ROUTE_MAX_COMP][32];
+    __shared__ float s_fr[CHAIN_PROD][32];
+    __shared__ volatile int s_ready[CHAIN_PROD], s_done[CHAIN_PROD];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int32_t w = __ldg(ch.ids + blockIdx.x);
+    const int32_t s0 = __ldg(ch.start + w), len = __ldg(ch.start + w + 1) - s0;
+    const int32_t nblocks = (len + 31) >> 5;
+    const bool has_frac = a.frac != nullptr;
+    const bool use_fr = has_frac || a.mode == MODE_CAPACITY;
+    if (threadIdx.x < CHAIN_PROD) { s_ready[threadIdx.x] = 0; s_done[threadIdx.x] = 0; }
+    __syncthreads();
+    if (warp == CHAIN_PROD) {
+        // ---- consumer: the chain itself
+        double prev[ROUTE_MAX_COMP];
+#pragma unroll
+        for (int c = 0; c < ROUTE_MAX_COMP; ++c) prev[c] = 0.0;
+        for (int32_t b = 0; b < nblocks; ++b) {
+            const int slot = b % CHAIN_PROD;
+            const int cnt = min(32, len - (b << 5));
+            while (s_ready[slot] != b + 1) { }
+            __syncwarp();
+            double lat[ROUTE_MAX_COMP], mytot[ROUTE_MAX_COMP];
+            for (int c = 0; c < a.ncomp; ++c) lat[c] = s_lat[slot][c][lane];
+            const float fr = use_fr ? s_fr[slot][lane] : 1.0f;
+            for (int j = 0; j < cnt; ++j) {
+                const float frj = use_fr ? __shfl_sync(0xffffffffu, fr, j) : 1.0f;
+                for (int c = 0; c < a.ncomp; ++c) {
+                    const double tot = __shfl_sync(0xffffffffu, lat[c], j) + prev[c];
+                    if (lane == j) mytot[c] = tot;
+                    prev[c] = (double)flux_of(a.mode, has_frac, tot, frj);
+                }
+            }
+            for (int c = 0; c < a.ncomp; ++c) s_tot[slot][c][lane] = mytot[c];
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) s_done[slot] = b + 1;
+        }
+        return;
+    }
+    // ---- producer / finisher of every CHAIN_PROD-th block
+    for (int32_t b = warp; b < nblocks; b += CHAIN_PROD) {
+        const int slot = warp;
+        const bool valid = (b << 5) + lane < len;
+        const int32_t s = s0 + (b << 5) + lane;
+        int32_t k = 0, i = 0, d[8];
+        if (valid) {
+            k = __ldg(ch.k + s);
+            i = __ldg(ch.cell + s);
+            const int4 d0 = __ldg(reinterpret_cast<const int4 *>(ch.don + (int64_t)s * 8));
+            const int4 d1 = __ldg(reinterpret_cast<const int4 *>(ch.don + (int64_t)s * 8) + 1);
+            d[0] = d0.x; d[1] = d0.y; d[2] = d0.z; d[3] = d0.w; d[4] = d1.x; d[5] = d1.y; d[6] = d1.z; d[7] = d1.w;
+        }
+        CellIn ci[ROUTE_MAX_COMP];
+        for (int c = 0; c < a.ncomp; ++c) {
+            double sum = 0.0;
+            if (valid) {
+                sum = (double)material(a, c, i);
+                ci[c] = load_cell_in(a, c, i);
+                const float *acc = a.acc + (int64_t)c * a.n;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (d[j] >= 0) sum += (double)(d[j] >= ch.k0 ? load_flux_wait(acc + d[j]) : acc[d[j]]);
+            }
+            s_lat[slot][c][lane] = sum;
+        }
+        s_fr[slot][lane] = valid ? ci[0].fr : 1.0f;
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) s_ready[slot] = b + 1;
+        while (s_done[slot] != b + 1) { }
+        __syncwarp();
+        if (valid)
+            for (int c = 0; c < a.ncomp; ++c) finish(a, c, k, i, s_tot[slot][c][lane], ci[c]);
+        __syncwarp();
+    }
+}
+
+// The levels between the per-level launches and the chains (a few hundred levels of 1 000 .. 65 000 cells): ONE cooperative
+// launch walks them level by level with a grid barrier in between, instead of one dependent launch per level.
+constexpr int MID_LEVEL_MAX = 1 << 16;
+
+__global__ void __launch_bounds__(256) k_sweep_mid(const __grid_constant__ SweepArgs a, int32_t l0, int32_t l1)
+{
+    cg::grid_group grid = cg::this_grid();
+    const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, gsz = (int64_t)gridDim.x * blockDim.x;
+    for (int32_t l = l0; l < l1; ++l) {
+        const int32_t kb = __ldg(a.level_ptr + l), ke = __ldg(a.level_ptr + l + 1);
+        for (int64_t k = kb + gt; k < ke; k += gsz) {
+            const int32_t i = __ldg(a.order + k);
+            const int32_t b = __ldg(a.dpos_ptr + k), e = __ldg(a.dpos_ptr + k + 1);
+            for (int c = 0; c < a.ncomp; ++c) {
+                double s = (double)material(a, c, i);
+                const float *acc = a.acc + (int64_t)c * a.n;
+                for (int32_t q = b; q < e; ++q) s += (double)__ldcg(acc + __ldg(a.dpos + q));
+                finish(a, c, k, i, s, load_cell_in(a, c, i));
+            }
+        }
+        grid.sync();
     }
 }
 
@@ -554,7 +673,8 @@ static int build_chains(sphy_ctx *ctx, cudaStream_t st)
     FK(cudaMalloc(&len, sizeof(int32_t) * (nch + 1)));
     int rc = SPHY_OK;
     if (e == cudaSuccess &&
-        ((rc = dev_alloc(ctx, &ctx->chain_start, (size_t)nch + 1)) || (rc = dev_alloc(ctx, &ctx->chain_k, (size_t)T)) ||
+        ((rc = dev_alloc(ctx, &ctx->chain_start, (size_t)nch + 1)) || (rc = dev_alloc(ctx, &ctx->chain_ids, (size_t)nch)) ||
+         (rc = dev_alloc(ctx, &ctx->chain_k, (size_t)T)) ||
          (rc = dev_alloc(ctx, &ctx->chain_cell, (size_t)T)) || (rc = dev_alloc(ctx, &ctx->chain_don, (size_t)T * 8)))) {
         cudaFree(heavy); cudaFree(next); cudaFree(chain_of); cudaFree(idx_in); cudaFree(len);
         return rc;
@@ -570,11 +690,38 @@ static int build_chains(sphy_ctx *ctx, cudaStream_t st)
         k_chain_tables<<<div_up(T, 256), 256, 0, st>>>(ctx->order, ctx->dpos_ptr, ctx->dpos, heavy, chain_of, idx_in, ctx->chain_start, k0,
                                                       ctx->n, ctx->chain_k, ctx->chain_cell, ctx->chain_don);
         FK(cudaGetLastError());
+        // short chains (one warp each) first, then the long ones (a warp-specialised CTA each): a short chain only ever
+        // waits for other short chains (whatever it waits for ends at a lower level than it does), so the two launches
+        // may run one after the other
+        std::vector<int32_t> hlen(nch), ids;
+        FK(cudaMemcpyAsync(hlen.data(), len, sizeof(int32_t) * nch, cudaMemcpyDeviceToHost, st));
+        FK(cudaStreamSynchronize(st));
+        if (e == cudaSuccess) {
+            for (int32_t c = 0; c < nch; ++c) if (hlen[c] <= CHAIN_LONG) ids.push_back(c);
+            ctx->n_chains_short = (int32_t)ids.size();
+            for (int32_t c = 0; c < nch; ++c) if (hlen[c] > CHAIN_LONG) ids.push_back(c);
+            ctx->n_chains_long = nch - ctx->n_chains_short;
+            FK(cudaMemcpyAsync(ctx->chain_ids, ids.data(), sizeof(int32_t) * nch, cudaMemcpyHostToDevice, st));
+        }
         FK(cudaStreamSynchronize(st));
     }
 #undef FK
     cudaFree(heavy); cudaFree(next); cudaFree(chain_of); cudaFree(idx_in); cudaFree(len); cudaFree(tmp);
     if (e != cudaSuccess) SPHY_FAIL(ctx, SPHY_E_CUDA, "build_chains: %s", cudaGetErrorString(e));
+    // the levels in front of the chains that are too narrow to be worth a launch each: one cooperative launch
+    ctx->mid_level0 = -1;
+    {
+        int coop = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+        const char *menv = getenv("SPHY_SWEEP_MID");
+        if (coop && !(menv && menv[0] == '0') &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_mid, 256, 0) == cudaSuccess && per_sm > 0) {
+            ctx->mid_grid = ctx->sm_count * (per_sm < 4 ? per_sm : 4);
+            int lm = l0;
+            while (lm > 0 && ctx->h_level_ptr[lm] - ctx->h_level_ptr[lm - 1] <= MID_LEVEL_MAX) --lm;
+            if (lm < l0) ctx->mid_level0 = lm;
+        }
+    }
     ctx->chain_k0 = k0;
     ctx->chain_level0 = l0;
     ctx->n_chains = nch;
@@ -662,7 +809,8 @@ int route_levels_run(sphy_ctx *ctx, SweepArgs &a, cudaStream_t st)
     bool warmed = false;
     const char *deep_env = getenv("SPHY_SWEEP_DEEP");           // 0 = the two-level pipeline for every narrow run
     const bool deep = !(deep_env && deep_env[0] == '0');
-    const int32_t level_end = ctx->n_chains > 0 ? ctx->chain_level0 : (int32_t)ctx->h_level_ptr.size() - 1;   // chains take over here
+    const int32_t chains_from = ctx->n_chains > 0 ? ctx->chain_level0 : (int32_t)ctx->h_level_ptr.size() - 1;   // chains take over here
+    const int32_t level_end = (ctx->n_chains > 0 && ctx->mid_level0 >= 0) ? ctx->mid_level0 : chains_from;       // ... after k_sweep_mid
     for (SweepPlanSeg seg : ctx->sweep_plan) {
         if (seg.first_level >= level_end) break;
         if (seg.first_level + seg.n_levels > level_end) seg.n_levels = level_end - seg.first_level;
@@ -683,11 +831,23 @@ int route_levels_run(sphy_ctx *ctx, SweepArgs &a, cudaStream_t st)
             else k_sweep_narrow<32><<<1, 32, (size_t)2 * a.ncomp * 4 * sizeof(float), st>>>(a, seg.first_level, seg.n_levels);
         }
     }
+    if (ctx->n_chains > 0 && ctx->mid_level0 >= 0) {
+        int32_t l0 = ctx->mid_level0, l1 = chains_from;
+        void *kargs[] = {(void *)&a, (void *)&l0, (void *)&l1};
+        SPHY_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)k_sweep_mid, dim3(ctx->mid_grid), dim3(256), kargs, 0, st));
+    }
     if (ctx->n_chains > 0) {
-        ChainArgs ch = {ctx->n_chains, ctx->chain_k0, ctx->chain_start, ctx->chain_k, ctx->chain_cell, ctx->chain_don};
         for (int c = 0; c < a.ncomp; ++c)                      // flux slots of the tail: pending until a chain writes them
             SPHY_CUDA(ctx, cudaMemsetAsync(a.acc + (int64_t)c * a.n + ctx->chain_k0, 0xFF, sizeof(float) * ctx->n_chain_cells, st));
-        k_sweep_chains<<<div_up(ctx->n_chains, CHAIN_WARPS), CHAIN_WARPS * 32, 0, st>>>(a, ch);
+        if (ctx->n_chains_short > 0) {
+            ChainArgs ch = {ctx->n_chains_short, ctx->chain_k0, ctx->chain_ids, ctx->chain_start, ctx->chain_k, ctx->chain_cell, ctx->chain_don};
+            k_sweep_chains<<<div_up(ctx->n_chains_short, CHAIN_WARPS), CHAIN_WARPS * 32, 0, st>>>(a, ch);
+        }
+        if (ctx->n_chains_long > 0) {
+            ChainArgs ch = {ctx->n_chains_long, ctx->chain_k0, ctx->chain_ids + ctx->n_chains_short, ctx->chain_start, ctx->chain_k,
+                            ctx->chain_cell, ctx->chain_don};
+            k_sweep_chain_long<<<ctx->n_chains_long, (CHAIN_PROD + 1) * 32, 0, st>>>(a, ch);
+        }
     }
     SPHY_LAUNCH_CHECK(ctx);
     return SPHY_OK;

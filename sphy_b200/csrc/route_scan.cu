@@ -1069,7 +1069,8 @@ extern "C" int sphy_set_partition(sphy_ctx *ctx, int64_t cell_begin, int64_t cel
                       (void **)&ctx->nup, (void **)&ctx->pos, (void **)&ctx->dpos_ptr, (void **)&ctx->dpos, (void **)&ctx->pre,
                       (void **)&ctx->cell_canon, (void **)&ctx->sub_size, (void **)&ctx->acc, (void **)&ctx->qsorted, (void **)&ctx->sweep_rec,
                       (void **)&ctx->tmp_n[0], (void **)&ctx->tmp_n[1], (void **)&ctx->tmp_n[2], (void **)&ctx->tmp_n[3],
-                      (void **)&ctx->chain_start, (void **)&ctx->chain_k, (void **)&ctx->chain_cell, (void **)&ctx->chain_don};
+                      (void **)&ctx->chain_start, (void **)&ctx->chain_k, (void **)&ctx->chain_cell, (void **)&ctx->chain_don,
+                      (void **)&ctx->chain_ids};
     for (void **pp : whole) {
         if (*pp) cudaFree(*pp);
         *pp = nullptr;
