@@ -31,12 +31,17 @@ STREAM_BYTES_WB = 90                   # what this instance streams: 4 forcing, 
 ALG_BYTES_SCAN = 16                    # k_scan_main per routed component: runoff, sub_size, Qold in, Q out
 
 
-def k1_traffic_per_cell():
-    """dram__bytes_read.sum + dram__bytes_write.sum per cell of the K1 launch, from the committed ncu --set full capture."""
+def kernel_traffic_per_cell(kernel="k_wb_step_pf"):
+    """dram__bytes_read.sum + dram__bytes_write.sum per cell of one launch, from the committed ncu --set full capture of the
+    benched kernels at the benched size (profiles/r2_kernel_traffic.json)."""
     try:
-        return float(json.load(open(os.path.join(ROOT, "profiles", "r1_k1_traffic.json")))["dram_bytes_per_cell"])
+        return float(json.load(open(os.path.join(ROOT, "profiles", "r2_kernel_traffic.json")))[kernel]["dram_bytes_per_cell"])
     except Exception:
         return None
+
+
+def k1_traffic_per_cell():
+    return kernel_traffic_per_cell("k_wb_step_pf")
 
 
 def measured_peak():
@@ -428,7 +433,7 @@ def main():
         "roofline": {"kernel": "k_wb_step (fused vertical water balance)", "bound": "hbm", "achieved": ach, "peak": peak,
                      "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak,
                      "traffic": (k1_traffic_per_cell() * n if k1_traffic_per_cell() else None),
-                     "traffic_note": "bytes per launch = ncu dram bytes per cell (profiles/r1_k1_traffic.json, 36e6-cell capture) x cells",
+                     "traffic_note": "bytes per launch = ncu dram bytes per cell (profiles/r2_kernel_traffic.json, 1e8-cell capture) x cells",
                      "alg_bytes_per_cell": ALG_BYTES_WB, "alg_bytes_per_launch": ALG_BYTES_WB * n, "kernel_ms": wb_ms, "route_ms": rt_ms,
                      "streamed_bytes_per_cell": STREAM_BYTES_WB, "achieved_on_streamed_bytes": STREAM_BYTES_WB * n / (wb_ms * 1e-3) / 1e9},
         "roofline_route": scan_roofline(rprof, n, 1, peak),
@@ -461,8 +466,9 @@ def scan_roofline(rprof, n, ncomp, peak):
     if not rprof:
         return None
     ach = ALG_BYTES_SCAN * ncomp * n / (rprof["scan_main_ms"] * 1e-3) / 1e9
+    t = kernel_traffic_per_cell("k_scan_main")
     return dict(rprof, kernel="k_scan_main (float64 tile prefix + range sums + recession blend)", bound="hbm", achieved=ach, peak=peak,
-                unit="GB/s", frac=ach / peak, alg_bytes_per_cell=ALG_BYTES_SCAN * ncomp, traffic=None)
+                unit="GB/s", frac=ach / peak, alg_bytes_per_cell=ALG_BYTES_SCAN * ncomp, traffic=t * n * ncomp if t else None)
 
 
 def model_plan(model):

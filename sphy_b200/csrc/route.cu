@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_sweep_tail(const __grid_constant
 //   parallel part    lane j finishes cell j (store, recession blend) exactly like the level kernels do.
 // The REAL8 sum of a cell adds the same terms as everywhere else (order does not matter: assumption A1), so the result
 // stays bit-identical with the oracle -- a level costs ~40 cycles of latency instead of a CTA barrier and 300 instructions.
-constexpr int CHAIN_MAX = 1024;
+constexpr int CHAIN_MAX = 1024;      // upper bound; build_chains lowers it until every long chain's CTA is resident at once
 constexpr unsigned FLUX_PENDING = 0xFFFFFFFFu;      // no arithmetic produces this NaN payload
 
 struct ChainArgs {
@@ -397,6 +397,27 @@ __device__ __forceinline__ float load_flux_wait(const float *p)
         __nanosleep(40);
     }
     return __uint_as_float(v);
+}
+
+// the lateral inflow of one cell: own material + every donor but the heavy one.  All donor loads are issued before any of
+// them is examined, so their latencies overlap; only slots that still hold the sentinel are polled again.
+__device__ __forceinline__ double chain_lateral(const float *acc, const int32_t (&d)[8], int32_t k0, double own)
+{
+    unsigned v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        v[j] = 0u;
+        if (d[j] >= 0) asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v[j]) : "l"(acc + d[j]));
+    }
+    double s = own;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (d[j] < 0) continue;
+        float f = __uint_as_float(v[j]);
+        if (d[j] >= k0 && v[j] == FLUX_PENDING) f = load_flux_wait(acc + d[j]);
+        s += (double)f;
+    }
+    return s;
 }
 
 constexpr int CHAIN_WARPS = 4;
@@ -438,12 +459,8 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32) k_sweep_chains(const __grid_
         for (int c = 0; c < a.ncomp; ++c) {
             double s = 0.0;
             if (valid) {
-                s = (double)material(a, c, i);
                 ci[c] = load_cell_in(a, c, i);
-                const float *acc = a.acc + (int64_t)c * a.n;
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (d[j] >= 0) s += (double)(d[j] >= ch.k0 ? load_flux_wait(acc + d[j]) : acc[d[j]]);
+                s = chain_lateral(a.acc + (int64_t)c * a.n, d, ch.k0, (double)material(a, c, i));
             }
             lat[c] = s;
         }
@@ -470,14 +487,17 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32) k_sweep_chains(const __grid_
 // warps take every fourth block (gather the laterals into a shared-memory slot, later finish the block's cells from the
 // totals), and ONE consumer warp does nothing but the serial recurrence, block after block, out of shared memory.
 // Slot s belongs to producer warp s: ready[s] = b + 1 announces the laterals of block b, done[s] = b + 1 its totals.
-constexpr int CHAIN_PROD = 4;
+constexpr int CHAIN_PROD = 7;
 constexpr int CHAIN_LONG = 64;             // chains longer than this get a CTA of their own
 
+// NC = 1: one routed map (the usual case) -- every per-component array is a scalar in a register and the 32 serial steps are
+// fully unrolled; NC = ROUTE_MAX_COMP: any number of components (arrays indexed at run time live in local memory).
+template <int NC>
 __global__ void __launch_bounds__((CHAIN_PROD + 1) * 32) k_sweep_chain_long(const __grid_constant__ SweepArgs a,
                                                                             const __grid_constant__ ChainArgs ch)
 {
-    __shared__ double s_lat[CHAIN_PROD][ROUTE_MAX_COMP][32];
-    __shared__ double s_tot[CHAIN_PROD][ROUTE_MAX_COMP][32];
+    __shared__ double s_lat[CHAIN_PROD][NC][32];
+    __shared__ double s_tot[CHAIN_PROD][NC][32];
     __shared__ float s_fr[CHAIN_PROD][32];
     __shared__ volatile int s_ready[CHAIN_PROD], s_done[CHAIN_PROD];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -488,28 +508,43 @@ __global__ void __launch_bounds__((CHAIN_PROD + 1) * 32) k_sweep_chain_long(cons
     const bool use_fr = has_frac || a.mode == MODE_CAPACITY;
     if (threadIdx.x < CHAIN_PROD) { s_ready[threadIdx.x] = 0; s_done[threadIdx.x] = 0; }
     __syncthreads();
+    const int ncomp = NC == 1 ? 1 : a.ncomp;
     if (warp == CHAIN_PROD) {
         // ---- consumer: the chain itself
-        double prev[ROUTE_MAX_COMP];
+        double prev[NC];
 #pragma unroll
-        for (int c = 0; c < ROUTE_MAX_COMP; ++c) prev[c] = 0.0;
+        for (int c = 0; c < NC; ++c) prev[c] = 0.0;
         for (int32_t b = 0; b < nblocks; ++b) {
             const int slot = b % CHAIN_PROD;
             const int cnt = min(32, len - (b << 5));
             while (s_ready[slot] != b + 1) { }
             __syncwarp();
-            double lat[ROUTE_MAX_COMP], mytot[ROUTE_MAX_COMP];
-            for (int c = 0; c < a.ncomp; ++c) lat[c] = s_lat[slot][c][lane];
+            double lat[NC], mytot[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                lat[c] = c < ncomp ? s_lat[slot][c][lane] : 0.0;
+                mytot[c] = 0.0;
+            }
             const float fr = use_fr ? s_fr[slot][lane] : 1.0f;
-            for (int j = 0; j < cnt; ++j) {
+            auto step = [&](int j) {
                 const float frj = use_fr ? __shfl_sync(0xffffffffu, fr, j) : 1.0f;
-                for (int c = 0; c < a.ncomp; ++c) {
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    if (c >= ncomp) break;
                     const double tot = __shfl_sync(0xffffffffu, lat[c], j) + prev[c];
                     if (lane == j) mytot[c] = tot;
                     prev[c] = (double)flux_of(a.mode, has_frac, tot, frj);
                 }
+            };
+            if (cnt == 32) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) step(j);
+            } else {
+                for (int j = 0; j < cnt; ++j) step(j);
             }
-            for (int c = 0; c < a.ncomp; ++c) s_tot[slot][c][lane] = mytot[c];
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+                if (c < ncomp) s_tot[slot][c][lane] = mytot[c];
             __threadfence_block();
             __syncwarp();
             if (lane == 0) s_done[slot] = b + 1;
@@ -529,16 +564,14 @@ __global__ void __launch_bounds__((CHAIN_PROD + 1) * 32) k_sweep_chain_long(cons
             const int4 d1 = __ldg(reinterpret_cast<const int4 *>(ch.don + (int64_t)s * 8) + 1);
             d[0] = d0.x; d[1] = d0.y; d[2] = d0.z; d[3] = d0.w; d[4] = d1.x; d[5] = d1.y; d[6] = d1.z; d[7] = d1.w;
         }
-        CellIn ci[ROUTE_MAX_COMP];
-        for (int c = 0; c < a.ncomp; ++c) {
+        CellIn ci[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            if (c >= ncomp) break;
             double sum = 0.0;
             if (valid) {
-                sum = (double)material(a, c, i);
                 ci[c] = load_cell_in(a, c, i);
-                const float *acc = a.acc + (int64_t)c * a.n;
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (d[j] >= 0) sum += (double)(d[j] >= ch.k0 ? load_flux_wait(acc + d[j]) : acc[d[j]]);
+                sum = chain_lateral(a.acc + (int64_t)c * a.n, d, ch.k0, (double)material(a, c, i));
             }
             s_lat[slot][c][lane] = sum;
         }
@@ -546,34 +579,86 @@ __global__ void __launch_bounds__((CHAIN_PROD + 1) * 32) k_sweep_chain_long(cons
         __threadfence_block();
         __syncwarp();
         if (lane == 0) s_ready[slot] = b + 1;
-        while (s_done[slot] != b + 1) { }
+        while (s_done[slot] != b + 1) __nanosleep(32);        // do not compete with the consumer warp for issue slots
         __syncwarp();
-        if (valid)
-            for (int c = 0; c < a.ncomp; ++c) finish(a, c, k, i, s_tot[slot][c][lane], ci[c]);
+        if (valid) {
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+                if (c < ncomp) finish(a, c, k, i, s_tot[slot][c][lane], ci[c]);
+        }
         __syncwarp();
     }
 }
 
 // The levels between the per-level launches and the chains (a few hundred levels of 1 000 .. 65 000 cells): ONE cooperative
 // launch walks them level by level with a grid barrier in between, instead of one dependent launch per level.
-constexpr int MID_LEVEL_MAX = 1 << 16;
+constexpr int MID_LEVEL_MAX = 1 << 16;       // levels up to 65 536 cells join the cooperative launch (one cell per thread on 148 x 512 threads; grid-stride if the grid is smaller)
 
-__global__ void __launch_bounds__(256) k_sweep_mid(const __grid_constant__ SweepArgs a, int32_t l0, int32_t l1)
+constexpr int MID_THREADS = 512;
+
+__global__ void __launch_bounds__(MID_THREADS) k_sweep_mid(const __grid_constant__ SweepArgs a, int32_t l0, int32_t l1)
 {
     cg::grid_group grid = cg::this_grid();
-    const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, gsz = (int64_t)gridDim.x * blockDim.x;
-    for (int32_t l = l0; l < l1; ++l) {
-        const int32_t kb = __ldg(a.level_ptr + l), ke = __ldg(a.level_ptr + l + 1);
-        for (int64_t k = kb + gt; k < ke; k += gsz) {
-            const int32_t i = __ldg(a.order + k);
-            const int32_t b = __ldg(a.dpos_ptr + k), e = __ldg(a.dpos_ptr + k + 1);
-            for (int c = 0; c < a.ncomp; ++c) {
-                double s = (double)material(a, c, i);
-                const float *acc = a.acc + (int64_t)c * a.n;
-                for (int32_t q = b; q < e; ++q) s += (double)__ldcg(acc + __ldg(a.dpos + q));
-                finish(a, c, k, i, s, load_cell_in(a, c, i));
+    const int32_t gt = blockIdx.x * MID_THREADS + threadIdx.x;       // one cell per thread and level (widths <= grid size)
+    // Everything that does not depend on the previous level -- the cell, its donors' routing positions, its material, old
+    // discharge, kx / fraction -- is fetched one level ahead, before the barrier: behind the barrier a level costs one
+    // round trip for the donors' fluxes plus the stores.  (Component 0 is prefetched; further components load in place.)
+    struct Pre { int32_t k, i, nd, d[8]; float mat; CellIn ci; bool on, wide; };
+    const int32_t gsz = gridDim.x * MID_THREADS;
+    auto prefetch = [&](int32_t l) {
+        Pre p;
+        p.on = p.wide = false; p.k = p.i = p.nd = 0; p.mat = 0.0f; p.ci = CellIn{1.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) p.d[j] = -1;
+        if (l < l1) {
+            const int32_t kb = __ldg(a.level_ptr + l), ke = __ldg(a.level_ptr + l + 1);
+            if (ke - kb > gsz) {                               // more cells than threads: plain grid-stride pass, no prefetch
+                p.wide = true;
+                p.k = kb;
+                p.i = ke;
+            } else if (kb + gt < ke) {
+                p.on = true;
+                p.k = kb + gt;
+                p.i = __ldg(a.order + p.k);
+                const int32_t b = __ldg(a.dpos_ptr + p.k), e = __ldg(a.dpos_ptr + p.k + 1);
+                p.nd = e - b;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (j < p.nd) p.d[j] = __ldg(a.dpos + b + j);
+                p.mat = material(a, 0, p.i);
+                p.ci = load_cell_in(a, 0, p.i);
             }
         }
+        return p;
+    };
+    Pre cur = prefetch(l0);
+    for (int32_t l = l0; l < l1; ++l) {
+        const Pre nxt = prefetch(l + 1);
+        if (cur.wide) {
+            for (int32_t k = cur.k + gt; k < cur.i; k += gsz) {
+                const int32_t i = __ldg(a.order + k);
+                const int32_t b = __ldg(a.dpos_ptr + k), e = __ldg(a.dpos_ptr + k + 1);
+                for (int c = 0; c < a.ncomp; ++c) {
+                    double s = (double)material(a, c, i);
+                    const float *acc = a.acc + (int64_t)c * a.n;
+                    for (int32_t q = b; q < e; ++q) s += (double)__ldcg(acc + __ldg(a.dpos + q));
+                    finish(a, c, k, i, s, load_cell_in(a, c, i));
+                }
+            }
+        } else if (cur.on) {
+            for (int c = 0; c < a.ncomp; ++c) {
+                const float *acc = a.acc + (int64_t)c * a.n;
+                float f[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = cur.d[j] >= 0 ? __ldcg(acc + cur.d[j]) : 0.0f;
+                double s = (double)(c == 0 ? cur.mat : material(a, c, cur.i));
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (cur.d[j] >= 0) s += (double)f[j];
+                finish(a, c, cur.k, cur.i, s, c == 0 ? cur.ci : load_cell_in(a, c, cur.i));
+            }
+        }
+        cur = nxt;
         grid.sync();
     }
 }
@@ -645,6 +730,8 @@ __global__ void k_upstream(const float *__restrict__ x, const int32_t *__restric
 
 }  // namespace
 
+static int build_chains_at(sphy_ctx *ctx, cudaStream_t st, int chain_max, int nlv);
+
 // one-time construction of the chain tables (synchronises)
 static int build_chains(sphy_ctx *ctx, cudaStream_t st)
 {
@@ -653,9 +740,25 @@ static int build_chains(sphy_ctx *ctx, cudaStream_t st)
     const char *env = getenv("SPHY_SWEEP_CHAINS");              // 0 = keep the level-by-level kernels for the narrow levels
     if (env && env[0] == '0') return SPHY_OK;
     const int nlv = (int)ctx->h_level_ptr.size() - 1;
+    int per_sm1 = 0, per_sm8 = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm1, k_sweep_chain_long<1>, (CHAIN_PROD + 1) * 32, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm8, k_sweep_chain_long<ROUTE_MAX_COMP>, (CHAIN_PROD + 1) * 32, 0);
+    const int resident = ctx->sm_count * (per_sm1 < per_sm8 ? per_sm1 : per_sm8);   // chains wait for one another: all or nothing
+    for (int cap = CHAIN_MAX; cap >= 256; cap /= 2) {
+        int rc = build_chains_at(ctx, st, cap, nlv);
+        if (rc != SPHY_OK) return rc;
+        if (ctx->n_chains == 0 || ctx->n_chains_long <= resident - ctx->sm_count) return SPHY_OK;
+    }
+    ctx->n_chains = 0;                                          // cannot happen on a real device; keep the level kernels
+    return SPHY_OK;
+}
+
+static int build_chains_at(sphy_ctx *ctx, cudaStream_t st, int chain_max, int nlv)
+{
+    ctx->n_chains = 0;
     int l0 = -1;
     for (int l = 0; l < nlv; ++l)
-        if (ctx->h_level_ptr[l + 1] - ctx->h_level_ptr[l] <= CHAIN_MAX) { l0 = l; break; }
+        if (ctx->h_level_ptr[l + 1] - ctx->h_level_ptr[l] <= chain_max) { l0 = l; break; }
     if (l0 < 0) return SPHY_OK;
     const int32_t k0 = ctx->h_level_ptr[l0];
     const int64_t T = ctx->n - k0;
@@ -715,10 +818,11 @@ static int build_chains(sphy_ctx *ctx, cudaStream_t st)
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
         const char *menv = getenv("SPHY_SWEEP_MID");
         if (coop && !(menv && menv[0] == '0') &&
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_mid, 256, 0) == cudaSuccess && per_sm > 0) {
-            ctx->mid_grid = ctx->sm_count * (per_sm < 4 ? per_sm : 4);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_mid, MID_THREADS, 0) == cudaSuccess && per_sm > 0) {
+            ctx->mid_grid = ctx->sm_count;                     // one CTA per SM: the cheaper the barrier
             int lm = l0;
-            while (lm > 0 && ctx->h_level_ptr[lm] - ctx->h_level_ptr[lm - 1] <= MID_LEVEL_MAX) --lm;
+            const int64_t cap = MID_LEVEL_MAX;
+            while (lm > 0 && ctx->h_level_ptr[lm] - ctx->h_level_ptr[lm - 1] <= cap) --lm;
             if (lm < l0) ctx->mid_level0 = lm;
         }
     }
@@ -834,7 +938,7 @@ int route_levels_run(sphy_ctx *ctx, SweepArgs &a, cudaStream_t st)
     if (ctx->n_chains > 0 && ctx->mid_level0 >= 0) {
         int32_t l0 = ctx->mid_level0, l1 = chains_from;
         void *kargs[] = {(void *)&a, (void *)&l0, (void *)&l1};
-        SPHY_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)k_sweep_mid, dim3(ctx->mid_grid), dim3(256), kargs, 0, st));
+        SPHY_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)k_sweep_mid, dim3(ctx->mid_grid), dim3(MID_THREADS), kargs, 0, st));
     }
     if (ctx->n_chains > 0) {
         for (int c = 0; c < a.ncomp; ++c)                      // flux slots of the tail: pending until a chain writes them
@@ -846,7 +950,8 @@ int route_levels_run(sphy_ctx *ctx, SweepArgs &a, cudaStream_t st)
         if (ctx->n_chains_long > 0) {
             ChainArgs ch = {ctx->n_chains_long, ctx->chain_k0, ctx->chain_ids + ctx->n_chains_short, ctx->chain_start, ctx->chain_k,
                             ctx->chain_cell, ctx->chain_don};
-            k_sweep_chain_long<<<ctx->n_chains_long, (CHAIN_PROD + 1) * 32, 0, st>>>(a, ch);
+            if (a.ncomp == 1) k_sweep_chain_long<1><<<ctx->n_chains_long, (CHAIN_PROD + 1) * 32, 0, st>>>(a, ch);
+            else k_sweep_chain_long<ROUTE_MAX_COMP><<<ctx->n_chains_long, (CHAIN_PROD + 1) * 32, 0, st>>>(a, ch);
         }
     }
     SPHY_LAUNCH_CHECK(ctx);

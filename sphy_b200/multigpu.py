@@ -221,7 +221,8 @@ def bench_main(args, rank, world):
                        "host_affinity": f"rank 0 bound to the {numa_cpus} CPUs NVML lists next to its GPU" if numa_cpus else "unchanged",
                        "l2": "per-GPU per-step working set %.2f GB (larger than the 126 MB L2)" % (bench.ALG_BYTES_WB * n_local / 1e9)},
             "roofline": {"kernel": "k_wb_step (fused vertical water balance), rank 0", "bound": "hbm", "achieved": ach, "peak": peak,
-                         "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                         "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": (bench.k1_traffic_per_cell() * n_local if bench.k1_traffic_per_cell() else None),
                          "alg_bytes_per_cell": bench.ALG_BYTES_WB, "kernel_ms": wb_ms, "route_ms": rt_ms,
                          "streamed_bytes_per_cell": bench.STREAM_BYTES_WB},
             "roofline_route": bench.scan_roofline(rprof, n_local, 1, peak),

@@ -580,7 +580,12 @@ def test_netcdf_forcing_matches_griddata():
     nc_model = SphyModel(cfg, src, route_method="levels")
     nc_model.initial()
     # what the reference computes per day (netcdf2PCraster.py:132-148, 167-197) -> REAL4 rasters, fed as plain maps
-    gx, gy = np.meshgrid(X, Y)
+    # (the subset of the forcing grid the reference triangulates: the model domain plus two forcing cells, :124-131 -- on a
+    # regular grid the Delaunay diagonals are a matter of tie-breaking, so the node set must be the same)
+    dy = Y[1] - Y[0]
+    x0, x1 = np.argmin(np.abs(X - (xul - 2 * dy))), np.argmin(np.abs(X - (xul + cs * ncols + 2 * dy)))
+    y0, y1 = np.argmin(np.abs(Y - (yul - cs * nrows - 2 * dy))), np.argmin(np.abs(Y - (yul + 2 * dy)))
+    gx, gy = np.meshgrid(X[x0:x1 + 1], Y[y0:y1 + 1])
     xi, yi = np.meshgrid(np.arange(xul + cs * 0.5, (xul + cs * 0.5) + ncols * cs, cs),
                          np.flipud(np.arange((yul + cs * 0.5) - nrows * cs, yul + cs * 0.5, cs)))
     cfg2 = configparser.RawConfigParser()
@@ -590,7 +595,7 @@ def test_netcdf_forcing_matches_griddata():
     def forcing(t):
         out = {}
         for key, (_, arr) in fields.items():
-            z = arr[t - 1].ravel()
+            z = arr[t - 1][y0:y1 + 1, x0:x1 + 1].ravel()
             z = np.where(z <= -9999, np.nan, z)
             ok = ~np.isnan(z)
             out[key] = griddata((gx.ravel()[ok], gy.ravel()[ok]), z[ok], (xi, yi), method="linear").astype(np.float32)
