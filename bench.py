@@ -304,8 +304,10 @@ def main():
     ap.add_argument("--route", default=os.environ.get("SPHY_BENCH_ROUTE", "scan"), choices=["levels", "scan"])
     ap.add_argument("--ring", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-overlap", action="store_true", help="route day t strictly before the water balance of day t + 1 "
-                                                              "(default: the routing runs on a second stream underneath it)")
+    ap.add_argument("--overlap", action="store_true", help="run the routing tail of day t on a second stream underneath the water "
+                                                           "balance of day t + 1 (default on a partitioned basin, where it hides the "
+                                                           "exchange latency; on one GPU it gains 1-2 %% and blurs the per-kernel timing)")
+    ap.add_argument("--no-overlap", action="store_true", help="route day t strictly before the water balance of day t + 1")
     ap.add_argument("--workload", default="basin", choices=["basin", "ensemble"],
                     help="basin: BASELINE config 4 (default, the headline); ensemble: BASELINE config 5")
     ap.add_argument("--members", type=int, default=64)
@@ -334,7 +336,7 @@ def main():
     tmp = tempfile.mkdtemp(prefix="sphy_bench_")
     cfg = cat.write_inputs(os.path.join(tmp, "in"), os.path.join(tmp, "out"))
     model = SphyModel(cfg, CatchmentSource(cat), device="cuda:0", route_method=args.route, diagnostics=False,
-                      overlap_routing=not args.no_overlap)
+                      overlap_routing=args.overlap and not args.no_overlap)
     model.initial()
     n = model.n
     dem_dev = torch.from_numpy(model._compact_np(cat.dem)).to(dev)
@@ -421,8 +423,10 @@ def main():
                "host_cores_available": os.cpu_count(), "pcraster": pcraster_probe()}
 
     # my kernels per step: k_ra_table, k_wb_step, k_sample + routing (3 scan kernels, or one launch per plan segment)
-    # (scan: main, tile-total scan, crossing cells + publish, drift, apply for the trunk cells)
-    nlaunch_step = 3 + ((3 + (3 if model.trunk_cells else 0)) if args.route == "scan" else len(model_plan(model)))
+    # k_ra_table, k_wb_step_pf, k_sample + routing.  scan: k_scan_main, tile-total scan (one kernel of this repo when the tail is
+    # overlapped, else the library's two), k_scan_cross_pub, and k_trunk_drift + k_trunk_apply when there is a trunk list
+    tile_scan = 1 if (model._ovl is not None or model.n < 4096 * 1024) else 0      # cub's kernels are not this repo's
+    nlaunch_step = 3 + ((2 + tile_scan + (2 if model.trunk_cells else 0)) if args.route == "scan" else len(model_plan(model)))
     line = {
         "metric": "Mcell-timesteps/s", "value": value, "unit": "Mcell-timesteps/s", "n_gpus": 1, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
@@ -474,15 +478,12 @@ def scan_roofline(rprof, n, ncomp, peak):
 
 
 def model_plan(model):
-    """Number of level-sweep launches per step (wide levels + narrow runs), from the level histogram."""
+    """Number of level-sweep launches per step, from the level histogram: one per level wider than 65 536 cells, the
+    cooperative launch of the middle levels, the short-chain and the long-chain kernel."""
     import torch
     lp = model.ldd_structure("level_ptr").cpu().numpy()
     sizes = np.diff(lp)
-    wide = sizes >= 2048
-    launches = int(wide.sum())
-    # runs of consecutive narrow levels
-    narrow = ~wide
-    launches += int(np.sum(narrow[1:] & ~narrow[:-1]) + (1 if narrow[0] else 0))
+    launches = int((sizes > 65536).sum()) + 3
     torch.cuda.synchronize()
     return [0] * launches
 

@@ -234,7 +234,7 @@ def bench_main(args, rank, world):
                     "note": "every rank pulls its own cells out of pinned host rasters (all ranks together: "
                             f"{h2d_bytes / (16.0 * model.nrows * model.ncols):.2f} x the raster, algorithmic bytes); ceiling = "
                             "concurrent pinned cudaMemcpyAsync of 1 GiB per GPU"},
-            "gpu_launches": 9 * args.steps * world,
+            "gpu_launches": 8 * args.steps * world,     # k_ra_table, K1, k_scan_main, tile scan, cross+publish, drift, apply, k_sample
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
