@@ -47,7 +47,7 @@ const char *sphy_last_error(const sphy_ctx *ctx);
 int sphy_sm_count(const sphy_ctx *ctx);
 /* sizeof() of the ABI structs, so foreign-language bindings can verify their layout without a GPU:
  * 0 sphy_param, 1 sphy_wb_params, 2 sphy_wb_state, 3 sphy_wb_forcing, 4 sphy_wb_out, 5 sphy_glac_table,
- * 6 sphy_glac_out, 7 sphy_reslake, 8 sphy_openwater, 9 sphy_veg, 10 sphy_mmf, 11 sphy_sedres */
+ * 6 sphy_glac_out, 7 sphy_reslake, 8 sphy_openwater, 9 sphy_veg, 10 sphy_mmf, 11 sphy_sedres, 12 sphy_reslake_plan */
 size_t sphy_abi_sizeof(int which);
 
 /* ---- K3: LDD -> integer structures (once per run) ------------------------------------------
@@ -435,6 +435,43 @@ int sphy_route_reslake_step(sphy_ctx *ctx, const sphy_reslake *rl, const float *
                             sphy_param kx, float one_minus_kx, int day_of_year,
                             int method /* SPHY_ROUTE_LEVELS (bit-exact) or SPHY_ROUTE_SCAN; structures listed by ascending cell */,
                             void *stream);
+
+/* Lakes / reservoirs on the trunk list: what a PARTITIONED basin runs instead of sphy_route_reslake_step (and what one GPU
+ * may run as well).  A structure cell (QFRAC = 0, modules/lakes.py:224) passes nothing downstream and its outflow enters
+ * the cell below it (modules/advanced_routing.py:29-38,159-161), so with E(c) the plain range sum of the per-cell material
+ *     flux(c) = E(c) - sum over the top-level structures k strictly inside the upstream range of c of (E(k) - Qout(k)).
+ * Only cells downstream of a structure see a correction: sphy_trunk_select_cuts puts them (and the structure cells) on the
+ * trunk list next to the cells whose range leaves their rank, every other cell keeps the plain scan, and the listed cells
+ * are finished from the published prefixes.  The structure table is replicated on every rank; what its update needs from
+ * cells of other ranks -- TotR at the structure cell, and the day's discharge at the cells draining into it for
+ * `upstream(ldd, Q)` (advanced_routing.py:35) -- travels in the same exchange block (SPHY_RL_EXTRA float64 per structure
+ * behind the prefixes: stride >= 1 + max n_pub + SPHY_RL_EXTRA * n_struct).  The discharge of the donors only exists once
+ * the listed cells are finished, so StorRES takes `- Qout + Qin` of day t at the head of day t + 1 (apply_pending != 0),
+ * from the values in that day's block; the host flushes the last one itself (sphy_b200/model.py: flush_structures).
+ * The tables are host logic over the exported trunk list (sphy_b200/multigpu.py: plan_reslake).  Call order:
+ *   sphy_trunk_select_cuts -> sphy_trunk_export / sphy_cell_donors -> [sphy_set_partition] -> sphy_trunk_set_plan, then per
+ *   step sphy_route_reslake_begin -> exchange (all-gather of `send`, or peer memory) -> sphy_route_reslake_finish. */
+#define SPHY_RL_EXTRA 9
+typedef struct {
+    const int32_t *cut_slot;         /* [n_struct] trunk-list slot of every structure cell */
+    const int32_t *entry_cut;        /* [m] structure index of a listed structure cell, -1 elsewhere */
+    const int32_t *entry_ptr, *entry_idx;   /* CSR over the m list entries: top-level structures strictly inside the range */
+    const int32_t *x_rank, *x_local; /* [n_struct * SPHY_RL_EXTRA] owner rank (-1: none) / local cell of donor 0..7 and of the structure cell */
+    const float *qmask;              /* [n local] 2 at listed cells, QFRAC elsewhere (the main pass leaves listed cells alone) */
+    float *material;                 /* [n local] workspace: routed material, m3/day */
+    float *qday;                     /* [n local] in/out: the day's blended discharge, m3/day (zero before the first step) */
+    double *extra;                   /* [n_struct * SPHY_RL_EXTRA] workspace */
+    double *top;                     /* [m] workspace: global prefix at the end of each listed cell's range (its noise scale) */
+} sphy_reslake_plan;
+int sphy_trunk_select_cuts(sphy_ctx *ctx, int32_t n_cut, const int32_t *cut_cell_dev /* ascending device indices */, int32_t min_level,
+                           int64_t min_cells, int world, const int64_t *bounds_host, int64_t *count_out, void *stream);
+/* the cells draining directly into each of n given cells: 8 device indices per cell, -1 padded (before sphy_set_partition) */
+int sphy_cell_donors(sphy_ctx *ctx, int32_t n_cells, const int32_t *cells_dev, int32_t *donors_out_dev, void *stream);
+int sphy_route_reslake_begin(sphy_ctx *ctx, const sphy_reslake *rl, const sphy_reslake_plan *plan, const float *totr_mm, float *q_state,
+                             sphy_param kx, float one_minus_kx, double *send_dev /* NULL: peer memory */, int32_t stride, void *stream);
+int sphy_route_reslake_finish(sphy_ctx *ctx, const sphy_reslake *rl, const sphy_reslake_plan *plan, float *q_state, sphy_param kx,
+                              float one_minus_kx, const double *gathered_dev /* NULL: peer memory */, int32_t stride, int rank, int world,
+                              int day_of_year, int apply_pending, void *stream);
 
 /* Open-water evaporation and precipitation on lakes/reservoirs (modules/advanced_routing.py:167-196, ETOpenWaterFLAG):
  * StorRES -= min(areatotal(ETOpenWater*cellarea*openWaterFrac, class)*0.001, StorRES); += areatotal(Precip*...)*0.001.

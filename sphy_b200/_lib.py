@@ -70,6 +70,11 @@ class ResLake(C.Structure):
                 ("Qout", P), ("Qin", P), ("lake_level", P), ("update_level", P)]
 
 
+class ResLakePlan(C.Structure):
+    _fields_ = [(k, P) for k in ("cut_slot", "entry_cut", "entry_ptr", "entry_idx", "x_rank", "x_local", "qmask", "material", "qday",
+                                 "extra", "top")]
+
+
 class OpenWater(C.Structure):
     _fields_ = [("ow_ptr", P), ("ow_cell", P), ("open_water_frac", P), ("et_open_water", P), ("prec", P), ("pcorr", C.c_float)]
 
@@ -101,6 +106,7 @@ class SedRes(C.Structure):
 
 
 RL_NPAR = 30
+RL_EXTRA = 9                          # float64 per structure at the end of an exchange block (include/sphy_b200.h)
 RL_OP_UPDATE_LAKE, RL_OP_QLAKE, RL_OP_QSIMPLE, RL_OP_QADV, RL_OP_QRES = range(5)
 WB_SNOW, WB_GROUND, WB_INFIL_EXCESS, WB_PWS, WB_ETREF_INPUT = 1, 2, 4, 8, 16
 RA_TABLE, RA_CELL = 0, 1
@@ -168,9 +174,14 @@ SYMBOLS = {
     "sphy_reslake_openwater": (C.c_int, [P, C.POINTER(ResLake), C.POINTER(OpenWater), P]),
     "sphy_reslake_op": (C.c_int, [P, C.POINTER(ResLake), C.c_int, C.c_int, P, P, P]),
     "sphy_route_reslake_step": (C.c_int, [P, C.POINTER(ResLake), P, P, SphyParam, C.c_float, C.c_int, C.c_int, P]),
+    "sphy_trunk_select_cuts": (C.c_int, [P, C.c_int32, P, C.c_int32, C.c_int64, C.c_int, P, C.POINTER(C.c_int64), P]),
+    "sphy_cell_donors": (C.c_int, [P, C.c_int32, P, P, P]),
+    "sphy_route_reslake_begin": (C.c_int, [P, C.POINTER(ResLake), C.POINTER(ResLakePlan), P, P, SphyParam, C.c_float, P, C.c_int32, P]),
+    "sphy_route_reslake_finish": (C.c_int, [P, C.POINTER(ResLake), C.POINTER(ResLakePlan), P, SphyParam, C.c_float, P, C.c_int32,
+                                            C.c_int, C.c_int, C.c_int, C.c_int, P]),
 }
 
-ABI_STRUCTS = (SphyParam, WbParams, WbState, WbForcing, WbOut, GlacTable, GlacOut, ResLake, OpenWater, Veg, Mmf, SedRes)
+ABI_STRUCTS = (SphyParam, WbParams, WbState, WbForcing, WbOut, GlacTable, GlacOut, ResLake, OpenWater, Veg, Mmf, SedRes, ResLakePlan)
 
 _LIB = None
 

@@ -84,6 +84,7 @@ struct sphy_ctx {
     int32_t *sl_cell = nullptr, *sl_sub = nullptr, *sl_last = nullptr, *sl_tdon = nullptr;   // sl_tdon: 8 slots per entry, -1 padded
     uint8_t *sl_trunk = nullptr;                             // 1: drift applies (0: listed only because its range leaves the rank)
     bool sl_plan = false;
+    bool sl_cuts = false;                                    // the list also holds the cells downstream of lakes / reservoirs
     int32_t *sl_brank = nullptr, *sl_bslot = nullptr, *sl_erank = nullptr, *sl_eslot = nullptr;   // (rank, pub slot) of j-1 and of the range end
     int32_t sl_stride = 0, sl_rank = 0, sl_world = 1, sl_nblk = 0;
     int sl_comp_cap = 0;
@@ -116,6 +117,8 @@ struct sphy_ctx {
     double *cut_work = nullptr;    // scan path with lakes/reservoirs: range sums of the cut cells
     int cut_work_cap = 0;
     int32_t *cut_ptr = nullptr;    // per-tile ranges of the cut-cell list
+    int32_t *zero_ptr = nullptr;   // [ntiles + 1] zeros: the empty cut list of sphy_route_reslake_begin
+    int32_t zero_ptr_cap = 0;
     std::string err;
 };
 
@@ -140,6 +143,23 @@ constexpr int ROUTE_WIDE_LEVEL = 2048;   // levels with at least this many cells
 #define SPHY_LAUNCH_CHECK(ctx) SPHY_CUDA(ctx, cudaGetLastError())
 
 static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// route.cu: the structure table of a lake / reservoir network updated on every rank from the exchange blocks
+// (sphy_route_reslake_finish, route_scan.cu)
+struct RlPartUpdate {
+    const double *gathered;        // [world][rank_pitch] blocks, or NULL: this rank's peer-memory receive buffer (parity by step)
+    int64_t rank_pitch;
+    int32_t stride, n_extra;       // the extras sit at [stride - n_extra, stride) of every block
+    const int32_t *x_rank;         // [n_struct * SPHY_RL_EXTRA] owner of each extra (-1: none)
+    int apply_pending;             // StorRES still has to take - Qout + Qin of the previous step
+    float vol_factor;
+    int doy;
+    const long long *p2p_local;
+    int p2p_world;
+    const double *p2p_recv;
+    int64_t p2p_pitch;
+};
+int reslake_part_update(sphy_ctx *ctx, const sphy_reslake *rl, const RlPartUpdate &u, cudaStream_t st);
 
 template <typename T>
 static inline int dev_alloc_once(sphy_ctx *ctx, T **p, size_t count)

@@ -33,7 +33,7 @@ extern "C" void sphy_ctx_destroy(sphy_ctx *ctx)
                     ctx->cidx, ctx->flat_active, ctx->down, ctx->level, ctx->order, ctx->level_ptr, ctx->don_ptr,
                     ctx->don_idx, ctx->indeg, ctx->nup, ctx->pos, ctx->dpos_ptr, ctx->dpos, ctx->pre, ctx->cell_canon,
                     ctx->sub_size, ctx->cross_r, ctx->cross_e, ctx->cross_ptr, ctx->end_e, ctx->end_k, ctx->end_ptr, ctx->park_before,
-                    ctx->park_end, ctx->scan_tile, ctx->scan_excl, ctx->scan_tmp, ctx->scan_base, ctx->scan_counter, ctx->cut_work, ctx->cut_ptr, ctx->acc, ctx->qsorted, ctx->pub_e, ctx->sweep_rec, ctx->chain_start, ctx->chain_k, ctx->chain_cell, ctx->chain_don, ctx->chain_ids,
+                    ctx->park_end, ctx->scan_tile, ctx->scan_excl, ctx->scan_tmp, ctx->scan_base, ctx->scan_counter, ctx->cut_work, ctx->cut_ptr, ctx->zero_ptr, ctx->acc, ctx->qsorted, ctx->pub_e, ctx->sweep_rec, ctx->chain_start, ctx->chain_k, ctx->chain_cell, ctx->chain_don, ctx->chain_ids,
                     ctx->sl_cell, ctx->sl_sub, ctx->sl_last, ctx->sl_tdon, ctx->sl_trunk, ctx->sl_brank, ctx->sl_bslot, ctx->sl_erank, ctx->sl_eslot,
                     ctx->sl_E, ctx->sl_Gl, ctx->sl_BS, ctx->sl_BP, ctx->sl_V, ctx->sl_counter,
                     ctx->ra_table, ctx->tmp_n[0], ctx->tmp_n[1], ctx->tmp_n[2], ctx->tmp_n[3]};
@@ -213,6 +213,7 @@ extern "C" size_t sphy_abi_sizeof(int which)
         case 9: return sizeof(sphy_veg);
         case 10: return sizeof(sphy_mmf);
         case 11: return sizeof(sphy_sedres);
+        case 12: return sizeof(sphy_reslake_plan);
         default: return 0;
     }
 }

@@ -1145,6 +1145,47 @@ __global__ void k_rl_op(sphy_reslake rl, int op, int doy, const float *__restric
     out[j] = r;
 }
 
+// The same on a partitioned basin (sphy_route_reslake_finish): the table is replicated on every rank; TotR at the structure
+// cells and the discharge of the previous step at their donors come from the owners' exchange blocks.  First the storage
+// takes `- Qout + Qin` of the previous step (advanced_routing.py:35-36: upstream(ldd, Q), REAL8 sum in donor order like
+// k_rl_post), then the step proceeds like k_rl_pre.
+__global__ void k_rl_part_update(sphy_reslake rl, RlPartUpdate u)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= rl.n_struct) return;
+    const double *G = u.gathered;
+    if (!G) {                                                   // k_trunk_drift has already advanced the step counter
+        const long long cur = *reinterpret_cast<const volatile long long *>(u.p2p_local + u.p2p_world + 1);
+        G = u.p2p_recv + (size_t)((cur - 1) & 1) * u.p2p_world * u.p2p_pitch;
+    }
+    const int32_t *xr = u.x_rank + (int64_t)j * SPHY_RL_EXTRA;
+    const int64_t xoff = (int64_t)u.stride - u.n_extra + (int64_t)j * SPHY_RL_EXTRA;
+    const RLPar P = {rl.par, rl.n_struct, j};
+    float S = rl.StorRES[j];
+    if (u.apply_pending) {
+        double s = 0.0;
+        for (int q = 0; q < SPHY_RL_EXTRA - 1; ++q)
+            if (xr[q] >= 0) s += G[(int64_t)xr[q] * u.rank_pitch + xoff + q];
+        const float qin = (float)s;
+        rl.Qin[j] = qin;
+        S = (S - rl.Qout[j]) + qin;                             // advanced_routing.py:36
+    }
+    const float totr = (float)G[(int64_t)xr[SPHY_RL_EXTRA - 1] * u.rank_pitch + xoff + SPHY_RL_EXTRA - 1];
+    S = S + u.vol_factor * totr;                                // advanced_routing.py:136-138
+    float q = 0.0f;
+    const int kind = rl.kind[j];
+    float measured = nanf("");
+    if (rl.lake_level) {
+        if (kind == 3 && rl.update_level[j] != 0) measured = rl.lake_level[j];
+        S = rl_storage_from_level(P, S, measured);
+    }
+    if (kind == 1) q = rl_qsimple(P, S);
+    else if (kind == 2) q = rl_qadv(P, S, u.doy);
+    else if (kind == 3) q = rl_qlake(P, rl_lake_level(P, S, measured));
+    rl.StorRES[j] = S;
+    rl.Qout[j] = q;
+}
+
 __global__ void k_rl_material(const float *__restrict__ totr, const float *__restrict__ qfrac, float vol_factor, int64_t n,
                               float *__restrict__ m)
 {
@@ -1190,6 +1231,13 @@ __global__ void k_rl_post(sphy_reslake rl, const int32_t *__restrict__ don_ptr, 
 }
 
 }  // namespace
+
+int reslake_part_update(sphy_ctx *ctx, const sphy_reslake *rl, const RlPartUpdate &u, cudaStream_t st)
+{
+    k_rl_part_update<<<div_up(rl->n_struct, 128), 128, 0, st>>>(*rl, u);
+    SPHY_LAUNCH_CHECK(ctx);
+    return SPHY_OK;
+}
 
 extern "C" int sphy_route_reslake_step(sphy_ctx *ctx, const sphy_reslake *rl, const float *totr, float *q_state, sphy_param kx,
                                        float one_minus_kx, int doy, int method, void *stream)

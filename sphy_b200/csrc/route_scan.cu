@@ -51,6 +51,9 @@ struct ScanArgs {
     const int32_t *pub_e;
     double *send;                         // [ncomp][stride]: range total, then range-local inclusive prefix at pub_e[j]
     int32_t stride;
+    // lakes / reservoirs on the trunk list: per-structure values that ride at the end of the block (component 0)
+    const double *extra;
+    int32_t n_extra;
     // lakes / reservoirs (advanced_routing.ROUT): material is already m3/day, cut cells take the structure outflow
     int adv;
     const float *frac;                    // dense QFRAC (0 at lake / reservoir cells)
@@ -236,7 +239,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_MIN_CTAS) k_scan_main(const
                         double pe = own;                               // headwater cell: the range is the cell itself
                         if (inside && szj > 1) pe = Ls[ls_slot(el)];   // predicated load: fewer lanes, fewer bank conflicts
                         if (ADV) {
-                            if (inside) qj = blend(a, tbase + o + j, (float)range_diff(pe, before), qj, kx, omk);
+                            // mask value 2 (sphy_reslake_plan.qmask): a listed cell, finished by k_trunk_apply_adv
+                            if (inside && __ldg(a.frac + tbase + o + j) != 2.0f)
+                                qj = blend(a, tbase + o + j, (float)range_diff(pe, before), qj, kx, omk);
                         } else {
                             const float qn = omk * (float)range_diff(pe, before) + kx * qj;   // routing.py:28
                             qj = inside ? qn : qj;
@@ -353,6 +358,13 @@ __global__ void __launch_bounds__(TAIL_THREADS, 5) k_scan_cross_pub(const __grid
             if (p.on)
                 for (int q = 0; q < p.world; ++q) p.peer_recv[q][slot + o] = v;
         }
+    } else if (i - a.n_pub - 1 < a.n_extra) {                  // per-structure extras, at the end of the block
+        const int32_t x = i - a.n_pub - 1;
+        const double v = a.extra[x];
+        const int64_t o = (int64_t)a.stride - a.n_extra + x;
+        if (a.send) a.send[o] = v;
+        if (p.on)
+            for (int q = 0; q < p.world; ++q) p.peer_recv[q][slot + o] = v;
     }
     if (!p.on) return;
     __threadfence_system();
@@ -391,6 +403,11 @@ struct TrunkArgs {
     int32_t stride, world;
     const int *timed_out;                 // peer-memory exchange: set when a bounded flag wait gave up (else NULL)
     P2PArgs p2p;
+    // lakes / reservoirs (k_trunk_apply_adv): static tables of sphy_reslake_plan, the structures' outflow of the day
+    double *H;                            // [m] global prefix at the end of each entry's range (the noise scale of E), or NULL
+    const int32_t *cut_slot, *entry_cut, *entry_ptr, *entry_idx;
+    const float *qout;
+    float *qday;
 };
 
 constexpr int TRUNK_BLOCK = TAIL_THREADS;
@@ -428,16 +445,19 @@ __global__ void __launch_bounds__(TRUNK_BLOCK, 5) k_trunk_drift(const __grid_con
         }
         __syncthreads();
         const double *V = gathered + (int64_t)c * t.stride + 1;
+        double hi_last = 0.0;
         auto eval = [&](int32_t e) {                           // exact accumulated flux of trunk entry e
             const int32_t er = __ldg(t.erank + e), br = __ldg(t.brank + e);
             const double hi = base[er] + V[(int64_t)er * t.rank_pitch + __ldg(t.eslot + e)];
             const double lo = br < 0 ? 0.0 : base[br] + V[(int64_t)br * t.rank_pitch + __ldg(t.bslot + e)];
+            hi_last = hi;
             return range_diff(hi, lo);
         };
         double g = 0.0;
         if (s < t.m) {
             const double E = eval(s);
             t.E[(int64_t)c * t.m + s] = E;
+            if (t.H && c == 0) t.H[s] = hi_last;
             if (t.trunk[s]) {
                 double X = E;
                 for (int k = 0; k < 8; ++k) {
@@ -499,6 +519,34 @@ __global__ void __launch_bounds__(TAIL_THREADS, 5) k_trunk_apply(const __grid_co
         float *qs = a.qstate[c];
         qs[r] = dead ? nanf("") : omk * f + kx * qs[r];        // routing.py:28
     }
+}
+
+// Listed cells of a basin with lakes / reservoirs (sphy_route_reslake_finish).  A structure keeps everything of its upstream
+// range and hands on its outflow, so flux(c) = E(c) - sum over the top-level structures k strictly inside the range of c of
+// (E(k) - Qout(k)); then the recession blend of advanced_routing.py:31-37 (a structure cell takes its outflow).
+__global__ void __launch_bounds__(TAIL_THREADS, 5) k_trunk_apply_adv(const __grid_constant__ ScanArgs a, const __grid_constant__ TrunkArgs t)
+{
+    const int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= t.m) return;
+    const int64_t r = (int64_t)__ldg(t.cell + s) - t.part_begin;
+    if (r < 0 || r >= a.n) return;                             // another rank's cell
+    const bool dead = t.timed_out && *reinterpret_cast<const volatile int *>(t.timed_out) != 0;
+    const double E = t.E[s];
+    double dz = 0.0;
+    for (int32_t q = __ldg(t.entry_ptr + s); q < __ldg(t.entry_ptr + s + 1); ++q) {
+        const int32_t k = __ldg(t.entry_idx + q);
+        dz += t.E[__ldg(t.cut_slot + k)] - (double)t.qout[k];
+    }
+    double F = E - dz;
+    if (fabs(F) <= 3.6e-15 * fabs(t.H[s])) F = 0.0;           // inside the rounding noise of the prefixes (see range_diff)
+    const float f = (float)F;
+    const float kx = a.kxc[0].map ? __ldg(a.kxc[0].map + r) : a.kxc[0].value;
+    const float omk = a.kxc[0].map ? 1.0f - kx : a.omkc[0];
+    float *qs = a.qstate[0];
+    const int32_t ec = __ldg(t.entry_cut + s);
+    const float qd = ec >= 0 ? t.qout[ec] : omk * f + ((qs[r] * 24.0f) * 3600.0f) * kx;    // advanced_routing.py:31-33
+    t.qday[r] = dead ? nanf("") : qd;
+    qs[r] = dead ? nanf("") : qd / 86400.0f;
 }
 
 // exclusive prefix of the tile totals (ntiles + 1 entries per component: the trailing 0 makes X[ntiles] the range total);
@@ -826,7 +874,7 @@ static int scan_launch_local(sphy_ctx *ctx, ScanArgs &a, cudaStream_t st, bool p
         }
     }
     const int ncb = div_up(ctx->n_cross, TAIL_THREADS * CROSS_ILP);
-    const int npb = publish ? div_up(ctx->n_pub + 1, TAIL_THREADS) : 0;
+    const int npb = publish ? div_up(ctx->n_pub + 1 + a.n_extra, TAIL_THREADS) : 0;
     if (ncb + npb > 0) k_scan_cross_pub<<<ncb + npb, TAIL_THREADS, 0, st>>>(a, p2p_args(ctx, push), ncb);
     prof_mark(ctx, st);
     return SPHY_OK;
@@ -848,9 +896,8 @@ static int trunk_prepare(sphy_ctx *ctx, int ncomp, cudaStream_t st)
 }
 
 // finish the trunk cells of this context from the published blocks of all ranks
-static int trunk_finish(sphy_ctx *ctx, const ScanArgs &a, const double *gathered, int64_t rank_pitch, cudaStream_t st, bool p2p = false)
+static TrunkArgs trunk_args(sphy_ctx *ctx, const double *gathered, int64_t rank_pitch, bool p2p)
 {
-    if (ctx->sl_n == 0) return SPHY_OK;
     TrunkArgs t = {};
     t.m = ctx->sl_n;
     t.nblk = ctx->sl_nblk;
@@ -874,6 +921,13 @@ static int trunk_finish(sphy_ctx *ctx, const ScanArgs &a, const double *gathered
     t.world = ctx->sl_world;
     t.p2p = p2p_args(ctx, p2p);
     t.timed_out = p2p ? reinterpret_cast<const int *>(ctx->p2p_flags + ctx->p2p_world) : nullptr;
+    return t;
+}
+
+static int trunk_finish(sphy_ctx *ctx, const ScanArgs &a, const double *gathered, int64_t rank_pitch, cudaStream_t st, bool p2p = false)
+{
+    if (ctx->sl_n == 0) return SPHY_OK;
+    const TrunkArgs t = trunk_args(ctx, gathered, rank_pitch, p2p);
     k_trunk_drift<<<ctx->sl_nblk, TRUNK_BLOCK, 0, st>>>(a, t);
     k_trunk_apply<<<div_up(ctx->sl_n, TAIL_THREADS), TAIL_THREADS, 0, st>>>(a, t);
     return SPHY_OK;
@@ -882,6 +936,7 @@ static int trunk_finish(sphy_ctx *ctx, const ScanArgs &a, const double *gathered
 int route_scan_run(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm, float *const *q_state, sphy_param kx,
                    float one_m_kx, cudaStream_t st)
 {
+    if (ctx->sl_plan && ctx->sl_cuts) SPHY_FAIL(ctx, SPHY_E_STATE, "the trunk list holds lake/reservoir cells: route with sphy_route_reslake_begin/_finish");
     ScanArgs a;
     int rc = scan_prepare(ctx, ncomp, runoff_mm, q_state, kx, one_m_kx, st, a);
     if (rc != SPHY_OK) return rc;
@@ -907,6 +962,7 @@ extern "C" int sphy_route_step_members(sphy_ctx *ctx, int nmaps, const float *co
     if (!ctx || !runoff_mm || !q_state || !kx || !one_minus_kx || nmaps < 1 || nmaps > ROUTE_MAX_COMP) return SPHY_E_INVALID;
     if (!ctx->ldd_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_route_step_members before sphy_ldd_build");
     if (ctx->partitioned) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_route_step_members is not available on a partitioned context");
+    if (ctx->sl_plan && ctx->sl_cuts) SPHY_FAIL(ctx, SPHY_E_STATE, "the trunk list holds lake/reservoir cells: route with sphy_route_reslake_begin/_finish");
     for (int c = 0; c < nmaps; ++c) {
         if (!runoff_mm[c] || !q_state[c]) SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_route_step_members: map %d is NULL", c);
         if ((kx[c].map != nullptr) != (kx[0].map != nullptr))
@@ -1101,18 +1157,6 @@ __device__ __forceinline__ int rank_of(const RankBounds &rb, int64_t j)
 }
 
 // 0: ordinary cell, 1: listed because its upstream range leaves its rank, 2: trunk (carries the rounding drift)
-__global__ void k_trunk_flag(const int32_t *__restrict__ sub_size, const int32_t *__restrict__ level, const int32_t *__restrict__ cell_canon,
-                             int64_t n, int32_t min_level, int64_t min_cells, const __grid_constant__ RankBounds rb, uint8_t *flag)
-{
-    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    const int32_t sz = sub_size[j];
-    uint8_t f = 0;
-    if (sz >= min_cells || level[cell_canon[j]] >= min_level) f = 2;
-    else if (rb.world > 1 && rank_of(rb, j) != rank_of(rb, j + sz - 1)) f = 1;
-    flag[j] = f;
-}
-
 __device__ __forceinline__ int32_t lower_bound_i32(const int32_t *a, int32_t n, int64_t key)
 {
     int32_t lo = 0, hi = n;
@@ -1121,6 +1165,24 @@ __device__ __forceinline__ int32_t lower_bound_i32(const int32_t *a, int32_t n, 
         if (a[mid] < key) lo = mid + 1; else hi = mid;
     }
     return lo;
+}
+
+// cut cells (lakes / reservoirs, ascending): every cell whose upstream range contains one of them is listed as well
+__global__ void k_trunk_flag(const int32_t *__restrict__ sub_size, const int32_t *__restrict__ level, const int32_t *__restrict__ cell_canon,
+                             int64_t n, int32_t min_level, int64_t min_cells, const __grid_constant__ RankBounds rb,
+                             const int32_t *__restrict__ cut, int32_t n_cut, uint8_t *flag)
+{
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int32_t sz = sub_size[j];
+    uint8_t f = 0;
+    if (sz >= min_cells || level[cell_canon[j]] >= min_level) f = 2;
+    else if (rb.world > 1 && rank_of(rb, j) != rank_of(rb, j + sz - 1)) f = 1;
+    if (f == 0 && n_cut > 0) {
+        const int32_t k = lower_bound_i32(cut, n_cut, j);      // first structure cell at or after j
+        if (k < n_cut && cut[k] <= j + sz - 1) f = 1;
+    }
+    flag[j] = f;
 }
 
 __global__ void k_trunk_entries(const int32_t *__restrict__ sl_cell, int32_t m, const int32_t *__restrict__ sub_size,
@@ -1148,7 +1210,14 @@ __global__ void k_trunk_entries(const int32_t *__restrict__ sl_cell, int32_t m, 
 extern "C" int sphy_trunk_select(sphy_ctx *ctx, int32_t min_level, int64_t min_cells, int world, const int64_t *bounds_host,
                                  int64_t *count_out, void *stream)
 {
-    if (!ctx || !count_out || world < 1 || world > 64 || (world > 1 && !bounds_host)) return SPHY_E_INVALID;
+    return sphy_trunk_select_cuts(ctx, 0, nullptr, min_level, min_cells, world, bounds_host, count_out, stream);
+}
+
+extern "C" int sphy_trunk_select_cuts(sphy_ctx *ctx, int32_t n_cut, const int32_t *cut_cell_dev, int32_t min_level, int64_t min_cells,
+                                      int world, const int64_t *bounds_host, int64_t *count_out, void *stream)
+{
+    if (!ctx || !count_out || world < 1 || world > 64 || (world > 1 && !bounds_host) || n_cut < 0 || (n_cut > 0 && !cut_cell_dev))
+        return SPHY_E_INVALID;
     if (!ctx->ldd_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_trunk_select before sphy_ldd_build");
     if (ctx->order_mode != SPHY_ORDER_DFS) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_trunk_select needs SPHY_ORDER_DFS");
     if (ctx->partitioned) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_trunk_select after sphy_set_partition (it needs the whole-basin structures)");
@@ -1176,7 +1245,8 @@ extern "C" int sphy_trunk_select(sphy_ctx *ctx, int32_t min_level, int64_t min_c
     FK(cudaMalloc(&sel, sizeof(int32_t) * n));
     FK(cudaMalloc(&nsel, sizeof(int32_t)));
     if (e == cudaSuccess) {
-        k_trunk_flag<<<div_up(n, 256), 256, 0, st>>>(ctx->sub_size, ctx->level, ctx->cell_canon, n, min_level, min_cells, rb, flag);
+        k_trunk_flag<<<div_up(n, 256), 256, 0, st>>>(ctx->sub_size, ctx->level, ctx->cell_canon, n, min_level, min_cells, rb, cut_cell_dev,
+                                                     n_cut, flag);
         cub::CountingInputIterator<int32_t> counting(0);
         FK(cub::DeviceSelect::Flagged(nullptr, tb, counting, flag, sel, nsel, (int)n, st));
         FK(cudaMalloc(&tmp, tb));
@@ -1208,7 +1278,32 @@ extern "C" int sphy_trunk_select(sphy_ctx *ctx, int32_t min_level, int64_t min_c
     ctx->sl_nblk = div_up(m, TRUNK_BLOCK);
     ctx->sl_plan = false;
     ctx->sl_comp_cap = 0;
+    ctx->sl_cuts = n_cut > 0;                     // such a list only serves sphy_route_reslake_begin / _finish
     *count_out = m;
+    return SPHY_OK;
+}
+
+namespace {
+__global__ void k_cell_donors(const int32_t *__restrict__ cells, int32_t n_cells, const int32_t *__restrict__ don_ptr,
+                              const int32_t *__restrict__ don_idx, int32_t *__restrict__ out)
+{
+    const int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_cells) return;
+    const int32_t c = cells[j];
+    int k = 0;
+    for (int32_t q = don_ptr[c]; q < don_ptr[c + 1] && k < 8; ++q) out[(int64_t)j * 8 + k++] = don_idx[q];
+    for (; k < 8; ++k) out[(int64_t)j * 8 + k] = -1;
+}
+}  // namespace
+
+extern "C" int sphy_cell_donors(sphy_ctx *ctx, int32_t n_cells, const int32_t *cells_dev, int32_t *donors_out_dev, void *stream)
+{
+    if (!ctx || n_cells < 0 || (n_cells > 0 && (!cells_dev || !donors_out_dev))) return SPHY_E_INVALID;
+    if (!ctx->ldd_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_cell_donors before sphy_ldd_build");
+    if (ctx->partitioned) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_cell_donors after sphy_set_partition (it needs the whole-basin structures)");
+    if (n_cells == 0) return SPHY_OK;
+    k_cell_donors<<<div_up(n_cells, 128), 128, 0, (cudaStream_t)stream>>>(cells_dev, n_cells, ctx->don_ptr, ctx->don_idx, donors_out_dev);
+    SPHY_LAUNCH_CHECK(ctx);
     return SPHY_OK;
 }
 
@@ -1273,6 +1368,7 @@ extern "C" int sphy_route_scan_begin(sphy_ctx *ctx, int ncomp, const float *cons
     if (!ctx->ldd_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_route_scan_begin before sphy_ldd_build");
     if (!ctx->sl_plan) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_route_scan_begin before sphy_trunk_set_plan");
     if (stride != ctx->sl_stride) SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_route_scan_begin: stride %d != planned %d", stride, ctx->sl_stride);
+    if (ctx->sl_cuts) SPHY_FAIL(ctx, SPHY_E_STATE, "the trunk list holds lake/reservoir cells: route with sphy_route_reslake_begin/_finish");
     cudaStream_t st = (cudaStream_t)stream;
     ScanArgs a;
     int rc = scan_prepare(ctx, ncomp, runoff_mm, q_state, kx, one_minus_kx, st, a);
@@ -1305,6 +1401,141 @@ extern "C" int sphy_route_scan_finish(sphy_ctx *ctx, int ncomp, float *const *q_
     // gathered_dev == NULL: what the peers stored into this rank's buffer (the trunk kernel acquires their flags first)
     const bool p2p = gathered_dev == nullptr;
     if ((rc = trunk_finish(ctx, a, gathered_dev, p2p ? ctx->p2p_pitch : (int64_t)ncomp * stride, st, p2p)) != SPHY_OK) return rc;
+    prof_mark(ctx, st);
+    SPHY_LAUNCH_CHECK(ctx);
+    return SPHY_OK;
+}
+
+// ---- lakes / reservoirs on the trunk list (a partitioned basin, or one GPU) ---------------------------------------------------
+namespace {
+
+// what the replicated structure update needs from this rank's cells: the day's discharge at the donors of every structure
+// (of the PREVIOUS step: the main pass is about to overwrite qday) and TotR at the structure cells; 0 for cells of other ranks
+__global__ void k_rl_part_gather(int32_t n_extra, const int32_t *__restrict__ x_rank, const int32_t *__restrict__ x_local, int rank,
+                                 const float *__restrict__ qday, const float *__restrict__ totr, double *__restrict__ extra)
+{
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_extra) return;
+    double v = 0.0;
+    if (x_rank[i] == rank) v = (double)((i % SPHY_RL_EXTRA) == SPHY_RL_EXTRA - 1 ? totr[x_local[i]] : qday[x_local[i]]);
+    extra[i] = v;
+}
+
+__global__ void k_rl_part_material(const float *__restrict__ totr, const float *__restrict__ qfrac, float vol_factor, int64_t n,
+                                   float *__restrict__ m)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    m[i] = qfrac[i] == 0.0f ? 0.0f : vol_factor * totr[i];     // advanced_routing.py:159-161 (second term)
+}
+
+int reslake_plan_check(sphy_ctx *ctx, const sphy_reslake *rl, const sphy_reslake_plan *plan, int32_t stride, const char *who)
+{
+    if (!ctx->ldd_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "%s before sphy_ldd_build", who);
+    if (ctx->order_mode != SPHY_ORDER_DFS) SPHY_FAIL(ctx, SPHY_E_STATE, "%s needs SPHY_ORDER_DFS", who);
+    if (!ctx->sl_plan) SPHY_FAIL(ctx, SPHY_E_STATE, "%s before sphy_trunk_set_plan", who);
+    if (rl->n_struct < 0 || !rl->qfrac || (rl->n_struct > 0 && (!rl->kind || !rl->par || !rl->StorRES || !rl->Qout || !rl->Qin)))
+        SPHY_FAIL(ctx, SPHY_E_INVALID, "%s: incomplete structure table", who);
+    if (rl->n_struct > 0 && !ctx->sl_cuts) SPHY_FAIL(ctx, SPHY_E_STATE, "%s: the trunk list was selected without the structure cells (sphy_trunk_select_cuts)", who);
+    if (!plan->qmask || !plan->material || !plan->qday || !plan->top || !plan->entry_cut || !plan->entry_ptr ||
+        (rl->n_struct > 0 && (!plan->cut_slot || !plan->entry_idx || !plan->x_rank || !plan->x_local || !plan->extra)))
+        SPHY_FAIL(ctx, SPHY_E_INVALID, "%s: incomplete plan", who);
+    if (stride != ctx->sl_stride) SPHY_FAIL(ctx, SPHY_E_INVALID, "%s: stride %d != planned %d", who, stride, ctx->sl_stride);
+    if ((int64_t)stride < 1 + (int64_t)ctx->n_pub + (int64_t)SPHY_RL_EXTRA * rl->n_struct)
+        SPHY_FAIL(ctx, SPHY_E_INVALID, "%s: stride %d leaves no room for %d structures behind %d prefixes", who, stride, rl->n_struct, ctx->n_pub);
+    return SPHY_OK;
+}
+
+}  // namespace
+
+extern "C" int sphy_route_reslake_begin(sphy_ctx *ctx, const sphy_reslake *rl, const sphy_reslake_plan *plan, const float *totr, float *q_state,
+                                        sphy_param kx, float one_minus_kx, double *send_dev, int32_t stride, void *stream)
+{
+    if (!ctx || !rl || !plan || !totr || !q_state) return SPHY_E_INVALID;
+    int rc = reslake_plan_check(ctx, rl, plan, stride, "sphy_route_reslake_begin");
+    if (rc != SPHY_OK) return rc;
+    if (!send_dev && ctx->partitioned && !ctx->p2p_peer_recv)
+        SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_route_reslake_begin: no send buffer and no peer exchange set up");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int32_t n_extra = SPHY_RL_EXTRA * rl->n_struct;
+    if (n_extra > 0)
+        k_rl_part_gather<<<div_up(n_extra, 128), 128, 0, st>>>(n_extra, plan->x_rank, plan->x_local, ctx->sl_rank, plan->qday, totr, plan->extra);
+    k_rl_part_material<<<div_up(ctx->n, 256), 256, 0, st>>>(totr, rl->qfrac, 0.001f * ctx->cellarea, ctx->n, plan->material);
+    SPHY_LAUNCH_CHECK(ctx);
+    ScanArgs a;
+    const float *mm[1] = {plan->material};
+    float *qq[1] = {q_state};
+    if ((rc = scan_prepare(ctx, 1, mm, qq, kx, one_minus_kx, st, a)) != SPHY_OK) return rc;
+    if ((rc = trunk_prepare(ctx, 1, st)) != SPHY_OK) return rc;
+    if (ctx->zero_ptr_cap < ctx->n_tiles + 1) {                // the main pass of a lake network walks a per-tile cut list: an empty one
+        if ((rc = dev_alloc(ctx, &ctx->zero_ptr, (size_t)ctx->n_tiles + 1)) != SPHY_OK) return rc;
+        SPHY_CUDA(ctx, cudaMemsetAsync(ctx->zero_ptr, 0, sizeof(int32_t) * ((size_t)ctx->n_tiles + 1), st));
+        ctx->zero_ptr_cap = ctx->n_tiles + 1;
+    }
+    const bool push = send_dev == nullptr && ctx->partitioned;  // the publishing blocks store into the peers' buffers
+    if (push && (int64_t)stride > ctx->p2p_pitch)
+        SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_route_reslake_begin: %d values exceed the peer buffer pitch", stride);
+    a.adv = 1;
+    a.frac = plan->qmask;
+    a.qout_dense = plan->qmask;                                // never read: no cell of the mask is 0
+    a.qday = plan->qday;
+    a.cut_ptr = ctx->zero_ptr;
+    a.extra = plan->extra;
+    a.n_extra = n_extra;
+    a.send = send_dev ? send_dev : (ctx->partitioned ? nullptr : ctx->sl_V);
+    a.stride = stride;
+    if ((rc = scan_launch_local(ctx, a, st, ctx->sl_n > 0, push && ctx->sl_n > 0)) != SPHY_OK) return rc;
+    SPHY_LAUNCH_CHECK(ctx);
+    return SPHY_OK;
+}
+
+extern "C" int sphy_route_reslake_finish(sphy_ctx *ctx, const sphy_reslake *rl, const sphy_reslake_plan *plan, float *q_state, sphy_param kx,
+                                         float one_minus_kx, const double *gathered_dev, int32_t stride, int rank, int world, int day_of_year,
+                                         int apply_pending, void *stream)
+{
+    if (!ctx || !rl || !plan || !q_state || rank < 0 || rank >= world) return SPHY_E_INVALID;
+    int rc = reslake_plan_check(ctx, rl, plan, stride, "sphy_route_reslake_finish");
+    if (rc != SPHY_OK) return rc;
+    if (!ctx->scan_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "sphy_route_reslake_finish before sphy_route_reslake_begin");
+    if (rank != ctx->sl_rank || world != ctx->sl_world) SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_route_reslake_finish: rank/world differ from the plan");
+    if (!gathered_dev && ctx->partitioned && !ctx->p2p_recv)
+        SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_route_reslake_finish: no gathered buffer and no peer exchange set up");
+    if (ctx->sl_n == 0) return SPHY_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    ScanArgs a;
+    float *qq[1] = {q_state};
+    if ((rc = scan_prepare(ctx, 1, nullptr, qq, kx, one_minus_kx, st, a)) != SPHY_OK) return rc;
+    const bool p2p = gathered_dev == nullptr && ctx->partitioned;
+    const double *gathered = gathered_dev ? gathered_dev : (p2p ? nullptr : ctx->sl_V);
+    const int64_t rank_pitch = p2p ? ctx->p2p_pitch : (int64_t)stride;
+    TrunkArgs t = trunk_args(ctx, gathered, rank_pitch, p2p);
+    t.H = plan->top;
+    t.cut_slot = plan->cut_slot;
+    t.entry_cut = plan->entry_cut;
+    t.entry_ptr = plan->entry_ptr;
+    t.entry_idx = plan->entry_idx;
+    t.qout = rl->Qout;
+    t.qday = plan->qday;
+    k_trunk_drift<<<ctx->sl_nblk, TRUNK_BLOCK, 0, st>>>(a, t);    // waits for the peers; E (and its noise scale) of every listed cell
+    if (rl->n_struct > 0) {
+        RlPartUpdate u = {};
+        u.gathered = gathered;
+        u.rank_pitch = rank_pitch;
+        u.stride = stride;
+        u.n_extra = SPHY_RL_EXTRA * rl->n_struct;
+        u.x_rank = plan->x_rank;
+        u.apply_pending = apply_pending;
+        u.vol_factor = 0.001f * ctx->cellarea;
+        u.doy = day_of_year;
+        if (p2p) {
+            u.p2p_local = ctx->p2p_flags;
+            u.p2p_world = ctx->p2p_world;
+            u.p2p_recv = ctx->p2p_recv;
+            u.p2p_pitch = ctx->p2p_pitch;
+        }
+        if ((rc = reslake_part_update(ctx, rl, u, st)) != SPHY_OK) return rc;
+    }
+    k_trunk_apply_adv<<<div_up(ctx->sl_n, TAIL_THREADS), TAIL_THREADS, 0, st>>>(a, t);
     prof_mark(ctx, st);
     SPHY_LAUNCH_CHECK(ctx);
     return SPHY_OK;

@@ -377,19 +377,34 @@ class SphyModel:
         reference's REAL4 rounding drift; on a partitioned basin it is also what crosses the rank boundaries."""
         from . import multigpu
         adv = self.ResFLAG == 1 or self.LakeFLAG == 1
-        if self.world > 1 and adv:
-            raise NotImplementedError("lakes/reservoirs are not supported on a partitioned basin yet")
+        # lakes / reservoirs: one GPU routes with float64 cut corrections inside the main pass (sphy_route_reslake_step); a
+        # partitioned basin (or SPHY_RESLAKE_PLAN=1) puts the cells downstream of the structures on the trunk list instead
+        self._rl_part = adv and (self.world > 1 or os.environ.get("SPHY_RESLAKE_PLAN", "0") == "1")
         self.trunk_cells = 0
-        if adv or (self.world == 1 and not self.scan_drift):
+        if (adv and not self._rl_part) or (self.world == 1 and not self.scan_drift and not adv):
             return                                   # accufractionflux cuts / plain float64 range sums
         big = 2 ** 31 - 1
-        min_level = int(os.environ.get("SPHY_TRUNK_MIN_LEVEL", multigpu.TRUNK_MIN_LEVEL)) if self.scan_drift else big
-        min_cells = int(os.environ.get("SPHY_TRUNK_MIN_CELLS", multigpu.TRUNK_MIN_CELLS)) if self.scan_drift else 2 ** 40
+        drift = self.scan_drift and not adv          # the structure path rounds like the one-GPU cut path: once per cell
+        min_level = int(os.environ.get("SPHY_TRUNK_MIN_LEVEL", multigpu.TRUNK_MIN_LEVEL)) if drift else big
+        min_cells = int(os.environ.get("SPHY_TRUNK_MIN_CELLS", multigpu.TRUNK_MIN_CELLS)) if drift else 2 ** 40
         bounds = multigpu.partition_bounds(self.n, self.world) if self.world > 1 else np.array([0, self.n], np.int64)
         barr = (C.c_int64 * len(bounds))(*[int(b) for b in bounds])
         m = C.c_int64(0)
-        self._ck(self.lib.sphy_trunk_select(self._ctx, min_level, min_cells, self.world, barr, C.byref(m), self._stream()),
-                 "sphy_trunk_select")
+        cut_dev = donors = None
+        if adv:
+            ids = self._structure_ids()                        # whole-basin id maps in device order (before the partition)
+            cut = np.flatnonzero((ids["lake"] > 0) | (ids["res"] > 0)).astype(np.int32)
+            self._rl_global = dict(ids, cut=cut)
+            cut_dev = self._dev(cut if cut.size else np.zeros(1, np.int32))
+            self._ck(self.lib.sphy_trunk_select_cuts(self._ctx, int(cut.size), cut_dev.data_ptr() if cut.size else None, min_level,
+                                                     min_cells, self.world, barr, C.byref(m), self._stream()), "sphy_trunk_select_cuts")
+            don = torch.full((max(cut.size, 1) * 8,), -1, dtype=torch.int32, device=self.device)
+            self._ck(self.lib.sphy_cell_donors(self._ctx, int(cut.size), cut_dev.data_ptr() if cut.size else None,
+                                               don.data_ptr() if cut.size else None, self._stream()), "sphy_cell_donors")
+            donors = don[:cut.size * 8].cpu().numpy().reshape(-1, 8)
+        else:
+            self._ck(self.lib.sphy_trunk_select(self._ctx, min_level, min_cells, self.world, barr, C.byref(m), self._stream()),
+                     "sphy_trunk_select")
         m = int(m.value)
         self.trunk_cells = m
 
@@ -406,16 +421,31 @@ class SphyModel:
             self.flat_active = self.flat_active[lo:hi]
             self.cell_order = self.cell_order[lo:hi]
             self.n = hi - lo
-        elif m == 0:
+        elif m == 0 and not adv:
             return
-        plan = multigpu.plan_trunk(export("cell", torch.int32), export("sub_size", torch.int32), bounds)
+        cells_l, sub_l = export("cell", torch.int32), export("sub_size", torch.int32)
+        plan = multigpu.plan_trunk(cells_l, sub_l, bounds)
+        stride = int(plan["stride"])
+        if adv:                                                # the per-structure extras ride at the end of every block
+            self._rl_plan_host = multigpu.plan_reslake(cells_l, sub_l, self._rl_global["cut"], donors, bounds)
+            self._rl_plan_host["listed"] = cells_l.astype(np.int64)
+            self._rl_plan_host["bounds"] = np.asarray(bounds, np.int64)
+            stride += _lib.RL_EXTRA * int(self._rl_global["cut"].size)
         d = {k: self._dev(np.ascontiguousarray(plan[k], np.int32)) for k in ("before_rank", "before_slot", "end_rank", "end_slot")}
         pub = self._dev(np.ascontiguousarray(plan["pub"][self.rank], np.int32))
         ptr = lambda t: t.data_ptr() if t.numel() else None  # noqa: E731
         self._ck(self.lib.sphy_trunk_set_plan(self._ctx, int(pub.numel()), ptr(pub), ptr(d["before_rank"]), ptr(d["before_slot"]),
-                                              ptr(d["end_rank"]), ptr(d["end_slot"]), int(plan["stride"]), self.rank, self.world,
+                                              ptr(d["end_rank"]), ptr(d["end_slot"]), stride, self.rank, self.world,
                                               self._stream()), "sphy_trunk_set_plan")
-        self._mg_stride = int(plan["stride"])
+        self._mg_stride = stride
+
+    def _structure_ids(self):
+        """LakeId / ResId over the active cells of the WHOLE basin, in device order (lakes.py:166, reservoirs.py:94)."""
+        cfg = self.config
+        pick = lambda name: np.maximum(np.asarray(self._readmap(name)).ravel()[self.flat_active].astype(np.int32), 0)  # noqa: E731
+        zero = np.zeros(self.flat_active.size, np.int32)
+        return {"lake": pick(cfg.get("LAKE", "LakeId")) if self.LakeFLAG == 1 else zero,
+                "res": pick(cfg.get("RESERVOIR", "ResId")) if self.ResFLAG == 1 else zero}
 
     def ldd_structure(self, name):
         """Device copy of one Appendix-C structure (bit-exact parity checks)."""
@@ -948,14 +978,20 @@ class SphyModel:
     # -- lakes.init/initial, reservoirs.init/initial, modules/lakes.py:162-224, reservoirs.py:90-162 ---
     def _reslake_initial(self):
         cfg = self.config
-        n = self.n
+        part = getattr(self, "_rl_part", False)    # structures on the trunk list: the table covers the WHOLE basin on every rank
+        if part and (self.ETOpenWaterFLAG == 1 or (self.LakeFLAG == 1 and cfg.has_option("LAKE", "updatelakelevel")
+                                                   and cfg.get("LAKE", "updatelakelevel").strip())):
+            raise NotImplementedError("open-water evaporation and measured lake levels are not available with the structures on "
+                                      "the trunk list (a partitioned basin)")
+        n = self.n_global if part else self.n
         res_id = np.zeros(n, np.int32)
         lake_id = np.zeros(n, np.int32)
         stor = np.zeros(n, np.float32)
         million = f32(10 ** 6)
         rows = {}                                   # cell -> parameter column
         if self.LakeFLAG == 1:
-            lake_id = np.maximum(self._compact_np(self._readmap(cfg.get("LAKE", "LakeId")), np.int32), 0)
+            lake_id = (self._rl_global["lake"] if part else
+                       np.maximum(self._compact_np(self._readmap(cfg.get("LAKE", "LakeId")), np.int32), 0))
             T = {k: _read_matrix_table(os.path.join(self.inpath, cfg.get("LAKE", k)))
                  for k in ("LakeStor", "LakeFunc", "LakeQH", "LakeSH", "LakeHS")}
             st = _table_col(T["LakeStor"], 1)
@@ -981,7 +1017,8 @@ class SphyModel:
                 except (FileNotFoundError, KeyError, configparser.Error):
                     self._lake_update = None
         if self.ResFLAG == 1:
-            res_id = np.maximum(self._compact_np(self._readmap(cfg.get("RESERVOIR", "ResId")), np.int32), 0)
+            res_id = (self._rl_global["res"] if part else
+                      np.maximum(self._compact_np(self._readmap(cfg.get("RESERVOIR", "ResId")), np.int32), 0))
             fs = _read_matrix_table(os.path.join(self.inpath, cfg.get("RESERVOIR", "ResFuncStor")))
             func, st = _table_col(fs, 1), _table_col(fs, 2)
             simple = adv = None
@@ -1015,8 +1052,9 @@ class SphyModel:
             kind[j], par[:, j] = rows[int(c)]
         qfrac = np.ones(n, np.float32)
         qfrac[cells] = 0.0
-        self.QFRAC = self._dev(qfrac)
-        self._rl_cells_host = cells
+        lo, hi = getattr(self, "part_range", (0, n))
+        self.QFRAC = self._dev(qfrac[lo:hi])
+        self._rl_cells_host = cells                # GLOBAL device indices when the structures sit on the trunk list
         self._rl = {"cell": self._dev(cells if ns else np.zeros(1, np.int32)), "kind": self._dev(kind), "par": self._dev(par),
                     "StorRES": self._dev(stor[cells] if ns else np.zeros(1, np.float32)),
                     "Qout": torch.zeros(max(ns, 1), dtype=torch.float32, device=self.device),
@@ -1032,6 +1070,35 @@ class SphyModel:
         self._rl_struct = _lib.ResLake(ns, r["cell"].data_ptr(), r["kind"].data_ptr(), r["par"].data_ptr(),
                                        self.QFRAC.data_ptr(), r["StorRES"].data_ptr(), r["Qout"].data_ptr(), r["Qin"].data_ptr(),
                                        None, r["update_level"].data_ptr() if "update_level" in r else None)
+        if part:
+            self._reslake_plan_initial(cells, qfrac[lo:hi], lo, hi)
+
+    def _reslake_plan_initial(self, cells, qfrac_local, lo, hi):
+        """Device tables of multigpu.plan_reslake (sphy_reslake_plan) and the local workspaces of the structure path."""
+        ph = self._rl_plan_host
+        if not np.array_equal(cells, self._rl_global["cut"]):
+            raise RuntimeError("structure cells changed between the trunk selection and the table build")
+        listed = ph["listed"]
+        mine = listed[(listed >= lo) & (listed < hi)] - lo
+        qmask = qfrac_local.copy()
+        qmask[mine] = 2.0                          # the main pass leaves listed cells to the trunk kernels
+        ns, m = len(cells), len(listed)
+        i32 = lambda a: self._dev(np.ascontiguousarray(a if len(a) else np.zeros(1), np.int32))  # noqa: E731
+        p = {k: i32(ph[k]) for k in ("cut_slot", "entry_cut", "entry_ptr", "entry_idx", "x_rank", "x_local")}
+        p["qmask"] = self._dev(qmask)
+        p["material"] = self._full(0.0)
+        p["qday"] = self._full(0.0)
+        p["extra"] = torch.zeros(max(ns * _lib.RL_EXTRA, 1), dtype=torch.float64, device=self.device)
+        p["top"] = torch.zeros(max(m, 1), dtype=torch.float64, device=self.device)
+        self._rl_plan_dev = p
+        self._rl_plan = _lib.ResLakePlan(*[p[k].data_ptr() for k in ("cut_slot", "entry_cut", "entry_ptr", "entry_idx", "x_rank",
+                                                                     "x_local", "qmask", "material", "qday", "extra", "top")])
+        self._rl_pending = False
+        # the slots of the exchange extras this rank owns (flush_structures)
+        xr, xl = ph["x_rank"].astype(np.int64), ph["x_local"].astype(np.int64)
+        donor_slot = (np.arange(xr.size) % _lib.RL_EXTRA) < _lib.RL_EXTRA - 1
+        own = np.flatnonzero((xr == self.rank) & donor_slot)
+        self._rl_flush = (self._dev(own), self._dev(xl[own]))
 
     def _openwater_initial(self, struct_cells):
         """sphy.py:425-431: 8-connected clumps of the open-water mask, each labelled with the largest ResID inside;
@@ -1064,8 +1131,16 @@ class SphyModel:
     def StorRES(self):
         """Dense view of the lake/reservoir storage map (reference attribute name), m3."""
         out = torch.zeros(self.n, dtype=torch.float32, device=self.device)
-        if len(self._rl_cells_host):
-            out[torch.from_numpy(self._rl_cells_host.astype(np.int64)).to(self.device)] = self._rl["StorRES"]
+        cells = self._rl_cells_host.astype(np.int64)
+        if getattr(self, "_rl_part", False):       # structures on the trunk list: global indices, storage possibly one update behind
+            self.flush_structures()
+            lo, hi = getattr(self, "part_range", (0, self.n))
+            sel = np.flatnonzero((cells >= lo) & (cells < hi))
+            if len(sel):
+                out[torch.from_numpy(cells[sel] - lo).to(self.device)] = self._rl["StorRES"][torch.from_numpy(sel).to(self.device)]
+            return out
+        if len(cells):
+            out[torch.from_numpy(cells).to(self.device)] = self._rl["StorRES"]
         return out
 
     # -- kernel argument structs ---------------------------------------------------------------------
@@ -1558,6 +1633,8 @@ class SphyModel:
 
     def _route_reslake(self, TotR):
         """advanced_routing.dynamic (modules/advanced_routing.py:134-217) incl. lakes.QLake / reservoirs.QRes."""
+        if getattr(self, "_rl_part", False):
+            return self._route_reslake_listed(TotR)
         self._ck(self.lib.sphy_route_reslake_step(self._ctx, C.byref(self._rl_struct), TotR.data_ptr(), self.QRAold.data_ptr(),
                                                   self._kx, C.c_float(self._one_m_kx), self._doy, self.route_method, self._stream()),
                  "sphy_route_reslake_step")
@@ -1567,6 +1644,57 @@ class SphyModel:
             self._ck(self.lib.sphy_reslake_openwater(self._ctx, C.byref(self._rl_struct), C.byref(ow), self._stream()),
                      "sphy_reslake_openwater")
         return self.QRAold
+
+    def _route_reslake_listed(self, TotR):
+        """The same with the structures on the trunk list (sphy_route_reslake_begin / _finish): a basin split across GPUs, one
+        exchange per step.  StorRES takes `- Qout + Qin` of day t at the head of day t + 1 (see flush_structures)."""
+        import torch.distributed as dist
+        st = self._stream()
+        gathered = send = None
+        if self.world > 1:
+            if getattr(self, "_mg_p2p", None) is None:
+                self._mg_p2p = self._p2p_connect()
+            if not self._mg_p2p:
+                if getattr(self, "_mg_send", None) is None:
+                    self._mg_send = torch.zeros(self._mg_stride, dtype=torch.float64, device=self.device)
+                    self._mg_recv = torch.zeros((self.world, self._mg_stride), dtype=torch.float64, device=self.device)
+                send = self._mg_send.data_ptr()
+        self._ck(self.lib.sphy_route_reslake_begin(self._ctx, C.byref(self._rl_struct), C.byref(self._rl_plan), TotR.data_ptr(),
+                                                   self.QRAold.data_ptr(), self._kx, C.c_float(self._one_m_kx), send, self._mg_stride, st),
+                 "sphy_route_reslake_begin")
+        if send is not None:
+            dist.all_gather_into_tensor(self._mg_recv.view(-1), self._mg_send)
+            gathered = self._mg_recv.data_ptr()
+        self._ck(self.lib.sphy_route_reslake_finish(self._ctx, C.byref(self._rl_struct), C.byref(self._rl_plan), self.QRAold.data_ptr(),
+                                                    self._kx, C.c_float(self._one_m_kx), gathered, self._mg_stride, self.rank, self.world,
+                                                    self._doy, int(self._rl_pending), st), "sphy_route_reslake_finish")
+        self._rl_pending = True
+        return self.QRAold
+
+    def flush_structures(self):
+        """Structures on the trunk list: bring StorRES / Qin up to date with the last routed day.  `upstream(ldd, Q)` at a
+        structure (advanced_routing.py:35) needs the discharge at its donors, which may live on other ranks and only exists
+        once the listed cells are finished -- so the storage update of day t normally rides in the exchange of day t + 1.
+        This applies it right away: every rank contributes the donors it owns (COLLECTIVE on a partitioned basin)."""
+        if not getattr(self, "_rl_part", False) or not self._rl_pending:
+            return
+        ns = len(self._rl_cells_host)
+        x = torch.zeros(max(ns, 1) * _lib.RL_EXTRA, dtype=torch.float64, device=self.device)
+        slots, local = self._rl_flush
+        if slots.numel():
+            x[slots] = self._rl_plan_dev["qday"][local].double()
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(x)                     # every slot has exactly one owner: the sum is exact
+        v = x.view(-1, _lib.RL_EXTRA)
+        s = v[:, 0].clone()
+        for q in range(1, _lib.RL_EXTRA - 1):      # REAL8 sum in donor order, like the kernels
+            s = s + v[:, q]
+        r = self._rl
+        qin = s[:max(ns, 1)].float()
+        r["Qin"].copy_(qin)
+        r["StorRES"].copy_((r["StorRES"] - r["Qout"]) + qin)                               # advanced_routing.py:36
+        self._rl_pending = False
 
     def structure_outflow(self, kind=None):
         """Dense map of the last step's lake/reservoir outflow Qout [m3/day] (0 elsewhere); kind 1 simple reservoir,
@@ -1581,7 +1709,13 @@ class SphyModel:
                 for k in ks:
                     sel |= kinds == k
                 q = torch.where(sel, q, torch.zeros_like(q))
-            out[torch.from_numpy(self._rl_cells_host.astype(np.int64)).to(self.device)] = q
+            cells = self._rl_cells_host.astype(np.int64)
+            if getattr(self, "_rl_part", False):               # global indices: keep this rank's structures
+                lo, hi = getattr(self, "part_range", (0, self.n))
+                own = np.flatnonzero((cells >= lo) & (cells < hi))
+                cells, q = cells[own] - lo, q[torch.from_numpy(own).to(self.device)]
+            if len(cells):
+                out[torch.from_numpy(cells).to(self.device)] = q
         return out
 
     def _route_partitioned(self, nc, srcp, dstp, st):

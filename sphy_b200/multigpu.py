@@ -83,6 +83,86 @@ def plan_trunk(cell, sub_size, bounds):
                 stride=1 + max(len(p) for p in pub))
 
 
+RL_EXTRA = _lib.RL_EXTRA  # per structure: the day's discharge [m3/day] at its <= 8 donors, then TotR at the structure cell
+
+
+def plan_reslake(cell, sub_size, cut_cell, donors, bounds):
+    """Lakes / reservoirs on the listed cells (pure host logic; the device side is sphy_route_reslake_begin / _finish).
+
+    A lake or reservoir cell has QFRAC = 0 (modules/lakes.py:224): `accufractionflux` passes nothing of what arrives there
+    downstream, and `advanced_routing.dynamic` puts the structure's outflow on the cell below it
+    (modules/advanced_routing.py:159-161).  With E(c) the plain range sum of the per-cell material over the upstream range
+    of c (structure cells carry none), the flux of any cell is
+        F(c) = E(c) - sum of (E(k) - Qout(k)) over the TOP-LEVEL structures k strictly inside the range of c
+    (top-level: no other structure between k and c -- whatever lies above k, nested structures included, stays behind k).
+    Only cells downstream of a structure have a non-empty sum, so they are put on the trunk list (sphy_trunk_select_cuts)
+    and finished from published prefixes; every other cell keeps the plain scan.  This function builds the static tables
+    of that correction.
+
+    cell, sub_size  the listed cells (global device indices, ascending) and their upstream counts; the list must contain
+                    every structure cell and every cell downstream of one
+    cut_cell        [ns] structure cells, global device indices, ascending
+    donors          [ns, 8] the cells draining directly into each structure cell (global device indices, -1 padded)
+    bounds          world + 1 partition bounds ([0, n] on one GPU)
+    Returns int32 arrays:
+      cut_slot   [ns]     list slot of each structure cell
+      entry_cut  [m]      structure index of a listed structure cell, -1 elsewhere
+      entry_ptr  [m + 1], entry_idx   CSR: the top-level structures strictly inside each listed cell's upstream range
+      x_rank, x_local  [ns * RL_EXTRA]   owner rank / local index of donor q (slots 0..7) and of the structure cell itself
+                                         (slot 8) of every structure; rank -1 = no such donor
+    """
+    cell = np.asarray(cell, np.int64)
+    end = cell + np.asarray(sub_size, np.int64) - 1
+    cut = np.asarray(cut_cell, np.int64)
+    donors = np.asarray(donors, np.int64).reshape(-1, 8) if len(cut) else np.zeros((0, 8), np.int64)
+    bounds = np.asarray(bounds, np.int64)
+    ns, m = cut.size, cell.size
+    if ns and np.any(np.diff(cut) <= 0):
+        raise ValueError("structure cells must be listed by ascending device index")
+    cut_slot = np.searchsorted(cell, cut)
+    if ns and (np.any(cut_slot >= m) or np.any(cell[np.minimum(cut_slot, m - 1)] != cut)):
+        raise ValueError("every structure cell must be on the trunk list")
+    entry_cut = np.full(m, -1, np.int32)
+    entry_cut[cut_slot] = np.arange(ns, dtype=np.int32)
+    cut_end = end[cut_slot] if ns else np.zeros(0, np.int64)
+    # nearest structure downstream of each structure (pre-order: an ancestor has a smaller index and a range that contains it)
+    parent = np.full(ns, -1, np.int64)
+    stack = []
+    for k in range(ns):
+        while stack and cut_end[stack[-1]] < cut[k]:
+            stack.pop()
+        if stack:
+            parent[k] = stack[-1]
+        stack.append(k)
+    # structure k is top-level inside the range of entry s  <=>  cell_s < cut_k <= end_s  and  its parent structure (if
+    # any) is not strictly inside that range, i.e. cut_parent <= cell_s
+    pairs_s, pairs_k = [], []
+    for k in range(ns):
+        lo = np.searchsorted(cell, cut[parent[k]]) if parent[k] >= 0 else 0
+        hi = cut_slot[k]                                   # entries with cell < cut_k
+        s = np.arange(lo, hi)
+        s = s[end[s] >= cut[k]]
+        pairs_s.append(s)
+        pairs_k.append(np.full(s.size, k, np.int64))
+    ps = np.concatenate(pairs_s) if pairs_s else np.zeros(0, np.int64)
+    pk = np.concatenate(pairs_k) if pairs_k else np.zeros(0, np.int64)
+    o = np.lexsort((pk, ps))
+    ps, pk = ps[o], pk[o]
+    entry_ptr = np.zeros(m + 1, np.int64)
+    np.add.at(entry_ptr, ps + 1, 1)
+    entry_ptr = np.cumsum(entry_ptr)
+    # where the per-structure extras of the exchange block come from
+    x_cell = np.concatenate([donors, cut[:, None]], axis=1).reshape(-1) if ns else np.zeros(0, np.int64)
+    has = x_cell >= 0
+    x_rank = np.full(x_cell.size, -1, np.int64)
+    x_rank[has] = np.searchsorted(bounds, x_cell[has], side="right") - 1
+    x_local = np.zeros(x_cell.size, np.int64)
+    x_local[has] = x_cell[has] - bounds[x_rank[has]]
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)  # noqa: E731
+    return dict(cut_slot=i32(cut_slot), entry_cut=entry_cut, entry_ptr=i32(entry_ptr), entry_idx=i32(pk),
+                x_rank=i32(x_rank), x_local=i32(x_local), n_struct=int(ns))
+
+
 # ----------------------------------------------------------------------------------------------
 def bind_to_gpu_numa_node(local):
     """Pin this process to the CPUs next to its GPU (NVML's CPU affinity of the device) before any pinned host buffer is

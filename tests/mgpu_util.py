@@ -42,16 +42,21 @@ def device_order_structures(st, pre):
     return down, level
 
 
-def trunk_select(sub_size, level, down, min_level, min_cells, bounds):
-    """NumPy restatement of sphy_trunk_select (csrc/route_scan.cu): the listed cells (ascending device index), their
-    upstream counts, the trunk flag, the last listed slot inside each upstream range and, per entry, the list slot of
-    its receiver when both are trunk cells (-1 otherwise)."""
+def trunk_select(sub_size, level, down, min_level, min_cells, bounds, cut_cell=None):
+    """NumPy restatement of sphy_trunk_select / sphy_trunk_select_cuts (csrc/route_scan.cu): the listed cells (ascending
+    device index), their upstream counts, the trunk flag, the last listed slot inside each upstream range and, per entry,
+    the list slot of its receiver when both are trunk cells (-1 otherwise).  With `cut_cell` (lake / reservoir cells,
+    ascending) every cell whose upstream range contains one of them is listed as well."""
     sub_size = np.asarray(sub_size, np.int64)
     n = sub_size.size
     j = np.arange(n)
     rank = lambda p: np.searchsorted(bounds, p, side="right") - 1  # noqa: E731
     trunk = (sub_size >= min_cells) | (level >= min_level)
     listed = trunk | (rank(j) != rank(j + sub_size - 1))
+    if cut_cell is not None and len(cut_cell):
+        cut = np.asarray(cut_cell, np.int64)
+        nxt = np.searchsorted(cut, j)                                # first structure cell at or after j
+        listed |= (nxt < cut.size) & (cut[np.minimum(nxt, cut.size - 1)] <= j + sub_size - 1)
     cell = np.flatnonzero(listed)
     is_trunk = trunk[cell]
     last = np.searchsorted(cell, cell + sub_size[cell]) - 1
@@ -104,3 +109,103 @@ def trunk_finish(plan, gathered, is_trunk, last, parent_slot):
     G = np.concatenate([[0.0], np.cumsum(g)])
     D = np.where(is_trunk, G[last + 1] - G[np.arange(E.size)], 0.0)
     return (r + D).astype(np.float32)
+
+
+def reslake_rule(S):
+    """Stand-in for lakes.QLake / reservoirs.QRes in the host-logic emulation (the real functions are per-structure device
+    code, tested on the GPU): a fixed fraction of the storage leaves per day."""
+    return (np.float32(0.05) * S).astype(np.float32)
+
+
+class ReslakeEmulation:
+    """What sphy_route_reslake_begin / _finish compute on `world` ranks (csrc/route_scan.cu, csrc/route.cu), in NumPy: the
+    plain scan on every rank, the exchange block with the per-structure extras, and the replicated structure update + the
+    correction of the listed cells.  The storage update of day t (it needs the discharge at the structures' donors, which
+    only exists after the listed cells are finished) is applied at the head of day t + 1 from values that travel in that
+    day's exchange block, or by flush()."""
+
+    def __init__(self, sub_size, level, down, bounds, cut_cell, donors, qfrac, kx, vol, S0):
+        from sphy_b200 import multigpu
+        self.b = np.asarray(bounds, np.int64)
+        self.world = self.b.size - 1
+        self.sub_size = np.asarray(sub_size, np.int64)
+        self.cell, self.sub, _, _, _ = trunk_select(self.sub_size, level, down, 2 ** 31 - 1, 2 ** 62, self.b, cut_cell)
+        self.plan = multigpu.plan_trunk(self.cell, self.sub, self.b)
+        self.rl = multigpu.plan_reslake(self.cell, self.sub, cut_cell, donors, self.b)
+        self.qfrac = qfrac
+        self.kx, self.omk, self.vol = np.float32(kx), np.float32(1 - kx), np.float32(vol)
+        self.S = S0.astype(np.float32).copy()
+        self.ns = len(cut_cell)
+        self.Qout = np.zeros(self.ns, np.float32)
+        self.Qin = np.zeros(self.ns, np.float32)
+        n = self.sub_size.size
+        self.q = np.zeros(n, np.float32)             # QRAold, m3/s
+        self.qday = np.zeros(n, np.float32)
+        self.pending = False
+        self.x_cell = np.where(self.rl["x_rank"] >= 0, self.b[np.maximum(self.rl["x_rank"], 0)] + self.rl["x_local"], -1)
+
+    def _extras(self, totr):
+        """Every rank writes the values of the cells it owns; the reader takes each slot from its owner's block."""
+        x = np.zeros(self.ns * 9)
+        has = self.x_cell >= 0
+        is_totr = (np.arange(self.ns * 9) % 9) == 8
+        x[has & ~is_totr] = self.qday[self.x_cell[has & ~is_totr]]
+        x[has & is_totr] = totr[self.x_cell[has & is_totr]]
+        return x
+
+    def _apply_lag(self, x):
+        v = x.reshape(self.ns, 9)[:, :8]
+        s = np.zeros(self.ns)
+        for q in range(8):
+            s = s + v[:, q]                          # REAL8 sum in donor order, like k_rl_post
+        self.Qin = s.astype(np.float32)
+        self.S = ((self.S - self.Qout) + self.Qin).astype(np.float32)
+        self.pending = False
+
+    def flush(self):
+        if self.pending:
+            self._apply_lag(self._extras(np.zeros_like(self.q)))
+
+    def step(self, totr):
+        f32 = np.float32
+        x = self._extras(totr)
+        m = np.where(self.qfrac == 0, f32(0), self.vol * totr).astype(np.float32)
+        blend = lambda f, qold: (self.omk * f + ((qold * f32(24)) * f32(3600)) * self.kx).astype(np.float32)  # noqa: E731
+        sends = []
+        for p in range(self.world):
+            lo, hi = int(self.b[p]), int(self.b[p + 1])
+            mine = self.cell[(self.cell >= lo) & (self.cell < hi)] - lo
+            acc, send = rank_begin(m[lo:hi], self.sub_size[lo:hi], self.plan["pub"][p], mine)
+            ordinary = ~np.isnan(acc)
+            qd = blend(np.nan_to_num(acc).astype(np.float32), self.q[lo:hi])
+            self.qday[lo:hi][ordinary] = qd[ordinary]
+            sends.append(send)
+        # ---- after the exchange: the same on every rank
+        if self.pending:
+            self._apply_lag(x)
+        xt = x.reshape(self.ns, 9)[:, 8].astype(np.float32)
+        self.S = (self.S + self.vol * xt).astype(np.float32)                # advanced_routing.py:136-138
+        self.Qout = reslake_rule(self.S)
+        world = self.world
+        base = np.concatenate([[0.0], np.cumsum([g[0] for g in sends])])[:world]
+
+        def prefix(rank, slot):
+            out = np.zeros(rank.size)
+            for r in range(world):
+                sel = rank == r
+                out[sel] = base[r] + np.asarray(sends[r])[1 + slot[sel]]
+            return out
+
+        P = self.plan
+        E = prefix(P["end_rank"], P["end_slot"]) - prefix(P["before_rank"], P["before_slot"])
+        ptr, idx = self.rl["entry_ptr"], self.rl["entry_idx"]
+        # a structure keeps everything of its upstream range (nested structures included) and hands on its outflow
+        W = E[self.rl["cut_slot"]] - self.Qout.astype(np.float64)
+        F = E - np.array([W[idx[ptr[s]:ptr[s + 1]]].sum() for s in range(E.size)])
+        qd = blend(F.astype(np.float32), self.q[self.cell])
+        ec = self.rl["entry_cut"]
+        qd[ec >= 0] = self.Qout[ec[ec >= 0]]
+        self.qday[self.cell] = qd
+        self.q = (self.qday / f32(86400)).astype(np.float32)
+        self.pending = True
+        return self.q

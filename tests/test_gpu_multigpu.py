@@ -131,9 +131,168 @@ def test_partitioned_scan_matches_single_context(world, shape, outlets, ncomp, t
     lib.sphy_ctx_destroy(ref)
 
 
-@pytest.mark.parametrize("exchange,glacier,overlap", [("p2p", False, False), ("nccl", False, False), ("p2p", True, False),
-                                                      ("p2p", False, True), ("nccl", False, True)])
-def test_real_two_gpu_exchange(exchange, glacier, overlap):
+def _install_reslake_plan(lib, torch, ctx, bounds, rank, world, cut, qfrac):
+    """sphy_trunk_select_cuts -> export / sphy_cell_donors -> [sphy_set_partition] -> plan_trunk + plan_reslake ->
+    sphy_trunk_set_plan, as SphyModel._install_trunk / _reslake_plan_initial do; returns the plan struct and its tensors."""
+    from sphy_b200 import _lib, multigpu
+    barr = (C.c_int64 * len(bounds))(*[int(b) for b in bounds])
+    m = C.c_int64(0)
+    cut_d = torch.from_numpy(cut.astype(np.int32)).cuda()
+    _lib.check(lib, ctx, lib.sphy_trunk_select_cuts(ctx, len(cut), cut_d.data_ptr(), 2 ** 31 - 1, 2 ** 40, world, barr, C.byref(m), None),
+               "trunk_select_cuts")
+    m = int(m.value)
+    arr = _trunk_arrays(lib, torch, ctx, m)
+    don = torch.empty(len(cut) * 8, dtype=torch.int32, device="cuda")
+    _lib.check(lib, ctx, lib.sphy_cell_donors(ctx, len(cut), cut_d.data_ptr(), don.data_ptr(), None), "cell_donors")
+    donors = don.cpu().numpy().reshape(-1, 8)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    if world > 1:
+        _lib.check(lib, ctx, lib.sphy_set_partition(ctx, lo, hi, None), "set_partition")
+    plan = multigpu.plan_trunk(arr["cell"], arr["sub_size"], bounds)
+    rl = multigpu.plan_reslake(arr["cell"], arr["sub_size"], cut, donors, bounds)
+    stride = int(plan["stride"]) + _lib.RL_EXTRA * len(cut)
+    d = {k: torch.from_numpy(np.ascontiguousarray(plan[k], np.int32)).cuda() for k in ("before_rank", "before_slot", "end_rank", "end_slot")}
+    pub = torch.from_numpy(np.ascontiguousarray(plan["pub"][rank], np.int32)).cuda()
+    ptr = lambda t: t.data_ptr() if t.numel() else None  # noqa: E731
+    _lib.check(lib, ctx, lib.sphy_trunk_set_plan(ctx, int(pub.numel()), ptr(pub), ptr(d["before_rank"]), ptr(d["before_slot"]),
+                                                 ptr(d["end_rank"]), ptr(d["end_slot"]), stride, rank, world, None), "trunk_set_plan")
+    listed = arr["cell"].astype(np.int64)
+    qmask = qfrac[lo:hi].copy()
+    qmask[listed[(listed >= lo) & (listed < hi)] - lo] = 2.0
+    t = {k: torch.from_numpy(np.ascontiguousarray(rl[k] if len(rl[k]) else np.zeros(1), np.int32)).cuda()
+         for k in ("cut_slot", "entry_cut", "entry_ptr", "entry_idx", "x_rank", "x_local")}
+    t["qmask"] = torch.from_numpy(qmask).cuda()
+    t["material"] = torch.zeros(hi - lo, device="cuda")
+    t["qday"] = torch.zeros(hi - lo, device="cuda")
+    t["extra"] = torch.zeros(len(cut) * _lib.RL_EXTRA, dtype=torch.float64, device="cuda")
+    t["top"] = torch.zeros(max(m, 1), dtype=torch.float64, device="cuda")
+    struct = _lib.ResLakePlan(*[t[k].data_ptr() for k in ("cut_slot", "entry_cut", "entry_ptr", "entry_idx", "x_rank", "x_local", "qmask",
+                                                          "material", "qday", "extra", "top")])
+    x_cell = np.where(rl["x_rank"] >= 0, np.asarray(bounds)[np.maximum(rl["x_rank"], 0)] + rl["x_local"], -1)
+    return struct, t, stride, listed, x_cell
+
+
+def _structure_table(torch, rng, cut, S0):
+    """Simple reservoirs, advanced reservoirs and lakes in turn, with parameters that keep every branch active."""
+    from sphy_b200 import _lib
+    ns = len(cut)
+    par = np.full((_lib.RL_NPAR, ns), np.nan, np.float32)
+    kind = (np.arange(ns) % 3 + 1).astype(np.int32)
+    for j in range(ns):
+        s0 = float(S0[j])
+        if kind[j] == 1:
+            par[0, j], par[1, j], par[2, j] = 0.04 + 0.02 * rng.random(), 1.5, 2.0 * s0
+        elif kind[j] == 2:
+            par[3, j], par[4, j], par[5, j], par[6, j], par[7, j], par[8, j] = 3.0 * s0, 0.2 * s0, 0.1 * s0, 0.02 * s0, 100, 250
+        else:
+            par[9, j], par[13, j], par[12, j] = 2, 1e-6, 0.5           # h = a1 * S + b
+            par[16, j], par[20, j], par[19, j] = 2, 0.4, 0.0           # Q = a1 * h + b  [m3/s]
+    return kind, par
+
+
+def _rl_struct(torch, cut, kind, par, qfrac_local, S0):
+    from sphy_b200 import _lib
+    ns = len(cut)
+    t = {"cell": torch.from_numpy(cut.astype(np.int32)).cuda(), "kind": torch.from_numpy(kind).cuda(), "par": torch.from_numpy(par).cuda(),
+         "qfrac": torch.from_numpy(qfrac_local).cuda(), "StorRES": torch.from_numpy(S0.copy()).cuda(),
+         "Qout": torch.zeros(ns, device="cuda"), "Qin": torch.zeros(ns, device="cuda")}
+    st = _lib.ResLake(ns, t["cell"].data_ptr(), t["kind"].data_ptr(), t["par"].data_ptr(), t["qfrac"].data_ptr(), t["StorRES"].data_ptr(),
+                      t["Qout"].data_ptr(), t["Qin"].data_ptr(), None, None)
+    return st, t
+
+
+@pytest.mark.parametrize("world,shape", [(1, (330, 300)), (2, (420, 380)), (4, (500, 610))])
+def test_partitioned_lakes_and_reservoirs_match_the_level_sweep(world, shape):
+    """sphy_route_reslake_begin / _finish (structures on the trunk list, the ranks emulated one after the other, the
+    all-gather a torch.stack) against the bit-exact level sweep of sphy_route_reslake_step on the whole basin: discharge
+    within the north star's 1e-5, and the replicated structure tables (storage one update behind until flushed)."""
+    import torch
+    from oracle.ldd_oracle import LddStruct
+    from sphy_b200 import _lib, multigpu, synth
+    lib = _lib.load()
+    cellsize = 250.0
+    _, _, ldd, _ = synth.make_dem_ldd(shape[0], shape[1], cellsize, seed=20 + world, outlets="single")
+    n = LddStruct(ldd).n
+    ref = _ctx(lib, torch, ldd, cellsize)
+    sub_dev = _export(lib, torch, ref, "sub_size", n)          # upstream cell counts, by device (DFS) index
+    rng = np.random.default_rng(world)
+    # structures on streams of very different size; two of them directly behind each other on the main stem
+    big = np.flatnonzero(sub_dev > 2000)
+    small = np.flatnonzero((sub_dev > 30) & (sub_dev < 600))
+    stem = np.flatnonzero(sub_dev > n // 3)
+    cut = np.unique(np.concatenate([rng.choice(big, 10, replace=False), rng.choice(small, 6, replace=False),
+                                    stem[[len(stem) // 2, len(stem) // 2 + 1]]]))
+    cut = cut[cut > 0]
+    ns = len(cut)
+    qfrac = np.ones(n, np.float32)
+    qfrac[cut] = 0.0
+    S0 = rng.uniform(2e6, 4e7, ns).astype(np.float32)
+    kind, par = _structure_table(torch, rng, cut, S0)
+    rl_ref, t_ref = _rl_struct(torch, cut, kind, par, qfrac, S0)
+    bounds = multigpu.partition_bounds(n, world) if world > 1 else np.array([0, n], np.int64)
+    ranks = []
+    for p in range(world):
+        ctx = _ctx(lib, torch, ldd, cellsize)
+        plan, pt, stride, listed, x_cell = _install_reslake_plan(lib, torch, ctx, bounds, p, world, cut, qfrac)
+        lo, hi = int(bounds[p]), int(bounds[p + 1])
+        rl, rt = _rl_struct(torch, cut, kind, par, qfrac[lo:hi], S0)
+        ranks.append(dict(ctx=ctx, plan=plan, pt=pt, rl=rl, rt=rt, q=torch.zeros(hi - lo, device="cuda"), lo=lo, hi=hi))
+    assert set(cut) <= set(listed)
+    kx = _lib.SphyParam(None, 0.93)
+    one_m = float(np.float32(1 - 0.93))
+    q_ref = torch.zeros(n, device="cuda")
+    for step in range(5):
+        doy = 150 + step
+        totr = torch.from_numpy((rng.gamma(0.8, 4.0, n) * (rng.random(n) < 0.6)).astype(np.float32)).cuda()      # device order
+        _lib.check(lib, ref, lib.sphy_route_reslake_step(ref, C.byref(rl_ref), totr.data_ptr(), q_ref.data_ptr(), kx, C.c_float(one_m), doy,
+                                                         _lib.ROUTE_LEVELS, None), "reslake_step")
+        sends, locs = [], []
+        for r in ranks:
+            loc = totr[r["lo"]:r["hi"]].clone()
+            locs.append(loc)
+            send = torch.zeros(stride, dtype=torch.float64, device="cuda") if world > 1 else None
+            _lib.check(lib, r["ctx"], lib.sphy_route_reslake_begin(r["ctx"], C.byref(r["rl"]), C.byref(r["plan"]), loc.data_ptr(),
+                                                                   r["q"].data_ptr(), kx, C.c_float(one_m),
+                                                                   send.data_ptr() if send is not None else None, stride, None), "reslake_begin")
+            sends.append(send)
+        gathered = torch.stack(sends).contiguous() if world > 1 else None                    # == all_gather_into_tensor
+        for p, r in enumerate(ranks):
+            _lib.check(lib, r["ctx"], lib.sphy_route_reslake_finish(r["ctx"], C.byref(r["rl"]), C.byref(r["plan"]), r["q"].data_ptr(), kx,
+                                                                    C.c_float(one_m), gathered.data_ptr() if gathered is not None else None,
+                                                                    stride, p, world, doy, int(step > 0), None), "reslake_finish")
+        torch.cuda.synchronize()
+        got = torch.cat([r["q"] for r in ranks]).cpu().numpy().astype(np.float64)
+        want = q_ref.cpu().numpy().astype(np.float64)
+        err = np.abs(got - want) / np.maximum(np.abs(want), 1e-9)
+        bad = np.flatnonzero(np.abs(got - want) > 1e-5 * np.abs(want) + 1e-9)
+        assert bad.size == 0, (f"step {step}: {bad.size} cells off, worst {err.max():.3e} at {int(err.argmax())}; listed among the bad: "
+                               f"{int(np.isin(bad, listed).sum())}; structure cells among the bad: {int(np.isin(bad, cut).sum())}; "
+                               f"first {bad[:8]} got {got[bad[:4]]} want {want[bad[:4]]}")
+        # the structure tables are the same on every rank, and one storage update behind the reference until flushed
+        for r in ranks[1:]:
+            for k in ("StorRES", "Qout", "Qin"):
+                assert torch.equal(r["rt"][k], ranks[0]["rt"][k]), (step, k)
+        qday = torch.cat([r["pt"]["qday"] for r in ranks]).cpu().numpy().astype(np.float64)
+        v = np.where(x_cell >= 0, qday[np.maximum(x_cell, 0)], 0.0).reshape(ns, _lib.RL_EXTRA)
+        qin = np.zeros(ns)
+        for q in range(_lib.RL_EXTRA - 1):
+            qin = qin + v[:, q]
+        qin = qin.astype(np.float32)
+        t0 = ranks[0]["rt"]
+        flushed = (t0["StorRES"].cpu().numpy() - t0["Qout"].cpu().numpy()) + qin
+        assert np.allclose(t0["Qout"].cpu().numpy(), t_ref["Qout"].cpu().numpy(), rtol=2e-5, atol=1e-3), step
+        assert np.allclose(qin, t_ref["Qin"].cpu().numpy(), rtol=2e-5, atol=1e-3), step
+        assert np.allclose(flushed, t_ref["StorRES"].cpu().numpy(), rtol=2e-5), step
+    for r in ranks:
+        lib.sphy_ctx_destroy(r["ctx"])
+    lib.sphy_ctx_destroy(ref)
+
+
+@pytest.mark.parametrize("exchange,glacier,overlap,reslake", [("p2p", False, False, False), ("nccl", False, False, False),
+                                                              ("p2p", True, False, False), ("p2p", False, True, False),
+                                                              ("nccl", False, True, False), ("p2p", False, False, True),
+                                                              ("nccl", False, False, True)])
+def test_real_two_gpu_exchange(exchange, glacier, overlap, reslake):
     """Two real ranks (one per GPU) under torch.distributed.run: both confluence exchanges -- stores into peer memory over
     NVLink with flags, and the NCCL all-gather -- against the unpartitioned basin and the level sweep
     (tools/check_multigpu.py).  Skipped where only one GPU is visible."""
@@ -146,12 +305,52 @@ def test_real_two_gpu_exchange(exchange, glacier, overlap):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    port = 29600 + (os.getpid() % 300) + (0 if exchange == "p2p" else 301) + (602 if glacier else 0) + (1203 if overlap else 0)
+    port = 29600 + (os.getpid() % 300) + (0 if exchange == "p2p" else 301) + (602 if glacier else 0) + (1203 if overlap else 0) + (2406 if reslake else 0)
     env = dict(os.environ, SPHY_MG_EXCHANGE=exchange)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", str(port), os.path.join(root, "tools", "check_multigpu.py"), "--rows", "1500", "--cols", "1300",
-                        "--steps", "4"] + (["--glacier"] if glacier else []) + (["--overlap"] if overlap else []), env=env, capture_output=True, text=True, timeout=900, cwd=root)
+                        "--steps", "4"] + (["--glacier"] if glacier else []) + (["--overlap"] if overlap else []) + (["--reslake"] if reslake else []),
+                       env=env, capture_output=True, text=True, timeout=900, cwd=root)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith('{"tool"')][-1])
     assert line["exchange"] == exchange and line["world"] == 2 and line["overlap_routing"] == overlap
-    assert line["worst_rel_partitioned_vs_one_gpu"] <= 3e-7 and line["worst_rel_partitioned_vs_level_sweep"] <= 1e-5
+    assert line["worst_rel_partitioned_vs_one_gpu"] <= (3e-6 if reslake else 3e-7) and line["worst_rel_partitioned_vs_level_sweep"] <= 1e-5
+
+
+def test_model_with_structures_on_the_trunk_list_matches_the_oracle_port(monkeypatch):
+    """SphyModel with lakes and reservoirs routed through sphy_route_reslake_begin / _finish (SPHY_RESLAKE_PLAN=1: the path a
+    partitioned basin runs, here on one GPU) against the oracle port over 12 days: discharge and lake / reservoir storage
+    within 1e-5, the water-balance states bit-identical."""
+    import datetime
+    import os
+    import tempfile
+
+    import torch
+    from oracle.sphy_port import PortInputs, PortModel
+    from sphy_b200 import synth
+    from sphy_b200.model import CatchmentSource, SphyModel
+    monkeypatch.setenv("SPHY_RESLAKE_PLAN", "1")
+    cat = synth.make_catchment(nrows=260, ncols=300, seed=23, cellsize=1000.0, reservoirs=True, lakes=True, n_res_simple=7, n_res_adv=5,
+                               n_lakes=5, nsteps=12, start=datetime.date(2001, 5, 1), params=dict(SubWater=470.0, RootDepthFlat=150.0, Pscale=2.5))
+    tmp = tempfile.mkdtemp(prefix="sphy_rlplan_")
+    cfg = cat.write_inputs(os.path.join(tmp, "in"), os.path.join(tmp, "out"))
+    model = SphyModel(cfg, CatchmentSource(cat), route_method="scan")
+    model.initial()
+    assert model._rl_part and model.trunk_cells >= len(model._rl_cells_host) > 0
+    inp = PortInputs(cat)
+    port = PortModel(inp)
+    g = inp.lddst.gather
+    order = model.cell_order
+    for t in range(1, 13):
+        port.dynamic({k: g(v) for k, v in cat.forcing(t).items()})
+        model.dynamic()
+        got, want = model.QRAold.cpu().numpy().astype(np.float64), port.QRAold[order].astype(np.float64)
+        bad = np.flatnonzero(np.abs(got - want) > 1e-5 * np.abs(want) + 1e-12)
+        assert bad.size == 0, (t, bad[:8], got[bad[:4]], want[bad[:4]])
+        if t % 3 == 0:                                         # StorRES applies the pending storage update first
+            s_got, s_want = model.StorRES.cpu().numpy().astype(np.float64), port.StorRES[order].astype(np.float64)
+            assert np.all(np.abs(s_got - s_want) <= 1e-5 * np.abs(s_want) + 1e-3), t
+    for k in ("RootWater", "SubWater", "Gw"):
+        assert np.array_equal(getattr(model, k).cpu().numpy(), getattr(port, k)[order]), k
+    torch.cuda.synchronize()
+    model.close()

@@ -136,3 +136,63 @@ def test_exchange_world2_gloo():
         p.join(120)
         assert p.exitcode == 0
     assert ret.get(timeout=5) == 1
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_lakes_and_reservoirs_on_the_trunk_list(world):
+    """Lakes / reservoirs on a (partitioned) basin: the plain scan plus a correction of the cells downstream of the
+    structures (multigpu.plan_reslake, what sphy_route_reslake_begin / _finish run on the device) against
+    accufractionflux + upstream of the oracle, several days, nested structures, any number of ranks."""
+    from tests.mgpu_util import ReslakeEmulation, reslake_rule
+    _, _, ldd, _ = synth.make_dem_ldd(190, 170, 100.0, seed=11, outlets="single")
+    st = LddStruct(ldd)
+    n = st.n
+    pre, sub_size = dfs_order(st)
+    down, level = device_order_structures(st, pre)
+    rng = np.random.default_rng(5)
+    # structures on streams of very different size, some nested on the main stem, one right below another
+    big = np.flatnonzero(sub_size > 400)
+    cut = np.unique(np.concatenate([rng.choice(big, 9, replace=False), rng.choice(np.flatnonzero((sub_size > 20) & (sub_size < 200)), 5, replace=False)]))
+    stem = np.flatnonzero(sub_size > n // 3)
+    cut = np.unique(np.concatenate([cut, stem[[len(stem) // 2, len(stem) // 2 + 1]]]))       # receiver of one is a structure itself
+    cut = cut[cut > 0]
+    ns = cut.size
+    canon = np.empty(n, np.int64)
+    canon[pre] = np.arange(n)                                   # device index -> canonical cell
+    donors = np.full((ns, 8), -1, np.int64)
+    for j, c in enumerate(cut):
+        d = st.don_idx[st.don_ptr[canon[c]]:st.don_ptr[canon[c] + 1]]
+        donors[j, :len(d)] = pre[d]
+    qfrac = np.ones(n, np.float32)
+    qfrac[cut] = 0
+    kx, vol = 0.93, np.float32(0.001) * np.float32(100.0 * 100.0)
+    S0 = rng.uniform(1e4, 1e6, ns).astype(np.float32)
+    b = multigpu.partition_bounds(n, world) if world > 1 else np.array([0, n], np.int64)
+    em = ReslakeEmulation(sub_size, level, down, b, cut, donors, qfrac, kx, vol, S0)
+    assert set(cut) <= set(em.cell)
+    # reference: the reference's own sequence (advanced_routing.py:134-217) with the oracle's accufractionflux / upstream
+    f32 = np.float32
+    fr_c = qfrac[pre]                                           # canonical order
+    S, q_c = S0.copy(), np.zeros(n, np.float32)
+    cut_c = canon[cut]
+    for day in range(5):
+        totr = (rng.gamma(0.8, 4.0, n) * (rng.random(n) < 0.6)).astype(np.float32)          # device order
+        got = em.step(totr)
+        totr_c = totr[pre]
+        S = (S + vol * totr_c[cut_c]).astype(np.float32)
+        Qout = reslake_rule(S)
+        qo = np.zeros(n, np.float32)
+        qo[cut_c] = Qout
+        m = (st.upstream(qo) + np.where(fr_c == 0, f32(0), vol * totr_c)).astype(np.float32)
+        F = st.accuflux_f64(m, fr_c).astype(np.float32)
+        qd = np.where(fr_c == 0, qo, f32(1 - kx) * F + ((q_c * f32(24)) * f32(3600)) * f32(kx)).astype(np.float32)
+        Qin = st.upstream(qd)[cut_c]
+        S = ((S - Qout) + Qin).astype(np.float32)
+        q_c = (qd / f32(86400)).astype(np.float32)
+        want = q_c[canon]
+        assert np.allclose(got, want, rtol=3e-6, atol=1e-9), (day, np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-9)))
+        em.flush() if day % 2 else None                        # the storage update may arrive late or right away
+        if not em.pending:
+            assert np.allclose(em.S, S, rtol=2e-6), day
+    em.flush()
+    assert np.allclose(em.S, S, rtol=2e-6) and np.allclose(em.Qin, Qin, rtol=2e-6, atol=1e-6)
