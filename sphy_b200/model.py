@@ -333,9 +333,11 @@ class SphyModel:
             o = self._share_from
             for k in ("n", "n_global", "nlevels", "flat_active", "cell_order", "full_raster", "_cidx_host"):
                 setattr(self, k, getattr(o, k))
-            for k in ("part_range", "_mg_stride", "trunk_cells"):
+            for k in ("part_range", "_mg_stride", "trunk_cells", "_rl_part", "_rl_global", "_rl_plan_host"):
                 if hasattr(o, k):
                     setattr(self, k, getattr(o, k))
+            if self.route_method != _lib.ROUTE_SCAN:
+                self._rl_part = False              # the level sweep does not use the trunk list
             return
         need_ldd = self.RoutFLAG == 1 or self.ResFLAG == 1 or self.LakeFLAG == 1
         if need_ldd:
@@ -377,9 +379,16 @@ class SphyModel:
         reference's REAL4 rounding drift; on a partitioned basin it is also what crosses the rank boundaries."""
         from . import multigpu
         adv = self.ResFLAG == 1 or self.LakeFLAG == 1
-        # lakes / reservoirs: one GPU routes with float64 cut corrections inside the main pass (sphy_route_reslake_step); a
-        # partitioned basin (or SPHY_RESLAKE_PLAN=1) puts the cells downstream of the structures on the trunk list instead
-        self._rl_part = adv and (self.world > 1 or os.environ.get("SPHY_RESLAKE_PLAN", "0") == "1")
+        # lakes / reservoirs: a partitioned basin puts the cells downstream of the structures on the trunk list
+        # (sphy_route_reslake_begin / _finish).  One GPU does the same from 1e6 cells on (measured on BASELINE config 3, 4e6
+        # cells: 0.207 instead of 0.234 ms per step, and no pass over a structure's whole upstream range), otherwise it routes
+        # with float64 cut corrections inside the main pass (sphy_route_reslake_step), which also serves open-water evaporation
+        # and measured lake levels.  SPHY_RESLAKE_PLAN=0/1 forces either path.
+        cfg = self.config
+        extras = (cfg.getint("OPENWATER", "ETOpenWaterFLAG") == 1 or
+                  (self.LakeFLAG == 1 and cfg.has_option("LAKE", "updatelakelevel") and bool(cfg.get("LAKE", "updatelakelevel").strip())))
+        force = os.environ.get("SPHY_RESLAKE_PLAN", "")
+        self._rl_part = adv and (self.world > 1 or force == "1" or (force != "0" and not extras and self.n >= 1_000_000))
         self.trunk_cells = 0
         if (adv and not self._rl_part) or (self.world == 1 and not self.scan_drift and not adv):
             return                                   # accufractionflux cuts / plain float64 range sums

@@ -48,11 +48,17 @@ def run(name, kw, steps, route):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=365)
+    ap.add_argument("--configs", default="C1,C2,C3", help="comma-separated subset of C1,C2,C3")
+    ap.add_argument("--routes", default="scan,levels")
     a = ap.parse_args()
     wet = dict(SubWater=470.0)
-    for route in ("scan", "levels"):
-        run("C1 500x500 ground+routing", dict(nrows=500, ncols=500, params=wet), a.steps, route)
-        run("C2 500x500 + snow + glacier", dict(nrows=500, ncols=500, snow=True, glacier=True, params=wet), a.steps, route)
-        run("C3 2000x2000 1 km, 34 reservoirs + 6 lakes", dict(nrows=2000, ncols=2000, cellsize=1000.0, reservoirs=True, lakes=True,
-                                                              n_res_simple=24, n_res_adv=10, n_lakes=6, params=wet),
-            min(a.steps, 100), route)
+    want = set(a.configs.split(","))
+    for route in a.routes.split(","):
+        if "C1" in want:
+            run("C1 500x500 ground+routing", dict(nrows=500, ncols=500, params=wet), a.steps, route)
+        if "C2" in want:
+            run("C2 500x500 + snow + glacier", dict(nrows=500, ncols=500, snow=True, glacier=True, params=wet), a.steps, route)
+        if "C3" in want:
+            run("C3 2000x2000 1 km, 34 reservoirs + 6 lakes" + (" (structures on the trunk list)" if os.environ.get("SPHY_RESLAKE_PLAN") == "1" else ""),
+                dict(nrows=2000, ncols=2000, cellsize=1000.0, reservoirs=True, lakes=True, n_res_simple=24, n_res_adv=10, n_lakes=6, params=wet),
+                min(a.steps, 100), route)
