@@ -222,13 +222,15 @@ typedef struct {
     const float *ndvi;               /* NDVI of the day (the caller keeps the previous map when a day is missing) */
     const float *prec, *tavg, *tmin, *tmax, *etref_in;   /* raw forcing; etref_in replaces Hargreaves when non-NULL */
     sphy_param lai_max, open_water_frac;
-    /* cfg floats folded on the host exactly like the reference's Python expressions (dynamic_veg.py:30-40) */
-    float sr_min;                    /* REAL4((1+NDVImin)/(1-NDVImin)) */
-    float sr_range;                  /* REAL4(SR_max - SR_min) */
-    float fpar_range;                /* REAL4(FPARmax - FPARmin) */
-    float log_one_m_fparmax;         /* REAL4(log10(REAL4(1 - FPARmax))) */
-    float kc_min, kc_range;          /* REAL4(KCmin), REAL4(KCmax - KCmin) */
-    float ndvi_min, ndvi_range;      /* REAL4(NDVImin), REAL4(NDVImax - NDVImin) */
+    /* the [DYNVEG] parameters folded on the host exactly like the reference's Python expressions (dynamic_veg.py:30-40):
+     * cfg floats combine as Python doubles and are rounded to REAL4 where they meet a map; parameters given as maps
+     * (dynamic_veg.py:57-63 tries readmap first) combine in REAL4 map arithmetic -- hence scalar-or-map, like every parameter */
+    sphy_param sr_min;               /* (1+NDVImin)/(1-NDVImin) */
+    sphy_param sr_range;             /* SR_max - SR_min */
+    sphy_param fpar_range;           /* FPARmax - FPARmin */
+    sphy_param log_one_m_fparmax;    /* log10(REAL4(1 - FPARmax)) */
+    sphy_param kc_min, kc_range;     /* KCmin, KCmax - KCmin */
+    sphy_param ndvi_min, ndvi_range; /* NDVImin, NDVImax - NDVImin */
     float *Scanopy;                  /* canopy storage, in/out */
     float *ETref, *Kc, *PrecipEff;   /* outputs consumed by sphy_glac_step / sphy_wb_step */
     float *LAI, *Int;                /* optional outputs (reporting: LAI, TotIntF) */

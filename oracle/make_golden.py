@@ -49,6 +49,8 @@ CASES = {
     "c1_masked": (dict(nrows=14, ncols=12, seed=18, mask="disk", rout_components=True, params=WET), 40),
     # dynamic vegetation: NDVI map series -> Kc, LAI, canopy interception (modules/dynamic_veg.py)
     "c1_dynveg": (dict(nrows=12, ncols=10, seed=19, dynveg=True, params=WET, start=(2001, 4, 1)), 50),
+    # the same with NDVImax, KCmax and FPARmax read as maps (dynamic_veg.py:57-63 tries readmap first)
+    "c1_dynveg_maps": (dict(nrows=12, ncols=10, seed=20, dynveg="maps", params=WET, start=(2001, 4, 1)), 40),
     "c2_dynveg_snow": (dict(nrows=12, ncols=10, seed=23, dynveg=True, snow=True, glacier=True, params=GLAC, start=(2001, 4, 15),
                             zrange=(1500.0, 5200.0)), 50),
     # crop-coefficient and seepage map series with missing days (sphy.py:824-830, 992-1000)

@@ -82,8 +82,8 @@ class OpenWater(C.Structure):
 class Veg(C.Structure):
     _fields_ = ([(k, P) for k in ("ndvi", "prec", "tavg", "tmin", "tmax", "etref_in")]
                 + [("lai_max", SphyParam), ("open_water_frac", SphyParam)]
-                + [(k, C.c_float) for k in ("sr_min", "sr_range", "fpar_range", "log_one_m_fparmax", "kc_min", "kc_range", "ndvi_min",
-                                            "ndvi_range")]
+                + [(k, SphyParam) for k in ("sr_min", "sr_range", "fpar_range", "log_one_m_fparmax", "kc_min", "kc_range", "ndvi_min",
+                                             "ndvi_range")]
                 + [(k, P) for k in ("Scanopy", "ETref", "Kc", "PrecipEff", "LAI", "Int")])
 
 

@@ -251,8 +251,9 @@ __global__ void k_veg_step(const __grid_constant__ VegArgs a)
     const float ndvi = fminf(__ldg(v.ndvi + i), 0.999f);                     // dynamic_veg.py:84
     const float lai_max = v.lai_max.map ? __ldg(v.lai_max.map + i) : v.lai_max.value;
     float Kc, Smax, LAI, Int, PreT, S;
-    sf::Veg_function(ndvi, lai_max, v.sr_min, v.sr_range, v.fpar_range, v.log_one_m_fparmax, v.kc_min, v.kc_range, v.ndvi_min,
-                     v.ndvi_range, Kc, Smax, LAI);
+    auto P = [&](const sphy_param &q) { return q.map ? __ldg(q.map + i) : q.value; };
+    sf::Veg_function(ndvi, lai_max, P(v.sr_min), P(v.sr_range), P(v.fpar_range), P(v.log_one_m_fparmax), P(v.kc_min), P(v.kc_range),
+                     P(v.ndvi_min), P(v.ndvi_range), Kc, Smax, LAI);
     sf::Inter_function(v.Scanopy[i] + Precip, Smax, ETref, Int, PreT, S);    // dynamic_veg.py:108-110
     v.Scanopy[i] = S;
     v.ETref[i] = ETref;

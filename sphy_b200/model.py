@@ -565,10 +565,7 @@ class SphyModel:
             self.ndvi = cfg.get("DYNVEG", "NDVI")
             self.LAImax = self._lookup_column_table(os.path.join(self.inpath, cfg.get("DYNVEG", "LAImax")), self.LandUse)
             for k in ("NDVImax", "NDVImin", "NDVIbase", "KCmax", "KCmin", "FPARmax", "FPARmin"):
-                try:
-                    setattr(self, k, cfg.getfloat("DYNVEG", k))
-                except ValueError:
-                    raise NotImplementedError(f"[DYNVEG] {k} as a map is not supported yet") from None
+                setattr(self, k, self._scalar_or_map("DYNVEG", k))            # map first, cfg float otherwise (dynamic_veg.py:57-63)
             self.Kc = None                         # per-cell map produced by sphy_veg_step every day
         else:
             self.KcStatFLAG = cfg.getint("LANDUSE", "KCstatic")                                # sphy.py:268-275
@@ -1296,19 +1293,27 @@ class SphyModel:
         P.pcorr = 1.0
         z = lambda: torch.zeros(self.n, dtype=torch.float32, device=self.device)  # noqa: E731
         self._veg_maps = {k: z() for k in ("ETref", "Kc", "PrecipEff", "LAI", "Int")}
-        self._ndvi_old = torch.full((self.n,), float(f32((self.NDVImax + self.NDVImin) / 2)), dtype=torch.float32,
-                                    device=self.device)                                      # dynamic_veg.py:70
+        # cfg floats combine as Python doubles and become REAL4 where they meet a map; parameters read as maps are float32
+        # arrays (0-d for a uniform map) and combine in REAL4 map arithmetic, exactly like the reference's expressions
+        ndvi0 = (self.NDVImax + self.NDVImin) / 2                                             # dynamic_veg.py:70
+        self._ndvi_old = (self._dev(np.broadcast_to(np.asarray(ndvi0, np.float32), (self.n,)).copy()) if isinstance(ndvi0, np.ndarray)
+                          else torch.full((self.n,), float(f32(ndvi0)), dtype=torch.float32, device=self.device))
         V = _lib.Veg()
         V.lai_max = self._param(self.LAImax)
         if self.openWaterFrac is not None:
             V.open_water_frac = SphyParam(self._ow_frac_dev.data_ptr(), 0.0)
-        sr_max = (1 + self.NDVImax) / (1 - self.NDVImax)
-        sr_min = (1 + self.NDVImin) / (1 - self.NDVImin)
-        V.sr_min, V.sr_range = float(f32(sr_min)), float(f32(sr_max - sr_min))
-        V.fpar_range = float(f32(self.FPARmax - self.FPARmin))
-        V.log_one_m_fparmax = float(f32(np.log10(np.float64(f32(1 - self.FPARmax)))))
-        V.kc_min, V.kc_range = float(f32(self.KCmin)), float(f32(self.KCmax - self.KCmin))
-        V.ndvi_min, V.ndvi_range = float(f32(self.NDVImin)), float(f32(self.NDVImax - self.NDVImin))
+        with np.errstate(all="ignore"):
+            sr_max = (1 + self.NDVImax) / (1 - self.NDVImax)
+            sr_min = (1 + self.NDVImin) / (1 - self.NDVImin)
+            one_m_f = 1 - self.FPARmax
+            log_f = (np.log10(one_m_f.astype(np.float64)).astype(np.float32) if isinstance(one_m_f, np.ndarray)
+                     else f32(np.log10(np.float64(f32(one_m_f)))))                           # double on the REAL4 operand
+            pr = self._param
+            V.sr_min, V.sr_range = pr(sr_min), pr(sr_max - sr_min)
+            V.fpar_range = pr(self.FPARmax - self.FPARmin)
+            V.log_one_m_fparmax = pr(log_f)
+            V.kc_min, V.kc_range = pr(self.KCmin), pr(self.KCmax - self.KCmin)
+            V.ndvi_min, V.ndvi_range = pr(self.NDVImin), pr(self.NDVImax - self.NDVImin)
         V.Scanopy = self.Scanopy.data_ptr()
         for k, t in self._veg_maps.items():
             setattr(V, k, t.data_ptr())

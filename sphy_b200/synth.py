@@ -139,6 +139,7 @@ class Catchment:
     glac_retreat: tuple | None = None    # (day, month) of the yearly glacier update (GlacRetreat = 1, glacier.py:562-736)
     glac_vars: tuple = ()                # per-glacier reporting (GlacID_flag = 1, glacier.py:501-559): GlacTable columns
     dynveg: bool = False                 # DynVegFLAG = 1: NDVI map series -> Kc, LAI, canopy interception (modules/dynamic_veg.py)
+    dynveg_maps: bool = False            # NDVImax, KCmax and FPARmax as maps instead of cfg floats (dynamic_veg.py:57-63 reads maps first)
     etref_input: bool = False            # ETREF_FLAG = 1: ETref map series instead of Hargreaves (sphy.py:814)
     mask: np.ndarray | None = None       # clone mask (True = inside the catchment); None = the whole rectangle
 
@@ -225,6 +226,12 @@ class Catchment:
             m["openwater_frac.map"] = self.open_water_frac.astype(np.float32)
         if self.lake_levels and self.lake_id is not None:
             m["update_lakelevel.map"] = (self.lake_id % 2 == 1)               # boolean: lakes with a gauge
+        if self.dynveg_maps:
+            rng = np.random.default_rng(self.seed + 4711)
+            z = _smooth_noise(rng, self.nrows, self.ncols, 4)
+            m["ndvimax.map"] = np.clip(0.65 + 0.08 * z, 0.5, 0.8).astype(np.float32)
+            m["kcmax.map"] = np.clip(1.4 + 0.2 * _smooth_noise(rng, self.nrows, self.ncols, 4), 1.0, 1.8).astype(np.float32)
+            m["fparmax.map"] = np.where(z > 0, np.float32(0.95), np.float32(0.9)).astype(np.float32)
         return m
 
     def forcing_map_names(self, day):
@@ -420,13 +427,13 @@ CropFac = kc.tbl
 KC = {"forcings/kc" if self.kc_series else ""}
 [DYNVEG]
 NDVI = forcings/ndvi
-NDVImax = 0.65
+NDVImax = {"ndvimax.map" if self.dynveg_maps else 0.65}
 NDVImin = 0.1
 NDVIbase = 0.15
-KCmax = 1.5
+KCmax = {"kcmax.map" if self.dynveg_maps else 1.5}
 KCmin = 0.5
 LAImax = laimax.tbl
-FPARmax = 0.95
+FPARmax = {"fparmax.map" if self.dynveg_maps else 0.95}
 FPARmin = 0.001
 [PWS]
 PWS_FLAG = {1 if self.pws else 0}
@@ -601,7 +608,7 @@ def make_catchment(nrows, ncols, cellsize=250.0, seed=1, nsteps=365, snow=False,
                     lat=lat, flags=flags, params=p, start=start, nsteps=nsteps, locations=locations,
                     soil_maps=soil_maps, rout_components=rout_components, infil_excess=infil_excess,
                     report_daily=tuple(report_daily), pws=bool(pws), report_opts=dict(report_opts or {}),
-                    etref_input=bool(etref_input), dynveg=bool(dynveg), kc_series=bool(kc_series),
+                    etref_input=bool(etref_input), dynveg=bool(dynveg), dynveg_maps=(dynveg == "maps"), kc_series=bool(kc_series),
                     seep_series=bool(seep_series), lake_levels=bool(lake_levels))
     if mask == "disk":                    # a non-rectangular catchment: everything outside the disk is MV
         rr, cc = np.ogrid[:nrows, :ncols]
