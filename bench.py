@@ -333,11 +333,15 @@ def main():
     torch.cuda.set_device(dev)
     t_setup = time.time()
     cat = make_case(args.size)
+    t_synth = time.time() - t_setup
     tmp = tempfile.mkdtemp(prefix="sphy_bench_")
     cfg = cat.write_inputs(os.path.join(tmp, "in"), os.path.join(tmp, "out"))
     model = SphyModel(cfg, CatchmentSource(cat), device="cuda:0", route_method=args.route, diagnostics=False,
                       overlap_routing=args.overlap and not args.no_overlap)
+    t_init = time.time()
     model.initial()
+    torch.cuda.synchronize()
+    setup_parts = dict(model.setup_times, synthetic_inputs_on_host_s=round(t_synth, 2), initial_s=round(time.time() - t_init, 2))
     n = model.n
     dem_dev = torch.from_numpy(model._compact_np(cat.dem)).to(dev)
     ring = device_forcing_ring(torch, dem_dev, args.ring, seed=1234)
@@ -435,7 +439,7 @@ def main():
                    "trunk_cells": getattr(model, "trunk_cells", 0), "overlap_routing": model._ovl is not None,
                    "l2": "per-step working set %.1f GB >> 126 MB L2 (inputs larger than L2, no flush needed)" % (ALG_BYTES_WB * n / 1e9)
                    if ALG_BYTES_WB * n > 4 * 126e6 else "working set fits L2: throughput only, no roofline claim",
-                   "forcing_ring_days": args.ring, "setup_s": round(setup_s, 1)},
+                   "forcing_ring_days": args.ring, "setup_s": round(setup_s, 1), "setup_parts": setup_parts},
         "roofline": {"kernel": "k_wb_step (fused vertical water balance)", "bound": "hbm", "achieved": ach, "peak": peak,
                      "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak,
                      "traffic": (k1_traffic_per_cell() * n if k1_traffic_per_cell() else None),

@@ -276,8 +276,13 @@ class SphyModel:
         self._keep = []               # tensors referenced by raw pointers
         self._stream = lambda: C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)  # noqa: E731
         # -- routing structures first: they define the active cells / compact order (routing.py:33-38)
+        import time
+        t0 = time.time()
         self._build_cells()
+        torch.cuda.synchronize(self.device)
+        t1 = time.time()
         self._read_parameters()
+        self.setup_times = {"ldd_build_and_trunk_s": round(t1 - t0, 2), "read_parameters_s": round(time.time() - t1, 2)}
         # the process modules under the reference's attribute names (sphy.py:60-78, 210-213, 297-300, 374-377 ...)
         from . import modules
         modules.bind(self)
