@@ -204,11 +204,15 @@ def bench_main(args, rank, world):
     dist.init_process_group("nccl", device_id=dev)
     t_setup = time.time()
     cat = bench.make_case(args.size)
+    t_synth = time.time() - t_setup
     tmp = tempfile.mkdtemp(prefix=f"sphy_bench_r{rank}_")
     cfg = cat.write_inputs(os.path.join(tmp, "in"), os.path.join(tmp, "out"))
     model = SphyModel(cfg, CatchmentSource(cat), device=str(dev), route_method="scan", diagnostics=False, rank=rank, world=world,
                       overlap_routing=not args.no_overlap)
+    t_init = time.time()
     model.initial()
+    torch.cuda.synchronize()
+    setup_parts = dict(model.setup_times, synthetic_inputs_on_host_s=round(t_synth, 2), initial_s=round(time.time() - t_init, 2))
     n_local, n_global = model.n, model.n_global
     dem_dev = torch.from_numpy(model._compact_np(cat.dem)).to(dev)
     ring = bench.device_forcing_ring(torch, dem_dev, args.ring, seed=1234, cell_begin=model.part_range[0])
@@ -298,6 +302,7 @@ def bench_main(args, rank, world):
                                     + ("stores into peer memory over NVLink + flags" if getattr(model, "_mg_p2p", False)
                                        else "NCCL all-gather") + ")",
                        "routing": "scan", "trunk_cells": model.trunk_cells, "overlap_routing": model._ovl is not None, "forcing_ring_days": args.ring, "setup_s": round(setup_s, 1),
+                       "setup_parts": setup_parts,
                        "host_affinity": f"rank 0 bound to the {numa_cpus} CPUs NVML lists next to its GPU" if numa_cpus else "unchanged",
                        "l2": "per-GPU per-step working set %.2f GB (larger than the 126 MB L2)" % (bench.ALG_BYTES_WB * n_local / 1e9)},
             "roofline": {"kernel": "k_wb_step (fused vertical water balance), rank 0", "bound": "hbm", "achieved": ach, "peak": peak,
