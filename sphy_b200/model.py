@@ -432,6 +432,9 @@ class SphyModel:
             lo, hi = int(bounds[self.rank]), int(bounds[self.rank + 1])
             self._ck(self.lib.sphy_set_partition(self._ctx, lo, hi, self._stream()), "sphy_set_partition")
             self.part_range = (lo, hi)
+            self._bounds = np.asarray(bounds, np.int64)
+            if self.rank == 0:                     # rank 0 assembles reported rasters from the ranks' slices (gather_raster)
+                self._flat_active_global = self.flat_active.astype(np.int32 if self.nrows * self.ncols < 2 ** 31 else np.int64)
             self.flat_active = self.flat_active[lo:hi]
             self.cell_order = self.cell_order[lo:hi]
             self.n = hi - lo
@@ -499,6 +502,27 @@ class SphyModel:
         """compact device map -> (nrows, ncols) ndarray (the `report` side)."""
         out = np.full(self.nrows * self.ncols, fill, np.float32)
         out[self.flat_active] = compact.detach().cpu().numpy()
+        return out.reshape(self.nrows, self.ncols)
+
+    def gather_raster(self, compact, fill=np.nan):
+        """to_raster for a basin split across GPUs: COLLECTIVE; rank 0 gets the whole (nrows, ncols) raster assembled from
+        every rank's slice of the compact map (one all-gather of the padded slices), the other ranks get None."""
+        if self.world == 1:
+            return self.to_raster(compact, fill)
+        import torch.distributed as dist
+        sizes = np.diff(self._bounds)
+        maxn = int(sizes.max())
+        send = torch.full((maxn,), float("nan"), dtype=torch.float32, device=self.device)
+        send[:self.n] = compact.detach().to(torch.float32)
+        recv = torch.empty(self.world * maxn, dtype=torch.float32, device=self.device)
+        dist.all_gather_into_tensor(recv, send)
+        if self.rank != 0:
+            return None
+        vals = recv.view(self.world, maxn).cpu().numpy()
+        out = np.full(self.nrows * self.ncols, fill, np.float32)
+        for r in range(self.world):
+            lo, hi = int(self._bounds[r]), int(self._bounds[r + 1])
+            out[self._flat_active_global[lo:hi]] = vals[r, :hi - lo]
         return out.reshape(self.nrows, self.ncols)
 
     def _param(self, x):
@@ -877,7 +901,9 @@ class SphyModel:
             if name.endswith(".csv"):
                 v.to_csv(path, index=False)
             else:
-                csf.write_map(path, self.to_raster(torch.from_numpy(np.ascontiguousarray(v))), cellsize=self.cellsize or 1.0)
+                raster = self.gather_raster(torch.from_numpy(np.ascontiguousarray(v)).to(self.device))   # collective when partitioned
+                if raster is not None:
+                    csf.write_map(path, raster, cellsize=self.cellsize or 1.0)
 
     def _glacier_reporting(self, F):
         """glacier.dynamic_reporting (modules/glacier.py:501-810).  It only depends on the fragment table as sphy_glac_step

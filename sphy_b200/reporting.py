@@ -78,7 +78,9 @@ class Reporting:
         return self._tmp
 
     def _report(self, tensor, rel_path):
-        raster = self.m.to_raster(tensor)
+        raster = self.m.gather_raster(tensor)       # a basin split across GPUs: collective, rank 0 holds and writes the raster
+        if raster is None:
+            return
         self.maps[rel_path] = raster
         if self.write_files:
             path = os.path.join(self.m.outpath, rel_path)
@@ -167,7 +169,34 @@ class Reporting:
                 if at_end:
                     self._report(self._divided(tot, m.simYears), f + "AvgY.map")
 
+    def tss_tables(self):
+        """tss name -> (station ids, [(timestep, values)]).  On a basin split across GPUs every rank sampled the stations
+        inside its own range: COLLECTIVE, rank 0 gets the merged tables (stations by ascending id, like the reference's
+        TimeoutputTimeseries), the other ranks an empty dict."""
+        m = self.m
+        if m.world == 1:
+            return {name: (m.station_ids, rows) for name, rows in self.tss.items()}
+        import torch.distributed as dist
+        mine = {"ids": [int(i) for i in m.station_ids], "tss": {k: [(t, v.tolist()) for t, v in rows] for k, rows in self.tss.items()}}
+        every = [None] * m.world
+        dist.all_gather_object(every, mine)
+        if m.rank != 0:
+            return {}
+        ids = np.array(sorted(i for e in every for i in e["ids"]), np.int64)
+        col = {int(i): k for k, i in enumerate(ids)}
+        out = {}
+        for name in sorted({k for e in every for k in e["tss"]}):
+            steps = sorted({t for e in every for t, _ in e["tss"].get(name, [])})
+            table = {t: np.full(len(ids), np.nan, np.float32) for t in steps}
+            for e in every:
+                cols = [col[i] for i in e["ids"]]
+                for t, v in e["tss"].get(name, []):
+                    table[t][cols] = np.asarray(v, np.float32)
+            out[name] = (ids, [(t, table[t]) for t in steps])
+        return out
+
     def write_tss(self):
         """The reference moves *.tss to the output directory at the end of the run (sphy.py:1273-1278)."""
-        for name, rows in self.tss.items():
-            csf.write_tss(os.path.join(self.m.outpath, name + ".tss"), self.m.station_ids, rows)
+        for name, (ids, rows) in self.tss_tables().items():
+            os.makedirs(self.m.outpath, exist_ok=True)
+            csf.write_tss(os.path.join(self.m.outpath, name + ".tss"), ids, rows)

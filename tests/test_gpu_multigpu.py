@@ -354,3 +354,49 @@ def test_model_with_structures_on_the_trunk_list_matches_the_oracle_port(monkeyp
         assert np.array_equal(getattr(model, k).cpu().numpy(), getattr(port, k)[order]), k
     torch.cuda.synchronize()
     model.close()
+
+
+def test_run_script_on_two_gpus_writes_the_same_outputs():
+    """`python -m torch.distributed.run --nproc-per-node 2 -m sphy_b200 sphy_config.cfg`: the basin split across two GPUs, rank 0
+    assembling the reported rasters and merging the .tss columns -- against the same run on one GPU, file by file."""
+    import datetime
+    import os
+    import subprocess
+    import sys
+    import tempfile
+
+    import torch
+    from sphy_b200 import csf, synth
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for world in (1, 2):
+        cat = synth.make_catchment(70, 64, seed=29, nsteps=6, start=datetime.date(2001, 6, 1), report_daily=("TotRF", "StorRootW"),
+                                   report_opts={"QallRAtot": ("D", "NONE", "D"), "TotRF": ("D", "NONE", "D")},
+                                   params=dict(SubWater=470.0, RootDepthFlat=150.0, Pscale=2.5))
+        tmp = tempfile.mkdtemp(prefix=f"sphy_cli{world}_")
+        cfg = cat.write_inputs(os.path.join(tmp, "in"), os.path.join(tmp, "out"))
+        cat.write_csf_inputs(os.path.join(tmp, "in"), 6)
+        launch = ([sys.executable, "-m", "sphy_b200", cfg] if world == 1 else
+                  [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                   "--master-port", str(29850 + os.getpid() % 100), "-m", "sphy_b200", cfg])
+        r = subprocess.run(launch, cwd=root, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+        assert r.stdout.count("Simulation succesfully completed") == 1
+        outs.append(os.path.join(tmp, "out"))
+    one, two = (sorted(os.listdir(o)) for o in outs)
+    assert one == two and len(one) >= 14, (one, two)
+    for f in one:
+        if f.endswith(".tss"):
+            a = np.loadtxt(os.path.join(outs[0], f), skiprows=3 + int(open(os.path.join(outs[0], f)).readlines()[1]) - 1)
+            b = np.loadtxt(os.path.join(outs[1], f), skiprows=3 + int(open(os.path.join(outs[1], f)).readlines()[1]) - 1)
+            assert a.shape == b.shape and a.shape[1] >= 2 and np.allclose(a, b, rtol=2e-5, atol=1e-9), f
+        else:
+            a, _ = csf.read_map(os.path.join(outs[0], f))
+            b, _ = csf.read_map(os.path.join(outs[1], f))
+            assert a.shape == b.shape == (70, 64)
+            if f.lower().startswith("qall"):
+                assert np.allclose(a, b, rtol=1e-5, atol=1e-12, equal_nan=True), f
+            else:
+                assert np.array_equal(a, b, equal_nan=True), f          # the water balance does not depend on the split
