@@ -138,6 +138,31 @@ def test_exchange_world2_gloo():
     assert ret.get(timeout=5) == 1
 
 
+def test_plan_reslake_edge_cases():
+    """No structures at all; a structure on the outlet cell (nothing before it in the DFS order); unsorted input is refused."""
+    _, _, ldd, _ = synth.make_dem_ldd(90, 80, 100.0, seed=4, outlets="single")
+    st = LddStruct(ldd)
+    pre, sub_size = dfs_order(st)
+    down, level = device_order_structures(st, pre)
+    b = multigpu.partition_bounds(st.n, 3)
+    cell, sub, *_ = trunk_select(sub_size, level, down, 2 ** 31 - 1, 2 ** 62, b, np.zeros(0, np.int64))
+    rl = multigpu.plan_reslake(cell, sub, np.zeros(0, np.int64), np.zeros((0, 8), np.int64), b)
+    assert rl["n_struct"] == 0 and rl["entry_idx"].size == 0 and (rl["entry_cut"] == -1).all() and rl["entry_ptr"][-1] == 0
+    cut = np.array([0, int(np.flatnonzero(sub_size > 500)[-1])], np.int64)          # the outlet itself and a tributary
+    cell, sub, *_ = trunk_select(sub_size, level, down, 2 ** 31 - 1, 2 ** 62, b, cut)
+    rl = multigpu.plan_reslake(cell, sub, cut, np.full((2, 8), -1, np.int64), b)
+    assert rl["cut_slot"][0] == 0 and rl["entry_cut"][0] == 0
+    ptr, idx = rl["entry_ptr"], rl["entry_idx"]
+    assert list(idx[ptr[0]:ptr[1]]) == [1]                     # the tributary structure is top-level inside the outlet's range
+    inner = rl["cut_slot"][1]
+    assert ptr[inner + 1] == ptr[inner]                        # nothing upstream of it
+    assert (rl["x_rank"].reshape(2, 9)[:, :8] == -1).all() and (rl["x_rank"].reshape(2, 9)[:, 8] >= 0).all()
+    with pytest.raises(ValueError):
+        multigpu.plan_reslake(cell, sub, cut[::-1], np.full((2, 8), -1, np.int64), b)
+    with pytest.raises(ValueError):
+        multigpu.plan_reslake(cell[1:], sub[1:], cut, np.full((2, 8), -1, np.int64), b)   # the outlet structure is not listed
+
+
 @pytest.mark.parametrize("world", [1, 2, 4])
 def test_lakes_and_reservoirs_on_the_trunk_list(world):
     """Lakes / reservoirs on a (partitioned) basin: the plain scan plus a correction of the cells downstream of the
@@ -155,7 +180,10 @@ def test_lakes_and_reservoirs_on_the_trunk_list(world):
     cut = np.unique(np.concatenate([rng.choice(big, 9, replace=False), rng.choice(np.flatnonzero((sub_size > 20) & (sub_size < 200)), 5, replace=False)]))
     stem = np.flatnonzero(sub_size > n // 3)
     cut = np.unique(np.concatenate([cut, stem[[len(stem) // 2, len(stem) // 2 + 1]]]))       # receiver of one is a structure itself
-    cut = cut[cut > 0]
+    if world != 2:
+        cut = cut[cut > 0]
+    else:
+        cut = np.unique(np.concatenate([[0], cut]))             # a reservoir on the outlet cell itself
     ns = cut.size
     canon = np.empty(n, np.int64)
     canon[pre] = np.arange(n)                                   # device index -> canonical cell
