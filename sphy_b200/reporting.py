@@ -23,6 +23,26 @@ from . import csf
 PERIODS = ("Day", "Month", "Year", "Final", "MonthSum", "YearSum", "MonthAvg", "YearAvg")
 
 
+def merge_tss(every):
+    """Time-series tables of a basin split across GPUs (pure host logic).  `every[r]` = {"ids": station ids rank r owns,
+    "tss": {name: [(timestep, values at those stations)]}}; -> {name: (all station ids ascending, [(timestep, values)])}
+    with the columns ordered by station id like the reference's TimeoutputTimeseries (NaN where nobody sampled)."""
+    ids = np.array(sorted(int(i) for e in every for i in e["ids"]), np.int64)
+    if len(set(ids.tolist())) != len(ids):
+        raise ValueError("a station id is owned by more than one rank")
+    col = {int(i): k for k, i in enumerate(ids)}
+    out = {}
+    for name in sorted({k for e in every for k in e["tss"]}):
+        steps = sorted({t for e in every for t, _ in e["tss"].get(name, [])})
+        table = {t: np.full(len(ids), np.nan, np.float32) for t in steps}
+        for e in every:
+            cols = [col[int(i)] for i in e["ids"]]
+            for t, v in e["tss"].get(name, []):
+                table[t][cols] = np.asarray(v, np.float32)
+        out[name] = (ids, [(t, table[t]) for t in steps])
+    return out
+
+
 class Reporting:
     def __init__(self, model, csv_path, write_files=False):
         self.m = model
@@ -180,20 +200,7 @@ class Reporting:
         mine = {"ids": [int(i) for i in m.station_ids], "tss": {k: [(t, v.tolist()) for t, v in rows] for k, rows in self.tss.items()}}
         every = [None] * m.world
         dist.all_gather_object(every, mine)
-        if m.rank != 0:
-            return {}
-        ids = np.array(sorted(i for e in every for i in e["ids"]), np.int64)
-        col = {int(i): k for k, i in enumerate(ids)}
-        out = {}
-        for name in sorted({k for e in every for k in e["tss"]}):
-            steps = sorted({t for e in every for t, _ in e["tss"].get(name, [])})
-            table = {t: np.full(len(ids), np.nan, np.float32) for t in steps}
-            for e in every:
-                cols = [col[i] for i in e["ids"]]
-                for t, v in e["tss"].get(name, []):
-                    table[t][cols] = np.asarray(v, np.float32)
-            out[name] = (ids, [(t, table[t]) for t in steps])
-        return out
+        return merge_tss(every) if m.rank == 0 else {}
 
     def write_tss(self):
         """The reference moves *.tss to the output directory at the end of the run (sphy.py:1273-1278)."""

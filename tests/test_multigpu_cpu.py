@@ -224,3 +224,20 @@ def test_lakes_and_reservoirs_on_the_trunk_list(world):
             assert np.allclose(em.S, S, rtol=2e-6), day
     em.flush()
     assert np.allclose(em.S, S, rtol=2e-6) and np.allclose(em.Qin, Qin, rtol=2e-6, atol=1e-6)
+
+
+def test_tss_tables_of_a_split_basin_merge_by_station_id():
+    """Every rank samples the stations inside its own range; rank 0 merges the columns by ascending station id
+    (sphy_b200/reporting.py: merge_tss), also when a rank owns no station or misses a step."""
+    from sphy_b200.reporting import merge_tss
+    every = [{"ids": [4, 1], "tss": {"QAllDTS": [(1, [40.0, 10.0]), (2, [41.0, 11.0])], "TotRDTS": [(1, [4.0, 1.0])]}},
+             {"ids": [], "tss": {}},
+             {"ids": [3], "tss": {"QAllDTS": [(1, [30.0]), (2, [31.0])]}}]
+    out = merge_tss(every)
+    ids, rows = out["QAllDTS"]
+    assert ids.tolist() == [1, 3, 4]
+    assert [t for t, _ in rows] == [1, 2] and rows[0][1].tolist() == [10.0, 30.0, 40.0] and rows[1][1].tolist() == [11.0, 31.0, 41.0]
+    ids, rows = out["TotRDTS"]
+    assert rows[0][1][0] == 1.0 and np.isnan(rows[0][1][1]) and rows[0][1][2] == 4.0
+    with pytest.raises(ValueError):
+        merge_tss([{"ids": [1], "tss": {}}, {"ids": [1], "tss": {}}])

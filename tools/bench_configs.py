@@ -27,6 +27,8 @@ def run(name, kw, steps, route):
     cfg = cat.write_inputs(os.path.join(tmp, "in"), os.path.join(tmp, "out"))
     model = SphyModel(cfg, CatchmentSource(cat), route_method=route, diagnostics=False)
     model.initial()
+    if getattr(model, "_rl_part", False):
+        name += " (structures on the trunk list)"
     dem = torch.from_numpy(np.ascontiguousarray(model._compact_np(cat.dem))).cuda()
     ring = bench.device_forcing_ring(torch, dem, 8, seed=7)
     model.set_device_forcing(lambda t: ring[t % len(ring)])
@@ -59,6 +61,5 @@ if __name__ == "__main__":
         if "C2" in want:
             run("C2 500x500 + snow + glacier", dict(nrows=500, ncols=500, snow=True, glacier=True, params=wet), a.steps, route)
         if "C3" in want:
-            run("C3 2000x2000 1 km, 34 reservoirs + 6 lakes" + (" (structures on the trunk list)" if os.environ.get("SPHY_RESLAKE_PLAN") == "1" else ""),
-                dict(nrows=2000, ncols=2000, cellsize=1000.0, reservoirs=True, lakes=True, n_res_simple=24, n_res_adv=10, n_lakes=6, params=wet),
+            run("C3 2000x2000 1 km, 34 reservoirs + 6 lakes", dict(nrows=2000, ncols=2000, cellsize=1000.0, reservoirs=True, lakes=True, n_res_simple=24, n_res_adv=10, n_lakes=6, params=wet),
                 min(a.steps, 100), route)
