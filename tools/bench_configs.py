@@ -50,7 +50,7 @@ def run(name, kw, steps, route):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=365)
-    ap.add_argument("--configs", default="C1,C2,C3", help="comma-separated subset of C1,C2,C3")
+    ap.add_argument("--configs", default="C1,C2,C3", help="comma-separated subset of C1,C2,C3,C3x")
     ap.add_argument("--routes", default="scan,levels")
     a = ap.parse_args()
     wet = dict(SubWater=470.0)
@@ -63,3 +63,7 @@ if __name__ == "__main__":
         if "C3" in want:
             run("C3 2000x2000 1 km, 34 reservoirs + 6 lakes", dict(nrows=2000, ncols=2000, cellsize=1000.0, reservoirs=True, lakes=True, n_res_simple=24, n_res_adv=10, n_lakes=6, params=wet),
                 min(a.steps, 100), route)
+        if "C3x" in want:      # config-3 physics on the basin of config 4: what the structure path costs at 1e8 cells
+            run("C3x 10000x10000 250 m, 34 reservoirs + 6 lakes", dict(nrows=10000, ncols=10000, cellsize=250.0, reservoirs=True, lakes=True,
+                                                                      n_res_simple=24, n_res_adv=10, n_lakes=6, params=wet),
+                min(a.steps, 20), route)
