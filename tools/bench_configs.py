@@ -36,11 +36,16 @@ def run(name, kw, steps, route):
         model.dynamic()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    profiled = os.environ.get("SPHY_BENCH_PROFILE") == "1"     # ncu --profile-from-start off: capture the timed steps only
+    if profiled:
+        torch.cuda.cudart().cudaProfilerStart()
     e0.record()
     for _ in range(steps):
         model.dynamic()
     e1.record()
     torch.cuda.synchronize()
+    if profiled:
+        torch.cuda.cudart().cudaProfilerStop()
     ms = e0.elapsed_time(e1)
     print(json.dumps({"config": name, "cells": model.n, "levels": model.nlevels, "steps": steps, "routing": route,
                       "ms_per_step": ms / steps, "Mcell_timesteps_per_s": model.n * steps / (ms * 1e-3) / 1e6}), flush=True)
