@@ -460,7 +460,7 @@ typedef struct {
     const int32_t *entry_ptr, *entry_idx;   /* CSR over the m list entries: top-level structures strictly inside the range */
     const int32_t *x_rank, *x_local; /* [n_struct * SPHY_RL_EXTRA] owner rank (-1: none) / local cell of donor 0..7 and of the structure cell */
     const float *qmask;              /* [n local] 2 at listed cells, QFRAC elsewhere (the main pass leaves listed cells alone) */
-    float *material;                 /* [n local] workspace: routed material, m3/day */
+    float *material;                 /* reserved (may be NULL): the main pass forms the material 0.001 * cellarea * TotR itself */
     float *qday;                     /* [n local] in/out: the day's blended discharge, m3/day (zero before the first step) */
     double *extra;                   /* [n_struct * SPHY_RL_EXTRA] workspace */
     double *top;                     /* [m] workspace: global prefix at the end of each listed cell's range (its noise scale) */

@@ -54,8 +54,9 @@ struct ScanArgs {
     // lakes / reservoirs on the trunk list: per-structure values that ride at the end of the block (component 0)
     const double *extra;
     int32_t n_extra;
-    // lakes / reservoirs (advanced_routing.ROUT): material is already m3/day, cut cells take the structure outflow
+    // lakes / reservoirs (advanced_routing.ROUT): material is m3/day, cut cells take the structure outflow
     int adv;
+    float volf;                           // material = volf * m (REAL4): 1 when m is already m3/day, 0.001 * cellarea when m is TotR [mm]
     const float *frac;                    // dense QFRAC (0 at lake / reservoir cells)
     const float *qout_dense;              // dense structure outflow, m3/day
     float *qday;                          // dense blended Q, m3/day (what upstream(ldd, Q) reads at the structures)
@@ -181,7 +182,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_MIN_CTAS) k_scan_main(const
                 const int o = i * SCAN_CHUNK + lane * 4;
                 double v0, v1, v2, v3;
                 if (ADV) {
-                    v0 = (double)x[i].x; v1 = (double)x[i].y; v2 = (double)x[i].z; v3 = (double)x[i].w;
+                    v0 = (double)(a.volf * x[i].x); v1 = (double)(a.volf * x[i].y);     // advanced_routing.py:137,159 (REAL4 product)
+                    v2 = (double)(a.volf * x[i].z); v3 = (double)(a.volf * x[i].w);
                     for (int32_t k = kb; k < ke; ++k) {        // float64 corrections at the cut cells of this tile
                         const int off = (__ldg(a.cut_cell + k) - tb32) - o;
                         if (off >= 0 && off < 4) {
@@ -799,6 +801,7 @@ static int scan_prepare(sphy_ctx *ctx, int ncomp, const float *const *runoff_mm,
         a.omkc[c] = one_m_kx;
     }
     a.to_m3s = (0.001 * (double)ctx->cellarea) / 86400.0;
+    a.volf = 1.0f;
     a.n = ctx->n;
     a.ntiles = ctx->n_tiles;
     return SPHY_OK;
@@ -1421,14 +1424,6 @@ __global__ void k_rl_part_gather(int32_t n_extra, const int32_t *__restrict__ x_
     extra[i] = v;
 }
 
-__global__ void k_rl_part_material(const float *__restrict__ totr, const float *__restrict__ qfrac, float vol_factor, int64_t n,
-                                   float *__restrict__ m)
-{
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    m[i] = qfrac[i] == 0.0f ? 0.0f : vol_factor * totr[i];     // advanced_routing.py:159-161 (second term)
-}
-
 int reslake_plan_check(sphy_ctx *ctx, const sphy_reslake *rl, const sphy_reslake_plan *plan, int32_t stride, const char *who)
 {
     if (!ctx->ldd_ready) SPHY_FAIL(ctx, SPHY_E_STATE, "%s before sphy_ldd_build", who);
@@ -1437,7 +1432,7 @@ int reslake_plan_check(sphy_ctx *ctx, const sphy_reslake *rl, const sphy_reslake
     if (rl->n_struct < 0 || !rl->qfrac || (rl->n_struct > 0 && (!rl->kind || !rl->par || !rl->StorRES || !rl->Qout || !rl->Qin)))
         SPHY_FAIL(ctx, SPHY_E_INVALID, "%s: incomplete structure table", who);
     if (rl->n_struct > 0 && !ctx->sl_cuts) SPHY_FAIL(ctx, SPHY_E_STATE, "%s: the trunk list was selected without the structure cells (sphy_trunk_select_cuts)", who);
-    if (!plan->qmask || !plan->material || !plan->qday || !plan->top || !plan->entry_cut || !plan->entry_ptr ||
+    if (!plan->qmask || !plan->qday || !plan->top || !plan->entry_cut || !plan->entry_ptr ||
         (rl->n_struct > 0 && (!plan->cut_slot || !plan->entry_idx || !plan->x_rank || !plan->x_local || !plan->extra)))
         SPHY_FAIL(ctx, SPHY_E_INVALID, "%s: incomplete plan", who);
     if (stride != ctx->sl_stride) SPHY_FAIL(ctx, SPHY_E_INVALID, "%s: stride %d != planned %d", who, stride, ctx->sl_stride);
@@ -1460,10 +1455,12 @@ extern "C" int sphy_route_reslake_begin(sphy_ctx *ctx, const sphy_reslake *rl, c
     const int32_t n_extra = SPHY_RL_EXTRA * rl->n_struct;
     if (n_extra > 0)
         k_rl_part_gather<<<div_up(n_extra, 128), 128, 0, st>>>(n_extra, plan->x_rank, plan->x_local, ctx->sl_rank, plan->qday, totr, plan->extra);
-    k_rl_part_material<<<div_up(ctx->n, 256), 256, 0, st>>>(totr, rl->qfrac, 0.001f * ctx->cellarea, ctx->n, plan->material);
     SPHY_LAUNCH_CHECK(ctx);
+    // The main pass forms the material itself, 0.001 * cellarea * TotR as a REAL4 product (advanced_routing.py:137,159), for every
+    // cell -- structure cells included: whatever they add to a range sum is taken out again with E(k) of the structure, which
+    // holds the same terms (every cell downstream of a structure subtracts E(k) - Qout(k)).
     ScanArgs a;
-    const float *mm[1] = {plan->material};
+    const float *mm[1] = {totr};
     float *qq[1] = {q_state};
     if ((rc = scan_prepare(ctx, 1, mm, qq, kx, one_minus_kx, st, a)) != SPHY_OK) return rc;
     if ((rc = trunk_prepare(ctx, 1, st)) != SPHY_OK) return rc;
@@ -1476,6 +1473,7 @@ extern "C" int sphy_route_reslake_begin(sphy_ctx *ctx, const sphy_reslake *rl, c
     if (push && (int64_t)stride > ctx->p2p_pitch)
         SPHY_FAIL(ctx, SPHY_E_INVALID, "sphy_route_reslake_begin: %d values exceed the peer buffer pitch", stride);
     a.adv = 1;
+    a.volf = 0.001f * ctx->cellarea;
     a.frac = plan->qmask;
     a.qout_dense = plan->qmask;                                // never read: no cell of the mask is 0
     a.qday = plan->qday;

@@ -1123,13 +1123,13 @@ class SphyModel:
         i32 = lambda a: self._dev(np.ascontiguousarray(a if len(a) else np.zeros(1), np.int32))  # noqa: E731
         p = {k: i32(ph[k]) for k in ("cut_slot", "entry_cut", "entry_ptr", "entry_idx", "x_rank", "x_local")}
         p["qmask"] = self._dev(qmask)
-        p["material"] = self._full(0.0)
         p["qday"] = self._full(0.0)
         p["extra"] = torch.zeros(max(ns * _lib.RL_EXTRA, 1), dtype=torch.float64, device=self.device)
         p["top"] = torch.zeros(max(m, 1), dtype=torch.float64, device=self.device)
         self._rl_plan_dev = p
-        self._rl_plan = _lib.ResLakePlan(*[p[k].data_ptr() for k in ("cut_slot", "entry_cut", "entry_ptr", "entry_idx", "x_rank",
-                                                                     "x_local", "qmask", "material", "qday", "extra", "top")])
+        self._rl_plan = _lib.ResLakePlan(*[p[k].data_ptr() if k in p else None for k in
+                                           ("cut_slot", "entry_cut", "entry_ptr", "entry_idx", "x_rank", "x_local", "qmask", "material", "qday",
+                                            "extra", "top")])
         self._rl_pending = False
         # the slots of the exchange extras this rank owns (flush_structures)
         xr, xl = ph["x_rank"].astype(np.int64), ph["x_local"].astype(np.int64)

@@ -169,7 +169,9 @@ class ReslakeEmulation:
     def step(self, totr):
         f32 = np.float32
         x = self._extras(totr)
-        m = np.where(self.qfrac == 0, f32(0), self.vol * totr).astype(np.float32)
+        # the material of EVERY cell, structure cells included (advanced_routing.py:159 zeroes them): what they add to a range
+        # sum is taken out again with E(k) of the structure, which holds the same terms
+        m = (self.vol * totr).astype(np.float32)
         blend = lambda f, qold: (self.omk * f + ((qold * f32(24)) * f32(3600)) * self.kx).astype(np.float32)  # noqa: E731
         sends = []
         for p in range(self.world):

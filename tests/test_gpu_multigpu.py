@@ -162,12 +162,11 @@ def _install_reslake_plan(lib, torch, ctx, bounds, rank, world, cut, qfrac):
     t = {k: torch.from_numpy(np.ascontiguousarray(rl[k] if len(rl[k]) else np.zeros(1), np.int32)).cuda()
          for k in ("cut_slot", "entry_cut", "entry_ptr", "entry_idx", "x_rank", "x_local")}
     t["qmask"] = torch.from_numpy(qmask).cuda()
-    t["material"] = torch.zeros(hi - lo, device="cuda")
     t["qday"] = torch.zeros(hi - lo, device="cuda")
     t["extra"] = torch.zeros(len(cut) * _lib.RL_EXTRA, dtype=torch.float64, device="cuda")
     t["top"] = torch.zeros(max(m, 1), dtype=torch.float64, device="cuda")
-    struct = _lib.ResLakePlan(*[t[k].data_ptr() for k in ("cut_slot", "entry_cut", "entry_ptr", "entry_idx", "x_rank", "x_local", "qmask",
-                                                          "material", "qday", "extra", "top")])
+    struct = _lib.ResLakePlan(*[t[k].data_ptr() if k in t else None for k in ("cut_slot", "entry_cut", "entry_ptr", "entry_idx", "x_rank",
+                                                                              "x_local", "qmask", "material", "qday", "extra", "top")])
     x_cell = np.where(rl["x_rank"] >= 0, np.asarray(bounds)[np.maximum(rl["x_rank"], 0)] + rl["x_local"], -1)
     return struct, t, stride, listed, x_cell
 
