@@ -241,3 +241,16 @@ def test_tss_tables_of_a_split_basin_merge_by_station_id():
     assert rows[0][1][0] == 1.0 and np.isnan(rows[0][1][1]) and rows[0][1][2] == 4.0
     with pytest.raises(ValueError):
         merge_tss([{"ids": [1], "tss": {}}, {"ids": [1], "tss": {}}])
+
+
+def test_write_tss_single_process_path(tmp_path):
+    """Reporting.write_tss on one GPU: the model's own station ids and rows go straight to the PCRaster .tss layout."""
+    import types
+    from sphy_b200.reporting import Reporting
+    m = types.SimpleNamespace(world=1, rank=0, station_ids=np.array([1, 2, 3]), outpath=str(tmp_path))
+    rep = types.SimpleNamespace(m=m, tss={"QAllDTS": [(1, np.array([1., 2., 3.], np.float32)), (2, np.array([4., 5., 6.], np.float32))]})
+    rep.tss_tables = lambda: Reporting.tss_tables(rep)
+    Reporting.write_tss(rep)
+    lines = open(os.path.join(str(tmp_path), "QAllDTS.tss")).read().splitlines()
+    assert lines[:6] == ["timeseries scalar", "4", "timestep", "1", "2", "3"]
+    assert [float(x) for x in lines[6].split()] == [1, 1, 2, 3] and [float(x) for x in lines[7].split()] == [2, 4, 5, 6]
