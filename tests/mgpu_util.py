@@ -124,7 +124,8 @@ class ReslakeEmulation:
     only exists after the listed cells are finished) is applied at the head of day t + 1 from values that travel in that
     day's exchange block, or by flush()."""
 
-    def __init__(self, sub_size, level, down, bounds, cut_cell, donors, qfrac, kx, vol, S0):
+    def __init__(self, sub_size, level, down, bounds, cut_cell, donors, qfrac, kx, vol, S0, rule=reslake_rule):
+        self.rule = rule                              # storage [ns] -> outflow [ns] (the stand-in, or the port's QLake / QRes)
         from sphy_b200 import multigpu
         self.b = np.asarray(bounds, np.int64)
         self.world = self.b.size - 1
@@ -187,7 +188,7 @@ class ReslakeEmulation:
             self._apply_lag(x)
         xt = x.reshape(self.ns, 9)[:, 8].astype(np.float32)
         self.S = (self.S + self.vol * xt).astype(np.float32)                # advanced_routing.py:136-138
-        self.Qout = reslake_rule(self.S)
+        self.Qout = self.rule(self.S)
         world = self.world
         base = np.concatenate([[0.0], np.cumsum([g[0] for g in sends])])[:world]
 

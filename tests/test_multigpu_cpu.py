@@ -254,3 +254,57 @@ def test_write_tss_single_process_path(tmp_path):
     lines = open(os.path.join(str(tmp_path), "QAllDTS.tss")).read().splitlines()
     assert lines[:6] == ["timeseries scalar", "4", "timestep", "1", "2", "3"]
     assert [float(x) for x in lines[6].split()] == [1, 1, 2, 3] and [float(x) for x in lines[7].split()] == [2, 4, 5, 6]
+
+
+@pytest.mark.parametrize("name", ["c3_res_lake", "c3_res_only", "c3_lake_only"])
+def test_structure_path_reproduces_the_reference_golden(name):
+    """The algorithm behind sphy_route_reslake_begin / _finish (plain range sums, E(k) - Qout(k) taken out downstream of every
+    structure, storage fed by upstream(ldd, Q) one step late) driven by the daily TotR maps the UNMODIFIED reference reported, with
+    the port's lakes.QLake / reservoirs.QRes as the outflow functions: discharge and storage must follow the reference's own
+    QRAold / StorRES states of the golden run (within the scan path's 1e-5; the reference rounds every cell's sum to REAL4)."""
+    from oracle.sphy_port import PortInputs, PortModel
+    from tests.golden_util import catchment_from_golden
+    from tests.mgpu_util import ReslakeEmulation
+    cat, z, meta = catchment_from_golden(name)
+    inp = PortInputs(cat)
+    port = PortModel(inp)                                       # only its structure functions and tables are used
+    st = inp.lddst
+    n = st.n
+    pre, sub_size = dfs_order(st)
+    down, level = device_order_structures(st, pre)
+    canon = np.empty(n, np.int64)
+    canon[pre] = np.arange(n)
+    cut_c = np.flatnonzero(port.QFRAC == 0)                      # canonical structure cells
+    cut = np.sort(pre[cut_c])
+    cut_c = canon[cut]                                          # reordered like the device list
+    donors = np.full((cut.size, 8), -1, np.int64)
+    for j, c in enumerate(cut_c):
+        d = st.don_idx[st.don_ptr[c]:st.don_ptr[c + 1]]
+        donors[j, :len(d)] = pre[d]
+    qfrac = np.ones(n, np.float32)
+    qfrac[cut] = 0
+    g = st.gather
+
+    def rule(S):                                                # the reference's outflow functions on the emulation's storages
+        port.StorRES = np.zeros(n, np.float32)
+        port.StorRES[cut_c] = S
+        q = np.zeros(n, np.float32)
+        if inp.lake is not None:
+            q[inp.lake["cells"]] = port.QLake(None)
+        if inp.res is not None:
+            q[inp.res["cells"]] = port.QRes()
+        return q[cut_c].astype(np.float32)
+
+    S0 = g(z["state/StorRES"][0])[cut_c]
+    em = ReslakeEmulation(sub_size, level, down, np.array([0, n], np.int64), cut, donors, qfrac, float(inp.kx),
+                          np.float32(0.001) * np.float32(inp.cellarea), S0, rule=rule)
+    em.q = g(z["state/QRAold"][0])[canon].astype(np.float32)
+    import datetime
+    for t in range(1, meta["nsteps"] + 1):
+        port.curdate = cat.start + datetime.timedelta(days=t - 1)
+        totr = g(z["report/TotR"][t - 1])[canon]                # the reference's own TotR of the day, device order
+        got = em.step(totr)
+        want = g(z["state/QRAold"][t])[canon]
+        assert np.allclose(got, want, rtol=1e-5, atol=1e-12), (name, t, float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-12))))
+        em.flush()
+        assert np.allclose(em.S, g(z["state/StorRES"][t])[cut_c], rtol=1e-5, atol=1e-3), (name, t)
