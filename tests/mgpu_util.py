@@ -167,9 +167,13 @@ class ReslakeEmulation:
         if self.pending:
             self._apply_lag(self._extras(np.zeros_like(self.q)))
 
-    def step(self, totr):
+    def step(self, totr, exchange=None):
+        """One day.  `exchange(blocks, stride)` stands for the all-gather of the ranks' blocks (default: in-process); a block is
+        [range total, prefixes at the rank's published positions, padding, the per-structure extras this rank owns]."""
         f32 = np.float32
-        x = self._extras(totr)
+        xg = self._extras(totr)
+        nx = self.ns * 9
+        stride = int(self.plan["stride"]) + nx
         # the material of EVERY cell, structure cells included (advanced_routing.py:159 zeroes them): what they add to a range
         # sum is taken out again with E(k) of the structure, which holds the same terms
         m = (self.vol * totr).astype(np.float32)
@@ -182,8 +186,16 @@ class ReslakeEmulation:
             ordinary = ~np.isnan(acc)
             qd = blend(np.nan_to_num(acc).astype(np.float32), self.q[lo:hi])
             self.qday[lo:hi][ordinary] = qd[ordinary]
-            sends.append(send)
-        # ---- after the exchange: the same on every rank
+            block = np.zeros(stride)
+            block[:send.size] = send
+            block[stride - nx:] = np.where(self.rl["x_rank"] == p, xg, 0.0)          # what k_rl_part_gather leaves on rank p
+            sends.append(block)
+        if exchange is not None:
+            sends = exchange(sends, stride)
+        # ---- after the exchange: the same on every rank; every extra is read from its owner's block
+        x = np.zeros(nx)
+        for i in np.flatnonzero(self.rl["x_rank"] >= 0):
+            x[i] = sends[self.rl["x_rank"][i]][stride - nx + i]
         if self.pending:
             self._apply_lag(x)
         xt = x.reshape(self.ns, 9)[:, 8].astype(np.float32)

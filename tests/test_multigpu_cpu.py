@@ -308,3 +308,81 @@ def test_structure_path_reproduces_the_reference_golden(name):
         assert np.allclose(got, want, rtol=1e-5, atol=1e-12), (name, t, float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-12))))
         em.flush()
         assert np.allclose(em.S, g(z["state/StorRES"][t])[cut_c], rtol=1e-5, atol=1e-3), (name, t)
+
+
+def _reslake_worker(rank, world, port, ret):
+    """One process per rank: the blocks (prefixes + per-structure extras) really travel through an all-gather."""
+    import torch
+    import torch.distributed as dist
+    from tests.mgpu_util import ReslakeEmulation, reslake_rule
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    _, _, ldd, _ = synth.make_dem_ldd(120, 110, 100.0, seed=9, outlets="single")
+    st = LddStruct(ldd)
+    n = st.n
+    pre, sub_size = dfs_order(st)
+    down, level = device_order_structures(st, pre)
+    rng = np.random.default_rng(2)
+    cut = np.unique(np.concatenate([rng.choice(np.flatnonzero(sub_size > 300), 6, replace=False), rng.choice(np.flatnonzero(sub_size > n // 4), 2)]))
+    cut = cut[cut > 0]
+    canon = np.empty(n, np.int64)
+    canon[pre] = np.arange(n)
+    donors = np.full((cut.size, 8), -1, np.int64)
+    for j, c in enumerate(cut):
+        d = st.don_idx[st.don_ptr[canon[c]]:st.don_ptr[canon[c] + 1]]
+        donors[j, :len(d)] = pre[d]
+    qfrac = np.ones(n, np.float32)
+    qfrac[cut] = 0
+    kx, vol = 0.9, np.float32(10.0)
+    S0 = rng.uniform(1e4, 1e6, cut.size).astype(np.float32)
+    b = multigpu.partition_bounds(n, world)
+    em = ReslakeEmulation(sub_size, level, down, b, cut, donors, qfrac, kx, vol, S0)
+
+    def exchange(blocks, stride):
+        recv = torch.zeros(world * stride, dtype=torch.float64)
+        dist.all_gather_into_tensor(recv, torch.from_numpy(np.ascontiguousarray(blocks[rank])))    # only this rank's own block
+        return list(recv.numpy().reshape(world, stride))
+
+    f32 = np.float32
+    fr_c, cut_c = qfrac[pre], canon[cut]
+    S, q_c, ok = S0.copy(), np.zeros(n, np.float32), True
+    lo, hi = int(b[rank]), int(b[rank + 1])
+    for day in range(4):
+        totr = (rng.gamma(0.8, 4.0, n) * (rng.random(n) < 0.6)).astype(np.float32)
+        got = em.step(totr, exchange=exchange)
+        totr_c = totr[pre]
+        S = (S + vol * totr_c[cut_c]).astype(np.float32)
+        Qout = reslake_rule(S)
+        qo = np.zeros(n, np.float32)
+        qo[cut_c] = Qout
+        m = (st.upstream(qo) + np.where(fr_c == 0, f32(0), vol * totr_c)).astype(np.float32)
+        F = st.accuflux_f64(m, fr_c).astype(np.float32)
+        qd = np.where(fr_c == 0, qo, f32(1 - kx) * F + ((q_c * f32(24)) * f32(3600)) * f32(kx)).astype(np.float32)
+        S = ((S - Qout) + st.upstream(qd)[cut_c]).astype(np.float32)
+        q_c = (qd / f32(86400)).astype(np.float32)
+        ok = ok and bool(np.allclose(got[lo:hi], q_c[canon][lo:hi], rtol=3e-6, atol=1e-9))
+    em.flush()
+    ok = ok and bool(np.allclose(em.S, S, rtol=2e-6))
+    flag = torch.tensor([1 if ok else 0])
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        ret.put(int(flag.item()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_structure_exchange_world2_gloo():
+    """World size 2 over gloo: every process contributes only its own rank's block (confluence prefixes + the per-structure
+    extras it owns); lakes / reservoirs downstream of the split see the other rank's water and structures."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_reslake_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert ret.get(timeout=5) == 1
