@@ -386,3 +386,99 @@ def test_structure_exchange_world2_gloo():
         p.join(180)
         assert p.exitcode == 0
     assert ret.get(timeout=5) == 1
+
+
+def _random_forest(rng, n, p_root=0.002):
+    """A random drainage forest with at most 8 donors per cell, numbered in depth-first pre-order (donors by ascending
+    original index): -> (down, sub_size) by device index."""
+    parent = np.full(n, -1, np.int64)
+    nchild = np.zeros(n, np.int64)
+    for i in range(1, n):
+        if rng.random() < p_root:
+            continue
+        for _ in range(20):
+            # mostly recent cells (long chains), sometimes anywhere (bushy confluences)
+            p = int(i - 1 - min(rng.geometric(0.3) - 1, i - 1)) if rng.random() < 0.7 else int(rng.integers(0, i))
+            if nchild[p] < 8:
+                parent[i] = p
+                nchild[p] += 1
+                break
+    kids = [[] for _ in range(n)]
+    for i in range(n):
+        if parent[i] >= 0:
+            kids[parent[i]].append(i)
+    pre = np.empty(n, np.int64)
+    size = np.ones(n, np.int64)
+    k = 0
+    for r in np.flatnonzero(parent < 0):
+        stack = [(int(r), 0)]
+        while stack:
+            v, j = stack.pop()
+            if j == 0:
+                pre[v] = k
+                k += 1
+            if j < len(kids[v]):
+                stack.append((v, j + 1))
+                stack.append((kids[v][j], 0))
+            elif parent[v] >= 0:
+                size[parent[v]] += size[v]
+    down = np.full(n, -1, np.int64)
+    has = parent >= 0
+    down[pre[has]] = pre[parent[has]]
+    sub = np.empty(n, np.int64)
+    sub[pre] = size
+    return down, sub
+
+
+@pytest.mark.parametrize("seed,world", [(1, 1), (2, 2), (3, 3), (4, 2)])
+def test_structure_plan_on_random_forests(seed, world):
+    """plan_reslake + the listed-cell correction on adversarial topologies: several outlets, bushy confluences, structures on
+    outlets, structures directly behind each other, structures whose donors live on another rank -- against a brute-force
+    accufractionflux walk."""
+    from tests.mgpu_util import ReslakeEmulation, reslake_rule
+    rng = np.random.default_rng(seed)
+    n = 3300
+    down, sub_size = _random_forest(rng, n)
+    assert np.all(down[1:][down[1:] >= 0] < np.arange(1, n)[down[1:] >= 0])            # pre-order: receivers come first
+    roots = np.flatnonzero(down < 0)
+    chain = [int(np.argmax(sub_size * (down >= 0)))]                                   # a cell and its receiver: adjacent structures
+    chain.append(int(down[chain[0]]))
+    cut = np.unique(np.concatenate([rng.choice(n, 25, replace=False), roots[:2], chain]))
+    ns = cut.size
+    kids = [[] for _ in range(n)]
+    for i in range(n):
+        if down[i] >= 0:
+            kids[down[i]].append(i)
+    donors = np.full((ns, 8), -1, np.int64)
+    for j, c in enumerate(cut):
+        donors[j, :len(kids[c])] = kids[c]
+    qfrac = np.ones(n, np.float32)
+    qfrac[cut] = 0
+    b = multigpu.partition_bounds(n, world) if world > 1 else np.array([0, n], np.int64)
+    kx, vol = 0.8, np.float32(7.5)
+    S0 = rng.uniform(1e3, 1e5, ns).astype(np.float32)
+    em = ReslakeEmulation(sub_size, np.zeros(n, np.int64), down, b, cut, donors, qfrac, kx, vol, S0)
+    f32 = np.float32
+    S, q = S0.copy(), np.zeros(n, np.float32)
+    for day in range(3):
+        totr = (rng.gamma(0.8, 4.0, n) * (rng.random(n) < 0.7)).astype(np.float32)
+        got = em.step(totr)
+        S = (S + vol * totr[cut]).astype(np.float32)
+        Qout = reslake_rule(S)
+        m = np.where(qfrac == 0, f32(0), vol * totr).astype(np.float64)
+        for j, c in enumerate(cut):
+            if down[c] >= 0:
+                m[down[c]] += float(Qout[j])                    # upstream(ldd, Qout) joins the receiver's material
+        F = m.copy()
+        for i in range(n - 1, -1, -1):                          # pre-order: every donor has a larger index
+            F[i] *= qfrac[i]
+            if down[i] >= 0:
+                F[down[i]] += F[i]
+        qd = (f32(1 - kx) * F.astype(np.float32) + ((q * f32(24)) * f32(3600)) * f32(kx)).astype(np.float32)
+        qd[cut] = Qout
+        Qin = np.array([np.sum(qd[kids[c]].astype(np.float64)) for c in cut]).astype(np.float32)
+        S = ((S - Qout) + Qin).astype(np.float32)
+        q = (qd / f32(86400)).astype(np.float32)
+        assert np.allclose(got, q, rtol=3e-6, atol=1e-9), (day, float(np.max(np.abs(got - q) / np.maximum(np.abs(q), 1e-9))))
+    em.flush()
+    assert np.allclose(em.S, S, rtol=3e-6)
