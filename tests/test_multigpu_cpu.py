@@ -482,3 +482,60 @@ def test_structure_plan_on_random_forests(seed, world):
         assert np.allclose(got, q, rtol=3e-6, atol=1e-9), (day, float(np.max(np.abs(got - q) / np.maximum(np.abs(q), 1e-9))))
     em.flush()
     assert np.allclose(em.S, S, rtol=3e-6)
+
+
+@pytest.mark.parametrize("uniform", [False, True])
+def test_rounding_drift_on_a_random_chain_heavy_forest(uniform):
+    """The drift accumulation on a topology no DEM produces: long chains (hundreds of levels) joined by random confluences of
+    very unequal size.  It must still follow the REAL4-per-cell reference, where plain float64 range sums drift away."""
+    rng = np.random.default_rng(11)
+    n = 30000
+    parent = np.full(n, -1, np.int64)
+    nchild = np.zeros(n, np.int64)
+    for i in range(1, n):
+        for _ in range(20):
+            p = i - 1 if rng.random() < 0.97 else int(rng.integers(0, i))
+            if nchild[p] < 8:
+                parent[i] = p
+                nchild[p] += 1
+                break
+    # the construction is already a pre-order only along the sticks: renumber depth-first
+    kids = [[] for _ in range(n)]
+    for i in range(1, n):
+        kids[parent[i]].append(i)
+    pre, size, k, stack = np.empty(n, np.int64), np.ones(n, np.int64), 0, [(0, 0)]
+    while stack:
+        v, j = stack.pop()
+        if j == 0:
+            pre[v] = k
+            k += 1
+        if j < len(kids[v]):
+            stack.append((v, j + 1))
+            stack.append((kids[v][j], 0))
+        elif parent[v] >= 0:
+            size[parent[v]] += size[v]
+    down = np.full(n, -1, np.int64)
+    down[pre[1:]] = pre[parent[1:]]
+    sub = np.empty(n, np.int64)
+    sub[pre] = size
+    level = np.zeros(n, np.int64)
+    for i in range(n - 1, -1, -1):
+        if down[i] >= 0:
+            level[down[i]] = max(level[down[i]], level[i] + 1)
+    assert level.max() > 300
+    m = (np.full(n, 3.3) if uniform else rng.gamma(0.8, 3.0, n) * (rng.random(n) < 0.7)).astype(np.float32)
+    exact, acc, real4 = m.astype(np.float64), m.astype(np.float64), np.zeros(n, np.float32)
+    for i in range(n - 1, -1, -1):                              # donors have larger indices: REAL4 rounding at every cell
+        real4[i] = np.float32(acc[i])
+        if down[i] >= 0:
+            acc[down[i]] += float(real4[i])
+            exact[down[i]] += exact[i]
+    case = dict(sub_size=sub, down=down, level=level, vals=m, exact=exact, real4=real4, n=n)
+    den = np.maximum(np.abs(real4), 1e-30)
+    plain = np.max(np.abs(exact.astype(np.float32).astype(np.float64) - real4) / den)
+    for world in (1, 3):
+        got, cell, _ = _route(case, world, 16, 64)
+        err = np.max(np.abs(got.astype(np.float64) - real4) / den)
+        assert cell.size > 10000 and err <= 5e-7, (world, err)
+        if uniform:
+            assert plain > 1.5e-6 and err < 0.25 * plain
