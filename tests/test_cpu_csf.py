@@ -44,3 +44,14 @@ def test_clone_mask_excludes_missing_values():
     assert _clone_mask(np.array([[1, -2147483648], [0, 7]], np.int32)).tolist() == [[True, False], [False, True]]
     assert _clone_mask(np.array([[1, 255], [0, 1]], np.uint8)).tolist() == [[True, False], [False, True]]
     assert _clone_mask(np.array([[True, False]])).tolist() == [[True, False]]
+
+
+def test_run_script_usage_errors(capsys):
+    """`python -m sphy_b200`: wrong invocations are refused with the usage line before anything touches a GPU."""
+    from sphy_b200.__main__ import main
+    assert main([]) == 2
+    assert main(["--route", "sideways", "x.cfg"]) == 2
+    assert main(["a.cfg", "b.cfg"]) == 2
+    assert main(["/nonexistent/sphy_config.cfg"]) == 2
+    err = capsys.readouterr().err
+    assert "usage: python -m sphy_b200" in err and "cannot read" in err
